@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- control-steps/s of the batched safety-filter solve (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+
+One "step" = one pass of the hot path over one batch of synthetic agents (default workload
+cfg2 = BASELINE.json configs[1]: 1024 DynamicUnicycle2D agents x 16 circular obstacles, cbf_qp).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+
+  value     whole-job control-steps/s, inputs resident in HBM, CUDA events on the launch stream,
+            max over ranks.  A pool of distinct batches larger than 2x L2 is cycled so no step
+            re-reads L2-resident inputs.
+  e2e       same metric through the host-pointer C-ABI call (scb_*_solve_host): pinned host
+            inputs -> H2D -> kernel -> D2H of (U, status, active) every step.
+  roofline  algorithmic bytes per launch / CUDA-event kernel time vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle port (oracle/, numpy, one agent at a time like the reference's
+            control_step loop) timed on a bounded sample on this box's host cores.
+  --impl reference   the reference-equivalent CPU path (same oracle port, all host cores).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, controller, N agents, M obstacles, horizon, dynamic obstacles)
+    "cfg2": dict(model="DynamicUnicycle2D", controller="cbf_qp", N=1024, M=16, H=0, dynamic=False,
+                 desc="1024 DynamicUnicycle2D agents, cbf_qp, 16 circular obstacles"),
+    "cfg3": dict(model="DynamicUnicycle2D", controller="mpc_cbf", N=4096, M=16, H=8, dynamic=False,
+                 desc="4096 DynamicUnicycle2D agents, mpc_cbf horizon 8, 16 obstacles"),
+    "cfg4": dict(model="KinematicBicycle2D_C3BF", controller="optimal_decay_cbf_qp", N=8192, M=32, H=0, dynamic=True,
+                 desc="8192 KinematicBicycle2D_C3BF agents, optimal_decay_cbf_qp, 32 dynamic obstacles"),
+}
+L2_BYTES = 126e6
+
+
+def algorithmic_bytes(w):
+    """bytes per agent-step on the contract layout (f64, per-agent lists)."""
+    nx, nu, M = (12, 4, w["M"]) if w["model"] == "Quad3D" else ((2, 2, w["M"]) if w["model"] == "SingleIntegrator2D" else (4, 2, w["M"]))
+    if w["controller"] == "mpc_cbf":
+        ng = 3 if w["model"] == "Quad3D" else 2
+        return 8 * (nx + ng + nu + 7 * M + nu) + 12
+    return 8 * (nx + nu + 7 * M + nu) + 4 + 8 * ((M + 2 * nu + 63) // 64)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def _cpu_solve_range(args):
+    """Worker: oracle port over a slice of agents, one at a time (the reference's control flow)."""
+    w, sc, lo, hi = args
+    from oracle.controllers import OracleCBFQP, OracleOptimalDecayCBFQP
+    M = w["M"]
+    t0 = time.perf_counter()
+    if w["controller"] == "cbf_qp":
+        ctrl = OracleCBFQP(sc["spec"], num_obs=M)
+        for i in range(lo, hi):
+            k = int(sc["nobs"][i])
+            ctrl.solve(sc["X"][i], sc["U_ref"][i], sc["OBS"][i][:k])
+    elif w["controller"] == "optimal_decay_cbf_qp":
+        ctrl = OracleOptimalDecayCBFQP(sc["spec"])
+        for i in range(lo, hi):
+            k = int(sc["nobs"][i])
+            ctrl.solve(sc["X"][i], sc["U_ref"][i], sc["OBS"][i][0] if k else None)   # lists are distance-sorted
+    else:
+        from oracle.mpc_cbf import OracleMPCCBF
+        ctrl = OracleMPCCBF(sc["spec"], num_obs=M, horizon=w["H"])
+        for i in range(lo, hi):
+            k = int(sc["nobs"][i])
+            ctrl.solve(sc["X"][i], sc["goal"][i], sc["u_prev"][i], sc["OBS"][i][:k])
+    return hi - lo, time.perf_counter() - t0
+
+
+def cpu_rate(w, sc, n_agents, procs):
+    """agent-steps/s of the oracle port on `procs` host processes over the first n_agents agents."""
+    n_agents = min(n_agents, sc["X"].shape[0])
+    if procs <= 1:
+        n, dt = _cpu_solve_range((w, sc, 0, n_agents))
+        return n / dt, n, dt
+    import multiprocessing as mp
+    bounds = np.linspace(0, n_agents, procs + 1).astype(int)
+    small = {k: sc[k] for k in ("spec", "X", "U_ref", "OBS", "nobs", "goal", "u_prev")}
+    with mp.get_context("fork").Pool(procs) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_solve_range, [(w, small, int(bounds[j]), int(bounds[j + 1])) for j in range(procs)])
+        dt = time.perf_counter() - t0
+    n = sum(r[0] for r in res)
+    return n / dt, n, dt
+
+
+def cpu_sample_size(w):
+    return {"cbf_qp": 4096, "optimal_decay_cbf_qp": 8192, "mpc_cbf": 48}[w["controller"]]
+
+
+# --------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload], name=args.workload)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from safe_control_b200 import scenes
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        procs = os.cpu_count() or 1
+        n_s = cpu_sample_size(w) * (2 if procs > 4 else 1)
+        sc = scenes.make_scene(w["model"], min(n_s, max(n_s, w["N"])), w["M"], seed=1234, dynamic=w["dynamic"],
+                               optimal_decay=w["controller"] == "optimal_decay_cbf_qp")
+        per_step = max(procs * 8, n_s // max(args.steps + args.warmup, 1))
+        per_step = min(per_step, n_s)
+        for _ in range(min(args.warmup, 1)):
+            cpu_rate(w, sc, per_step, procs)
+        t_tot, n_tot = 0.0, 0
+        budget = 120.0
+        for s in range(args.steps):
+            r, n, dt = cpu_rate(w, sc, per_step, procs)
+            t_tot += dt; n_tot += n
+            if t_tot > budget:
+                break
+        val = n_tot / t_tot
+        sample = f"{n_tot} agent-steps of the {w['name']} scene (seed 1234), oracle port, {procs} processes"
+        print(json.dumps({
+            "impl": "reference", "metric": "control-steps/sec (batched QP solves/s)", "value": val, "unit": "control-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * w["N"] / val,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step": w["N"], "obstacles": w["M"]},
+            "cpu_baseline": {"value": val, "unit": "control-steps/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference's cvxpy/GUROBI + do-mpc/IPOPT stack is not installable here (no network); this is the "
+                    "oracle restatement driven one agent at a time like tracking.py:control_step",
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from safe_control_b200 import BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, HostContext
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    N, M = w["N"], w["M"]
+    B = algorithmic_bytes(w)
+    od = w["controller"] == "optimal_decay_cbf_qp"
+
+    # ---- input pool: P distinct batches, > 2x L2 in total (or 8 for the compute-bound MPC) ----
+    P = int(np.ceil(2.2 * L2_BYTES / (B * N))) if w["controller"] != "mpc_cbf" else 4
+    sc = scenes.make_scene(w["model"], N * P, M, seed=1234 + rank, dynamic=w["dynamic"], optimal_decay=od)
+    spec = sc["spec"]
+    t = lambda a: torch.from_numpy(a).to(dev)
+    Xp, Urp, OBSp, nobsp = t(sc["X"]).view(P, N, -1), t(sc["U_ref"]).view(P, N, -1), t(sc["OBS"]).view(P, N, M, 7), t(sc["nobs"]).view(P, N)
+    goalp, uprevp = t(sc["goal"]).view(P, N, -1), t(sc["u_prev"]).view(P, N, -1)
+
+    if w["controller"] == "cbf_qp":
+        ctrl = BatchedCBFQP(spec, num_obs=M)
+        outs = (torch.empty((N, 2), dtype=torch.float64, device=dev), torch.empty(N, dtype=torch.int32, device=dev),
+                torch.empty((N, ctrl.words), dtype=torch.int64, device=dev))
+        step = lambda k: ctrl.solve(Xp[k % P], Urp[k % P], OBSp[k % P], nobsp[k % P], out=outs)
+    elif od:
+        ctrl = BatchedOptimalDecayCBFQP(spec, num_obs=M)
+        step = lambda k: ctrl.solve(Xp[k % P], Urp[k % P], OBSp[k % P], nobsp[k % P])
+    else:
+        ctrl = BatchedMPCCBF(spec, num_obs=M, horizon=w["H"])
+        step = lambda k: ctrl.solve(Xp[k % P], goalp[k % P], uprevp[k % P], OBSp[k % P], nobsp[k % P])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctrl.launches
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctrl.launches - l0
+
+    # ---- kernel-only time for the roofline (same stream, CUDA events around each launch) ----
+    n_k = min(args.steps, 200)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
+    for k in range(n_k):
+        evs[k][0].record(); step(args.warmup + args.steps + k); evs[k][1].record()
+    torch.cuda.synchronize()
+    k_ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # asymptote of the same kernel on a batch that fills the machine (not the headline; explains it)
+    big = None
+    if w["controller"] != "mpc_cbf":
+        NB = 1 << 20
+        reps = NB // (N * P) + 1
+        Xb = Xp.reshape(N * P, -1).repeat(reps, 1)[:NB].contiguous(); Ub = Urp.reshape(N * P, -1).repeat(reps, 1)[:NB].contiguous()
+        Ob = OBSp.reshape(N * P, M, 7).repeat(reps, 1, 1)[:NB].contiguous(); nb = nobsp.reshape(-1).repeat(reps)[:NB].contiguous()
+        for _ in range(3):
+            ctrl.solve(Xb, Ub, Ob, nb)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(10):
+            ctrl.solve(Xb, Ub, Ob, nb)
+        b1.record(); torch.cuda.synchronize()
+        big_ms = b0.elapsed_time(b1) / 10
+        big = dict(agents=NB, ms_per_launch=big_ms, control_steps_per_s=NB / big_ms * 1e3, gbs=B * NB / big_ms / 1e6)
+        del Xb, Ub, Ob, nb
+
+    # ---- activity mix of the timed inputs (iteration counts depend on it) ----
+    mix = None
+    if w["controller"] == "cbf_qp":
+        st_all, cbf_act, box_act = [], [], []
+        for k in range(min(P, 16)):
+            U, st, act = ctrl.solve(Xp[k], Urp[k], OBSp[k], nobsp[k])
+            st_all.append(st.clone()); a = act[:, 0].clone()
+            cbf_act.append((a & ((1 << M) - 1)) != 0); box_act.append((a >> M) != 0)
+        st_all = torch.cat(st_all); cbf_act = torch.cat(cbf_act); box_act = torch.cat(box_act)
+        mix = dict(infeasible=float((st_all == 1).float().mean()), cbf_active=float(cbf_act.float().mean()),
+                   box_active=float(box_act.float().mean()))
+
+    # ---- end to end through the host-pointer C ABI ----
+    ctx = HostContext(local_rank)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    P_h = min(P, 32)
+    hX = [pin(sc["X"][k * N:(k + 1) * N]) for k in range(P_h)]
+    hU = [pin(sc["U_ref"][k * N:(k + 1) * N]) for k in range(P_h)]
+    hO = [pin(sc["OBS"][k * N:(k + 1) * N]) for k in range(P_h)]
+    hn = [pin(sc["nobs"][k * N:(k + 1) * N]) for k in range(P_h)]
+    hg = [pin(sc["goal"][k * N:(k + 1) * N]) for k in range(P_h)]
+    hp = [pin(sc["u_prev"][k * N:(k + 1) * N]) for k in range(P_h)]
+    if w["controller"] == "cbf_qp":
+        ho = (pin(np.empty((N, 2))), pin(np.empty(N, np.int32)), pin(np.empty((N, ctrl.words), np.uint64)))
+        estep = lambda k: ctx.cbfqp_solve(ctrl.params, M, hX[k % P_h], hU[k % P_h], hO[k % P_h], hn[k % P_h], out=ho)
+        h2d = N * (4 + 2) * 8 + N * M * 56 + N * 4; d2h = N * 2 * 8 + N * 4 + N * ctrl.words * 8
+    elif od:
+        estep = lambda k: ctx.odcbf_solve(ctrl.params, M, hX[k % P_h], hU[k % P_h], hO[k % P_h], hn[k % P_h])
+        h2d = N * (4 + 2) * 8 + N * M * 56 + N * 4; d2h = N * 2 * 8 * 2 + N * 4 * 2 + N * 8
+    else:
+        estep = lambda k: ctx.mpccbf_solve(ctrl.params, M, w["H"], hX[k % P_h], hg[k % P_h], hp[k % P_h], hO[k % P_h], hn[k % P_h])
+        h2d = N * (ctrl.nx + ctrl.ngoal + ctrl.nu) * 8 + N * M * 56 + N * 4; d2h = N * ctrl.nu * 8 + N * 4 * 2 + N * 8
+    e_steps = max(10, min(args.steps, 400 if w["controller"] != "mpc_cbf" else 20))
+    for k in range(min(args.warmup, 10)):
+        estep(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e_steps):
+        estep(k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = ctx.launches
+
+    tm = torch.tensor([ms, e2e_s * 1e3 / e_steps * args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(tm[0]), float(tm[1])
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        achieved = B * N / (k_ms * 1e-3) / 1e9
+        out = {
+            "metric": "control-steps/sec (batched QP solves/s)",
+            "value": world * N * args.steps / (ms_max * 1e-3), "unit": "control-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step_per_gpu": N, "obstacles": M,
+                       "horizon": w["H"], "scene": "SURVEY 8d generator, seed 1234+rank, num_constraints=M",
+                       "l2_policy": f"inputs larger than L2: {P} distinct batches ({P * N * B / 1e6:.0f} MB) cycled",
+                       "parallelism": f"agents sharded, {world} rank(s), no data-path collective", "activity_mix": mix},
+            "e2e": {"value": world * N * args.steps / (e2e_ms_max * 1e-3), "unit": "control-steps/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": e_steps,
+                    "how": "scb_*_solve_host: pinned host arrays -> H2D -> kernel -> D2H(U,status,active) -> sync, per step"},
+            "gpu_launches": launches,
+            "e2e_gpu_launches": e2e_launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_agent": B, "agents_per_launch": N,
+                         "note": "one launch covers only 1024 agents (~1 MB): latency-bound, see large_batch",
+                         "large_batch": big},
+        }
+        if not args.no_cpu:
+            n_s = cpu_sample_size(w)
+            rate, n, dt = cpu_rate(w, sc, n_s, 1)
+            out["cpu_baseline"] = {"value": rate, "unit": "control-steps/s", "cores": 1, "kind": "port",
+                                   "host_cores_available": os.cpu_count(),
+                                   "sample": f"first {n} agents of the timed scene, oracle port (numpy, one agent at a time), {dt:.1f} s"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

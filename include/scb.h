@@ -1,0 +1,174 @@
+/* scb.h -- C ABI of libscb.so: the B200-native batched safety-filter solve.
+ *
+ * This is the drop-in boundary for the reference's per-step position-controller
+ * solve (tkkim-robot/safe_control):
+ *
+ *   scb_cbfqp_solve*      replaces  CBFQP.solve_control_problem            position_control/cbf_qp.py:108-199
+ *   scb_cbfqp_rows        replaces  the row loop of the same method        position_control/cbf_qp.py:122-185
+ *   scb_odcbf_solve*      replaces  OptimalDecayCBFQP.solve_control_problem position_control/optimal_decay_cbf_qp.py:132-159
+ *   scb_mpccbf_solve*     replaces  MPCCBF.solve_control_problem           position_control/mpc_cbf.py:366-402
+ *   scb_params            replaces  the robot_spec / cbf_param dictionaries robots/*.py ctor setdefault cascades,
+ *                                                                          cbf_qp.py:12-43, optimal_decay_cbf_qp.py:17-50,
+ *                                                                          mpc_cbf.py:15-95
+ *
+ * for a BATCH of N independent agents (the reference solves one agent per call,
+ * tracking.py:611-616).  Plain C types only; all arithmetic is IEEE float64 like
+ * the reference's numpy / GUROBI / IPOPT path.
+ *
+ * Two families of entry points:
+ *   *_solve       device pointers owned by the caller (e.g. torch tensors), asynchronous
+ *                 on `stream`; nothing is allocated.
+ *   *_solve_host  HOST pointers (e.g. numpy arrays): stages through the context's device
+ *                 buffers (H2D, launch, D2H) and returns when the outputs are in host
+ *                 memory.  This is what a reference-side ctypes binding calls.
+ *
+ * Array layouts (row-major, float64 unless noted):
+ *   X      [N, nx]     agent states                       (robot.X, robots/robot.py:38)
+ *   Uref   [N, nu]     nominal inputs                     (control_ref['u_ref'], tracking.py:607-609)
+ *   OBS    [N, M, 7]   per-agent obstacle lists, or [M, 7] shared by all agents when
+ *                      obs_stride_agent == 0.  Row = [x, y, r, vx, vy, -, flag=0] (circle) or
+ *                      [x, y, a, b, e, theta, flag=1] (superellipsoid)  (README.md:133-138).
+ *                      obs_stride_agent is in doubles (normally 7*M).
+ *   nobs   [N] int32   number of valid rows per agent (NULL = all M); rows >= nobs[i] are
+ *                      vacuous `0 >= 0` rows exactly like the reference's zeroed A1/b1
+ *                      (cbf_qp.py:110-111).  nobs[i] < 0 means "obs_list is None": the QP
+ *                      controller returns u_ref unclipped (cbf_qp.py:113-118).
+ *   U      [N, nu]     filtered inputs (out)
+ *   status [N] int32   (out) SCB_OPTIMAL / SCB_INFEASIBLE / SCB_MAXITER / SCB_NUMERICAL.
+ *                      The reference's `.status == 'optimal'` <=> status == 0 (tracking.py:628).
+ *   active [N, W] u64  (out, may be NULL) bitmask of the optimal working set;
+ *                      W = scb_active_words(M, nu).  Bit j < M: CBF row of obstacle slot j;
+ *                      bit M+2i: u_i at its upper bound; bit M+2i+1: u_i at its lower bound.
+ *
+ * All functions return 0 on success or a negative scb_error code; they never throw and
+ * never touch errno.  No global mutable state: calls with distinct contexts/streams are
+ * re-entrant.
+ */
+#ifndef SCB_H_
+#define SCB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCB_VERSION 100
+
+/* model ids (robot_spec['model'], robots/robot.py:65-175) */
+enum scb_model {
+  SCB_SINGLE_INTEGRATOR_2D = 0,     /* robots/single_integrator2D.py */
+  SCB_DYNAMIC_UNICYCLE_2D = 1,      /* robots/dynamic_unicycle2D.py */
+  SCB_KINEMATIC_BICYCLE_2D = 2,     /* robots/kinematic_bicycle2D.py */
+  SCB_KINEMATIC_BICYCLE_2D_C3BF = 3,/* dynamic_env/kinematic_bicycle2D_c3bf.py */
+  SCB_QUAD_3D = 4,                  /* robots/quad3D.py (MPC only: agent_barrier raises, quad3D.py:269-273) */
+  SCB_NUM_MODELS = 5
+};
+
+enum scb_status { SCB_OPTIMAL = 0, SCB_INFEASIBLE = 1, SCB_MAXITER = 2, SCB_NUMERICAL = 3 };
+
+enum scb_error {
+  SCB_OK = 0,
+  SCB_ERR_BAD_ARG = -1,        /* NULL pointer, negative size, unknown model */
+  SCB_ERR_UNSUPPORTED = -2,    /* model/controller pair the reference does not support either */
+  SCB_ERR_TOO_LARGE = -3,      /* M or horizon beyond the compiled limits (see scb_limits) */
+  SCB_ERR_CUDA = -4,           /* launch / memcpy failure; scb_last_cuda_error() has the code */
+  SCB_ERR_NO_DEVICE = -5,
+  SCB_ERR_ALLOC = -6
+};
+
+/* Everything the reference keeps in robot_spec / cbf_param for one (model, controller)
+ * group, resolved once on the host.  POD, passed by pointer, copied at launch. */
+typedef struct scb_params {
+  int32_t model;          /* enum scb_model */
+  int32_t cbf_mode;       /* 0 = 'cbf', 1 = 'hard'      robot_spec['cbf_mode'], cbf_qp.py:120 */
+  int32_t nx, nu;         /* filled by scb_params_default */
+  double dt;              /* tracking.py:39 */
+  double radius;          /* robot_spec['radius'], robots/robot.py:49-50 */
+  double alpha;           /* rel-degree-1 gain        cbf_qp.py:12-35 / mpc_cbf.py:49-82 / optimal_decay:17-50 */
+  double alpha1, alpha2;  /* rel-degree-2 gains */
+  double u_lb[4], u_ub[4];/* input box               cbf_qp.py:54-73, mpc_cbf.py:183-221 */
+  double v_min, v_max;    /* KB step clip (kinematic_bicycle2D.py:116-121); MPC state bound |x[3]| <= v_max */
+  double rear_ax_dist;    /* KB L_r (kinematic_bicycle2D.py:48) */
+  double omega1_0, omega2_0, p_sb1, p_sb2;   /* optimal_decay_cbf_qp.py:17-50 */
+  double Q[12];           /* MPC state weights (diagonal)  mpc_cbf.py:19-39 */
+  double R[4];            /* MPC input-rate weights        mpc_cbf.py:19-39, 180 */
+  double mass, Ix, Iy, Iz, arm_L, nu_coef, gravity;     /* quad3D.py:53-69 */
+  int32_t mpc_max_iter;   /* interior-point iteration cap (ours) */
+  int32_t reserved;
+  double mpc_tol;         /* KKT tolerance (ours; IPOPT default 1e-8) */
+} scb_params;
+
+typedef struct scb_ctx scb_ctx;   /* opaque: device staging buffers + stream for the *_host calls */
+
+/* ---- library / parameter helpers ------------------------------------------------------- */
+int         scb_version(void);
+const char* scb_strerror(int err);
+int         scb_last_cuda_error(void);                 /* cudaError_t of the last SCB_ERR_CUDA on this thread */
+int         scb_device_count(void);
+/* Fill `p` with the reference's defaults for (model, controller); controller is one of
+ * "cbf_qp", "optimal_decay_cbf_qp", "mpc_cbf".  Returns SCB_ERR_UNSUPPORTED for pairs the
+ * reference has no branch for. */
+int         scb_params_default(scb_params* p, int model, const char* controller);
+int         scb_model_dims(int model, int* nx, int* nu);
+int         scb_active_words(int M, int nu);           /* ceil((M + 2 nu) / 64) */
+/* compiled limits: max obstacle slots for the QP kernels, max slots and horizon for MPC */
+int         scb_limits(int* max_obs_qp, int* max_obs_mpc, int* max_horizon);
+
+/* ---- context for the host-pointer calls ------------------------------------------------- */
+int  scb_ctx_create(scb_ctx** out, int device);
+void scb_ctx_destroy(scb_ctx* ctx);
+/* number of kernel launches issued through this context so far (for benchmarks) */
+long scb_ctx_launches(const scb_ctx* ctx);
+
+/* ---- CBF-QP  (position_control/cbf_qp.py) ------------------------------------------------ */
+/* constraint rows only: A [N, M, nu], b [N, M]   (A u + b >= 0) */
+int scb_cbfqp_rows(const scb_params* p, int N, int M,
+                   const double* X, const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                   double* A, double* b, void* stream);
+int scb_cbfqp_solve(const scb_params* p, int N, int M,
+                    const double* X, const double* Uref,
+                    const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                    double* U, int32_t* status, uint64_t* active, void* stream);
+int scb_cbfqp_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M,
+                         const double* X, const double* Uref,
+                         const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                         double* U, int32_t* status, uint64_t* active);
+
+/* ---- optimal-decay CBF-QP  (position_control/optimal_decay_cbf_qp.py) -------------------- */
+/* ONE CBF row per agent, built from the nearest valid obstacle (by centre distance) of the
+ * agent's list -- i.e. nearest_multi_obs[0] of tracking.py:585-586.  omega [N, 2] (out, may
+ * be NULL): omega1 (, omega2; NaN for rel-degree-1 models).  sel [N] int32 (out, may be NULL):
+ * the obstacle slot the row was built from (-1 if none). */
+int scb_odcbf_solve(const scb_params* p, int N, int M,
+                    const double* X, const double* Uref,
+                    const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                    double* U, double* omega, int32_t* sel, int32_t* status, uint64_t* active, void* stream);
+int scb_odcbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M,
+                         const double* X, const double* Uref,
+                         const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                         double* U, double* omega, int32_t* sel, int32_t* status, uint64_t* active);
+
+/* ---- MPC-CBF  (position_control/mpc_cbf.py) ---------------------------------------------- */
+/* goal [N, 2] (3 for Quad3D: x, y, z), u_prev [N, nu] (last applied input, 0 at the first
+ * call), track [N] int32 or NULL (0 => state_machine != 'track': return Uref untouched,
+ * mpc_cbf.py:379-381).  pred_x [N, H+1, nx], pred_u [N, H, nu], iters [N] may be NULL.
+ * kkt [N] (out, may be NULL): final KKT error. */
+int scb_mpccbf_solve(const scb_params* p, int N, int M, int H,
+                     const double* X, const double* Uref, const double* goal, const double* u_prev,
+                     const int32_t* track,
+                     const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                     double* U, int32_t* status, double* pred_x, double* pred_u,
+                     int32_t* iters, double* kkt, void* stream);
+int scb_mpccbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M, int H,
+                          const double* X, const double* Uref, const double* goal, const double* u_prev,
+                          const int32_t* track,
+                          const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                          double* U, int32_t* status, double* pred_x, double* pred_u,
+                          int32_t* iters, double* kkt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCB_H_ */

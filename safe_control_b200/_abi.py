@@ -1,0 +1,71 @@
+"""ctypes mirror of include/scb.h (struct scb_params + prototypes)."""
+import ctypes as C
+
+MODEL_IDS = {
+    "SingleIntegrator2D": 0,
+    "DynamicUnicycle2D": 1,
+    "KinematicBicycle2D": 2,
+    "KinematicBicycle2D_C3BF": 3,
+    "Quad3D": 4,
+}
+MODEL_NAMES = {v: k for k, v in MODEL_IDS.items()}
+MODEL_DIMS = {0: (2, 2), 1: (4, 2), 2: (4, 2), 3: (4, 2), 4: (12, 4)}
+
+OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL = 0, 1, 2, 3
+STATUS_STR = {0: "optimal", 1: "infeasible", 2: "user_limit", 3: "solver_error"}   # cvxpy's vocabulary
+
+ERR_UNSUPPORTED = -2
+
+
+class ScbParams(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("cbf_mode", C.c_int32), ("nx", C.c_int32), ("nu", C.c_int32),
+        ("dt", C.c_double), ("radius", C.c_double),
+        ("alpha", C.c_double), ("alpha1", C.c_double), ("alpha2", C.c_double),
+        ("u_lb", C.c_double * 4), ("u_ub", C.c_double * 4),
+        ("v_min", C.c_double), ("v_max", C.c_double), ("rear_ax_dist", C.c_double),
+        ("omega1_0", C.c_double), ("omega2_0", C.c_double), ("p_sb1", C.c_double), ("p_sb2", C.c_double),
+        ("Q", C.c_double * 12), ("R", C.c_double * 4),
+        ("mass", C.c_double), ("Ix", C.c_double), ("Iy", C.c_double), ("Iz", C.c_double),
+        ("arm_L", C.c_double), ("nu_coef", C.c_double), ("gravity", C.c_double),
+        ("mpc_max_iter", C.c_int32), ("reserved", C.c_int32), ("mpc_tol", C.c_double),
+    ]
+
+
+_P = C.POINTER(ScbParams)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/scb.h declares
+PROTOTYPES = {
+    "scb_version": (C.c_int, []),
+    "scb_strerror": (C.c_char_p, [C.c_int]),
+    "scb_last_cuda_error": (C.c_int, []),
+    "scb_device_count": (C.c_int, []),
+    "scb_params_default": (C.c_int, [_P, C.c_int, C.c_char_p]),
+    "scb_model_dims": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "scb_active_words": (C.c_int, [C.c_int, C.c_int]),
+    "scb_limits": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "scb_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "scb_ctx_destroy": (None, [_vp]),
+    "scb_ctx_launches": (C.c_long, [_vp]),
+    "scb_cbfqp_rows": (C.c_int, [_P, C.c_int, C.c_int, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),
+    "scb_cbfqp_solve": (C.c_int, [_P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp]),
+    "scb_cbfqp_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),
+    "scb_odcbf_solve": (C.c_int, [_P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_odcbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_mpccbf_solve": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_mpccbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
+                                        _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+def bind(lib, names=None):
+    """Attach restype/argtypes; raises AttributeError if a declared symbol is missing."""
+    for name, (res, args) in PROTOTYPES.items():
+        if names is not None and name not in names:
+            continue
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib

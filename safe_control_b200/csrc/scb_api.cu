@@ -1,0 +1,360 @@
+// scb_api.cu -- the C ABI of libscb.so (include/scb.h): argument checks, launch dispatch,
+// and the host-pointer staging context.  No torch, no exceptions, no global mutable state
+// (only a thread-local copy of the last CUDA error code).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "scb_kernels.cuh"
+#include "scb_mpc_kernels.cuh"
+
+using namespace scb;
+
+static thread_local int g_last_cuda = 0;
+
+static int cuda_fail(cudaError_t e) {
+  g_last_cuda = (int)e;
+  return SCB_ERR_CUDA;
+}
+#define CK(x)                                  \
+  do {                                         \
+    cudaError_t e__ = (x);                     \
+    if (e__ != cudaSuccess) return cuda_fail(e__); \
+  } while (0)
+
+static int sm_count_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    n = v;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------ dispatch
+template <int MODEL>
+static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
+                          const double* OBS, long stride, const int32_t* nobs, double* U, int32_t* status,
+                          uint64_t* active, int words, cudaStream_t s) {
+#define GO(L, R)                                                                                           \
+  if (g.lanes == L && g.rpl == R) {                                                                        \
+    cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
+    return SCB_OK;                                                                                         \
+  }
+  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 4) GO(8, 8)
+#undef GO
+  return SCB_ERR_TOO_LARGE;
+}
+
+template <int MODEL, int NW>
+static int launch_od_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
+                       const double* OBS, long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel,
+                       int32_t* status, uint64_t* active, cudaStream_t s) {
+#define GO(L, R)                                                                                              \
+  if (g.lanes == L && g.rpl == R) {                                                                           \
+    odcbf_kernel<MODEL, NW, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active); \
+    return SCB_OK;                                                                                            \
+  }
+  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 4) GO(8, 8)
+#undef GO
+  return SCB_ERR_TOO_LARGE;
+}
+
+static bool qp_model_ok(int m) {
+  return m == SCB_SINGLE_INTEGRATOR_2D || m == SCB_DYNAMIC_UNICYCLE_2D || m == SCB_KINEMATIC_BICYCLE_2D ||
+         m == SCB_KINEMATIC_BICYCLE_2D_C3BF;
+}
+
+extern "C" {
+
+int scb_last_cuda_error(void) { return g_last_cuda; }
+
+int scb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int scb_limits(int* max_obs_qp, int* max_obs_mpc, int* max_horizon) {
+  if (max_obs_qp) *max_obs_qp = 124;       // rows = M + 4 <= 128
+  if (max_obs_mpc) *max_obs_mpc = kMpcMaxObs;
+  if (max_horizon) *max_horizon = kMpcMaxH;
+  return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------ CBF-QP
+int scb_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const double* OBS, long stride,
+                   const int32_t* nobs, double* A, double* b, void* stream) {
+  if (!p || N < 0 || M < 0 || (N > 0 && M > 0 && (!X || !OBS || !A || !b))) return SCB_ERR_BAD_ARG;
+  if (!qp_model_ok(p->model)) return p->model == SCB_QUAD_3D ? SCB_ERR_UNSUPPORTED : SCB_ERR_BAD_ARG;
+  if (N == 0 || M == 0) return SCB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long total = (long)N * M;
+  long blocks = (total + 255) / 256;
+  const long cap = (long)sm_count_cached() * 8;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  switch (p->model) {
+    case SCB_SINGLE_INTEGRATOR_2D: cbfqp_rows_kernel<SCB_SINGLE_INTEGRATOR_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_DYNAMIC_UNICYCLE_2D: cbfqp_rows_kernel<SCB_DYNAMIC_UNICYCLE_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_KINEMATIC_BICYCLE_2D: cbfqp_rows_kernel<SCB_KINEMATIC_BICYCLE_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: cbfqp_rows_kernel<SCB_KINEMATIC_BICYCLE_2D_C3BF><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+  }
+  CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
+                    long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active, void* stream) {
+  if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
+  if (!qp_model_ok(p->model)) return p->model == SCB_QUAD_3D ? SCB_ERR_UNSUPPORTED : SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
+  LaunchGeom g;
+  if (!pick_geom(N, M + 2 * p->nu, sm_count_cached(), g)) return SCB_ERR_TOO_LARGE;
+  const int words = scb_active_words(M, p->nu);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = SCB_ERR_BAD_ARG;
+  switch (p->model) {
+    case SCB_SINGLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_SINGLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_DYNAMIC_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+  }
+  if (rc != SCB_OK) return rc;
+  CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------ optimal decay
+int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
+                    long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
+                    uint64_t* active, void* stream) {
+  if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
+  if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D) return SCB_ERR_UNSUPPORTED;
+  if (!qp_model_ok(p->model)) return SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
+  LaunchGeom g;
+  if (!pick_geom(N, M > 1 ? M : 1, sm_count_cached(), g)) return SCB_ERR_TOO_LARGE;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = SCB_ERR_BAD_ARG;
+  switch (p->model) {
+    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_od_m<SCB_DYNAMIC_UNICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
+    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D_C3BF, 1>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
+  }
+  if (rc != SCB_OK) return rc;
+  CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------ MPC-CBF
+int scb_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, const double* Uref,
+                     const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
+                     const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
+                     int32_t* iters, double* kkt, void* stream) {
+  if (!p || N < 0 || M < 0 || H < 1) return SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !goal || !u_prev || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
+  if (track && !Uref) return SCB_ERR_BAD_ARG;
+  int rc = mpc_launch(*p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u, iters,
+                      kkt, (cudaStream_t)stream, sm_count_cached());
+  if (rc != SCB_OK) return rc;
+  CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------ host-pointer context
+struct scb_ctx {
+  int device;
+  cudaStream_t stream;
+  char* dbuf;
+  size_t dcap;
+  long launches;
+};
+
+int scb_ctx_create(scb_ctx** out, int device) {
+  if (!out) return SCB_ERR_BAD_ARG;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return SCB_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return SCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(device));
+  scb_ctx* c = new (std::nothrow) scb_ctx();
+  if (!c) return SCB_ERR_ALLOC;
+  c->device = device; c->dbuf = nullptr; c->dcap = 0; c->launches = 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return cuda_fail(e); }
+  *out = c;
+  return SCB_OK;
+}
+
+void scb_ctx_destroy(scb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->dbuf) cudaFree(c->dbuf);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+long scb_ctx_launches(const scb_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"
+
+// bump allocator over the context's device buffer (256-byte aligned pieces)
+struct Carver {
+  char* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t n) {
+    T* p = (T*)(base + off);
+    off += (n * sizeof(T) + 255) & ~(size_t)255;
+    return p;
+  }
+};
+static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+static int ctx_reserve(scb_ctx* c, size_t bytes) {
+  if (bytes <= c->dcap) return SCB_OK;
+  if (c->dbuf) { cudaFree(c->dbuf); c->dbuf = nullptr; c->dcap = 0; }
+  size_t want = bytes + bytes / 4;
+  cudaError_t e = cudaMalloc((void**)&c->dbuf, want);
+  if (e != cudaSuccess) return e == cudaErrorMemoryAllocation ? SCB_ERR_ALLOC : cuda_fail(e);
+  c->dcap = want;
+  return SCB_OK;
+}
+
+#define H2D(dst, src, n, T) CK(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyHostToDevice, c->stream))
+#define D2H(dst, src, n, T) CK(cudaMemcpyAsync(dst, src, (size_t)(n) * sizeof(T), cudaMemcpyDeviceToHost, c->stream))
+
+extern "C" {
+
+int scb_cbfqp_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const double* X, const double* Uref,
+                         const double* OBS, long stride, const int32_t* nobs, double* U, int32_t* status,
+                         uint64_t* active) {
+  if (!c || !p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  const int nx = p->nx, nu = p->nu, words = scb_active_words(M, nu);
+  const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
+  size_t need = padded((size_t)N * nx * 8) + padded((size_t)N * nu * 8) * 2 + padded(nobs_el * 8) +
+                padded((size_t)N * 4) * 2 + padded((size_t)N * words * 8);
+  int rc = ctx_reserve(c, need);
+  if (rc != SCB_OK) return rc;
+  Carver cv{c->dbuf, 0};
+  double* dX = cv.take<double>((size_t)N * nx);
+  double* dUr = cv.take<double>((size_t)N * nu);
+  double* dU = cv.take<double>((size_t)N * nu);
+  double* dO = cv.take<double>(nobs_el);
+  int32_t* dN = cv.take<int32_t>(N);
+  int32_t* dS = cv.take<int32_t>(N);
+  uint64_t* dA = cv.take<uint64_t>((size_t)N * words);
+  H2D(dX, X, (size_t)N * nx, double);
+  H2D(dUr, Uref, (size_t)N * nu, double);
+  if (nobs_el) H2D(dO, OBS, nobs_el, double);
+  if (nobs) H2D(dN, nobs, N, int32_t);
+  rc = scb_cbfqp_solve(p, N, M, dX, dUr, dO, stride, nobs ? dN : nullptr, dU, dS, active ? dA : nullptr, c->stream);
+  if (rc != SCB_OK) return rc;
+  c->launches += 1;
+  D2H(U, dU, (size_t)N * nu, double);
+  D2H(status, dS, N, int32_t);
+  if (active) D2H(active, dA, (size_t)N * words, uint64_t);
+  CK(cudaStreamSynchronize(c->stream));
+  return SCB_OK;
+}
+
+int scb_odcbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const double* X, const double* Uref,
+                         const double* OBS, long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel,
+                         int32_t* status, uint64_t* active) {
+  if (!c || !p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
+  size_t need = padded((size_t)N * 4 * 8) + padded((size_t)N * 2 * 8) * 3 + padded(nobs_el * 8) +
+                padded((size_t)N * 4) * 3 + padded((size_t)N * 8);
+  int rc = ctx_reserve(c, need);
+  if (rc != SCB_OK) return rc;
+  Carver cv{c->dbuf, 0};
+  double* dX = cv.take<double>((size_t)N * 4);
+  double* dUr = cv.take<double>((size_t)N * 2);
+  double* dU = cv.take<double>((size_t)N * 2);
+  double* dW = cv.take<double>((size_t)N * 2);
+  double* dO = cv.take<double>(nobs_el);
+  int32_t* dN = cv.take<int32_t>(N);
+  int32_t* dS = cv.take<int32_t>(N);
+  int32_t* dSel = cv.take<int32_t>(N);
+  uint64_t* dA = cv.take<uint64_t>(N);
+  H2D(dX, X, (size_t)N * 4, double);
+  H2D(dUr, Uref, (size_t)N * 2, double);
+  if (nobs_el) H2D(dO, OBS, nobs_el, double);
+  if (nobs) H2D(dN, nobs, N, int32_t);
+  rc = scb_odcbf_solve(p, N, M, dX, dUr, dO, stride, nobs ? dN : nullptr, dU, omega ? dW : nullptr,
+                       sel ? dSel : nullptr, dS, active ? dA : nullptr, c->stream);
+  if (rc != SCB_OK) return rc;
+  c->launches += 1;
+  D2H(U, dU, (size_t)N * 2, double);
+  if (omega) D2H(omega, dW, (size_t)N * 2, double);
+  if (sel) D2H(sel, dSel, N, int32_t);
+  D2H(status, dS, N, int32_t);
+  if (active) D2H(active, dA, N, uint64_t);
+  CK(cudaStreamSynchronize(c->stream));
+  return SCB_OK;
+}
+
+int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, const double* X, const double* Uref,
+                          const double* goal, const double* u_prev, const int32_t* track, const double* OBS,
+                          long stride, const int32_t* nobs, double* U, int32_t* status, double* pred_x,
+                          double* pred_u, int32_t* iters, double* kkt) {
+  if (!c || !p || N < 0 || M < 0 || H < 1) return SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !goal || !u_prev || !U || !status || (M > 0 && !OBS) || (track && !Uref)) return SCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  const int nx = p->nx, nu = p->nu, ng = (p->model == SCB_QUAD_3D) ? 3 : 2;
+  const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
+  size_t need = padded((size_t)N * nx * 8) + padded((size_t)N * nu * 8) * 3 + padded((size_t)N * ng * 8) +
+                padded(nobs_el * 8) + padded((size_t)N * 4) * 4 + padded((size_t)N * 8) +
+                padded((size_t)N * (H + 1) * nx * 8) + padded((size_t)N * H * nu * 8);
+  int rc = ctx_reserve(c, need);
+  if (rc != SCB_OK) return rc;
+  Carver cv{c->dbuf, 0};
+  double* dX = cv.take<double>((size_t)N * nx);
+  double* dUr = cv.take<double>((size_t)N * nu);
+  double* dUp = cv.take<double>((size_t)N * nu);
+  double* dU = cv.take<double>((size_t)N * nu);
+  double* dG = cv.take<double>((size_t)N * ng);
+  double* dO = cv.take<double>(nobs_el);
+  int32_t* dN = cv.take<int32_t>(N);
+  int32_t* dT = cv.take<int32_t>(N);
+  int32_t* dS = cv.take<int32_t>(N);
+  int32_t* dI = cv.take<int32_t>(N);
+  double* dK = cv.take<double>(N);
+  double* dPx = cv.take<double>((size_t)N * (H + 1) * nx);
+  double* dPu = cv.take<double>((size_t)N * H * nu);
+  H2D(dX, X, (size_t)N * nx, double);
+  if (Uref) H2D(dUr, Uref, (size_t)N * nu, double);
+  H2D(dUp, u_prev, (size_t)N * nu, double);
+  H2D(dG, goal, (size_t)N * ng, double);
+  if (nobs_el) H2D(dO, OBS, nobs_el, double);
+  if (nobs) H2D(dN, nobs, N, int32_t);
+  if (track) H2D(dT, track, N, int32_t);
+  rc = scb_mpccbf_solve(p, N, M, H, dX, Uref ? dUr : nullptr, dG, dUp, track ? dT : nullptr, dO, stride,
+                        nobs ? dN : nullptr, dU, dS, pred_x ? dPx : nullptr, pred_u ? dPu : nullptr,
+                        iters ? dI : nullptr, kkt ? dK : nullptr, c->stream);
+  if (rc != SCB_OK) return rc;
+  c->launches += 1;
+  D2H(U, dU, (size_t)N * nu, double);
+  D2H(status, dS, N, int32_t);
+  if (pred_x) D2H(pred_x, dPx, (size_t)N * (H + 1) * nx, double);
+  if (pred_u) D2H(pred_u, dPu, (size_t)N * H * nu, double);
+  if (iters) D2H(iters, dI, N, int32_t);
+  if (kkt) D2H(kkt, dK, N, double);
+  CK(cudaStreamSynchronize(c->stream));
+  return SCB_OK;
+}
+
+}  // extern "C"

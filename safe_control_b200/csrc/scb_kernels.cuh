@@ -1,0 +1,93 @@
+// scb_kernels.cuh -- __global__ wrappers + launch dispatch for the QP paths.
+//
+// Grid mapping: a lane group (LANES lanes of one warp) owns one agent; groups grid-stride
+// over the batch.  The host picks LANES from the batch size: 32 (warp per QP, lowest
+// latency) while 32*N threads still fit the machine a few times over, 8 for large
+// batches where throughput matters (4 QPs per warp, fewer redundant replicas of the
+// replicated NV x NV algebra).  RPL (rows per lane) = ceil((M + 2 nu) / LANES).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "scb_qp.cuh"
+
+namespace scb {
+
+constexpr int kBlock = 128;
+
+template <int MODEL, int LANES, int RPL>
+__global__ void __launch_bounds__(kBlock)
+cbfqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
+             const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
+             const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
+             uint64_t* __restrict__ active, int words) {
+  constexpr int NX = ModelCT<MODEL>::NX, NU = ModelCT<MODEL>::NU;
+  constexpr int GPB = kBlock / LANES;
+  for (long a = (long)blockIdx.x * GPB + threadIdx.x / LANES; a < N; a += (long)gridDim.x * GPB) {
+    cbfqp_agent<MODEL, LANES, RPL>(p, M, nobs ? nobs[a] : M, X + a * NX, Uref + a * NU, OBS + a * stride,
+                                   U + a * NU, status + a, active ? active + a * words : nullptr, words);
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(256)
+cbfqp_rows_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
+                  const double* __restrict__ OBS, long stride, const int32_t* __restrict__ nobs,
+                  double* __restrict__ A, double* __restrict__ b) {
+  constexpr int NX = ModelCT<MODEL>::NX, NU = ModelCT<MODEL>::NU;
+  const long total = (long)N * M;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long a = t / M;
+    const int r = (int)(t - a * M);
+    int no = nobs ? nobs[a] : M;
+    no = no < 0 ? 0 : (no > M ? M : no);
+    double xs[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = __ldg(X + a * NX + i);
+    AgentCT g;
+    ModelCT<MODEL>::prep(p, xs, g);
+    double av[NU], bv;
+    cbfqp_row<MODEL>(p, g, OBS + a * stride, M, no, r, av, bv);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) A[t * NU + i] = av[i];
+    b[t] = bv;
+  }
+}
+
+template <int MODEL, int NW, int LANES, int RPL>
+__global__ void __launch_bounds__(kBlock)
+odcbf_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
+             const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
+             const int32_t* __restrict__ nobs, double* __restrict__ U, double* __restrict__ omega,
+             int32_t* __restrict__ sel, int32_t* __restrict__ status, uint64_t* __restrict__ active) {
+  constexpr int GPB = kBlock / LANES;
+  for (long a = (long)blockIdx.x * GPB + threadIdx.x / LANES; a < N; a += (long)gridDim.x * GPB) {
+    odcbf_agent<MODEL, NW, LANES, RPL>(p, M, nobs ? nobs[a] : M, X + a * 4, Uref + a * 2, OBS + a * stride,
+                                       U + a * 2, omega ? omega + a * 2 : nullptr, sel ? sel + a : nullptr,
+                                       status + a, active ? active + a : nullptr);
+  }
+}
+
+struct LaunchGeom {
+  int lanes, rpl, grid;
+};
+
+// total rows -> (LANES, RPL); returns false if beyond the compiled instantiations
+inline bool pick_geom(long N, int rows, int sm_count, LaunchGeom& g) {
+  const bool small = N * 32 <= (long)sm_count * 2048 * 2;   // warp-per-QP still under ~2 waves
+  if (small || rows > 64) {
+    g.lanes = 32;
+    g.rpl = rows <= 32 ? 1 : rows <= 64 ? 2 : rows <= 128 ? 4 : 0;
+  } else {
+    g.lanes = 8;
+    g.rpl = rows <= 32 ? 4 : 8;
+  }
+  if (g.rpl == 0) return false;
+  const long groups_per_block = kBlock / g.lanes;
+  long blocks = (N + groups_per_block - 1) / groups_per_block;
+  const long cap = (long)sm_count * 16;                     // persistent-ish: <= 16 CTAs of 128 thr per SM
+  g.grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+  return true;
+}
+
+}  // namespace scb

@@ -1,0 +1,188 @@
+// scb_models.cuh -- continuous-time CBF row assembly, one (agent, obstacle) pair per call.
+//
+// Each ModelCT<MODEL>::row() produces the row (a[0..nu), b) of the reference's
+//     A1[row] u + b1[row] >= 0                         (position_control/cbf_qp.py:152-183)
+// i.e. rel-degree 1:  a = dh/dx g,      b = dh/dx f + alpha h            (:164-165)
+//      rel-degree 2:  a = d(hdot)/dx g, b = d(hdot)/dx f + (a1+a2) hdot + a1 a2 h   (:180-183)
+//      cbf_mode 'hard': b = h/dt + dh/dx f   or   h/dt^2 + 2 hdot/dt + d(hdot)/dx f   (:161,177)
+// from the model's f, g and agent_barrier:
+//   SingleIntegrator2D        robots/single_integrator2D.py:44-62, 114-146
+//   DynamicUnicycle2D         robots/dynamic_unicycle2D.py:42-73, 121-186
+//   KinematicBicycle2D        robots/kinematic_bicycle2D.py:75-110, 160-173
+//   KinematicBicycle2D_C3BF   dynamic_env/kinematic_bicycle2D_c3bf.py:15-75
+// The arithmetic follows the reference's operation order where that is cheap, so rows
+// agree with the numpy path to a few ulp.  Quad3D has no continuous barrier
+// (quad3D.py:269-273) and is rejected on the host.
+#pragma once
+
+#include "scb_core.cuh"
+
+namespace scb {
+
+// per-agent quantities shared by all of the agent's rows
+struct AgentCT {
+  double px, py;     // position
+  double c, s, v;    // cos(theta), sin(theta), speed (models with heading)
+  double fx, fy;     // f(x)[0:2] = v c, v s
+};
+
+// real power with the reference's numpy semantics for the cases the superellipsoid
+// formula meets (x ** e, e = obs[4]): negative base with integer exponent is fine.
+SCB_HD double rpow(double x, double e) { return pow(x, e); }
+
+struct RowOut {
+  double a[4];
+  double b;
+};
+
+template <int MODEL>
+struct ModelCT;
+
+// ---------------------------------------------------------------------------------------
+template <>
+struct ModelCT<SCB_SINGLE_INTEGRATOR_2D> {
+  static constexpr int NX = 2, NU = 2;
+  static SCB_HD void prep(const scb_params&, const double* x, AgentCT& g) {
+    g.px = x[0]; g.py = x[1]; g.c = 1.0; g.s = 0.0; g.v = 0.0; g.fx = 0.0; g.fy = 0.0;
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    double h = 0.0, d0 = 0.0, d1 = 0.0;
+    const double flag = o[6];
+    if (flag == 0.0) {                                        // single_integrator2D.py:120-127
+      const double dx = g.px - o[0], dy = g.py - o[1];
+      const double dmin = o[2] + p.radius;
+      h = (dx * dx + dy * dy) - 1.01 * (dmin * dmin);
+      d0 = 2.0 * dx; d1 = 2.0 * dy;
+    } else if (flag == 1.0) {                                 // :128-143
+      const double a = o[2], b = o[3], e = o[4];
+      double st, ct; sincos_pair(o[5], st, ct);
+      const double xp = ct * (g.px - o[0]) + st * (g.py - o[1]);
+      const double yp = -st * (g.px - o[0]) + ct * (g.py - o[1]);
+      const double ar = a + p.radius, br = b + p.radius;
+      h = rpow(xp / ar, e) + rpow(yp / br, e) - 1.0;
+      const double ga = e * rpow(xp, e - 1.0), gb = e * rpow(yp, e - 1.0);
+      const double ae = rpow(ar, e), be = rpow(br, e);
+      d0 = ga * (ct / ae) + gb * (-st / be);
+      d1 = ga * (st / ae) + gb * (ct / be);
+    }
+    r.a[0] = d0; r.a[1] = d1;                                 // g = I, f = 0
+    r.b = (p.cbf_mode == 1) ? h / p.dt : p.alpha * h;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// shared by DU and KB: h, hdot, d(hdot)/dx for the distance barrier (circle), beta differs
+SCB_HD void hocbf_circle(const AgentCT& g, const double* o, double radius, double beta,
+                         double& h, double& hd, double* dhd) {
+  const double dx = g.px - o[0], dy = g.py - o[1];
+  const double dmin = o[2] + radius;
+  h = (dx * dx + dy * dy) - beta * (dmin * dmin);
+  hd = 2.0 * dx * g.fx + 2.0 * dy * g.fy;
+  dhd[0] = 2.0 * g.fx;
+  dhd[1] = 2.0 * g.fy;
+  dhd[2] = 2.0 * dx * (-g.v * g.s) + 2.0 * dy * (g.v * g.c);
+  dhd[3] = 2.0 * dx * g.c + 2.0 * dy * g.s;
+}
+
+SCB_HD double rel2_b(const scb_params& p, double h, double hd, double lf) {
+  if (p.cbf_mode == 1) return h / (p.dt * p.dt) + 2.0 * hd / p.dt + lf;
+  return lf + (p.alpha1 + p.alpha2) * hd + (p.alpha1 * p.alpha2) * h;
+}
+
+template <>
+struct ModelCT<SCB_DYNAMIC_UNICYCLE_2D> {
+  static constexpr int NX = 4, NU = 2;
+  static SCB_HD void prep(const scb_params&, const double* x, AgentCT& g) {
+    g.px = x[0]; g.py = x[1]; g.v = x[3];
+    sincos_pair(x[2], g.s, g.c);
+    g.fx = g.v * g.c; g.fy = g.v * g.s;
+  }
+  // h, hdot, d(hdot)/dx by obstacle flag; anything else -> vacuous zeros
+  static SCB_HD void barrier(const scb_params& p, const AgentCT& g, const double* o, double& h, double& hd, double* dhd) {
+    h = 0.0; hd = 0.0; dhd[0] = dhd[1] = dhd[2] = dhd[3] = 0.0;
+    const double flag = o[6];
+    if (flag == 0.0) {                                        // dynamic_unicycle2D.py:136-146
+      hocbf_circle(g, o, p.radius, 1.01, h, hd, dhd);
+    } else if (flag == 1.0) {                                 // :148-183
+      const double a = o[2], b = o[3], e = o[4];
+      double st, ct; sincos_pair(o[5], st, ct);
+      const double xp = ct * (g.px - o[0]) + st * (g.py - o[1]);
+      const double yp = -st * (g.px - o[0]) + ct * (g.py - o[1]);
+      const double ar = a + p.radius, br = b + p.radius;
+      const double ae = rpow(ar, e), be = rpow(br, e);
+      h = rpow(xp / ar, e) + rpow(yp / br, e) - 1.0;
+      const double ga = (e / ae) * rpow(xp, e - 1.0), gb = (e / be) * rpow(yp, e - 1.0);
+      const double ka = (e * (e - 1.0) / ae) * rpow(xp, e - 2.0), kb = (e * (e - 1.0) / be) * rpow(yp, e - 2.0);
+      const double gx = ga * ct - gb * st, gy = ga * st + gb * ct;   // dh/dx, dh/dy
+      hd = gx * g.fx + gy * g.fy;
+      const double hxx = ka * ct * ct + kb * st * st;
+      const double hxy = (ka - kb) * ct * st;
+      const double hyy = ka * st * st + kb * ct * ct;
+      dhd[0] = hxx * g.fx + hxy * g.fy;
+      dhd[1] = hxy * g.fx + hyy * g.fy;
+      dhd[2] = gx * (-g.v * g.s) + gy * (g.v * g.c);
+      dhd[3] = gx * g.c + gy * g.s;
+    }
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    double h, hd, dhd[4];
+    barrier(p, g, o, h, hd, dhd);
+    // g = [[0,0],[0,0],[0,1],[1,0]]  (:64-73)
+    r.a[0] = dhd[3];
+    r.a[1] = dhd[2];
+    const double lf = dhd[0] * g.fx + dhd[1] * g.fy;
+    r.b = rel2_b(p, h, hd, lf);
+  }
+};
+
+template <>
+struct ModelCT<SCB_KINEMATIC_BICYCLE_2D> {
+  static constexpr int NX = 4, NU = 2;
+  static SCB_HD void prep(const scb_params& p, const double* x, AgentCT& g) {
+    ModelCT<SCB_DYNAMIC_UNICYCLE_2D>::prep(p, x, g);
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    double h, hd, dhd[4];
+    hocbf_circle(g, o, p.radius, 1.1, h, hd, dhd);            // kinematic_bicycle2D.py:160-173 (flag ignored)
+    // g = [[0,-v s],[0, v c],[0, v/L_r],[1, 0]]  (:93-110)
+    r.a[0] = dhd[3];
+    r.a[1] = dhd[0] * (-g.v * g.s) + dhd[1] * (g.v * g.c) + dhd[2] * (g.v / p.rear_ax_dist);
+    const double lf = dhd[0] * g.fx + dhd[1] * g.fy;
+    r.b = rel2_b(p, h, hd, lf);
+  }
+};
+
+template <>
+struct ModelCT<SCB_KINEMATIC_BICYCLE_2D_C3BF> {
+  static constexpr int NX = 4, NU = 2;
+  static SCB_HD void prep(const scb_params& p, const double* x, AgentCT& g) {
+    ModelCT<SCB_DYNAMIC_UNICYCLE_2D>::prep(p, x, g);
+  }
+  // h and the reference's hand-written dh/dx incl. its +eps terms (kinematic_bicycle2D_c3bf.py:43-73)
+  static SCB_HD void barrier(const scb_params& p, const AgentCT& g, const double* o, double& h, double* dh) {
+    const double ovx = o[3], ovy = o[4];
+    const double ego = (o[2] + p.radius) * 1.0;
+    const double prx = o[0] - g.px, pry = o[1] - g.py;
+    const double vrx = ovx - g.v * g.c, vry = ovy - g.v * g.s;
+    const double pm = sqrt(prx * prx + pry * pry);
+    const double vm = sqrt(vrx * vrx + vry * vry);
+    const double eps = 1e-6;
+    const double sq = sqrt(fmax(pm * pm - ego * ego, eps));
+    const double cosphi = sq / (pm + eps);
+    h = (prx * vrx + pry * vry) + pm * vm * cosphi;
+    dh[0] = -vrx - vm * prx / (sq + eps);
+    dh[1] = -vry - vm * pry / (sq + eps);
+    dh[2] = g.v * g.s * prx - g.v * g.c * pry + (sq + eps) / vm * (g.v * (ovx * g.s - ovy * g.c));
+    dh[3] = -g.c * prx - g.s * pry + (sq + eps) / vm * (g.v - (ovx * g.c + ovy * g.s));
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    double h, dh[4];
+    barrier(p, g, o, h, dh);
+    r.a[0] = dh[3];
+    r.a[1] = dh[0] * (-g.v * g.s) + dh[1] * (g.v * g.c) + dh[2] * (g.v / p.rear_ax_dist);
+    const double lf = dh[0] * g.fx + dh[1] * g.fy;
+    r.b = (p.cbf_mode == 1) ? h / p.dt + lf : lf + p.alpha * h;
+  }
+};
+
+}  // namespace scb

@@ -1,0 +1,115 @@
+// scb_params.cc -- the reference's per-(model, controller) defaults as a POD.
+// No CUDA here: compiled into libscb.so by nvcc and into the CPU host-sim test aid by g++.
+//
+// Sources of every constant:
+//   robots/robot.py:49                         radius 0.25 (set before the model ctor)
+//   robots/single_integrator2D.py:41-42        v_max 1.0
+//   robots/dynamic_unicycle2D.py:38-40         a_max 0.5, w_max 0.5, v_max 1.0
+//   robots/kinematic_bicycle2D.py:44-53        wheel_base 0.4, rear_ax_dist 0.2, v_max 3.5, a_max 5.0,
+//                                              delta_max 32 deg, beta_max = atan(L_r/L tan(delta_max)), v_min 0.2
+//   robots/quad3D.py:53-61                     mass 3, Ix=Iy=Iz 0.5, L 0.3, nu 0.1, u in [-10, 10], g 9.8
+//   position_control/cbf_qp.py:12-35           alpha 1.0 (SI) / 1.5 (C3BF); alpha1 = alpha2 = 1.5 (DU, KB)
+//   position_control/optimal_decay_cbf_qp.py:17-50   alpha(1,2) 0.5, omega0 1.0, p_sb 1e4
+//   position_control/mpc_cbf.py:19-39,49-82    Q, R, alpha per model
+#include <math.h>
+#include <string.h>
+
+#include "../../include/scb.h"
+
+extern "C" {
+
+int scb_version(void) { return SCB_VERSION; }
+
+const char* scb_strerror(int err) {
+  switch (err) {
+    case SCB_OK: return "ok";
+    case SCB_ERR_BAD_ARG: return "bad argument (null pointer, negative size or unknown model)";
+    case SCB_ERR_UNSUPPORTED: return "model/controller pair not supported (the reference has no branch for it either)";
+    case SCB_ERR_TOO_LARGE: return "obstacle slots or horizon beyond the compiled limits (see scb_limits)";
+    case SCB_ERR_CUDA: return "CUDA launch or copy failed (see scb_last_cuda_error)";
+    case SCB_ERR_NO_DEVICE: return "no CUDA device";
+    case SCB_ERR_ALLOC: return "allocation failed";
+    default: return "unknown error";
+  }
+}
+
+int scb_model_dims(int model, int* nx, int* nu) {
+  int x, u;
+  switch (model) {
+    case SCB_SINGLE_INTEGRATOR_2D: x = 2; u = 2; break;
+    case SCB_DYNAMIC_UNICYCLE_2D:
+    case SCB_KINEMATIC_BICYCLE_2D:
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: x = 4; u = 2; break;
+    case SCB_QUAD_3D: x = 12; u = 4; break;
+    default: return SCB_ERR_BAD_ARG;
+  }
+  if (nx) *nx = x;
+  if (nu) *nu = u;
+  return SCB_OK;
+}
+
+int scb_active_words(int M, int nu) { return (M + 2 * nu + 63) / 64; }
+
+int scb_params_default(scb_params* p, int model, const char* controller) {
+  if (!p || !controller) return SCB_ERR_BAD_ARG;
+  memset(p, 0, sizeof(*p));
+  int nx, nu;
+  if (scb_model_dims(model, &nx, &nu) != SCB_OK) return SCB_ERR_BAD_ARG;
+  const bool qp = strcmp(controller, "cbf_qp") == 0;
+  const bool od = strcmp(controller, "optimal_decay_cbf_qp") == 0;
+  const bool mpc = strcmp(controller, "mpc_cbf") == 0;
+  if (!qp && !od && !mpc) return SCB_ERR_BAD_ARG;
+  p->model = model; p->nx = nx; p->nu = nu;
+  p->dt = 0.05;
+  p->radius = 0.25;
+  p->gravity = 9.8;
+  p->mpc_max_iter = 200;
+  p->mpc_tol = 1e-8;
+  p->v_min = -1e300; p->v_max = 1e300;
+  switch (model) {
+    case SCB_SINGLE_INTEGRATOR_2D:
+      p->u_lb[0] = p->u_lb[1] = -1.0; p->u_ub[0] = p->u_ub[1] = 1.0;
+      if (qp) p->alpha = 1.0;
+      if (mpc) { p->alpha = 0.05; p->Q[0] = p->Q[1] = 50; p->R[0] = p->R[1] = 5; }
+      if (od) return SCB_ERR_UNSUPPORTED;             // optimal_decay_cbf_qp.py:51-52 raises
+      break;
+    case SCB_DYNAMIC_UNICYCLE_2D:
+      p->u_lb[0] = -0.5; p->u_ub[0] = 0.5; p->u_lb[1] = -0.5; p->u_ub[1] = 0.5;
+      p->v_max = 1.0; p->v_min = -1.0;
+      if (qp) p->alpha1 = p->alpha2 = 1.5;
+      if (od) { p->alpha1 = p->alpha2 = 0.5; p->omega1_0 = p->omega2_0 = 1.0; p->p_sb1 = p->p_sb2 = 1e4; }
+      if (mpc) { p->alpha1 = p->alpha2 = 0.15; p->Q[0] = p->Q[1] = 50; p->Q[2] = 0.01; p->Q[3] = 30; p->R[0] = p->R[1] = 0.5; }
+      break;
+    case SCB_KINEMATIC_BICYCLE_2D:
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: {
+      const double Lr = 0.2, L = 0.4, dmax = 32.0 * M_PI / 180.0;
+      const double bmax = atan(Lr / L * tan(dmax));
+      p->rear_ax_dist = Lr;
+      p->u_lb[0] = -5.0; p->u_ub[0] = 5.0; p->u_lb[1] = -bmax; p->u_ub[1] = bmax;
+      p->v_min = 0.2; p->v_max = 3.5;
+      const bool c3 = model == SCB_KINEMATIC_BICYCLE_2D_C3BF;
+      if (qp) { if (c3) p->alpha = 1.5; else p->alpha1 = p->alpha2 = 1.5; }
+      if (od) {
+        p->omega1_0 = 1.0; p->p_sb1 = 1e4;
+        if (c3) p->alpha = 0.5; else { p->alpha1 = p->alpha2 = 0.5; p->omega2_0 = 1.0; p->p_sb2 = 1e4; }
+      }
+      if (mpc) {
+        if (c3) p->alpha = 0.15; else p->alpha1 = p->alpha2 = 0.1;
+        p->Q[0] = p->Q[1] = 50; p->Q[2] = 1; p->Q[3] = 1; p->R[0] = 0.5; p->R[1] = 5000.0;
+      }
+      break;
+    }
+    case SCB_QUAD_3D: {
+      if (!mpc) return SCB_ERR_UNSUPPORTED;            // agent_barrier raises, quad3D.py:269-273
+      p->mass = 3.0; p->Ix = p->Iy = p->Iz = 0.5; p->arm_L = 0.3; p->nu_coef = 0.1;
+      for (int i = 0; i < 4; ++i) { p->u_lb[i] = -10.0; p->u_ub[i] = 10.0; p->R[i] = 1.0; }
+      const double Q[12] = {30, 30, 5, 20, 20, 1, 10, 10, 10, 20, 20, 1};
+      for (int i = 0; i < 12; ++i) p->Q[i] = Q[i];
+      p->alpha = 0.15;
+      break;
+    }
+  }
+  return SCB_OK;
+}
+
+}  // extern "C"

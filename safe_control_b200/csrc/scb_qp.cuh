@@ -1,0 +1,213 @@
+// scb_qp.cuh -- per-agent bodies of the two QP controllers (device + host-sim).
+//
+//   cbfqp_agent  : CBFQP.solve_control_problem            position_control/cbf_qp.py:108-199
+//   odcbf_agent  : OptimalDecayCBFQP.solve_control_problem position_control/optimal_decay_cbf_qp.py:132-159
+//
+// Both are "fused": the constraint rows are assembled straight into the lane registers
+// the solver reads (they never touch HBM), then solved exactly (scb_gi.cuh).
+#pragma once
+
+#include "scb_gi.cuh"
+#include "scb_models.cuh"
+
+namespace scb {
+
+// Row r of the CBF-QP, r in [0, M + 2 NU):
+//   r <  M      : CBF row of obstacle slot r (vacuous 0 >= 0 when r >= nobs, cbf_qp.py:110-111)
+//   r = M + 2i  : u_i <= ub_i      r = M + 2i + 1 : u_i >= lb_i          (cbf_qp.py:54-73)
+template <int MODEL>
+SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, int M, int nobs, int r,
+                      double* a, double& b) {
+  constexpr int NU = ModelCT<MODEL>::NU;
+#pragma unroll
+  for (int i = 0; i < NU; ++i) a[i] = 0.0;
+  b = 0.0;
+  if (r < M) {
+    if (r < nobs) {
+      double o[7];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) o[q] = ld(obs + (size_t)r * 7 + q);
+      RowOut ro;
+      ModelCT<MODEL>::row(p, g, o, ro);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) a[i] = ro.a[i];
+      b = ro.b;
+    }
+  } else if (r < M + 2 * NU) {
+    const int q = r - M, i = q >> 1;
+    if (q & 1) {
+#pragma unroll
+      for (int t = 0; t < NU; ++t) if (t == i) { a[t] = 1.0; b = -p.u_lb[t]; }
+    } else {
+#pragma unroll
+      for (int t = 0; t < NU; ++t) if (t == i) { a[t] = -1.0; b = p.u_ub[t]; }
+    }
+  }
+}
+
+template <int MODEL, int LANES, int RPL>
+SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
+                        const double* obs, double* U, int32_t* status, uint64_t* active, int words) {
+  using Mod = ModelCT<MODEL>;
+  using G = Grp<LANES>;
+  constexpr int NU = Mod::NU;
+  const int lane = G::lane();
+
+  double ur[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) ur[i] = ld(uref + i);
+
+  if (nobs < 0) {                    // obs_list is None -> u_ref unclipped (cbf_qp.py:113-118)
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) U[i] = ur[i];
+      *status = SCB_OPTIMAL;
+      if (active) for (int w = 0; w < words; ++w) active[w] = 0ull;
+    }
+    return;
+  }
+  if (nobs > M) nobs = M;            // "Stop if we exceed allocated constraints" (cbf_qp.py:128-129)
+
+  double xs[Mod::NX];
+#pragma unroll
+  for (int i = 0; i < Mod::NX; ++i) xs[i] = ld(x + i);
+  AgentCT g;
+  Mod::prep(p, xs, g);
+
+  double ra[RPL][NU], rb[RPL];
+  const int mrows = M + 2 * NU;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) cbfqp_row<MODEL>(p, g, obs, M, nobs, j * LANES + lane, ra[j], rb[j]);
+
+  double hd[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) hd[i] = 2.0;
+  QpOut<NU> q;
+  gi_solve<NU, LANES, RPL>(hd, ur, ra, rb, mrows, 8 * mrows + 16, q);
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      double v = q.x[i];
+      if (q.status != SCB_OPTIMAL) v = fmin(fmax(v, p.u_lb[i]), p.u_ub[i]);   // never NaN out of the box
+      U[i] = v;
+    }
+    *status = q.status;
+    if (active) {
+      for (int w = 0; w < words; ++w) {
+        uint64_t bits = 0ull;
+#pragma unroll
+        for (int a = 0; a < NU; ++a)
+          if (a < q.wk && q.lam[a] > 0.0 && (q.widx[a] >> 6) == w) bits |= 1ull << (q.widx[a] & 63);
+        active[w] = bits;
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Optimal-decay CBF-QP.  Variables z = [u (2), omega1 (, omega2)], ONE CBF row
+// (optimal_decay_cbf_qp.py:61) built from the nearest valid obstacle of the agent's list
+// (tracking.py:585-586), 4 box rows.  NW = number of omega variables (1: C3BF, 2: DU/KB).
+// Active bits: bit 0 = CBF row, bit 1+2i = u_i upper, bit 2+2i = u_i lower.
+template <int MODEL, int NW, int LANES, int RPL>
+SCB_HD void odcbf_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
+                        const double* obs, double* U, double* omega, int32_t* sel, int32_t* status,
+                        uint64_t* active) {
+  using Mod = ModelCT<MODEL>;
+  using G = Grp<LANES>;
+  constexpr int NU = 2, NV = NU + NW;
+  const int lane = G::lane();
+  if (nobs > M || nobs < 0) nobs = (nobs < 0) ? 0 : M;
+
+  double xs[Mod::NX];
+#pragma unroll
+  for (int i = 0; i < Mod::NX; ++i) xs[i] = ld(x + i);
+  AgentCT g;
+  Mod::prep(p, xs, g);
+
+  // nearest obstacle by centre distance (first row of tracking.py:get_nearest_unpassed_obs' sort)
+  double bestd = kInf;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    const int r = j * LANES + lane;
+    if (r < nobs) {
+      const double dx = ld(obs + (size_t)r * 7) - g.px, dy = ld(obs + (size_t)r * 7 + 1) - g.py;
+      const double d2 = dx * dx + dy * dy;
+      if (d2 < bestd) { bestd = d2; bi = r; }
+    }
+  }
+  G::argmin(bestd, bi);
+  const bool has = (bi != 0x7fffffff);
+
+  // the single CBF row, replicated in every lane
+  double ra[5][NV], rb[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ra[r][i] = 0.0;
+    rb[r] = 0.0;
+  }
+  if (has) {
+    double o[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) o[q] = ld(obs + (size_t)bi * 7 + q);
+    if (MODEL == SCB_KINEMATIC_BICYCLE_2D_C3BF) {                       // optimal_decay_cbf_qp.py:139-143
+      double h, dh[4];
+      ModelCT<SCB_KINEMATIC_BICYCLE_2D_C3BF>::barrier(p, g, o, h, dh);
+      ra[0][0] = dh[3];
+      ra[0][1] = dh[0] * (-g.v * g.s) + dh[1] * (g.v * g.c) + dh[2] * (g.v / p.rear_ax_dist);
+      rb[0] = dh[0] * g.fx + dh[1] * g.fy;
+      ra[0][2] = p.alpha * h;
+    } else if (MODEL == SCB_DYNAMIC_UNICYCLE_2D) {                       // :144-149
+      double h, hd, dhd[4];
+      ModelCT<SCB_DYNAMIC_UNICYCLE_2D>::barrier(p, g, o, h, hd, dhd);
+      ra[0][0] = dhd[3]; ra[0][1] = dhd[2];
+      rb[0] = dhd[0] * g.fx + dhd[1] * g.fy;
+      if (NW == 2) {
+        ra[0][2] = (p.alpha1 + p.alpha2) * hd;
+        ra[0][NV - 1] = (p.alpha1 * p.alpha2) * h;
+      }
+    }
+    // plain KinematicBicycle2D: the reference has no branch -> zero row
+  }
+#pragma unroll
+  for (int i = 0; i < NU; ++i) {
+    ra[1 + 2 * i][i] = -1.0; rb[1 + 2 * i] = p.u_ub[i];
+    ra[2 + 2 * i][i] = 1.0;  rb[2 + 2 * i] = -p.u_lb[i];
+  }
+
+  double hd[NV], z0[NV];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) { hd[i] = 2.0; z0[i] = ld(uref + i); }
+  hd[NU] = 2.0 * p.p_sb1; z0[NU] = p.omega1_0;
+  if (NW == 2) { hd[NV - 1] = 2.0 * p.p_sb2; z0[NV - 1] = p.omega2_0; }
+
+  QpOut<NV> q;
+  gi_solve<NV, 1, 5>(hd, z0, ra, rb, 5, 64, q);     // 5 rows: replicated per lane, no shuffles
+
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      double v = q.x[i];
+      if (q.status != SCB_OPTIMAL) v = fmin(fmax(v, p.u_lb[i]), p.u_ub[i]);
+      U[i] = v;
+    }
+    if (omega) {
+      omega[0] = q.x[NU];
+      omega[1] = (NW == 2) ? q.x[NV - 1] : nan("");
+    }
+    if (sel) *sel = has ? bi : -1;
+    *status = q.status;
+    if (active) {
+      uint64_t bits = 0ull;
+#pragma unroll
+      for (int a = 0; a < NV; ++a)
+        if (a < q.wk && q.lam[a] > 0.0) bits |= 1ull << q.widx[a];
+      *active = bits;
+    }
+  }
+}
+
+}  // namespace scb

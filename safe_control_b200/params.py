@@ -1,0 +1,95 @@
+"""robot_spec dict -> scb_params POD.
+
+Mirrors the reference's `setdefault` cascades and gain overrides:
+  robots/robot.py:49, robots/<model>.py ctor defaults      (model parameters)
+  position_control/cbf_qp.py:12-43                         ('cbf_alpha*', 'cbf_mode')
+  position_control/optimal_decay_cbf_qp.py:17-50
+  position_control/mpc_cbf.py:15,19-95                     ('mpc_cbf_alpha*', 'mpc_horizon')
+The library supplies the defaults (scb_params_default); this module only applies
+what the caller put in robot_spec, using the reference's own key names.
+"""
+import math
+
+from ._abi import MODEL_IDS, ScbParams, ERR_UNSUPPORTED
+
+CONTROLLERS = ("cbf_qp", "optimal_decay_cbf_qp", "mpc_cbf")
+
+
+class NotCompatibleError(Exception):
+    """Same name as position_control/optimal_decay_cbf_qp.py:4-12."""
+
+    def __init__(self, message="Currently not compatible with the robot model."):
+        self.message = message
+        super().__init__(self.message)
+
+
+def resolve_params(robot_spec, controller, dt=0.05, lib=None):
+    """-> (ScbParams, resolved_spec dict).  `lib` defaults to the CUDA library."""
+    if lib is None:
+        from ._lib import lib as _get
+        lib = _get()
+    if controller not in CONTROLLERS:
+        raise ValueError(f"Unknown controller type: {controller}")
+    model = robot_spec.get("model")
+    if model not in MODEL_IDS:
+        raise ValueError(f"Invalid robot model: {model!r} (supported: {sorted(MODEL_IDS)})")
+    p = ScbParams()
+    rc = lib.scb_params_default(p, MODEL_IDS[model], controller.encode())
+    if rc == ERR_UNSUPPORTED:
+        raise NotCompatibleError(f"{controller} is not compatible with {model}")
+    if rc != 0:
+        raise RuntimeError(lib.scb_strerror(rc).decode())
+    s = dict(robot_spec)
+    p.dt = float(dt)
+    p.radius = float(s.setdefault("radius", 0.25))
+    p.cbf_mode = 1 if s.get("cbf_mode", "cbf") == "hard" else 0
+
+    if model == "SingleIntegrator2D":
+        v = float(s.setdefault("v_max", 1.0))
+        s.setdefault("w_max", 0.5)
+        p.u_lb[0] = p.u_lb[1] = -v
+        p.u_ub[0] = p.u_ub[1] = v
+    elif model == "DynamicUnicycle2D":
+        a = float(s.setdefault("a_max", 0.5)); w = float(s.setdefault("w_max", 0.5))
+        v = float(s.setdefault("v_max", 1.0))
+        p.u_lb[0], p.u_ub[0], p.u_lb[1], p.u_ub[1] = -a, a, -w, w
+        p.v_max = v; p.v_min = -v
+    elif model.startswith("KinematicBicycle2D"):
+        s.setdefault("wheel_base", 0.4); s.setdefault("front_ax_dist", 0.2)
+        lr = float(s.setdefault("rear_ax_dist", 0.2))
+        v = float(s.setdefault("v_max", 3.5)); a = float(s.setdefault("a_max", 5.0))
+        dmax = float(s.setdefault("delta_max", math.radians(32)))
+        b = float(s.setdefault("beta_max", math.atan(lr / s["wheel_base"] * math.tan(dmax))))
+        vmin = float(s.setdefault("v_min", 0.2))
+        p.rear_ax_dist = lr
+        p.u_lb[0], p.u_ub[0], p.u_lb[1], p.u_ub[1] = -a, a, -b, b
+        p.v_min, p.v_max = vmin, v
+    elif model == "Quad3D":
+        p.mass = float(s.setdefault("mass", 3.0))
+        p.Ix = float(s.setdefault("Ix", 0.5)); p.Iy = float(s.setdefault("Iy", 0.5)); p.Iz = float(s.setdefault("Iz", 0.5))
+        p.arm_L = float(s.setdefault("L", 0.3)); p.nu_coef = float(s.setdefault("nu", 0.1))
+        umax = float(s.setdefault("u_max", 10.0)); umin = float(s.setdefault("u_min", -10.0))
+        for i in range(4):
+            p.u_lb[i], p.u_ub[i] = umin, umax
+
+    prefix = {"cbf_qp": "cbf_", "mpc_cbf": "mpc_cbf_"}.get(controller)
+    if prefix:
+        for k in ("alpha", "alpha1", "alpha2"):
+            if prefix + k in s:
+                setattr(p, k, float(s[prefix + k]))
+    if "mpc_max_iter" in s:
+        p.mpc_max_iter = int(s["mpc_max_iter"])
+    if "mpc_tol" in s:
+        p.mpc_tol = float(s["mpc_tol"])
+    return p, s
+
+
+def cbf_param_dict(p, controller, model):
+    """The `.cbf_param` dict the reference exposes (tracking.py:738 reads alpha1/alpha2)."""
+    rel2 = model in ("DynamicUnicycle2D", "KinematicBicycle2D")
+    d = {"alpha1": p.alpha1, "alpha2": p.alpha2} if rel2 else {"alpha": p.alpha}
+    if controller == "optimal_decay_cbf_qp":
+        d.update(omega1=p.omega1_0, p_sb1=p.p_sb1)
+        if rel2:
+            d.update(omega2=p.omega2_0, p_sb2=p.p_sb2)
+    return d

@@ -1,0 +1,165 @@
+"""Synthetic waypoint/obstacle scenes for tests and bench.py.
+
+Vectorised numpy, float64, seeded.  Produces exactly what the reference's caller hands the
+controller each step:
+  X        robot.X                                                  (robots/robot.py:38)
+  U_ref    robot.nominal_input(goal)                                (tracking.py:589-604)
+  OBS/nobs get_nearest_unpassed_obs(..., obs_num=num_constraints)   (tracking.py:345-403), padded
+           to M rows with the reference's own dummy row [1000, 1000, 0, 0, 0, 0, 0] (mpc_cbf.py:346)
+  goal     current waypoint
+
+Host-side input preparation only -- nothing here is on the timed hot path.
+"""
+import math
+
+import numpy as np
+
+DUMMY_OBS = np.array([1000.0, 1000.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+ANGLE_UNPASSED = {   # tracking.py:352-357
+    "SingleIntegrator2D": 2.0 * np.pi, "Quad3D": 2.0 * np.pi, "DynamicUnicycle2D": 1.2 * np.pi,
+    "KinematicBicycle2D": 2.0 * np.pi, "KinematicBicycle2D_C3BF": 2.0 * np.pi,
+}
+BARRIER_BETA = {"SingleIntegrator2D": 1.01, "DynamicUnicycle2D": 1.01, "KinematicBicycle2D": 1.1,
+                "KinematicBicycle2D_C3BF": 1.1, "Quad3D": 1.01}
+
+
+def angle_normalize(x):
+    return ((x + np.pi) % (2 * np.pi)) - np.pi
+
+
+# ------------------------------------------------------------------ nominal inputs (vectorised)
+def nominal_input(model, spec, X, goal, optimal_decay=False):
+    """Vectorised robots/<model>.py:nominal_input as called through the facade
+    (robots/robot.py:401-415; optimal-decay gains from tracking.py:601-602)."""
+    X = np.asarray(X, float); goal = np.asarray(goal, float)
+    if model == "SingleIntegrator2D":                          # single_integrator2D.py:72-90
+        err = goal[:, 0:2] - X[:, 0:2]
+        err = np.sign(err) * np.maximum(np.abs(err) - 0.05, 0.0)
+        mag = np.linalg.norm(err, axis=1, keepdims=True)
+        vmax = spec["v_max"]
+        return np.where(mag > vmax, err * vmax / np.maximum(mag, 1e-300), err)
+    if model == "DynamicUnicycle2D":                           # dynamic_unicycle2D.py:80-104
+        k_omega, k_a, k_v = (3.0, 0.5, 0.5) if optimal_decay else (2.0, 1.0, 1.0)
+        k_omega = spec.get("nominal_k_omega", k_omega); k_a = spec.get("nominal_k_a", k_a)
+        k_v = spec.get("nominal_k_v", k_v)
+        dist = np.maximum(np.linalg.norm(X[:, 0:2] - goal[:, 0:2], axis=1) - 0.05, 0.0)
+        err = angle_normalize(np.arctan2(goal[:, 1] - X[:, 1], goal[:, 0] - X[:, 0]) - X[:, 2])
+        v = np.where(np.abs(err) > np.deg2rad(90), 0.0, np.minimum(k_v * dist * np.cos(err), spec["v_max"]))
+        return np.stack([k_a * (v - X[:, 3]), k_omega * err], axis=1)
+    if model.startswith("KinematicBicycle2D"):                 # kinematic_bicycle2D.py:125-147
+        # facade passes (d_min, k_omega, k_a, k_v) positionally -> k_theta = k_omega
+        k_theta, k_a, k_v = (3.0, 0.5, 0.5) if optimal_decay else (2.0, 1.0, 1.0)
+        dist = np.maximum(np.linalg.norm(X[:, 0:2] - goal[:, 0:2], axis=1) - 0.05, 0.05)
+        err = angle_normalize(np.arctan2(goal[:, 1] - X[:, 1], goal[:, 0] - X[:, 0]) - X[:, 2])
+        delta = np.clip(k_theta * err, -spec["delta_max"], spec["delta_max"])
+        beta = np.arctan(spec["rear_ax_dist"] / spec["wheel_base"] * np.tan(delta))
+        v = np.clip(k_v * dist * np.maximum(0.0, np.cos(err)), spec["v_min"], spec["v_max"])
+        return np.stack([k_a * (v - X[:, 3]), beta], axis=1)
+    if model == "Quad3D":                                      # quad3D.py:160-206
+        g, m = 9.8, spec["mass"]
+        k_p, k_d, k_ang = 1.0, 2.0, 5.0
+        acc = k_p * (goal[:, 0:3] - X[:, 0:3]) + k_d * (-X[:, 6:9])
+        th_des, ph_des, F = acc[:, 0] / g, -acc[:, 1] / g, m * acc[:, 2]
+        tau_y = spec["Iy"] * (k_ang * (th_des - X[:, 3]) + k_d * (-X[:, 9]))
+        tau_x = spec["Ix"] * (k_ang * (ph_des - X[:, 4]) + k_d * (-X[:, 10]))
+        tau_z = spec["Iz"] * (k_ang * (0 - X[:, 5]) + k_d * (-X[:, 11]))
+        L, nu = spec["L"], spec["nu"]
+        B2 = np.array([[1, 1, 1, 1], [0, L, 0, -L], [L, 0, -L, 0], [nu, -nu, nu, -nu]], float)
+        u = np.stack([F, tau_y, tau_x, tau_z], axis=1) @ np.linalg.pinv(B2).T
+        return np.clip(u, spec["u_min"], spec["u_max"])
+    raise ValueError(model)
+
+
+# ------------------------------------------------------------------ obstacle selection (vectorised)
+def nearest_unpassed_obs(model, pos, yaw, scene_obs, obs_num):
+    """Vectorised tracking.py:345-403 for N agents over one shared scene.
+    -> OBS [N, obs_num, 7] (padded with DUMMY_OBS), nobs [N] int32, idx [N, obs_num] (-1 = pad)."""
+    N, K = pos.shape[0], scene_obs.shape[0]
+    d = scene_obs[None, :, 0:2] - pos[:, None, 0:2]
+    ang = np.arctan2(d[..., 1], d[..., 0])
+    keep = np.abs(angle_normalize(ang - yaw[:, None])) <= ANGLE_UNPASSED[model] / 2
+    none = ~keep.any(axis=1)
+    keep[none] = True                                          # fallback: nearest of all (tracking.py:393-397)
+    dist = np.linalg.norm(d, axis=2)
+    dist = np.where(keep, dist, np.inf)
+    order = np.argsort(dist, axis=1, kind="stable")[:, :obs_num]
+    cnt = np.minimum(keep.sum(axis=1), obs_num).astype(np.int32)
+    take = min(obs_num, K)
+    valid = np.arange(take)[None, :] < cnt[:, None]
+    OBS = np.tile(DUMMY_OBS, (N, obs_num, 1))
+    sel = scene_obs[order]                                     # [N, take, 7]
+    OBS[:, :take][valid] = sel[valid]
+    idx = np.full((N, obs_num), -1, dtype=np.int64)
+    idx[:, :take][valid] = order[valid]
+    return OBS, cnt, idx
+
+
+# ------------------------------------------------------------------ scenes
+def default_spec(model):
+    s = {"model": model, "radius": 0.25}
+    if model == "SingleIntegrator2D":
+        s.update(v_max=1.0, w_max=0.5)
+    elif model == "DynamicUnicycle2D":
+        s.update(a_max=0.5, w_max=0.5, v_max=1.0)
+    elif model.startswith("KinematicBicycle2D"):
+        dmax = math.radians(32)
+        s.update(wheel_base=0.4, front_ax_dist=0.2, rear_ax_dist=0.2, v_max=3.5, a_max=5.0, delta_max=dmax,
+                 beta_max=math.atan(0.5 * math.tan(dmax)), v_min=0.2)
+    elif model == "Quad3D":
+        s.update(mass=3.0, Ix=0.5, Iy=0.5, Iz=0.5, L=0.3, nu=0.1, u_max=10.0, u_min=-10.0)
+    return s
+
+
+def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=False, spec=None):
+    """-> dict(X, U_ref, goal, OBS [N,M,7], nobs [N] i32, scene_obs [M,7], u_prev, spec)"""
+    rng = np.random.default_rng(seed)
+    spec = dict(default_spec(model), **(spec or {}))
+    if dynamic is None:
+        dynamic = model.endswith("C3BF")
+    L = (2.5 if dense else 4.0) * math.sqrt(M)
+    scene = np.zeros((M, 7))
+    scene[:, 0:2] = rng.uniform(0, L, (M, 2))
+    scene[:, 2] = rng.uniform(0.2, 0.6, M)
+    if dynamic:
+        scene[:, 3:5] = rng.uniform(-0.5, 0.5, (M, 2))
+    R, beta = spec["radius"], BARRIER_BETA[model]
+    # agents: rejection-sample positions so every h > 0.05 (start safe)
+    pos = np.empty((N, 2)); todo = np.arange(N)
+    while todo.size:
+        cand = rng.uniform(0, L, (todo.size, 2))
+        d2 = ((cand[:, None, :] - scene[None, :, 0:2]) ** 2).sum(-1)
+        h = d2 - beta * (scene[None, :, 2] + R) ** 2
+        ok = (h > 0.05).all(axis=1)
+        pos[todo[ok]] = cand[ok]
+        todo = todo[~ok]
+    goal2 = rng.uniform(0, L, (N, 2))
+    nx = {"SingleIntegrator2D": 2, "Quad3D": 12}.get(model, 4)
+    X = np.zeros((N, nx)); X[:, 0:2] = pos
+    yaw = np.zeros(N)
+    if nx == 4:
+        theta = rng.uniform(-np.pi, np.pi, N)
+        if model == "DynamicUnicycle2D":
+            v = rng.uniform(0, spec["v_max"], N)
+        else:
+            v = rng.uniform(spec["v_min"], spec["v_max"], N)
+        if dense:   # head at the nearest obstacle, fast
+            d = scene[None, :, 0:2] - pos[:, None, :]
+            j = np.argmin((d ** 2).sum(-1), axis=1)
+            theta = np.arctan2(d[np.arange(N), j, 1], d[np.arange(N), j, 0]) + rng.normal(0, 0.2, N)
+            theta = angle_normalize(theta)
+            v = rng.uniform(0.5, 1.0, N) * spec["v_max"]
+        X[:, 2] = theta; X[:, 3] = v; yaw = theta
+        goal = goal2
+    elif nx == 12:
+        X[:, 2] = rng.uniform(1, 3, N)
+        X[:, 3:6] = rng.normal(0, 0.05, (N, 3)); X[:, 6:9] = rng.normal(0, 0.5, (N, 3))
+        X[:, 9:12] = rng.normal(0, 0.05, (N, 3)); yaw = X[:, 5].copy()
+        goal = np.concatenate([goal2, rng.uniform(1, 3, (N, 1))], axis=1)
+    else:
+        goal = goal2
+    U_ref = nominal_input(model, spec, X, goal, optimal_decay=optimal_decay)
+    OBS, nobs, idx = nearest_unpassed_obs(model, pos, yaw, scene, M)
+    nu = 4 if model == "Quad3D" else 2
+    return dict(model=model, spec=spec, X=np.ascontiguousarray(X), U_ref=np.ascontiguousarray(U_ref),
+                goal=np.ascontiguousarray(goal), OBS=np.ascontiguousarray(OBS), nobs=nobs, obs_idx=idx,
+                scene_obs=scene, u_prev=np.zeros((N, nu)), L=L)

@@ -1,0 +1,66 @@
+"""Loader for the CPU host-sim of the kernel bodies (test aid, see tests/_hostsim/hostsim.cpp)."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+from safe_control_b200 import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def hostsim():
+    global _lib
+    if _lib is None:
+        spec = importlib.util.spec_from_file_location("hostsim_build", os.path.join(_HERE, "_hostsim", "build.py"))
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        _lib = C.CDLL(mod.build())
+        _abi.bind(_lib, names=("scb_params_default", "scb_strerror", "scb_model_dims", "scb_active_words", "scb_version"))
+    return _lib
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def hs_cbfqp_rows(p, X, OBS, nobs=None):
+    lib = hostsim()
+    N, M = OBS.shape[0], OBS.shape[1]
+    X, OBS = f64(X), f64(OBS)
+    A = np.zeros((N, M, p.nu)); b = np.zeros((N, M))
+    no = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)
+    rc = lib.hostsim_cbfqp_rows(C.byref(p), N, M, ptr(X), ptr(OBS), C.c_long(7 * M), ptr(no), ptr(A), ptr(b))
+    assert rc == 0, rc
+    return A, b
+
+
+def hs_cbfqp_solve(p, X, Uref, OBS, nobs=None):
+    lib = hostsim()
+    N, M = OBS.shape[0], OBS.shape[1]
+    X, Uref, OBS = f64(X), f64(Uref), f64(OBS)
+    words = (M + 2 * p.nu + 63) // 64
+    U = np.zeros((N, p.nu)); st = np.zeros(N, np.int32); act = np.zeros((N, words), np.uint64)
+    no = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)
+    rc = lib.hostsim_cbfqp_solve(C.byref(p), N, M, ptr(X), ptr(Uref), ptr(OBS), C.c_long(7 * M), ptr(no),
+                                 ptr(U), ptr(st), ptr(act))
+    assert rc == 0, rc
+    return U, st, act
+
+
+def hs_odcbf_solve(p, X, Uref, OBS, nobs=None):
+    lib = hostsim()
+    N, M = OBS.shape[0], OBS.shape[1]
+    X, Uref, OBS = f64(X), f64(Uref), f64(OBS)
+    U = np.zeros((N, 2)); om = np.zeros((N, 2)); sel = np.zeros(N, np.int32)
+    st = np.zeros(N, np.int32); act = np.zeros(N, np.uint64)
+    no = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)
+    rc = lib.hostsim_odcbf_solve(C.byref(p), N, M, ptr(X), ptr(Uref), ptr(OBS), C.c_long(7 * M), ptr(no),
+                                 ptr(U), ptr(om), ptr(sel), ptr(st), ptr(act))
+    assert rc == 0, rc
+    return U, om, sel, st, act

@@ -1,0 +1,73 @@
+"""Shared parity checks: any backend (CUDA C-ABI or CPU host-sim) vs the oracle."""
+import numpy as np
+
+from oracle.controllers import OracleCBFQP, OracleOptimalDecayCBFQP
+
+U_TOL = 1e-8          # ||u - u*||_inf <= U_TOL * max(1, ||u*||_inf)     (SURVEY 8c "stated tolerances")
+GAP_MIN = 1e-7        # active masks compared bit-exactly when strict complementarity gap > GAP_MIN
+
+
+def mask_from_bool(active, words):
+    out = np.zeros(words, dtype=np.uint64)
+    for j in np.nonzero(active)[0]:
+        out[j >> 6] |= np.uint64(1) << np.uint64(j & 63)
+    return out
+
+
+def check_cbfqp(spec, M, X, Uref, OBS, nobs, U, status, active, sample=None):
+    """-> stats dict; asserts parity."""
+    ctrl = OracleCBFQP(spec, num_obs=M)
+    N = X.shape[0]
+    idx = range(N) if sample is None else sample
+    words = (M + 2 * ctrl.model.nu + 63) // 64
+    n_inf = n_act = n_box = n_cmp = 0
+    for i in idx:
+        k = M if nobs is None else int(nobs[i])
+        obs = None if k < 0 else OBS[i][:k]
+        u, info = ctrl.solve(X[i], Uref[i], obs)
+        assert info["status"] == status[i], f"agent {i}: status {status[i]} vs oracle {info['status']}"
+        if info["status"] != 0:
+            n_inf += 1
+            continue
+        err = np.max(np.abs(u - U[i]))
+        assert err <= U_TOL * max(1.0, np.max(np.abs(u))), f"agent {i}: |du|={err:.3e} u*={u} got={U[i]}"
+        if k < 0:
+            continue
+        act = info["active"]
+        n_act += bool(act[:M].any()); n_box += bool(act[M:].any())
+        if active is not None and info["gap"] > GAP_MIN:
+            n_cmp += 1
+            want = mask_from_bool(act, words)
+            got = np.asarray(active[i]).view(np.uint64).reshape(-1)
+            assert np.array_equal(want, got), f"agent {i}: active {got} vs oracle {want} (gap {info['gap']:.2e})"
+    return dict(n=len(list(idx)), infeasible=n_inf, cbf_active=n_act, box_active=n_box, masks_compared=n_cmp)
+
+
+def check_odcbf(spec, M, X, Uref, OBS, nobs, U, omega, sel, status, active, sample=None):
+    ctrl = OracleOptimalDecayCBFQP(spec)
+    N = X.shape[0]
+    idx = range(N) if sample is None else sample
+    n_cmp = n_act = 0
+    for i in idx:
+        k = M if nobs is None else max(int(nobs[i]), 0)
+        if k > 0:
+            d = np.linalg.norm(OBS[i][:k, :2] - X[i][:2], axis=1)
+            j = int(np.argmin(d))
+            assert sel[i] == j, f"agent {i}: sel {sel[i]} vs nearest {j}"
+            obs = OBS[i][j]
+        else:
+            assert sel[i] == -1
+            obs = None
+        u, om, info = ctrl.solve(X[i], Uref[i], obs)
+        assert info["status"] == status[i]
+        if info["status"] != 0:
+            continue
+        assert np.max(np.abs(u - U[i])) <= U_TOL * max(1.0, np.max(np.abs(u))), (i, u, U[i])
+        nw = om.size
+        assert np.max(np.abs(om - omega[i][:nw])) <= U_TOL * max(1.0, np.max(np.abs(om))), (i, om, omega[i])
+        n_act += bool(info["active"][0])
+        if active is not None and info["gap"] > GAP_MIN:
+            n_cmp += 1
+            want = mask_from_bool(info["active"], 1)[0]
+            assert np.uint64(active[i]) == want, f"agent {i}: active {active[i]} vs {want}"
+    return dict(n=len(list(idx)), cbf_active=n_act, masks_compared=n_cmp)
