@@ -1,0 +1,267 @@
+"""Oracle restatement of MPCCBF (TEST INFRASTRUCTURE).
+
+The reference builds this NLP with do-mpc/CasADi and solves it with IPOPT+MUMPS
+(position_control/mpc_cbf.py:108-160 model, 162-259 MPC, 295-325 CBF rows, 366-402 solve);
+do-mpc >= 5.1.1 and casadi are NOT in /root/reference and not installed.
+We restate the NLP exactly as do-mpc's MPC._prepare_nlp formulates it (multiple shooting,
+n_robust = 0, discrete model) and solve it with scipy (SLSQP, cross-checkable with
+trust-constr), derivatives by torch.autograd in float64:
+
+  vars   x_0..x_H, u_0..u_{H-1}
+  min    sum_{k<H} [(x_k-g)'Q(x_k-g) + sum_i R_i (u_k,i - u_{k-1,i})^2] + (x_H-g)'Q(x_H-g)
+         u_{-1} = u_prev  (set_rterm penalises the input RATE, mpc_cbf.py:180)
+         g = [goal, 0...]  (mpc_cbf.py:267)
+  s.t.   x_0 = x_init;  x_{k+1} = x_k + (f(x_k) + g(x_k) u_k) dt        (mpc_cbf.py:135-141)
+         cbf_j(x_k, u_k) >= 0   k < H, j < num_obs                       (mpc_cbf.py:301-325)
+             built from the model's agent_barrier_dt, i.e. the model's OWN step (clip / RK4)
+         u_lb <= u_k <= u_ub;  DU/KB: |x_k[3]| <= v_max                   (mpc_cbf.py:183-221)
+         missing obstacle slots = [1000, 1000, 0, 0, 0, 0, 0]             (mpc_cbf.py:346-364)
+  start  x_k = x_init, u_k = u_prev for all k (set_initial_guess, mpc_cbf.py:368-369)
+
+PARITY UNPINNED for the NLP *assembly* (no do-mpc to run); the component functions it is
+built from (f, g, step, agent_barrier_dt, Q/R/alpha constants) are pinned against the
+reference's own code by tests/test_oracle_pinned.py.
+"""
+import math
+
+import numpy as np
+import torch
+from scipy.optimize import minimize, NonlinearConstraint, Bounds
+
+from .models import resolve_spec
+
+torch.set_default_dtype(torch.float64)
+
+MPC_PARAM = {   # mpc_cbf.py:19-39 (Q diag, R), 49-82 (alpha)
+    "SingleIntegrator2D": dict(Q=[50, 50], R=[5, 5], alpha=0.05),
+    "DynamicUnicycle2D": dict(Q=[50, 50, 0.01, 30], R=[0.5, 0.5], alpha1=0.15, alpha2=0.15),
+    "KinematicBicycle2D": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha1=0.1, alpha2=0.1),
+    "KinematicBicycle2D_C3BF": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha=0.15),
+    "Quad3D": dict(Q=[30, 30, 5, 20, 20, 1, 10, 10, 10, 20, 20, 1], R=[1, 1, 1, 1], alpha=0.15),
+}
+DUMMY = [1000.0, 1000.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+
+
+class TorchModel:
+    """f, g, the model's own step and the discrete barrier h, in torch (batched over stages)."""
+
+    def __init__(self, spec, dt):
+        self.s, self.dt, self.name = spec, dt, spec["model"]
+        self.R = float(spec["radius"])
+        n = self.name
+        self.nx, self.nu = {"SingleIntegrator2D": (2, 2), "Quad3D": (12, 4)}.get(n, (4, 2))
+        if n == "Quad3D":
+            L, nu, gr = spec["L"], spec["nu"], 9.8
+            B2 = torch.tensor([[1, 1, 1, 1], [0, L, 0, -L], [L, 0, -L, 0], [nu, -nu, nu, -nu]], dtype=torch.float64)
+            A = torch.zeros(12, 12)
+            for i in range(6):
+                A[i, 6 + i] = 1
+            A[6, 3] = gr; A[7, 4] = -gr
+            B1 = torch.zeros(12, 4)
+            B1[8, 0] = 1 / spec["mass"]; B1[9, 1] = 1 / spec["Iy"]; B1[10, 2] = 1 / spec["Ix"]; B1[11, 3] = 1 / spec["Iz"]
+            self.A, self.B = A, B1 @ B2
+
+    def rhs(self, x, u):
+        """x_dot = f(x) + g(x) u, rows = stages."""
+        n = self.name
+        if n == "SingleIntegrator2D":
+            return u
+        if n == "Quad3D":
+            return x @ self.A.T + u @ self.B.T
+        th, v = x[:, 2], x[:, 3]
+        c, s = torch.cos(th), torch.sin(th)
+        if n == "DynamicUnicycle2D":
+            return torch.stack([v * c, v * s, u[:, 1], u[:, 0]], dim=1)
+        Lr = self.s["rear_ax_dist"]
+        b = u[:, 1]
+        return torch.stack([v * c - v * s * b, v * s + v * c * b, v / Lr * b, u[:, 0]], dim=1)
+
+    def euler(self, x, u):
+        return x + self.rhs(x, u) * self.dt
+
+    def own_step(self, x, u):
+        """The model's step() as used inside agent_barrier_dt (wrap omitted: the barriers only
+        see the heading through cos/sin, or not at all)."""
+        n = self.name
+        if n == "Quad3D":
+            dt = self.dt
+            k1 = self.rhs(x, u); k2 = self.rhs(x + dt / 2 * k1, u)
+            k3 = self.rhs(x + dt / 2 * k2, u); k4 = self.rhs(x + dt * k3, u)
+            return x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        xn = self.euler(x, u)
+        if n.startswith("KinematicBicycle2D"):
+            v = torch.clamp(xn[:, 3], self.s["v_min"], self.s["v_max"])
+            xn = torch.cat([xn[:, :3], v[:, None]], dim=1)
+        return xn
+
+    def h(self, x, obs):
+        """x [K, nx], obs [M, 7] -> [K, M] barrier values."""
+        n = self.name
+        if n == "KinematicBicycle2D_C3BF":                      # kinematic_bicycle2D_c3bf.py:82-108
+            th, v = x[:, 2:3], x[:, 3:4]
+            ego = (obs[None, :, 2] + self.R) * 1.01
+            px, py = obs[None, :, 0] - x[:, 0:1], obs[None, :, 1] - x[:, 1:2]
+            vx, vy = obs[None, :, 3] - v * torch.cos(th), obs[None, :, 4] - v * torch.sin(th)
+            pm = torch.sqrt(px * px + py * py); vm = torch.sqrt(vx * vx + vy * vy)
+            return (px * vx + py * vy) + pm * vm * torch.sqrt(torch.clamp(pm ** 2 - ego ** 2, min=0.0)) / pm
+        beta = 1.1 if n == "KinematicBicycle2D" else 1.01
+        dx, dy = x[:, 0:1] - obs[None, :, 0], x[:, 1:2] - obs[None, :, 1]
+        circ = dx * dx + dy * dy - beta * (obs[None, :, 2] + self.R) ** 2
+        if n in ("SingleIntegrator2D", "DynamicUnicycle2D") and bool((obs[:, 6] >= 0.5).any()):
+            a = torch.clamp(obs[:, 2].abs(), min=1e-3); b = torch.clamp(obs[:, 3].abs(), min=1e-3)
+            e = torch.clamp(obs[:, 4].abs(), min=2.0)
+            ct, st = torch.cos(obs[:, 5]), torch.sin(obs[:, 5])
+            xp = ct[None] * dx + st[None] * dy; yp = -st[None] * dx + ct[None] * dy
+            sup = (xp.abs() / (a + self.R)[None]) ** e[None] + (yp.abs() / (b + self.R)[None]) ** e[None] - 1
+            return torch.where(obs[None, :, 6] < 0.5, circ, sup)
+        return circ
+
+
+class OracleMPCCBF:
+    def __init__(self, robot_spec, num_obs=5, horizon=None, dt=0.05):
+        self.spec = resolve_spec(robot_spec)
+        self.name = self.spec["model"]
+        self.dt, self.M = dt, num_obs
+        self.H = int(horizon if horizon is not None else self.spec.get("mpc_horizon", 10))
+        par = dict(MPC_PARAM[self.name])
+        for k in ("alpha", "alpha1", "alpha2"):                  # mpc_cbf.py:90-95
+            if "mpc_cbf_" + k in self.spec:
+                par[k] = float(self.spec["mpc_cbf_" + k])
+        self.par = par
+        self.tm = TorchModel(self.spec, dt)
+        self.nx, self.nu = self.tm.nx, self.tm.nu
+        self.Q = torch.tensor(par["Q"], dtype=torch.float64)
+        self.Rw = torch.tensor(par["R"], dtype=torch.float64)
+        s = self.spec
+        if self.name == "SingleIntegrator2D":
+            lb, ub = [-s["v_max"]] * 2, [s["v_max"]] * 2
+        elif self.name == "DynamicUnicycle2D":
+            lb, ub = [-s["a_max"], -s["w_max"]], [s["a_max"], s["w_max"]]
+        elif self.name.startswith("KinematicBicycle2D"):
+            lb, ub = [-s["a_max"], -s["beta_max"]], [s["a_max"], s["beta_max"]]
+        else:
+            lb, ub = [s["u_min"]] * 4, [s["u_max"]] * 4
+        self.u_lb, self.u_ub = np.array(lb, float), np.array(ub, float)
+        self.has_vbound = self.nx == 4
+        self.status = "optimal"
+
+    # ---- packing: w = [x_0..x_H | u_0..u_{H-1}] ----
+    def split(self, w):
+        H, nx, nu = self.H, self.nx, self.nu
+        return w[: (H + 1) * nx].reshape(H + 1, nx), w[(H + 1) * nx:].reshape(H, nu)
+
+    def pad_obs(self, obs):
+        rows = [] if obs is None else [list(np.asarray(o, float).reshape(-1)) for o in obs][: self.M]
+        rows = [r + [0.0] * (7 - len(r)) for r in rows]
+        rows += [DUMMY] * (self.M - len(rows))
+        return torch.tensor(rows, dtype=torch.float64).reshape(self.M, 7)
+
+    def cost(self, w, goal_full, u_prev):
+        x, u = self.split(w)
+        e = x - goal_full[None]
+        du = u - torch.cat([u_prev[None], u[:-1]], dim=0)
+        return (e * e * self.Q[None]).sum() + (du * du * self.Rw[None]).sum()
+
+    def eq(self, w, x0):
+        x, u = self.split(w)
+        return torch.cat([(x[0] - x0), (x[1:] - self.tm.euler(x[:-1], u)).reshape(-1)])
+
+    def cbf(self, w, obs):
+        """[H*M] values of the CBF constraints (>= 0)."""
+        x, u = self.split(w)
+        xk = x[:-1]
+        tm, p = self.tm, self.par
+        x1 = tm.own_step(xk, u)
+        h0, h1 = tm.h(xk, obs), tm.h(x1, obs)
+        if "alpha" in p:                                          # mpc_cbf.py:312-315
+            return ((h1 - h0) + p["alpha"] * h0).reshape(-1)
+        x2 = tm.own_step(x1, u)
+        h2 = tm.h(x2, obs)
+        return ((h2 - 2 * h1 + h0) + (p["alpha1"] + p["alpha2"]) * (h1 - h0) + p["alpha1"] * p["alpha2"] * h0).reshape(-1)
+
+    def solve(self, x_init, goal, u_prev, obs, method="SLSQP", w0=None, tol=1e-10, maxiter=400):
+        """-> u0 (nu,), info dict(w, fun, success, x_pred, u_pred, cbf_min, eq_res)."""
+        H, nx, nu = self.H, self.nx, self.nu
+        x0 = torch.tensor(np.asarray(x_init, float).reshape(-1))
+        up = torch.tensor(np.asarray(u_prev, float).reshape(-1))
+        g = np.zeros(nx); gl = np.asarray(goal, float).reshape(-1); g[: gl.size] = gl
+        gf = torch.tensor(g)
+        ob = self.pad_obs(obs)
+        if w0 is None:
+            w0 = np.concatenate([np.tile(x0.numpy(), H + 1), np.tile(up.numpy(), H)])     # cold start
+
+        def tn(v):
+            return torch.tensor(v, dtype=torch.float64, requires_grad=True)
+
+        def f(v):
+            t = tn(v); c = self.cost(t, gf, up); c.backward()
+            return float(c), t.grad.numpy().copy()
+
+        def jac(fn):
+            def j(v):
+                return torch.autograd.functional.jacobian(fn, torch.tensor(v, dtype=torch.float64), vectorize=True).numpy()
+            return j
+
+        eqf = lambda t: self.eq(t, x0)
+        cbff = lambda t: self.cbf(t, ob)
+        lo = np.full(w0.size, -np.inf); hi = np.full(w0.size, np.inf)
+        xl, ul = self.split(lo); xh, uh = self.split(hi)
+        ul[:] = self.u_lb; uh[:] = self.u_ub
+        if self.has_vbound:
+            xl[:, 3] = -self.spec["v_max"]; xh[:, 3] = self.spec["v_max"]
+        if method == "SLSQP":
+            cons = [dict(type="eq", fun=lambda v: eqf(torch.tensor(v)).numpy(), jac=jac(eqf)),
+                    dict(type="ineq", fun=lambda v: cbff(torch.tensor(v)).numpy(), jac=jac(cbff))]
+            res = minimize(f, w0, jac=True, method="SLSQP", bounds=list(zip(lo, hi)), constraints=cons,
+                           options=dict(ftol=tol, maxiter=maxiter))
+        else:
+            def lag_hess(v, lam_eq, lam_in):
+                return None
+            cons = [NonlinearConstraint(lambda v: eqf(torch.tensor(v)).numpy(), 0.0, 0.0, jac=jac(eqf)),
+                    NonlinearConstraint(lambda v: cbff(torch.tensor(v)).numpy(), 0.0, np.inf, jac=jac(cbff))]
+            res = minimize(f, w0, jac=True, method="trust-constr", bounds=Bounds(lo, hi), constraints=cons,
+                           options=dict(gtol=1e-9, xtol=1e-12, maxiter=3000))
+        w = torch.tensor(res.x)
+        xs, us = self.split(w)
+        info = dict(w=res.x, fun=float(res.fun), success=bool(res.success), nit=int(res.nit),
+                    x_pred=xs.numpy().copy(), u_pred=us.numpy().copy(),
+                    cbf_min=float(self.cbf(w, ob).min()), eq_res=float(self.eq(w, x0).abs().max()))
+        return us[0].numpy().copy(), info
+
+    # ---- condensed (single-shooting) view used to verify KKT points independently of the solver ----
+    def rollout(self, x_init, u_seq):
+        x = [torch.as_tensor(x_init, dtype=torch.float64).reshape(1, -1)]
+        for k in range(self.H):
+            x.append(self.tm.euler(x[-1], u_seq[k:k + 1]))
+        return torch.cat(x, dim=0)
+
+    def condensed(self, x_init, goal, u_prev, obs, z):
+        """z = flattened u sequence (torch, requires_grad ok) -> (J, g_ineq>=0 incl. bounds)."""
+        H, nu = self.H, self.nu
+        u = z.reshape(H, nu)
+        x = self.rollout(x_init, u)
+        g = torch.zeros(self.nx); gl = torch.as_tensor(np.asarray(goal, float).reshape(-1)); g[: gl.numel()] = gl
+        w = torch.cat([x.reshape(-1), u.reshape(-1)])
+        J = self.cost(w, g, torch.as_tensor(np.asarray(u_prev, float).reshape(-1)))
+        parts = [self.cbf(w, self.pad_obs(obs)),
+                 (torch.as_tensor(self.u_ub)[None] - u).reshape(-1), (u - torch.as_tensor(self.u_lb)[None]).reshape(-1)]
+        if self.has_vbound:
+            parts += [self.spec["v_max"] - x[1:, 3], x[1:, 3] + self.spec["v_max"]]
+        return J, torch.cat(parts)
+
+    def kkt_error(self, x_init, goal, u_prev, obs, z, tol_act=1e-6):
+        """Least-squares multiplier estimate on the near-active set -> (stationarity residual, min g)."""
+        zt = torch.tensor(np.asarray(z, float).reshape(-1), requires_grad=True)
+        J, g = self.condensed(x_init, goal, u_prev, obs, zt)
+        gradJ = torch.autograd.grad(J, zt, retain_graph=True)[0].numpy()
+        gv = g.detach().numpy()
+        act = np.nonzero(gv < tol_act * (1 + np.abs(gv).min()) + tol_act)[0]
+        if act.size == 0:
+            return float(np.abs(gradJ).max()), float(gv.min()), act
+        rows = []
+        for i in act:
+            rows.append(torch.autograd.grad(g[i], zt, retain_graph=True)[0].numpy())
+        A = np.stack(rows, axis=1)
+        from scipy.optimize import nnls
+        lam, _ = nnls(A, gradJ)
+        return float(np.abs(gradJ - A @ lam).max()), float(gv.min()), act

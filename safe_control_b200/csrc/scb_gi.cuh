@@ -136,6 +136,9 @@ SCB_HD void gi_solve(const double (&hd)[NV], const double (&x0)[NV],
       }
     }
     G::argmin(bestv, bi);
+#if defined(SCB_GI_TRACE) && !defined(__CUDA_ARCH__)
+    printf("[gi] it=%d k=%d W=(%d,%d) x=(%.6g,%.6g) pick=%d sn=%.3e\n", it, k, Wi[0], NV > 1 ? Wi[1] : -1, x[0], x[1], bi, bestv);
+#endif
     if (bi == kNone) break;                       // primal feasible -> optimal
     if (++it > max_iter) { status = SCB_MAXITER; break; }
 
@@ -204,7 +207,10 @@ SCB_HD void gi_solve(const double (&hd)[NV], const double (&x0)[NV],
         z[i] = d[i] - hinv[i] * v;
         zap = fma(z[i], ap[i], zap);
       }
-      const bool zzero = !(zap > 1e-11 * dap);
+      // z is the H^-1-projection of a_p onto the null space of the working rows: identically 0
+      // once k == NV; otherwise zap/dap = sin^2(angle(a_p, span W)), and below ~1e-9 the
+      // computed value is rounding noise of the k x k solve (cond ~ 1/sin^2) -> treat as dependent.
+      const bool zzero = (k >= NV) || !(zap > 1e-9 * dap);
       double t1 = kInf;
       int l = -1;
 #pragma unroll
@@ -215,6 +221,9 @@ SCB_HD void gi_solve(const double (&hd)[NV], const double (&x0)[NV],
         }
       }
       const double t2 = zzero ? kInf : (-sp / zap);
+#if defined(SCB_GI_TRACE) && !defined(__CUDA_ARCH__)
+      printf("[gi]   k=%d sp=%.6g zap=%.3e dap=%.3e zzero=%d t1=%.6g l=%d t2=%.6g r=(%.3e,%.3e) lam=(%.3e,%.3e)\n", k, sp, zap, dap, (int)zzero, t1, l, t2, r[0], NV > 1 ? r[1] : 0.0, lam[0], NV > 1 ? lam[1] : 0.0);
+#endif
       if (l < 0 && zzero) { status = SCB_INFEASIBLE; done = true; break; }
       if (t2 <= t1) {
         // full step: row bi becomes active

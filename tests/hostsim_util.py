@@ -8,17 +8,34 @@ import numpy as np
 from safe_control_b200 import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_lib = None
+_libs = {}
+_fma = False          # which build hostsim() returns; tests flip it with use_fma()
 
 
-def hostsim():
-    global _lib
-    if _lib is None:
+def use_fma(flag):
+    global _fma
+    _fma = bool(flag)
+
+
+def _has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " fma " in f.read().replace("\n", " ")
+    except OSError:
+        return False
+
+
+def hostsim(fma=None):
+    fma = _fma if fma is None else fma
+    if fma and not _has_fma():
+        fma = False
+    if fma not in _libs:
         spec = importlib.util.spec_from_file_location("hostsim_build", os.path.join(_HERE, "_hostsim", "build.py"))
         mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
-        _lib = C.CDLL(mod.build())
-        _abi.bind(_lib, names=("scb_params_default", "scb_strerror", "scb_model_dims", "scb_active_words", "scb_version"))
-    return _lib
+        lib = C.CDLL(mod.build(fma=fma))
+        _abi.bind(lib, names=("scb_params_default", "scb_strerror", "scb_model_dims", "scb_active_words", "scb_version"))
+        _libs[fma] = lib
+    return _libs[fma]
 
 
 def ptr(a):

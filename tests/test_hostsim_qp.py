@@ -5,6 +5,7 @@ test_gpu_qp.py; this file exists so kernel-math regressions are caught on the CP
 import numpy as np
 import pytest
 
+import hostsim_util
 from hostsim_util import hostsim, hs_cbfqp_rows, hs_cbfqp_solve, hs_odcbf_solve
 from parity_util import check_cbfqp, check_odcbf
 from safe_control_b200.params import resolve_params
@@ -12,6 +13,15 @@ from safe_control_b200 import scenes
 from test_oracle_pinned import _load, _spec_from_tag
 from oracle.models import make_model
 from oracle.controllers import nearest_unpassed_obs as oracle_select
+
+
+@pytest.fixture(autouse=True, params=[False, True], ids=["nofma", "fma"])
+def _fp_variant(request):
+    """Run every check on both CPU builds: without FMA contraction and with it (nvcc contracts,
+    and a rounding-path bug once hid behind that difference)."""
+    hostsim_util.use_fma(request.param)
+    yield
+    hostsim_util.use_fma(False)
 
 
 def test_reference_fixtures_cbfqp():
@@ -47,8 +57,8 @@ def test_reference_fixtures_odcbf():
                                          ("KinematicBicycle2D", True), ("KinematicBicycle2D_C3BF", True),
                                          ("SingleIntegrator2D", True)])
 def test_scene_cbfqp_vs_oracle(model, dense):
-    M, N = 16, 96
-    sc = scenes.make_scene(model, N, M, seed=7, dense=dense)
+    M, N = 16, 160
+    sc = scenes.make_scene(model, N, M, seed=1234, dense=dense)
     p, spec = resolve_params(sc["spec"], "cbf_qp", lib=hostsim())
     U, st, act = hs_cbfqp_solve(p, sc["X"], sc["U_ref"], sc["OBS"], sc["nobs"])
     stats = check_cbfqp(spec, M, sc["X"], sc["U_ref"], sc["OBS"], sc["nobs"], U, st, act)
