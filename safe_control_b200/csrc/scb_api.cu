@@ -3,6 +3,7 @@
 // (only a thread-local copy of the last CUDA error code).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -45,7 +46,7 @@ static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M
     cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
     return SCB_OK;                                                                                         \
   }
-  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 4) GO(8, 8)
+  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 4) GO(8, 8) GO(4, 8)
 #undef GO
   return SCB_ERR_TOO_LARGE;
 }
@@ -62,6 +63,11 @@ static int launch_od_m(const scb_params& p, const LaunchGeom& g, int N, int M, c
   GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 4) GO(8, 8)
 #undef GO
   return SCB_ERR_TOO_LARGE;
+}
+
+static int forced_lanes() {      // tuning override, read per call (no cached state)
+  const char* e = getenv("SCB_QP_LANES");
+  return e ? atoi(e) : 0;
 }
 
 static bool qp_model_ok(int m) {
@@ -114,7 +120,7 @@ int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const do
   if (N == 0) return SCB_OK;
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
   LaunchGeom g;
-  if (!pick_geom(N, M + 2 * p->nu, sm_count_cached(), g)) return SCB_ERR_TOO_LARGE;
+  if (!pick_geom(N, M + 2 * p->nu, sm_count_cached(), g, forced_lanes())) return SCB_ERR_TOO_LARGE;
   const int words = scb_active_words(M, p->nu);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = SCB_ERR_BAD_ARG;

@@ -18,7 +18,9 @@
 #if defined(__CUDACC__)
 #define SCB_HD __host__ __device__ __forceinline__
 #define SCB_D __device__ __forceinline__
+#define SCB_HD_NOINLINE __host__ __device__ __noinline__
 #else
+#define SCB_HD_NOINLINE __attribute__((noinline))
 #define SCB_HD inline
 #define SCB_D inline
 #endif
@@ -110,6 +112,14 @@ SCB_HD void sincos_pair(double th, double& s, double& c) {
 #else
   s = sin(th);
   c = cos(th);
+#endif
+}
+
+SCB_HD double rsqrt_pos(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
 #endif
 }
 

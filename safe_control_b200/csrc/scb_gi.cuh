@@ -283,4 +283,114 @@ SCB_HD void gi_solve(const double (&hd)[NV], const double (&x0)[NV],
   out.iters = it;
 }
 
+// ----------------------------------------------------------------------------------------
+// NV = 2 specialisation (the CBF-QP of every 2-input model): the working set has 0, 1 or 2
+// rows, so each pivot is a closed form -- no generic k x k factorisation, no guarded
+// unrolled loops.  Rows must be PRE-NORMALISED (||a_r|| = 1, or a_r = 0 for a constant
+// row), which makes the slack a signed distance and removes a multiply + a register per
+// row; the multipliers returned are those of the normalised rows (same sign pattern, which
+// is all the active mask needs).  Hessian = hd * I (hd = 2 for ||u - u_ref||^2).
+struct Qp2Out {
+  double x0, x1;
+  double lam0, lam1;
+  int w0, w1;        // working-set row indices (-1 = empty)
+  int status, iters;
+};
+
+template <int LANES, int RPL>
+SCB_HD void gi_solve2(double hd, double x0, double x1, const double (&r0)[RPL], const double (&r1)[RPL],
+                      const double (&rb)[RPL], int mrows, int max_iter, Qp2Out& out) {
+  using G = Grp<LANES>;
+  const int lane = G::lane();
+  constexpr int kNone = 0x7fffffff;
+  const double hinv = 1.0 / hd;
+  // working set
+  double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0, l0 = 0.0, l1 = 0.0;
+  int w0 = -1, w1 = -1, k = 0;
+  int status = SCB_OPTIMAL, it = 0;
+
+  while (true) {
+    // most violated row (signed distance), working rows excluded
+    double bestv = 0.0;
+    int bi = kNone;
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+      const int r = j * LANES + lane;
+      const double sdist = fma(r1[j], x1, fma(r0[j], x0, rb[j]));
+      const double tol = -1e-12 * (1.0 + fabs(rb[j]));
+      if (r < mrows && r != w0 && r != w1 && sdist < tol && sdist < bestv) { bestv = sdist; bi = r; }
+    }
+    G::argmin(bestv, bi);
+    if (bi == kNone) break;
+    if (++it > max_iter) { status = SCB_MAXITER; break; }
+
+    // fetch the row into every lane
+    double p0 = 0.0, p1 = 0.0, pb = 0.0;
+    {
+      const int slot = bi / LANES;
+#pragma unroll
+      for (int j = 0; j < RPL; ++j)
+        if (j == slot) { p0 = r0[j]; p1 = r1[j]; pb = rb[j]; }
+      const int src = bi % LANES;
+      p0 = G::bcast(p0, src); p1 = G::bcast(p1, src); pb = G::bcast(pb, src);
+    }
+    double sp = fma(p1, x1, fma(p0, x0, pb));
+    double lp = 0.0;
+    const double pp = p0 * p0 + p1 * p1;            // 1 for a normalised row, 0 for a constant row
+
+    bool done = false;
+    while (!done) {
+      if (k == 0) {
+        if (!(pp > 0.0)) { status = SCB_INFEASIBLE; break; }       // constant row b < 0
+        const double t = -sp / (hinv * pp);
+        x0 = fma(t * hinv, p0, x0); x1 = fma(t * hinv, p1, x1);
+        a00 = p0; a01 = p1; w0 = bi; l0 = t; k = 1;
+        done = true;
+      } else if (k == 1) {
+        // r = (a0.p)/(a0.a0);  z = hinv (p - a0 r);  z.p = hinv (pp - (a0.p)^2/(a0.a0))
+        const double aa = a00 * a00 + a01 * a01;
+        const double ap = a00 * p0 + a01 * p1;
+        const double r = ap / aa;
+        const double z0 = hinv * fma(-r, a00, p0), z1 = hinv * fma(-r, a01, p1);
+        const double zap = z0 * p0 + z1 * p1;
+        const bool zzero = !(zap > 1e-9 * hinv * pp);
+        const double t1 = (r > 0.0) ? l0 / r : kInf;
+        const double t2 = zzero ? kInf : -sp / zap;
+        if (t1 >= kInf && t2 >= kInf) { status = SCB_INFEASIBLE; break; }
+        if (t2 <= t1) {
+          x0 = fma(t2, z0, x0); x1 = fma(t2, z1, x1);
+          l0 = fmax(l0 - t2 * r, 0.0); lp += t2;
+          a10 = p0; a11 = p1; w1 = bi; l1 = lp; k = 2;
+          done = true;
+        } else {
+          if (!zzero) { x0 = fma(t1, z0, x0); x1 = fma(t1, z1, x1); sp = fma(t1, zap, sp); }
+          lp += t1;
+          w0 = -1; l0 = 0.0; k = 0;
+          if (++it > max_iter) { status = SCB_MAXITER; break; }
+        }
+      } else {
+        // two working rows span the plane: z = 0, solve [a0;a1] hinv [a0;a1]' r = [a0;a1] hinv p
+        const double s00 = a00 * a00 + a01 * a01, s01 = a00 * a10 + a01 * a11, s11 = a10 * a10 + a11 * a11;
+        const double q0 = a00 * p0 + a01 * p1, q1 = a10 * p0 + a11 * p1;
+        const double det = s00 * s11 - s01 * s01;
+        if (!(det > 0.0)) { status = SCB_NUMERICAL; break; }
+        const double ra = (s11 * q0 - s01 * q1) / det, rb2 = (s00 * q1 - s01 * q0) / det;
+        const double ta = (ra > 0.0) ? l0 / ra : kInf, tb = (rb2 > 0.0) ? l1 / rb2 : kInf;
+        if (ta >= kInf && tb >= kInf) { status = SCB_INFEASIBLE; break; }
+        const double t = fmin(ta, tb);
+        lp += t;
+        l0 = fmax(l0 - t * ra, 0.0); l1 = fmax(l1 - t * rb2, 0.0);
+        if (ta <= tb) { a00 = a10; a01 = a11; w0 = w1; l0 = l1; }   // drop row 0: row 1 moves down
+        w1 = -1; l1 = 0.0; k = 1;
+        if (++it > max_iter) { status = SCB_MAXITER; break; }
+      }
+    }
+    if (status != SCB_OPTIMAL) break;
+  }
+  out.x0 = x0; out.x1 = x1;
+  out.lam0 = (k > 0) ? l0 : 0.0; out.lam1 = (k > 1) ? l1 : 0.0;
+  out.w0 = (k > 0) ? w0 : -1; out.w1 = (k > 1) ? w1 : -1;
+  out.status = status; out.iters = it;
+}
+
 }  // namespace scb

@@ -72,16 +72,17 @@ struct LaunchGeom {
   int lanes, rpl, grid;
 };
 
-// total rows -> (LANES, RPL); returns false if beyond the compiled instantiations
-inline bool pick_geom(long N, int rows, int sm_count, LaunchGeom& g) {
+// total rows -> (LANES, RPL); returns false if beyond the compiled instantiations.
+// Compiled: (32,1) (32,2) (32,4) (8,4) (8,8) (4,8).  `force_lanes` (0 = auto) is a tuning override
+// (env SCB_QP_LANES), honoured only when an instantiation exists for it.
+inline bool pick_geom(long N, int rows, int sm_count, LaunchGeom& g, int force_lanes = 0) {
   const bool small = N * 32 <= (long)sm_count * 2048 * 2;   // warp-per-QP still under ~2 waves
-  if (small || rows > 64) {
-    g.lanes = 32;
-    g.rpl = rows <= 32 ? 1 : rows <= 64 ? 2 : rows <= 128 ? 4 : 0;
-  } else {
-    g.lanes = 8;
-    g.rpl = rows <= 32 ? 4 : 8;
-  }
+  int lanes = (small || rows > 64) ? 32 : 8;
+  if (force_lanes == 32 || (force_lanes == 8 && rows <= 64) || (force_lanes == 4 && rows <= 32)) lanes = force_lanes;
+  g.lanes = lanes;
+  if (lanes == 32) g.rpl = rows <= 32 ? 1 : rows <= 64 ? 2 : rows <= 128 ? 4 : 0;
+  else if (lanes == 8) g.rpl = rows <= 32 ? 4 : 8;
+  else g.rpl = 8;
   if (g.rpl == 0) return false;
   const long groups_per_block = kBlock / g.lanes;
   long blocks = (N + groups_per_block - 1) / groups_per_block;

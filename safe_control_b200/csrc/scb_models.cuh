@@ -26,10 +26,6 @@ struct AgentCT {
   double fx, fy;     // f(x)[0:2] = v c, v s
 };
 
-// real power with the reference's numpy semantics for the cases the superellipsoid
-// formula meets (x ** e, e = obs[4]): negative base with integer exponent is fine.
-SCB_HD double rpow(double x, double e) { return pow(x, e); }
-
 struct RowOut {
   double a[4];
   double b;
@@ -37,6 +33,30 @@ struct RowOut {
 
 template <int MODEL>
 struct ModelCT;
+
+// Superellipsoid obstacles (flag == 1) are the rare, pow()-heavy branch: keep them out of line so
+// the unrolled per-lane row loops of the fused kernels carry one call, not RPL inlined copies.
+// h, dh/dx, dh/dy and (optionally) the second derivatives hxx, hxy, hyy at position (px, py).
+// Everything is passed and returned BY VALUE so the callers' obstacle row stays in registers.
+struct SEOut { double h, gx, gy, hxx, hxy, hyy; };
+SCB_HD_NOINLINE SEOut superellipsoid_terms(double px, double py, double ox, double oy, double a, double b, double e,
+                                           double th, double radius) {
+  SEOut r;
+  double st, ct; sincos_pair(th, st, ct);
+  const double xp = ct * (px - ox) + st * (py - oy);
+  const double yp = -st * (px - ox) + ct * (py - oy);
+  const double ar = a + radius, br = b + radius;
+  const double ae = pow(ar, e), be = pow(br, e);
+  r.h = pow(xp / ar, e) + pow(yp / br, e) - 1.0;
+  const double ga = e * pow(xp, e - 1.0), gb = e * pow(yp, e - 1.0);
+  r.gx = ga * (ct / ae) + gb * (-st / be);
+  r.gy = ga * (st / ae) + gb * (ct / be);
+  const double ka = (e * (e - 1.0) / ae) * pow(xp, e - 2.0), kb = (e * (e - 1.0) / be) * pow(yp, e - 2.0);
+  r.hxx = ka * ct * ct + kb * st * st;
+  r.hxy = (ka - kb) * ct * st;
+  r.hyy = ka * st * st + kb * ct * ct;
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------
 template <>
@@ -54,16 +74,8 @@ struct ModelCT<SCB_SINGLE_INTEGRATOR_2D> {
       h = (dx * dx + dy * dy) - 1.01 * (dmin * dmin);
       d0 = 2.0 * dx; d1 = 2.0 * dy;
     } else if (flag == 1.0) {                                 // :128-143
-      const double a = o[2], b = o[3], e = o[4];
-      double st, ct; sincos_pair(o[5], st, ct);
-      const double xp = ct * (g.px - o[0]) + st * (g.py - o[1]);
-      const double yp = -st * (g.px - o[0]) + ct * (g.py - o[1]);
-      const double ar = a + p.radius, br = b + p.radius;
-      h = rpow(xp / ar, e) + rpow(yp / br, e) - 1.0;
-      const double ga = e * rpow(xp, e - 1.0), gb = e * rpow(yp, e - 1.0);
-      const double ae = rpow(ar, e), be = rpow(br, e);
-      d0 = ga * (ct / ae) + gb * (-st / be);
-      d1 = ga * (st / ae) + gb * (ct / be);
+      const SEOut se = superellipsoid_terms(g.px, g.py, o[0], o[1], o[2], o[3], o[4], o[5], p.radius);
+      h = se.h; d0 = se.gx; d1 = se.gy;
     }
     r.a[0] = d0; r.a[1] = d1;                                 // g = I, f = 0
     r.b = (p.cbf_mode == 1) ? h / p.dt : p.alpha * h;
@@ -104,24 +116,13 @@ struct ModelCT<SCB_DYNAMIC_UNICYCLE_2D> {
     if (flag == 0.0) {                                        // dynamic_unicycle2D.py:136-146
       hocbf_circle(g, o, p.radius, 1.01, h, hd, dhd);
     } else if (flag == 1.0) {                                 // :148-183
-      const double a = o[2], b = o[3], e = o[4];
-      double st, ct; sincos_pair(o[5], st, ct);
-      const double xp = ct * (g.px - o[0]) + st * (g.py - o[1]);
-      const double yp = -st * (g.px - o[0]) + ct * (g.py - o[1]);
-      const double ar = a + p.radius, br = b + p.radius;
-      const double ae = rpow(ar, e), be = rpow(br, e);
-      h = rpow(xp / ar, e) + rpow(yp / br, e) - 1.0;
-      const double ga = (e / ae) * rpow(xp, e - 1.0), gb = (e / be) * rpow(yp, e - 1.0);
-      const double ka = (e * (e - 1.0) / ae) * rpow(xp, e - 2.0), kb = (e * (e - 1.0) / be) * rpow(yp, e - 2.0);
-      const double gx = ga * ct - gb * st, gy = ga * st + gb * ct;   // dh/dx, dh/dy
-      hd = gx * g.fx + gy * g.fy;
-      const double hxx = ka * ct * ct + kb * st * st;
-      const double hxy = (ka - kb) * ct * st;
-      const double hyy = ka * st * st + kb * ct * ct;
-      dhd[0] = hxx * g.fx + hxy * g.fy;
-      dhd[1] = hxy * g.fx + hyy * g.fy;
-      dhd[2] = gx * (-g.v * g.s) + gy * (g.v * g.c);
-      dhd[3] = gx * g.c + gy * g.s;
+      const SEOut se = superellipsoid_terms(g.px, g.py, o[0], o[1], o[2], o[3], o[4], o[5], p.radius);
+      h = se.h;
+      hd = se.gx * g.fx + se.gy * g.fy;
+      dhd[0] = se.hxx * g.fx + se.hxy * g.fy;
+      dhd[1] = se.hxy * g.fx + se.hyy * g.fy;
+      dhd[2] = se.gx * (-g.v * g.s) + se.gy * (g.v * g.c);
+      dhd[3] = se.gx * g.c + se.gy * g.s;
     }
   }
   static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {

@@ -74,31 +74,35 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
   AgentCT g;
   Mod::prep(p, xs, g);
 
-  double ra[RPL][NU], rb[RPL];
+  // rows, normalised to unit normals (slack = signed distance in u-space), one per lane slot
+  static_assert(NU == 2, "the fused CBF-QP kernel covers the 2-input models");
+  double r0[RPL], r1[RPL], rb[RPL];
   const int mrows = M + 2 * NU;
 #pragma unroll
-  for (int j = 0; j < RPL; ++j) cbfqp_row<MODEL>(p, g, obs, M, nobs, j * LANES + lane, ra[j], rb[j]);
+  for (int j = 0; j < RPL; ++j) {
+    double a[NU], b;
+    cbfqp_row<MODEL>(p, g, obs, M, nobs, j * LANES + lane, a, b);
+    const double n2 = a[0] * a[0] + a[1] * a[1];
+    const double inv = (n2 > 0.0) ? rsqrt_pos(n2) : 1.0;
+    r0[j] = a[0] * inv; r1[j] = a[1] * inv; rb[j] = b * inv;
+  }
 
-  double hd[NU];
-#pragma unroll
-  for (int i = 0; i < NU; ++i) hd[i] = 2.0;
-  QpOut<NU> q;
-  gi_solve<NU, LANES, RPL>(hd, ur, ra, rb, mrows, 8 * mrows + 16, q);
+  Qp2Out q;
+  gi_solve2<LANES, RPL>(2.0, ur[0], ur[1], r0, r1, rb, mrows, 8 * mrows + 16, q);
 
   if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < NU; ++i) {
-      double v = q.x[i];
-      if (q.status != SCB_OPTIMAL) v = fmin(fmax(v, p.u_lb[i]), p.u_ub[i]);   // never NaN out of the box
-      U[i] = v;
+    double v0 = q.x0, v1 = q.x1;
+    if (q.status != SCB_OPTIMAL) {     // never leave the box / never NaN on failure
+      v0 = fmin(fmax(v0, p.u_lb[0]), p.u_ub[0]);
+      v1 = fmin(fmax(v1, p.u_lb[1]), p.u_ub[1]);
     }
+    U[0] = v0; U[1] = v1;
     *status = q.status;
     if (active) {
       for (int w = 0; w < words; ++w) {
         uint64_t bits = 0ull;
-#pragma unroll
-        for (int a = 0; a < NU; ++a)
-          if (a < q.wk && q.lam[a] > 0.0 && (q.widx[a] >> 6) == w) bits |= 1ull << (q.widx[a] & 63);
+        if (q.w0 >= 0 && q.lam0 > 0.0 && (q.w0 >> 6) == w) bits |= 1ull << (q.w0 & 63);
+        if (q.w1 >= 0 && q.lam1 > 0.0 && (q.w1 >> 6) == w) bits |= 1ull << (q.w1 & 63);
         active[w] = bits;
       }
     }
