@@ -249,13 +249,13 @@ class OracleMPCCBF:
             parts += [self.spec["v_max"] - x[1:, 3], x[1:, 3] + self.spec["v_max"]]
         return J, torch.cat(parts)
 
-    def kkt_error(self, x_init, goal, u_prev, obs, z, tol_act=1e-6):
+    def kkt_error(self, x_init, goal, u_prev, obs, z, tol_act=1e-4):
         """Least-squares multiplier estimate on the near-active set -> (stationarity residual, min g)."""
         zt = torch.tensor(np.asarray(z, float).reshape(-1), requires_grad=True)
         J, g = self.condensed(x_init, goal, u_prev, obs, zt)
         gradJ = torch.autograd.grad(J, zt, retain_graph=True)[0].numpy()
         gv = g.detach().numpy()
-        act = np.nonzero(gv < tol_act * (1 + np.abs(gv).min()) + tol_act)[0]
+        act = np.nonzero(gv < tol_act)[0]
         if act.size == 0:
             return float(np.abs(gradJ).max()), float(gv.min()), act
         rows = []

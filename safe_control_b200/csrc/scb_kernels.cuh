@@ -76,7 +76,9 @@ struct LaunchGeom {
 // Compiled: (32,1) (32,2) (32,4) (8,4) (8,8) (4,8).  `force_lanes` (0 = auto) is a tuning override
 // (env SCB_QP_LANES), honoured only when an instantiation exists for it.
 inline bool pick_geom(long N, int rows, int sm_count, LaunchGeom& g, int force_lanes = 0) {
-  const bool small = N * 32 <= (long)sm_count * 2048 * 2;   // warp-per-QP still under ~2 waves
+  // measured on B200 (tools/sweep_qp.py, M = 16): 32 lanes/QP wins at N = 1024 (5.4 vs 5.8 us), 8 lanes/QP
+  // from N = 8192 up (7.3 vs 12.8 us; 0.55 vs 1.30 ms at N = 1M).  Switch at ~16 warps per SM.
+  const bool small = N <= (long)sm_count * 16;
   int lanes = (small || rows > 64) ? 32 : 8;
   if (force_lanes == 32 || (force_lanes == 8 && rows <= 64) || (force_lanes == 4 && rows <= 32)) lanes = force_lanes;
   g.lanes = lanes;

@@ -1,0 +1,804 @@
+// scb_mpc.cuh -- per-agent body of the MPC-CBF path (device + host-sim).
+//
+// Replaces MPCCBF.solve_control_problem (position_control/mpc_cbf.py:366-402), i.e. the NLP that
+// do-mpc assembles (mpc_cbf.py:108-160, 162-259, 295-325) and IPOPT solves:
+//
+//   min  sum_{k<H} [(x_k-g)'Q(x_k-g) + sum_i R_i (u_k,i - u_{k-1,i})^2] + (x_H-g)'Q(x_H-g)
+//   s.t. x_{k+1} = x_k + (f(x_k) + g(x_k) u_k) dt                      (plain Euler, :135-141)
+//        cbf_j(x_k, u_k) >= 0, k < H, j < num_obs   built from the model's own step()   (:308-325)
+//        u_lb <= u_k <= u_ub,  |x_k[3]| <= v_max                        (:183-221)
+//
+// Method: the states are eliminated by the rollout (single shooting, z = (u_0..u_{H-1})), and the
+// resulting inequality-constrained NLP is solved by a primal-dual interior-point loop with slacks
+// (g(z) - s = 0, s > 0), monotone barrier schedule, fraction-to-the-boundary rule, an l1-merit
+// backtracking line search and diagonal regularisation when the reduced Hessian is not positive
+// definite -- the same family of method as IPOPT, so it converges to a KKT point of the same NLP
+// from the same cold start (x_k = x_init, u_k = u_prev, mpc_cbf.py:368-369).
+//
+// Exact second derivatives, obtained structurally instead of densely:
+//   * per stage, second-order jets (scb_jet.cuh) of the Euler map F and of the barrier points
+//     p1 = step(x,u), p2 = step(step(x,u),u) in the 6 stage variables y = (x, u);
+//   * every circle barrier is  c_j = sum_i w_i |p_i - o_j|^2 - W beta d_j^2, hence its gradient and
+//     Hessian are AFFINE in the obstacle centre:  grad c_j = gE - o_jx gX - o_jy gY,
+//     hess c_j = KE - o_jx KX - o_jy KY, with (gE,KE), (gX,KX), (gY,KY) the jets of
+//     E = sum w_i |p_i|^2, 2 sum w_i p_ix, 2 sum w_i p_iy.  The M obstacle rows of a stage therefore
+//     enter the Newton system only through 12 weighted sums over j;
+//   * the stage Hessians G_k (6x6) are condensed with the state sensitivities S_k = dx_k/dz into the
+//     n x n reduced Hessian (n = H nu <= 32), factored by Cholesky.
+// Work split in a lane group: lanes stride over stages / (stage, obstacle) pairs / matrix columns;
+// all scratch lives in a per-agent workspace (shared memory on the device).
+#pragma once
+
+#include "scb_jet.cuh"
+
+namespace scb {
+
+// double overloads so the stage maps below serve both jets (derivatives) and plain values (line search)
+SCB_HD void jsincos(double& s, double& c, double a) { sincos_pair(a, s, c); }
+SCB_HD void jmul(double& r, double a, double b) { r = a * b; }
+SCB_HD void jaxpy(double& r, double a, double s, double b) { r = a + s * b; }
+SCB_HD void jscale(double& r, double a, double s) { r = s * a; }
+SCB_HD void jclip(double& r, double a, double lo, double hi) { r = a > hi ? hi : (a < lo ? lo : a); }
+
+template <int MODEL>
+struct MpcModel;
+
+// DynamicUnicycle2D: f, g robots/dynamic_unicycle2D.py:42-73, step :75-78, barrier_dt :188-238
+template <>
+struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
+  static constexpr int NX = 4, NU = 2, NY = 6;
+  static constexpr bool VBOUND = true;
+  static SCB_HD double beta() { return 1.01; }
+  // y = (px, py, theta, v, a, omega).  F = Euler map; (P1,Q1), (P2,Q2) = positions after 1 and 2 own steps.
+  template <class T>
+  static SCB_HD void stage(const scb_params& p, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+    T s, c, vc, vs;
+    jsincos(s, c, y[2]);
+    jmul(vc, y[3], c); jmul(vs, y[3], s);
+    jaxpy(F[0], y[0], p.dt, vc);
+    jaxpy(F[1], y[1], p.dt, vs);
+    jaxpy(F[2], y[2], p.dt, y[5]);
+    jaxpy(F[3], y[3], p.dt, y[4]);
+    P1 = F[0]; Q1 = F[1];
+    T s1, c1, v1c, v1s;
+    jsincos(s1, c1, F[2]);
+    jmul(v1c, F[3], c1); jmul(v1s, F[3], s1);
+    jaxpy(P2, P1, p.dt, v1c);
+    jaxpy(Q2, Q1, p.dt, v1s);
+  }
+};
+
+// KinematicBicycle2D: f, g robots/kinematic_bicycle2D.py:75-110, step (clips v) :112-123, barrier_dt :175-199
+template <>
+struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
+  static constexpr int NX = 4, NU = 2, NY = 6;
+  static constexpr bool VBOUND = true;
+  static SCB_HD double beta() { return 1.1; }
+  template <class T>
+  static SCB_HD void euler(const scb_params& p, const T& px, const T& py, const T& th, const T& v, const T& a,
+                           const T& b, T* F) {
+    T s, c, vc, vs, vsb, vcb, t0, t1, vb;
+    jsincos(s, c, th);
+    jmul(vc, v, c); jmul(vs, v, s);
+    jmul(vsb, vs, b); jmul(vcb, vc, b);
+    jaxpy(t0, vc, -1.0, vsb);                 // v c - v s beta
+    jaxpy(t1, vs, 1.0, vcb);                  // v s + v c beta
+    jaxpy(F[0], px, p.dt, t0);
+    jaxpy(F[1], py, p.dt, t1);
+    jmul(vb, v, b);
+    jaxpy(F[2], th, p.dt / p.rear_ax_dist, vb);
+    jaxpy(F[3], v, p.dt, a);
+  }
+  template <class T>
+  static SCB_HD void stage(const scb_params& p, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+    euler(p, y[0], y[1], y[2], y[3], y[4], y[5], F);
+    P1 = F[0]; Q1 = F[1];
+    T v1, G[4];
+    jclip(v1, F[3], p.v_min, p.v_max);        // the model's own step clips v (:116-121)
+    euler(p, P1, Q1, F[2], v1, y[4], y[5], G);
+    P2 = G[0]; Q2 = G[1];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout (in doubles), computed identically on host and device
+struct MpcLayout {
+  int H, M, n, NS;
+  int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, RHS, DZ, SEN,
+      T, HR, LC, DY, ZT, XT, RG;
+  int total;
+};
+
+template <int NX, int NU, bool VBOUND>
+SCB_HD MpcLayout mpc_layout(int H, int M) {
+  constexpr int NY = NX + NU, NH = NY * (NY + 1) / 2;
+  MpcLayout L;
+  L.H = H; L.M = M; L.n = H * NU; L.NS = 2 * H * NU + (VBOUND ? 2 * H : 0);
+  int o = 0;
+  auto take = [&](int cnt) { int r = o; o += cnt; return r; };
+  L.X = take((H + 1) * NX);  L.Z = take(H * NU);
+  L.A = take(H * NX * NX);   L.B = take(H * NX * NU);
+  L.FH = take(H * NX * NH);
+  L.JE = take(H * (NY + NH)); L.JX = take(H * (NY + NH)); L.JY = take(H * (NY + NH));
+  L.PT = take(H * 6);        L.OB = take(M * 3);
+  L.C = take(H * M); L.S = take(H * M); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
+  L.SS = take(L.NS); L.SL = take(L.NS); L.SDS = take(L.NS); L.SDL = take(L.NS);
+  L.SUM = take(H * 12);
+  L.G = take((H + 1) * NH);  L.GAM = take((H + 1) * NY);
+  L.MU = take((H + 1) * NX);
+  L.RD = take(L.n); L.RHS = take(L.n); L.DZ = take(L.n);
+  L.SEN = take((H + 1) * NX * L.n);
+  L.T = take(NY * L.n);
+  L.HR = take(L.n * L.n); L.LC = take(L.n * L.n);
+  L.DY = take((H + 1) * NY);
+  L.ZT = take(L.n); L.XT = take((H + 1) * NX); L.RG = take(L.n);
+  L.total = o;
+  return L;
+}
+
+// simple (bound) constraint q:  g_q = sgn * y_k[var] + off >= 0
+struct SimpleCon { int k, var; double sgn, off; };
+template <int NX, int NU>
+SCB_HD SimpleCon decode_simple(const scb_params& p, int H, int q) {
+  SimpleCon c;
+  if (q < 2 * H * NU) {
+    c.k = q / (2 * NU);
+    const int r = q - c.k * 2 * NU, i = r >> 1;
+    c.var = NX + i;
+    if (r & 1) { c.sgn = 1.0; c.off = -p.u_lb[i]; } else { c.sgn = -1.0; c.off = p.u_ub[i]; }
+  } else {
+    const int t = q - 2 * H * NU;
+    c.k = 1 + (t >> 1); c.var = 3;
+    if (t & 1) { c.sgn = 1.0; c.off = p.v_max; } else { c.sgn = -1.0; c.off = p.v_max; }
+  }
+  return c;
+}
+
+template <int MODEL, int LANES>
+struct MpcSolver {
+  using Mod = MpcModel<MODEL>;
+  using G = Grp<LANES>;
+  static constexpr int NX = Mod::NX, NU = Mod::NU, NY = Mod::NY, NH = NY * (NY + 1) / 2;
+  using J = Jet<NY>;
+
+  const scb_params& p;
+  const MpcLayout& L;
+  double* w;
+  int H, M, n, lane;
+  double w0, w1, w2, Wsum;      // c_j = w0 h(p0) + w1 h(p1) + w2 h(p2),  h = |p - o|^2 - beta d^2
+  double goal[NX];
+  double uprev[NU];
+
+  SCB_HD MpcSolver(const scb_params& p_, const MpcLayout& L_, double* w_) : p(p_), L(L_), w(w_) {
+    H = L.H; M = L.M; n = L.n; lane = G::lane();
+    const double g1 = p.alpha1 + p.alpha2, g2 = p.alpha1 * p.alpha2;
+    w2 = 1.0; w1 = g1 - 2.0; w0 = 1.0 - g1 + g2; Wsum = g2;    // dd_h + (a1+a2) d_h + a1 a2 h_k  (mpc_cbf.py:320-321)
+  }
+
+  static SCB_HD void sync() {
+#if defined(__CUDA_ARCH__)
+    if (LANES > 1) __syncwarp(G::gmask());
+#endif
+  }
+
+  // ---- rollout + cost at the control sequence `z` (lane 0), states -> xs ----
+  SCB_HD double rollout(const double* z, double* xs) const {
+    double Jc = 0.0;
+    double x[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xs[i];
+    for (int k = 0; k < H; ++k) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { const double e = x[i] - goal[i]; Jc = fma(p.Q[i] * e, e, Jc); }
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        const double d = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]);
+        Jc = fma(p.R[i] * d, d, Jc);
+      }
+      double y[NY], F[NX], a, b, c, d;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) y[i] = x[i];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
+      Mod::stage(p, y, F, a, b, c, d);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { x[i] = F[i]; xs[(k + 1) * NX + i] = F[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { const double e = x[i] - goal[i]; Jc = fma(p.Q[i] * e, e, Jc); }
+    return Jc;
+  }
+
+  // barrier points of every stage at (xs, z) -> w[L.PT]; CBF values -> dst[H*M]
+  SCB_HD void points_and_cbf(const double* z, const double* xs, double* dst) const {
+    for (int k = lane; k < H; k += LANES) {
+      double y[NY], F[NX], P1, Q1, P2, Q2;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
+      Mod::stage(p, y, F, P1, Q1, P2, Q2);
+      double* pt = w + L.PT + k * 6;
+      pt[0] = y[0]; pt[1] = y[1]; pt[2] = P1; pt[3] = Q1; pt[4] = P2; pt[5] = Q2;
+    }
+    sync();
+    for (int t = lane; t < H * M; t += LANES) {
+      const int k = t / M, j = t - k * M;
+      const double* pt = w + L.PT + k * 6;
+      const double* ob = w + L.OB + j * 3;
+      double v = -Wsum * ob[2];
+      double dx = pt[0] - ob[0], dy = pt[1] - ob[1];
+      v = fma(w0, dx * dx + dy * dy, v);
+      dx = pt[2] - ob[0]; dy = pt[3] - ob[1];
+      v = fma(w1, dx * dx + dy * dy, v);
+      dx = pt[4] - ob[0]; dy = pt[5] - ob[1];
+      v = fma(w2, dx * dx + dy * dy, v);
+      dst[t] = v;
+    }
+    sync();
+  }
+
+  SCB_HD double simple_value(const SimpleCon& c, const double* z, const double* xs) const {
+    const double yv = (c.var < NX) ? xs[c.k * NX + c.var] : z[c.k * NU + (c.var - NX)];
+    return fma(c.sgn, yv, c.off);
+  }
+
+  // ---- exact stage derivatives at the current iterate (lanes over stages) ----
+  SCB_HD void stage_derivatives() {
+    const double* xs = w + L.X;
+    const double* z = w + L.Z;
+    for (int k = lane; k < H; k += LANES) {
+      J y[NY], F[NX], P1, Q1, P2, Q2;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) jvar(y[i], xs[k * NX + i], i);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) jvar(y[NX + i], z[k * NU + i], NX + i);
+      Mod::stage(p, y, F, P1, Q1, P2, Q2);
+      double* A = w + L.A + k * NX * NX;
+      double* B = w + L.B + k * NX * NU;
+      double* FH = w + L.FH + k * NX * NH;
+#pragma unroll
+      for (int c = 0; c < NX; ++c) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) A[c * NX + i] = F[c].g[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) B[c * NU + i] = F[c].g[NX + i];
+#pragma unroll
+        for (int t = 0; t < NH; ++t) FH[c * NH + t] = F[c].h[t];
+      }
+      // E = sum_i w_i (P_i^2 + Q_i^2),  PX = 2 sum w_i P_i,  PY = 2 sum w_i Q_i
+      J E, PX, PY, t;
+      jmul(E, y[0], y[0]); jmul(t, y[1], y[1]); jaxpy(E, E, 1.0, t); jscale(E, E, w0);
+      jmul(t, P1, P1); jaxpy(E, E, w1, t); jmul(t, Q1, Q1); jaxpy(E, E, w1, t);
+      jmul(t, P2, P2); jaxpy(E, E, w2, t); jmul(t, Q2, Q2); jaxpy(E, E, w2, t);
+      jscale(PX, y[0], 2.0 * w0); jaxpy(PX, PX, 2.0 * w1, P1); jaxpy(PX, PX, 2.0 * w2, P2);
+      jscale(PY, y[1], 2.0 * w0); jaxpy(PY, PY, 2.0 * w1, Q1); jaxpy(PY, PY, 2.0 * w2, Q2);
+      double* je = w + L.JE + k * (NY + NH);
+      double* jx = w + L.JX + k * (NY + NH);
+      double* jy = w + L.JY + k * (NY + NH);
+#pragma unroll
+      for (int i = 0; i < NY; ++i) { je[i] = E.g[i]; jx[i] = PX.g[i]; jy[i] = PY.g[i]; }
+#pragma unroll
+      for (int i = 0; i < NH; ++i) { je[NY + i] = E.h[i]; jx[NY + i] = PX.h[i]; jy[NY + i] = PY.h[i]; }
+    }
+    sync();
+  }
+
+  // gradient of the input-rate term sum R (u_k - u_{k-1})^2 at z -> out[n]
+  SCB_HD void rate_gradient(const double* z, double* out) const {
+    for (int t = lane; t < n; t += LANES) {
+      const int k = t / NU, i = t - k * NU;
+      const double um = (k == 0) ? uprev[i] : z[(k - 1) * NU + i];
+      double g = 2.0 * p.R[i] * (z[t] - um);
+      if (k + 1 < H) g -= 2.0 * p.R[i] * (z[(k + 1) * NU + i] - z[t]);
+      out[t] = g;
+    }
+    sync();
+  }
+
+  // adjoint sweep: stage gradients gam[(H+1)*NY] -> z-gradient out[n]; costates -> w[L.MU] (lane 0)
+  SCB_HD void adjoint(const double* gam, double* out) {
+    if (lane == 0) {
+      double mu[NX];
+      double* MU = w + L.MU;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { mu[i] = gam[H * NY + i]; MU[H * NX + i] = mu[i]; }
+      for (int k = H - 1; k >= 0; --k) {
+        const double* A = w + L.A + k * NX * NX;
+        const double* B = w + L.B + k * NX * NU;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = gam[k * NY + NX + i];
+#pragma unroll
+          for (int c = 0; c < NX; ++c) v = fma(B[c * NU + i], mu[c], v);
+          out[k * NU + i] = v;
+        }
+        double m2[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = gam[k * NY + i];
+#pragma unroll
+          for (int c = 0; c < NX; ++c) v = fma(A[c * NX + i], mu[c], v);
+          m2[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { mu[i] = m2[i]; MU[k * NX + i] = m2[i]; }
+      }
+    }
+    sync();
+  }
+
+  // weighted obstacle sums of stage k: which = 0 (sigma moments, 6) / 1 (lambda, 3) / 2 (rhs weights, 3)
+  SCB_HD void stage_sums(double mu_bar, bool with_rhs) {
+    const int per = 12;
+    for (int t = lane; t < H * per; t += LANES) {
+      const int k = t / per, q = t - k * per;
+      if (q >= 9 && !with_rhs) continue;
+      const double* s = w + L.S + k * M;
+      const double* lam = w + L.L + k * M;
+      const double* c = w + L.C + k * M;
+      double acc = 0.0;
+      for (int j = 0; j < M; ++j) {
+        const double* ob = w + L.OB + j * 3;
+        double wt;
+        if (q < 6) wt = lam[j] / s[j];
+        else if (q < 9) wt = lam[j];
+        else wt = mu_bar / s[j] - (lam[j] / s[j]) * (c[j] - s[j]);
+        double f;
+        switch (q) {
+          case 0: case 6: case 9: f = 1.0; break;
+          case 1: case 7: case 10: f = ob[0]; break;
+          case 2: case 8: case 11: f = ob[1]; break;
+          case 3: f = ob[0] * ob[0]; break;
+          case 4: f = ob[0] * ob[1]; break;
+          default: f = ob[1] * ob[1]; break;
+        }
+        acc = fma(wt, f, acc);
+      }
+      w[L.SUM + t] = acc;
+    }
+    sync();
+  }
+
+  // stage gradient for the dual residual / costates:  gam = grad l_k - sum lam grad g
+  // (sign = +1)  or for the Newton rhs:  gam = -grad l_k + sum wt grad g   (sign = -1, weights 9..11)
+  SCB_HD void stage_gradients(bool rhs, double mu_bar) {
+    double* gam = w + L.GAM;
+    const double* xs = w + L.X;
+    for (int t = lane; t < (H + 1) * NY; t += LANES) {
+      const int k = t / NY, i = t - k * NY;
+      double v = 0.0;
+      if (i < NX) v = 2.0 * p.Q[i] * (xs[k * NX + i] - goal[i]);
+      if (rhs) v = -v;
+      if (k < H) {
+        const double* sm = w + L.SUM + k * 12 + (rhs ? 9 : 6);
+        const double ge = w[L.JE + k * (NY + NH) + i], gx = w[L.JX + k * (NY + NH) + i], gy = w[L.JY + k * (NY + NH) + i];
+        const double cg = sm[0] * ge - sm[1] * gx - sm[2] * gy;      // sum_j wt_j grad c_j
+        v += rhs ? cg : -cg;
+      }
+      gam[t] = v;
+    }
+    sync();
+    // simple bounds
+    for (int q = lane; q < L.NS; q += LANES) {
+      const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+      const double s = w[L.SS + q], lam = w[L.SL + q];
+      double wt;
+      if (rhs) {
+        const double g = simple_value(c, w + L.Z, w + L.X);
+        wt = mu_bar / s - (lam / s) * (g - s);
+      } else {
+        wt = -lam;
+      }
+      // distinct q may hit the same entry (upper/lower of one variable): serialise per group
+      atomic_add_ws(gam + c.k * NY + c.var, wt * c.sgn);
+    }
+    sync();
+  }
+
+  static SCB_HD void atomic_add_ws(double* addr, double v) {
+#if defined(__CUDA_ARCH__)
+    if (LANES > 1) atomicAdd(addr, v); else *addr += v;
+#else
+    *addr += v;
+#endif
+  }
+
+  // stage Hessians G_k = hess l_k - sum lam hess c + sum sigma grad c grad c' + bound sigmas + costate curvature
+  SCB_HD void stage_hessians() {
+    double* Gm = w + L.G;
+    for (int t = lane; t < (H + 1) * NH; t += LANES) {
+      const int k = t / NH, e = t - k * NH;
+      // unpack (i, j) of packed entry e
+      int i = 0, rem = e;
+      while (rem >= NY - i) { rem -= NY - i; ++i; }
+      const int j = i + rem;
+      double v = 0.0;
+      if (i == j && i < NX) v = 2.0 * p.Q[i];
+      if (k < H) {
+        const double* sm = w + L.SUM + k * 12;
+        const double* je = w + L.JE + k * (NY + NH);
+        const double* jx = w + L.JX + k * (NY + NH);
+        const double* jy = w + L.JY + k * (NY + NH);
+        // - sum_j lam_j hess c_j
+        v -= sm[6] * je[NY + e] - sm[7] * jx[NY + e] - sm[8] * jy[NY + e];
+        // + sum_j sigma_j grad c_j grad c_j'
+        const double ei = je[i], ej = je[j], xi = jx[i], xj = jx[j], yi = jy[i], yj = jy[j];
+        v += sm[0] * ei * ej - sm[1] * (ei * xj + xi * ej) - sm[2] * (ei * yj + yi * ej) + sm[3] * xi * xj +
+             sm[4] * (xi * yj + yi * xj) + sm[5] * yi * yj;
+        // + sum_c mu_{k+1,c} hess F_c
+        const double* FH = w + L.FH + k * NX * NH;
+        const double* mu = w + L.MU + (k + 1) * NX;
+#pragma unroll
+        for (int c = 0; c < NX; ++c) v = fma(mu[c], FH[c * NH + e], v);
+      }
+      Gm[t] = v;
+    }
+    sync();
+    for (int q = lane; q < L.NS; q += LANES) {
+      const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+      atomic_add_ws(Gm + c.k * NH + hidx<NY>(c.var, c.var), w[L.SL + q] / w[L.SS + q]);
+    }
+    sync();
+  }
+
+  // state sensitivities S_k = dx_k / dz  (NX x n), lanes over columns
+  SCB_HD void sensitivities() {
+    double* S = w + L.SEN;
+    for (int c = lane; c < n; c += LANES) {
+      double col[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { col[i] = 0.0; S[i * n + c] = 0.0; }
+      const int kc = c / NU, ic = c - kc * NU;
+      for (int k = 0; k < H; ++k) {
+        double nc[NX];
+        if (k < kc) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) nc[i] = 0.0;
+        } else if (k == kc) {
+          const double* B = w + L.B + k * NX * NU;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) nc[i] = B[i * NU + ic];
+        } else {
+          const double* A = w + L.A + k * NX * NX;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < NX; ++a) v = fma(A[i * NX + a], col[a], v);
+            nc[i] = v;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { col[i] = nc[i]; S[((k + 1) * NX + i) * n + c] = nc[i]; }
+      }
+    }
+    sync();
+  }
+
+  // entry (a, c) of the stage-variable sensitivity  d y_k / d z  (NY x n)
+  SCB_HD double sy(int k, int a, int c) const {
+    if (a < NX) return w[L.SEN + (k * NX + a) * n + c];
+    return (k < H && c == k * NU + (a - NX)) ? 1.0 : 0.0;
+  }
+
+  // reduced Hessian  Hr = H_R + sum_k Sy_k' G_k Sy_k   (lower triangle filled, then mirrored)
+  SCB_HD void reduced_hessian() {
+    double* Hr = w + L.HR;
+    double* T = w + L.T;
+    for (int t = lane; t < n * n; t += LANES) Hr[t] = 0.0;
+    sync();
+    for (int t = lane; t < n; t += LANES) {
+      const int k = t / NU, i = t - k * NU;
+      Hr[t * n + t] = (k + 1 < H) ? 4.0 * p.R[i] : 2.0 * p.R[i];
+      if (k + 1 < H) { Hr[(t + NU) * n + t] = -2.0 * p.R[i]; }
+    }
+    sync();
+    for (int k = 0; k <= H; ++k) {
+      const double* Gk = w + L.G + k * NH;
+      const int ncol = (k < H) ? (k + 1) * NU : n;       // columns of Sy_k that can be non-zero
+      const int ny = (k < H) ? NY : NX;
+      // T = G_k Sy_k   (ny x ncol), lanes over columns
+      for (int c = lane; c < ncol; c += LANES) {
+        double sc[NY];
+#pragma unroll
+        for (int a = 0; a < NY; ++a) sc[a] = (a < ny) ? sy(k, a, c) : 0.0;
+#pragma unroll
+        for (int a = 0; a < NY; ++a) {
+          double v = 0.0;
+#pragma unroll
+          for (int b = 0; b < NY; ++b) {
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            v = fma(Gk[hidx<NY>(lo, hi)], sc[b], v);
+          }
+          T[a * n + c] = (a < ny) ? v : 0.0;
+        }
+      }
+      sync();
+      // Hr[r][c] += Sy_k[:, r] . T[:, c]  for r >= c, lanes over (r, c)
+      for (int t = lane; t < ncol * ncol; t += LANES) {
+        const int r = t / ncol, c = t - r * ncol;
+        if (r < c) continue;
+        double v = 0.0;
+#pragma unroll
+        for (int a = 0; a < NY; ++a)
+          if (a < ny) v = fma(sy(k, a, r), T[a * n + c], v);
+        Hr[r * n + c] += v;
+      }
+      sync();
+    }
+  }
+
+  // Cholesky of (Hr + delta I) into LC (lower); returns false on a non-positive pivot
+  SCB_HD bool cholesky(double delta) {
+    const double* Hr = w + L.HR;
+    double* Lc = w + L.LC;
+    bool ok = true;
+    for (int j = 0; j < n; ++j) {
+      // diagonal (every lane computes it redundantly)
+      double d = Hr[j * n + j] + delta;
+      for (int t = 0; t < j; ++t) d -= Lc[j * n + t] * Lc[j * n + t];
+      if (!(d > 1e-300) || !(d < 1e300)) { ok = false; break; }
+      const double dj = sqrt(d), inv = 1.0 / dj;
+      sync();
+      if (lane == 0) Lc[j * n + j] = dj;
+      for (int i = j + 1 + lane; i < n; i += LANES) {
+        double v = Hr[i * n + j];
+        for (int t = 0; t < j; ++t) v -= Lc[i * n + t] * Lc[j * n + t];
+        Lc[i * n + j] = v * inv;
+      }
+      sync();
+    }
+    sync();
+    return ok;
+  }
+
+  // solve Lc Lc' dz = rhs  (lane 0; n <= 32)
+  SCB_HD void chol_solve(const double* rhs, double* dz) {
+    if (lane == 0) {
+      const double* Lc = w + L.LC;
+      for (int i = 0; i < n; ++i) {
+        double v = rhs[i];
+        for (int t = 0; t < i; ++t) v -= Lc[i * n + t] * dz[t];
+        dz[i] = v / Lc[i * n + i];
+      }
+      for (int i = n - 1; i >= 0; --i) {
+        double v = dz[i];
+        for (int t = i + 1; t < n; ++t) v -= Lc[t * n + i] * dz[t];
+        dz[i] = v / Lc[i * n + i];
+      }
+    }
+    sync();
+  }
+
+  // ------------------------------------------------------------------------------------------
+  SCB_HD void solve(int nobs, const double* x0, const double* goal_in, int ngoal, const double* up, const double* obs,
+                    double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) goal[i] = (i < ngoal) ? ld(goal_in + i) : 0.0;      // goal padded with zeros (mpc_cbf.py:267)
+#pragma unroll
+    for (int i = 0; i < NU; ++i) uprev[i] = ld(up + i);
+    const double beta = Mod::beta();
+    // obstacles: (ox, oy, beta d^2); missing slots = the reference's dummy [1000, 1000, 0, ...] (mpc_cbf.py:346-364)
+    for (int j = lane; j < M; j += LANES) {
+      double ox = 1000.0, oy = 1000.0, r = 0.0;
+      if (j < nobs) { ox = ld(obs + j * 7); oy = ld(obs + j * 7 + 1); r = ld(obs + j * 7 + 2); }
+      const double d = r + p.radius;
+      w[L.OB + j * 3] = ox; w[L.OB + j * 3 + 1] = oy; w[L.OB + j * 3 + 2] = beta * d * d;
+    }
+    // cold start: u_k = u_prev (mpc_cbf.py:368-369)
+    for (int t = lane; t < n; t += LANES) w[L.Z + t] = uprev[t % NU];
+    for (int i = lane; i < NX; i += LANES) { w[L.X + i] = ld(x0 + i); w[L.XT + i] = w[L.X + i]; }
+    sync();
+    double Jcur = 0.0;
+    if (lane == 0) Jcur = rollout(w + L.Z, w + L.X);
+    Jcur = G::bcast(Jcur, 0);
+    sync();
+    points_and_cbf(w + L.Z, w + L.X, w + L.C);
+
+    double mu_bar = 0.1;
+    const double tol = p.mpc_tol, s_min = 1e-2;
+    for (int t = lane; t < H * M; t += LANES) {
+      const double s = fmax(w[L.C + t], s_min);
+      w[L.S + t] = s; w[L.L + t] = mu_bar / s;
+    }
+    for (int q = lane; q < L.NS; q += LANES) {
+      const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+      const double s = fmax(simple_value(c, w + L.Z, w + L.X), s_min);
+      w[L.SS + q] = s; w[L.SL + q] = mu_bar / s;
+    }
+    sync();
+
+    int it = 0, st = SCB_MAXITER;
+    double err = kInf;
+    const int max_iter = p.mpc_max_iter > 0 ? p.mpc_max_iter : 200;
+    for (; it < max_iter; ++it) {
+      stage_derivatives();
+      stage_sums(mu_bar, false);
+      stage_gradients(false, mu_bar);
+      adjoint(w + L.GAM, w + L.RD);                 // costates + d/dz of (J_stage - lam' g)
+      rate_gradient(w + L.Z, w + L.RG);
+      // residuals
+      double e_d = 0.0, e_p = 0.0, e_c = 0.0, e_cm = 0.0, lam_max = 0.0;
+      for (int t = lane; t < n; t += LANES) e_d = fmax(e_d, fabs(w[L.RD + t] + w[L.RG + t]));
+      for (int t = lane; t < H * M; t += LANES) {
+        const double s = w[L.S + t], lam = w[L.L + t];
+        e_p = fmax(e_p, fabs(w[L.C + t] - s)); e_c = fmax(e_c, s * lam); e_cm = fmax(e_cm, fabs(s * lam - mu_bar));
+        lam_max = fmax(lam_max, lam);
+      }
+      for (int q = lane; q < L.NS; q += LANES) {
+        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        const double s = w[L.SS + q], lam = w[L.SL + q];
+        e_p = fmax(e_p, fabs(simple_value(c, w + L.Z, w + L.X) - s)); e_c = fmax(e_c, s * lam);
+        e_cm = fmax(e_cm, fabs(s * lam - mu_bar)); lam_max = fmax(lam_max, lam);
+      }
+      e_d = -G::vmin(-e_d); e_p = -G::vmin(-e_p); e_c = -G::vmin(-e_c); e_cm = -G::vmin(-e_cm);
+      lam_max = -G::vmin(-lam_max);
+      err = fmax(e_d, fmax(e_p, e_c));
+      if (!(err == err)) { st = SCB_NUMERICAL; break; }
+      if (err <= tol) { st = SCB_OPTIMAL; break; }
+      // monotone barrier update (Fiacco-McCormick with IPOPT's kappa_mu = 0.2, theta_mu = 1.5, kappa_eps = 10)
+      while (fmax(e_d, fmax(e_p, e_cm)) <= 10.0 * mu_bar && mu_bar > tol / 10.0) {
+        mu_bar = fmax(tol / 10.0, fmin(0.2 * mu_bar, mu_bar * sqrt(mu_bar)));
+        e_cm = 0.0;
+        for (int t = lane; t < H * M; t += LANES) e_cm = fmax(e_cm, fabs(w[L.S + t] * w[L.L + t] - mu_bar));
+        for (int q = lane; q < L.NS; q += LANES) e_cm = fmax(e_cm, fabs(w[L.SS + q] * w[L.SL + q] - mu_bar));
+        e_cm = -G::vmin(-e_cm);
+      }
+      // Newton system
+      stage_hessians();
+      stage_sums(mu_bar, true);
+      stage_gradients(true, mu_bar);
+      {
+        // keep the costates of the first sweep: the rhs sweep must not overwrite them before use -> done (G built)
+        adjoint(w + L.GAM, w + L.RHS);
+        for (int t = lane; t < n; t += LANES) w[L.RHS + t] -= w[L.RG + t];
+        sync();
+      }
+      sensitivities();
+      reduced_hessian();
+      double delta = 0.0;
+      int tries = 0;
+      while (!cholesky(delta)) {
+        delta = (delta == 0.0) ? 1e-4 : delta * 10.0;
+        if (++tries > 24) break;
+      }
+      if (tries > 24) { st = SCB_NUMERICAL; break; }
+      chol_solve(w + L.RHS, w + L.DZ);
+      // stage directions dy_k = Sy_k dz
+      for (int t = lane; t < (H + 1) * NY; t += LANES) {
+        const int k = t / NY, a = t - k * NY;
+        double v = 0.0;
+        if (k < H || a < NX) {
+          const int ncol = (k < H) ? (k + 1) * NU : n;
+          for (int c = 0; c < ncol; ++c) v = fma(sy(k, a, c), w[L.DZ + c], v);
+        }
+        w[L.DY + t] = v;
+      }
+      sync();
+      // slack / multiplier directions, fraction to the boundary
+      const double tau = fmax(0.99, 1.0 - mu_bar);
+      double ap = 1.0, ad = 1.0, dphi_c = 0.0, rp1 = 0.0;
+      for (int t = lane; t < H * M; t += LANES) {
+        const int k = t / M, j = t - k * M;
+        const double* ob = w + L.OB + j * 3;
+        const double* dy = w + L.DY + k * NY;
+        double dg = 0.0;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) {
+          const double gi = w[L.JE + k * (NY + NH) + i] - ob[0] * w[L.JX + k * (NY + NH) + i] - ob[1] * w[L.JY + k * (NY + NH) + i];
+          dg = fma(gi, dy[i], dg);
+        }
+        const double s = w[L.S + t], lam = w[L.L + t], rp = w[L.C + t] - s;
+        const double ds = dg + rp, dl = -((s * lam - mu_bar) + lam * ds) / s;
+        w[L.DS + t] = ds; w[L.DL + t] = dl;
+        if (ds < 0.0) ap = fmin(ap, -tau * s / ds);
+        if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
+        dphi_c -= mu_bar * ds / s; rp1 += fabs(rp);
+      }
+      for (int q = lane; q < L.NS; q += LANES) {
+        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        const double dg = c.sgn * w[L.DY + c.k * NY + c.var];
+        const double s = w[L.SS + q], lam = w[L.SL + q], rp = simple_value(c, w + L.Z, w + L.X) - s;
+        const double ds = dg + rp, dl = -((s * lam - mu_bar) + lam * ds) / s;
+        w[L.SDS + q] = ds; w[L.SDL + q] = dl;
+        if (ds < 0.0) ap = fmin(ap, -tau * s / ds);
+        if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
+        dphi_c -= mu_bar * ds / s; rp1 += fabs(rp);
+      }
+      ap = G::vmin(ap); ad = G::vmin(ad);
+      dphi_c = G::sum(dphi_c); rp1 = G::sum(rp1);
+      // directional derivative of the cost: grad J . dz = sum_k grad l_k . dy_k + rate_grad . dz
+      double dJ = 0.0;
+      for (int t = lane; t < (H + 1) * NX; t += LANES) {
+        const int k = t / NX, i = t - k * NX;
+        dJ = fma(2.0 * p.Q[i] * (w[L.X + t] - goal[i]), w[L.DY + k * NY + i], dJ);
+      }
+      for (int t = lane; t < n; t += LANES) dJ = fma(w[L.RG + t], w[L.DZ + t], dJ);
+      dJ = G::sum(dJ);
+      const double nu_pen = fmax(1.0, 1.1 * lam_max);
+      const double dphi = dJ + dphi_c - nu_pen * rp1;
+      // merit at alpha = 0
+      double phi0 = 0.0;
+      for (int t = lane; t < H * M; t += LANES) phi0 += -mu_bar * log(w[L.S + t]) + nu_pen * fabs(w[L.C + t] - w[L.S + t]);
+      for (int q = lane; q < L.NS; q += LANES) {
+        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        phi0 += -mu_bar * log(w[L.SS + q]) + nu_pen * fabs(simple_value(c, w + L.Z, w + L.X) - w[L.SS + q]);
+      }
+      phi0 = G::sum(phi0) + Jcur;
+      // backtracking
+      double alpha = ap, Jt = Jcur;
+      for (int bt = 0; bt < 14; ++bt) {
+        for (int t = lane; t < n; t += LANES) w[L.ZT + t] = fma(alpha, w[L.DZ + t], w[L.Z + t]);
+        sync();
+        if (lane == 0) Jt = rollout(w + L.ZT, w + L.XT);
+        Jt = G::bcast(Jt, 0);
+        sync();
+        points_and_cbf(w + L.ZT, w + L.XT, w + L.CT);
+        double phi = 0.0;
+        for (int t = lane; t < H * M; t += LANES) {
+          const double s = fma(alpha, w[L.DS + t], w[L.S + t]);
+          phi += -mu_bar * log(s) + nu_pen * fabs(w[L.CT + t] - s);
+        }
+        for (int q = lane; q < L.NS; q += LANES) {
+          const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+          const double s = fma(alpha, w[L.SDS + q], w[L.SS + q]);
+          phi += -mu_bar * log(s) + nu_pen * fabs(simple_value(c, w + L.ZT, w + L.XT) - s);
+        }
+        phi = G::sum(phi) + Jt;
+        if (phi <= phi0 + 1e-4 * alpha * fmin(dphi, 0.0) + 1e-12 * fabs(phi0)) break;
+        alpha *= 0.5;
+      }
+      // accept
+      for (int t = lane; t < n; t += LANES) w[L.Z + t] = w[L.ZT + t];
+      for (int t = lane; t < (H + 1) * NX; t += LANES) w[L.X + t] = w[L.XT + t];
+      for (int t = lane; t < H * M; t += LANES) {
+        w[L.C + t] = w[L.CT + t];
+        w[L.S + t] = fma(alpha, w[L.DS + t], w[L.S + t]);
+        w[L.L + t] = fma(ad, w[L.DL + t], w[L.L + t]);
+      }
+      for (int q = lane; q < L.NS; q += LANES) {
+        w[L.SS + q] = fma(alpha, w[L.SDS + q], w[L.SS + q]);
+        w[L.SL + q] = fma(ad, w[L.SDL + q], w[L.SL + q]);
+      }
+      Jcur = Jt;
+      sync();
+    }
+    // outputs
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        double v = w[L.Z + i];
+        if (!(v == v)) v = uprev[i];
+        U[i] = fmin(fmax(v, p.u_lb[i]), p.u_ub[i]);
+      }
+      if (st == SCB_MAXITER && err > 1e-4) {
+        // distinguish "did not converge" from "locally infeasible" by the primal residual
+        double e_p = 0.0;
+        for (int t = 0; t < H * M; ++t) e_p = fmax(e_p, -w[L.C + t]);
+        if (e_p > 1e-6) st = SCB_INFEASIBLE;
+      }
+      *status = st;
+      if (iters) *iters = it;
+      if (kkt) *kkt = err;
+      if (pred_x) for (int t = 0; t < (H + 1) * NX; ++t) pred_x[t] = w[L.X + t];
+      if (pred_u) for (int t = 0; t < n; ++t) pred_u[t] = w[L.Z + t];
+    }
+    sync();
+  }
+};
+
+// entry point shared by the kernel and the host-sim
+template <int MODEL, int LANES>
+SCB_HD void mpc_agent(const scb_params& p, int H, int M, int nobs, const double* x0, const double* goal,
+                      const double* uprev, const double* obs, double* workspace, double* U, int32_t* status,
+                      double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+  using Mod = MpcModel<MODEL>;
+  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND>(H, M);
+  MpcSolver<MODEL, LANES> s(p, L, workspace);
+  if (nobs < 0) nobs = 0;
+  if (nobs > M) nobs = M;
+  s.solve(nobs, x0, goal, 2, uprev, obs, U, status, pred_x, pred_u, iters, kkt);
+}
+
+}  // namespace scb

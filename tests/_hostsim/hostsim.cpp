@@ -85,4 +85,34 @@ int hostsim_odcbf_solve(const scb_params* p, int N, int M, const double* X, cons
   return 0;
 }
 
+#ifdef SCB_HOSTSIM_MPC
+int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, const double* goal,
+                         const double* u_prev, const double* OBS, long stride, const int32_t* nobs, double* U,
+                         int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+  const int nx = p->nx, nu = p->nu;
+  for (int i = 0; i < N; ++i) {
+    const int no = nobs ? nobs[i] : M;
+    double* px = pred_x ? pred_x + (size_t)i * (H + 1) * nx : nullptr;
+    double* pu = pred_u ? pred_u + (size_t)i * H * nu : nullptr;
+    switch (p->model) {
+#define MPCCASE(MODEL)                                                                                          \
+  case MODEL: {                                                                                                 \
+    using Mod = MpcModel<MODEL>;                                                                                \
+    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND>(H, M);                                        \
+    double* ws = new double[L.total];                                                                           \
+    for (int t = 0; t < L.total; ++t) ws[t] = 0.0;                                                              \
+    mpc_agent<MODEL, 1>(*p, H, M, no, X + (size_t)i * nx, goal + (size_t)i * 2, u_prev + (size_t)i * nu,        \
+                        OBS + (size_t)i * stride, ws, U + (size_t)i * nu, status + i, px, pu,                   \
+                        iters ? iters + i : nullptr, kkt ? kkt + i : nullptr);                                  \
+    delete[] ws;                                                                                                \
+  } break;
+      MPCCASE(SCB_DYNAMIC_UNICYCLE_2D)
+      MPCCASE(SCB_KINEMATIC_BICYCLE_2D)
+      default: return SCB_ERR_UNSUPPORTED;
+    }
+  }
+  return 0;
+}
+#endif
+
 }  // extern "C"

@@ -71,3 +71,49 @@ def check_odcbf(spec, M, X, Uref, OBS, nobs, U, omega, sel, status, active, samp
             want = mask_from_bool(info["active"], 1)[0]
             assert np.uint64(active[i]) == want, f"agent {i}: active {active[i]} vs {want}"
     return dict(n=len(list(idx)), cbf_active=n_act, masks_compared=n_cmp)
+
+
+def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1e-4, min_agree=0.9):
+    """MPC parity: (a) every 'optimal' answer must be a KKT point of the ORACLE's restated NLP
+    (independent derivatives: torch.autograd on oracle/mpc_cbf.py), feasible to 1e-7; (b) u0 must agree
+    with the oracle's own SLSQP solve within u0_tol (box-normalised) on >= min_agree of the cases the
+    oracle converged on -- the NLP is non-convex, so a different local optimum (different cost) is
+    counted and reported, not hidden."""
+    import warnings
+    from oracle.mpc_cbf import OracleMPCCBF
+    warnings.filterwarnings("ignore")
+    o = OracleMPCCBF(spec, num_obs=M, horizon=H)
+    N = X.shape[0]
+    idx = list(range(N) if sample is None else sample)
+    rng = o.u_ub - o.u_lb
+    n_ok = n_cmp = n_agree = n_other = 0
+    worst_kkt = worst_du = 0.0
+    for i in idx:
+        k = M if nobs is None else max(int(nobs[i]), 0)
+        obs = OBS[i][:k]
+        if out["status"][i] != 0:
+            continue
+        n_ok += 1
+        kk, gmin, _ = o.kkt_error(X[i], goal[i], u_prev[i], obs, out["pred_u"][i])
+        scale = 1.0 + float(np.abs(out["pred_u"][i]).max())
+        assert gmin >= -1e-7, f"agent {i}: infeasible point reported optimal (min g = {gmin:.2e})"
+        assert kk <= 1e-4 * scale, f"agent {i}: not a KKT point of the oracle NLP (residual {kk:.2e})"
+        worst_kkt = max(worst_kkt, kk)
+        u, info = o.solve(X[i], goal[i], u_prev[i], obs)
+        if not info["success"] or info["cbf_min"] < -1e-6:
+            continue
+        n_cmp += 1
+        du = float(np.max(np.abs(out["U"][i] - u) / rng))
+        import torch
+        Jo = info["fun"]
+        Jm = float(o.condensed(X[i], goal[i], u_prev[i], obs, torch.tensor(out["pred_u"][i].reshape(-1)))[0])
+        if du <= u0_tol:
+            n_agree += 1; worst_du = max(worst_du, du)
+        elif abs(Jm - Jo) > 1e-7 * max(1.0, abs(Jo)):
+            n_other += 1                      # a different local optimum (or SLSQP stopped early)
+        else:
+            n_other += 1
+    stats = dict(n=len(idx), optimal=n_ok, compared=n_cmp, agree=n_agree, other_local=n_other,
+                 worst_kkt=worst_kkt, worst_du=worst_du)
+    assert n_cmp == 0 or n_agree >= min_agree * n_cmp, stats
+    return stats

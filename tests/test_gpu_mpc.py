@@ -1,0 +1,80 @@
+"""Parity tests for the MPC-CBF kernel through the C ABI (device-pointer and host-pointer paths)."""
+import numpy as np
+import pytest
+import torch
+
+from parity_util import check_mpc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def near_goal(sc, dist=3.0):
+    X = sc["X"]
+    return X[:, :2] + dist * np.stack([np.cos(X[:, 2]), np.sin(X[:, 2])], 1)
+
+
+def solve(ctrl, sc, goal, **kw):
+    out = ctrl.solve(dev(sc["X"]), dev(goal), dev(sc["u_prev"]), dev(sc["OBS"]), dev(sc["nobs"]), want_pred=True, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("model,N,H,M,near,n_check", [
+    ("DynamicUnicycle2D", 4096, 8, 16, False, 48),     # BASELINE config 3 at full size, oracle on a sample
+    ("DynamicUnicycle2D", 256, 8, 16, True, 32),       # goals nearby: interior optima, CBF rows active
+    ("KinematicBicycle2D", 128, 10, 64, False, 12),    # config-5 sized stage (H = 10, 64 obstacle slots)
+    ("DynamicUnicycle2D", 64, 10, 64, True, 8),
+])
+def test_mpc_vs_oracle(model, N, H, M, near, n_check):
+    from safe_control_b200 import BatchedMPCCBF, scenes
+    sc = scenes.make_scene(model, N, M, seed=1234)
+    goal = near_goal(sc) if near else sc["goal"]
+    ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
+    out = solve(ctrl, sc, goal)
+    frac_ok = (out["status"] == 0).mean()
+    assert frac_ok > 0.9, (frac_ok, np.bincount(out["status"]))
+    rng = np.random.default_rng(0)
+    sample = rng.choice(N, n_check, replace=False)
+    stats = check_mpc(ctrl.robot_spec, M, H, sc["X"], goal, sc["u_prev"], sc["OBS"], sc["nobs"], out, sample=sample,
+                      min_agree=0.75 if model.startswith("Kin") else 0.9)
+    print(model, N, H, M, stats, "iters mean", out["iters"].mean(), "max", out["iters"].max(), "ok", frac_ok)
+    # size-independent properties on the WHOLE batch: predictions satisfy the Euler model, inputs in the box
+    U, px, pu = out["U"], out["pred_x"], out["pred_u"]
+    lb = np.array(list(ctrl.params.u_lb)[:2]); ub = np.array(list(ctrl.params.u_ub)[:2])
+    assert ((U >= lb - 1e-12) & (U <= ub + 1e-12)).all()
+    ok = out["status"] == 0
+    np.testing.assert_allclose(px[:, 0], sc["X"], atol=0)
+    assert np.abs(pu[ok][:, 0] - U[ok]).max() < 1e-12
+    assert (np.abs(px[ok][:, :, 3]) <= ctrl.params.v_max + 1e-7).all()
+
+
+def test_mpc_track_mask_and_host_path():
+    from safe_control_b200 import BatchedMPCCBF, HostContext, scenes
+    N, H, M = 96, 8, 16
+    sc = scenes.make_scene("DynamicUnicycle2D", N, M, seed=3)
+    ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
+    track = np.ones(N, np.int32); track[::3] = 0
+    out = ctrl.solve(dev(sc["X"]), dev(sc["goal"]), dev(sc["u_prev"]), dev(sc["OBS"]), dev(sc["nobs"]),
+                     U_ref=dev(sc["U_ref"]), track=dev(track))
+    U = out["U"].cpu().numpy()
+    np.testing.assert_array_equal(U[::3], sc["U_ref"][::3])          # not 'track' -> u_ref untouched (mpc_cbf.py:379-381)
+    ref = solve(ctrl, sc, sc["goal"])
+    np.testing.assert_allclose(U[track == 1], ref["U"][track == 1], atol=0)
+    ctx = HostContext(0)
+    h = ctx.mpccbf_solve(ctrl.params, M, H, sc["X"], sc["goal"], sc["u_prev"], sc["OBS"], sc["nobs"], want_pred=True)
+    np.testing.assert_array_equal(h["U"], ref["U"]); np.testing.assert_array_equal(h["status"], ref["status"])
+    np.testing.assert_array_equal(h["pred_u"], ref["pred_u"])
+    ctx.close()
+
+
+def test_mpc_unsupported_models_fail_loudly():
+    from safe_control_b200 import BatchedMPCCBF
+    from safe_control_b200._lib import ScbError
+    ctrl = BatchedMPCCBF({"model": "KinematicBicycle2D_C3BF"}, num_obs=4, horizon=4)
+    z = lambda *s: torch.zeros(s, dtype=torch.float64, device="cuda")
+    with pytest.raises(ScbError):
+        ctrl.solve(z(2, 4), z(2, 2), z(2, 2), z(2, 4, 7))

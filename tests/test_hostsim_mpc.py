@@ -1,0 +1,44 @@
+"""CPU check of the MPC-CBF kernel body (g++ build of scb_mpc.cuh at LANES = 1) against the oracle NLP."""
+import numpy as np
+import pytest
+
+from hostsim_util import hostsim, hs_mpccbf_solve
+from parity_util import check_mpc
+from safe_control_b200.params import resolve_params
+from safe_control_b200 import scenes
+
+
+def near_goal(sc, dist=3.0):
+    X = sc["X"]
+    return X[:, :2] + dist * np.stack([np.cos(X[:, 2]), np.sin(X[:, 2])], 1)
+
+
+@pytest.mark.parametrize("model,N,H,M,near", [("DynamicUnicycle2D", 10, 8, 16, False),
+                                               ("DynamicUnicycle2D", 8, 8, 16, True),
+                                               ("KinematicBicycle2D", 6, 6, 8, False)])
+def test_mpc_vs_oracle(model, N, H, M, near):
+    sc = scenes.make_scene(model, N, M, seed=4321)
+    goal = near_goal(sc) if near else sc["goal"]
+    p, spec = resolve_params(sc["spec"], "mpc_cbf", lib=hostsim())
+    out = hs_mpccbf_solve(p, H, sc["X"], goal, sc["u_prev"], sc["OBS"], sc["nobs"])
+    assert (out["status"] == 0).mean() >= 0.8, out["status"]
+    stats = check_mpc(spec, M, H, sc["X"], goal, sc["u_prev"], sc["OBS"], sc["nobs"], out,
+                      min_agree=0.75 if model.startswith("Kin") else 0.9)
+    print(model, stats, "iters", out["iters"])
+
+
+def test_mpc_no_obstacles_is_box_clipped_tracking():
+    """Without obstacles the solution must equal the unconstrained-by-CBF MPC; with the goal far
+    ahead and straight, full acceleration saturates: u0 = [a_max, ~0]."""
+    p, spec = resolve_params({"model": "DynamicUnicycle2D"}, "mpc_cbf", lib=hostsim())
+    X = np.array([[0.0, 0.0, 0.0, 0.2]]); goal = np.array([[10.0, 0.0]]); up = np.zeros((1, 2))
+    OBS = np.zeros((1, 4, 7)); nobs = np.array([0], np.int32)
+    out = hs_mpccbf_solve(p, 8, X, goal, up, OBS, nobs)
+    assert out["status"][0] == 0
+    assert abs(out["U"][0, 0] - 0.5) < 1e-6 and abs(out["U"][0, 1]) < 1e-6
+    # Euler prediction is consistent with the inputs
+    x = X[0].copy()
+    for k in range(8):
+        u = out["pred_u"][0, k]
+        x = x + 0.05 * np.array([x[3] * np.cos(x[2]), x[3] * np.sin(x[2]), u[1], u[0]])
+        np.testing.assert_allclose(out["pred_x"][0, k + 1], x, atol=1e-12)
