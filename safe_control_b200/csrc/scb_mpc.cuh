@@ -168,11 +168,18 @@ struct MpcSolver {
   double w0, w1, w2, Wsum;      // c_j = w0 h(p0) + w1 h(p1) + w2 h(p2),  h = |p - o|^2 - beta d^2
   double goal[NX];
   double uprev[NU];
+  double Qs[NX], Rs[NU];        // cost weights times the objective scaling factor (IPOPT-style gradient-based scaling)
+  bool gauss_newton;            // assemble stage Hessians without the (possibly indefinite) curvature terms
 
   SCB_HD MpcSolver(const scb_params& p_, const MpcLayout& L_, double* w_) : p(p_), L(L_), w(w_) {
     H = L.H; M = L.M; n = L.n; lane = G::lane();
     const double g1 = p.alpha1 + p.alpha2, g2 = p.alpha1 * p.alpha2;
     w2 = 1.0; w1 = g1 - 2.0; w0 = 1.0 - g1 + g2; Wsum = g2;    // dd_h + (a1+a2) d_h + a1 a2 h_k  (mpc_cbf.py:320-321)
+#pragma unroll
+    for (int i = 0; i < NX; ++i) Qs[i] = p.Q[i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) Rs[i] = p.R[i];
+    gauss_newton = false;
   }
 
   static SCB_HD void sync() {
@@ -189,11 +196,11 @@ struct MpcSolver {
     for (int i = 0; i < NX; ++i) x[i] = xs[i];
     for (int k = 0; k < H; ++k) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) { const double e = x[i] - goal[i]; Jc = fma(p.Q[i] * e, e, Jc); }
+      for (int i = 0; i < NX; ++i) { const double e = x[i] - goal[i]; Jc = fma(Qs[i] * e, e, Jc); }
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
         const double d = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]);
-        Jc = fma(p.R[i] * d, d, Jc);
+        Jc = fma(Rs[i] * d, d, Jc);
       }
       double y[NY], F[NX], a, b, c, d;
 #pragma unroll
@@ -205,7 +212,7 @@ struct MpcSolver {
       for (int i = 0; i < NX; ++i) { x[i] = F[i]; xs[(k + 1) * NX + i] = F[i]; }
     }
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { const double e = x[i] - goal[i]; Jc = fma(p.Q[i] * e, e, Jc); }
+    for (int i = 0; i < NX; ++i) { const double e = x[i] - goal[i]; Jc = fma(Qs[i] * e, e, Jc); }
     return Jc;
   }
 
@@ -289,8 +296,8 @@ struct MpcSolver {
     for (int t = lane; t < n; t += LANES) {
       const int k = t / NU, i = t - k * NU;
       const double um = (k == 0) ? uprev[i] : z[(k - 1) * NU + i];
-      double g = 2.0 * p.R[i] * (z[t] - um);
-      if (k + 1 < H) g -= 2.0 * p.R[i] * (z[(k + 1) * NU + i] - z[t]);
+      double g = 2.0 * Rs[i] * (z[t] - um);
+      if (k + 1 < H) g -= 2.0 * Rs[i] * (z[(k + 1) * NU + i] - z[t]);
       out[t] = g;
     }
     sync();
@@ -368,7 +375,7 @@ struct MpcSolver {
     for (int t = lane; t < (H + 1) * NY; t += LANES) {
       const int k = t / NY, i = t - k * NY;
       double v = 0.0;
-      if (i < NX) v = 2.0 * p.Q[i] * (xs[k * NX + i] - goal[i]);
+      if (i < NX) v = 2.0 * Qs[i] * (xs[k * NX + i] - goal[i]);
       if (rhs) v = -v;
       if (k < H) {
         const double* sm = w + L.SUM + k * 12 + (rhs ? 9 : 6);
@@ -414,23 +421,25 @@ struct MpcSolver {
       while (rem >= NY - i) { rem -= NY - i; ++i; }
       const int j = i + rem;
       double v = 0.0;
-      if (i == j && i < NX) v = 2.0 * p.Q[i];
+      if (i == j && i < NX) v = 2.0 * Qs[i];
       if (k < H) {
         const double* sm = w + L.SUM + k * 12;
         const double* je = w + L.JE + k * (NY + NH);
         const double* jx = w + L.JX + k * (NY + NH);
         const double* jy = w + L.JY + k * (NY + NH);
-        // - sum_j lam_j hess c_j
-        v -= sm[6] * je[NY + e] - sm[7] * jx[NY + e] - sm[8] * jy[NY + e];
+        // - sum_j lam_j hess c_j   (exact Lagrangian Hessian only; dropped in Gauss-Newton mode)
+        if (!gauss_newton) v -= sm[6] * je[NY + e] - sm[7] * jx[NY + e] - sm[8] * jy[NY + e];
         // + sum_j sigma_j grad c_j grad c_j'
         const double ei = je[i], ej = je[j], xi = jx[i], xj = jx[j], yi = jy[i], yj = jy[j];
         v += sm[0] * ei * ej - sm[1] * (ei * xj + xi * ej) - sm[2] * (ei * yj + yi * ej) + sm[3] * xi * xj +
              sm[4] * (xi * yj + yi * xj) + sm[5] * yi * yj;
         // + sum_c mu_{k+1,c} hess F_c
-        const double* FH = w + L.FH + k * NX * NH;
-        const double* mu = w + L.MU + (k + 1) * NX;
+        if (!gauss_newton) {
+          const double* FH = w + L.FH + k * NX * NH;
+          const double* mu = w + L.MU + (k + 1) * NX;
 #pragma unroll
-        for (int c = 0; c < NX; ++c) v = fma(mu[c], FH[c * NH + e], v);
+          for (int c = 0; c < NX; ++c) v = fma(mu[c], FH[c * NH + e], v);
+        }
       }
       Gm[t] = v;
     }
@@ -490,8 +499,8 @@ struct MpcSolver {
     sync();
     for (int t = lane; t < n; t += LANES) {
       const int k = t / NU, i = t - k * NU;
-      Hr[t * n + t] = (k + 1 < H) ? 4.0 * p.R[i] : 2.0 * p.R[i];
-      if (k + 1 < H) { Hr[(t + NU) * n + t] = -2.0 * p.R[i]; }
+      Hr[t * n + t] = (k + 1 < H) ? 4.0 * Rs[i] : 2.0 * Rs[i];
+      if (k + 1 < H) { Hr[(t + NU) * n + t] = -2.0 * Rs[i]; }
     }
     sync();
     for (int k = 0; k <= H; ++k) {
@@ -596,74 +605,116 @@ struct MpcSolver {
     sync();
     points_and_cbf(w + L.Z, w + L.X, w + L.C);
 
-    double mu_bar = 0.1;
-    const double tol = p.mpc_tol, s_min = 1e-2;
-    for (int t = lane; t < H * M; t += LANES) {
-      const double s = fmax(w[L.C + t], s_min);
-      w[L.S + t] = s; w[L.L + t] = mu_bar / s;
+    // objective scaling as IPOPT's default gradient-based scaling: max |dJ/dz| at the start <= 100
+    {
+      stage_derivatives();
+      double* gam = w + L.GAM;
+      for (int t = lane; t < (H + 1) * NY; t += LANES) {
+        const int k = t / NY, i = t - k * NY;
+        gam[t] = (i < NX) ? 2.0 * Qs[i] * (w[L.X + k * NX + i] - goal[i]) : 0.0;
+      }
+      sync();
+      adjoint(gam, w + L.RD);
+      rate_gradient(w + L.Z, w + L.RG);
+      double gmax = 0.0;
+      for (int t = lane; t < n; t += LANES) gmax = fmax(gmax, fabs(w[L.RD + t] + w[L.RG + t]));
+      gmax = -G::vmin(-gmax);
+      const double sf = (gmax > 100.0) ? 100.0 / gmax : 1.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Qs[i] *= sf;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) Rs[i] *= sf;
+      Jcur *= sf;
+      sync();
     }
-    for (int q = lane; q < L.NS; q += LANES) {
-      const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-      const double s = fmax(simple_value(c, w + L.Z, w + L.X), s_min);
-      w[L.SS + q] = s; w[L.SL + q] = mu_bar / s;
-    }
+    double mu_bar = 0.1, nu_pen = 10.0;
+    const double tol = p.mpc_tol;
+    // slacks are not independent iterates: s_i = max(g_i(z), mu/nu) is re-derived from the constraint values
+    // every iteration, so satisfied rows carry no primal residual however non-linear they are, and only rows
+    // below the floor act as (linearly penalised) violations.  The line search runs on the matching
+    // penalty-barrier merit  psi(z) = J(z) + sum_i rho(g_i(z)),  rho(g) = -mu log g  (g >= mu/nu), linear below.
+    auto reset_slacks = [&](double floor_) {
+      for (int t = lane; t < H * M; t += LANES) w[L.S + t] = fmax(w[L.C + t], floor_);
+      for (int q = lane; q < L.NS; q += LANES) {
+        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        w[L.SS + q] = fmax(simple_value(c, w + L.Z, w + L.X), floor_);
+      }
+      sync();
+    };
+    reset_slacks(mu_bar / nu_pen);
+    for (int t = lane; t < H * M; t += LANES) w[L.L + t] = mu_bar / w[L.S + t];
+    for (int q = lane; q < L.NS; q += LANES) w[L.SL + q] = mu_bar / w[L.SS + q];
     sync();
 
-    int it = 0, st = SCB_MAXITER;
-    double err = kInf;
-    const int max_iter = p.mpc_max_iter > 0 ? p.mpc_max_iter : 200;
+    int it = 0, st = SCB_MAXITER, it_best = 0, tiny_steps = 0;
+    double err = kInf, err_best = kInf;
+    const int max_iter = p.mpc_max_iter > 0 ? p.mpc_max_iter : 150;
     for (; it < max_iter; ++it) {
       stage_derivatives();
       stage_sums(mu_bar, false);
       stage_gradients(false, mu_bar);
       adjoint(w + L.GAM, w + L.RD);                 // costates + d/dz of (J_stage - lam' g)
       rate_gradient(w + L.Z, w + L.RG);
-      // residuals
+      // residuals (e_p = constraint violation, e_c = complementarity)
       double e_d = 0.0, e_p = 0.0, e_c = 0.0, e_cm = 0.0, lam_max = 0.0;
       for (int t = lane; t < n; t += LANES) e_d = fmax(e_d, fabs(w[L.RD + t] + w[L.RG + t]));
       for (int t = lane; t < H * M; t += LANES) {
-        const double s = w[L.S + t], lam = w[L.L + t];
-        e_p = fmax(e_p, fabs(w[L.C + t] - s)); e_c = fmax(e_c, s * lam); e_cm = fmax(e_cm, fabs(s * lam - mu_bar));
+        const double g = w[L.C + t], lam = w[L.L + t], sg = fmax(g, 0.0);
+        e_p = fmax(e_p, -g); e_c = fmax(e_c, sg * lam); e_cm = fmax(e_cm, fabs(sg * lam - mu_bar));
         lam_max = fmax(lam_max, lam);
       }
       for (int q = lane; q < L.NS; q += LANES) {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-        const double s = w[L.SS + q], lam = w[L.SL + q];
-        e_p = fmax(e_p, fabs(simple_value(c, w + L.Z, w + L.X) - s)); e_c = fmax(e_c, s * lam);
-        e_cm = fmax(e_cm, fabs(s * lam - mu_bar)); lam_max = fmax(lam_max, lam);
+        const double g = simple_value(c, w + L.Z, w + L.X), lam = w[L.SL + q], sg = fmax(g, 0.0);
+        e_p = fmax(e_p, -g); e_c = fmax(e_c, sg * lam); e_cm = fmax(e_cm, fabs(sg * lam - mu_bar));
+        lam_max = fmax(lam_max, lam);
       }
       e_d = -G::vmin(-e_d); e_p = -G::vmin(-e_p); e_c = -G::vmin(-e_c); e_cm = -G::vmin(-e_cm);
       lam_max = -G::vmin(-lam_max);
       err = fmax(e_d, fmax(e_p, e_c));
-      if (!(err == err)) { st = SCB_NUMERICAL; break; }
+      if (!(err == err) || !(lam_max < 1e200)) { st = SCB_NUMERICAL; break; }
       if (err <= tol) { st = SCB_OPTIMAL; break; }
+      if (err < 0.5 * err_best) { err_best = err; it_best = it; }
+      else if (it - it_best > 50) break;             // no progress for 50 iterations: give up
       // monotone barrier update (Fiacco-McCormick with IPOPT's kappa_mu = 0.2, theta_mu = 1.5, kappa_eps = 10)
       while (fmax(e_d, fmax(e_p, e_cm)) <= 10.0 * mu_bar && mu_bar > tol / 10.0) {
         mu_bar = fmax(tol / 10.0, fmin(0.2 * mu_bar, mu_bar * sqrt(mu_bar)));
         e_cm = 0.0;
-        for (int t = lane; t < H * M; t += LANES) e_cm = fmax(e_cm, fabs(w[L.S + t] * w[L.L + t] - mu_bar));
-        for (int q = lane; q < L.NS; q += LANES) e_cm = fmax(e_cm, fabs(w[L.SS + q] * w[L.SL + q] - mu_bar));
+        for (int t = lane; t < H * M; t += LANES) e_cm = fmax(e_cm, fabs(fmax(w[L.C + t], 0.0) * w[L.L + t] - mu_bar));
+        for (int q = lane; q < L.NS; q += LANES) {
+          const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+          e_cm = fmax(e_cm, fabs(fmax(simple_value(c, w + L.Z, w + L.X), 0.0) * w[L.SL + q] - mu_bar));
+        }
         e_cm = -G::vmin(-e_cm);
       }
-      // Newton system
-      stage_hessians();
+      nu_pen = fmax(nu_pen, 1.1 * lam_max);
+      if (nu_pen > 1e12) { st = SCB_INFEASIBLE; break; }
+      const double floor_s = mu_bar / nu_pen;
+      reset_slacks(floor_s);
+      // Newton system: exact Lagrangian Hessian first; if the reduced matrix is not positive definite,
+      // fall back to the Gauss-Newton stage Hessians (PSD by construction) before any diagonal shift
       stage_sums(mu_bar, true);
+      gauss_newton = false;
+      stage_hessians();
       stage_gradients(true, mu_bar);
-      {
-        // keep the costates of the first sweep: the rhs sweep must not overwrite them before use -> done (G built)
-        adjoint(w + L.GAM, w + L.RHS);
-        for (int t = lane; t < n; t += LANES) w[L.RHS + t] -= w[L.RG + t];
-        sync();
-      }
+      adjoint(w + L.GAM, w + L.RHS);                // (costates of the first sweep were consumed by stage_hessians)
+      for (int t = lane; t < n; t += LANES) w[L.RHS + t] -= w[L.RG + t];
+      sync();
       sensitivities();
       reduced_hessian();
       double delta = 0.0;
-      int tries = 0;
-      while (!cholesky(delta)) {
-        delta = (delta == 0.0) ? 1e-4 : delta * 10.0;
-        if (++tries > 24) break;
+      bool pd = cholesky(0.0);
+      if (!pd) {
+        gauss_newton = true;
+        stage_hessians();
+        reduced_hessian();
+        gauss_newton = false;
+        int tries = 0;
+        pd = cholesky(0.0);
+        while (!pd && tries < 12) { delta = (delta == 0.0) ? 1e-8 : delta * 100.0; pd = cholesky(delta); ++tries; }
+        if (delta == 0.0) delta = -1.0;             // marks "Gauss-Newton step" in traces
       }
-      if (tries > 24) { st = SCB_NUMERICAL; break; }
+      if (!pd) { st = SCB_NUMERICAL; break; }
       chol_solve(w + L.RHS, w + L.DZ);
       // stage directions dy_k = Sy_k dz
       for (int t = lane; t < (H + 1) * NY; t += LANES) {
@@ -676,9 +727,10 @@ struct MpcSolver {
         w[L.DY + t] = v;
       }
       sync();
-      // slack / multiplier directions, fraction to the boundary
+      // linearised constraint change dg (stored in DS), multiplier direction, fraction to the boundary,
+      // and the directional derivative of the merit
       const double tau = fmax(0.99, 1.0 - mu_bar);
-      double ap = 1.0, ad = 1.0, dphi_c = 0.0, rp1 = 0.0;
+      double ap = 1.0, ad = 1.0, dpsi = 0.0;
       for (int t = lane; t < H * M; t += LANES) {
         const int k = t / M, j = t - k * M;
         const double* ob = w + L.OB + j * 3;
@@ -689,77 +741,86 @@ struct MpcSolver {
           const double gi = w[L.JE + k * (NY + NH) + i] - ob[0] * w[L.JX + k * (NY + NH) + i] - ob[1] * w[L.JY + k * (NY + NH) + i];
           dg = fma(gi, dy[i], dg);
         }
-        const double s = w[L.S + t], lam = w[L.L + t], rp = w[L.C + t] - s;
-        const double ds = dg + rp, dl = -((s * lam - mu_bar) + lam * ds) / s;
-        w[L.DS + t] = ds; w[L.DL + t] = dl;
+        const double g = w[L.C + t], s = w[L.S + t], lam = w[L.L + t];
+        const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) / s;
+        w[L.DS + t] = dg; w[L.DL + t] = dl;
         if (ds < 0.0) ap = fmin(ap, -tau * s / ds);
         if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
-        dphi_c -= mu_bar * ds / s; rp1 += fabs(rp);
+        dpsi += (g >= floor_s) ? -mu_bar * dg / g : -nu_pen * dg;
       }
       for (int q = lane; q < L.NS; q += LANES) {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
         const double dg = c.sgn * w[L.DY + c.k * NY + c.var];
-        const double s = w[L.SS + q], lam = w[L.SL + q], rp = simple_value(c, w + L.Z, w + L.X) - s;
-        const double ds = dg + rp, dl = -((s * lam - mu_bar) + lam * ds) / s;
-        w[L.SDS + q] = ds; w[L.SDL + q] = dl;
+        const double g = simple_value(c, w + L.Z, w + L.X), s = w[L.SS + q], lam = w[L.SL + q];
+        const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) / s;
+        w[L.SDS + q] = dg; w[L.SDL + q] = dl;
         if (ds < 0.0) ap = fmin(ap, -tau * s / ds);
         if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
-        dphi_c -= mu_bar * ds / s; rp1 += fabs(rp);
+        dpsi += (g >= floor_s) ? -mu_bar * dg / g : -nu_pen * dg;
       }
       ap = G::vmin(ap); ad = G::vmin(ad);
-      dphi_c = G::sum(dphi_c); rp1 = G::sum(rp1);
+      dpsi = G::sum(dpsi);
       // directional derivative of the cost: grad J . dz = sum_k grad l_k . dy_k + rate_grad . dz
       double dJ = 0.0;
       for (int t = lane; t < (H + 1) * NX; t += LANES) {
         const int k = t / NX, i = t - k * NX;
-        dJ = fma(2.0 * p.Q[i] * (w[L.X + t] - goal[i]), w[L.DY + k * NY + i], dJ);
+        dJ = fma(2.0 * Qs[i] * (w[L.X + t] - goal[i]), w[L.DY + k * NY + i], dJ);
       }
       for (int t = lane; t < n; t += LANES) dJ = fma(w[L.RG + t], w[L.DZ + t], dJ);
       dJ = G::sum(dJ);
-      const double nu_pen = fmax(1.0, 1.1 * lam_max);
-      const double dphi = dJ + dphi_c - nu_pen * rp1;
-      // merit at alpha = 0
-      double phi0 = 0.0;
-      for (int t = lane; t < H * M; t += LANES) phi0 += -mu_bar * log(w[L.S + t]) + nu_pen * fabs(w[L.C + t] - w[L.S + t]);
-      for (int q = lane; q < L.NS; q += LANES) {
-        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-        phi0 += -mu_bar * log(w[L.SS + q]) + nu_pen * fabs(simple_value(c, w + L.Z, w + L.X) - w[L.SS + q]);
-      }
-      phi0 = G::sum(phi0) + Jcur;
+      dpsi += dJ;
+      const double rho_lin0 = -mu_bar * log(floor_s) + nu_pen * floor_s;     // rho(g) = rho_lin0 - nu g  below the floor
+      auto merit_terms = [&](const double* cb, const double* zz, const double* xx) {
+        double acc = 0.0;
+        for (int t = lane; t < H * M; t += LANES) {
+          const double g = cb[t];
+          acc += (g >= floor_s) ? -mu_bar * log(g) : rho_lin0 - nu_pen * g;
+        }
+        for (int q = lane; q < L.NS; q += LANES) {
+          const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+          const double g = simple_value(c, zz, xx);
+          acc += (g >= floor_s) ? -mu_bar * log(g) : rho_lin0 - nu_pen * g;
+        }
+        return G::sum(acc);
+      };
+      const double psi0 = merit_terms(w + L.C, w + L.Z, w + L.X) + Jcur;
       // backtracking
       double alpha = ap, Jt = Jcur;
-      for (int bt = 0; bt < 14; ++bt) {
+      int bt = 0;
+      for (; bt < 20; ++bt) {
         for (int t = lane; t < n; t += LANES) w[L.ZT + t] = fma(alpha, w[L.DZ + t], w[L.Z + t]);
         sync();
         if (lane == 0) Jt = rollout(w + L.ZT, w + L.XT);
         Jt = G::bcast(Jt, 0);
         sync();
         points_and_cbf(w + L.ZT, w + L.XT, w + L.CT);
-        double phi = 0.0;
-        for (int t = lane; t < H * M; t += LANES) {
-          const double s = fma(alpha, w[L.DS + t], w[L.S + t]);
-          phi += -mu_bar * log(s) + nu_pen * fabs(w[L.CT + t] - s);
-        }
-        for (int q = lane; q < L.NS; q += LANES) {
-          const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-          const double s = fma(alpha, w[L.SDS + q], w[L.SS + q]);
-          phi += -mu_bar * log(s) + nu_pen * fabs(simple_value(c, w + L.ZT, w + L.XT) - s);
-        }
-        phi = G::sum(phi) + Jt;
-        if (phi <= phi0 + 1e-4 * alpha * fmin(dphi, 0.0) + 1e-12 * fabs(phi0)) break;
+        const double psi = merit_terms(w + L.CT, w + L.ZT, w + L.XT) + Jt;
+        if (psi <= psi0 + 1e-4 * alpha * fmin(dpsi, 0.0) + 1e-13 * fabs(psi0)) break;
         alpha *= 0.5;
       }
-      // accept
+#if defined(SCB_MPC_TRACE) && !defined(__CUDA_ARCH__)
+      printf("[mpc] it=%3d J=%.6f ed=%.2e ep=%.2e ec=%.2e mu=%.1e ap=%.2e ad=%.2e alpha=%.2e bt=%d delta=%.1e dpsi=%.2e nu=%.2e\n", it, Jcur, e_d, e_p, e_c,
+             mu_bar, ap, ad, alpha, bt, delta, dpsi, nu_pen);
+#endif
+      tiny_steps = (alpha < 1e-10) ? tiny_steps + 1 : 0;
+      if (tiny_steps >= 5) { st = (e_p > 1e-6) ? SCB_INFEASIBLE : SCB_MAXITER; break; }
+      // accept: z, x, g; multipliers move with their own step and are kept within kappa_Sigma of mu/g
       for (int t = lane; t < n; t += LANES) w[L.Z + t] = w[L.ZT + t];
       for (int t = lane; t < (H + 1) * NX; t += LANES) w[L.X + t] = w[L.XT + t];
+      sync();
       for (int t = lane; t < H * M; t += LANES) {
         w[L.C + t] = w[L.CT + t];
-        w[L.S + t] = fma(alpha, w[L.DS + t], w[L.S + t]);
-        w[L.L + t] = fma(ad, w[L.DL + t], w[L.L + t]);
+        const double sN = fmax(w[L.CT + t], floor_s);
+        double lam = fma(ad, w[L.DL + t], w[L.L + t]);
+        lam = fmin(fmax(lam, mu_bar / (1e10 * sN)), 1e10 * mu_bar / sN);
+        w[L.L + t] = lam;
       }
       for (int q = lane; q < L.NS; q += LANES) {
-        w[L.SS + q] = fma(alpha, w[L.SDS + q], w[L.SS + q]);
-        w[L.SL + q] = fma(ad, w[L.SDL + q], w[L.SL + q]);
+        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        const double sN = fmax(simple_value(c, w + L.Z, w + L.X), floor_s);
+        double lam = fma(ad, w[L.SDL + q], w[L.SL + q]);
+        lam = fmin(fmax(lam, mu_bar / (1e10 * sN)), 1e10 * mu_bar / sN);
+        w[L.SL + q] = lam;
       }
       Jcur = Jt;
       sync();

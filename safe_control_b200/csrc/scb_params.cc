@@ -63,7 +63,7 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
   p->dt = 0.05;
   p->radius = 0.25;
   p->gravity = 9.8;
-  p->mpc_max_iter = 200;
+  p->mpc_max_iter = 150;
   p->mpc_tol = 1e-8;
   p->v_min = -1e300; p->v_max = 1e300;
   switch (model) {
