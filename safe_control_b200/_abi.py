@@ -38,6 +38,7 @@ _vp = C.c_void_p
 # name -> (restype, argtypes); every symbol include/scb.h declares
 PROTOTYPES = {
     "scb_version": (C.c_int, []),
+    "scb_params_sizeof": (C.c_size_t, []),
     "scb_strerror": (C.c_char_p, [C.c_int]),
     "scb_last_cuda_error": (C.c_int, []),
     "scb_device_count": (C.c_int, []),

@@ -43,10 +43,25 @@ SCB_HD void jclip(double& r, double a, double lo, double hi) { r = a > hi ? hi :
 template <int MODEL>
 struct MpcModel;
 
+// SingleIntegrator2D: f = 0, g = I (robots/single_integrator2D.py:44-62), step :64-66, barrier_dt :148-195.
+// Relative degree 1: cbf = d_h + alpha h_k (mpc_cbf.py:312-315).
+template <>
+struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
+  static constexpr int NX = 2, NU = 2, NY = 4, REL = 1;
+  static constexpr bool VBOUND = false;
+  static SCB_HD double beta() { return 1.01; }
+  template <class T>
+  static SCB_HD void stage(const scb_params& p, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+    jaxpy(F[0], y[0], p.dt, y[2]);
+    jaxpy(F[1], y[1], p.dt, y[3]);
+    P1 = F[0]; Q1 = F[1]; P2 = F[0]; Q2 = F[1];
+  }
+};
+
 // DynamicUnicycle2D: f, g robots/dynamic_unicycle2D.py:42-73, step :75-78, barrier_dt :188-238
 template <>
 struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
-  static constexpr int NX = 4, NU = 2, NY = 6;
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2;
   static constexpr bool VBOUND = true;
   static SCB_HD double beta() { return 1.01; }
   // y = (px, py, theta, v, a, omega).  F = Euler map; (P1,Q1), (P2,Q2) = positions after 1 and 2 own steps.
@@ -71,7 +86,7 @@ struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
 // KinematicBicycle2D: f, g robots/kinematic_bicycle2D.py:75-110, step (clips v) :112-123, barrier_dt :175-199
 template <>
 struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
-  static constexpr int NX = 4, NU = 2, NY = 6;
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2;
   static constexpr bool VBOUND = true;
   static SCB_HD double beta() { return 1.1; }
   template <class T>
@@ -173,8 +188,12 @@ struct MpcSolver {
 
   SCB_HD MpcSolver(const scb_params& p_, const MpcLayout& L_, double* w_) : p(p_), L(L_), w(w_) {
     H = L.H; M = L.M; n = L.n; lane = G::lane();
-    const double g1 = p.alpha1 + p.alpha2, g2 = p.alpha1 * p.alpha2;
-    w2 = 1.0; w1 = g1 - 2.0; w0 = 1.0 - g1 + g2; Wsum = g2;    // dd_h + (a1+a2) d_h + a1 a2 h_k  (mpc_cbf.py:320-321)
+    if (Mod::REL == 2) {
+      const double g1 = p.alpha1 + p.alpha2, g2 = p.alpha1 * p.alpha2;
+      w2 = 1.0; w1 = g1 - 2.0; w0 = 1.0 - g1 + g2; Wsum = g2;  // dd_h + (a1+a2) d_h + a1 a2 h_k  (mpc_cbf.py:320-321)
+    } else {
+      w2 = 0.0; w1 = 1.0; w0 = p.alpha - 1.0; Wsum = p.alpha;  // d_h + alpha h_k                 (mpc_cbf.py:314-315)
+    }
 #pragma unroll
     for (int i = 0; i < NX; ++i) Qs[i] = p.Q[i];
 #pragma unroll

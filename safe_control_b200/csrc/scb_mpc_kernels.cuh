@@ -83,6 +83,9 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X,
                       cudaStream_t s, int sm_count) {
   if (M > kMpcMaxObs || H > kMpcMaxH || H * p.nu > 32) return SCB_ERR_TOO_LARGE;
   switch (p.model) {
+    case SCB_SINGLE_INTEGRATOR_2D:
+      return mpc_launch_m<SCB_SINGLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
+                                                    pred_x, pred_u, iters, kkt, s, sm_count);
     case SCB_DYNAMIC_UNICYCLE_2D:
       return mpc_launch_m<SCB_DYNAMIC_UNICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
                                                    pred_x, pred_u, iters, kkt, s, sm_count);
@@ -90,7 +93,7 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X,
       return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
                                                     pred_x, pred_u, iters, kkt, s, sm_count);
     default:
-      return SCB_ERR_UNSUPPORTED;     // round 1: circle-barrier 4-state models only
+      return SCB_ERR_UNSUPPORTED;     // round 1: circle-barrier SI / DU / KB only
   }
 }
 

@@ -20,6 +20,8 @@ extern "C" {
 
 int scb_version(void) { return SCB_VERSION; }
 
+size_t scb_params_sizeof(void) { return sizeof(scb_params); }
+
 const char* scb_strerror(int err) {
   switch (err) {
     case SCB_OK: return "ok";

@@ -106,6 +106,7 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
                         iters ? iters + i : nullptr, kkt ? kkt + i : nullptr);                                  \
     delete[] ws;                                                                                                \
   } break;
+      MPCCASE(SCB_SINGLE_INTEGRATOR_2D)
       MPCCASE(SCB_DYNAMIC_UNICYCLE_2D)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D)
       default: return SCB_ERR_UNSUPPORTED;

@@ -10,12 +10,14 @@ from safe_control_b200 import scenes
 
 def near_goal(sc, dist=3.0):
     X = sc["X"]
-    return X[:, :2] + dist * np.stack([np.cos(X[:, 2]), np.sin(X[:, 2])], 1)
+    th = X[:, 2] if X.shape[1] > 2 else np.zeros(len(X))
+    return X[:, :2] + dist * np.stack([np.cos(th), np.sin(th)], 1)
 
 
 @pytest.mark.parametrize("model,N,H,M,near", [("DynamicUnicycle2D", 10, 8, 16, False),
                                                ("DynamicUnicycle2D", 8, 8, 16, True),
-                                               ("KinematicBicycle2D", 6, 6, 8, False)])
+                                               ("KinematicBicycle2D", 6, 6, 8, False),
+                                               ("SingleIntegrator2D", 8, 10, 8, False)])
 def test_mpc_vs_oracle(model, N, H, M, near):
     sc = scenes.make_scene(model, N, M, seed=4321)
     goal = near_goal(sc) if near else sc["goal"]
