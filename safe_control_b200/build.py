@@ -34,7 +34,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu"] + SRCS + ["-o", OUT]
+    extra = os.environ.get("SCB_EXTRA_NVCC_FLAGS", "").split()          # e.g. -DSCB_MPC_PROFILE (debug)
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu"] + SRCS + ["-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -174,6 +174,15 @@ int scb_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, 
   return SCB_OK;
 }
 
+#if defined(SCB_MPC_PROFILE)
+// debug build only: per-phase cycle counters of warp 0 / block 0 (see scb_mpc.cuh)
+int scb_debug_mpc_profile(long long* out, int reset) {
+  if (out) CK(cudaMemcpyFromSymbol(out, g_mpc_prof, sizeof(long long) * 24));
+  if (reset) { long long z[24] = {0}; CK(cudaMemcpyToSymbol(g_mpc_prof, z, sizeof(z))); }
+  return SCB_OK;
+}
+#endif
+
 // ------------------------------------------------------------------------------ host-pointer context
 struct scb_ctx {
   int device;

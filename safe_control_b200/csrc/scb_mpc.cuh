@@ -169,6 +169,29 @@ SCB_HD SimpleCon decode_simple(const scb_params& p, int H, int q) {
   return c;
 }
 
+// Optional per-phase cycle counters (device debug build, -DSCB_MPC_PROFILE): warp 0 of block 0 accumulates
+// clock64() deltas at phase boundaries into g_mpc_prof; read back with scb_debug_mpc_profile().
+#if defined(SCB_MPC_PROFILE) && defined(__CUDACC__)
+__device__ long long g_mpc_prof[24];
+SCB_HD long long prof_clock() {
+#if defined(__CUDA_ARCH__)
+  return clock64();
+#else
+  return 0;
+#endif
+}
+SCB_HD void prof_add(int i, long long& tlast) {
+#if defined(__CUDA_ARCH__)
+  if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t = clock64(); g_mpc_prof[i] += t - tlast; tlast = t; }
+#endif
+}
+#define SCB_PH(i) prof_add(i, tlast)
+#define SCB_PH_INIT long long tlast = prof_clock()
+#else
+#define SCB_PH(i) do { } while (0)
+#define SCB_PH_INIT do { } while (0)
+#endif
+
 template <int MODEL, int LANES>
 struct MpcSolver {
   using Mod = MpcModel<MODEL>;
@@ -356,32 +379,31 @@ struct MpcSolver {
 
   // weighted obstacle sums of stage k: which = 0 (sigma moments, 6) / 1 (lambda, 3) / 2 (rhs weights, 3)
   SCB_HD void stage_sums(double mu_bar, bool with_rhs) {
-    const int per = 12;
-    for (int t = lane; t < H * per; t += LANES) {
-      const int k = t / per, q = t - k * per;
-      if (q >= 9 && !with_rhs) continue;
-      const double* s = w + L.S + k * M;
-      const double* lam = w + L.L + k * M;
-      const double* c = w + L.C + k * M;
-      double acc = 0.0;
-      for (int j = 0; j < M; ++j) {
-        const double* ob = w + L.OB + j * 3;
-        double wt;
-        if (q < 6) wt = lam[j] / s[j];
-        else if (q < 9) wt = lam[j];
-        else wt = mu_bar / s[j] - (lam[j] / s[j]) * (c[j] - s[j]);
-        double f;
-        switch (q) {
-          case 0: case 6: case 9: f = 1.0; break;
-          case 1: case 7: case 10: f = ob[0]; break;
-          case 2: case 8: case 11: f = ob[1]; break;
-          case 3: f = ob[0] * ob[0]; break;
-          case 4: f = ob[0] * ob[1]; break;
-          default: f = ob[1] * ob[1]; break;
+    // lanes own obstacles (registers hold ox, oy), loop over stages, 12 partial sums per stage reduced by
+    // xor-shuffles: one division per (stage, obstacle), no divergent per-sum code paths
+    for (int k = 0; k < H; ++k) {
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, l0 = 0, l1 = 0, l2 = 0, r0 = 0, r1 = 0, r2 = 0;
+      for (int j = lane; j < M; j += LANES) {
+        const double ox = w[L.OB + j * 3], oy = w[L.OB + j * 3 + 1];
+        const double s = w[L.S + k * M + j], lam = w[L.L + k * M + j];
+        const double inv = 1.0 / s, sig = lam * inv;
+        a0 += sig; a1 = fma(sig, ox, a1); a2 = fma(sig, oy, a2);
+        a3 = fma(sig * ox, ox, a3); a4 = fma(sig * ox, oy, a4); a5 = fma(sig * oy, oy, a5);
+        l0 += lam; l1 = fma(lam, ox, l1); l2 = fma(lam, oy, l2);
+        if (with_rhs) {
+          const double wt = mu_bar * inv - sig * (w[L.C + k * M + j] - s);
+          r0 += wt; r1 = fma(wt, ox, r1); r2 = fma(wt, oy, r2);
         }
-        acc = fma(wt, f, acc);
       }
-      w[L.SUM + t] = acc;
+      a0 = G::sum(a0); a1 = G::sum(a1); a2 = G::sum(a2); a3 = G::sum(a3); a4 = G::sum(a4); a5 = G::sum(a5);
+      l0 = G::sum(l0); l1 = G::sum(l1); l2 = G::sum(l2);
+      if (with_rhs) { r0 = G::sum(r0); r1 = G::sum(r1); r2 = G::sum(r2); }
+      if (lane == 0) {
+        double* sm = w + L.SUM + k * 12;
+        sm[0] = a0; sm[1] = a1; sm[2] = a2; sm[3] = a3; sm[4] = a4; sm[5] = a5;
+        sm[6] = l0; sm[7] = l1; sm[8] = l2;
+        if (with_rhs) { sm[9] = r0; sm[10] = r1; sm[11] = r2; }
+      }
     }
     sync();
   }
@@ -510,51 +532,49 @@ struct MpcSolver {
     return (k < H && c == k * NU + (a - NX)) ? 1.0 : 0.0;
   }
 
-  // reduced Hessian  Hr = H_R + sum_k Sy_k' G_k Sy_k   (lower triangle filled, then mirrored)
+  // reduced Hessian  Hr = H_R + sum_k Sy_k' G_k Sy_k  (lower triangle).  Lane c owns COLUMN c (rows r >= c):
+  // it forms t = G_k Sy_k[:, c] in registers and accumulates Sy_k[:, r] . t down its column, stage after
+  // stage -- no shared scratch, no barrier between stages, reads of Sy_k[:, r] are warp broadcasts.
   SCB_HD void reduced_hessian() {
     double* Hr = w + L.HR;
-    double* T = w + L.T;
-    for (int t = lane; t < n * n; t += LANES) Hr[t] = 0.0;
-    sync();
-    for (int t = lane; t < n; t += LANES) {
-      const int k = t / NU, i = t - k * NU;
-      Hr[t * n + t] = (k + 1 < H) ? 4.0 * Rs[i] : 2.0 * Rs[i];
-      if (k + 1 < H) { Hr[(t + NU) * n + t] = -2.0 * Rs[i]; }
-    }
-    sync();
-    for (int k = 0; k <= H; ++k) {
-      const double* Gk = w + L.G + k * NH;
-      const int ncol = (k < H) ? (k + 1) * NU : n;       // columns of Sy_k that can be non-zero
-      const int ny = (k < H) ? NY : NX;
-      // T = G_k Sy_k   (ny x ncol), lanes over columns
-      for (int c = lane; c < ncol; c += LANES) {
-        double sc[NY];
+    const double* S = w + L.SEN;
+    for (int c = lane; c < n; c += LANES) {
+      const int kc = c / NU, ic = c - kc * NU;
+      for (int r = c; r < n; ++r) Hr[r * n + c] = 0.0;
+      Hr[c * n + c] = (kc + 1 < H) ? 4.0 * Rs[ic] : 2.0 * Rs[ic];
+      if (kc + 1 < H) Hr[(c + NU) * n + c] = -2.0 * Rs[ic];
+      for (int k = kc; k <= H; ++k) {               // Sy_k[:, c] == 0 for k < kc
+        const double* Gk = w + L.G + k * NH;
+        const int ncol = (k < H) ? (k + 1) * NU : n;
+        double sc[NY], tc[NY];
 #pragma unroll
-        for (int a = 0; a < NY; ++a) sc[a] = (a < ny) ? sy(k, a, c) : 0.0;
+        for (int a = 0; a < NX; ++a) sc[a] = S[(k * NX + a) * n + c];
+#pragma unroll
+        for (int a = NX; a < NY; ++a) sc[a] = (k < H && k == kc && a - NX == ic) ? 1.0 : 0.0;
 #pragma unroll
         for (int a = 0; a < NY; ++a) {
           double v = 0.0;
 #pragma unroll
-          for (int b = 0; b < NY; ++b) {
-            const int lo = a < b ? a : b, hi = a < b ? b : a;
-            v = fma(Gk[hidx<NY>(lo, hi)], sc[b], v);
+          for (int bb = 0; bb < NY; ++bb) {
+            const int lo = a < bb ? a : bb, hi = a < bb ? bb : a;
+            v = fma(Gk[lo * NY - (lo * (lo - 1)) / 2 + (hi - lo)], sc[bb], v);
           }
-          T[a * n + c] = (a < ny) ? v : 0.0;
+          tc[a] = v;
+        }
+        for (int r = c; r < ncol; ++r) {
+          double v = 0.0;
+#pragma unroll
+          for (int a = 0; a < NX; ++a) v = fma(S[(k * NX + a) * n + r], tc[a], v);
+          if (k < H && r >= k * NU) {
+            const int ir = r - k * NU;
+#pragma unroll
+            for (int a = 0; a < NU; ++a) if (a == ir) v += tc[NX + a];
+          }
+          Hr[r * n + c] += v;
         }
       }
-      sync();
-      // Hr[r][c] += Sy_k[:, r] . T[:, c]  for r >= c, lanes over (r, c)
-      for (int t = lane; t < ncol * ncol; t += LANES) {
-        const int r = t / ncol, c = t - r * ncol;
-        if (r < c) continue;
-        double v = 0.0;
-#pragma unroll
-        for (int a = 0; a < NY; ++a)
-          if (a < ny) v = fma(sy(k, a, r), T[a * n + c], v);
-        Hr[r * n + c] += v;
-      }
-      sync();
     }
+    sync();
   }
 
   // Cholesky of (Hr + delta I) into LC (lower); returns false on a non-positive pivot
@@ -569,7 +589,7 @@ struct MpcSolver {
       if (!(d > 1e-300) || !(d < 1e300)) { ok = false; break; }
       const double dj = sqrt(d), inv = 1.0 / dj;
       sync();
-      if (lane == 0) Lc[j * n + j] = dj;
+      if (lane == 0) Lc[j * n + j] = inv;        // the DIAGONAL holds 1/L_jj (solves multiply instead of divide)
       for (int i = j + 1 + lane; i < n; i += LANES) {
         double v = Hr[i * n + j];
         for (int t = 0; t < j; ++t) v -= Lc[i * n + t] * Lc[j * n + t];
@@ -588,12 +608,12 @@ struct MpcSolver {
       for (int i = 0; i < n; ++i) {
         double v = rhs[i];
         for (int t = 0; t < i; ++t) v -= Lc[i * n + t] * dz[t];
-        dz[i] = v / Lc[i * n + i];
+        dz[i] = v * Lc[i * n + i];
       }
       for (int i = n - 1; i >= 0; --i) {
         double v = dz[i];
         for (int t = i + 1; t < n; ++t) v -= Lc[t * n + i] * dz[t];
-        dz[i] = v / Lc[i * n + i];
+        dz[i] = v * Lc[i * n + i];
       }
     }
     sync();
@@ -668,12 +688,16 @@ struct MpcSolver {
     int it = 0, st = SCB_MAXITER, it_best = 0, tiny_steps = 0;
     double err = kInf, err_best = kInf;
     const int max_iter = p.mpc_max_iter > 0 ? p.mpc_max_iter : 150;
+    SCB_PH_INIT;
     for (; it < max_iter; ++it) {
       stage_derivatives();
+      SCB_PH(0);
       stage_sums(mu_bar, false);
+      SCB_PH(1);
       stage_gradients(false, mu_bar);
       adjoint(w + L.GAM, w + L.RD);                 // costates + d/dz of (J_stage - lam' g)
       rate_gradient(w + L.Z, w + L.RG);
+      SCB_PH(2);
       // residuals (e_p = constraint violation, e_c = complementarity)
       double e_d = 0.0, e_p = 0.0, e_c = 0.0, e_cm = 0.0, lam_max = 0.0;
       for (int t = lane; t < n; t += LANES) e_d = fmax(e_d, fabs(w[L.RD + t] + w[L.RG + t]));
@@ -710,17 +734,22 @@ struct MpcSolver {
       if (nu_pen > 1e12) { st = SCB_INFEASIBLE; break; }
       const double floor_s = mu_bar / nu_pen;
       reset_slacks(floor_s);
+      SCB_PH(3);
       // Newton system: exact Lagrangian Hessian first; if the reduced matrix is not positive definite,
       // fall back to the Gauss-Newton stage Hessians (PSD by construction) before any diagonal shift
       stage_sums(mu_bar, true);
       gauss_newton = false;
       stage_hessians();
+      SCB_PH(4);
       stage_gradients(true, mu_bar);
       adjoint(w + L.GAM, w + L.RHS);                // (costates of the first sweep were consumed by stage_hessians)
       for (int t = lane; t < n; t += LANES) w[L.RHS + t] -= w[L.RG + t];
       sync();
+      SCB_PH(5);
       sensitivities();
+      SCB_PH(6);
       reduced_hessian();
+      SCB_PH(7);
       double delta = 0.0;
       bool pd = cholesky(0.0);
       if (!pd) {
@@ -734,6 +763,7 @@ struct MpcSolver {
         if (delta == 0.0) delta = -1.0;             // marks "Gauss-Newton step" in traces
       }
       if (!pd) { st = SCB_NUMERICAL; break; }
+      SCB_PH(8);
       chol_solve(w + L.RHS, w + L.DZ);
       // stage directions dy_k = Sy_k dz
       for (int t = lane; t < (H + 1) * NY; t += LANES) {
@@ -746,6 +776,7 @@ struct MpcSolver {
         w[L.DY + t] = v;
       }
       sync();
+      SCB_PH(9);
       // linearised constraint change dg (stored in DS), multiplier direction, fraction to the boundary,
       // and the directional derivative of the merit
       const double tau = fmax(0.99, 1.0 - mu_bar);
@@ -779,6 +810,7 @@ struct MpcSolver {
       }
       ap = G::vmin(ap); ad = G::vmin(ad);
       dpsi = G::sum(dpsi);
+      SCB_PH(10);
       // directional derivative of the cost: grad J . dz = sum_k grad l_k . dy_k + rate_grad . dz
       double dJ = 0.0;
       for (int t = lane; t < (H + 1) * NX; t += LANES) {
@@ -803,6 +835,7 @@ struct MpcSolver {
         return G::sum(acc);
       };
       const double psi0 = merit_terms(w + L.C, w + L.Z, w + L.X) + Jcur;
+      SCB_PH(11);
       // backtracking
       double alpha = ap, Jt = Jcur;
       int bt = 0;
@@ -821,6 +854,7 @@ struct MpcSolver {
       printf("[mpc] it=%3d J=%.6f ed=%.2e ep=%.2e ec=%.2e mu=%.1e ap=%.2e ad=%.2e alpha=%.2e bt=%d delta=%.1e dpsi=%.2e nu=%.2e\n", it, Jcur, e_d, e_p, e_c,
              mu_bar, ap, ad, alpha, bt, delta, dpsi, nu_pen);
 #endif
+      SCB_PH(12);
       tiny_steps = (alpha < 1e-10) ? tiny_steps + 1 : 0;
       if (tiny_steps >= 5) { st = (e_p > 1e-6) ? SCB_INFEASIBLE : SCB_MAXITER; break; }
       // accept: z, x, g; multipliers move with their own step and are kept within kappa_Sigma of mu/g
@@ -843,6 +877,7 @@ struct MpcSolver {
       }
       Jcur = Jt;
       sync();
+      SCB_PH(13);
     }
     // outputs
     if (lane == 0) {
