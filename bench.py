@@ -51,6 +51,15 @@ def algorithmic_bytes(w):
     return 8 * (nx + nu + 7 * M + nu) + 4 + 8 * ((M + 2 * nu + 63) // 64)
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read+write per launch from the committed ncu capture of this kernel (profiles/r1_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
 def hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -132,19 +141,31 @@ def _cpu_solve_range(args):
     return hi - lo, time.perf_counter() - t0
 
 
-def cpu_rate(w, sc, n_agents, procs):
-    """agent-steps/s of the oracle port on `procs` host processes over the first n_agents agents."""
-    n_agents = min(n_agents, sc["X"].shape[0])
+_POOL = {}
+
+
+def _close_pools():
+    for pool in _POOL.values():
+        pool.close(); pool.join()
+    _POOL.clear()
+
+
+def cpu_rate(w, sc, n_agents, procs, offset=0):
+    """agent-steps/s of the oracle port on `procs` host processes over agents [offset, offset + n_agents)."""
+    n_tot = sc["X"].shape[0]
+    offset = offset % max(n_tot - n_agents + 1, 1)
+    n_agents = min(n_agents, n_tot)
     if procs <= 1:
-        n, dt = _cpu_solve_range((w, sc, 0, n_agents))
+        n, dt = _cpu_solve_range((w, sc, offset, offset + n_agents))
         return n / dt, n, dt
     import multiprocessing as mp
-    bounds = np.linspace(0, n_agents, procs + 1).astype(int)
+    if procs not in _POOL:
+        _POOL[procs] = mp.get_context("fork").Pool(procs)      # created once; workers import the oracle lazily
+    bounds = offset + np.linspace(0, n_agents, procs + 1).astype(int)
     small = {k: sc[k] for k in ("spec", "X", "U_ref", "OBS", "nobs", "goal", "u_prev")}
-    with mp.get_context("fork").Pool(procs) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_solve_range, [(w, small, int(bounds[j]), int(bounds[j + 1])) for j in range(procs)])
-        dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    res = _POOL[procs].map(_cpu_solve_range, [(w, small, int(bounds[j]), int(bounds[j + 1])) for j in range(procs)])
+    dt = time.perf_counter() - t0
     n = sum(r[0] for r in res)
     return n / dt, n, dt
 
@@ -169,36 +190,42 @@ def main():
     from safe_control_b200 import scenes
 
     if args.impl == "reference":
+        # The reference's own CPU implementation of this path (cvxpy->GUROBI, do-mpc->IPOPT) cannot be installed
+        # (no network, no wheels); this arm times the reference-equivalent CPU path: the oracle port, one agent at
+        # a time per process like tracking.py:control_step, on every host core.  One "step" = a bounded sample of
+        # the workload (per_step agents); value = agent-steps/s over the K timed steps.
         if rank != 0:
             return
         procs = os.cpu_count() or 1
-        n_s = cpu_sample_size(w) * (2 if procs > 4 else 1)
-        sc = scenes.make_scene(w["model"], min(n_s, max(n_s, w["N"])), w["M"], seed=1234, dynamic=w["dynamic"],
+        per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 1}[w["controller"]] * procs
+        budget_s = 150.0
+        n_scene = min(max(per_step * 8, 2048), 16384)
+        sc = scenes.make_scene(w["model"], n_scene, w["M"], seed=1234, dynamic=w["dynamic"],
                                optimal_decay=w["controller"] == "optimal_decay_cbf_qp")
-        per_step = max(procs * 8, n_s // max(args.steps + args.warmup, 1))
-        per_step = min(per_step, n_s)
-        for _ in range(min(args.warmup, 1)):
-            cpu_rate(w, sc, per_step, procs)
-        t_tot, n_tot = 0.0, 0
-        budget = 120.0
-        for s in range(args.steps):
-            r, n, dt = cpu_rate(w, sc, per_step, procs)
-            t_tot += dt; n_tot += n
-            if t_tot > budget:
+        for k in range(max(1, min(args.warmup, 3))):
+            cpu_rate(w, sc, per_step, procs, offset=k * per_step)
+        t_tot, n_tot, done = 0.0, 0, 0
+        for k in range(args.steps):
+            r, n, dt = cpu_rate(w, sc, per_step, procs, offset=(k + 3) * per_step)
+            t_tot += dt; n_tot += n; done += 1
+            if t_tot > budget_s:
                 break
         val = n_tot / t_tot
-        sample = f"{n_tot} agent-steps of the {w['name']} scene (seed 1234), oracle port, {procs} processes"
+        sample = (f"{done} steps x {per_step} agents of the {w['name']} scene (seed 1234), oracle port (numpy/scipy), "
+                  f"{procs} processes" + ("" if done == args.steps else f"; stopped at the {budget_s:.0f} s budget"))
         print(json.dumps({
             "impl": "reference", "metric": "control-steps/sec (batched QP solves/s)", "value": val, "unit": "control-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * w["N"] / val,
+            "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step": w["N"], "obstacles": w["M"]},
+            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step": per_step, "obstacles": w["M"],
+                       "horizon": w["H"]},
             "cpu_baseline": {"value": val, "unit": "control-steps/s", "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "reference's cvxpy/GUROBI + do-mpc/IPOPT stack is not installable here (no network); this is the "
-                    "oracle restatement driven one agent at a time like tracking.py:control_step",
+            "note": "reference's cvxpy/GUROBI + do-mpc/IPOPT stack is not installable here (no network, no wheels); this is "
+                    "the oracle restatement driven one agent at a time like tracking.py:control_step",
         }))
+        _close_pools()
         return
 
     import torch
@@ -367,9 +394,11 @@ def main():
             "e2e_gpu_launches": e2e_launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms, "kernel_ms_how": "CUDA-graph replay of the timed steps / steps (median of 5), includes the inter-kernel dependency gap",
+                         "traffic": ncu_traffic(w["name"]), "peak_source": peak_src, "kernel_ms": k_ms, "kernel_ms_how": "CUDA-graph replay of the timed steps / steps (median of 5), includes the inter-kernel dependency gap",
                          "algorithmic_bytes_per_agent": B, "agents_per_launch": N,
-                         "note": "one launch covers only 1024 agents (~1 MB): latency-bound, see large_batch",
+                         "note": ("the MPC path is FP64-compute/latency bound (iterative NLP solve per agent), HBM traffic is negligible; see DESIGN.md 3.3"
+                                  if w["controller"] == "mpc_cbf" else
+                                  f"one launch covers only {N} agents ({B * N / 1e6:.1f} MB): latency-bound; large_batch shows the same kernel on 1M agents"),
                          "large_batch": big},
         }
         if not args.no_cpu:
