@@ -14,9 +14,12 @@
 namespace scb {
 
 constexpr int kBlock = 128;
+#ifndef SCB_QP_MINBLOCKS
+#define SCB_QP_MINBLOCKS 1          // __launch_bounds__ min CTAs/SM for the QP kernels (register cap); tuned on B200
+#endif
 
 template <int MODEL, int LANES, int RPL>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, SCB_QP_MINBLOCKS)
 cbfqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
              const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
              const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,

@@ -7,14 +7,16 @@ t = lambda a: torch.from_numpy(a).cuda()
 M = 16
 base = scenes.make_scene("DynamicUnicycle2D", 1 << 18, M, seed=1234)
 ctrl = BatchedCBFQP(base["spec"], num_obs=M)
-for N in (1024, 8192, 65536, 1 << 20):
+SIZES = [int(x) for x in os.environ.get('SWEEP_N', '1024,8192,65536,1048576').split(',')]
+LANES = [int(x) for x in os.environ.get('SWEEP_LANES', '32,8,4').split(',')]
+for N in SIZES:
     rep = max(1, N // (1 << 18))
     pool = 8 if N <= 65536 else 2
     ins = []
     for q in range(pool):
         sl = slice((q * N) % (1 << 18), (q * N) % (1 << 18) + min(N, 1 << 18))
         ins.append([t(np.tile(base[k][sl], (rep,) + (1,) * (base[k].ndim - 1))) for k in ("X", "U_ref", "OBS", "nobs")])
-    for lanes in (32, 8, 4):
+    for lanes in LANES:
         os.environ["SCB_QP_LANES"] = str(lanes)
         for q in range(3):
             ctrl.solve(*ins[q % pool])
