@@ -47,11 +47,11 @@ struct MpcModel;
 // Relative degree 1: cbf = d_h + alpha h_k (mpc_cbf.py:312-315).
 template <>
 struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
-  static constexpr int NX = 2, NU = 2, NY = 4, REL = 1;
-  static constexpr bool VBOUND = false;
+  static constexpr int NX = 2, NU = 2, NY = 4, REL = 1, NGOAL = 2, AUX = 0;
+  static constexpr bool VBOUND = false, LINEAR = false;
   static SCB_HD double beta() { return 1.01; }
   template <class T>
-  static SCB_HD void stage(const scb_params& p, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
     jaxpy(F[0], y[0], p.dt, y[2]);
     jaxpy(F[1], y[1], p.dt, y[3]);
     P1 = F[0]; Q1 = F[1]; P2 = F[0]; Q2 = F[1];
@@ -61,12 +61,12 @@ struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
 // DynamicUnicycle2D: f, g robots/dynamic_unicycle2D.py:42-73, step :75-78, barrier_dt :188-238
 template <>
 struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
-  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2;
-  static constexpr bool VBOUND = true;
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0;
+  static constexpr bool VBOUND = true, LINEAR = false;
   static SCB_HD double beta() { return 1.01; }
   // y = (px, py, theta, v, a, omega).  F = Euler map; (P1,Q1), (P2,Q2) = positions after 1 and 2 own steps.
   template <class T>
-  static SCB_HD void stage(const scb_params& p, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
     T s, c, vc, vs;
     jsincos(s, c, y[2]);
     jmul(vc, y[3], c); jmul(vs, y[3], s);
@@ -86,8 +86,8 @@ struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
 // KinematicBicycle2D: f, g robots/kinematic_bicycle2D.py:75-110, step (clips v) :112-123, barrier_dt :175-199
 template <>
 struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
-  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2;
-  static constexpr bool VBOUND = true;
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0;
+  static constexpr bool VBOUND = true, LINEAR = false;
   static SCB_HD double beta() { return 1.1; }
   template <class T>
   static SCB_HD void euler(const scb_params& p, const T& px, const T& py, const T& th, const T& v, const T& a,
@@ -105,7 +105,7 @@ struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
     jaxpy(F[3], v, p.dt, a);
   }
   template <class T>
-  static SCB_HD void stage(const scb_params& p, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
     euler(p, y[0], y[1], y[2], y[3], y[4], y[5], F);
     P1 = F[0]; Q1 = F[1];
     T v1, G[4];
@@ -115,16 +115,88 @@ struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
   }
 };
 
+// Quad3D: linear 12-state model xdot = A x + B u (robots/quad3D.py:81-97); the MPC uses plain Euler
+// (mpc_cbf.py:135-141) while the barrier uses the model's own RK4 step (quad3D.py:121-158, 275-297), which for a
+// linear system is the constant affine map x1 = Ad x + Bd u.  Relative degree 1: cbf = d_h + alpha h_k.  Because
+// everything is linear the stage derivatives are written down directly (no jets); per-agent constants live in
+// the AUX block: Ae = I + dt A (12x12), Be = dt B (12x4), rows 0 and 1 of [Ad | Bd] (2 x 16).
+template <>
+struct MpcModel<SCB_QUAD_3D> {
+  static constexpr int NX = 12, NU = 4, NY = 16, REL = 1, NGOAL = 3, AUX = 144 + 48 + 32;
+  static constexpr bool VBOUND = false, LINEAR = true;
+  static SCB_HD double beta() { return 1.01; }
+
+  static SCB_HD void setup_aux(const scb_params& p, double* aux) {
+    double A[144], B[48];
+    for (int i = 0; i < 144; ++i) A[i] = 0.0;
+    for (int i = 0; i < 48; ++i) B[i] = 0.0;
+    for (int i = 0; i < 6; ++i) A[i * 12 + 6 + i] = 1.0;
+    A[6 * 12 + 3] = p.gravity; A[7 * 12 + 4] = -p.gravity;
+    // B = B1 B2 (quad3D.py:70-97)
+    const double L = p.arm_L, nu = p.nu_coef;
+    const double B2[4][4] = {{1, 1, 1, 1}, {0, L, 0, -L}, {L, 0, -L, 0}, {nu, -nu, nu, -nu}};
+    const double b1[4] = {1.0 / p.mass, 1.0 / p.Iy, 1.0 / p.Ix, 1.0 / p.Iz};
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) B[(8 + r) * 4 + c] = b1[r] * B2[r][c];
+    double* Ae = aux; double* Be = aux + 144; double* R = aux + 192;
+    for (int i = 0; i < 12; ++i)
+      for (int j = 0; j < 12; ++j) Ae[i * 12 + j] = (i == j ? 1.0 : 0.0) + p.dt * A[i * 12 + j];
+    for (int i = 0; i < 48; ++i) Be[i] = p.dt * B[i];
+    // rows 0, 1 of Ad = sum_{m<=4} dt^m/m! A^m and Bd = (sum_{m<=3} dt^{m+1}/(m+1)! A^m) B
+    for (int row = 0; row < 2; ++row) {
+      double q[12], acc_a[12], acc_b[12];
+      for (int j = 0; j < 12; ++j) { q[j] = (j == row) ? 1.0 : 0.0; acc_a[j] = q[j]; acc_b[j] = p.dt * q[j]; }
+      double ca = 1.0, cb = p.dt;
+      for (int m = 1; m <= 4; ++m) {
+        double qn[12];
+        for (int j = 0; j < 12; ++j) {
+          double v = 0.0;
+          for (int t = 0; t < 12; ++t) v = fma(q[t], A[t * 12 + j], v);
+          qn[j] = v;
+        }
+        for (int j = 0; j < 12; ++j) q[j] = qn[j];
+        ca *= p.dt / m;
+        for (int j = 0; j < 12; ++j) acc_a[j] = fma(ca, q[j], acc_a[j]);
+        if (m <= 3) {
+          cb *= p.dt / (m + 1);
+          for (int j = 0; j < 12; ++j) acc_b[j] = fma(cb, q[j], acc_b[j]);
+        }
+      }
+      for (int j = 0; j < 12; ++j) R[row * 16 + j] = acc_a[j];
+      for (int c = 0; c < 4; ++c) {
+        double v = 0.0;
+        for (int t = 0; t < 12; ++t) v = fma(acc_b[t], B[t * 4 + c], v);
+        R[row * 16 + 12 + c] = v;
+      }
+    }
+  }
+
+  // plain-value stage map (rollout / line search)
+  static SCB_HD void stage(const scb_params&, const double* aux, const double* y, double* F, double& P1, double& Q1,
+                           double& P2, double& Q2) {
+    const double* Ae = aux; const double* Be = aux + 144; const double* R = aux + 192;
+    for (int i = 0; i < 12; ++i) {
+      double v = 0.0;
+      for (int j = 0; j < 12; ++j) v = fma(Ae[i * 12 + j], y[j], v);
+      for (int j = 0; j < 4; ++j) v = fma(Be[i * 4 + j], y[12 + j], v);
+      F[i] = v;
+    }
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < 16; ++j) { a = fma(R[j], y[j], a); b = fma(R[16 + j], y[j], b); }
+    P1 = a; Q1 = b; P2 = a; Q2 = b;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // workspace layout (in doubles), computed identically on host and device
 struct MpcLayout {
   int H, M, n, NS;
   int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, RHS, DZ, SEN,
-      T, HR, LC, DY, ZT, XT, RG;
+      HR, LC, DY, ZT, XT, RG, AUX;
   int total;
 };
 
-template <int NX, int NU, bool VBOUND>
+template <int NX, int NU, bool VBOUND, bool LINEAR = false, int AUXN = 0>
 SCB_HD MpcLayout mpc_layout(int H, int M) {
   constexpr int NY = NX + NU, NH = NY * (NY + 1) / 2;
   MpcLayout L;
@@ -133,7 +205,8 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   auto take = [&](int cnt) { int r = o; o += cnt; return r; };
   L.X = take((H + 1) * NX);  L.Z = take(H * NU);
   L.A = take(H * NX * NX);   L.B = take(H * NX * NU);
-  L.FH = take(H * NX * NH);
+  L.FH = take(LINEAR ? 0 : H * NX * NH);
+  L.AUX = take(AUXN);
   L.JE = take(H * (NY + NH)); L.JX = take(H * (NY + NH)); L.JY = take(H * (NY + NH));
   L.PT = take(H * 6);        L.OB = take(M * 3);
   L.C = take(H * M); L.S = take(H * M); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
@@ -143,7 +216,6 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   L.MU = take((H + 1) * NX);
   L.RD = take(L.n); L.RHS = take(L.n); L.DZ = take(L.n);
   L.SEN = take((H + 1) * NX * L.n);
-  L.T = take(NY * L.n);
   L.HR = take(L.n * L.n); L.LC = take(L.n * L.n);
   L.DY = take((H + 1) * NY);
   L.ZT = take(L.n); L.XT = take((H + 1) * NX); L.RG = take(L.n);
@@ -249,7 +321,7 @@ struct MpcSolver {
       for (int i = 0; i < NX; ++i) y[i] = x[i];
 #pragma unroll
       for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
-      Mod::stage(p, y, F, a, b, c, d);
+      Mod::stage(p, w + L.AUX, y, F, a, b, c, d);
 #pragma unroll
       for (int i = 0; i < NX; ++i) { x[i] = F[i]; xs[(k + 1) * NX + i] = F[i]; }
     }
@@ -266,7 +338,7 @@ struct MpcSolver {
       for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
 #pragma unroll
       for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
-      Mod::stage(p, y, F, P1, Q1, P2, Q2);
+      Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
       double* pt = w + L.PT + k * 6;
       pt[0] = y[0]; pt[1] = y[1]; pt[2] = P1; pt[3] = Q1; pt[4] = P2; pt[5] = Q2;
     }
@@ -296,13 +368,49 @@ struct MpcSolver {
   SCB_HD void stage_derivatives() {
     const double* xs = w + L.X;
     const double* z = w + L.Z;
+    if constexpr (Mod::LINEAR) {
+      // linear model: A, B constant; barrier points affine in y -> E has a constant Hessian, PX/PY none
+      const double* aux = w + L.AUX;
+      const double* R0 = aux + NX * NX + NX * NU;
+      const double* R1 = R0 + NY;
+      for (int k = lane; k < H; k += LANES) {
+        double y[NY];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
+        double* A = w + L.A + k * NX * NX;
+        double* B = w + L.B + k * NX * NU;
+        for (int t = 0; t < NX * NX; ++t) A[t] = aux[t];
+        for (int t = 0; t < NX * NU; ++t) B[t] = aux[NX * NX + t];
+        double P1 = 0.0, Q1 = 0.0;
+        for (int i = 0; i < NY; ++i) { P1 = fma(R0[i], y[i], P1); Q1 = fma(R1[i], y[i], Q1); }
+        double* je = w + L.JE + k * (NY + NH);
+        double* jx = w + L.JX + k * (NY + NH);
+        double* jy = w + L.JY + k * (NY + NH);
+        int t = 0;
+        for (int i = 0; i < NY; ++i) {
+          const double d0 = (i == 0) ? 1.0 : 0.0, d1 = (i == 1) ? 1.0 : 0.0;
+          je[i] = 2.0 * w0 * (y[0] * d0 + y[1] * d1) + 2.0 * w1 * (P1 * R0[i] + Q1 * R1[i]);
+          jx[i] = 2.0 * w0 * d0 + 2.0 * w1 * R0[i];
+          jy[i] = 2.0 * w0 * d1 + 2.0 * w1 * R1[i];
+          for (int j = i; j < NY; ++j, ++t) {
+            const double e0 = (j == 0) ? 1.0 : 0.0, e1 = (j == 1) ? 1.0 : 0.0;
+            je[NY + t] = 2.0 * w0 * (d0 * e0 + d1 * e1) + 2.0 * w1 * (R0[i] * R0[j] + R1[i] * R1[j]);
+            jx[NY + t] = 0.0; jy[NY + t] = 0.0;
+          }
+        }
+      }
+      sync();
+      return;
+    } else {
     for (int k = lane; k < H; k += LANES) {
       J y[NY], F[NX], P1, Q1, P2, Q2;
 #pragma unroll
       for (int i = 0; i < NX; ++i) jvar(y[i], xs[k * NX + i], i);
 #pragma unroll
       for (int i = 0; i < NU; ++i) jvar(y[NX + i], z[k * NU + i], NX + i);
-      Mod::stage(p, y, F, P1, Q1, P2, Q2);
+      Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
       double* A = w + L.A + k * NX * NX;
       double* B = w + L.B + k * NX * NU;
       double* FH = w + L.FH + k * NX * NH;
@@ -331,6 +439,7 @@ struct MpcSolver {
       for (int i = 0; i < NH; ++i) { je[NY + i] = E.h[i]; jx[NY + i] = PX.h[i]; jy[NY + i] = PY.h[i]; }
     }
     sync();
+    }
   }
 
   // gradient of the input-rate term sum R (u_k - u_{k-1})^2 at z -> out[n]
@@ -475,7 +584,7 @@ struct MpcSolver {
         v += sm[0] * ei * ej - sm[1] * (ei * xj + xi * ej) - sm[2] * (ei * yj + yi * ej) + sm[3] * xi * xj +
              sm[4] * (xi * yj + yi * xj) + sm[5] * yi * yj;
         // + sum_c mu_{k+1,c} hess F_c
-        if (!gauss_newton) {
+        if (!Mod::LINEAR && !gauss_newton) {
           const double* FH = w + L.FH + k * NX * NH;
           const double* mu = w + L.MU + (k + 1) * NX;
 #pragma unroll
@@ -627,6 +736,10 @@ struct MpcSolver {
 #pragma unroll
     for (int i = 0; i < NU; ++i) uprev[i] = ld(up + i);
     const double beta = Mod::beta();
+    if constexpr (Mod::LINEAR) {
+      if (lane == 0) Mod::setup_aux(p, w + L.AUX);
+      sync();
+    }
     // obstacles: (ox, oy, beta d^2); missing slots = the reference's dummy [1000, 1000, 0, ...] (mpc_cbf.py:346-364)
     for (int j = lane; j < M; j += LANES) {
       double ox = 1000.0, oy = 1000.0, r = 0.0;
@@ -909,11 +1022,11 @@ SCB_HD void mpc_agent(const scb_params& p, int H, int M, int nobs, const double*
                       const double* uprev, const double* obs, double* workspace, double* U, int32_t* status,
                       double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
   using Mod = MpcModel<MODEL>;
-  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND>(H, M);
+  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX>(H, M);
   MpcSolver<MODEL, LANES> s(p, L, workspace);
   if (nobs < 0) nobs = 0;
   if (nobs > M) nobs = M;
-  s.solve(nobs, x0, goal, 2, uprev, obs, U, status, pred_x, pred_u, iters, kkt);
+  s.solve(nobs, x0, goal, Mod::NGOAL, uprev, obs, U, status, pred_x, pred_u, iters, kkt);
 }
 
 }  // namespace scb

@@ -42,7 +42,7 @@ __global__ void mpc_kernel(const __grid_constant__ scb_params p, int N, int M, i
       }
       continue;
     }
-    mpc_agent<MODEL, LANES>(p, H, M, nobs ? nobs[a] : M, X + a * NX, goal + a * 2, u_prev + a * NU, OBS + a * stride, ws,
+    mpc_agent<MODEL, LANES>(p, H, M, nobs ? nobs[a] : M, X + a * NX, goal + a * Mod::NGOAL, u_prev + a * NU, OBS + a * stride, ws,
                             U + a * NU, status + a, pred_x ? pred_x + a * (H + 1) * NX : nullptr,
                             pred_u ? pred_u + a * H * NU : nullptr, iters ? iters + a : nullptr,
                             kkt ? kkt + a : nullptr);
@@ -55,7 +55,7 @@ inline int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* 
                         const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
                         int32_t* iters, double* kkt, cudaStream_t s, int sm_count) {
   using Mod = MpcModel<MODEL>;
-  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND>(H, M);
+  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX>(H, M);
   const size_t per = (size_t)L.total * sizeof(double);
   const size_t budget = 220 * 1024;
   int gpb = (int)(budget / per);
@@ -81,7 +81,7 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X,
                       const double* u_prev, const int32_t* track, const double* OBS, long stride, const int32_t* nobs,
                       double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt,
                       cudaStream_t s, int sm_count) {
-  if (M > kMpcMaxObs || H > kMpcMaxH || H * p.nu > 32) return SCB_ERR_TOO_LARGE;
+  if (M > kMpcMaxObs || H > kMpcMaxH || H * p.nu > 64) return SCB_ERR_TOO_LARGE;
   switch (p.model) {
     case SCB_SINGLE_INTEGRATOR_2D:
       return mpc_launch_m<SCB_SINGLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
@@ -92,8 +92,11 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X,
     case SCB_KINEMATIC_BICYCLE_2D:
       return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
                                                     pred_x, pred_u, iters, kkt, s, sm_count);
+    case SCB_QUAD_3D:
+      return mpc_launch_m<SCB_QUAD_3D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
+                                       pred_u, iters, kkt, s, sm_count);
     default:
-      return SCB_ERR_UNSUPPORTED;     // round 1: circle-barrier SI / DU / KB only
+      return SCB_ERR_UNSUPPORTED;     // C3BF (collision-cone) barriers in MPC: not yet
   }
 }
 

@@ -98,10 +98,10 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
 #define MPCCASE(MODEL)                                                                                          \
   case MODEL: {                                                                                                 \
     using Mod = MpcModel<MODEL>;                                                                                \
-    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND>(H, M);                                        \
+    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX>(H, M);                                        \
     double* ws = new double[L.total];                                                                           \
     for (int t = 0; t < L.total; ++t) ws[t] = 0.0;                                                              \
-    mpc_agent<MODEL, 1>(*p, H, M, no, X + (size_t)i * nx, goal + (size_t)i * 2, u_prev + (size_t)i * nu,        \
+    mpc_agent<MODEL, 1>(*p, H, M, no, X + (size_t)i * nx, goal + (size_t)i * Mod::NGOAL, u_prev + (size_t)i * nu,        \
                         OBS + (size_t)i * stride, ws, U + (size_t)i * nu, status + i, px, pu,                   \
                         iters ? iters + i : nullptr, kkt ? kkt + i : nullptr);                                  \
     delete[] ws;                                                                                                \
@@ -109,6 +109,7 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
       MPCCASE(SCB_SINGLE_INTEGRATOR_2D)
       MPCCASE(SCB_DYNAMIC_UNICYCLE_2D)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D)
+      MPCCASE(SCB_QUAD_3D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }

@@ -14,7 +14,11 @@ def dev(a):
 
 def near_goal(sc, dist=3.0):
     X = sc["X"]
-    return X[:, :2] + dist * np.stack([np.cos(X[:, 2]), np.sin(X[:, 2])], 1)
+    th = X[:, 2] if X.shape[1] == 4 else np.zeros(len(X))
+    g = X[:, :2] + dist * np.stack([np.cos(th), np.sin(th)], 1)
+    if X.shape[1] == 12:
+        g = np.concatenate([g, X[:, 2:3]], axis=1)
+    return g
 
 
 def solve(ctrl, sc, goal, **kw):
@@ -28,10 +32,13 @@ def solve(ctrl, sc, goal, **kw):
     ("DynamicUnicycle2D", 256, 8, 16, True, 32),       # goals nearby: interior optima, CBF rows active
     ("KinematicBicycle2D", 128, 10, 64, False, 12),    # config-5 sized stage (H = 10, 64 obstacle slots)
     ("DynamicUnicycle2D", 64, 10, 64, True, 8),
+    ("SingleIntegrator2D", 128, 10, 16, False, 12),
+    ("Quad3D", 160, 10, 64, False, 8),                 # config-5's third model family
+    ("Quad3D", 64, 8, 16, True, 8),
 ])
 def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     from safe_control_b200 import BatchedMPCCBF, scenes
-    sc = scenes.make_scene(model, N, M, seed=1234)
+    sc = scenes.make_scene(model, N, M, seed=1234, dense=(model == "Quad3D" and near))
     goal = near_goal(sc) if near else sc["goal"]
     ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
     out = solve(ctrl, sc, goal)
@@ -44,12 +51,14 @@ def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     print(model, N, H, M, stats, "iters mean", out["iters"].mean(), "max", out["iters"].max(), "ok", frac_ok)
     # size-independent properties on the WHOLE batch: predictions satisfy the Euler model, inputs in the box
     U, px, pu = out["U"], out["pred_x"], out["pred_u"]
-    lb = np.array(list(ctrl.params.u_lb)[:2]); ub = np.array(list(ctrl.params.u_ub)[:2])
+    nu = ctrl.nu
+    lb = np.array(list(ctrl.params.u_lb)[:nu]); ub = np.array(list(ctrl.params.u_ub)[:nu])
     assert ((U >= lb - 1e-12) & (U <= ub + 1e-12)).all()
     ok = out["status"] == 0
     np.testing.assert_allclose(px[:, 0], sc["X"], atol=0)
     assert np.abs(pu[ok][:, 0] - U[ok]).max() < 1e-12
-    assert (np.abs(px[ok][:, :, 3]) <= ctrl.params.v_max + 1e-7).all()
+    if ctrl.nx == 4:
+        assert (np.abs(px[ok][:, :, 3]) <= ctrl.params.v_max + 1e-7).all()
 
 
 def test_mpc_track_mask_and_host_path():

@@ -10,16 +10,21 @@ from safe_control_b200 import scenes
 
 def near_goal(sc, dist=3.0):
     X = sc["X"]
-    th = X[:, 2] if X.shape[1] > 2 else np.zeros(len(X))
-    return X[:, :2] + dist * np.stack([np.cos(th), np.sin(th)], 1)
+    th = X[:, 2] if X.shape[1] == 4 else np.zeros(len(X))
+    g = X[:, :2] + dist * np.stack([np.cos(th), np.sin(th)], 1)
+    if X.shape[1] == 12:                       # Quad3D goals are (x, y, z)
+        g = np.concatenate([g, X[:, 2:3]], axis=1)
+    return g
 
 
 @pytest.mark.parametrize("model,N,H,M,near", [("DynamicUnicycle2D", 10, 8, 16, False),
                                                ("DynamicUnicycle2D", 8, 8, 16, True),
                                                ("KinematicBicycle2D", 6, 6, 8, False),
-                                               ("SingleIntegrator2D", 8, 10, 8, False)])
+                                               ("SingleIntegrator2D", 8, 10, 8, False),
+                                               ("Quad3D", 6, 6, 8, False),
+                                               ("Quad3D", 5, 5, 6, True)])
 def test_mpc_vs_oracle(model, N, H, M, near):
-    sc = scenes.make_scene(model, N, M, seed=4321)
+    sc = scenes.make_scene(model, N, M, seed=4321, dense=(model == "Quad3D" and near))
     goal = near_goal(sc) if near else sc["goal"]
     p, spec = resolve_params(sc["spec"], "mpc_cbf", lib=hostsim())
     out = hs_mpccbf_solve(p, H, sc["X"], goal, sc["u_prev"], sc["OBS"], sc["nobs"])
