@@ -338,49 +338,59 @@ SCB_HD void gi_solve2(double hd, double x0, double x1, const double (&r0)[RPL], 
     double lp = 0.0;
     const double pp = p0 * p0 + p1 * p1;            // 1 for a normalised row, 0 for a constant row
 
+    // All rows are unit-normal (pp == 1) or constant (pp == 0), so the Gram entries of the working set are 1 and
+    // every pivot needs ONE division: step lengths are compared by cross-multiplication before dividing.
     bool done = false;
     while (!done) {
       if (k == 0) {
         if (!(pp > 0.0)) { status = SCB_INFEASIBLE; break; }       // constant row b < 0
-        const double t = -sp / (hinv * pp);
-        x0 = fma(t * hinv, p0, x0); x1 = fma(t * hinv, p1, x1);
-        a00 = p0; a01 = p1; w0 = bi; l0 = t; k = 1;
+        // z = hinv p, t = -sp / (hinv pp)  ->  x += t z = -(sp / pp) p
+        const double step = -sp / pp;
+        x0 = fma(step, p0, x0); x1 = fma(step, p1, x1);
+        a00 = p0; a01 = p1; w0 = bi; l0 = step * hd; k = 1;
         done = true;
       } else if (k == 1) {
-        // r = (a0.p)/(a0.a0);  z = hinv (p - a0 r);  z.p = hinv (pp - (a0.p)^2/(a0.a0))
-        const double aa = a00 * a00 + a01 * a01;
-        const double ap = a00 * p0 + a01 * p1;
-        const double r = ap / aa;
-        const double z0 = hinv * fma(-r, a00, p0), z1 = hinv * fma(-r, a01, p1);
-        const double zap = z0 * p0 + z1 * p1;
-        const bool zzero = !(zap > 1e-9 * hinv * pp);
-        const double t1 = (r > 0.0) ? l0 / r : kInf;
-        const double t2 = zzero ? kInf : -sp / zap;
-        if (t1 >= kInf && t2 >= kInf) { status = SCB_INFEASIBLE; break; }
-        if (t2 <= t1) {
+        // r = a0.p (|a0| = 1);  z = hinv (p - r a0);  z.p = hinv (pp - r^2)
+        const double r = a00 * p0 + a01 * p1;
+        const double g = pp - r * r;                                // sin^2 of the angle between the rows
+        const bool zzero = !(g > 1e-9 * pp);
+        const double zap = hinv * g;
+        const bool has1 = r > 0.0;
+        if (!has1 && zzero) { status = SCB_INFEASIBLE; break; }
+        // full step iff t2 = -sp/zap <= t1 = l0/r   <=>   -sp r <= l0 zap   (r, zap > 0)
+        const bool full = !zzero && (!has1 || (-sp * r <= l0 * zap));
+        if (full) {
+          const double t2 = -sp / zap;
+          const double z0 = hinv * fma(-r, a00, p0), z1 = hinv * fma(-r, a01, p1);
           x0 = fma(t2, z0, x0); x1 = fma(t2, z1, x1);
           l0 = fmax(l0 - t2 * r, 0.0); lp += t2;
           a10 = p0; a11 = p1; w1 = bi; l1 = lp; k = 2;
           done = true;
         } else {
-          if (!zzero) { x0 = fma(t1, z0, x0); x1 = fma(t1, z1, x1); sp = fma(t1, zap, sp); }
+          const double t1 = l0 / r;
+          if (!zzero) {
+            const double z0 = hinv * fma(-r, a00, p0), z1 = hinv * fma(-r, a01, p1);
+            x0 = fma(t1, z0, x0); x1 = fma(t1, z1, x1); sp = fma(t1, zap, sp);
+          }
           lp += t1;
           w0 = -1; l0 = 0.0; k = 0;
           if (++it > max_iter) { status = SCB_MAXITER; break; }
         }
       } else {
-        // two working rows span the plane: z = 0, solve [a0;a1] hinv [a0;a1]' r = [a0;a1] hinv p
-        const double s00 = a00 * a00 + a01 * a01, s01 = a00 * a10 + a01 * a11, s11 = a10 * a10 + a11 * a11;
+        // two unit rows span the plane (z = 0): solve [[1,c],[c,1]] (ra, rb) = (q0, q1),  c = a0.a1
+        const double c = a00 * a10 + a01 * a11;
         const double q0 = a00 * p0 + a01 * p1, q1 = a10 * p0 + a11 * p1;
-        const double det = s00 * s11 - s01 * s01;
+        const double det = 1.0 - c * c;
         if (!(det > 0.0)) { status = SCB_NUMERICAL; break; }
-        const double ra = (s11 * q0 - s01 * q1) / det, rb2 = (s00 * q1 - s01 * q0) / det;
-        const double ta = (ra > 0.0) ? l0 / ra : kInf, tb = (rb2 > 0.0) ? l1 / rb2 : kInf;
-        if (ta >= kInf && tb >= kInf) { status = SCB_INFEASIBLE; break; }
-        const double t = fmin(ta, tb);
-        lp += t;
-        l0 = fmax(l0 - t * ra, 0.0); l1 = fmax(l1 - t * rb2, 0.0);
-        if (ta <= tb) { a00 = a10; a01 = a11; w0 = w1; l0 = l1; }   // drop row 0: row 1 moves down
+        const double na = q0 - c * q1, nb = q1 - c * q0;            // ra = na / det, rb = nb / det (same signs)
+        const bool pa = na > 0.0, pb = nb > 0.0;
+        if (!pa && !pb) { status = SCB_INFEASIBLE; break; }
+        // ta = l0 det / na, tb = l1 det / nb: pick the smaller by cross-multiplication, divide once
+        const bool drop_a = pa && (!pb || (l0 * nb <= l1 * na));
+        const double tq = drop_a ? l0 / na : l1 / nb;               // = t / det
+        lp += tq * det;
+        l0 = fmax(l0 - tq * na, 0.0); l1 = fmax(l1 - tq * nb, 0.0);
+        if (drop_a) { a00 = a10; a01 = a11; w0 = w1; l0 = l1; }     // drop row 0: row 1 moves down
         w1 = -1; l1 = 0.0; k = 1;
         if (++it > max_iter) { status = SCB_MAXITER; break; }
       }

@@ -14,12 +14,17 @@
 namespace scb {
 
 constexpr int kBlock = 128;
-#ifndef SCB_QP_MINBLOCKS
-#define SCB_QP_MINBLOCKS 1          // __launch_bounds__ min CTAs/SM for the QP kernels (register cap); tuned on B200
+// __launch_bounds__ min CTAs/SM (register cap) for the QP kernels, measured on B200 (tools/sweep_qp.py, M = 16):
+// warp-per-QP (latency regime, N = 1024): 4 -> 5.28 us, 6 -> 5.46 us;  4-8 lanes/QP (N = 1M): 4 -> 487/553 us,
+// 6 -> 477/503 us.  Override both with -DSCB_QP_MINBLOCKS=n.
+#ifdef SCB_QP_MINBLOCKS
+#define SCB_QP_MINB(LANES) SCB_QP_MINBLOCKS
+#else
+#define SCB_QP_MINB(LANES) ((LANES) == 32 ? 4 : 6)
 #endif
 
 template <int MODEL, int LANES, int RPL>
-__global__ void __launch_bounds__(kBlock, SCB_QP_MINBLOCKS)
+__global__ void __launch_bounds__(kBlock, SCB_QP_MINB(LANES))
 cbfqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
              const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
              const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
@@ -82,7 +87,7 @@ inline bool pick_geom(long N, int rows, int sm_count, LaunchGeom& g, int force_l
   // measured on B200 (tools/sweep_qp.py, M = 16): 32 lanes/QP wins at N = 1024 (5.4 vs 5.8 us), 8 lanes/QP
   // from N = 8192 up (7.3 vs 12.8 us; 0.55 vs 1.30 ms at N = 1M).  Switch at ~16 warps per SM.
   const bool small = N <= (long)sm_count * 16;
-  int lanes = (small || rows > 64) ? 32 : 8;
+  int lanes = (small || rows > 64) ? 32 : (rows <= 32 ? 4 : 8);
   if (force_lanes == 32 || (force_lanes == 8 && rows <= 64) || (force_lanes == 4 && rows <= 32)) lanes = force_lanes;
   g.lanes = lanes;
   if (lanes == 32) g.rpl = rows <= 32 ? 1 : rows <= 64 ? 2 : rows <= 128 ? 4 : 0;
