@@ -38,8 +38,12 @@ WORKLOADS = {
                  desc="4096 DynamicUnicycle2D agents, mpc_cbf horizon 8, 16 obstacles"),
     "cfg4": dict(model="KinematicBicycle2D_C3BF", controller="optimal_decay_cbf_qp", N=8192, M=32, H=0, dynamic=True,
                  desc="8192 KinematicBicycle2D_C3BF agents, optimal_decay_cbf_qp, 32 dynamic obstacles"),
+    # config 5 is 65536 mixed-model agents on 8 GPUs; per GPU that is 8192 agents (1/3 DU, 1/3 KB, 1/3 Quad3D)
+    "cfg5": dict(model="mixed", controller="mpc_cbf", N=8192, M=64, H=10, dynamic=False,
+                 desc="8192 agents per GPU = 1/8 of config 5 (65536 mixed du/kb/quad3d agents, mpc_cbf N=10, 64 obstacles, 8 GPUs)"),
 }
 L2_BYTES = 126e6
+MIXED = ("DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D")
 
 
 def algorithmic_bytes(w):
@@ -174,6 +178,101 @@ def cpu_sample_size(w):
     return {"cbf_qp": 4096, "optimal_decay_cbf_qp": 8192, "mpc_cbf": 48}[w["controller"]]
 
 
+def run_mixed(args, w, rank, world, local_rank):
+    """Config 5 share per GPU: three model groups (DU / KB / Quad3D), each one launch, on concurrent streams."""
+    import torch
+    import torch.distributed as dist
+    from safe_control_b200 import scenes, HostContext
+    from safe_control_b200.mixed import MixedMPCCBF, split_counts
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    N, M, H = w["N"], w["M"], w["H"]
+    counts = split_counts(N, len(MIXED))
+    P = 2
+    scs = [[scenes.make_scene(m, c, M, seed=1234 + 17 * rank + 101 * q) for m, c in zip(MIXED, counts)] for q in range(P)]
+    t = lambda a: torch.from_numpy(a).to(dev)
+    ins = [[{k: t(sc[k]) for k in ("X", "goal", "u_prev", "OBS", "nobs")} for sc in row] for row in scs]
+    ctrl = MixedMPCCBF([sc["spec"] for sc in scs[0]], num_obs=M, horizon=H)
+    step = lambda k: ctrl.solve(ins[k % P])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctrl.launches
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        outs = step(args.warmup + k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctrl.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    stat = {m: {"optimal_frac": float((o["status"] == 0).float().mean()), "iters_mean": float(o["iters"].float().mean()),
+                "iters_max": int(o["iters"].max())} for m, o in zip(MIXED, outs)}
+    # end to end: three host-pointer calls per step (one per model group), pinned inputs
+    ctx = HostContext(local_rank)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hin = [{k: pin(sc[k]) for k in ("X", "goal", "u_prev", "OBS", "nobs")} for sc in scs[0]]
+    def estep():
+        for g, a in zip(ctrl.groups, hin):
+            ctx.mpccbf_solve(g.params, M, H, a["X"], a["goal"], a["u_prev"], a["OBS"], a["nobs"])
+    e_steps = max(2, min(args.steps, 5))
+    estep(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        estep()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps * args.steps
+    h2d = sum(a[k].nbytes for a in hin for k in a)
+    d2h = sum(c * (g.nu * 8 + 4) for c, g in zip(counts, ctrl.groups))
+    tm = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        B = {"DynamicUnicycle2D": 3680, "KinematicBicycle2D": 3680, "Quad3D": 3784}
+        bytes_step = sum(B[m] * c for m, c in zip(MIXED, counts))
+        k_ms = float(tm[0]) / args.steps
+        out = {
+            "metric": "control-steps/sec (batched QP solves/s)", "value": world * N * args.steps / (float(tm[0]) * 1e-3),
+            "unit": "control-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": k_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step_per_gpu": N, "groups": dict(zip(MIXED, counts)),
+                       "obstacles": M, "horizon": H, "scene": "SURVEY 8d generator per model group", "launch": "3 launches per step on 3 streams (eager)",
+                       "l2_policy": "compute-bound NLP solves; 2 distinct batches alternated", "solver": stat,
+                       "parallelism": f"agents sharded per model group, {world} rank(s), no data-path collective"},
+            "e2e": {"value": world * N * args.steps / (float(tm[1]) * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps_timed": e_steps, "how": "three scb_mpccbf_solve_host calls per step"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": bytes_step / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_step / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "note": "FP64-compute/latency bound iterative NLP solves; HBM traffic negligible (DESIGN.md 3.3)"},
+        }
+        if not args.no_cpu:
+            rates = []
+            for m, sc in zip(MIXED, scs[0]):
+                wm = dict(w, model=m)
+                r, n, dt = cpu_rate(wm, sc, 6, 1)
+                rates.append((m, r, n, dt))
+            harm = len(rates) / sum(1.0 / r for _, r, _, _ in rates)
+            out["cpu_baseline"] = {"value": harm, "unit": "control-steps/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+                                   "sample": "; ".join(f"{m}: {n} agents in {dt:.1f} s" for m, _, n, dt in rates) + " (oracle port; harmonic mean over the 1/3-1/3-1/3 mix)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -200,7 +299,8 @@ def main():
         per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 1}[w["controller"]] * procs
         budget_s = 150.0
         n_scene = min(max(per_step * 8, 2048), 16384)
-        sc = scenes.make_scene(w["model"], n_scene, w["M"], seed=1234, dynamic=w["dynamic"],
+        ref_model = "DynamicUnicycle2D" if w["model"] == "mixed" else w["model"]     # mixed: the DU third as representative
+        sc = scenes.make_scene(ref_model, n_scene, w["M"], seed=1234, dynamic=w["dynamic"],
                                optimal_decay=w["controller"] == "optimal_decay_cbf_qp")
         for k in range(max(1, min(args.warmup, 3))):
             cpu_rate(w, sc, per_step, procs, offset=k * per_step)
@@ -228,6 +328,8 @@ def main():
         _close_pools()
         return
 
+    if w["model"] == "mixed":
+        return run_mixed(args, w, rank, world, local_rank)
     import torch
     import torch.distributed as dist
     from safe_control_b200 import BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, HostContext

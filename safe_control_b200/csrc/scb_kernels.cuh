@@ -84,10 +84,11 @@ struct LaunchGeom {
 // Compiled: (32,1) (32,2) (32,4) (8,4) (8,8) (4,8).  `force_lanes` (0 = auto) is a tuning override
 // (env SCB_QP_LANES), honoured only when an instantiation exists for it.
 inline bool pick_geom(long N, int rows, int sm_count, LaunchGeom& g, int force_lanes = 0) {
-  // measured on B200 (tools/sweep_qp.py, M = 16): 32 lanes/QP wins at N = 1024 (5.4 vs 5.8 us), 8 lanes/QP
-  // from N = 8192 up (7.3 vs 12.8 us; 0.55 vs 1.30 ms at N = 1M).  Switch at ~16 warps per SM.
+  // measured on B200 (tools/sweep_qp.py, M = 16, us per launch, lanes 32 / 8 / 4):
+  //   N = 1024: 4.42 / 5.14 / 7.28     N = 8192: 10.8 / 6.47 / 8.27     N = 1M: 1186 / 420 / 390
+  // -> warp per QP up to ~16 warps per SM, 8 lanes per QP for mid-size batches, 4 lanes per QP beyond ~32k agents.
   const bool small = N <= (long)sm_count * 16;
-  int lanes = (small || rows > 64) ? 32 : (rows <= 32 ? 4 : 8);
+  int lanes = (small || rows > 64) ? 32 : ((rows <= 32 && N > 32768) ? 4 : 8);
   if (force_lanes == 32 || (force_lanes == 8 && rows <= 64) || (force_lanes == 4 && rows <= 32)) lanes = force_lanes;
   g.lanes = lanes;
   if (lanes == 32) g.rpl = rows <= 32 ? 1 : rows <= 64 ? 2 : rows <= 128 ? 4 : 0;

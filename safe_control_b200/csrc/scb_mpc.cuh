@@ -495,7 +495,7 @@ struct MpcSolver {
       for (int j = lane; j < M; j += LANES) {
         const double ox = w[L.OB + j * 3], oy = w[L.OB + j * 3 + 1];
         const double s = w[L.S + k * M + j], lam = w[L.L + k * M + j];
-        const double inv = 1.0 / s, sig = lam * inv;
+        const double inv = w[L.DS + k * M + j], sig = lam * inv;
         a0 += sig; a1 = fma(sig, ox, a1); a2 = fma(sig, oy, a2);
         a3 = fma(sig * ox, ox, a3); a4 = fma(sig * ox, oy, a4); a5 = fma(sig * oy, oy, a5);
         l0 += lam; l1 = fma(lam, ox, l1); l2 = fma(lam, oy, l2);
@@ -539,11 +539,11 @@ struct MpcSolver {
     // simple bounds
     for (int q = lane; q < L.NS; q += LANES) {
       const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-      const double s = w[L.SS + q], lam = w[L.SL + q];
+      const double s = w[L.SS + q], lam = w[L.SL + q], is = w[L.SDS + q];
       double wt;
       if (rhs) {
         const double g = simple_value(c, w + L.Z, w + L.X);
-        wt = mu_bar / s - (lam / s) * (g - s);
+        wt = mu_bar * is - (lam * is) * (g - s);
       } else {
         wt = -lam;
       }
@@ -596,7 +596,7 @@ struct MpcSolver {
     sync();
     for (int q = lane; q < L.NS; q += LANES) {
       const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-      atomic_add_ws(Gm + c.k * NH + hidx<NY>(c.var, c.var), w[L.SL + q] / w[L.SS + q]);
+      atomic_add_ws(Gm + c.k * NH + hidx<NY>(c.var, c.var), w[L.SL + q] * w[L.SDS + q]);
     }
     sync();
   }
@@ -696,7 +696,7 @@ struct MpcSolver {
       double d = Hr[j * n + j] + delta;
       for (int t = 0; t < j; ++t) d -= Lc[j * n + t] * Lc[j * n + t];
       if (!(d > 1e-300) || !(d < 1e300)) { ok = false; break; }
-      const double dj = sqrt(d), inv = 1.0 / dj;
+      const double inv = rsqrt_pos(d);
       sync();
       if (lane == 0) Lc[j * n + j] = inv;        // the DIAGONAL holds 1/L_jj (solves multiply instead of divide)
       for (int i = j + 1 + lane; i < n; i += LANES) {
@@ -786,16 +786,21 @@ struct MpcSolver {
     // below the floor act as (linearly penalised) violations.  The line search runs on the matching
     // penalty-barrier merit  psi(z) = J(z) + sum_i rho(g_i(z)),  rho(g) = -mu log g  (g >= mu/nu), linear below.
     auto reset_slacks = [&](double floor_) {
-      for (int t = lane; t < H * M; t += LANES) w[L.S + t] = fmax(w[L.C + t], floor_);
+      // s -> S, 1/s -> DS (the only division per constraint per iteration; everything else multiplies)
+      for (int t = lane; t < H * M; t += LANES) {
+        const double sv = fmax(w[L.C + t], floor_);
+        w[L.S + t] = sv; w[L.DS + t] = 1.0 / sv;
+      }
       for (int q = lane; q < L.NS; q += LANES) {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-        w[L.SS + q] = fmax(simple_value(c, w + L.Z, w + L.X), floor_);
+        const double sv = fmax(simple_value(c, w + L.Z, w + L.X), floor_);
+        w[L.SS + q] = sv; w[L.SDS + q] = 1.0 / sv;
       }
       sync();
     };
     reset_slacks(mu_bar / nu_pen);
-    for (int t = lane; t < H * M; t += LANES) w[L.L + t] = mu_bar / w[L.S + t];
-    for (int q = lane; q < L.NS; q += LANES) w[L.SL + q] = mu_bar / w[L.SS + q];
+    for (int t = lane; t < H * M; t += LANES) w[L.L + t] = mu_bar * w[L.DS + t];
+    for (int q = lane; q < L.NS; q += LANES) w[L.SL + q] = mu_bar * w[L.SDS + q];
     sync();
 
     int it = 0, st = SCB_MAXITER, it_best = 0, tiny_steps = 0;
@@ -847,6 +852,16 @@ struct MpcSolver {
       if (nu_pen > 1e12) { st = SCB_INFEASIBLE; break; }
       const double floor_s = mu_bar / nu_pen;
       reset_slacks(floor_s);
+      // keep every multiplier within kappa_Sigma = 1e10 of mu/s (IPOPT's safeguard), using the fresh 1/s
+      for (int t = lane; t < H * M; t += LANES) {
+        const double c0 = mu_bar * w[L.DS + t];
+        w[L.L + t] = fmin(fmax(w[L.L + t], 1e-10 * c0), 1e10 * c0);
+      }
+      for (int q = lane; q < L.NS; q += LANES) {
+        const double c0 = mu_bar * w[L.SDS + q];
+        w[L.SL + q] = fmin(fmax(w[L.SL + q], 1e-10 * c0), 1e10 * c0);
+      }
+      sync();
       SCB_PH(3);
       // Newton system: exact Lagrangian Hessian first; if the reduced matrix is not positive definite,
       // fall back to the Gauss-Newton stage Hessians (PSD by construction) before any diagonal shift
@@ -905,8 +920,8 @@ struct MpcSolver {
           dg = fma(gi, dy[i], dg);
         }
         const double g = w[L.C + t], s = w[L.S + t], lam = w[L.L + t];
-        const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) / s;
-        w[L.DS + t] = dg; w[L.DL + t] = dl;
+        const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) * w[L.DS + t];
+        w[L.DL + t] = dl;
         if (ds < 0.0) ap = fmin(ap, -tau * s / ds);
         if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
         dpsi += (g >= floor_s) ? -mu_bar * dg / g : -nu_pen * dg;
@@ -915,8 +930,8 @@ struct MpcSolver {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
         const double dg = c.sgn * w[L.DY + c.k * NY + c.var];
         const double g = simple_value(c, w + L.Z, w + L.X), s = w[L.SS + q], lam = w[L.SL + q];
-        const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) / s;
-        w[L.SDS + q] = dg; w[L.SDL + q] = dl;
+        const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) * w[L.SDS + q];
+        w[L.SDL + q] = dl;
         if (ds < 0.0) ap = fmin(ap, -tau * s / ds);
         if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
         dpsi += (g >= floor_s) ? -mu_bar * dg / g : -nu_pen * dg;
@@ -976,17 +991,10 @@ struct MpcSolver {
       sync();
       for (int t = lane; t < H * M; t += LANES) {
         w[L.C + t] = w[L.CT + t];
-        const double sN = fmax(w[L.CT + t], floor_s);
-        double lam = fma(ad, w[L.DL + t], w[L.L + t]);
-        lam = fmin(fmax(lam, mu_bar / (1e10 * sN)), 1e10 * mu_bar / sN);
-        w[L.L + t] = lam;
+        w[L.L + t] = fma(ad, w[L.DL + t], w[L.L + t]);
       }
       for (int q = lane; q < L.NS; q += LANES) {
-        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
-        const double sN = fmax(simple_value(c, w + L.Z, w + L.X), floor_s);
-        double lam = fma(ad, w[L.SDL + q], w[L.SL + q]);
-        lam = fmin(fmax(lam, mu_bar / (1e10 * sN)), 1e10 * mu_bar / sN);
-        w[L.SL + q] = lam;
+        w[L.SL + q] = fma(ad, w[L.SDL + q], w[L.SL + q]);
       }
       Jcur = Jt;
       sync();
