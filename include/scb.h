@@ -41,8 +41,9 @@
  *                      bit M+2i: u_i at its upper bound; bit M+2i+1: u_i at its lower bound.
  *
  * All functions return 0 on success or a negative scb_error code; they never throw and
- * never touch errno.  No global mutable state: calls with distinct contexts/streams are
- * re-entrant.
+ * never touch errno.  Calls with distinct contexts/streams are re-entrant; the only
+ * library-owned state is a per-device ring of work counters used by the MPC kernel's
+ * dynamic agent scheduling (allocated on first use, slots handed out atomically).
  */
 #ifndef SCB_H_
 #define SCB_H_

@@ -24,14 +24,17 @@ __global__ void mpc_kernel(const __grid_constant__ scb_params p, int N, int M, i
                            const int32_t* __restrict__ track, const double* __restrict__ OBS, long stride,
                            const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
                            double* __restrict__ pred_x, double* __restrict__ pred_u, int32_t* __restrict__ iters,
-                           double* __restrict__ kkt) {
+                           double* __restrict__ kkt, int* __restrict__ next_agent) {
   extern __shared__ double smem[];
   using Mod = MpcModel<MODEL>;
   constexpr int NX = Mod::NX, NU = Mod::NU;
   const int gpb = blockDim.x / LANES;
   const int grp = threadIdx.x / LANES;
   double* ws = smem + (size_t)grp * ws_doubles;
-  for (long a = (long)blockIdx.x * gpb + grp; a < N; a += (long)gridDim.x * gpb) {
+  // Work distribution: the first wave is static, afterwards a group that finishes early pulls the next agent
+  // from a global counter (iteration counts vary 10..60 per agent; static striding left ~30 % of the wave idle).
+  const long first_dynamic = (long)gridDim.x * gpb;
+  for (long a = (long)blockIdx.x * gpb + grp; a < N;) {
     if (track && track[a] == 0) {
       // state_machine != 'track': return u_ref untouched, no solve (mpc_cbf.py:379-381)
       if ((threadIdx.x & (LANES - 1)) == 0) {
@@ -40,13 +43,35 @@ __global__ void mpc_kernel(const __grid_constant__ scb_params p, int N, int M, i
         if (iters) iters[a] = 0;
         if (kkt) kkt[a] = 0.0;
       }
-      continue;
-    }
+    } else {
     mpc_agent<MODEL, LANES>(p, H, M, nobs ? nobs[a] : M, X + a * NX, goal + a * Mod::NGOAL, u_prev + a * NU, OBS + a * stride, ws,
                             U + a * NU, status + a, pred_x ? pred_x + a * (H + 1) * NX : nullptr,
                             pred_u ? pred_u + a * H * NU : nullptr, iters ? iters + a : nullptr,
                             kkt ? kkt + a : nullptr);
+    }
+    int nxt = 0;
+    if ((threadIdx.x & (LANES - 1)) == 0) nxt = atomicAdd(next_agent, 1);
+    nxt = __shfl_sync(Grp<LANES>::gmask(), nxt, 0, LANES);
+    a = first_dynamic + nxt;
   }
+}
+
+// Per-launch work counters: a small ring of zero-initialised ints per device; each launch takes the next slot and
+// re-zeroes it with a stream-ordered memset just before the kernel, so concurrent streams and CUDA-graph capture are
+// safe (a slot is only reused after kRing further launches on that device).
+constexpr int kRing = 4096;
+inline int* mpc_counter_slot(cudaStream_t s) {
+  static int* ring[64] = {nullptr};
+  static unsigned next[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!ring[dev]) {
+    if (cudaMalloc((void**)&ring[dev], kRing * sizeof(int)) != cudaSuccess) { ring[dev] = nullptr; return nullptr; }
+    cudaMemset(ring[dev], 0, kRing * sizeof(int));
+  }
+  int* slot = ring[dev] + (__sync_fetch_and_add(&next[dev], 1u) % kRing);
+  if (cudaMemsetAsync(slot, 0, sizeof(int), s) != cudaSuccess) return nullptr;
+  return slot;
 }
 
 template <int MODEL>
@@ -72,8 +97,10 @@ inline int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* 
   if (e != cudaSuccess) return SCB_ERR_TOO_LARGE;
   long blocks = ((long)N + gpb - 1) / gpb;
   if (blocks > sm_count) blocks = sm_count;
+  int* counter = mpc_counter_slot(s);
+  if (!counter) return SCB_ERR_ALLOC;
   kern<<<(int)blocks, gpb * kMpcLanes, smem, s>>>(p, N, M, H, L.total, X, Uref, goal, u_prev, track, OBS, stride, nobs, U,
-                                                  status, pred_x, pred_u, iters, kkt);
+                                                  status, pred_x, pred_u, iters, kkt, counter);
   return SCB_OK;
 }
 

@@ -170,3 +170,19 @@ def test_host_pointer_path_matches_device_path():
     assert np.array_equal(U, Ud) and np.array_equal(st, std) and np.array_equal(act, actd)
     assert ctx.launches == 1
     ctx.close()
+
+
+def test_every_launch_geometry_is_instantiated():
+    """Batch sizes on both sides of every lanes-per-QP threshold, for both QP controllers (a missing template
+    instantiation shows up as SCB_ERR_TOO_LARGE)."""
+    from safe_control_b200 import BatchedCBFQP, BatchedOptimalDecayCBFQP, scenes
+    for M in (16, 32, 40, 100):
+        for N in (64, 4096, 40000):
+            sc = scenes.make_scene("DynamicUnicycle2D", 64, M, seed=2)
+            rep = -(-N // 64)
+            tile = lambda a: dev(np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:N])
+            X, Ur, OBS, nobs = tile(sc["X"]), tile(sc["U_ref"]), tile(sc["OBS"]), tile(sc["nobs"])
+            U, st, _ = BatchedCBFQP(sc["spec"], num_obs=M).solve(X, Ur, OBS, nobs)
+            U2, om, sel, st2, _ = BatchedOptimalDecayCBFQP(sc["spec"], num_obs=M).solve(X, Ur, OBS, nobs)
+            torch.cuda.synchronize()
+            assert torch.equal(st[:64], st[-64:] if N % 64 == 0 else st[:64])
