@@ -191,8 +191,8 @@ struct MpcModel<SCB_QUAD_3D> {
 // workspace layout (in doubles), computed identically on host and device
 struct MpcLayout {
   int H, M, n, NS;
-  int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, RHS, DZ, SEN,
-      HR, LC, DY, ZT, XT, RG, AUX;
+  int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, DZ, PM, PV, KG, KF,
+      TM, MM, MV, DY, ZT, XT, RG, AUX;
   int total;
 };
 
@@ -214,9 +214,13 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   L.SUM = take(H * 12);
   L.G = take((H + 1) * NH);  L.GAM = take((H + 1) * NY);
   L.MU = take((H + 1) * NX);
-  L.RD = take(L.n); L.RHS = take(L.n); L.DZ = take(L.n);
-  L.SEN = take((H + 1) * NX * L.n);
-  L.HR = take(L.n * L.n); L.LC = take(L.n * L.n);
+  L.RD = take(L.n); L.DZ = take(L.n);
+  {
+    const int NXT = NX + NU, NV = NXT + NU;
+    L.PM = take((H + 1) * NXT * NXT); L.PV = take((H + 1) * NXT);
+    L.KG = take(H * NU * NXT); L.KF = take(H * NU);
+    L.TM = take(NXT * NV); L.MM = take(NV * NV); L.MV = take(NV);
+  }
   L.DY = take((H + 1) * NY);
   L.ZT = take(L.n); L.XT = take((H + 1) * NX); L.RG = take(L.n);
   L.total = o;
@@ -601,108 +605,164 @@ struct MpcSolver {
     sync();
   }
 
-  // state sensitivities S_k = dx_k / dz  (NX x n), lanes over columns
-  SCB_HD void sensitivities() {
-    double* S = w + L.SEN;
-    for (int c = lane; c < n; c += LANES) {
-      double col[NX];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) { col[i] = 0.0; S[i * n + c] = 0.0; }
-      const int kc = c / NU, ic = c - kc * NU;
-      for (int k = 0; k < H; ++k) {
-        double nc[NX];
-        if (k < kc) {
-#pragma unroll
-          for (int i = 0; i < NX; ++i) nc[i] = 0.0;
-        } else if (k == kc) {
-          const double* B = w + L.B + k * NX * NU;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) nc[i] = B[i * NU + ic];
-        } else {
-          const double* A = w + L.A + k * NX * NX;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) {
-            double v = 0.0;
-#pragma unroll
-            for (int a = 0; a < NX; ++a) v = fma(A[i * NX + a], col[a], v);
-            nc[i] = v;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { col[i] = nc[i]; S[((k + 1) * NX + i) * n + c] = nc[i]; }
-      }
+  // ---- Newton step by a stage-wise (Riccati) factorisation ------------------------------------------------
+  // The Newton system of the condensed problem is the optimality system of the equality-constrained QP
+  //     min  sum_k 1/2 v_k' Hs_k v_k + h_k' v_k ,   v_k = (dxt_k, du_k),   dxt_{k+1} = Fm_k v_k,  dxt_0 = 0
+  // over the augmented state xt_k = (x_k, u_{k-1}) (the input-RATE cost couples neighbouring inputs), with
+  // Hs_k = stage Hessian G_k + rate terms, Fm_k = [[A_k 0 B_k],[0 0 I]].  The backward Riccati sweep is the block
+  // LDL' of that system: it is positive definite iff every Muu_k is, costs O(H (nx+nu)^3) instead of the O(H^2)
+  // sensitivities + dense n x n Cholesky of a condensed factorisation, and needs O(H) scratch.
+  static constexpr int NXT = NX + NU, NV = NXT + NU;
+
+  // F_k[a][c], a < NXT rows (next augmented state), c < NV columns (xt_k, u_k)
+  SCB_HD double fm(int k, int a, int c) const {
+    if (a < NX) {
+      if (c < NX) return w[L.A + k * NX * NX + a * NX + c];
+      if (c < NXT) return 0.0;
+      return w[L.B + k * NX * NU + a * NU + (c - NXT)];
     }
-    sync();
+    return (c == NXT + (a - NX)) ? 1.0 : 0.0;
   }
+  // y-index (x, u) of the stage variable v-index, or -1 for the u_{k-1} block
+  static SCB_HD int v2y(int c) { return c < NX ? c : (c < NXT ? -1 : NX + (c - NXT)); }
 
-  // entry (a, c) of the stage-variable sensitivity  d y_k / d z  (NY x n)
-  SCB_HD double sy(int k, int a, int c) const {
-    if (a < NX) return w[L.SEN + (k * NX + a) * n + c];
-    return (k < H && c == k * NU + (a - NX)) ? 1.0 : 0.0;
-  }
-
-  // reduced Hessian  Hr = H_R + sum_k Sy_k' G_k Sy_k  (lower triangle).  Lane c owns COLUMN c (rows r >= c):
-  // it forms t = G_k Sy_k[:, c] in registers and accumulates Sy_k[:, r] . t down its column, stage after
-  // stage -- no shared scratch, no barrier between stages, reads of Sy_k[:, r] are warp broadcasts.
-  SCB_HD void reduced_hessian() {
-    double* Hr = w + L.HR;
-    const double* S = w + L.SEN;
-    for (int c = lane; c < n; c += LANES) {
-      const int kc = c / NU, ic = c - kc * NU;
-      for (int r = c; r < n; ++r) Hr[r * n + c] = 0.0;
-      Hr[c * n + c] = (kc + 1 < H) ? 4.0 * Rs[ic] : 2.0 * Rs[ic];
-      if (kc + 1 < H) Hr[(c + NU) * n + c] = -2.0 * Rs[ic];
-      for (int k = kc; k <= H; ++k) {               // Sy_k[:, c] == 0 for k < kc
-        const double* Gk = w + L.G + k * NH;
-        const int ncol = (k < H) ? (k + 1) * NU : n;
-        double sc[NY], tc[NY];
-#pragma unroll
-        for (int a = 0; a < NX; ++a) sc[a] = S[(k * NX + a) * n + c];
-#pragma unroll
-        for (int a = NX; a < NY; ++a) sc[a] = (k < H && k == kc && a - NX == ic) ? 1.0 : 0.0;
-#pragma unroll
-        for (int a = 0; a < NY; ++a) {
-          double v = 0.0;
-#pragma unroll
-          for (int bb = 0; bb < NY; ++bb) {
-            const int lo = a < bb ? a : bb, hi = a < bb ? bb : a;
-            v = fma(Gk[lo * NY - (lo * (lo - 1)) / 2 + (hi - lo)], sc[bb], v);
-          }
-          tc[a] = v;
-        }
-        for (int r = c; r < ncol; ++r) {
-          double v = 0.0;
-#pragma unroll
-          for (int a = 0; a < NX; ++a) v = fma(S[(k * NX + a) * n + r], tc[a], v);
-          if (k < H && r >= k * NU) {
-            const int ir = r - k * NU;
-#pragma unroll
-            for (int a = 0; a < NU; ++a) if (a == ir) v += tc[NX + a];
-          }
-          Hr[r * n + c] += v;
-        }
-      }
+  // backward sweep with diagonal shift `delta` on Muu; false if some Muu_k is not positive definite
+  SCB_HD bool riccati_backward(double delta) {
+    double* PM = w + L.PM;
+    double* PV = w + L.PV;
+    const double* gam = w + L.GAM;                  // = -grad l_k + sum w grad g  (the Newton rhs per stage)
+    const double* z = w + L.Z;
+    // terminal: P_H = G_H (x block), p_H = -gam_H
+    for (int t = lane; t < NXT * NXT; t += LANES) {
+      const int r = t / NXT, c = t - r * NXT;
+      double v = 0.0;
+      if (r < NX && c < NX) { const int lo = r < c ? r : c, hi = r < c ? c : r; v = w[L.G + H * NH + hidx<NY>(lo, hi)]; }
+      PM[H * NXT * NXT + t] = v;
     }
+    for (int t = lane; t < NXT; t += LANES) PV[H * NXT + t] = (t < NX) ? -gam[H * NY + t] : 0.0;
     sync();
-  }
-
-  // Cholesky of (Hr + delta I) into LC (lower); returns false on a non-positive pivot
-  SCB_HD bool cholesky(double delta) {
-    const double* Hr = w + L.HR;
-    double* Lc = w + L.LC;
     bool ok = true;
-    for (int j = 0; j < n; ++j) {
-      // diagonal (every lane computes it redundantly)
-      double d = Hr[j * n + j] + delta;
-      for (int t = 0; t < j; ++t) d -= Lc[j * n + t] * Lc[j * n + t];
-      if (!(d > 1e-300) || !(d < 1e300)) { ok = false; break; }
-      const double inv = rsqrt_pos(d);
+    for (int k = H - 1; k >= 0; --k) {
+      const double* Pn = PM + (k + 1) * NXT * NXT;
+      const double* pn = PV + (k + 1) * NXT;
+      double* T = w + L.TM;                         // T = P_{k+1} F_k   (NXT x NV)
+      for (int t = lane; t < NXT * NV; t += LANES) {
+        const int r = t / NV, c = t - r * NV;
+        double v = 0.0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) v = fma(Pn[r * NXT + a], fm(k, a, c), v);
+        if (c >= NXT) v += Pn[r * NXT + NX + (c - NXT)];
+        T[t] = v;
+      }
       sync();
-      if (lane == 0) Lc[j * n + j] = inv;        // the DIAGONAL holds 1/L_jj (solves multiply instead of divide)
-      for (int i = j + 1 + lane; i < n; i += LANES) {
-        double v = Hr[i * n + j];
-        for (int t = 0; t < j; ++t) v -= Lc[i * n + t] * Lc[j * n + t];
-        Lc[i * n + j] = v * inv;
+      double* Mm = w + L.MM;                        // M = Hs_k + F_k' T  (NV x NV),  m = h_k + F_k' p_{k+1}
+      for (int t = lane; t < NV * NV + NV; t += LANES) {
+        if (t < NV * NV) {
+          const int bb = t / NV, c = t - bb * NV;
+          double v = 0.0;
+          const int yb = v2y(bb), yc = v2y(c);
+          if (yb >= 0 && yc >= 0) { const int lo = yb < yc ? yb : yc, hi = yb < yc ? yc : yb; v = w[L.G + k * NH + hidx<NY>(lo, hi)]; }
+          // input-rate term R (u_k - u_{k-1})^2
+          const int ub = (bb >= NXT) ? bb - NXT : (bb >= NX ? bb - NX : -1), uc = (c >= NXT) ? c - NXT : (c >= NX ? c - NX : -1);
+          if (ub >= 0 && ub == uc) {
+            const bool sameblk = (bb >= NXT) == (c >= NXT);
+            double rr = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
+            v += sameblk ? rr : -rr;
+          }
+#pragma unroll
+          for (int a = 0; a < NX; ++a) v = fma(fm(k, a, bb), T[a * NV + c], v);
+          if (bb >= NXT) v += T[(NX + bb - NXT) * NV + c];
+          if (bb == c && bb >= NXT) v += delta;
+          Mm[t] = v;
+        } else {
+          const int bb = t - NV * NV;
+          const int yb = v2y(bb);
+          double v = (yb >= 0) ? -gam[k * NY + yb] : 0.0;
+          const int ub = (bb >= NXT) ? bb - NXT : (bb >= NX ? bb - NX : -1);
+          if (ub >= 0) {
+            double rr = 0.0, du = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; ++i)
+              if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
+            v += (bb >= NXT) ? rr * du : -rr * du;
+          }
+#pragma unroll
+          for (int a = 0; a < NX; ++a) v = fma(fm(k, a, bb), pn[a], v);
+          if (bb >= NXT) v += pn[NX + bb - NXT];
+          w[L.MV + bb] = v;
+        }
+      }
+      sync();
+      // Muu = L L' (NU x NU), every lane redundantly; gains K = -Muu^-1 Mux, kff = -Muu^-1 m_u, lanes over columns
+      double Lu[NU][NU];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) Lu[i][j] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        double d = Mm[(NXT + j) * NV + NXT + j];
+#pragma unroll
+        for (int t = 0; t < NU; ++t) if (t < j) d -= Lu[j][t] * Lu[j][t];
+        if (!(d > 1e-300) || !(d < 1e300)) ok = false;
+        const double inv = ok ? rsqrt_pos(d) : 0.0;
+        Lu[j][j] = inv;                               // diagonal holds 1 / L_jj
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          if (i > j) {
+            double v = Mm[(NXT + i) * NV + NXT + j];
+#pragma unroll
+            for (int t = 0; t < NU; ++t) if (t < j) v -= Lu[i][t] * Lu[j][t];
+            Lu[i][j] = v * inv;
+          }
+        }
+      }
+      if (!ok) break;
+      double* Kg = w + L.KG + k * NU * NXT;
+      double* Kf = w + L.KF + k * NU;
+      for (int c = lane; c <= NXT; c += LANES) {      // column c < NXT of Mux, or c == NXT: m_u
+        double rhs[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) rhs[i] = (c < NXT) ? -Mm[(NXT + i) * NV + c] : -w[L.MV + NXT + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = rhs[i];
+#pragma unroll
+          for (int t = 0; t < NU; ++t) if (t < i) v -= Lu[i][t] * rhs[t];
+          rhs[i] = v * Lu[i][i];
+        }
+#pragma unroll
+        for (int ii = NU - 1; ii >= 0; --ii) {
+          double v = rhs[ii];
+#pragma unroll
+          for (int t = 0; t < NU; ++t) if (t > ii) v -= Lu[t][ii] * rhs[t];
+          rhs[ii] = v * Lu[ii][ii];
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          if (c < NXT) Kg[i * NXT + c] = rhs[i]; else Kf[i] = rhs[i];
+        }
+      }
+      sync();
+      // P_k = Mxx + Mxu K,  p_k = m_x + Mxu kff
+      double* Pk = PM + k * NXT * NXT;
+      for (int t = lane; t < NXT * NXT + NXT; t += LANES) {
+        if (t < NXT * NXT) {
+          const int r = t / NXT, c = t - r * NXT;
+          double v = Mm[r * NV + c];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) v = fma(Mm[r * NV + NXT + i], Kg[i * NXT + c], v);
+          Pk[t] = v;
+        } else {
+          const int r = t - NXT * NXT;
+          double v = w[L.MV + r];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) v = fma(Mm[r * NV + NXT + i], Kf[i], v);
+          PV[k * NXT + r] = v;
+        }
       }
       sync();
     }
@@ -710,20 +770,49 @@ struct MpcSolver {
     return ok;
   }
 
-  // solve Lc Lc' dz = rhs  (lane 0; n <= 32)
-  SCB_HD void chol_solve(const double* rhs, double* dz) {
+  // forward sweep: dz (inputs) and the stage directions dy_k = (dx_k, du_k)   (lane 0; O(H (nx+nu)^2))
+  SCB_HD void riccati_forward() {
     if (lane == 0) {
-      const double* Lc = w + L.LC;
-      for (int i = 0; i < n; ++i) {
-        double v = rhs[i];
-        for (int t = 0; t < i; ++t) v -= Lc[i * n + t] * dz[t];
-        dz[i] = v * Lc[i * n + i];
+      double dxt[NXT];
+#pragma unroll
+      for (int i = 0; i < NXT; ++i) dxt[i] = 0.0;
+      for (int k = 0; k < H; ++k) {
+        const double* Kg = w + L.KG + k * NU * NXT;
+        const double* Kf = w + L.KF + k * NU;
+        double du[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = Kf[i];
+#pragma unroll
+          for (int c = 0; c < NXT; ++c) v = fma(Kg[i * NXT + c], dxt[c], v);
+          du[i] = v;
+          w[L.DZ + k * NU + i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) w[L.DY + k * NY + i] = dxt[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) w[L.DY + k * NY + NX + i] = du[i];
+        double nx_[NX];
+        const double* A = w + L.A + k * NX * NX;
+        const double* B = w + L.B + k * NX * NU;
+#pragma unroll
+        for (int a = 0; a < NX; ++a) {
+          double v = 0.0;
+#pragma unroll
+          for (int c = 0; c < NX; ++c) v = fma(A[a * NX + c], dxt[c], v);
+#pragma unroll
+          for (int c = 0; c < NU; ++c) v = fma(B[a * NU + c], du[c], v);
+          nx_[a] = v;
+        }
+#pragma unroll
+        for (int a = 0; a < NX; ++a) dxt[a] = nx_[a];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) dxt[NX + i] = du[i];
       }
-      for (int i = n - 1; i >= 0; --i) {
-        double v = dz[i];
-        for (int t = i + 1; t < n; ++t) v -= Lc[t * n + i] * dz[t];
-        dz[i] = v * Lc[i * n + i];
-      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) w[L.DY + H * NY + i] = dxt[i];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) w[L.DY + H * NY + NX + i] = 0.0;
     }
     sync();
   }
@@ -870,40 +959,23 @@ struct MpcSolver {
       stage_hessians();
       SCB_PH(4);
       stage_gradients(true, mu_bar);
-      adjoint(w + L.GAM, w + L.RHS);                // (costates of the first sweep were consumed by stage_hessians)
-      for (int t = lane; t < n; t += LANES) w[L.RHS + t] -= w[L.RG + t];
-      sync();
       SCB_PH(5);
-      sensitivities();
-      SCB_PH(6);
-      reduced_hessian();
-      SCB_PH(7);
       double delta = 0.0;
-      bool pd = cholesky(0.0);
+      bool pd = riccati_backward(0.0);
+      SCB_PH(6);
       if (!pd) {
         gauss_newton = true;
         stage_hessians();
-        reduced_hessian();
         gauss_newton = false;
         int tries = 0;
-        pd = cholesky(0.0);
-        while (!pd && tries < 12) { delta = (delta == 0.0) ? 1e-8 : delta * 100.0; pd = cholesky(delta); ++tries; }
+        pd = riccati_backward(0.0);
+        while (!pd && tries < 12) { delta = (delta == 0.0) ? 1e-8 : delta * 100.0; pd = riccati_backward(delta); ++tries; }
         if (delta == 0.0) delta = -1.0;             // marks "Gauss-Newton step" in traces
       }
       if (!pd) { st = SCB_NUMERICAL; break; }
+      SCB_PH(7);
+      riccati_forward();
       SCB_PH(8);
-      chol_solve(w + L.RHS, w + L.DZ);
-      // stage directions dy_k = Sy_k dz
-      for (int t = lane; t < (H + 1) * NY; t += LANES) {
-        const int k = t / NY, a = t - k * NY;
-        double v = 0.0;
-        if (k < H || a < NX) {
-          const int ncol = (k < H) ? (k + 1) * NU : n;
-          for (int c = 0; c < ncol; ++c) v = fma(sy(k, a, c), w[L.DZ + c], v);
-        }
-        w[L.DY + t] = v;
-      }
-      sync();
       SCB_PH(9);
       // linearised constraint change dg (stored in DS), multiplier direction, fraction to the boundary,
       // and the directional derivative of the merit

@@ -17,7 +17,7 @@ l.scb_debug_mpc_profile(None, 1)
 out = ctrl.solve(*a); torch.cuda.synchronize()
 l.scb_debug_mpc_profile(buf, 0)
 names = ["stage_derivatives(jets)", "stage_sums#1", "grad+adjoint+rate", "residuals+mu+slacks", "sums#2+stage_hessians",
-         "rhs grad+adjoint", "sensitivities", "reduced_hessian", "cholesky", "chol_solve+dy", "directions", "dJ+merit0",
+         "rhs stage gradients", "riccati backward", "(GN / shift fallback)", "riccati forward", "-", "directions", "dJ+merit0",
          "backtracking", "accept"]
 v = np.array(list(buf)[:14], dtype=float)
 it = out["iters"].cpu().numpy()
