@@ -99,4 +99,57 @@ SCB_HD void jclip(Jet<N>& r, const Jet<N>& a, double lo, double hi) {
   else r = a;
 }
 
+// ---- first-order jets (value + gradient): same vocabulary, used where no curvature is needed ----------
+template <int N>
+struct Jet1 {
+  double v;
+  double g[N];
+};
+
+template <int N>
+SCB_HD void jvar(Jet1<N>& r, double val, int idx) {
+  r.v = val;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.g[i] = (i == idx) ? 1.0 : 0.0;
+}
+template <int N>
+SCB_HD void jconst(Jet1<N>& r, double c) {
+  r.v = c;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.g[i] = 0.0;
+}
+template <int N>
+SCB_HD void jaxpy(Jet1<N>& r, const Jet1<N>& a, double s, const Jet1<N>& b) {
+  r.v = a.v + s * b.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.g[i] = a.g[i] + s * b.g[i];
+}
+template <int N>
+SCB_HD void jscale(Jet1<N>& r, const Jet1<N>& a, double s) {
+  r.v = s * a.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.g[i] = s * a.g[i];
+}
+template <int N>
+SCB_HD void jmul(Jet1<N>& r, const Jet1<N>& a, const Jet1<N>& b) {
+  const double av = a.v, bv = b.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.g[i] = av * b.g[i] + bv * a.g[i];
+  r.v = av * bv;
+}
+template <int N>
+SCB_HD void jsincos(Jet1<N>& s, Jet1<N>& c, const Jet1<N>& a) {
+  double sv, cv;
+  sincos_pair(a.v, sv, cv);
+#pragma unroll
+  for (int i = 0; i < N; ++i) { s.g[i] = cv * a.g[i]; c.g[i] = -sv * a.g[i]; }
+  s.v = sv; c.v = cv;
+}
+template <int N>
+SCB_HD void jclip(Jet1<N>& r, const Jet1<N>& a, double lo, double hi) {
+  if (a.v > hi) jconst(r, hi);
+  else if (a.v < lo) jconst(r, lo);
+  else r = a;
+}
+
 }  // namespace scb

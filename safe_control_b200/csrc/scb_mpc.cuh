@@ -205,11 +205,11 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   auto take = [&](int cnt) { int r = o; o += cnt; return r; };
   L.X = take((H + 1) * NX);  L.Z = take(H * NU);
   L.A = take(H * NX * NX);   L.B = take(H * NX * NU);
-  L.FH = take(LINEAR ? 0 : H * NX * NH);
+  L.FH = take(0);                        // (curvature is contracted on the fly, see stage_hessians)
   L.AUX = take(AUXN);
-  L.JE = take(H * (NY + NH)); L.JX = take(H * (NY + NH)); L.JY = take(H * (NY + NH));
+  L.JE = take(H * NY); L.JX = take(H * NY); L.JY = take(H * NY);       // gradients gE, gX, gY
   L.PT = take(H * 6);        L.OB = take(M * 3);
-  L.C = take(H * M); L.S = take(H * M); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
+  L.C = take(H * M); L.S = take(0); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
   L.SS = take(L.NS); L.SL = take(L.NS); L.SDS = take(L.NS); L.SDL = take(L.NS);
   L.SUM = take(H * 12);
   L.G = take((H + 1) * NH);  L.GAM = take((H + 1) * NY);
@@ -368,12 +368,26 @@ struct MpcSolver {
     return fma(c.sgn, yv, c.off);
   }
 
-  // ---- exact stage derivatives at the current iterate (lanes over stages) ----
+  // ---- first derivatives of every stage at the current iterate (lanes over stages) ----
+  // A_k, B_k and the gradients gE, gX, gY (see header).  Curvature is NOT stored: stage_hessians() re-evaluates
+  // the stage with second-order jets once the multipliers and costates that weight it are known and keeps only
+  // the contracted 21-entry stage Hessian (saves 4 NX + 3 Hessians per stage of workspace).
+  template <class JT>
+  SCB_HD void barrier_jets(const JT* y, const JT& P1, const JT& Q1, const JT& P2, const JT& Q2, JT& E, JT& PX, JT& PY) const {
+    // E = sum_i w_i (P_i^2 + Q_i^2),  PX = 2 sum w_i P_i,  PY = 2 sum w_i Q_i
+    JT t;
+    jmul(E, y[0], y[0]); jmul(t, y[1], y[1]); jaxpy(E, E, 1.0, t); jscale(E, E, w0);
+    jmul(t, P1, P1); jaxpy(E, E, w1, t); jmul(t, Q1, Q1); jaxpy(E, E, w1, t);
+    jmul(t, P2, P2); jaxpy(E, E, w2, t); jmul(t, Q2, Q2); jaxpy(E, E, w2, t);
+    jscale(PX, y[0], 2.0 * w0); jaxpy(PX, PX, 2.0 * w1, P1); jaxpy(PX, PX, 2.0 * w2, P2);
+    jscale(PY, y[1], 2.0 * w0); jaxpy(PY, PY, 2.0 * w1, Q1); jaxpy(PY, PY, 2.0 * w2, Q2);
+  }
+
   SCB_HD void stage_derivatives() {
     const double* xs = w + L.X;
     const double* z = w + L.Z;
     if constexpr (Mod::LINEAR) {
-      // linear model: A, B constant; barrier points affine in y -> E has a constant Hessian, PX/PY none
+      // linear model: A, B constant; barrier points affine in y
       const double* aux = w + L.AUX;
       const double* R0 = aux + NX * NX + NX * NU;
       const double* R1 = R0 + NY;
@@ -389,60 +403,44 @@ struct MpcSolver {
         for (int t = 0; t < NX * NU; ++t) B[t] = aux[NX * NX + t];
         double P1 = 0.0, Q1 = 0.0;
         for (int i = 0; i < NY; ++i) { P1 = fma(R0[i], y[i], P1); Q1 = fma(R1[i], y[i], Q1); }
-        double* je = w + L.JE + k * (NY + NH);
-        double* jx = w + L.JX + k * (NY + NH);
-        double* jy = w + L.JY + k * (NY + NH);
-        int t = 0;
+        double* je = w + L.JE + k * NY;
+        double* jx = w + L.JX + k * NY;
+        double* jy = w + L.JY + k * NY;
         for (int i = 0; i < NY; ++i) {
           const double d0 = (i == 0) ? 1.0 : 0.0, d1 = (i == 1) ? 1.0 : 0.0;
           je[i] = 2.0 * w0 * (y[0] * d0 + y[1] * d1) + 2.0 * w1 * (P1 * R0[i] + Q1 * R1[i]);
           jx[i] = 2.0 * w0 * d0 + 2.0 * w1 * R0[i];
           jy[i] = 2.0 * w0 * d1 + 2.0 * w1 * R1[i];
-          for (int j = i; j < NY; ++j, ++t) {
-            const double e0 = (j == 0) ? 1.0 : 0.0, e1 = (j == 1) ? 1.0 : 0.0;
-            je[NY + t] = 2.0 * w0 * (d0 * e0 + d1 * e1) + 2.0 * w1 * (R0[i] * R0[j] + R1[i] * R1[j]);
-            jx[NY + t] = 0.0; jy[NY + t] = 0.0;
-          }
         }
       }
       sync();
-      return;
     } else {
-    for (int k = lane; k < H; k += LANES) {
-      J y[NY], F[NX], P1, Q1, P2, Q2;
+      using J1 = Jet1<NY>;
+      for (int k = lane; k < H; k += LANES) {
+        J1 y[NY], F[NX], P1, Q1, P2, Q2;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) jvar(y[i], xs[k * NX + i], i);
+        for (int i = 0; i < NX; ++i) jvar(y[i], xs[k * NX + i], i);
 #pragma unroll
-      for (int i = 0; i < NU; ++i) jvar(y[NX + i], z[k * NU + i], NX + i);
-      Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
-      double* A = w + L.A + k * NX * NX;
-      double* B = w + L.B + k * NX * NU;
-      double* FH = w + L.FH + k * NX * NH;
+        for (int i = 0; i < NU; ++i) jvar(y[NX + i], z[k * NU + i], NX + i);
+        Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
+        double* A = w + L.A + k * NX * NX;
+        double* B = w + L.B + k * NX * NU;
 #pragma unroll
-      for (int c = 0; c < NX; ++c) {
+        for (int c = 0; c < NX; ++c) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) A[c * NX + i] = F[c].g[i];
+          for (int i = 0; i < NX; ++i) A[c * NX + i] = F[c].g[i];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) B[c * NU + i] = F[c].g[NX + i];
+          for (int i = 0; i < NU; ++i) B[c * NU + i] = F[c].g[NX + i];
+        }
+        J1 E, PX, PY;
+        barrier_jets(y, P1, Q1, P2, Q2, E, PX, PY);
+        double* je = w + L.JE + k * NY;
+        double* jx = w + L.JX + k * NY;
+        double* jy = w + L.JY + k * NY;
 #pragma unroll
-        for (int t = 0; t < NH; ++t) FH[c * NH + t] = F[c].h[t];
+        for (int i = 0; i < NY; ++i) { je[i] = E.g[i]; jx[i] = PX.g[i]; jy[i] = PY.g[i]; }
       }
-      // E = sum_i w_i (P_i^2 + Q_i^2),  PX = 2 sum w_i P_i,  PY = 2 sum w_i Q_i
-      J E, PX, PY, t;
-      jmul(E, y[0], y[0]); jmul(t, y[1], y[1]); jaxpy(E, E, 1.0, t); jscale(E, E, w0);
-      jmul(t, P1, P1); jaxpy(E, E, w1, t); jmul(t, Q1, Q1); jaxpy(E, E, w1, t);
-      jmul(t, P2, P2); jaxpy(E, E, w2, t); jmul(t, Q2, Q2); jaxpy(E, E, w2, t);
-      jscale(PX, y[0], 2.0 * w0); jaxpy(PX, PX, 2.0 * w1, P1); jaxpy(PX, PX, 2.0 * w2, P2);
-      jscale(PY, y[1], 2.0 * w0); jaxpy(PY, PY, 2.0 * w1, Q1); jaxpy(PY, PY, 2.0 * w2, Q2);
-      double* je = w + L.JE + k * (NY + NH);
-      double* jx = w + L.JX + k * (NY + NH);
-      double* jy = w + L.JY + k * (NY + NH);
-#pragma unroll
-      for (int i = 0; i < NY; ++i) { je[i] = E.g[i]; jx[i] = PX.g[i]; jy[i] = PY.g[i]; }
-#pragma unroll
-      for (int i = 0; i < NH; ++i) { je[NY + i] = E.h[i]; jx[NY + i] = PX.h[i]; jy[NY + i] = PY.h[i]; }
-    }
-    sync();
+      sync();
     }
   }
 
@@ -491,20 +489,21 @@ struct MpcSolver {
   }
 
   // weighted obstacle sums of stage k: which = 0 (sigma moments, 6) / 1 (lambda, 3) / 2 (rhs weights, 3)
-  SCB_HD void stage_sums(double mu_bar, bool with_rhs) {
+  SCB_HD void stage_sums(double mu_bar, bool with_rhs, double floor_s = 0.0) {
     // lanes own obstacles (registers hold ox, oy), loop over stages, 12 partial sums per stage reduced by
     // xor-shuffles: one division per (stage, obstacle), no divergent per-sum code paths
     for (int k = 0; k < H; ++k) {
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, l0 = 0, l1 = 0, l2 = 0, r0 = 0, r1 = 0, r2 = 0;
       for (int j = lane; j < M; j += LANES) {
         const double ox = w[L.OB + j * 3], oy = w[L.OB + j * 3 + 1];
-        const double s = w[L.S + k * M + j], lam = w[L.L + k * M + j];
+        const double lam = w[L.L + k * M + j];
         const double inv = w[L.DS + k * M + j], sig = lam * inv;
         a0 += sig; a1 = fma(sig, ox, a1); a2 = fma(sig, oy, a2);
         a3 = fma(sig * ox, ox, a3); a4 = fma(sig * ox, oy, a4); a5 = fma(sig * oy, oy, a5);
         l0 += lam; l1 = fma(lam, ox, l1); l2 = fma(lam, oy, l2);
         if (with_rhs) {
-          const double wt = mu_bar * inv - sig * (w[L.C + k * M + j] - s);
+          const double g = w[L.C + k * M + j];
+          const double wt = mu_bar * inv - sig * (g - fmax(g, floor_s));
           r0 += wt; r1 = fma(wt, ox, r1); r2 = fma(wt, oy, r2);
         }
       }
@@ -533,7 +532,7 @@ struct MpcSolver {
       if (rhs) v = -v;
       if (k < H) {
         const double* sm = w + L.SUM + k * 12 + (rhs ? 9 : 6);
-        const double ge = w[L.JE + k * (NY + NH) + i], gx = w[L.JX + k * (NY + NH) + i], gy = w[L.JY + k * (NY + NH) + i];
+        const double ge = w[L.JE + k * NY + i], gx = w[L.JX + k * NY + i], gy = w[L.JY + k * NY + i];
         const double cg = sm[0] * ge - sm[1] * gx - sm[2] * gy;      // sum_j wt_j grad c_j
         v += rhs ? cg : -cg;
       }
@@ -568,32 +567,61 @@ struct MpcSolver {
   // stage Hessians G_k = hess l_k - sum lam hess c + sum sigma grad c grad c' + bound sigmas + costate curvature
   SCB_HD void stage_hessians() {
     double* Gm = w + L.G;
+    // pass 1 (lanes over stages): all curvature of stage k is the Hessian of ONE scalar function of y,
+    //   Psi_k = sum_c mu_{k+1,c} F_c(y) - Lam0 E(y) + LamX PX(y) + LamY PY(y),
+    // evaluated with second-order jets; only its 21-entry Hessian is kept.  Skipped in Gauss-Newton mode.
+    if constexpr (!Mod::LINEAR) {
+      for (int k = lane; k <= H; k += LANES) {
+        double* Gk = Gm + k * NH;
+        if (k == H || gauss_newton) {
+#pragma unroll
+          for (int e = 0; e < NH; ++e) Gk[e] = 0.0;
+          continue;
+        }
+        J y[NY], F[NX], P1, Q1, P2, Q2, E, PX, PY;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) jvar(y[i], w[L.X + k * NX + i], i);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) jvar(y[NX + i], w[L.Z + k * NU + i], NX + i);
+        Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
+        barrier_jets(y, P1, Q1, P2, Q2, E, PX, PY);
+        const double* sm = w + L.SUM + k * 12;
+        const double* mu = w + L.MU + (k + 1) * NX;
+#pragma unroll
+        for (int e = 0; e < NH; ++e) {
+          double v = -sm[6] * E.h[e] + sm[7] * PX.h[e] + sm[8] * PY.h[e];
+#pragma unroll
+          for (int c = 0; c < NX; ++c) v = fma(mu[c], F[c].h[e], v);
+          Gk[e] = v;
+        }
+      }
+      sync();
+    }
+    // pass 2 (lanes over entries): cost Hessian, barrier terms sum sigma grad c grad c', linear-model curvature
     for (int t = lane; t < (H + 1) * NH; t += LANES) {
       const int k = t / NH, e = t - k * NH;
       // unpack (i, j) of packed entry e
       int i = 0, rem = e;
       while (rem >= NY - i) { rem -= NY - i; ++i; }
       const int j = i + rem;
-      double v = 0.0;
-      if (i == j && i < NX) v = 2.0 * Qs[i];
+      double v = Mod::LINEAR ? 0.0 : Gm[t];
+      if (i == j && i < NX) v += 2.0 * Qs[i];
       if (k < H) {
         const double* sm = w + L.SUM + k * 12;
-        const double* je = w + L.JE + k * (NY + NH);
-        const double* jx = w + L.JX + k * (NY + NH);
-        const double* jy = w + L.JY + k * (NY + NH);
-        // - sum_j lam_j hess c_j   (exact Lagrangian Hessian only; dropped in Gauss-Newton mode)
-        if (!gauss_newton) v -= sm[6] * je[NY + e] - sm[7] * jx[NY + e] - sm[8] * jy[NY + e];
+        const double* je = w + L.JE + k * NY;
+        const double* jx = w + L.JX + k * NY;
+        const double* jy = w + L.JY + k * NY;
+        if (Mod::LINEAR && !gauss_newton) {
+          // hess E is constant: 2 w0 (e0 e0' + e1 e1') + 2 w1 (R0 R0' + R1 R1');  PX, PY are linear
+          const double* R0 = w + L.AUX + NX * NX + NX * NU;
+          const double* R1 = R0 + NY;
+          const double d = (i == j && i < 2) ? 1.0 : 0.0;
+          v -= sm[6] * (2.0 * w0 * d + 2.0 * w1 * (R0[i] * R0[j] + R1[i] * R1[j]));
+        }
         // + sum_j sigma_j grad c_j grad c_j'
         const double ei = je[i], ej = je[j], xi = jx[i], xj = jx[j], yi = jy[i], yj = jy[j];
         v += sm[0] * ei * ej - sm[1] * (ei * xj + xi * ej) - sm[2] * (ei * yj + yi * ej) + sm[3] * xi * xj +
              sm[4] * (xi * yj + yi * xj) + sm[5] * yi * yj;
-        // + sum_c mu_{k+1,c} hess F_c
-        if (!Mod::LINEAR && !gauss_newton) {
-          const double* FH = w + L.FH + k * NX * NH;
-          const double* mu = w + L.MU + (k + 1) * NX;
-#pragma unroll
-          for (int c = 0; c < NX; ++c) v = fma(mu[c], FH[c * NH + e], v);
-        }
       }
       Gm[t] = v;
     }
@@ -876,10 +904,7 @@ struct MpcSolver {
     // penalty-barrier merit  psi(z) = J(z) + sum_i rho(g_i(z)),  rho(g) = -mu log g  (g >= mu/nu), linear below.
     auto reset_slacks = [&](double floor_) {
       // s -> S, 1/s -> DS (the only division per constraint per iteration; everything else multiplies)
-      for (int t = lane; t < H * M; t += LANES) {
-        const double sv = fmax(w[L.C + t], floor_);
-        w[L.S + t] = sv; w[L.DS + t] = 1.0 / sv;
-      }
+      for (int t = lane; t < H * M; t += LANES) w[L.DS + t] = 1.0 / fmax(w[L.C + t], floor_);
       for (int q = lane; q < L.NS; q += LANES) {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
         const double sv = fmax(simple_value(c, w + L.Z, w + L.X), floor_);
@@ -954,7 +979,7 @@ struct MpcSolver {
       SCB_PH(3);
       // Newton system: exact Lagrangian Hessian first; if the reduced matrix is not positive definite,
       // fall back to the Gauss-Newton stage Hessians (PSD by construction) before any diagonal shift
-      stage_sums(mu_bar, true);
+      stage_sums(mu_bar, true, floor_s);
       gauss_newton = false;
       stage_hessians();
       SCB_PH(4);
@@ -988,10 +1013,10 @@ struct MpcSolver {
         double dg = 0.0;
 #pragma unroll
         for (int i = 0; i < NY; ++i) {
-          const double gi = w[L.JE + k * (NY + NH) + i] - ob[0] * w[L.JX + k * (NY + NH) + i] - ob[1] * w[L.JY + k * (NY + NH) + i];
+          const double gi = w[L.JE + k * NY + i] - ob[0] * w[L.JX + k * NY + i] - ob[1] * w[L.JY + k * NY + i];
           dg = fma(gi, dy[i], dg);
         }
-        const double g = w[L.C + t], s = w[L.S + t], lam = w[L.L + t];
+        const double g = w[L.C + t], s = fmax(g, floor_s), lam = w[L.L + t];
         const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) * w[L.DS + t];
         w[L.DL + t] = dl;
         if (ds < 0.0) ap = fmin(ap, -tau * s / ds);
