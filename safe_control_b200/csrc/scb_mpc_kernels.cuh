@@ -17,8 +17,13 @@ constexpr int kMpcMaxObs = 64;
 constexpr int kMpcMaxH = 16;
 constexpr int kMpcLanes = 32;
 
+#ifndef SCB_MPC_MAXTHREADS
+#define SCB_MPC_MAXTHREADS 384       // register cap (65536 / 384 = 170 regs): up to 12 agent-warps per CTA
+#endif
+constexpr int kMpcMaxGroups = SCB_MPC_MAXTHREADS / kMpcLanes;
+
 template <int MODEL, int LANES>
-__global__ void mpc_kernel(const __grid_constant__ scb_params p, int N, int M, int H, int ws_doubles,
+__global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid_constant__ scb_params p, int N, int M, int H, int ws_doubles,
                            const double* __restrict__ X, const double* __restrict__ Uref,
                            const double* __restrict__ goal, const double* __restrict__ u_prev,
                            const int32_t* __restrict__ track, const double* __restrict__ OBS, long stride,
@@ -85,7 +90,7 @@ inline int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* 
   const size_t budget = 220 * 1024;
   int gpb = (int)(budget / per);
   if (gpb < 1) return SCB_ERR_TOO_LARGE;
-  if (gpb > 1024 / kMpcLanes) gpb = 1024 / kMpcLanes;
+  if (gpb > kMpcMaxGroups) gpb = kMpcMaxGroups;
   const long need = ((long)N + gpb - 1) / gpb;
   if (need < sm_count) {                       // small batch: spread over all SMs first
     gpb = (int)(((long)N + sm_count - 1) / sm_count);
