@@ -219,7 +219,7 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
     const int NXT = NX + NU, NV = NXT + NU;
     L.PM = take((H + 1) * NXT * NXT); L.PV = take((H + 1) * NXT);
     L.KG = take(H * NU * NXT); L.KF = take(H * NU);
-    L.TM = take(NXT * NV); L.MM = take(NV * NV); L.MV = take(NV);
+    L.TM = take((NV + 1) * NV); L.MM = take(NU * NV); L.MV = take(0);
   }
   L.DY = take((H + 1) * NY);
   L.ZT = take(L.n); L.XT = take((H + 1) * NX); L.RG = take(L.n);
@@ -654,7 +654,10 @@ struct MpcSolver {
   // y-index (x, u) of the stage variable v-index, or -1 for the u_{k-1} block
   static SCB_HD int v2y(int c) { return c < NX ? c : (c < NXT ? -1 : NX + (c - NXT)); }
 
-  // backward sweep with diagonal shift `delta` on Muu; false if some Muu_k is not positive definite
+  // backward sweep with diagonal shift `delta` on Muu; false if some Muu_k is not positive definite.
+  // Lane c owns COLUMN c of the stage matrix M_k = Hs_k + F_k' P_{k+1} F_k (c < NV) and lane NV the vector
+  // m_k = h_k + F_k' p_{k+1}: t_c = P f_c and M[:, c] = Hs[:, c] + F' t_c need no cross-lane data, so a stage is
+  // two barriers (publish the input columns of M; publish P_k, K_k), everything else lives in registers.
   SCB_HD bool riccati_backward(double delta) {
     double* PM = w + L.PM;
     double* PV = w + L.PV;
@@ -670,60 +673,83 @@ struct MpcSolver {
     for (int t = lane; t < NXT; t += LANES) PV[H * NXT + t] = (t < NX) ? -gam[H * NY + t] : 0.0;
     sync();
     bool ok = true;
+    double* MU_ = w + L.MM;                         // published input columns: MU_[i * NV + r] = M[r][NXT + i]
     for (int k = H - 1; k >= 0; --k) {
       const double* Pn = PM + (k + 1) * NXT * NXT;
       const double* pn = PV + (k + 1) * NXT;
-      double* T = w + L.TM;                         // T = P_{k+1} F_k   (NXT x NV)
-      for (int t = lane; t < NXT * NV; t += LANES) {
-        const int r = t / NV, c = t - r * NV;
-        double v = 0.0;
+      const double* A = w + L.A + k * NX * NX;
+      const double* B = w + L.B + k * NX * NU;
+      double Mc[NV];                                // this lane's column of M (or the vector m)
 #pragma unroll
-        for (int a = 0; a < NX; ++a) v = fma(Pn[r * NXT + a], fm(k, a, c), v);
-        if (c >= NXT) v += Pn[r * NXT + NX + (c - NXT)];
-        T[t] = v;
-      }
-      sync();
-      double* Mm = w + L.MM;                        // M = Hs_k + F_k' T  (NV x NV),  m = h_k + F_k' p_{k+1}
-      for (int t = lane; t < NV * NV + NV; t += LANES) {
-        if (t < NV * NV) {
-          const int bb = t / NV, c = t - bb * NV;
+      for (int b2 = 0; b2 < NV; ++b2) Mc[b2] = 0.0;
+      for (int c = lane; c <= NV; c += LANES) {     // (one pass: NV + 1 <= LANES on the device; sequential on the host)
+        const bool isvec = (c == NV);
+        const int ci = (c >= NXT && !isvec) ? c - NXT : -1;       // input index of an input column
+        // t = P f_c   (f_c = column c of F_k)   or   t = p_{k+1}
+        double tc[NXT];
+#pragma unroll
+        for (int r = 0; r < NXT; ++r) {
           double v = 0.0;
-          const int yb = v2y(bb), yc = v2y(c);
-          if (yb >= 0 && yc >= 0) { const int lo = yb < yc ? yb : yc, hi = yb < yc ? yc : yb; v = w[L.G + k * NH + hidx<NY>(lo, hi)]; }
-          // input-rate term R (u_k - u_{k-1})^2
-          const int ub = (bb >= NXT) ? bb - NXT : (bb >= NX ? bb - NX : -1), uc = (c >= NXT) ? c - NXT : (c >= NX ? c - NX : -1);
-          if (ub >= 0 && ub == uc) {
-            const bool sameblk = (bb >= NXT) == (c >= NXT);
-            double rr = 0.0;
+          if (isvec) v = pn[r];
+          else if (c < NX) {
 #pragma unroll
-            for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
-            v += sameblk ? rr : -rr;
+            for (int a = 0; a < NX; ++a) v = fma(Pn[r * NXT + a], A[a * NX + c], v);
+          } else if (ci >= 0) {
+#pragma unroll
+            for (int a = 0; a < NX; ++a) v = fma(Pn[r * NXT + a], B[a * NU + ci], v);
+            v += Pn[r * NXT + NX + ci];
           }
+          tc[r] = v;
+        }
+        // column of Hs_k (stage Hessian + input-rate terms) or the stage gradient h_k
+        const int yc = isvec ? -1 : v2y(c);
+        const int uc = isvec ? -1 : ((c >= NXT) ? c - NXT : (c >= NX ? c - NX : -1));
 #pragma unroll
-          for (int a = 0; a < NX; ++a) v = fma(fm(k, a, bb), T[a * NV + c], v);
-          if (bb >= NXT) v += T[(NX + bb - NXT) * NV + c];
-          if (bb == c && bb >= NXT) v += delta;
-          Mm[t] = v;
-        } else {
-          const int bb = t - NV * NV;
-          const int yb = v2y(bb);
-          double v = (yb >= 0) ? -gam[k * NY + yb] : 0.0;
-          const int ub = (bb >= NXT) ? bb - NXT : (bb >= NX ? bb - NX : -1);
-          if (ub >= 0) {
-            double rr = 0.0, du = 0.0;
+        for (int b2 = 0; b2 < NV; ++b2) {
+          const int yb = v2y(b2);
+          const int ub = (b2 >= NXT) ? b2 - NXT : (b2 >= NX ? b2 - NX : -1);
+          double v = 0.0;
+          if (isvec) {
+            if (yb >= 0) v = -gam[k * NY + yb];
+            if (ub >= 0) {
+              double rr = 0.0, du = 0.0;
 #pragma unroll
-            for (int i = 0; i < NU; ++i)
-              if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
-            v += (bb >= NXT) ? rr * du : -rr * du;
+              for (int i = 0; i < NU; ++i)
+                if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
+              v += (b2 >= NXT) ? rr * du : -rr * du;
+            }
+          } else {
+            if (yb >= 0 && yc >= 0) { const int lo = yb < yc ? yb : yc, hi = yb < yc ? yc : yb; v = w[L.G + k * NH + hidx<NY>(lo, hi)]; }
+            if (ub >= 0 && ub == uc) {
+              double rr = 0.0;
+#pragma unroll
+              for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
+              v += ((b2 >= NXT) == (c >= NXT)) ? rr : -rr;
+            }
+            if (b2 == c && b2 >= NXT) v += delta;
           }
+          // + (F' t)[b2]
+          if (b2 < NX) {
 #pragma unroll
-          for (int a = 0; a < NX; ++a) v = fma(fm(k, a, bb), pn[a], v);
-          if (bb >= NXT) v += pn[NX + bb - NXT];
-          w[L.MV + bb] = v;
+            for (int a = 0; a < NX; ++a) v = fma(A[a * NX + b2], tc[a], v);
+          } else if (b2 >= NXT) {
+#pragma unroll
+            for (int a = 0; a < NX; ++a) v = fma(B[a * NU + (b2 - NXT)], tc[a], v);
+            v += tc[NX + (b2 - NXT)];
+          }
+          Mc[b2] = v;
+        }
+        if (ci >= 0) {
+#pragma unroll
+          for (int r = 0; r < NV; ++r) MU_[ci * NV + r] = Mc[r];
+        }
+        if (LANES == 1) {                            // host-sim: one lane plays all columns -> stash them
+#pragma unroll
+          for (int r = 0; r < NV; ++r) w[L.TM + c * NV + r] = Mc[r];
         }
       }
       sync();
-      // Muu = L L' (NU x NU), every lane redundantly; gains K = -Muu^-1 Mux, kff = -Muu^-1 m_u, lanes over columns
+      // Muu = L L' (NU x NU) from the published input columns, every lane redundantly
       double Lu[NU][NU];
 #pragma unroll
       for (int i = 0; i < NU; ++i) {
@@ -732,7 +758,7 @@ struct MpcSolver {
       }
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
-        double d = Mm[(NXT + j) * NV + NXT + j];
+        double d = MU_[j * NV + NXT + j];
 #pragma unroll
         for (int t = 0; t < NU; ++t) if (t < j) d -= Lu[j][t] * Lu[j][t];
         if (!(d > 1e-300) || !(d < 1e300)) ok = false;
@@ -741,7 +767,7 @@ struct MpcSolver {
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
           if (i > j) {
-            double v = Mm[(NXT + i) * NV + NXT + j];
+            double v = MU_[j * NV + NXT + i];
 #pragma unroll
             for (int t = 0; t < NU; ++t) if (t < j) v -= Lu[i][t] * Lu[j][t];
             Lu[i][j] = v * inv;
@@ -749,12 +775,19 @@ struct MpcSolver {
         }
       }
       if (!ok) break;
+      // gains for this lane's column (K[:, c] or kff), then its column of P_k (or p_k)
       double* Kg = w + L.KG + k * NU * NXT;
       double* Kf = w + L.KF + k * NU;
-      for (int c = lane; c <= NXT; c += LANES) {      // column c < NXT of Mux, or c == NXT: m_u
+      double* Pk = PM + k * NXT * NXT;
+      for (int c = lane; c <= NV; c += LANES) {
+        if (c >= NXT && c < NV) continue;            // input columns carry no gain
+        if (LANES == 1) {
+#pragma unroll
+          for (int r = 0; r < NV; ++r) Mc[r] = w[L.TM + c * NV + r];
+        }
         double rhs[NU];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) rhs[i] = (c < NXT) ? -Mm[(NXT + i) * NV + c] : -w[L.MV + NXT + i];
+        for (int i = 0; i < NU; ++i) rhs[i] = -Mc[NXT + i];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
           double v = rhs[i];
@@ -769,27 +802,17 @@ struct MpcSolver {
           for (int t = 0; t < NU; ++t) if (t > ii) v -= Lu[t][ii] * rhs[t];
           rhs[ii] = v * Lu[ii][ii];
         }
+        const bool isvec = (c == NV);
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          if (c < NXT) Kg[i * NXT + c] = rhs[i]; else Kf[i] = rhs[i];
+          if (isvec) Kf[i] = rhs[i]; else Kg[i * NXT + c] = rhs[i];
         }
-      }
-      sync();
-      // P_k = Mxx + Mxu K,  p_k = m_x + Mxu kff
-      double* Pk = PM + k * NXT * NXT;
-      for (int t = lane; t < NXT * NXT + NXT; t += LANES) {
-        if (t < NXT * NXT) {
-          const int r = t / NXT, c = t - r * NXT;
-          double v = Mm[r * NV + c];
 #pragma unroll
-          for (int i = 0; i < NU; ++i) v = fma(Mm[r * NV + NXT + i], Kg[i * NXT + c], v);
-          Pk[t] = v;
-        } else {
-          const int r = t - NXT * NXT;
-          double v = w[L.MV + r];
+        for (int r = 0; r < NXT; ++r) {
+          double v = Mc[r];
 #pragma unroll
-          for (int i = 0; i < NU; ++i) v = fma(Mm[r * NV + NXT + i], Kf[i], v);
-          PV[k * NXT + r] = v;
+          for (int i = 0; i < NU; ++i) v = fma(MU_[i * NV + r], rhs[i], v);
+          if (isvec) PV[k * NXT + r] = v; else Pk[r * NXT + c] = v;
         }
       }
       sync();
