@@ -18,7 +18,7 @@ constexpr int kMpcMaxH = 16;
 constexpr int kMpcLanes = 32;
 
 #ifndef SCB_MPC_MAXTHREADS
-#define SCB_MPC_MAXTHREADS 384       // register cap (65536 / 384 = 170 regs): up to 12 agent-warps per CTA
+#define SCB_MPC_MAXTHREADS 256       // measured (cfg3): 256 threads (255 regs, 8 agent-warps) 8.3 ms, 384 (168 regs + spills) 8.9 ms, 512 9.5 ms
 #endif
 constexpr int kMpcMaxGroups = SCB_MPC_MAXTHREADS / kMpcLanes;
 
