@@ -192,7 +192,7 @@ struct MpcModel<SCB_QUAD_3D> {
 struct MpcLayout {
   int H, M, n, NS;
   int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, DZ, PM, PV, KG, KF,
-      TM, MM, MV, DY, ZT, XT, RG, AUX;
+      TM, MM, MV, PT2, DY, ZT, XT, RG, AUX;
   int total;
 };
 
@@ -219,7 +219,8 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
     const int NXT = NX + NU, NV = NXT + NU;
     L.PM = take((H + 1) * NXT * NXT); L.PV = take((H + 1) * NXT);
     L.KG = take(H * NU * NXT); L.KF = take(H * NU);
-    L.TM = take((NV + 1) * NV); L.MM = take(NU * NV); L.MV = take(0);
+    L.TM = take(NXT * NV + NV * NV + NV); L.MM = take(NU * NV); L.MV = take(0);
+    L.PT2 = take((NV + 1) * NV);      // host-sim only scratch (LANES == 1 plays all columns); tiny
   }
   L.DY = take((H + 1) * NY);
   L.ZT = take(L.n); L.XT = take((H + 1) * NX); L.RG = take(L.n);
@@ -674,78 +675,76 @@ struct MpcSolver {
     sync();
     bool ok = true;
     double* MU_ = w + L.MM;                         // published input columns: MU_[i * NV + r] = M[r][NXT + i]
+    double* FD = w + L.TM;                          // dense F_k            (NXT x NV)
+    double* HS = FD + NXT * NV;                     // dense Hs_k           (NV x NV): stage Hessian + rate terms
+    double* HV = HS + NV * NV;                      // h_k                  (NV)
     for (int k = H - 1; k >= 0; --k) {
       const double* Pn = PM + (k + 1) * NXT * NXT;
       const double* pn = PV + (k + 1) * NXT;
-      const double* A = w + L.A + k * NX * NX;
-      const double* B = w + L.B + k * NX * NU;
-      double Mc[NV];                                // this lane's column of M (or the vector m)
+      // (a) dense blocks of this stage, lanes over entries: afterwards every lane runs the SAME straight-line code
+      for (int t = lane; t < NXT * NV + NV * NV + NV; t += LANES) {
+        if (t < NXT * NV) {
+          const int a2 = t / NV, c = t - a2 * NV;
+          FD[t] = fm(k, a2, c);
+        } else if (t < NXT * NV + NV * NV) {
+          const int e = t - NXT * NV, b2 = e / NV, c = e - b2 * NV;
+          const int yb = v2y(b2), yc = v2y(c);
+          const int ub = (b2 >= NXT) ? b2 - NXT : (b2 >= NX ? b2 - NX : -1), uc = (c >= NXT) ? c - NXT : (c >= NX ? c - NX : -1);
+          double v = 0.0;
+          if (yb >= 0 && yc >= 0) { const int lo = yb < yc ? yb : yc, hi = yb < yc ? yc : yb; v = w[L.G + k * NH + hidx<NY>(lo, hi)]; }
+          if (ub >= 0 && ub == uc) {
+            double rr = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
+            v += ((b2 >= NXT) == (c >= NXT)) ? rr : -rr;
+          }
+          if (b2 == c && b2 >= NXT) v += delta;
+          HS[e] = v;
+        } else {
+          const int b2 = t - NXT * NV - NV * NV;
+          const int yb = v2y(b2);
+          const int ub = (b2 >= NXT) ? b2 - NXT : (b2 >= NX ? b2 - NX : -1);
+          double v = (yb >= 0) ? -gam[k * NY + yb] : 0.0;
+          if (ub >= 0) {
+            double rr = 0.0, du = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; ++i)
+              if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
+            v += (b2 >= NXT) ? rr * du : -rr * du;
+          }
+          HV[b2] = v;
+        }
+      }
+      sync();
+      // (b) lane c: t = P f_c (or p), M[:, c] = Hs[:, c] + F' t  (or m = h + F' p)
+      double Mc[NV];
 #pragma unroll
       for (int b2 = 0; b2 < NV; ++b2) Mc[b2] = 0.0;
       for (int c = lane; c <= NV; c += LANES) {     // (one pass: NV + 1 <= LANES on the device; sequential on the host)
         const bool isvec = (c == NV);
-        const int ci = (c >= NXT && !isvec) ? c - NXT : -1;       // input index of an input column
-        // t = P f_c   (f_c = column c of F_k)   or   t = p_{k+1}
+        const int cc = isvec ? 0 : c;
         double tc[NXT];
 #pragma unroll
         for (int r = 0; r < NXT; ++r) {
           double v = 0.0;
-          if (isvec) v = pn[r];
-          else if (c < NX) {
 #pragma unroll
-            for (int a = 0; a < NX; ++a) v = fma(Pn[r * NXT + a], A[a * NX + c], v);
-          } else if (ci >= 0) {
-#pragma unroll
-            for (int a = 0; a < NX; ++a) v = fma(Pn[r * NXT + a], B[a * NU + ci], v);
-            v += Pn[r * NXT + NX + ci];
-          }
-          tc[r] = v;
+          for (int a2 = 0; a2 < NXT; ++a2) v = fma(Pn[r * NXT + a2], FD[a2 * NV + cc], v);
+          tc[r] = isvec ? pn[r] : v;
         }
-        // column of Hs_k (stage Hessian + input-rate terms) or the stage gradient h_k
-        const int yc = isvec ? -1 : v2y(c);
-        const int uc = isvec ? -1 : ((c >= NXT) ? c - NXT : (c >= NX ? c - NX : -1));
 #pragma unroll
         for (int b2 = 0; b2 < NV; ++b2) {
-          const int yb = v2y(b2);
-          const int ub = (b2 >= NXT) ? b2 - NXT : (b2 >= NX ? b2 - NX : -1);
-          double v = 0.0;
-          if (isvec) {
-            if (yb >= 0) v = -gam[k * NY + yb];
-            if (ub >= 0) {
-              double rr = 0.0, du = 0.0;
+          double v = isvec ? HV[b2] : HS[b2 * NV + cc];
 #pragma unroll
-              for (int i = 0; i < NU; ++i)
-                if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
-              v += (b2 >= NXT) ? rr * du : -rr * du;
-            }
-          } else {
-            if (yb >= 0 && yc >= 0) { const int lo = yb < yc ? yb : yc, hi = yb < yc ? yc : yb; v = w[L.G + k * NH + hidx<NY>(lo, hi)]; }
-            if (ub >= 0 && ub == uc) {
-              double rr = 0.0;
-#pragma unroll
-              for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
-              v += ((b2 >= NXT) == (c >= NXT)) ? rr : -rr;
-            }
-            if (b2 == c && b2 >= NXT) v += delta;
-          }
-          // + (F' t)[b2]
-          if (b2 < NX) {
-#pragma unroll
-            for (int a = 0; a < NX; ++a) v = fma(A[a * NX + b2], tc[a], v);
-          } else if (b2 >= NXT) {
-#pragma unroll
-            for (int a = 0; a < NX; ++a) v = fma(B[a * NU + (b2 - NXT)], tc[a], v);
-            v += tc[NX + (b2 - NXT)];
-          }
+          for (int a2 = 0; a2 < NXT; ++a2) v = fma(FD[a2 * NV + b2], tc[a2], v);
           Mc[b2] = v;
         }
-        if (ci >= 0) {
+        if (c >= NXT && !isvec) {
 #pragma unroll
-          for (int r = 0; r < NV; ++r) MU_[ci * NV + r] = Mc[r];
+          for (int r = 0; r < NV; ++r) MU_[(c - NXT) * NV + r] = Mc[r];
         }
         if (LANES == 1) {                            // host-sim: one lane plays all columns -> stash them
 #pragma unroll
-          for (int r = 0; r < NV; ++r) w[L.TM + c * NV + r] = Mc[r];
+          for (int r = 0; r < NV; ++r) w[L.PT2 + c * NV + r] = Mc[r];
         }
       }
       sync();
@@ -783,7 +782,7 @@ struct MpcSolver {
         if (c >= NXT && c < NV) continue;            // input columns carry no gain
         if (LANES == 1) {
 #pragma unroll
-          for (int r = 0; r < NV; ++r) Mc[r] = w[L.TM + c * NV + r];
+          for (int r = 0; r < NV; ++r) Mc[r] = w[L.PT2 + c * NV + r];
         }
         double rhs[NU];
 #pragma unroll
