@@ -490,32 +490,54 @@ struct MpcSolver {
   }
 
   // weighted obstacle sums of stage k: which = 0 (sigma moments, 6) / 1 (lambda, 3) / 2 (rhs weights, 3)
+  // segmented xor-shuffle sum over the `seg` (power of two) consecutive lanes this lane belongs to
+  static SCB_HD double seg_sum(double v, int seg) {
+#if defined(__CUDA_ARCH__)
+    for (int o = seg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(G::gmask(), v, o, 32);
+#endif
+    (void)seg;
+    return v;
+  }
+
+  // mode 0: lambda sums only (dual residual / costates); 1: + sigma moments and Newton-rhs weights
   SCB_HD void stage_sums(double mu_bar, bool with_rhs, double floor_s = 0.0) {
-    // lanes own obstacles (registers hold ox, oy), loop over stages, 12 partial sums per stage reduced by
-    // xor-shuffles: one division per (stage, obstacle), no divergent per-sum code paths
-    for (int k = 0; k < H; ++k) {
+    // A segment of `seg` lanes (smallest power of two >= M, capped at LANES) owns one stage at a time, so
+    // LANES/seg stages are processed per pass and each of the <= 12 partial sums needs log2(seg) shuffle steps.
+    int seg = 1;
+    while (seg < M && seg < LANES) seg <<= 1;
+    const int spp = LANES / seg;                       // stages per pass
+    const int sub = lane / seg, jl = lane - sub * seg;
+    for (int k0 = 0; k0 < H; k0 += spp) {
+      const int k = k0 + sub;
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, l0 = 0, l1 = 0, l2 = 0, r0 = 0, r1 = 0, r2 = 0;
-      for (int j = lane; j < M; j += LANES) {
-        const double ox = w[L.OB + j * 3], oy = w[L.OB + j * 3 + 1];
-        const double lam = w[L.L + k * M + j];
-        const double inv = w[L.DS + k * M + j], sig = lam * inv;
-        a0 += sig; a1 = fma(sig, ox, a1); a2 = fma(sig, oy, a2);
-        a3 = fma(sig * ox, ox, a3); a4 = fma(sig * ox, oy, a4); a5 = fma(sig * oy, oy, a5);
-        l0 += lam; l1 = fma(lam, ox, l1); l2 = fma(lam, oy, l2);
-        if (with_rhs) {
-          const double g = w[L.C + k * M + j];
-          const double wt = mu_bar * inv - sig * (g - fmax(g, floor_s));
-          r0 += wt; r1 = fma(wt, ox, r1); r2 = fma(wt, oy, r2);
+      if (k < H) {
+        for (int j = jl; j < M; j += seg) {
+          const double ox = w[L.OB + j * 3], oy = w[L.OB + j * 3 + 1];
+          const double lam = w[L.L + k * M + j];
+          l0 += lam; l1 = fma(lam, ox, l1); l2 = fma(lam, oy, l2);
+          if (with_rhs) {
+            const double inv = w[L.DS + k * M + j], sig = lam * inv;
+            a0 += sig; a1 = fma(sig, ox, a1); a2 = fma(sig, oy, a2);
+            a3 = fma(sig * ox, ox, a3); a4 = fma(sig * ox, oy, a4); a5 = fma(sig * oy, oy, a5);
+            const double g = w[L.C + k * M + j];
+            const double wt = mu_bar * inv - sig * (g - fmax(g, floor_s));
+            r0 += wt; r1 = fma(wt, ox, r1); r2 = fma(wt, oy, r2);
+          }
         }
       }
-      a0 = G::sum(a0); a1 = G::sum(a1); a2 = G::sum(a2); a3 = G::sum(a3); a4 = G::sum(a4); a5 = G::sum(a5);
-      l0 = G::sum(l0); l1 = G::sum(l1); l2 = G::sum(l2);
-      if (with_rhs) { r0 = G::sum(r0); r1 = G::sum(r1); r2 = G::sum(r2); }
-      if (lane == 0) {
+      l0 = seg_sum(l0, seg); l1 = seg_sum(l1, seg); l2 = seg_sum(l2, seg);
+      if (with_rhs) {
+        a0 = seg_sum(a0, seg); a1 = seg_sum(a1, seg); a2 = seg_sum(a2, seg);
+        a3 = seg_sum(a3, seg); a4 = seg_sum(a4, seg); a5 = seg_sum(a5, seg);
+        r0 = seg_sum(r0, seg); r1 = seg_sum(r1, seg); r2 = seg_sum(r2, seg);
+      }
+      if (jl == 0 && k < H) {
         double* sm = w + L.SUM + k * 12;
-        sm[0] = a0; sm[1] = a1; sm[2] = a2; sm[3] = a3; sm[4] = a4; sm[5] = a5;
         sm[6] = l0; sm[7] = l1; sm[8] = l2;
-        if (with_rhs) { sm[9] = r0; sm[10] = r1; sm[11] = r2; }
+        if (with_rhs) {
+          sm[0] = a0; sm[1] = a1; sm[2] = a2; sm[3] = a3; sm[4] = a4; sm[5] = a5;
+          sm[9] = r0; sm[10] = r1; sm[11] = r2;
+        }
       }
     }
     sync();
