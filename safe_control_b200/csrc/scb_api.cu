@@ -46,7 +46,7 @@ static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M
     cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
     return SCB_OK;                                                                                         \
   }
-  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 4) GO(8, 8) GO(4, 8)
+  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 3) GO(8, 4) GO(8, 8) GO(4, 5) GO(4, 8)
 #undef GO
   return SCB_ERR_TOO_LARGE;
 }
@@ -60,7 +60,7 @@ static int launch_od_m(const scb_params& p, const LaunchGeom& g, int N, int M, c
     odcbf_kernel<MODEL, NW, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active); \
     return SCB_OK;                                                                                            \
   }
-  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 4) GO(8, 8) GO(4, 8)
+  GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 3) GO(8, 4) GO(8, 8) GO(4, 5) GO(4, 8)
 #undef GO
   return SCB_ERR_TOO_LARGE;
 }

@@ -81,19 +81,26 @@ struct LaunchGeom {
 };
 
 // total rows -> (LANES, RPL); returns false if beyond the compiled instantiations.
-// Compiled: (32,1) (32,2) (32,4) (8,4) (8,8) (4,8).  `force_lanes` (0 = auto) is a tuning override
-// (env SCB_QP_LANES), honoured only when an instantiation exists for it.
+// Compiled (LANES, RPL): (32,1) (32,2) (32,4)  (8,3) (8,4) (8,8)  (4,5) (4,8); RPL slots are fully unrolled, so the
+// smallest RPL >= ceil(rows / LANES) is used (rows = 20 for M = 16: (8,3) and (4,5) waste no slot).
+// `force_lanes` (0 = auto) is a tuning override (env SCB_QP_LANES), honoured only when an instantiation exists.
+inline int pick_rpl(int lanes, int rows) {
+  const int need = (rows + lanes - 1) / lanes;
+  if (lanes == 32) return need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : 0;
+  if (lanes == 8) return need <= 3 ? 3 : need <= 4 ? 4 : need <= 8 ? 8 : 0;
+  if (lanes == 4) return need <= 5 ? 5 : need <= 8 ? 8 : 0;
+  return 0;
+}
+
 inline bool pick_geom(long N, int rows, int sm_count, LaunchGeom& g, int force_lanes = 0) {
   // measured on B200 (tools/sweep_qp.py, M = 16, us per launch, lanes 32 / 8 / 4):
   //   N = 1024: 4.42 / 5.14 / 7.28     N = 8192: 10.8 / 6.47 / 8.27     N = 1M: 1186 / 420 / 390
   // -> warp per QP up to ~16 warps per SM, 8 lanes per QP for mid-size batches, 4 lanes per QP beyond ~32k agents.
   const bool small = N <= (long)sm_count * 16;
   int lanes = (small || rows > 64) ? 32 : ((rows <= 32 && N > 32768) ? 4 : 8);
-  if (force_lanes == 32 || (force_lanes == 8 && rows <= 64) || (force_lanes == 4 && rows <= 32)) lanes = force_lanes;
+  if ((force_lanes == 32 || force_lanes == 8 || force_lanes == 4) && pick_rpl(force_lanes, rows) > 0) lanes = force_lanes;
   g.lanes = lanes;
-  if (lanes == 32) g.rpl = rows <= 32 ? 1 : rows <= 64 ? 2 : rows <= 128 ? 4 : 0;
-  else if (lanes == 8) g.rpl = rows <= 32 ? 4 : 8;
-  else g.rpl = 8;
+  g.rpl = pick_rpl(lanes, rows);
   if (g.rpl == 0) return false;
   const long groups_per_block = kBlock / g.lanes;
   long blocks = (N + groups_per_block - 1) / groups_per_block;
