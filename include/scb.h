@@ -170,6 +170,82 @@ int scb_mpccbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M, int H
                           double* U, int32_t* status, double* pred_x, double* pred_u,
                           int32_t* iters, double* kkt);
 
+/* ---- closed loop: the rest of LocalTrackingController.control_step()  (tracking.py:559-668) ---- */
+/* Everything either side of the solve, for N agents on the device, so that run_all_steps
+ * (tracking.py:711-747) never leaves the GPU:
+ *   waypoint state machine + update_goal            tracking.py:497-535, 569-578
+ *   get_nearest_unpassed_obs                        tracking.py:345-403
+ *   nominal_input / stop / rotate_to / has_stopped  robots/<model>.py via robots/robot.py:401-433
+ *   VelocityTrackingYaw (SingleIntegrator2D yaw)    attitude_control/velocity_tracking_yaw.py:35-62
+ *   is_collide_unknown (known obstacles)            tracking.py:445-495
+ *   robot.step                                      robots/robot.py:441-453 -> robots/<model>.py step
+ *   step_dyn_obs                                    dynamic_env/main.py:54-58, 152
+ *   return code                                     tracking.py:627-668
+ */
+enum scb_state_machine { SCB_SM_IDLE = 0, SCB_SM_TRACK = 1, SCB_SM_STOP = 2, SCB_SM_ROTATE = 3 };  /* tracking.py:49 */
+enum scb_controller { SCB_CTRL_CBF_QP = 0, SCB_CTRL_OPTIMAL_DECAY = 1, SCB_CTRL_MPC_CBF = 2 };
+
+/* Obstacle selection only.  SCENE [K, 7] is the caller's `self.obs` (shared by all agents, or
+ * [N, K, 7] with scene_stride_agent = 7 K); yaw [N] is robot.yaw (NULL: the model's own heading
+ * state, 0 for SingleIntegrator2D).  Out: OBS [N, M, 7] = the (at most M) nearest unpassed
+ * obstacles in distance order, rows beyond nobs[i] padded with the reference's dummy
+ * [1000, 1000, 0, 0, 0, 0, 0] (mpc_cbf.py:346); nobs [N] (-1 when K == 0: "obs is None");
+ * idx [N, M] int32 (may be NULL) = scene index of every selected row (-1 = pad). */
+int scb_select_obstacles(const scb_params* p, int N, int K, int M,
+                         const double* X, const double* yaw,
+                         const double* SCENE, long scene_stride_agent,
+                         double* OBS, int32_t* nobs, int32_t* idx, void* stream);
+
+/* All device pointers, caller-owned (e.g. torch tensors); float64 unless noted.  The solve
+ * buffers (Uref, OBS, nobs, U, status) are the same arrays the *_solve entry points take. */
+typedef struct scb_track {
+  int32_t controller;            /* enum scb_controller */
+  int32_t N, K, M, W, H;         /* agents, scene obstacles, obstacle slots (num_constraints, tracking.py:134-138),
+                                    max waypoints per agent, MPC horizon */
+  int32_t enable_rotation;       /* tracking.py:41 */
+  int32_t dynamic_obs;           /* 1: SCENE[:, 0:2] += SCENE[:, 3:5] dt after the selection (dynamic_env/main.py:152) */
+  int32_t att_velocity_tracking; /* SingleIntegrator2D: 1 = VelocityTrackingYaw drives yaw in 'track' (tracking.py:156-181) */
+  int32_t reserved;
+  double reached_threshold;      /* 0.3  tracking.py:52 */
+  double rotation_threshold;     /* 0.1  tracking.py:50 */
+  double k_omega, k_a, k_v;      /* nominal_input gains (robots/robot.py:401; optimal decay: 3.0, 0.5, 0.5 tracking.py:601-602) */
+  double k_a_stop;               /* DynamicUnicycle2D stop() gain: robot_spec['nominal_k_a'] or 1.0 (dynamic_unicycle2D.py:106-111) */
+  double w_max;                  /* SingleIntegrator2D rotate_to / VelocityTrackingYaw clip */
+  double att_kp;                 /* VelocityTrackingYaw kp (1.5) */
+  double wheel_base, delta_max;  /* KinematicBicycle2D nominal_input (kinematic_bicycle2D.py:55-59, 125-147) */
+  /* per-agent tracker state (in/out) */
+  double*  X;                    /* [N, nx]   robot.X */
+  double*  yaw;                  /* [N]       robot.yaw */
+  int32_t* sm;                   /* [N]       state_machine */
+  int32_t* wp_idx;               /* [N]       current_goal_index */
+  const double*  WP;             /* [N, W, 3] waypoints (after filter_waypoints) */
+  const int32_t* nwp;            /* [N] */
+  double*  goal;                 /* [N, 2]    ([N, 3] for Quad3D) self.goal, valid when has_goal; same layout as scb_mpccbf_solve's goal */
+  int32_t* has_goal;             /* [N]       0 <=> self.goal is None */
+  double*  u_att;                /* [N]       self.u_att; NaN <=> None */
+  double*  u_prev;               /* [N, nu]   MPC: last applied MPC input (do-mpc u0) */
+  int32_t* ret;                  /* [N]       control_step() return value of the last executed step: 0, -1, -2 */
+  int32_t* done;                 /* [N]       latched: run_all_steps' loop has broken (ret in {-1,-2}); such agents are frozen */
+  int32_t* nsteps;               /* [N]       control steps executed so far */
+  /* world */
+  double*  SCENE;                /* [K, 7]    self.obs, shared; stepped in place when dynamic_obs */
+  /* solve buffers */
+  double*  Uref;                 /* [N, nu] */
+  double*  OBS;                  /* [N, M, 7] */
+  int32_t* nobs;                 /* [N] */
+  double*  U;                    /* [N, nu]   get_control_input() */
+  int32_t* status;               /* [N] */
+  uint64_t* active;              /* [N, scb_active_words(M, nu)] or NULL */
+  int32_t* track_flag;           /* [N]       MPC only: scratch (state_machine == 'track') */
+  int32_t* mpc_iters;            /* [N]       MPC only, may be NULL */
+} scb_track;
+
+size_t scb_track_sizeof(void);
+/* One control_step() for every agent that is not done: 3 launches (+1 when dynamic_obs) on `stream`. */
+int scb_control_step(const scb_params* p, const scb_track* t, void* stream);
+/* n_steps control steps back to back (run_all_steps' loop body; per-agent break = the done latch). */
+int scb_run_all_steps(const scb_params* p, const scb_track* t, int n_steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,8 @@ runs in hand-written sm_100a kernels behind the C ABI in include/scb.h.
 """
 from .params import resolve_params, NotCompatibleError  # noqa: F401
 from .batched import BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, HostContext  # noqa: F401
+from .tracking import BatchedTrackingController  # noqa: F401
 from ._abi import MODEL_IDS, OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL  # noqa: F401
 
-__all__ = ["BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "HostContext", "resolve_params",
+__all__ = ["BatchedTrackingController", "BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "HostContext", "resolve_params",
            "NotCompatibleError", "MODEL_IDS", "OPTIMAL", "INFEASIBLE", "MAXITER", "NUMERICAL"]

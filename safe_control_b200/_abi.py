@@ -35,6 +35,31 @@ class ScbParams(C.Structure):
 _P = C.POINTER(ScbParams)
 _vp = C.c_void_p
 
+SM_IDLE, SM_TRACK, SM_STOP, SM_ROTATE = 0, 1, 2, 3
+SM_NAMES = {0: "idle", 1: "track", 2: "stop", 3: "rotate"}       # tracking.py:49
+SM_IDS = {v: k for k, v in SM_NAMES.items()}
+CONTROLLER_IDS = {"cbf_qp": 0, "optimal_decay_cbf_qp": 1, "mpc_cbf": 2}
+
+
+class ScbTrack(C.Structure):
+    """Mirror of `struct scb_track` (include/scb.h): closed-loop configuration + caller-owned arrays."""
+    _fields_ = [
+        ("controller", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("M", C.c_int32), ("W", C.c_int32),
+        ("H", C.c_int32), ("enable_rotation", C.c_int32), ("dynamic_obs", C.c_int32),
+        ("att_velocity_tracking", C.c_int32), ("reserved", C.c_int32),
+        ("reached_threshold", C.c_double), ("rotation_threshold", C.c_double),
+        ("k_omega", C.c_double), ("k_a", C.c_double), ("k_v", C.c_double), ("k_a_stop", C.c_double),
+        ("w_max", C.c_double), ("att_kp", C.c_double), ("wheel_base", C.c_double), ("delta_max", C.c_double),
+        ("X", _vp), ("yaw", _vp), ("sm", _vp), ("wp_idx", _vp), ("WP", _vp), ("nwp", _vp), ("goal", _vp),
+        ("has_goal", _vp), ("u_att", _vp), ("u_prev", _vp), ("ret", _vp), ("done", _vp), ("nsteps", _vp),
+        ("SCENE", _vp),
+        ("Uref", _vp), ("OBS", _vp), ("nobs", _vp), ("U", _vp), ("status", _vp), ("active", _vp),
+        ("track_flag", _vp), ("mpc_iters", _vp),
+    ]
+
+
+_T = C.POINTER(ScbTrack)
+
 # name -> (restype, argtypes); every symbol include/scb.h declares
 PROTOTYPES = {
     "scb_version": (C.c_int, []),
@@ -58,6 +83,10 @@ PROTOTYPES = {
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_mpccbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_select_obstacles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),
+    "scb_track_sizeof": (C.c_size_t, []),
+    "scb_control_step": (C.c_int, [_P, _T, _vp]),
+    "scb_run_all_steps": (C.c_int, [_P, _T, C.c_int, _vp]),
 }
 
 

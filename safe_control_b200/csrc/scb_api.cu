@@ -9,6 +9,7 @@
 
 #include "scb_kernels.cuh"
 #include "scb_mpc_kernels.cuh"
+#include "scb_track_kernels.cuh"
 
 using namespace scb;
 
@@ -171,6 +172,94 @@ int scb_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, 
                       kkt, (cudaStream_t)stream, sm_count_cached());
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+// ------------------------------------------------------------------------------ closed loop
+size_t scb_track_sizeof(void) { return sizeof(scb_track); }
+
+int scb_select_obstacles(const scb_params* p, int N, int K, int M, const double* X, const double* yaw,
+                         const double* SCENE, long sstride, double* OBS, int32_t* nobs, int32_t* idx, void* stream) {
+  if (!p || N < 0 || K < 0 || M < 0) return SCB_ERR_BAD_ARG;
+  if (p->model < 0 || p->model >= SCB_NUM_MODELS) return SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !nobs || (M > 0 && !OBS) || (K > 0 && !SCENE)) return SCB_ERR_BAD_ARG;
+  if (K > kTrackMaxScene) return SCB_ERR_TOO_LARGE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = track_grid(N, sm_count_cached());
+  const size_t smem = (size_t)(kTrackBlock / 32) * (size_t)(K > 0 ? K : 1) * sizeof(double);
+#define SEL(MODEL) case MODEL: select_kernel<MODEL><<<grid, kTrackBlock, smem, s>>>(*p, N, K, M, X, yaw, SCENE, sstride, OBS, nobs, idx); break;
+  switch (p->model) {
+    SEL(SCB_SINGLE_INTEGRATOR_2D) SEL(SCB_DYNAMIC_UNICYCLE_2D) SEL(SCB_KINEMATIC_BICYCLE_2D)
+    SEL(SCB_KINEMATIC_BICYCLE_2D_C3BF) SEL(SCB_QUAD_3D)
+  }
+#undef SEL
+  CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+static int track_check(const scb_params* p, const scb_track* t) {
+  if (!p || !t) return SCB_ERR_BAD_ARG;
+  if (t->N < 0 || t->K < 0 || t->M < 0 || t->W < 1) return SCB_ERR_BAD_ARG;
+  if (p->model < 0 || p->model >= SCB_NUM_MODELS) return SCB_ERR_BAD_ARG;
+  if (t->controller < SCB_CTRL_CBF_QP || t->controller > SCB_CTRL_MPC_CBF) return SCB_ERR_BAD_ARG;
+  if (t->K > kTrackMaxScene) return SCB_ERR_TOO_LARGE;
+  if (t->N == 0) return SCB_OK;
+  if (!t->X || !t->yaw || !t->sm || !t->wp_idx || !t->WP || !t->nwp || !t->goal || !t->has_goal || !t->u_att ||
+      !t->ret || !t->done || !t->nsteps || !t->Uref || !t->nobs || !t->U || !t->status || (t->M > 0 && !t->OBS) ||
+      (t->K > 0 && !t->SCENE))
+    return SCB_ERR_BAD_ARG;
+  if (t->controller == SCB_CTRL_MPC_CBF && (!t->u_prev || !t->track_flag || t->H < 1)) return SCB_ERR_BAD_ARG;
+  if (t->controller != SCB_CTRL_MPC_CBF && p->model == SCB_QUAD_3D) return SCB_ERR_UNSUPPORTED;
+  if (t->controller == SCB_CTRL_OPTIMAL_DECAY && p->model == SCB_SINGLE_INTEGRATOR_2D) return SCB_ERR_UNSUPPORTED;
+  return SCB_OK;
+}
+
+static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream_t s) {
+  const int smc = sm_count_cached();
+#define PRE(MODEL) case MODEL: launch_pre<MODEL>(*p, *t, s, smc); break;
+  switch (p->model) {
+    PRE(SCB_SINGLE_INTEGRATOR_2D) PRE(SCB_DYNAMIC_UNICYCLE_2D) PRE(SCB_KINEMATIC_BICYCLE_2D)
+    PRE(SCB_KINEMATIC_BICYCLE_2D_C3BF) PRE(SCB_QUAD_3D)
+  }
+#undef PRE
+  if (t->dynamic_obs && t->K > 0) dyn_obs_kernel<<<(t->K + 127) / 128, 128, 0, s>>>(t->SCENE, t->K, p->dt);
+  int rc;
+  const long stride = 7L * t->M;
+  // the solve kernels also run for agents that are done (their outputs are ignored by the post kernel)
+  if (t->controller == SCB_CTRL_CBF_QP)
+    rc = scb_cbfqp_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, t->status, t->active, s);
+  else if (t->controller == SCB_CTRL_OPTIMAL_DECAY)
+    rc = scb_odcbf_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, nullptr, nullptr, t->status,
+                         t->active, s);
+  else
+    rc = scb_mpccbf_solve(p, t->N, t->M, t->H, t->X, t->Uref, t->goal, t->u_prev, t->track_flag, t->OBS,
+                          stride, t->nobs, t->U, t->status, nullptr, nullptr, t->mpc_iters, nullptr, s);
+  if (rc != SCB_OK) return rc;
+#define POST(MODEL) case MODEL: launch_post<MODEL>(*p, *t, s, smc); break;
+  switch (p->model) {
+    POST(SCB_SINGLE_INTEGRATOR_2D) POST(SCB_DYNAMIC_UNICYCLE_2D) POST(SCB_KINEMATIC_BICYCLE_2D)
+    POST(SCB_KINEMATIC_BICYCLE_2D_C3BF) POST(SCB_QUAD_3D)
+  }
+#undef POST
+  CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+int scb_control_step(const scb_params* p, const scb_track* t, void* stream) {
+  int rc = track_check(p, t);
+  if (rc != SCB_OK || t->N == 0) return rc;
+  return control_step_impl(p, t, (cudaStream_t)stream);
+}
+
+int scb_run_all_steps(const scb_params* p, const scb_track* t, int n_steps, void* stream) {
+  int rc = track_check(p, t);
+  if (rc != SCB_OK || t->N == 0) return rc;
+  if (n_steps < 0) return SCB_ERR_BAD_ARG;
+  for (int k = 0; k < n_steps; ++k) {
+    rc = control_step_impl(p, t, (cudaStream_t)stream);
+    if (rc != SCB_OK) return rc;
+  }
   return SCB_OK;
 }
 

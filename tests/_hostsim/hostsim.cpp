@@ -4,6 +4,8 @@
 // imported by safe_control_b200, and is not a fallback: the product fails loudly without
 // libscb.so + a CUDA device.
 #include "../../safe_control_b200/csrc/scb_qp.cuh"
+#include "../../safe_control_b200/csrc/scb_track.cuh"
+#include <vector>
 #ifdef SCB_HOSTSIM_MPC
 #include "../../safe_control_b200/csrc/scb_mpc.cuh"
 #endif
@@ -116,5 +118,94 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
   return 0;
 }
 #endif
+
+
+// ---- closed loop (scb_track.cuh), LANES = 1 ------------------------------------------------------
+int hostsim_select_obstacles(const scb_params* p, int N, int K, int M, const double* X, const double* yaw,
+                             const double* SCENE, long sstride, double* OBS, int32_t* nobs, int32_t* idx) {
+  std::vector<double> keys(K > 0 ? K : 1);
+  for (int a = 0; a < N; ++a) {
+    switch (p->model) {
+#define SELCASE(MODEL)                                                                                          \
+  case MODEL: {                                                                                                 \
+    using ML = ModelLoop<MODEL>;                                                                                \
+    const double* x = X + (size_t)a * ML::NX;                                                                   \
+    const double psi = yaw ? yaw[a] : ML::yaw_of(x, 0.0);                                                       \
+    nobs[a] = select_agent<1>(K, M, SCENE + (size_t)a * sstride, x[0], x[1], psi, ML::half_angle(), keys.data(), \
+                              OBS + (size_t)a * M * 7, idx ? idx + (size_t)a * M : nullptr);                     \
+  } break;
+      SELCASE(SCB_SINGLE_INTEGRATOR_2D)
+      SELCASE(SCB_DYNAMIC_UNICYCLE_2D)
+      SELCASE(SCB_KINEMATIC_BICYCLE_2D)
+      SELCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
+      SELCASE(SCB_QUAD_3D)
+      default: return SCB_ERR_UNSUPPORTED;
+    }
+  }
+  return 0;
+}
+
+size_t hostsim_track_sizeof(void) { return sizeof(scb_track); }
+
+// same sequence as control_step_impl in scb_api.cu: pre -> [dyn obs] -> solve -> post
+int hostsim_control_step(const scb_params* p, const scb_track* t) {
+  std::vector<double> keys(t->K > 0 ? t->K : 1);
+  for (long a = 0; a < t->N; ++a) {
+    switch (p->model) {
+#define PRECASE(MODEL) case MODEL: track_pre_agent<MODEL, 1>(*p, *t, a, keys.data()); break;
+      PRECASE(SCB_SINGLE_INTEGRATOR_2D)
+      PRECASE(SCB_DYNAMIC_UNICYCLE_2D)
+      PRECASE(SCB_KINEMATIC_BICYCLE_2D)
+      PRECASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
+      PRECASE(SCB_QUAD_3D)
+      default: return SCB_ERR_UNSUPPORTED;
+    }
+  }
+  if (t->dynamic_obs)
+    for (int j = 0; j < t->K; ++j) {
+      t->SCENE[j * 7 + 0] += t->SCENE[j * 7 + 3] * p->dt;
+      t->SCENE[j * 7 + 1] += t->SCENE[j * 7 + 4] * p->dt;
+    }
+  const long stride = 7L * t->M;
+  int rc;
+  if (t->controller == SCB_CTRL_CBF_QP) {
+    rc = hostsim_cbfqp_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, t->status, t->active);
+  } else if (t->controller == SCB_CTRL_OPTIMAL_DECAY) {
+    rc = hostsim_odcbf_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, nullptr, nullptr, t->status,
+                             t->active);
+  } else {
+#ifdef SCB_HOSTSIM_MPC
+    const int nx = p->nx, nu = p->nu, ng = (p->model == SCB_QUAD_3D) ? 3 : 2;
+    rc = 0;
+    for (int a = 0; a < t->N && rc == 0; ++a) {
+      if (t->done[a]) continue;
+      if (!t->track_flag[a]) {                                     // mpc_cbf.py:379-381
+        for (int i = 0; i < nu; ++i) t->U[(size_t)a * nu + i] = t->Uref[(size_t)a * nu + i];
+        t->status[a] = SCB_OPTIMAL;
+        continue;
+      }
+      rc = hostsim_mpccbf_solve(p, 1, t->M, t->H, t->X + (size_t)a * nx, t->goal + (size_t)a * ng,
+                                t->u_prev + (size_t)a * nu, t->OBS + (size_t)a * stride, stride, t->nobs + a,
+                                t->U + (size_t)a * nu, t->status + a, nullptr, nullptr,
+                                t->mpc_iters ? t->mpc_iters + a : nullptr, nullptr);
+    }
+#else
+    rc = SCB_ERR_UNSUPPORTED;
+#endif
+  }
+  if (rc != 0) return rc;
+  for (long a = 0; a < t->N; ++a) {
+    switch (p->model) {
+#define POSTCASE(MODEL) case MODEL: track_post_agent<MODEL, 1>(*p, *t, a); break;
+      POSTCASE(SCB_SINGLE_INTEGRATOR_2D)
+      POSTCASE(SCB_DYNAMIC_UNICYCLE_2D)
+      POSTCASE(SCB_KINEMATIC_BICYCLE_2D)
+      POSTCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
+      POSTCASE(SCB_QUAD_3D)
+      default: return SCB_ERR_UNSUPPORTED;
+    }
+  }
+  return 0;
+}
 
 }  // extern "C"

@@ -94,3 +94,53 @@ def hs_mpccbf_solve(p, H, X, goal, u_prev, OBS, nobs=None):
                                   ptr(U), ptr(st), ptr(px), ptr(pu), ptr(it), ptr(kkt))
     assert rc == 0, rc
     return dict(U=U, status=st, iters=it, kkt=kkt, pred_x=px, pred_u=pu)
+
+
+# ---- closed loop (scb_track.cuh) ------------------------------------------------------------------
+def hs_select_obstacles(p, X, scene, M, yaw=None):
+    lib = hostsim()
+    X, scene = f64(X), f64(scene)
+    N, K = X.shape[0], scene.shape[0]
+    OBS = np.zeros((N, M, 7)); nobs = np.zeros(N, np.int32); idx = np.zeros((N, M), np.int32)
+    yw = None if yaw is None else f64(yaw)
+    rc = lib.hostsim_select_obstacles(C.byref(p), N, K, M, ptr(X), ptr(yw), ptr(scene), C.c_long(0), ptr(OBS), ptr(nobs),
+                                      ptr(idx))
+    assert rc == 0, rc
+    return OBS, nobs, idx
+
+
+class HostSimTracker:
+    """Drives hostsim_control_step on numpy arrays prepared by safe_control_b200.tracking.TrackerHostState."""
+
+    def __init__(self, X0, robot_spec, controller="cbf_qp", dt=0.05, enable_rotation=True, obs=None, dynamic_obs=False):
+        from safe_control_b200.tracking import TrackerHostState
+        self.lib = hostsim()
+        self.host = TrackerHostState(X0, robot_spec, controller, dt, enable_rotation, obs, dynamic_obs, lib=self.lib)
+        self.params = self.host.params
+        self.bufs = None
+
+    def set_waypoints(self, wp):
+        self.host.set_waypoints(wp)
+        self._bind()
+
+    def _bind(self):
+        h = self.host
+        assert self.lib.hostsim_track_sizeof() == C.sizeof(_abi.ScbTrack)
+        self.bufs = {k: np.ascontiguousarray(getattr(h, k)) for k in h.STATE_ARRAYS}
+        self.bufs["SCENE"] = np.ascontiguousarray(h.scene.copy())
+        self.bufs.update(h.solve_buffers())
+        t = h.config()
+        for k, v in self.bufs.items():
+            setattr(t, k, v.ctypes.data)
+        self.t = t
+
+    def load_state(self, **arrays):
+        """Overwrite tracker state arrays in place (teacher forcing)."""
+        for k, v in arrays.items():
+            self.bufs[k][...] = v
+
+    def control_step(self):
+        self.lib.hostsim_control_step.restype = C.c_int
+        rc = self.lib.hostsim_control_step(C.byref(self.params), C.byref(self.t))
+        assert rc == 0, rc
+        return self.bufs["ret"]

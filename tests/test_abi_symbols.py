@@ -36,6 +36,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_struct_mirror_and_helpers(lib):
     assert lib.scb_params_sizeof() == C.sizeof(_abi.ScbParams)
+    assert lib.scb_track_sizeof() == C.sizeof(_abi.ScbTrack)
     assert lib.scb_version() == 100
     assert b"ok" == lib.scb_strerror(0)
     assert lib.scb_active_words(16, 2) == 1 and lib.scb_active_words(61, 2) == 2

@@ -1,0 +1,191 @@
+"""GPU: the device-side closed loop (scb_control_step / scb_run_all_steps / scb_select_obstacles through the
+C ABI, BatchedTrackingController) against golden runs of the REFERENCE'S OWN LocalTrackingController and
+against oracle/tracking.py.  Mirrors tests/test_hostsim_track.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from track_util import (X_TOL, check_forced, forced_arrays, golden_initial_state, load_tracking_golden,
+                        random_closed_loop_case)
+
+GOLD = load_tracking_golden()
+OUT_KEYS = ("ret", "Uref", "nobs", "OBS", "status", "U", "X", "yaw", "sm", "wp_idx", "has_goal", "u_att")
+
+
+def _waypoints(d):
+    wp = d["waypoints"]
+    start = np.zeros((1, wp.shape[1])); start[0, :2] = d["X"][0][:2]
+    return np.vstack([start, wp])
+
+
+def _tracker(d, X0, scene, dynamic=None):
+    from safe_control_b200 import BatchedTrackingController
+    tc = BatchedTrackingController(X0, d["spec"], {"pos": "cbf_qp"}, enable_rotation=d["enable_rotation"], obs=scene,
+                                   dynamic_obs=d["dynamic"] if dynamic is None else dynamic)
+    tc.set_waypoints(_waypoints(d))
+    return tc
+
+
+def _np(tc, keys=OUT_KEYS):
+    import torch
+    torch.cuda.synchronize()
+    return {k: tc.buffers()[k].cpu().numpy() for k in keys}
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_free_running_matches_reference(name):
+    d = GOLD[name]
+    tc = _tracker(d, golden_initial_state(d), d["scene"][0])
+    T = len(d["ret"])
+    for k in range(T):
+        ret = tc.control_step()
+        o = _np(tc, ("ret", "X", "sm"))
+        assert o["ret"][0] == d["ret"][k], (k, o["ret"][0])
+        np.testing.assert_allclose(o["X"][0], d["X"][k + 1], rtol=0, atol=X_TOL, err_msg=f"step {k}")
+        assert o["sm"][0] == d["sm"][k + 1]
+    assert int(tc.done.cpu()[0]) == int(d["ret"][-1] != 0) and int(tc.nsteps.cpu()[0]) == T
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_run_all_steps_matches_reference(name):
+    """scb_run_all_steps: the whole run in one C call, per-agent loop break = the done latch."""
+    d = GOLD[name]
+    tc = _tracker(d, np.repeat(golden_initial_state(d), 5, axis=0), d["scene"][0])
+    T = len(d["ret"])
+    tc.run_steps(T + 7)                       # 7 extra steps: agents that finished stay frozen
+    o = _np(tc, ("ret", "X", "nsteps", "done"))
+    finished = d["ret"][-1] != 0
+    if finished:
+        assert (o["nsteps"] == T).all() and (o["done"] == 1).all() and (o["ret"] == d["ret"][-1]).all()
+        np.testing.assert_allclose(o["X"], np.repeat(d["X"][T][None], 5, axis=0), rtol=0, atol=X_TOL)
+    else:
+        assert (o["nsteps"] == T + 7).all() and (o["done"] == 0).all()
+
+
+@pytest.mark.parametrize("name", sorted(n for n in GOLD if not GOLD[n]["dynamic"]))
+def test_teacher_forced_steps_match_reference(name):
+    """Every recorded step of the reference run as one agent of a batch: one launch sequence, T answers."""
+    import torch
+    d = GOLD[name]
+    T = len(d["ret"])
+    tc = _tracker(d, np.repeat(golden_initial_state(d), T, axis=0), d["scene"][0])
+    for k, v in forced_arrays(d).items():
+        tc.buffers()[k].copy_(torch.from_numpy(np.ascontiguousarray(v)).reshape(tc.buffers()[k].shape))
+    tc.control_step()
+    check_forced(d, _np(tc))
+
+
+def test_teacher_forced_dynamic_scene():
+    import torch
+    d = GOLD["c3bf_dynamic_env"]
+    T = len(d["ret"])
+    fa = forced_arrays(d)
+    outs = {k: [] for k in OUT_KEYS}
+    tc = _tracker(d, golden_initial_state(d), d["scene"][0])
+    for k in range(0, T, 3):
+        tc.buffers()["SCENE"].copy_(torch.from_numpy(d["scene"][k]))
+        tc.buffers()["done"].zero_()
+        for n, v in fa.items():
+            tc.buffers()[n].copy_(torch.from_numpy(np.ascontiguousarray(v[k:k + 1])).reshape(tc.buffers()[n].shape))
+        tc.control_step()
+        o = _np(tc)
+        assert o["ret"][0] == d["ret"][k]
+        np.testing.assert_allclose(o["X"][0], d["X"][k + 1], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(o["Uref"][0], d["u_ref"][k], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(tc.buffers()["SCENE"].cpu().numpy(), d["scene"][k + 1], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("model", ["SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D"])
+def test_select_obstacles_matches_oracle(model):
+    import torch
+    from oracle.controllers import nearest_unpassed_obs
+    from safe_control_b200._lib import lib, check
+    from safe_control_b200.params import resolve_params
+    rng = np.random.default_rng(3)
+    p, _ = resolve_params({"model": model}, "mpc_cbf" if model == "Quad3D" else "cbf_qp")
+    for K, M in [(1, 4), (16, 16), (40, 10), (300, 64), (1024, 32)]:
+        N = 133
+        scene = np.zeros((K, 7)); scene[:, :2] = rng.uniform(0, 20, (K, 2)); scene[:, 2] = rng.uniform(0.1, 0.5, K)
+        X = np.zeros((N, p.nx)); X[:, :2] = rng.uniform(0, 20, (N, 2))
+        yaw = rng.uniform(-np.pi, np.pi, N)
+        if p.nx == 4:
+            X[:, 2] = yaw
+        elif p.nx == 12:
+            X[:, 5] = yaw
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dX, dS, dY = t(X), t(scene), t(yaw)
+        OBS = torch.empty((N, M, 7), dtype=torch.float64, device="cuda")
+        nobs = torch.empty(N, dtype=torch.int32, device="cuda"); idx = torch.empty((N, M), dtype=torch.int32, device="cuda")
+        check(lib().scb_select_obstacles(p, N, K, M, dX.data_ptr(), dY.data_ptr() if p.nx == 2 else None, dS.data_ptr(), 0,
+                                         OBS.data_ptr(), nobs.data_ptr(), idx.data_ptr(),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "scb_select_obstacles")
+        torch.cuda.synchronize()
+        OBS, nobs, idx = OBS.cpu().numpy(), nobs.cpu().numpy(), idx.cpu().numpy()
+        for i in range(0, N, 3):
+            sel, sidx = nearest_unpassed_obs(model, X[i, :2], yaw[i], scene, M)
+            assert nobs[i] == len(sidx)
+            assert np.array_equal(idx[i, :nobs[i]], sidx) and (idx[i, nobs[i]:] == -1).all()
+            assert np.array_equal(OBS[i, :nobs[i]], sel)
+    assert lib().scb_select_obstacles(p, 4, 2000, 4, dX.data_ptr(), None, dS.data_ptr(), 0, OBS.ctypes.data,
+                                      nobs.ctypes.data, None, None) == -3            # K beyond the compiled limit
+
+
+@pytest.mark.parametrize("model,controller,dynamic", [
+    ("DynamicUnicycle2D", "cbf_qp", False),
+    ("SingleIntegrator2D", "cbf_qp", False),
+    ("KinematicBicycle2D", "cbf_qp", False),
+    ("KinematicBicycle2D_C3BF", "cbf_qp", True),
+    ("DynamicUnicycle2D", "optimal_decay_cbf_qp", False),
+    ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True),
+])
+def test_random_closed_loop_matches_oracle(model, controller, dynamic):
+    from oracle.tracking import OracleTrackingController
+    from safe_control_b200 import BatchedTrackingController
+    N, K, T = 48, 16, 150
+    X0, scene, wps = random_closed_loop_case(model, N, K, seed=23, dynamic=dynamic)
+    spec = {"model": model, "num_constraints": 8}
+    tc = BatchedTrackingController(X0, spec, {"pos": controller}, obs=scene, dynamic_obs=dynamic)
+    tc.set_waypoints(wps)
+    orc = []
+    for i in range(N):
+        o = OracleTrackingController(X0[i], spec, controller, obs=scene.copy(), dynamic_obs=dynamic)
+        o.set_waypoints(wps[i]); orc.append(o)
+    done = np.zeros(N, bool)
+    seen = set()
+    for k in range(T):
+        tc.control_step()
+        o = _np(tc, ("ret", "X"))
+        for i, oc in enumerate(orc):
+            if done[i]:
+                continue
+            r = oc.control_step(); seen.add(oc.state_machine)
+            assert r == o["ret"][i], (k, i, r, o["ret"][i])
+            np.testing.assert_allclose(o["X"][i], oc.X, rtol=0, atol=1e-7, err_msg=f"step {k} agent {i}")
+            done[i] = r in (-1, -2)
+    assert len(seen) >= 2
+
+
+@pytest.mark.parametrize("model", ["DynamicUnicycle2D", "Quad3D"])
+def test_mpc_closed_loop(model):
+    """MPC in the loop: solved only in 'track' (mpc_cbf.py:379-381), u_prev carried, no collision, progress."""
+    from safe_control_b200 import BatchedTrackingController
+    N, K, T = 32, 9, 60
+    X0, scene, wps = random_closed_loop_case(model, N, K, seed=5)
+    spec = {"model": model, "num_constraints": 6, "mpc_horizon": 8}
+    tc = BatchedTrackingController(X0, spec, {"pos": "mpc_cbf"}, obs=scene)
+    tc.set_waypoints(wps)
+    b = tc.buffers()
+    start = b["X"].cpu().numpy().copy()
+    for k in range(T):
+        tc.control_step()
+        o = _np(tc, ("ret", "sm", "U", "Uref", "u_prev", "done", "X"))
+        nt = (o["sm"] != 1) & (o["done"] == 0)
+        np.testing.assert_array_equal(o["U"][nt], o["Uref"][nt])
+        tk = (o["sm"] == 1) & (o["done"] == 0)
+        np.testing.assert_array_equal(o["u_prev"][tk], o["U"][tk])
+    assert (o["ret"] != -2).mean() >= 0.9
+    moved = np.linalg.norm(o["X"][:, :2] - start[:, :2], axis=1)
+    assert np.median(moved) > 0.5
