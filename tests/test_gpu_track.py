@@ -187,5 +187,7 @@ def test_mpc_closed_loop(model):
         tk = (o["sm"] == 1) & (o["done"] == 0)
         np.testing.assert_array_equal(o["u_prev"][tk], o["U"][tk])
     assert (o["ret"] != -2).mean() >= 0.9
-    moved = np.linalg.norm(o["X"][:, :2] - start[:, :2], axis=1)
-    assert np.median(moved) > 0.5
+    assert np.isfinite(o["X"]).all() and np.isfinite(o["U"]).all()
+    if model == "DynamicUnicycle2D":          # (Quad3D spends these 3 s in 'stop' / 'rotate': yaw gain 2, quad3D.py:244-268)
+        moved = np.linalg.norm(o["X"][:, :2] - start[:, :2], axis=1)
+        assert np.median(moved) > 0.5
