@@ -42,6 +42,12 @@ WORKLOADS = {
     "cfg5": dict(model="mixed", controller="mpc_cbf", N=8192, M=64, H=10, dynamic=False,
                  desc="8192 agents per GPU = 1/8 of config 5 (65536 mixed du/kb/quad3d agents, mpc_cbf N=10, 64 obstacles, 8 GPUs)"),
 }
+WORKLOADS["loop2"] = dict(model="DynamicUnicycle2D", controller="cbf_qp", N=1024, M=16, H=0, dynamic=False, loop=True,
+                          desc="closed loop of config 2 (SURVEY 8f-1): 1024 DynamicUnicycle2D agents x 16 obstacles, full "
+                               "control_step() per agent on the device (state machine, selection, nominal input, cbf_qp, collision, step)")
+WORKLOADS["loop4"] = dict(model="KinematicBicycle2D_C3BF", controller="optimal_decay_cbf_qp", N=8192, M=32, H=0, dynamic=True,
+                          loop=True, desc="closed loop of config 4: 8192 KinematicBicycle2D_C3BF agents, optimal_decay_cbf_qp, "
+                                          "32 moving obstacles, full control_step() on the device")
 L2_BYTES = 126e6
 MIXED = ("DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D")
 
@@ -273,6 +279,188 @@ def run_mixed(args, w, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def _oracle_loop_range(args):
+    """Worker: the reference's control flow (oracle/tracking.py), one agent at a time, `steps` control steps each."""
+    w, X0, scene, wps, spec, lo, hi, steps = args
+    from oracle.tracking import OracleTrackingController
+    t0 = time.perf_counter()
+    n = 0
+    for i in range(lo, hi):
+        tc = OracleTrackingController(X0[i], spec, w["controller"], obs=scene.copy(), dynamic_obs=w["dynamic"])
+        tc.set_waypoints(wps[i])
+        for _ in range(steps):
+            n += 1
+            if tc.control_step() in (-1, -2):
+                break
+    return n, time.perf_counter() - t0
+
+
+def loop_case(w, N, seed):
+    """Seeded closed-loop scene (SURVEY 8d arena: side 4 sqrt(M), radii U[0.2, 0.6]) + 3 waypoints per agent."""
+    rng = np.random.default_rng(seed)
+    M = w["M"]
+    L = 4.0 * np.sqrt(M)
+    scene = np.zeros((M, 7))
+    scene[:, 0:2] = rng.uniform(0, L, (M, 2)); scene[:, 2] = rng.uniform(0.2, 0.6, M)
+    if w["dynamic"]:
+        scene[:, 3:5] = rng.uniform(-0.5, 0.5, (M, 2))
+    pos = np.empty((N, 2)); todo = np.arange(N)
+    while todo.size:
+        cand = rng.uniform(0, L, (todo.size, 2))
+        ok = ((np.sqrt(((cand[:, None] - scene[None, :, :2]) ** 2).sum(-1)) - scene[None, :, 2] - 0.8) > 0).all(1)
+        pos[todo[ok]] = cand[ok]; todo = todo[~ok]
+    v = rng.uniform(0.2, 1.0, N)
+    X0 = np.hstack([pos, rng.uniform(-np.pi, np.pi, (N, 1)), v[:, None]])
+    wps = np.zeros((N, 4, 3))
+    wps[:, 0, :2] = pos
+    wps[:, 1:, :2] = np.clip(pos[:, None, :] + np.cumsum(rng.uniform(-0.35 * L, 0.35 * L, (N, 3, 2)), axis=1), 0, L)
+    return X0, scene, wps
+
+
+def reference_loop(args, w, procs):
+    """--impl reference for the closed-loop workloads: oracle/tracking.py, one agent at a time per process."""
+    import multiprocessing as mp
+    per_proc, n_s = 2, 25
+    n_agents = per_proc * procs
+    X0, scene, wps = loop_case(w, n_agents * (args.steps + 3), 1234)
+    spec = {"model": w["model"], "num_constraints": w["M"]}
+    pool = mp.get_context("fork").Pool(procs)
+    def one(k):
+        lo = k * n_agents
+        jobs = [(w, X0, scene, wps, spec, lo + j * per_proc, lo + (j + 1) * per_proc, n_s) for j in range(procs)]
+        t0 = time.perf_counter()
+        res = pool.map(_oracle_loop_range, jobs)
+        return sum(r[0] for r in res), time.perf_counter() - t0
+    for k in range(max(1, min(args.warmup, 2))):
+        one(k)
+    n_tot, t_tot, done = 0, 0.0, 0
+    for k in range(args.steps):
+        n, dt = one(k + 2)
+        n_tot += n; t_tot += dt; done += 1
+        if t_tot > 150.0:
+            break
+    pool.close(); pool.join()
+    val = n_tot / t_tot
+    sample = f"{done} steps x {n_agents} agents x up to {n_s} control steps through oracle/tracking.py, {procs} processes"
+    print(json.dumps({
+        "impl": "reference", "metric": "control-steps/sec (batched QP solves/s)", "value": val, "unit": "control-steps/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['desc']}", "obstacles": w["M"]},
+        "cpu_baseline": {"value": val, "unit": "control-steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's cvxpy/GUROBI stack is not installable here; this is the oracle restatement of tracking.py:control_step",
+    }))
+
+
+def run_loop(args, w, rank, world, local_rank):
+    """Closed loop on the device: one step = scb_control_step over N agents (3-4 launches)."""
+    import torch
+    import torch.distributed as dist
+    from safe_control_b200 import BatchedTrackingController
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    N, M = w["N"], w["M"]
+    X0, scene, wps = loop_case(w, N, 1234 + rank)
+    spec = {"model": w["model"], "num_constraints": M}
+    mk = lambda: BatchedTrackingController(X0, spec, {"pos": w["controller"]}, obs=scene, dynamic_obs=w["dynamic"], device=dev)
+    tc = mk(); tc.set_waypoints(wps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tc.run_steps(args.warmup)
+    barrier()
+    graph = torch.cuda.CUDAGraph()
+    l0 = tc.launches
+    with torch.cuda.graph(graph):
+        tc.run_steps(args.steps)
+    launches = tc.launches - l0
+    # every timed replay starts from the same tracker state (after the warm-up steps): snapshot / restore
+    keys = ("X", "yaw", "sm", "wp_idx", "goal", "has_goal", "u_att", "u_prev", "ret", "done", "nsteps", "SCENE")
+    snap = {k: tc.buffers()[k].clone() for k in keys}
+    def restore():
+        for k in keys:
+            tc.buffers()[k].copy_(snap[k])
+    graph.replay(); restore(); barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    reps = []
+    for _ in range(5):
+        restore(); barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); graph.replay(); b.record(); barrier()
+        reps.append(a.elapsed_time(b))
+    ms = float(np.median(reps))
+    clocks = sampler.stop() if rank == 0 else None
+    bufs = tc.buffers()
+    active_frac = float((bufs["nsteps"] - snap["nsteps"]).float().mean()) / args.steps
+    rets = bufs["ret"].cpu().numpy(); done = bufs["done"].cpu().numpy()
+    # eager: one C call launching 3-4 kernels per step, no graph
+    restore(); barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(); tc.run_steps(args.steps); g1.record(); torch.cuda.synchronize()
+    eager_ms = g0.elapsed_time(g1)
+    # end to end: initial state from pinned host memory -> device, run K steps, final state + return codes back
+    host = {k: snap[k].cpu().pin_memory() for k in keys}
+    out_h = {k: torch.empty_like(host[k]).pin_memory() for k in ("X", "ret", "nsteps")}
+    def e2e_run():
+        for k in keys:
+            tc.buffers()[k].copy_(host[k], non_blocking=True)
+        tc.run_steps(args.steps)
+        for k in out_h:
+            out_h[k].copy_(tc.buffers()[k], non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_run(); barrier()
+    t0 = time.perf_counter(); e2e_run(); e2e_ms = (time.perf_counter() - t0) * 1e3
+    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+    d2h = sum(v.numel() * v.element_size() for v in out_h.values())
+    tm = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        nx, nu = 4, 2
+        # tracker state read + written once per agent-step; the selected obstacle rows are written by the pre kernel and
+        # read by the solve kernel (they stay in L2); the shared scene is read from L2
+        B = 2 * 8 * (nx + 1 + 2 + 1 + nu + nu) + 2 * 4 * 6 + 2 * 56 * M + 24
+        k_ms = float(tm[0]) / args.steps
+        out = {
+            "metric": "control-steps/sec (batched QP solves/s)", "value": world * N * args.steps / (float(tm[0]) * 1e-3),
+            "unit": "control-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": k_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step_per_gpu": N, "obstacles": M, "scene_obstacles": M,
+                       "waypoints_per_agent": 3, "launch": f"K steps ({launches} launches) captured in one CUDA graph; every replay restarts from the same tracker state",
+                       "l2_policy": "closed loop: the state produced by step k is the input of step k+1 (nothing is re-read from a warm copy); agents_active_frac = share of agent-steps not yet frozen by a -1/-2 return",
+                       "agents_active_frac": active_frac, "final_ret": {"0": int((rets == 0).sum()), "-1": int((rets == -1).sum()), "-2": int((rets == -2).sum())},
+                       "parallelism": f"agents sharded, {world} rank(s), no data-path collective"},
+            "e2e": {"value": world * N * args.steps / (float(tm[1]) * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps, "steps_timed": args.steps,
+                    "how": "whole run_all_steps: tracker state pinned host -> device, K control steps on the device, final X / ret / nsteps -> pinned host, sync"},
+            "gpu_launches": launches,
+            "eager": {"value": world * N * args.steps / (eager_ms * 1e-3), "unit": "control-steps/s", "how": "scb_run_all_steps without the CUDA graph"},
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": B * N / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": B * N / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_agent": B, "agents_per_launch": N,
+                         "note": "three dependent launches per control step over ~3 MB of state: latency-bound by construction (step k+1 needs step k)"},
+        }
+        if not args.no_cpu:
+            n_a, n_s = 24, 50
+            n, dt = _oracle_loop_range((w, X0, scene, wps, spec, 0, n_a, n_s))
+            out["cpu_baseline"] = {"value": n / dt, "unit": "control-steps/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+                                   "sample": f"{n_a} agents x up to {n_s} control steps of the same scene through oracle/tracking.py (one agent at a time), {dt:.1f} s"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -296,6 +484,8 @@ def main():
         if rank != 0:
             return
         procs = os.cpu_count() or 1
+        if w.get("loop"):
+            return reference_loop(args, w, procs)
         per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 1}[w["controller"]] * procs
         budget_s = 150.0
         n_scene = min(max(per_step * 8, 2048), 16384)
@@ -330,6 +520,8 @@ def main():
 
     if w["model"] == "mixed":
         return run_mixed(args, w, rank, world, local_rank)
+    if w.get("loop"):
+        return run_loop(args, w, rank, world, local_rank)
     import torch
     import torch.distributed as dist
     from safe_control_b200 import BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, HostContext
