@@ -172,7 +172,10 @@ class BatchedMPCCBF(_Base):
 
 class HostContext:
     """Host-buffer (numpy) entry points: H2D + kernel + D2H inside one C call.
-    This is the path a reference-side binding uses and what bench.py's e2e times."""
+    This is the path a reference-side binding uses and what bench.py's e2e times.
+    When every array is page-locked (e.g. `torch.from_numpy(a).pin_memory().numpy()`) the QP calls run
+    zero-copy: the kernel reads / writes the host buffers over PCIe directly (env SCB_HOST_PATH=staged|mapped
+    overrides the automatic choice, see csrc/scb_api.cu)."""
 
     def __init__(self, device=0):
         require_cuda()
@@ -222,13 +225,16 @@ class HostContext:
               "scb_cbfqp_solve_host")
         return U, status, active
 
-    def odcbf_solve(self, params, M, X, U_ref, OBS, nobs=None):
+    def odcbf_solve(self, params, M, X, U_ref, OBS, nobs=None, out=None):
         N = X.shape[0]
         X = self._np(X, np.float64, "X"); U_ref = self._np(U_ref, np.float64, "U_ref")
         OBS = self._np(OBS, np.float64, "OBS"); nobs = self._np(nobs, np.int32, "nobs")
         stride = 0 if OBS.ndim == 2 else 7 * M
-        U = np.empty((N, 2)); omega = np.empty((N, 2)); sel = np.empty(N, np.int32)
-        status = np.empty(N, np.int32); active = np.empty(N, np.uint64)
+        if out is None:
+            U = np.empty((N, 2)); omega = np.empty((N, 2)); sel = np.empty(N, np.int32)
+            status = np.empty(N, np.int32); active = np.empty(N, np.uint64)
+        else:
+            U, omega, sel, status, active = out
         check(lib().scb_odcbf_solve_host(self._h, params, N, M, self._p(X), self._p(U_ref), self._p(OBS), stride,
                                          self._p(nobs), self._p(U), self._p(omega), self._p(sel), self._p(status),
                                          self._p(active)), "scb_odcbf_solve_host")
