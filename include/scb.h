@@ -64,7 +64,10 @@ enum scb_model {
   SCB_KINEMATIC_BICYCLE_2D = 2,     /* robots/kinematic_bicycle2D.py */
   SCB_KINEMATIC_BICYCLE_2D_C3BF = 3,/* dynamic_env/kinematic_bicycle2D_c3bf.py */
   SCB_QUAD_3D = 4,                  /* robots/quad3D.py (MPC only: agent_barrier raises, quad3D.py:269-273) */
-  SCB_NUM_MODELS = 5
+  SCB_DOUBLE_INTEGRATOR_2D = 5,     /* robots/double_integrator2D.py        (QP paths) */
+  SCB_QUAD_2D = 6,                  /* robots/quad2D.py                      (QP paths) */
+  SCB_KINEMATIC_BICYCLE_2D_DPCBF = 7,/* dynamic_env/kinematic_bicycle2D_dpcbf.py (cbf_qp + closed loop) */
+  SCB_NUM_MODELS = 8
 };
 
 enum scb_status { SCB_OPTIMAL = 0, SCB_INFEASIBLE = 1, SCB_MAXITER = 2, SCB_NUMERICAL = 3 };
@@ -95,7 +98,7 @@ typedef struct scb_params {
   double omega1_0, omega2_0, p_sb1, p_sb2;   /* optimal_decay_cbf_qp.py:17-50 */
   double Q[12];           /* MPC state weights (diagonal)  mpc_cbf.py:19-39 */
   double R[4];            /* MPC input-rate weights        mpc_cbf.py:19-39, 180 */
-  double mass, Ix, Iy, Iz, arm_L, nu_coef, gravity;     /* quad3D.py:53-69 */
+  double mass, Ix, Iy, Iz, arm_L, nu_coef, gravity;     /* quad3D.py:53-69; Quad2D: mass, Iy = inertia, gravity 9.81 (quad2D.py:40-46) */
   int32_t mpc_max_iter;   /* interior-point iteration cap (ours) */
   int32_t reserved;
   double mpc_tol;         /* KKT tolerance (ours; IPOPT default 1e-8) */

@@ -14,8 +14,8 @@ import numpy as np
 from .models import make_model, angle_normalize
 from .qp_exact import solve_qp_exact, OPTIMAL
 
-REL1 = ("SingleIntegrator2D", "KinematicBicycle2D_C3BF", "Quad3D")
-REL2 = ("DynamicUnicycle2D", "KinematicBicycle2D")
+REL1 = ("SingleIntegrator2D", "KinematicBicycle2D_C3BF", "KinematicBicycle2D_DPCBF", "Quad3D")
+REL2 = ("DynamicUnicycle2D", "KinematicBicycle2D", "DoubleIntegrator2D", "Quad2D")
 
 CBFQP_ALPHA = {                       # cbf_qp.py:12-35
     "SingleIntegrator2D": dict(alpha=1.0),
@@ -23,6 +23,9 @@ CBFQP_ALPHA = {                       # cbf_qp.py:12-35
     "KinematicBicycle2D": dict(alpha1=1.5, alpha2=1.5),
     "KinematicBicycle2D_C3BF": dict(alpha=1.5),
     "Quad3D": dict(alpha=1.5),
+    "DoubleIntegrator2D": dict(alpha1=1.5, alpha2=1.5),
+    "Quad2D": dict(alpha1=1.5, alpha2=1.5),
+    "KinematicBicycle2D_DPCBF": dict(alpha=1.5),
 }
 
 
@@ -99,6 +102,7 @@ OD_PARAM = {                          # optimal_decay_cbf_qp.py:17-50
     "DynamicUnicycle2D": dict(alpha1=0.5, alpha2=0.5, omega1=1.0, p_sb1=1e4, omega2=1.0, p_sb2=1e4),
     "KinematicBicycle2D": dict(alpha1=0.5, alpha2=0.5, omega1=1.0, p_sb1=1e4, omega2=1.0, p_sb2=1e4),
     "KinematicBicycle2D_C3BF": dict(alpha=0.5, omega1=1.0, p_sb1=1e4),
+    "Quad2D": dict(alpha1=0.5, alpha2=0.5, omega1=1.0, p_sb1=1e4, omega2=1.0, p_sb2=1e4),
 }
 
 
@@ -122,7 +126,7 @@ class OracleOptimalDecayCBFQP:
             if self.name == "KinematicBicycle2D_C3BF":            # :139-143
                 h, dh = m.agent_barrier(X, obs)
                 A = dh @ m.g(X); b = dh @ m.f(X)
-            elif self.name == "DynamicUnicycle2D":                # :144-149
+            elif self.name in ("DynamicUnicycle2D", "Quad2D"):    # :144-149
                 h, hd, dhd = m.agent_barrier(X, obs)
                 A = dhd @ m.g(X); b = dhd @ m.f(X)
             # plain KinematicBicycle2D: no branch -> row stays zero
@@ -158,6 +162,7 @@ ANGLE_UNPASSED = {                    # tracking.py:352-357
     "SingleIntegrator2D": 2.0 * np.pi, "Quad3D": 2.0 * np.pi,
     "DynamicUnicycle2D": 1.2 * np.pi,
     "KinematicBicycle2D": 2.0 * np.pi, "KinematicBicycle2D_C3BF": 2.0 * np.pi,
+    "KinematicBicycle2D_DPCBF": 2.0 * np.pi, "DoubleIntegrator2D": 2.0 * np.pi, "Quad2D": 2.0 * np.pi,
 }
 
 

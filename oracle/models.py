@@ -22,6 +22,7 @@ import numpy as np
 
 MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D",
           "KinematicBicycle2D_C3BF", "Quad3D")
+MODELS_QP_EXTRA = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")     # SURVEY 8f-2 (QP paths only)
 
 
 def angle_normalize(x):
@@ -42,7 +43,12 @@ def resolve_spec(robot_spec):
         s.setdefault("v_max", 1.0); s.setdefault("w_max", 0.5)
     elif model == "DynamicUnicycle2D":
         s.setdefault("a_max", 0.5); s.setdefault("w_max", 0.5); s.setdefault("v_max", 1.0)
-    elif model in ("KinematicBicycle2D", "KinematicBicycle2D_C3BF"):
+    elif model == "DoubleIntegrator2D":                       # double_integrator2D.py:40-44
+        s.setdefault("a_max", 1.0); s.setdefault("v_max", 1.0)
+        s.setdefault("ax_max", s["a_max"]); s.setdefault("ay_max", s["a_max"]); s.setdefault("w_max", 0.5)
+    elif model == "Quad2D":                                   # quad2D.py:40-46
+        s.setdefault("mass", 1.0); s.setdefault("inertia", 0.01); s.setdefault("f_min", 1.0); s.setdefault("f_max", 10.0)
+    elif model in ("KinematicBicycle2D", "KinematicBicycle2D_C3BF", "KinematicBicycle2D_DPCBF"):
         s.setdefault("wheel_base", 0.4); s.setdefault("front_ax_dist", 0.2)
         s.setdefault("rear_ax_dist", 0.2); s.setdefault("v_max", 3.5)
         s.setdefault("a_max", 5.0); s.setdefault("delta_max", np.deg2rad(32))
@@ -313,6 +319,154 @@ class KinematicBicycle2D_C3BF(KinematicBicycle2D):
         return hk, self._h_dt(x1, obs) - hk
 
 
+class KinematicBicycle2D_DPCBF(KinematicBicycle2D):
+    """Dynamic-parabolic CBF (dynamic_env/kinematic_bicycle2D_dpcbf.py).  The hand-written dh/dx is not the
+    gradient of h: both are transcribed literally."""
+    rel_degree = 1
+    k_lambda, k_mu, s_margin = 0.1, 0.5, 1.05
+
+    def _parts(self, x, obs):
+        th, v = x[2], x[3]
+        ovx, ovy = (obs[3], obs[4]) if len(obs) > 3 else (0.0, 0.0)
+        ego = (obs[2] + self.radius) * self.s_margin
+        px, py = obs[0] - x[0], obs[1] - x[1]
+        vx, vy = ovx - v * math.cos(th), ovy - v * math.sin(th)
+        pm = math.sqrt(px * px + py * py); vm = math.sqrt(vx * vx + vy * vy)
+        rot = math.atan2(py, px)
+        vnx = math.cos(rot) * vx + math.sin(rot) * vy
+        vny = -math.sin(rot) * vx + math.cos(rot) * vy
+        d_safe = max(pm ** 2 - ego ** 2, 1e-6)
+        return th, v, ovx, ovy, ego, px, py, pm, vm, rot, vnx, vny, d_safe
+
+    def agent_barrier(self, X, obs):
+        """-> h, dh_dx(4,)   (:16-84)"""
+        th, v, ovx, ovy, ego, px, py, pm, vm, rot, vnx, vny, d_safe = self._parts(X, obs)
+        kl, km, s = self.k_lambda, self.k_mu, self.s_margin
+        sd = math.sqrt(d_safe)
+        lam = kl * sd / vm * math.sqrt(s ** 2 - 1) / ego
+        mu = km * sd * math.sqrt(s ** 2 - 1) / ego
+        h = vnx + lam * vny ** 2 + mu
+        dh = np.array([
+            py * vny / pm ** 2 - kl * px * vny ** 2 / vm / sd - 2 * kl * sd / vm * vny * py / pm ** 2 * vnx - km * px / sd,
+            -px * vny / pm ** 2 - kl * py * vny ** 2 / vm / sd + 2 * kl * sd / vm * vny * px / pm ** 2 * vnx - km * py / sd,
+            -v * math.sin(rot - th) - kl * sd * v * (ovx * math.sin(th) - ovy * math.cos(th)) * vny ** 2 / vm ** 3
+            - 2 * kl * sd * vny * v * math.cos(rot - th) / vm,
+            -math.cos(rot - th) - kl * sd / vm ** 3 * (v - ovx * math.cos(th) - ovy * math.sin(th)) * vny ** 2
+            - 2 * kl * sd * vny * math.sin(rot - th) / vm])
+        return h, dh
+
+    def _h_dt(self, x, obs):
+        """(:86-136)"""
+        th, v, ovx, ovy, ego, px, py, pm, vm, rot, vnx, vny, d_safe = self._parts(x, obs)
+        s = self.s_margin
+        k_l, k_m = 0.1 * math.sqrt(s ** 2 - 1) / ego, 0.5 * math.sqrt(s ** 2 - 1) / ego
+        return vnx + k_l * math.sqrt(d_safe) / vm * vny ** 2 + k_m * math.sqrt(d_safe)
+
+    def barrier_dt(self, x, u, obs):
+        x1 = self.step(x, u)
+        hk = self._h_dt(x, obs)
+        return hk, self._h_dt(x1, obs) - hk
+
+
+class DoubleIntegrator2D(Model):
+    """X = [x, y, vx, vy] (yaw kept outside the state), U = [ax, ay]   (robots/double_integrator2D.py)."""
+    nx, nu, rel_degree = 4, 2, 2
+    beta = 1.01
+
+    def f(self, X): return np.array([X[2], X[3], 0.0, 0.0])
+    def g(self, X): return np.array([[0.0, 0], [0, 0], [1, 0], [0, 1]])
+
+    def step(self, X, U):                                      # :82-110 (velocity magnitude clipped to v_max)
+        Xn = X + (self.f(X) + self.g(X) @ U) * self.dt
+        v_max = self.spec.get("v_max")
+        if v_max is not None:
+            vm = math.sqrt(Xn[2] ** 2 + Xn[3] ** 2)
+            if vm > v_max:
+                Xn[2] *= v_max / vm; Xn[3] *= v_max / vm
+        return Xn
+
+    def u_bounds(self):
+        a = self.spec["a_max"]; return np.array([-a, -a]), np.array([a, a])
+
+    def nominal_input(self, X, G, d_min=0.05, k_v=1.0, k_a=1.0):     # :116-143
+        k_v = self.spec.get("nominal_k_v", k_v); k_a = self.spec.get("nominal_k_a", k_a)
+        v_max, a_max = self.spec["v_max"], self.spec["a_max"]
+        err = np.asarray(G[0:2], float) - X[0:2]
+        err = np.sign(err) * np.maximum(np.abs(err) - d_min, 0.0)
+        v_des = k_v * err
+        mag = np.linalg.norm(v_des)
+        if mag > v_max:
+            v_des = v_des * v_max / mag
+        a = k_a * (v_des - X[2:4])
+        am = np.linalg.norm(a)
+        if am > a_max:
+            a = a * a_max / am
+        return a
+
+    def agent_barrier(self, X, obs):
+        """-> h, h_dot, dh_dot_dx(4,)   (:167-222)"""
+        h, h_dot, dhd = 0.0, 0.0, np.zeros(4)
+        if obs[-1] == 0:
+            h = np.linalg.norm(X[0:2] - obs[0:2]) ** 2 - self.beta * (obs[2] + self.radius) ** 2
+            h_dot = 2 * (X[0:2] - obs[0:2]) @ X[2:4]
+            dhd = np.append(2 * X[2:4], 2 * (X[0:2] - obs[0:2]))
+        elif obs[-1] == 1:
+            R = self.radius
+            a, b, e = obs[2], obs[3], obs[4]
+            h, dh2, (pxp, pyp, c, s) = _superellipsoid(X[0], X[1], obs, R)
+            h_dot = dh2 @ X[2:4]
+            ka = e * (e - 1) / (a + R) ** e * pxp ** (e - 2)
+            kb = e * (e - 1) / (b + R) ** e * pyp ** (e - 2)
+            dhd = np.array([(ka * c * c + kb * s * s) * X[2] + ((ka - kb) * c * s) * X[3],
+                            ((ka - kb) * c * s) * X[2] + (ka * s * s + kb * c * c) * X[3], dh2[0], dh2[1]])
+        return h, h_dot, dhd
+
+    def barrier_dt(self, x, u, obs):
+        x1 = self.step(x, u); x2 = self.step(x1, u)
+        hk = _h_dt_flag(x[0], x[1], obs, self.radius, self.beta)
+        h1 = _h_dt_flag(x1[0], x1[1], obs, self.radius, self.beta)
+        h2 = _h_dt_flag(x2[0], x2[1], obs, self.radius, self.beta)
+        return hk, h1 - hk, h2 - 2 * h1 + hk
+
+
+class Quad2D(Model):
+    """X = [x, z, theta, vx, vz, theta_dot], U = [f_right, f_left]   (robots/quad2D.py)."""
+    nx, nu, rel_degree = 6, 2, 2
+    beta = 1.01
+    gravity = 9.81
+
+    def f(self, X): return np.array([X[3], X[4], X[5], 0.0, -self.gravity, 0.0])
+
+    def g(self, X):
+        m, I, r = self.spec["mass"], self.spec["inertia"], self.radius
+        th = X[2]
+        return np.array([[0, 0, 0, -math.sin(th) / m, math.cos(th) / m, r / I],
+                         [0, 0, 0, -math.sin(th) / m, math.cos(th) / m, -r / I]]).T
+
+    def step(self, X, U):
+        Xn = X + (self.f(X) + self.g(X) @ U) * self.dt
+        Xn[2] = angle_normalize(Xn[2])
+        return Xn
+
+    def u_bounds(self):
+        return np.full(2, self.spec["f_min"]), np.full(2, self.spec["f_max"])
+
+    def agent_barrier(self, X, obs):
+        """-> h, h_dot, dh_dot_dx(6,)   (:166-177; circle only, flag ignored)"""
+        d = X[0:2] - obs[0:2]
+        h = np.linalg.norm(d) ** 2 - self.beta * (obs[2] + self.radius) ** 2
+        h_dot = 2 * d @ X[3:5]
+        dhd = np.array([2 * X[3], 2 * X[4], 0.0, 2 * d[0], 2 * d[1], 0.0])
+        return h, h_dot, dhd
+
+    def barrier_dt(self, x, u, obs):
+        x1 = self.step(x, u); x2 = self.step(x1, u)
+        hk = _circle_h(x[0], x[1], obs, self.radius, self.beta)
+        h1 = _circle_h(x1[0], x1[1], obs, self.radius, self.beta)
+        h2 = _circle_h(x2[0], x2[1], obs, self.radius, self.beta)
+        return hk, h1 - hk, h2 - 2 * h1 + hk
+
+
 class Quad3D(Model):
     nx, nu, rel_degree = 12, 4, 1
     beta = 1.01
@@ -375,6 +529,9 @@ _REGISTRY = {
     "KinematicBicycle2D": KinematicBicycle2D,
     "KinematicBicycle2D_C3BF": KinematicBicycle2D_C3BF,
     "Quad3D": Quad3D,
+    "DoubleIntegrator2D": DoubleIntegrator2D,
+    "Quad2D": Quad2D,
+    "KinematicBicycle2D_DPCBF": KinematicBicycle2D_DPCBF,
 }
 
 

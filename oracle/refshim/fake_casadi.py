@@ -29,13 +29,24 @@ class MX(_Sym):
     pass
 
 
-def DM(x):
-    return np.array(x, dtype=float)
+class DM(_Sym):
+    """`ca.DM([...])` -> a plain float64 ndarray; still a type for isinstance checks (double_integrator2D.py:84)."""
+
+    def __new__(cls, x):
+        return np.array(x, dtype=float)
 
 
 def vertcat(*args):
-    parts = [np.atleast_1d(np.asarray(a, dtype=float)).reshape(-1) for a in args]
+    arrs = [np.asarray(a, dtype=float) for a in args]
+    if arrs and all(a.ndim == 2 and a.shape[0] == 1 and a.shape[1] > 1 for a in arrs):
+        return np.vstack(arrs)                     # rows from horzcat -> matrix (kinematic_bicycle2D_dpcbf.py:114-117)
+    parts = [np.atleast_1d(a).reshape(-1) for a in arrs]
     return np.concatenate(parts).reshape(-1, 1)
+
+
+def horzcat(*args):
+    parts = [np.atleast_1d(np.asarray(a, dtype=float)).reshape(-1) for a in args]
+    return np.concatenate(parts).reshape(1, -1)
 
 
 def mtimes(*args):

@@ -7,9 +7,12 @@ MODEL_IDS = {
     "KinematicBicycle2D": 2,
     "KinematicBicycle2D_C3BF": 3,
     "Quad3D": 4,
+    "DoubleIntegrator2D": 5,
+    "Quad2D": 6,
+    "KinematicBicycle2D_DPCBF": 7,
 }
 MODEL_NAMES = {v: k for k, v in MODEL_IDS.items()}
-MODEL_DIMS = {0: (2, 2), 1: (4, 2), 2: (4, 2), 3: (4, 2), 4: (12, 4)}
+MODEL_DIMS = {0: (2, 2), 1: (4, 2), 2: (4, 2), 3: (4, 2), 4: (12, 4), 5: (4, 2), 6: (6, 2), 7: (4, 2)}
 
 OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL = 0, 1, 2, 3
 STATUS_STR = {0: "optimal", 1: "infeasible", 2: "user_limit", 3: "solver_error"}   # cvxpy's vocabulary

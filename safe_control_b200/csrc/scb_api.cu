@@ -73,7 +73,8 @@ static int forced_lanes() {      // tuning override, read per call (no cached st
 
 static bool qp_model_ok(int m) {
   return m == SCB_SINGLE_INTEGRATOR_2D || m == SCB_DYNAMIC_UNICYCLE_2D || m == SCB_KINEMATIC_BICYCLE_2D ||
-         m == SCB_KINEMATIC_BICYCLE_2D_C3BF;
+         m == SCB_KINEMATIC_BICYCLE_2D_C3BF || m == SCB_DOUBLE_INTEGRATOR_2D || m == SCB_QUAD_2D ||
+         m == SCB_KINEMATIC_BICYCLE_2D_DPCBF;
 }
 
 extern "C" {
@@ -109,6 +110,9 @@ int scb_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const dou
     case SCB_DYNAMIC_UNICYCLE_2D: cbfqp_rows_kernel<SCB_DYNAMIC_UNICYCLE_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
     case SCB_KINEMATIC_BICYCLE_2D: cbfqp_rows_kernel<SCB_KINEMATIC_BICYCLE_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
     case SCB_KINEMATIC_BICYCLE_2D_C3BF: cbfqp_rows_kernel<SCB_KINEMATIC_BICYCLE_2D_C3BF><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_DOUBLE_INTEGRATOR_2D: cbfqp_rows_kernel<SCB_DOUBLE_INTEGRATOR_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_QUAD_2D: cbfqp_rows_kernel<SCB_QUAD_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: cbfqp_rows_kernel<SCB_KINEMATIC_BICYCLE_2D_DPCBF><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
   }
   CK(cudaGetLastError());
   return SCB_OK;
@@ -130,6 +134,9 @@ int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const do
     case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_DYNAMIC_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
     case SCB_KINEMATIC_BICYCLE_2D: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
     case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_DOUBLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_DOUBLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_QUAD_2D: rc = launch_cbfqp_m<SCB_QUAD_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
   }
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
@@ -141,7 +148,9 @@ int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const do
                     long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
                     uint64_t* active, void* stream) {
   if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
-  if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D) return SCB_ERR_UNSUPPORTED;
+  if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D || p->model == SCB_DOUBLE_INTEGRATOR_2D ||
+      p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+    return SCB_ERR_UNSUPPORTED;                        // optimal_decay_cbf_qp.py:51-52 raises NotCompatibleError
   if (!qp_model_ok(p->model)) return SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
@@ -153,6 +162,7 @@ int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const do
     case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_od_m<SCB_DYNAMIC_UNICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
     case SCB_KINEMATIC_BICYCLE_2D: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
     case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D_C3BF, 1>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
+    case SCB_QUAD_2D: rc = launch_od_m<SCB_QUAD_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
   }
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
@@ -191,7 +201,8 @@ int scb_select_obstacles(const scb_params* p, int N, int K, int M, const double*
 #define SEL(MODEL) case MODEL: select_kernel<MODEL><<<grid, kTrackBlock, smem, s>>>(*p, N, K, M, X, yaw, SCENE, sstride, OBS, nobs, idx); break;
   switch (p->model) {
     SEL(SCB_SINGLE_INTEGRATOR_2D) SEL(SCB_DYNAMIC_UNICYCLE_2D) SEL(SCB_KINEMATIC_BICYCLE_2D)
-    SEL(SCB_KINEMATIC_BICYCLE_2D_C3BF) SEL(SCB_QUAD_3D)
+    SEL(SCB_KINEMATIC_BICYCLE_2D_C3BF) SEL(SCB_QUAD_3D) SEL(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+    default: return SCB_ERR_UNSUPPORTED;               // DoubleIntegrator2D / Quad2D: closed-loop laws not built yet
   }
 #undef SEL
   CK(cudaGetLastError());
@@ -210,7 +221,9 @@ static int track_check(const scb_params* p, const scb_track* t) {
       (t->K > 0 && !t->SCENE))
     return SCB_ERR_BAD_ARG;
   if (t->controller == SCB_CTRL_MPC_CBF && (!t->u_prev || !t->track_flag || t->H < 1)) return SCB_ERR_BAD_ARG;
+  if (p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_QUAD_2D) return SCB_ERR_UNSUPPORTED;   // loop laws not built yet
   if (t->controller != SCB_CTRL_MPC_CBF && p->model == SCB_QUAD_3D) return SCB_ERR_UNSUPPORTED;
+  if (t->controller != SCB_CTRL_CBF_QP && p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF) return SCB_ERR_UNSUPPORTED;
   if (t->controller == SCB_CTRL_OPTIMAL_DECAY && p->model == SCB_SINGLE_INTEGRATOR_2D) return SCB_ERR_UNSUPPORTED;
   return SCB_OK;
 }
@@ -220,7 +233,7 @@ static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream
 #define PRE(MODEL) case MODEL: launch_pre<MODEL>(*p, *t, s, smc); break;
   switch (p->model) {
     PRE(SCB_SINGLE_INTEGRATOR_2D) PRE(SCB_DYNAMIC_UNICYCLE_2D) PRE(SCB_KINEMATIC_BICYCLE_2D)
-    PRE(SCB_KINEMATIC_BICYCLE_2D_C3BF) PRE(SCB_QUAD_3D)
+    PRE(SCB_KINEMATIC_BICYCLE_2D_C3BF) PRE(SCB_QUAD_3D) PRE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
   }
 #undef PRE
   if (t->dynamic_obs && t->K > 0) dyn_obs_kernel<<<(t->K + 127) / 128, 128, 0, s>>>(t->SCENE, t->K, p->dt);
@@ -239,7 +252,7 @@ static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream
 #define POST(MODEL) case MODEL: launch_post<MODEL>(*p, *t, s, smc); break;
   switch (p->model) {
     POST(SCB_SINGLE_INTEGRATOR_2D) POST(SCB_DYNAMIC_UNICYCLE_2D) POST(SCB_KINEMATIC_BICYCLE_2D)
-    POST(SCB_KINEMATIC_BICYCLE_2D_C3BF) POST(SCB_QUAD_3D)
+    POST(SCB_KINEMATIC_BICYCLE_2D_C3BF) POST(SCB_QUAD_3D) POST(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
   }
 #undef POST
   CK(cudaGetLastError());
@@ -425,7 +438,8 @@ int scb_odcbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const do
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
   const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
-  size_t need = padded((size_t)N * 4 * 8) + padded((size_t)N * 2 * 8) * 3 + padded(nobs_el * 8) +
+  const int nx = p->nx;
+  size_t need = padded((size_t)N * nx * 8) + padded((size_t)N * 2 * 8) * 3 + padded(nobs_el * 8) +
                 padded((size_t)N * 4) * 3 + padded((size_t)N * 8);
   int rc;
   if (use_mapped(need)) {
@@ -443,7 +457,7 @@ int scb_odcbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const do
   rc = ctx_reserve(c, need);
   if (rc != SCB_OK) return rc;
   Carver cv{c->dbuf, 0};
-  double* dX = cv.take<double>((size_t)N * 4);
+  double* dX = cv.take<double>((size_t)N * nx);
   double* dUr = cv.take<double>((size_t)N * 2);
   double* dU = cv.take<double>((size_t)N * 2);
   double* dW = cv.take<double>((size_t)N * 2);
@@ -452,7 +466,7 @@ int scb_odcbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const do
   int32_t* dS = cv.take<int32_t>(N);
   int32_t* dSel = cv.take<int32_t>(N);
   uint64_t* dA = cv.take<uint64_t>(N);
-  H2D(dX, X, (size_t)N * 4, double);
+  H2D(dX, X, (size_t)N * nx, double);
   H2D(dUr, Uref, (size_t)N * 2, double);
   if (nobs_el) H2D(dO, OBS, nobs_el, double);
   if (nobs) H2D(dN, nobs, N, int32_t);

@@ -70,7 +70,7 @@ odcbf_kernel(const __grid_constant__ scb_params p, int N, int M, const double* _
              int32_t* __restrict__ sel, int32_t* __restrict__ status, uint64_t* __restrict__ active) {
   constexpr int GPB = kBlock / LANES;
   for (long a = (long)blockIdx.x * GPB + threadIdx.x / LANES; a < N; a += (long)gridDim.x * GPB) {
-    odcbf_agent<MODEL, NW, LANES, RPL>(p, M, nobs ? nobs[a] : M, X + a * 4, Uref + a * 2, OBS + a * stride,
+    odcbf_agent<MODEL, NW, LANES, RPL>(p, M, nobs ? nobs[a] : M, X + a * ModelCT<MODEL>::NX, Uref + a * 2, OBS + a * stride,
                                        U + a * 2, omega ? omega + a * 2 : nullptr, sel ? sel + a : nullptr,
                                        status + a, active ? active + a : nullptr);
   }

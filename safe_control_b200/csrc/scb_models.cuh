@@ -10,6 +10,9 @@
 //   DynamicUnicycle2D         robots/dynamic_unicycle2D.py:42-73, 121-186
 //   KinematicBicycle2D        robots/kinematic_bicycle2D.py:75-110, 160-173
 //   KinematicBicycle2D_C3BF   dynamic_env/kinematic_bicycle2D_c3bf.py:15-75
+//   KinematicBicycle2D_DPCBF  dynamic_env/kinematic_bicycle2D_dpcbf.py:16-84
+//   DoubleIntegrator2D        robots/double_integrator2D.py:46-79, 167-222
+//   Quad2D                    robots/quad2D.py:46-82, 166-177
 // The arithmetic follows the reference's operation order where that is cheap, so rows
 // agree with the numpy path to a few ulp.  Quad3D has no continuous barrier
 // (quad3D.py:269-273) and is rejected on the host.
@@ -24,6 +27,7 @@ struct AgentCT {
   double px, py;     // position
   double c, s, v;    // cos(theta), sin(theta), speed (models with heading)
   double fx, fy;     // f(x)[0:2] = v c, v s
+  double th;         // heading itself (models whose rows need it)
 };
 
 struct RowOut {
@@ -183,6 +187,117 @@ struct ModelCT<SCB_KINEMATIC_BICYCLE_2D_C3BF> {
     r.a[1] = dh[0] * (-g.v * g.s) + dh[1] * (g.v * g.c) + dh[2] * (g.v / p.rear_ax_dist);
     const double lf = dh[0] * g.fx + dh[1] * g.fy;
     r.b = (p.cbf_mode == 1) ? h / p.dt + lf : lf + p.alpha * h;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Dynamic-parabolic CBF.  The reference's hand-written dh/dx is NOT the gradient of its h (it drops the
+// sqrt(s^2-1)/ego_dim factor): transcribed literally, never differentiated.
+template <>
+struct ModelCT<SCB_KINEMATIC_BICYCLE_2D_DPCBF> {
+  static constexpr int NX = 4, NU = 2;
+  static SCB_HD void prep(const scb_params& p, const double* x, AgentCT& g) {
+    ModelCT<SCB_DYNAMIC_UNICYCLE_2D>::prep(p, x, g);
+    g.th = x[2];
+  }
+  static SCB_HD void barrier(const scb_params& p, const AgentCT& g, const double* o, double& h, double* dh) {
+    const double k_lambda = 0.1, k_mu = 0.5, sm = 1.05;                        // ctor defaults (:11), s (:16)
+    const double ovx = o[3], ovy = o[4];
+    const double ego = (o[2] + p.radius) * sm;
+    const double prx = o[0] - g.px, pry = o[1] - g.py;
+    const double vrx = ovx - g.v * g.c, vry = ovy - g.v * g.s;
+    const double pm = sqrt(prx * prx + pry * pry);
+    const double vm = sqrt(vrx * vrx + vry * vry);
+    const double rot = atan2(pry, prx);
+    double sr, cr; sincos_pair(rot, sr, cr);
+    const double vnx = cr * vrx + sr * vry;                                     // R @ v_rel (:57-63)
+    const double vny = -sr * vrx + cr * vry;
+    const double eps = 1e-6;
+    const double dsafe = fmax(pm * pm - ego * ego, eps);
+    const double sd = sqrt(dsafe);
+    const double k2 = sqrt(sm * sm - 1.0) / ego;
+    const double lam = k_lambda * sd / vm * k2;
+    const double mu = k_mu * sd * k2;
+    h = vnx + lam * (vny * vny) + mu;
+    const double pm2 = pm * pm;
+    double srt, crt; sincos_pair(rot - g.th, srt, crt);
+    dh[0] = pry * vny / pm2 - k_lambda * prx * (vny * vny) / vm / sd - 2.0 * k_lambda * sd / vm * vny * pry / pm2 * vnx - k_mu * prx / sd;
+    dh[1] = -prx * vny / pm2 - k_lambda * pry * (vny * vny) / vm / sd + 2.0 * k_lambda * sd / vm * vny * prx / pm2 * vnx - k_mu * pry / sd;
+    dh[2] = -g.v * srt - k_lambda * sd * g.v * (ovx * g.s - ovy * g.c) * (vny * vny) / (vm * vm * vm) - 2.0 * k_lambda * sd * vny * g.v * crt / vm;
+    dh[3] = -crt - k_lambda * sd / (vm * vm * vm) * (g.v - ovx * g.c - ovy * g.s) * (vny * vny) - 2.0 * k_lambda * sd * vny * srt / vm;
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    double h, dh[4];
+    barrier(p, g, o, h, dh);
+    r.a[0] = dh[3];
+    r.a[1] = dh[0] * (-g.v * g.s) + dh[1] * (g.v * g.c) + dh[2] * (g.v / p.rear_ax_dist);
+    const double lf = dh[0] * g.fx + dh[1] * g.fy;
+    r.b = (p.cbf_mode == 1) ? h / p.dt + lf : lf + p.alpha * h;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// DoubleIntegrator2D: X = [x, y, vx, vy], f = [vx, vy, 0, 0], g = [[0,0],[0,0],[1,0],[0,1]]
+template <>
+struct ModelCT<SCB_DOUBLE_INTEGRATOR_2D> {
+  static constexpr int NX = 4, NU = 2;
+  static SCB_HD void prep(const scb_params&, const double* x, AgentCT& g) {
+    g.px = x[0]; g.py = x[1]; g.c = 1.0; g.s = 0.0; g.v = 0.0; g.th = 0.0;
+    g.fx = x[2]; g.fy = x[3];
+  }
+  static SCB_HD void barrier(const scb_params& p, const AgentCT& g, const double* o, double& h, double& hd, double* dhd) {
+    h = 0.0; hd = 0.0; dhd[0] = dhd[1] = dhd[2] = dhd[3] = 0.0;
+    const double flag = o[6];
+    if (flag == 0.0) {                                        // double_integrator2D.py:172-184
+      const double dx = g.px - o[0], dy = g.py - o[1];
+      const double dmin = o[2] + p.radius;
+      h = (dx * dx + dy * dy) - 1.01 * (dmin * dmin);
+      hd = 2.0 * dx * g.fx + 2.0 * dy * g.fy;
+      dhd[0] = 2.0 * g.fx; dhd[1] = 2.0 * g.fy; dhd[2] = 2.0 * dx; dhd[3] = 2.0 * dy;
+    } else if (flag == 1.0) {                                 // :185-220
+      const SEOut se = superellipsoid_terms(g.px, g.py, o[0], o[1], o[2], o[3], o[4], o[5], p.radius);
+      h = se.h;
+      hd = se.gx * g.fx + se.gy * g.fy;
+      dhd[0] = se.hxx * g.fx + se.hxy * g.fy;
+      dhd[1] = se.hxy * g.fx + se.hyy * g.fy;
+      dhd[2] = se.gx; dhd[3] = se.gy;
+    }
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    double h, hd, dhd[4];
+    barrier(p, g, o, h, hd, dhd);
+    r.a[0] = dhd[2]; r.a[1] = dhd[3];
+    const double lf = dhd[0] * g.fx + dhd[1] * g.fy;
+    r.b = rel2_b(p, h, hd, lf);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Quad2D: X = [x, z, theta, vx, vz, theta_dot], U = [f_right, f_left]; f = [vx, vz, theta_dot, 0, -g, 0],
+// g columns = [0, 0, 0, -sin(theta)/m, cos(theta)/m, +-r/I] (quad2D.py:46-82).  Circle barrier on (x, z) only
+// (flag ignored, :166-177): dh_dot/dx = [2 vx, 2 vz, 0, 2 dx, 2 dz, 0].
+template <>
+struct ModelCT<SCB_QUAD_2D> {
+  static constexpr int NX = 6, NU = 2;
+  static SCB_HD void prep(const scb_params&, const double* x, AgentCT& g) {
+    g.px = x[0]; g.py = x[1]; g.th = x[2]; g.v = 0.0;
+    sincos_pair(x[2], g.s, g.c);
+    g.fx = x[3]; g.fy = x[4];
+  }
+  static SCB_HD void barrier(const scb_params& p, const AgentCT& g, const double* o, double& h, double& hd, double* dhd) {
+    const double dx = g.px - o[0], dy = g.py - o[1];
+    const double dmin = o[2] + p.radius;
+    h = (dx * dx + dy * dy) - 1.01 * (dmin * dmin);
+    hd = 2.0 * dx * g.fx + 2.0 * dy * g.fy;
+    dhd[0] = 2.0 * g.fx; dhd[1] = 2.0 * g.fy; dhd[2] = 2.0 * dx; dhd[3] = 2.0 * dy;    // w.r.t. (x, z, vx, vz)
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    double h, hd, dhd[4];
+    barrier(p, g, o, h, hd, dhd);
+    const double a = dhd[2] * (-g.s / p.mass) + dhd[3] * (g.c / p.mass);
+    r.a[0] = a; r.a[1] = a;
+    const double lf = dhd[0] * g.fx + dhd[1] * g.fy + dhd[3] * (-p.gravity);
+    r.b = rel2_b(p, h, hd, lf);
   }
 };
 

@@ -43,6 +43,9 @@ int scb_model_dims(int model, int* nx, int* nu) {
     case SCB_KINEMATIC_BICYCLE_2D:
     case SCB_KINEMATIC_BICYCLE_2D_C3BF: x = 4; u = 2; break;
     case SCB_QUAD_3D: x = 12; u = 4; break;
+    case SCB_DOUBLE_INTEGRATOR_2D:
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: x = 4; u = 2; break;
+    case SCB_QUAD_2D: x = 6; u = 2; break;
     default: return SCB_ERR_BAD_ARG;
   }
   if (nx) *nx = x;
@@ -83,13 +86,15 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       if (mpc) { p->alpha1 = p->alpha2 = 0.15; p->Q[0] = p->Q[1] = 50; p->Q[2] = 0.01; p->Q[3] = 30; p->R[0] = p->R[1] = 0.5; }
       break;
     case SCB_KINEMATIC_BICYCLE_2D:
-    case SCB_KINEMATIC_BICYCLE_2D_C3BF: {
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF:
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: {
       const double Lr = 0.2, L = 0.4, dmax = 32.0 * M_PI / 180.0;
       const double bmax = atan(Lr / L * tan(dmax));
       p->rear_ax_dist = Lr;
       p->u_lb[0] = -5.0; p->u_ub[0] = 5.0; p->u_lb[1] = -bmax; p->u_ub[1] = bmax;
       p->v_min = 0.2; p->v_max = 3.5;
-      const bool c3 = model == SCB_KINEMATIC_BICYCLE_2D_C3BF;
+      const bool c3 = model != SCB_KINEMATIC_BICYCLE_2D;          // C3BF and DPCBF: relative degree 1
+      if (model == SCB_KINEMATIC_BICYCLE_2D_DPCBF && !qp) return SCB_ERR_UNSUPPORTED;   // optimal_decay_cbf_qp.py:51-52 raises; MPC: not built
       if (qp) { if (c3) p->alpha = 1.5; else p->alpha1 = p->alpha2 = 1.5; }
       if (od) {
         p->omega1_0 = 1.0; p->p_sb1 = 1e4;
@@ -101,6 +106,19 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       }
       break;
     }
+    case SCB_DOUBLE_INTEGRATOR_2D:                     // double_integrator2D.py:40-44, cbf_qp.py:18-20,66-69
+      if (!qp) return SCB_ERR_UNSUPPORTED;             // optimal decay raises NotCompatibleError; MPC: not built
+      p->u_lb[0] = p->u_lb[1] = -1.0; p->u_ub[0] = p->u_ub[1] = 1.0;
+      p->v_max = 1.0; p->v_min = -1.0;
+      p->alpha1 = p->alpha2 = 1.5;
+      break;
+    case SCB_QUAD_2D:                                  // quad2D.py:40-46, cbf_qp.py:30-32,74-79, optimal_decay_cbf_qp.py:38-45
+      if (mpc) return SCB_ERR_UNSUPPORTED;             // MPC: not built
+      p->mass = 1.0; p->Iy = 0.01; p->gravity = 9.81;
+      p->u_lb[0] = p->u_lb[1] = 1.0; p->u_ub[0] = p->u_ub[1] = 10.0;
+      if (qp) p->alpha1 = p->alpha2 = 1.5;
+      if (od) { p->alpha1 = p->alpha2 = 0.5; p->omega1_0 = p->omega2_0 = 1.0; p->p_sb1 = p->p_sb2 = 1e4; }
+      break;
     case SCB_QUAD_3D: {
       if (!mpc) return SCB_ERR_UNSUPPORTED;            // agent_barrier raises, quad3D.py:269-273
       p->mass = 3.0; p->Ix = p->Iy = p->Iz = 0.5; p->arm_L = 0.3; p->nu_coef = 0.1;

@@ -173,6 +173,16 @@ SCB_HD void odcbf_agent(const scb_params& p, int M, int nobs, const double* x, c
         ra[0][2] = (p.alpha1 + p.alpha2) * hd;
         ra[0][NV - 1] = (p.alpha1 * p.alpha2) * h;
       }
+    } else if (MODEL == SCB_QUAD_2D) {                                   // :144-149 (same branch as DynamicUnicycle2D)
+      double h, hd, dhd[4];
+      ModelCT<SCB_QUAD_2D>::barrier(p, g, o, h, hd, dhd);
+      const double a = dhd[2] * (-g.s / p.mass) + dhd[3] * (g.c / p.mass);
+      ra[0][0] = a; ra[0][1] = a;
+      rb[0] = dhd[0] * g.fx + dhd[1] * g.fy + dhd[3] * (-p.gravity);
+      if (NW == 2) {
+        ra[0][2] = (p.alpha1 + p.alpha2) * hd;
+        ra[0][NV - 1] = (p.alpha1 * p.alpha2) * h;
+      }
     }
     // plain KinematicBicycle2D: the reference has no branch -> zero row
   }

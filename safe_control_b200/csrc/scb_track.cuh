@@ -140,6 +140,8 @@ struct ModelLoop<SCB_KINEMATIC_BICYCLE_2D> {
 
 template <>
 struct ModelLoop<SCB_KINEMATIC_BICYCLE_2D_C3BF> : ModelLoop<SCB_KINEMATIC_BICYCLE_2D> {};
+template <>
+struct ModelLoop<SCB_KINEMATIC_BICYCLE_2D_DPCBF> : ModelLoop<SCB_KINEMATIC_BICYCLE_2D> {};
 
 template <>
 struct ModelLoop<SCB_QUAD_3D> {

@@ -64,6 +64,17 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
         p.rear_ax_dist = lr
         p.u_lb[0], p.u_ub[0], p.u_lb[1], p.u_ub[1] = -a, a, -b, b
         p.v_min, p.v_max = vmin, v
+    elif model == "DoubleIntegrator2D":                       # double_integrator2D.py:40-44
+        a = float(s.setdefault("a_max", 1.0)); v = float(s.setdefault("v_max", 1.0))
+        s.setdefault("ax_max", a); s.setdefault("ay_max", a); s.setdefault("w_max", 0.5)
+        p.u_lb[0] = p.u_lb[1] = -a
+        p.u_ub[0] = p.u_ub[1] = a
+        p.v_max = v; p.v_min = -v
+    elif model == "Quad2D":                                   # quad2D.py:40-46
+        p.mass = float(s.setdefault("mass", 1.0)); p.Iy = float(s.setdefault("inertia", 0.01))
+        fmin = float(s.setdefault("f_min", 1.0)); fmax = float(s.setdefault("f_max", 10.0))
+        p.u_lb[0] = p.u_lb[1] = fmin
+        p.u_ub[0] = p.u_ub[1] = fmax
     elif model == "Quad3D":
         p.mass = float(s.setdefault("mass", 3.0))
         p.Ix = float(s.setdefault("Ix", 0.5)); p.Iy = float(s.setdefault("Iy", 0.5)); p.Iz = float(s.setdefault("Iz", 0.5))
@@ -86,7 +97,7 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
 
 def cbf_param_dict(p, controller, model):
     """The `.cbf_param` dict the reference exposes (tracking.py:738 reads alpha1/alpha2)."""
-    rel2 = model in ("DynamicUnicycle2D", "KinematicBicycle2D")
+    rel2 = model in ("DynamicUnicycle2D", "KinematicBicycle2D", "DoubleIntegrator2D", "Quad2D")
     d = {"alpha1": p.alpha1, "alpha2": p.alpha2} if rel2 else {"alpha": p.alpha}
     if controller == "optimal_decay_cbf_qp":
         d.update(omega1=p.omega1_0, p_sb1=p.p_sb1)

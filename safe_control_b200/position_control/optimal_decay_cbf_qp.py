@@ -25,7 +25,8 @@ class OptimalDecayCBFQP:
         X = np.ascontiguousarray(np.asarray(getattr(self.robot, "X", robot_state), dtype=np.float64).reshape(1, -1))
         OBS, nobs = obs_rows(nearest_obs, self.num_obs)
         nobs = np.maximum(nobs, 0).astype(np.int32)        # None -> zero row (optimal_decay_cbf_qp.py:134-138)
-        U, om, sel, st, act = host_ctx(self.device).odcbf_solve(self.params, self.num_obs, X[:, :4], u_ref, OBS, nobs)
+        U, om, sel, st, act = host_ctx(self.device).odcbf_solve(self.params, self.num_obs,
+                                                                np.ascontiguousarray(X[:, :self.params.nx]), u_ref, OBS, nobs)
         self.status = status_string(st[0])
         self.omega = om[0]
         return U.reshape(-1, 1)

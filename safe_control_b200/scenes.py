@@ -18,9 +18,11 @@ DUMMY_OBS = np.array([1000.0, 1000.0, 0.0, 0.0, 0.0, 0.0, 0.0])
 ANGLE_UNPASSED = {   # tracking.py:352-357
     "SingleIntegrator2D": 2.0 * np.pi, "Quad3D": 2.0 * np.pi, "DynamicUnicycle2D": 1.2 * np.pi,
     "KinematicBicycle2D": 2.0 * np.pi, "KinematicBicycle2D_C3BF": 2.0 * np.pi,
+    "KinematicBicycle2D_DPCBF": 2.0 * np.pi, "DoubleIntegrator2D": 2.0 * np.pi, "Quad2D": 2.0 * np.pi,
 }
 BARRIER_BETA = {"SingleIntegrator2D": 1.01, "DynamicUnicycle2D": 1.01, "KinematicBicycle2D": 1.1,
-                "KinematicBicycle2D_C3BF": 1.1, "Quad3D": 1.01}
+                "KinematicBicycle2D_C3BF": 1.1, "Quad3D": 1.01, "KinematicBicycle2D_DPCBF": 1.1,
+                "DoubleIntegrator2D": 1.01, "Quad2D": 1.01}
 
 
 def angle_normalize(x):
@@ -55,6 +57,18 @@ def nominal_input(model, spec, X, goal, optimal_decay=False):
         beta = np.arctan(spec["rear_ax_dist"] / spec["wheel_base"] * np.tan(delta))
         v = np.clip(k_v * dist * np.maximum(0.0, np.cos(err)), spec["v_min"], spec["v_max"])
         return np.stack([k_a * (v - X[:, 3]), beta], axis=1)
+    if model == "DoubleIntegrator2D":                          # double_integrator2D.py:116-143
+        err = goal[:, 0:2] - X[:, 0:2]
+        err = np.sign(err) * np.maximum(np.abs(err) - 0.05, 0.0)
+        mag = np.linalg.norm(err, axis=1, keepdims=True)
+        v_des = np.where(mag > spec["v_max"], err * spec["v_max"] / np.maximum(mag, 1e-300), err)
+        a = v_des - X[:, 2:4]
+        am = np.linalg.norm(a, axis=1, keepdims=True)
+        return np.where(am > spec["a_max"], a * spec["a_max"] / np.maximum(am, 1e-300), a)
+    if model == "Quad2D":      # the reference's cascaded PD law is off the solve path: hover thrust + a seeded perturbation
+        rng = np.random.default_rng(X.shape[0])
+        hover = spec["mass"] * 9.81 / 2.0
+        return hover + rng.uniform(-2.0, 2.0, (X.shape[0], 2))
     if model == "Quad3D":                                      # quad3D.py:160-206
         g, m = 9.8, spec["mass"]
         k_p, k_d, k_ang = 1.0, 2.0, 5.0
@@ -107,6 +121,10 @@ def default_spec(model):
                  beta_max=math.atan(0.5 * math.tan(dmax)), v_min=0.2)
     elif model == "Quad3D":
         s.update(mass=3.0, Ix=0.5, Iy=0.5, Iz=0.5, L=0.3, nu=0.1, u_max=10.0, u_min=-10.0)
+    elif model == "DoubleIntegrator2D":
+        s.update(a_max=1.0, v_max=1.0, w_max=0.5)
+    elif model == "Quad2D":
+        s.update(mass=1.0, inertia=0.01, f_min=1.0, f_max=10.0)
     return s
 
 
@@ -115,7 +133,7 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
     rng = np.random.default_rng(seed)
     spec = dict(default_spec(model), **(spec or {}))
     if dynamic is None:
-        dynamic = model.endswith("C3BF")
+        dynamic = model.endswith("C3BF") or model.endswith("DPCBF")
     L = (2.5 if dense else 4.0) * math.sqrt(M)
     scene = np.zeros((M, 7))
     scene[:, 0:2] = rng.uniform(0, L, (M, 2))
@@ -133,10 +151,29 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
         pos[todo[ok]] = cand[ok]
         todo = todo[~ok]
     goal2 = rng.uniform(0, L, (N, 2))
-    nx = {"SingleIntegrator2D": 2, "Quad3D": 12}.get(model, 4)
+    nx = {"SingleIntegrator2D": 2, "Quad3D": 12, "Quad2D": 6}.get(model, 4)
     X = np.zeros((N, nx)); X[:, 0:2] = pos
     yaw = np.zeros(N)
-    if nx == 4:
+    if model == "DoubleIntegrator2D":
+        sp = rng.uniform(0, spec["v_max"], N); hd = rng.uniform(-np.pi, np.pi, N)
+        if dense:   # head at the nearest obstacle
+            d = scene[None, :, 0:2] - pos[:, None, :]
+            j = np.argmin((d ** 2).sum(-1), axis=1)
+            hd = np.arctan2(d[np.arange(N), j, 1], d[np.arange(N), j, 0]) + rng.normal(0, 0.2, N)
+            sp = rng.uniform(0.5, 1.0, N) * spec["v_max"]
+        X[:, 2] = sp * np.cos(hd); X[:, 3] = sp * np.sin(hd)
+        yaw = rng.uniform(-np.pi, np.pi, N)
+        goal = goal2
+    elif model == "Quad2D":
+        X[:, 2] = rng.uniform(-0.4, 0.4, N); X[:, 3:5] = rng.uniform(-1.0, 1.0, (N, 2)); X[:, 5] = rng.normal(0, 0.2, N)
+        if dense:
+            d = scene[None, :, 0:2] - pos[:, None, :]
+            j = np.argmin((d ** 2).sum(-1), axis=1)
+            dirn = d[np.arange(N), j]; dirn /= np.linalg.norm(dirn, axis=1, keepdims=True)
+            X[:, 3:5] = dirn * rng.uniform(0.5, 1.5, (N, 1))
+        yaw = X[:, 2].copy()
+        goal = goal2
+    elif nx == 4:
         theta = rng.uniform(-np.pi, np.pi, N)
         if model == "DynamicUnicycle2D":
             v = rng.uniform(0, spec["v_max"], N)

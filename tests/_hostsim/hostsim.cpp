@@ -28,7 +28,7 @@ static void run_od(const scb_params& p, int N, int M, const double* X, const dou
                    long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
                    uint64_t* active) {
   for (int i = 0; i < N; ++i)
-    odcbf_agent<MODEL, NW, 1, 128>(p, M, nobs ? nobs[i] : M, X + (size_t)i * 4, Uref + (size_t)i * 2,
+    odcbf_agent<MODEL, NW, 1, 128>(p, M, nobs ? nobs[i] : M, X + (size_t)i * ModelCT<MODEL>::NX, Uref + (size_t)i * 2,
                                    OBS + (size_t)i * stride, U + (size_t)i * 2, omega ? omega + (size_t)i * 2 : nullptr,
                                    sel ? sel + i : nullptr, status + i, active ? active + i : nullptr);
 }
@@ -52,6 +52,9 @@ int hostsim_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const
         ROWCASE(SCB_DYNAMIC_UNICYCLE_2D)
         ROWCASE(SCB_KINEMATIC_BICYCLE_2D)
         ROWCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
+        ROWCASE(SCB_DOUBLE_INTEGRATOR_2D)
+        ROWCASE(SCB_QUAD_2D)
+        ROWCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
         default: return SCB_ERR_UNSUPPORTED;
       }
       for (int t = 0; t < p->nu; ++t) A[((size_t)i * M + r) * p->nu + t] = a[t];
@@ -69,6 +72,9 @@ int hostsim_cbfqp_solve(const scb_params* p, int N, int M, const double* X, cons
     case SCB_DYNAMIC_UNICYCLE_2D: run_cbfqp<SCB_DYNAMIC_UNICYCLE_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     case SCB_KINEMATIC_BICYCLE_2D: run_cbfqp<SCB_KINEMATIC_BICYCLE_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     case SCB_KINEMATIC_BICYCLE_2D_C3BF: run_cbfqp<SCB_KINEMATIC_BICYCLE_2D_C3BF, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
+    case SCB_DOUBLE_INTEGRATOR_2D: run_cbfqp<SCB_DOUBLE_INTEGRATOR_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
+    case SCB_QUAD_2D: run_cbfqp<SCB_QUAD_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: run_cbfqp<SCB_KINEMATIC_BICYCLE_2D_DPCBF, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;
@@ -82,6 +88,7 @@ int hostsim_odcbf_solve(const scb_params* p, int N, int M, const double* X, cons
     case SCB_DYNAMIC_UNICYCLE_2D: run_od<SCB_DYNAMIC_UNICYCLE_2D, 2>(*p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active); break;
     case SCB_KINEMATIC_BICYCLE_2D: run_od<SCB_KINEMATIC_BICYCLE_2D, 2>(*p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active); break;
     case SCB_KINEMATIC_BICYCLE_2D_C3BF: run_od<SCB_KINEMATIC_BICYCLE_2D_C3BF, 1>(*p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active); break;
+    case SCB_QUAD_2D: run_od<SCB_QUAD_2D, 2>(*p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active); break;
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;
@@ -139,6 +146,7 @@ int hostsim_select_obstacles(const scb_params* p, int N, int K, int M, const dou
       SELCASE(SCB_KINEMATIC_BICYCLE_2D)
       SELCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       SELCASE(SCB_QUAD_3D)
+      SELCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -158,6 +166,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       PRECASE(SCB_KINEMATIC_BICYCLE_2D)
       PRECASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       PRECASE(SCB_QUAD_3D)
+      PRECASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -202,6 +211,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       POSTCASE(SCB_KINEMATIC_BICYCLE_2D)
       POSTCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       POSTCASE(SCB_QUAD_3D)
+      POSTCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }

@@ -36,6 +36,9 @@ from safe_control.robots.dynamic_unicycle2D import DynamicUnicycle2D  # noqa: E4
 from safe_control.robots.kinematic_bicycle2D import KinematicBicycle2D  # noqa: E402
 from safe_control.dynamic_env.kinematic_bicycle2D_c3bf import KinematicBicycle2D_C3BF  # noqa: E402
 from safe_control.robots.quad3D import Quad3D  # noqa: E402
+from safe_control.robots.double_integrator2D import DoubleIntegrator2D  # noqa: E402
+from safe_control.robots.quad2D import Quad2D  # noqa: E402
+from safe_control.dynamic_env.kinematic_bicycle2D_dpcbf import KinematicBicycle2D_DPCBF  # noqa: E402
 from safe_control.position_control.cbf_qp import CBFQP  # noqa: E402
 from safe_control.position_control.optimal_decay_cbf_qp import OptimalDecayCBFQP  # noqa: E402
 
@@ -45,7 +48,12 @@ MODEL_CLS = {
     "KinematicBicycle2D": KinematicBicycle2D,
     "KinematicBicycle2D_C3BF": KinematicBicycle2D_C3BF,
     "Quad3D": Quad3D,
+    "DoubleIntegrator2D": DoubleIntegrator2D,
+    "Quad2D": Quad2D,
+    "KinematicBicycle2D_DPCBF": KinematicBicycle2D_DPCBF,
 }
+BASE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D")
+EXTRA_MODELS = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")      # SURVEY 8f-2, second fixture set
 DT = 0.05
 
 
@@ -74,6 +82,10 @@ def rand_state(rng, name):
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi), rng.uniform(0, 1.0)])
     if name.startswith("KinematicBicycle2D"):
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi), rng.uniform(0.2, 3.5)])
+    if name == "DoubleIntegrator2D":
+        return np.array([*rng.uniform(0, 10, 2), *rng.uniform(-0.7, 0.7, 2)])
+    if name == "Quad2D":
+        return np.array([*rng.uniform(0, 10, 2), rng.uniform(-0.5, 0.5), *rng.uniform(-1, 1, 2), rng.uniform(-0.3, 0.3)])
     x = np.zeros(12)
     x[0:2] = rng.uniform(0, 10, 2); x[2] = rng.uniform(1, 3)
     x[3:6] = rng.normal(0, 0.05, 3); x[6:9] = rng.normal(0, 0.5, 3); x[9:12] = rng.normal(0, 0.05, 3)
@@ -87,6 +99,10 @@ def rand_input(rng, spec, name):
         return rng.uniform(-0.5, 0.5, 2)
     if name.startswith("KinematicBicycle2D"):
         return np.array([rng.uniform(-5, 5), rng.uniform(-0.3, 0.3)])
+    if name == "DoubleIntegrator2D":
+        return rng.uniform(-1, 1, 2)
+    if name == "Quad2D":
+        return rng.uniform(1, 10, 2)
     return rng.uniform(-10, 10, 4)
 
 
@@ -108,18 +124,18 @@ def rand_superellipsoid(rng, near):
                      rng.uniform(-np.pi, np.pi), 1.0])
 
 
-def gen_models(rng, n=48):
+def gen_models(rng, n=48, names=BASE_MODELS, fname="ref_models.npz"):
     out = {}
-    for name in MODEL_CLS:
+    for name in names:
         X, U, OBS, G = [], [], [], []
         F, Gm, STEP, NOM = [], [], [], []
         CT, DTB = [], []
         for _ in range(n):
             x = rand_state(rng, name); fac = Facade(name, x); m = fac.robot
             u = rand_input(rng, fac.robot_spec, name)
-            dyn = name.endswith("C3BF")
+            dyn = name.endswith("C3BF") or name.endswith("DPCBF")
             obs = [rand_circle(rng, x, dyn) for _ in range(3)]
-            if name in ("SingleIntegrator2D", "DynamicUnicycle2D"):
+            if name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D"):
                 obs.append(rand_superellipsoid(rng, x))
             else:
                 obs.append(rand_circle(rng, x, dyn))
@@ -128,12 +144,16 @@ def gen_models(rng, n=48):
             F.append(np.asarray(fac.f(), float).reshape(-1))
             Gm.append(np.asarray(fac.g(), float))
             xc, uc = x.reshape(-1, 1).copy(), u.reshape(-1, 1)
-            if name in ("SingleIntegrator2D", "DynamicUnicycle2D"):
+            if name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D", "Quad2D"):
                 STEP.append(np.asarray(m.step(xc, uc), float).reshape(-1))
             else:
                 STEP.append(np.asarray(m.step(xc, uc, casadi=False), float).reshape(-1))
             if name == "SingleIntegrator2D":
                 NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2]), float).reshape(-1))
+            elif name == "DoubleIntegrator2D":   # facade: (X, goal, d_min, k_v, k_a) (robots/robot.py:408-409)
+                NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2], 0.05, 1.0, 1.0), float).reshape(-1))
+            elif name == "Quad2D":               # cascaded PD law, not on the solve path: not restated
+                NOM.append(np.full(2, np.nan))
             elif name == "Quad3D":
                 NOM.append(np.asarray(m.nominal_input(fac.X, goal), float).reshape(-1))
             else:   # facade passes (X, goal, d_min, k_omega, k_a, k_v) positionally (robots/robot.py:406-407)
@@ -150,25 +170,30 @@ def gen_models(rng, n=48):
         out[name] = dict(X=np.stack(X), U=np.stack(U), OBS=np.stack(OBS), GOAL=np.stack(G), F=np.stack(F),
                          G=np.stack(Gm), STEP=np.stack(STEP), NOM=np.stack(NOM), CT=np.stack(CT), DT=np.stack(DTB))
     flat = {f"{k}/{kk}": v for k, d in out.items() for kk, v in d.items()}
-    np.savez_compressed(os.path.join(HERE, "ref_models.npz"), **flat)
-    print("ref_models.npz:", {k: v["X"].shape for k, v in out.items()})
+    np.savez_compressed(os.path.join(HERE, fname), **flat)
+    print(fname, {k: v["X"].shape for k, v in out.items()})
 
 
-def gen_cbfqp(rng, n=64, num_obs=6):
+BASE_CBFQP = [("SingleIntegrator2D", {}), ("DynamicUnicycle2D", {}), ("KinematicBicycle2D", {}),
+              ("KinematicBicycle2D_C3BF", {}), ("DynamicUnicycle2D", {"cbf_mode": "hard"}),
+              ("DynamicUnicycle2D", {"cbf_alpha1": 0.7, "cbf_alpha2": 2.5, "a_max": 1.0, "radius": 0.3})]
+EXTRA_CBFQP = [("DoubleIntegrator2D", {}), ("Quad2D", {}), ("KinematicBicycle2D_DPCBF", {}),
+               ("KinematicBicycle2D_DPCBF", {"cbf_mode": "hard"}), ("DoubleIntegrator2D", {"cbf_mode": "hard", "a_max": 2.0})]
+
+
+def gen_cbfqp(rng, n=64, num_obs=6, cases=BASE_CBFQP, fname="ref_cbfqp.npz"):
     """Reference CBFQP end to end (row assembly + problem + status)."""
     flat = {}
-    for name, spec in [("SingleIntegrator2D", {}), ("DynamicUnicycle2D", {}), ("KinematicBicycle2D", {}),
-                       ("KinematicBicycle2D_C3BF", {}), ("DynamicUnicycle2D", {"cbf_mode": "hard"}),
-                       ("DynamicUnicycle2D", {"cbf_alpha1": 0.7, "cbf_alpha2": 2.5, "a_max": 1.0, "radius": 0.3})]:
+    for name, spec in cases:
         tag = name + ("" if not spec else "+" + ",".join(f"{k}={v}" for k, v in spec.items()))
         X, UR, OBS, NOBS, A, B, Uo, ST = [], [], [], [], [], [], [], []
         for i in range(n):
             x = rand_state(rng, name); fac = Facade(name, x, spec)
             ctrl = CBFQP(fac, fac.robot_spec, num_obs=num_obs)
             k = int(rng.integers(0, num_obs + 3))             # also more obstacles than rows
-            dyn = name.endswith("C3BF")
+            dyn = name.endswith("C3BF") or name.endswith("DPCBF")
             obs = np.stack([rand_circle(rng, x, dyn) for _ in range(k)]) if k else None
-            if k and name in ("SingleIntegrator2D", "DynamicUnicycle2D") and i % 4 == 0:
+            if k and name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D") and i % 4 == 0:
                 obs[0] = rand_superellipsoid(rng, x)
             u_ref = rand_input(rng, fac.robot_spec, name) * 1.3   # sometimes outside the box
             u = ctrl.solve_control_problem(fac.X, {"u_ref": u_ref.reshape(-1, 1)}, obs)
@@ -182,12 +207,12 @@ def gen_cbfqp(rng, n=64, num_obs=6):
         for k_, v in dict(X=X, UREF=UR, OBS=OBS, NOBS=NOBS, A=A, B=B, U=Uo, STATUS=ST).items():
             flat[f"{tag}/{k_}"] = np.asarray(v)
         print(tag, "infeasible:", int(np.sum(ST)), "of", n)
-    np.savez_compressed(os.path.join(HERE, "ref_cbfqp.npz"), **flat)
+    np.savez_compressed(os.path.join(HERE, fname), **flat)
 
 
-def gen_odcbf(rng, n=64):
+def gen_odcbf(rng, n=64, names=("KinematicBicycle2D_C3BF", "DynamicUnicycle2D", "KinematicBicycle2D"), fname="ref_odcbf.npz"):
     flat = {}
-    for name in ("KinematicBicycle2D_C3BF", "DynamicUnicycle2D", "KinematicBicycle2D"):
+    for name in names:
         X, UR, OBS, HAS, Uo, OM, ST = [], [], [], [], [], [], []
         for i in range(n):
             x = rand_state(rng, name); fac = Facade(name, x)
@@ -207,7 +232,7 @@ def gen_odcbf(rng, n=64):
         for k_, v in dict(X=X, UREF=UR, OBS=OBS, HAS=HAS, U=Uo, OMEGA=OM, STATUS=ST).items():
             flat[f"{name}/{k_}"] = np.asarray(v)
         print("od", name, "infeasible:", int(np.sum(ST)), "of", n)
-    np.savez_compressed(os.path.join(HERE, "ref_odcbf.npz"), **flat)
+    np.savez_compressed(os.path.join(HERE, fname), **flat)
 
 
 if __name__ == "__main__":
@@ -215,3 +240,7 @@ if __name__ == "__main__":
     gen_models(rng)
     gen_cbfqp(rng)
     gen_odcbf(rng)
+    rng2 = np.random.default_rng(20261017)                   # second fixture set: the models added for SURVEY 8f-2
+    gen_models(rng2, names=EXTRA_MODELS, fname="ref_models2.npz")
+    gen_cbfqp(rng2, cases=EXTRA_CBFQP, fname="ref_cbfqp2.npz")
+    gen_odcbf(rng2, names=("Quad2D",), fname="ref_odcbf2.npz")

@@ -69,6 +69,10 @@ def test_reference_fixtures_odcbf():
     ("SingleIntegrator2D", 2, True),       # config-1 sized rows
     ("DynamicUnicycle2D", 40, True),       # RPL=2 path
     ("DynamicUnicycle2D", 100, False),     # RPL=4 path
+    ("DoubleIntegrator2D", 16, True),      # SURVEY 8f-2 barrier families
+    ("Quad2D", 16, True),
+    ("KinematicBicycle2D_DPCBF", 16, True),
+    ("KinematicBicycle2D_DPCBF", 8, False),
 ])
 def test_scene_cbfqp_vs_oracle(model, M, dense):
     from safe_control_b200 import BatchedCBFQP, scenes
@@ -80,7 +84,7 @@ def test_scene_cbfqp_vs_oracle(model, M, dense):
     print(model, M, dense, stats)
 
 
-@pytest.mark.parametrize("model", ["KinematicBicycle2D_C3BF", "DynamicUnicycle2D", "KinematicBicycle2D"])
+@pytest.mark.parametrize("model", ["KinematicBicycle2D_C3BF", "DynamicUnicycle2D", "KinematicBicycle2D", "Quad2D"])
 def test_scene_odcbf_vs_oracle(model):
     from safe_control_b200 import BatchedOptimalDecayCBFQP, scenes
     M, N = 32, 256

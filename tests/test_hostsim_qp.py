@@ -55,7 +55,8 @@ def test_reference_fixtures_odcbf():
 
 @pytest.mark.parametrize("model,dense", [("DynamicUnicycle2D", False), ("DynamicUnicycle2D", True),
                                          ("KinematicBicycle2D", True), ("KinematicBicycle2D_C3BF", True),
-                                         ("SingleIntegrator2D", True)])
+                                         ("SingleIntegrator2D", True), ("DoubleIntegrator2D", True),
+                                         ("Quad2D", True), ("KinematicBicycle2D_DPCBF", True)])
 def test_scene_cbfqp_vs_oracle(model, dense):
     M, N = 16, 160
     sc = scenes.make_scene(model, N, M, seed=1234, dense=dense)
@@ -66,7 +67,7 @@ def test_scene_cbfqp_vs_oracle(model, dense):
     assert stats["masks_compared"] + stats["infeasible"] > N // 2
 
 
-@pytest.mark.parametrize("model", ["KinematicBicycle2D_C3BF", "DynamicUnicycle2D", "KinematicBicycle2D"])
+@pytest.mark.parametrize("model", ["KinematicBicycle2D_C3BF", "DynamicUnicycle2D", "KinematicBicycle2D", "Quad2D"])
 def test_scene_odcbf_vs_oracle(model):
     M, N = 32, 96
     sc = scenes.make_scene(model, N, M, seed=11, dense=True, dynamic=True, optimal_decay=True)
