@@ -18,9 +18,15 @@ trust-constr), derivatives by torch.autograd in float64:
          missing obstacle slots = [1000, 1000, 0, 0, 0, 0, 0]             (mpc_cbf.py:346-364)
   start  x_k = x_init, u_k = u_prev for all k (set_initial_guess, mpc_cbf.py:368-369)
 
-PARITY UNPINNED for the NLP *assembly* (no do-mpc to run); the component functions it is
-built from (f, g, step, agent_barrier_dt, Q/R/alpha constants) are pinned against the
-reference's own code by tests/test_oracle_pinned.py.
+PARITY: the problem STATEMENT is pinned against the reference's own position_control/mpc_cbf.py --
+tests/golden/gen_mpc_from_reference.py constructs the unmodified MPCCBF through oracle/refshim
+(numeric casadi, probing do_mpc stand-in) and records what it hands to do-mpc at seeded probe points
+(x_next of set_rhs, the cost expression, every CBF constraint value, bounds, rterm weights, horizon,
+tvp goal / dummy-obstacle padding, alphas); tests/test_oracle_pinned.py::test_mpc_statement_matches_reference
+checks euler(), the stage cost, cbf pieces, pad_obs, bounds and constants of this file against them.
+PARITY UNPINNED for what do-mpc itself does with those pieces (lterm summed over k < H plus mterm, rterm
+as a penalty on u_k - u_{k-1}, nl_cons at every stage but the terminal node) and for IPOPT's output:
+neither do-mpc nor casadi can be installed here.
 """
 import math
 

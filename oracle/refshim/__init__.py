@@ -20,6 +20,10 @@ those are installed and there is no network.  install() registers
     hands it to oracle/qp_exact.py.  The QPs are strictly convex, so the
     optimum is unique and solver independent -- what this pins is the
     reference's row assembly, constants, bounds and objective;
+  * `do_mpc`  -> a probing stand-in (fake_do_mpc.py): records what the
+    reference's mpc_cbf.py hands to do-mpc (rhs, cost, CBF constraints, bounds,
+    rterm, horizon, tvp padding) evaluated at numeric probe points; nothing is
+    solved;
   * `matplotlib*` -> inert mocks (robots/kinematic_bicycle2D.py:4-5);
   * `safe_control` -> a namespace package rooted at the reference checkout
     (pyproject.toml:25-27 maps the package to the repo root).
@@ -42,10 +46,11 @@ def install():
     """Register the stub modules and the `safe_control` namespace. Idempotent."""
     if not available():
         raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
-    from . import fake_casadi, fake_cvxpy
+    from . import fake_casadi, fake_cvxpy, fake_do_mpc
 
     sys.modules.setdefault("casadi", fake_casadi)
     sys.modules.setdefault("cvxpy", fake_cvxpy)
+    sys.modules.setdefault("do_mpc", fake_do_mpc)
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.transforms",
                  "matplotlib.patches", "matplotlib.animation"):
         if name not in sys.modules:

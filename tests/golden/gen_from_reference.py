@@ -71,6 +71,8 @@ class Facade:
 
     def f(self): return self.robot.f(self.X)
     def g(self): return self.robot.g(self.X)
+    def f_casadi(self, X): return self.robot.f(X, casadi=True)          # robots/robot.py:395-399
+    def g_casadi(self, X): return self.robot.g(X, casadi=True)
     def agent_barrier(self, obs): return self.robot.agent_barrier(self.X, obs, self.robot_radius)
     def agent_barrier_dt(self, x, u, obs): return self.robot.agent_barrier_dt(x, u, obs, self.robot_radius)
 

@@ -102,3 +102,64 @@ def test_optimal_decay_matches_reference_end_to_end():
             if d["STATUS"][i] == 0:
                 np.testing.assert_allclose(u, d["U"][i], rtol=1e-9, atol=1e-10, err_msg=name)
                 np.testing.assert_allclose(om, d["OMEGA"][i], rtol=1e-9, atol=1e-10, err_msg=name)
+
+
+# ---- MPC-CBF problem statement: oracle/mpc_cbf.py vs what the REFERENCE'S OWN mpc_cbf.py hands to do-mpc ----------
+# (tests/golden/gen_mpc_from_reference.py; probing stand-in for do_mpc, nothing solved).  Pins the Euler rhs, the
+# stage cost (Q, goal padding), every CBF constraint value incl. the model's own step and the alphas, the dummy
+# obstacle padding, input / state bounds, the rterm weights and the horizon.  do-mpc's transcription of these pieces
+# into the NLP (sum over stages + terminal cost, rterm on input increments) stays as documented in SURVEY.md 8a.
+MPC_ORACLE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D")
+
+
+def test_mpc_statement_matches_reference():
+    import torch
+    from oracle.mpc_cbf import OracleMPCCBF
+    data = _load("ref_mpc_statement.npz")
+    seen = 0
+    for tag, d in data.items():
+        spec = _spec_from_tag(tag)
+        if "mpc_horizon" in spec:
+            spec["mpc_horizon"] = int(spec["mpc_horizon"])
+        if spec["model"] not in MPC_ORACLE_MODELS:
+            continue                                   # DI / Quad2D / DPCBF: recorded, MPC not built yet
+        seen += 1
+        M = d["cbf"].shape[1]
+        o = OracleMPCCBF(spec, num_obs=M)
+        assert o.H == int(d["horizon"][0]) and int(d["n_robust"][0]) == 0 and float(d["t_step"][0]) == o.dt
+        assert float(d["lterm_is_mterm"][0]) == 1.0                       # terminal cost == stage cost expression
+        np.testing.assert_array_equal(o.Rw.numpy(), d["R"][0])
+        np.testing.assert_array_equal(o.u_lb, d["lb_u"][0]); np.testing.assert_array_equal(o.u_ub, d["ub_u"][0])
+        if o.has_vbound:                                                    # |x[3]| <= v_max, nothing else bounded
+            v = o.spec["v_max"]
+            np.testing.assert_array_equal(d["ub_x"][0], [np.inf, np.inf, np.inf, v])
+            np.testing.assert_array_equal(d["lb_x"][0], [-np.inf, -np.inf, -np.inf, -v])
+        else:
+            assert np.isinf(d["ub_x"][0]).all() and np.isinf(d["lb_x"][0]).all()
+        assert (d["cons_ub"] == 0).all()
+        al = d["alphas"][0]
+        if "alpha" in o.par:
+            assert o.par["alpha"] == al[0]
+        else:
+            assert (o.par["alpha1"], o.par["alpha2"]) == (al[1], al[2])
+        for i in range(len(d["X"])):
+            x, u = torch.tensor(d["X"][i])[None], torch.tensor(d["U"][i])[None]
+            k = int(d["NOBS"][i])
+            obs = d["OBS"][i][:k] if k else None
+            np.testing.assert_allclose(o.tm.euler(x, u)[0].numpy(), d["x_next"][i], rtol=1e-13, atol=1e-13, err_msg=tag)
+            ob = o.pad_obs(obs)
+            np.testing.assert_array_equal(ob.numpy(), d["tvp_obs"][i])       # dummy rows [1000, 1000, 0, ...]
+            g = np.zeros(o.nx); gl = d["GOAL"][i][: (3 if spec["model"] == "Quad3D" else 2)]; g[: gl.size] = gl
+            np.testing.assert_array_equal(g, d["tvp_goal"][i])               # goal padded with zeros
+            e = d["X"][i] - g
+            np.testing.assert_allclose(float((e * e * o.Q.numpy()).sum()), d["cost"][i], rtol=1e-12, err_msg=tag)
+            # CBF constraints of one stage: w = [x_0, x_1 | u_0] with H = 1 semantics -> call the stage pieces directly
+            tm, p = o.tm, o.par
+            x1 = tm.own_step(x, u); h0, h1 = tm.h(x, ob), tm.h(x1, ob)
+            if "alpha" in p:
+                c = (h1 - h0) + p["alpha"] * h0
+            else:
+                x2 = tm.own_step(x1, u); h2 = tm.h(x2, ob)
+                c = (h2 - 2 * h1 + h0) + (p["alpha1"] + p["alpha2"]) * (h1 - h0) + p["alpha1"] * p["alpha2"] * h0
+            np.testing.assert_allclose(c[0].numpy(), d["cbf"][i], rtol=1e-9, atol=1e-9, err_msg=f"{tag} probe {i}")
+    assert seen == 6
