@@ -890,8 +890,11 @@ struct MpcSolver {
   }
 
   // ------------------------------------------------------------------------------------------
-  SCB_HD void solve(int nobs, const double* x0, const double* goal_in, int ngoal, const double* up, const double* obs,
-                    double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+  // Problem data + cold start: goal padding, obstacle table, z = u_prev, rollout and the CBF values of every
+  // (stage, obstacle) pair at the cold start (-> w[L.C]).  Returns the unscaled objective.  Split from solve() so
+  // the CPU host-sim can compare the kernel's own statement (Euler map, stage cost, CBF rows) with the values the
+  // reference's mpc_cbf.py hands to do-mpc (tests/golden/ref_mpc_statement.npz).
+  SCB_HD double init(int nobs, const double* x0, const double* goal_in, int ngoal, const double* up, const double* obs) {
 #pragma unroll
     for (int i = 0; i < NX; ++i) goal[i] = (i < ngoal) ? ld(goal_in + i) : 0.0;      // goal padded with zeros (mpc_cbf.py:267)
 #pragma unroll
@@ -917,6 +920,12 @@ struct MpcSolver {
     Jcur = G::bcast(Jcur, 0);
     sync();
     points_and_cbf(w + L.Z, w + L.X, w + L.C);
+    return Jcur;
+  }
+
+  SCB_HD void solve(int nobs, const double* x0, const double* goal_in, int ngoal, const double* up, const double* obs,
+                    double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+    double Jcur = init(nobs, x0, goal_in, ngoal, up, obs);
 
     // objective scaling as IPOPT's default gradient-based scaling: max |dJ/dz| at the start <= 100
     {

@@ -124,6 +124,37 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
   }
   return 0;
 }
+
+// The kernel's own problem statement at a probe point: horizon 1, cold start u_0 = u (passed as u_prev), so
+// init() leaves x_1 = Euler(x, u) in the rollout, the stage cost of x_0 (+ terminal cost of x_1) in J and the CBF
+// value of every obstacle slot in w[L.C].  Compared with what the reference's mpc_cbf.py hands to do-mpc.
+int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x, const double* u, const double* goal,
+                          const double* obs, double* x_next, double* stage_cost, double* cbf) {
+  switch (p->model) {
+#define STCASE(MODEL)                                                                                           \
+  case MODEL: {                                                                                                 \
+    using Mod = MpcModel<MODEL>;                                                                                \
+    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX>(1, M);                 \
+    std::vector<double> ws(L.total, 0.0);                                                                       \
+    MpcSolver<MODEL, 1> s(*p, L, ws.data());                                                                    \
+    const double J = s.init(nobs, x, goal, Mod::NGOAL, u, obs);                                                 \
+    double term = 0.0;                                                                                          \
+    for (int i = 0; i < Mod::NX; ++i) {                                                                         \
+      x_next[i] = ws[L.X + Mod::NX + i];                                                                        \
+      const double g = i < Mod::NGOAL ? goal[i] : 0.0;                                                          \
+      term += p->Q[i] * (x_next[i] - g) * (x_next[i] - g);                                                      \
+    }                                                                                                           \
+    *stage_cost = J - term;                                                                                     \
+    for (int j = 0; j < M; ++j) cbf[j] = ws[L.C + j];                                                           \
+  } break;
+    STCASE(SCB_SINGLE_INTEGRATOR_2D)
+    STCASE(SCB_DYNAMIC_UNICYCLE_2D)
+    STCASE(SCB_KINEMATIC_BICYCLE_2D)
+    STCASE(SCB_QUAD_3D)
+    default: return SCB_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
 #endif
 
 

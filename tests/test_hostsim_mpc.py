@@ -49,3 +49,36 @@ def test_mpc_no_obstacles_is_box_clipped_tracking():
         u = out["pred_u"][0, k]
         x = x + 0.05 * np.array([x[3] * np.cos(x[2]), x[3] * np.sin(x[2]), u[1], u[0]])
         np.testing.assert_allclose(out["pred_x"][0, k + 1], x, atol=1e-12)
+
+
+def test_kernel_statement_matches_reference():
+    """The MPC kernel's own problem statement (Euler map, stage cost, CBF constraint of every obstacle slot incl.
+    the model's own step, dummy-obstacle padding) vs what the REFERENCE'S mpc_cbf.py hands to do-mpc at seeded probe
+    points (tests/golden/ref_mpc_statement.npz, generated through oracle/refshim's probing do_mpc stand-in)."""
+    import ctypes as C
+    from hostsim_util import ptr
+    from test_oracle_pinned import _load, _spec_from_tag
+    lib = hostsim()
+    seen = 0
+    for tag, d in _load("ref_mpc_statement.npz").items():
+        spec = _spec_from_tag(tag)
+        if spec["model"] not in ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D"):
+            continue
+        spec.pop("mpc_horizon", None)
+        p, _ = resolve_params(spec, "mpc_cbf", lib=lib)
+        M = d["cbf"].shape[1]
+        for i in range(len(d["X"])):
+            k = int(d["NOBS"][i])
+            obs = np.nan_to_num(d["OBS"][i][:M].copy(), nan=0.0)
+            if (obs[:k, 6] != 0).any():
+                continue                                  # superellipsoid rows: not built in the MPC kernel yet
+            x, u, goal = np.ascontiguousarray(d["X"][i]), np.ascontiguousarray(d["U"][i]), np.ascontiguousarray(d["GOAL"][i])
+            xn = np.zeros(p.nx); cost = C.c_double(); cbf = np.zeros(M)
+            rc = lib.hostsim_mpc_statement(C.byref(p), M, k, ptr(x), ptr(u), ptr(goal), ptr(np.ascontiguousarray(obs)),
+                                           ptr(xn), C.byref(cost), ptr(cbf))
+            assert rc == 0
+            np.testing.assert_allclose(xn, d["x_next"][i], rtol=1e-13, atol=1e-13, err_msg=tag)
+            np.testing.assert_allclose(cost.value, d["cost"][i], rtol=1e-12, err_msg=tag)
+            np.testing.assert_allclose(cbf, d["cbf"][i], rtol=1e-9, atol=1e-8, err_msg=f"{tag} probe {i}")
+            seen += 1
+    assert seen > 80
