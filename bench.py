@@ -407,6 +407,13 @@ def run_loop(args, w, rank, world, local_rank):
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record(); tc.run_steps(args.steps); g1.record(); torch.cuda.synchronize()
     eager_ms = g0.elapsed_time(g1)
+    # the same K steps through n x scb_control_step (3-4 launches per step), for comparison with the fused launch
+    os.environ["SCB_TRACK_FUSED"] = "0"
+    restore(); barrier()
+    g0.record(); tc.run_steps(args.steps); g1.record(); torch.cuda.synchronize()
+    per_step = {"value": world * N * args.steps / (g0.elapsed_time(g1) * 1e-3), "unit": "control-steps/s",
+                "how": "SCB_TRACK_FUSED=0: pre / solve / post kernels per step, eager launches (this rank)"}
+    del os.environ["SCB_TRACK_FUSED"]
     # end to end: initial state from pinned host memory -> device, run K steps, final state + return codes back
     host = {k: snap[k].cpu().pin_memory() for k in keys}
     out_h = {k: torch.empty_like(host[k]).pin_memory() for k in ("X", "ret", "nsteps")}
@@ -436,7 +443,7 @@ def run_loop(args, w, rank, world, local_rank):
             "unit": "control-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": k_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step_per_gpu": N, "obstacles": M, "scene_obstacles": M,
-                       "waypoints_per_agent": 3, "launch": f"K steps ({launches} launches) captured in one CUDA graph; every replay restarts from the same tracker state",
+                       "waypoints_per_agent": 3, "launch": f"K steps = {launches} launch(es) (QP controllers: one fused kernel keeps every agent in a warp for all K steps) captured in a CUDA graph; every replay restarts from the same tracker state",
                        "l2_policy": "closed loop: the state produced by step k is the input of step k+1 (nothing is re-read from a warm copy); agents_active_frac = share of agent-steps not yet frozen by a -1/-2 return",
                        "agents_active_frac": active_frac, "final_ret": {"0": int((rets == 0).sum()), "-1": int((rets == -1).sum()), "-2": int((rets == -2).sum())},
                        "parallelism": f"agents sharded, {world} rank(s), no data-path collective"},
@@ -445,11 +452,12 @@ def run_loop(args, w, rank, world, local_rank):
                     "how": "whole run_all_steps: tracker state pinned host -> device, K control steps on the device, final X / ret / nsteps -> pinned host, sync"},
             "gpu_launches": launches,
             "eager": {"value": world * N * args.steps / (eager_ms * 1e-3), "unit": "control-steps/s", "how": "scb_run_all_steps without the CUDA graph"},
+            "per_step_path": per_step,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": B * N / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": B * N / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_agent": B, "agents_per_launch": N,
-                         "note": "three dependent launches per control step over ~3 MB of state: latency-bound by construction (step k+1 needs step k)"},
+                         "note": "closed loop: step k+1 needs step k, so one agent-warp runs its K steps back to back (latency-bound by construction); per-step traffic stays in L1/L2"},
         }
         if not args.no_cpu:
             n_a, n_s = 24, 50

@@ -246,8 +246,13 @@ typedef struct scb_track {
 size_t scb_track_sizeof(void);
 /* One control_step() for every agent that is not done: 3 launches (+1 when dynamic_obs) on `stream`. */
 int scb_control_step(const scb_params* p, const scb_track* t, void* stream);
-/* n_steps control steps back to back (run_all_steps' loop body; per-agent break = the done latch). */
+/* n_steps control steps back to back (run_all_steps' loop body; per-agent break = the done latch).  For the QP
+ * controllers with M <= 60 and K <= 512 this is ONE kernel launch (a warp keeps its agent for all n_steps steps,
+ * each CTA steps its own shared-memory copy of a moving scene); otherwise n_steps x scb_control_step.  Both give
+ * bit-identical results.  Environment SCB_TRACK_FUSED=0 forces the per-step path. */
 int scb_run_all_steps(const scb_params* p, const scb_track* t, int n_steps, void* stream);
+/* number of kernel launches scb_run_all_steps(p, t, n_steps) issues (for benchmarks' gpu_launches) */
+long scb_run_all_steps_launches(const scb_params* p, const scb_track* t, int n_steps);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,7 @@ PROTOTYPES = {
     "scb_track_sizeof": (C.c_size_t, []),
     "scb_control_step": (C.c_int, [_P, _T, _vp]),
     "scb_run_all_steps": (C.c_int, [_P, _T, C.c_int, _vp]),
+    "scb_run_all_steps_launches": (C.c_long, [_P, _T, C.c_int]),
 }
 
 

@@ -265,10 +265,60 @@ int scb_control_step(const scb_params* p, const scb_track* t, void* stream) {
   return control_step_impl(p, t, (cudaStream_t)stream);
 }
 
+static bool fused_applicable(const scb_params* p, const scb_track* t) {
+  const char* e = getenv("SCB_TRACK_FUSED");                 // tuning / A-B switch, read per call: "0" disables
+  if (e && e[0] == '0') return false;
+  if (t->K > kFusedMaxScene) return false;
+  if (t->controller == SCB_CTRL_CBF_QP)
+    return t->M + 4 <= 64 && (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_DYNAMIC_UNICYCLE_2D ||
+                              p->model == SCB_KINEMATIC_BICYCLE_2D || p->model == SCB_KINEMATIC_BICYCLE_2D_C3BF ||
+                              p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF);
+  if (t->controller == SCB_CTRL_OPTIMAL_DECAY)
+    return t->M <= 64 && (p->model == SCB_DYNAMIC_UNICYCLE_2D || p->model == SCB_KINEMATIC_BICYCLE_2D ||
+                          p->model == SCB_KINEMATIC_BICYCLE_2D_C3BF);
+  return false;
+}
+
+// fused single-launch path for the QP controllers (scb_track_kernels.cuh); false -> not applicable, use the 3-launch loop
+static bool run_fused(const scb_params* p, const scb_track* t, int n_steps, cudaStream_t s) {
+  if (!fused_applicable(p, t)) return false;
+  if (t->controller == SCB_CTRL_CBF_QP) {
+    switch (p->model) {
+      case SCB_SINGLE_INTEGRATOR_2D: return launch_fused<SCB_SINGLE_INTEGRATOR_2D, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
+      case SCB_DYNAMIC_UNICYCLE_2D: return launch_fused<SCB_DYNAMIC_UNICYCLE_2D, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
+      case SCB_KINEMATIC_BICYCLE_2D: return launch_fused<SCB_KINEMATIC_BICYCLE_2D, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
+      case SCB_KINEMATIC_BICYCLE_2D_C3BF: return launch_fused<SCB_KINEMATIC_BICYCLE_2D_C3BF, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
+      case SCB_KINEMATIC_BICYCLE_2D_DPCBF: return launch_fused<SCB_KINEMATIC_BICYCLE_2D_DPCBF, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
+      default: return false;
+    }
+  }
+  if (t->controller == SCB_CTRL_OPTIMAL_DECAY) {
+    switch (p->model) {
+      case SCB_DYNAMIC_UNICYCLE_2D: return launch_fused<SCB_DYNAMIC_UNICYCLE_2D, SCB_CTRL_OPTIMAL_DECAY, 2>(*p, *t, n_steps, s);
+      case SCB_KINEMATIC_BICYCLE_2D: return launch_fused<SCB_KINEMATIC_BICYCLE_2D, SCB_CTRL_OPTIMAL_DECAY, 2>(*p, *t, n_steps, s);
+      case SCB_KINEMATIC_BICYCLE_2D_C3BF: return launch_fused<SCB_KINEMATIC_BICYCLE_2D_C3BF, SCB_CTRL_OPTIMAL_DECAY, 1>(*p, *t, n_steps, s);
+      default: return false;
+    }
+  }
+  return false;
+}
+
+long scb_run_all_steps_launches(const scb_params* p, const scb_track* t, int n_steps) {
+  if (track_check(p, t) != SCB_OK || t->N == 0 || n_steps <= 0) return 0;
+  const long dyn = (t->dynamic_obs && t->K > 0) ? 1 : 0;
+  if (fused_applicable(p, t)) return 1 + dyn;
+  return (long)n_steps * (3 + dyn);
+}
+
 int scb_run_all_steps(const scb_params* p, const scb_track* t, int n_steps, void* stream) {
   int rc = track_check(p, t);
   if (rc != SCB_OK || t->N == 0) return rc;
   if (n_steps < 0) return SCB_ERR_BAD_ARG;
+  if (n_steps == 0) return SCB_OK;
+  if (run_fused(p, t, n_steps, (cudaStream_t)stream)) {
+    CK(cudaGetLastError());
+    return SCB_OK;
+  }
   for (int k = 0; k < n_steps; ++k) {
     rc = control_step_impl(p, t, (cudaStream_t)stream);
     if (rc != SCB_OK) return rc;

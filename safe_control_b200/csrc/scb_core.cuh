@@ -131,4 +131,14 @@ SCB_HD double ld(const double* p) {
 #endif
 }
 
+// NC = true: read-only (non-coherent) load of a kernel INPUT; NC = false: plain load, for buffers the same kernel
+// wrote earlier (the fused closed-loop kernel solves on rows / inputs it produced itself a few lines above).
+template <bool NC>
+SCB_HD double ldx(const double* p) {
+#if defined(__CUDA_ARCH__)
+  if (NC) return __ldg(p);
+#endif
+  return *p;
+}
+
 }  // namespace scb

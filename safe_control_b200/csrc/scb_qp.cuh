@@ -15,7 +15,7 @@ namespace scb {
 // Row r of the CBF-QP, r in [0, M + 2 NU):
 //   r <  M      : CBF row of obstacle slot r (vacuous 0 >= 0 when r >= nobs, cbf_qp.py:110-111)
 //   r = M + 2i  : u_i <= ub_i      r = M + 2i + 1 : u_i >= lb_i          (cbf_qp.py:54-73)
-template <int MODEL>
+template <int MODEL, bool NC = true>
 SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, int M, int nobs, int r,
                       double* a, double& b) {
   constexpr int NU = ModelCT<MODEL>::NU;
@@ -26,7 +26,7 @@ SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, 
     if (r < nobs) {
       double o[7];
 #pragma unroll
-      for (int q = 0; q < 7; ++q) o[q] = ld(obs + (size_t)r * 7 + q);
+      for (int q = 0; q < 7; ++q) o[q] = ldx<NC>(obs + (size_t)r * 7 + q);
       RowOut ro;
       ModelCT<MODEL>::row(p, g, o, ro);
 #pragma unroll
@@ -45,7 +45,7 @@ SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, 
   }
 }
 
-template <int MODEL, int LANES, int RPL>
+template <int MODEL, int LANES, int RPL, bool NC = true>
 SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
                         const double* obs, double* U, int32_t* status, uint64_t* active, int words) {
   using Mod = ModelCT<MODEL>;
@@ -55,7 +55,7 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
 
   double ur[NU];
 #pragma unroll
-  for (int i = 0; i < NU; ++i) ur[i] = ld(uref + i);
+  for (int i = 0; i < NU; ++i) ur[i] = ldx<NC>(uref + i);
 
   if (nobs < 0) {                    // obs_list is None -> u_ref unclipped (cbf_qp.py:113-118)
     if (lane == 0) {
@@ -70,7 +70,7 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
 
   double xs[Mod::NX];
 #pragma unroll
-  for (int i = 0; i < Mod::NX; ++i) xs[i] = ld(x + i);
+  for (int i = 0; i < Mod::NX; ++i) xs[i] = ldx<NC>(x + i);
   AgentCT g;
   Mod::prep(p, xs, g);
 
@@ -81,7 +81,7 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     double a[NU], b;
-    cbfqp_row<MODEL>(p, g, obs, M, nobs, j * LANES + lane, a, b);
+    cbfqp_row<MODEL, NC>(p, g, obs, M, nobs, j * LANES + lane, a, b);
     const double n2 = a[0] * a[0] + a[1] * a[1];
     const double inv = (n2 > 0.0) ? rsqrt_pos(n2) : 1.0;
     r0[j] = a[0] * inv; r1[j] = a[1] * inv; rb[j] = b * inv;
@@ -114,7 +114,7 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
 // (optimal_decay_cbf_qp.py:61) built from the nearest valid obstacle of the agent's list
 // (tracking.py:585-586), 4 box rows.  NW = number of omega variables (1: C3BF, 2: DU/KB).
 // Active bits: bit 0 = CBF row, bit 1+2i = u_i upper, bit 2+2i = u_i lower.
-template <int MODEL, int NW, int LANES, int RPL>
+template <int MODEL, int NW, int LANES, int RPL, bool NC = true>
 SCB_HD void odcbf_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
                         const double* obs, double* U, double* omega, int32_t* sel, int32_t* status,
                         uint64_t* active) {
@@ -126,7 +126,7 @@ SCB_HD void odcbf_agent(const scb_params& p, int M, int nobs, const double* x, c
 
   double xs[Mod::NX];
 #pragma unroll
-  for (int i = 0; i < Mod::NX; ++i) xs[i] = ld(x + i);
+  for (int i = 0; i < Mod::NX; ++i) xs[i] = ldx<NC>(x + i);
   AgentCT g;
   Mod::prep(p, xs, g);
 
@@ -137,7 +137,7 @@ SCB_HD void odcbf_agent(const scb_params& p, int M, int nobs, const double* x, c
   for (int j = 0; j < RPL; ++j) {
     const int r = j * LANES + lane;
     if (r < nobs) {
-      const double dx = ld(obs + (size_t)r * 7) - g.px, dy = ld(obs + (size_t)r * 7 + 1) - g.py;
+      const double dx = ldx<NC>(obs + (size_t)r * 7) - g.px, dy = ldx<NC>(obs + (size_t)r * 7 + 1) - g.py;
       const double d2 = dx * dx + dy * dy;
       if (d2 < bestd) { bestd = d2; bi = r; }
     }
@@ -156,7 +156,7 @@ SCB_HD void odcbf_agent(const scb_params& p, int M, int nobs, const double* x, c
   if (has) {
     double o[7];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) o[q] = ld(obs + (size_t)bi * 7 + q);
+    for (int q = 0; q < 7; ++q) o[q] = ldx<NC>(obs + (size_t)bi * 7 + q);
     if (MODEL == SCB_KINEMATIC_BICYCLE_2D_C3BF) {                       // optimal_decay_cbf_qp.py:139-143
       double h, dh[4];
       ModelCT<SCB_KINEMATIC_BICYCLE_2D_C3BF>::barrier(p, g, o, h, dh);
@@ -194,7 +194,7 @@ SCB_HD void odcbf_agent(const scb_params& p, int M, int nobs, const double* x, c
 
   double hd[NV], z0[NV];
 #pragma unroll
-  for (int i = 0; i < NU; ++i) { hd[i] = 2.0; z0[i] = ld(uref + i); }
+  for (int i = 0; i < NU; ++i) { hd[i] = 2.0; z0[i] = ldx<NC>(uref + i); }
   hd[NU] = 2.0 * p.p_sb1; z0[NU] = p.omega1_0;
   if (NW == 2) { hd[NV - 1] = 2.0 * p.p_sb2; z0[NV - 1] = p.omega2_0; }
 

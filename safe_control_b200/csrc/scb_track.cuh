@@ -346,8 +346,9 @@ SCB_HD bool update_goal(const scb_track& t, const double* x, double yaw, const d
 
 // ------------------------------------------------------------------------------------------
 // Everything before the solve.  All lanes of the group call this; lane 0 stores the scalars.
+// `scene` = the obstacle array to select from (t.SCENE, or the fused kernel's shared-memory copy of it).
 template <int MODEL, int LANES>
-SCB_HD void track_pre_agent(const scb_params& p, const scb_track& t, long a, double* keys) {
+SCB_HD void track_pre_agent(const scb_params& p, const scb_track& t, long a, double* keys, const double* scene) {
   using ML = ModelLoop<MODEL>;
   using G = Grp<LANES>;
   constexpr int NX = ML::NX, NU = ML::NU;
@@ -385,7 +386,7 @@ SCB_HD void track_pre_agent(const scb_params& p, const scb_track& t, long a, dou
   }
 
   // obstacle selection (tracking.py:583)
-  const int no = select_agent<LANES>(t.K, t.M, t.SCENE, x[0], x[1], yaw, ML::half_angle(), keys,
+  const int no = select_agent<LANES>(t.K, t.M, scene, x[0], x[1], yaw, ML::half_angle(), keys,
                                      t.OBS + (size_t)a * t.M * 7, nullptr);
 
   // nominal input (tracking.py:589-604)
@@ -413,7 +414,7 @@ SCB_HD void track_pre_agent(const scb_params& p, const scb_track& t, long a, dou
 
 // Everything after the solve.
 template <int MODEL, int LANES>
-SCB_HD void track_post_agent(const scb_params& p, const scb_track& t, long a) {
+SCB_HD void track_post_agent(const scb_params& p, const scb_track& t, long a, const double* scene) {
   using ML = ModelLoop<MODEL>;
   using G = Grp<LANES>;
   constexpr int NX = ML::NX, NU = ML::NU;
@@ -442,14 +443,14 @@ SCB_HD void track_post_agent(const scb_params& p, const scb_track& t, long a) {
   }
 
   int ret;
-  bool collide = collides<LANES>(t.K, t.SCENE, x[0], x[1], p.radius);
+  bool collide = collides<LANES>(t.K, scene, x[0], x[1], p.radius);
   if (!ok || collide) {
     ret = -2;                                                 // :627-634 (no step)
   } else {
     ML::step(p, x, u);                                        // :637
     if (ML::HAS_ATT) { if (!(u_att != u_att)) yaw = wrap_floor(yaw + u_att * p.dt); }      // step_rotate, robots/robot.py:446-448
     else yaw = ML::yaw_of(x, yaw);
-    collide = collides<LANES>(t.K, t.SCENE, x[0], x[1], p.radius);
+    collide = collides<LANES>(t.K, scene, x[0], x[1], p.radius);
     if (collide) ret = -2;                                    // :640-646
     else ret = (!has_goal && sm != SCB_SM_STOP) ? -1 : 0;     // :666-668
   }

@@ -254,12 +254,12 @@ class BatchedTrackingController:
     def control_step(self):
         """One control_step() for every agent still running -> ret [N] int32 (device tensor)."""
         self._check(self._lib.scb_control_step(self.params, self._t, self._stream()), "scb_control_step")
-        self.launches += 3 + int(self.host.dynamic_obs)
+        self.launches += 3 + int(self.host.dynamic_obs and self.host.scene.shape[0] > 0)
         return self._bufs["ret"]
 
     def run_steps(self, n_steps):
         self._check(self._lib.scb_run_all_steps(self.params, self._t, int(n_steps), self._stream()), "scb_run_all_steps")
-        self.launches += (3 + int(self.host.dynamic_obs)) * int(n_steps)
+        self.launches += int(self._lib.scb_run_all_steps_launches(self.params, self._t, int(n_steps)))
 
     def run_all_steps(self, tf=30, chunk=64):
         """tracking.py:711-747: int(tf/dt) steps, each agent stops at its first -1 / -2.

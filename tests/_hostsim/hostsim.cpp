@@ -191,7 +191,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
   std::vector<double> keys(t->K > 0 ? t->K : 1);
   for (long a = 0; a < t->N; ++a) {
     switch (p->model) {
-#define PRECASE(MODEL) case MODEL: track_pre_agent<MODEL, 1>(*p, *t, a, keys.data()); break;
+#define PRECASE(MODEL) case MODEL: track_pre_agent<MODEL, 1>(*p, *t, a, keys.data(), t->SCENE); break;
       PRECASE(SCB_SINGLE_INTEGRATOR_2D)
       PRECASE(SCB_DYNAMIC_UNICYCLE_2D)
       PRECASE(SCB_KINEMATIC_BICYCLE_2D)
@@ -236,7 +236,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
   if (rc != 0) return rc;
   for (long a = 0; a < t->N; ++a) {
     switch (p->model) {
-#define POSTCASE(MODEL) case MODEL: track_post_agent<MODEL, 1>(*p, *t, a); break;
+#define POSTCASE(MODEL) case MODEL: track_post_agent<MODEL, 1>(*p, *t, a, t->SCENE); break;
       POSTCASE(SCB_SINGLE_INTEGRATOR_2D)
       POSTCASE(SCB_DYNAMIC_UNICYCLE_2D)
       POSTCASE(SCB_KINEMATIC_BICYCLE_2D)
