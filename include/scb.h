@@ -166,6 +166,20 @@ int scb_mpccbf_solve(const scb_params* p, int N, int M, int H,
                      const double* OBS, long obs_stride_agent, const int32_t* nobs,
                      double* U, int32_t* status, double* pred_x, double* pred_u,
                      int32_t* iters, double* kkt, void* stream);
+/* Same call with a caller-owned device scratch of scb_mpccbf_workspace_bytes(N) bytes (contents undefined before
+ * and after).  With it the kernel starts the agents in order of their cold-start CBF margin (most violated first)
+ * instead of index order: per-agent results are identical, the batch finishes sooner because the long-tailed
+ * iteration counts no longer leave a late-started straggler running alone.  workspace == NULL or too small: index
+ * order, exactly scb_mpccbf_solve. */
+size_t scb_mpccbf_workspace_bytes(int N);
+/* kernel launches one scb_mpccbf_solve[_ws] call issues (1, or 3 with a schedule: key, counting sort, solve) */
+int scb_mpccbf_launch_count(const scb_params* p, int N, int M, int H, int with_workspace);
+int scb_mpccbf_solve_ws(const scb_params* p, int N, int M, int H,
+                        const double* X, const double* Uref, const double* goal, const double* u_prev,
+                        const int32_t* track,
+                        const double* OBS, long obs_stride_agent, const int32_t* nobs,
+                        double* U, int32_t* status, double* pred_x, double* pred_u,
+                        int32_t* iters, double* kkt, void* workspace, size_t workspace_bytes, void* stream);
 int scb_mpccbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M, int H,
                           const double* X, const double* Uref, const double* goal, const double* u_prev,
                           const int32_t* track,
@@ -241,6 +255,8 @@ typedef struct scb_track {
   uint64_t* active;              /* [N, scb_active_words(M, nu)] or NULL */
   int32_t* track_flag;           /* [N]       MPC only: scratch (state_machine == 'track') */
   int32_t* mpc_iters;            /* [N]       MPC only, may be NULL */
+  void*    mpc_ws;               /* MPC only, may be NULL: scheduling scratch, scb_mpccbf_workspace_bytes(N) bytes */
+  uint64_t mpc_ws_bytes;
 } scb_track;
 
 size_t scb_track_sizeof(void);

@@ -57,7 +57,7 @@ class ScbTrack(C.Structure):
         ("has_goal", _vp), ("u_att", _vp), ("u_prev", _vp), ("ret", _vp), ("done", _vp), ("nsteps", _vp),
         ("SCENE", _vp),
         ("Uref", _vp), ("OBS", _vp), ("nobs", _vp), ("U", _vp), ("status", _vp), ("active", _vp),
-        ("track_flag", _vp), ("mpc_iters", _vp),
+        ("track_flag", _vp), ("mpc_iters", _vp), ("mpc_ws", _vp), ("mpc_ws_bytes", C.c_uint64),
     ]
 
 
@@ -84,6 +84,10 @@ PROTOTYPES = {
     "scb_odcbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_mpccbf_solve": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_mpccbf_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "scb_mpccbf_launch_count": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "scb_mpccbf_solve_ws": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "scb_mpccbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_select_obstacles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),

@@ -10,7 +10,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscb.so")
+# SCB_LIB selects another build of the same library (tuning variants, profiling builds); never a different backend
+LIB_PATH = os.environ.get("SCB_LIB") or os.path.join(_HERE, "libscb.so")
 _lib = None
 
 

@@ -141,6 +141,14 @@ class BatchedMPCCBF(_Base):
         super().__init__(robot_spec, num_obs, dt)
         self.horizon = int(horizon if horizon is not None else self.robot_spec.get("mpc_horizon", 10))
         self.ngoal = 3 if self.model == "Quad3D" else 2
+        self._ws = None                 # scheduling scratch (scb_mpccbf_workspace_bytes), grown on demand
+        self.schedule = True            # False: index order (scb_mpccbf_solve)
+
+    def _workspace(self, N, dev):
+        need = int(lib().scb_mpccbf_workspace_bytes(N))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+        return self._ws, need
 
     def solve(self, X, goal, u_prev, OBS, nobs=None, U_ref=None, track=None, want_pred=False):
         """-> dict(U, status, iters, kkt[, pred_x, pred_u])"""
@@ -160,10 +168,12 @@ class BatchedMPCCBF(_Base):
         kkt = torch.empty((N,), dtype=F64, device=dev)
         px = torch.empty((N, H + 1, self.nx), dtype=F64, device=dev) if want_pred else None
         pu = torch.empty((N, H, self.nu), dtype=F64, device=dev) if want_pred else None
-        check(lib().scb_mpccbf_solve(self.params, N, self.num_obs, H, _ptr(X), _ptr(U_ref), _ptr(goal), _ptr(u_prev),
-                                     _ptr(track), _ptr(OBS), stride, _ptr(nobs), _ptr(U), _ptr(status), _ptr(px),
-                                     _ptr(pu), _ptr(iters), _ptr(kkt), _stream()), "scb_mpccbf_solve")
-        self.launches += 1
+        ws, ws_bytes = self._workspace(N, dev) if self.schedule else (None, 0)
+        check(lib().scb_mpccbf_solve_ws(self.params, N, self.num_obs, H, _ptr(X), _ptr(U_ref), _ptr(goal), _ptr(u_prev),
+                                        _ptr(track), _ptr(OBS), stride, _ptr(nobs), _ptr(U), _ptr(status), _ptr(px),
+                                        _ptr(pu), _ptr(iters), _ptr(kkt), _ptr(ws), ws_bytes, _stream()),
+              "scb_mpccbf_solve_ws")
+        self.launches += int(lib().scb_mpccbf_launch_count(self.params, N, self.num_obs, H, int(self.schedule)))
         out = dict(U=U, status=status, iters=iters, kkt=kkt)
         if want_pred:
             out.update(pred_x=px, pred_u=pu)

@@ -8,7 +8,18 @@
 #include <new>
 
 #include "scb_kernels.cuh"
+#if defined(SCB_SINGLE_TU) || defined(SCB_MPC_PROFILE)
+// one translation unit (debug / profiling builds): the MPC kernels are instantiated here instead of in scb_mpc_inst.cu
+#include "scb_mpc_impl.cuh"
+namespace scb {
+SCB_MPC_INSTANTIATE(SCB_SINGLE_INTEGRATOR_2D)
+SCB_MPC_INSTANTIATE(SCB_DYNAMIC_UNICYCLE_2D)
+SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D)
+SCB_MPC_INSTANTIATE(SCB_QUAD_3D)
+}
+#else
 #include "scb_mpc_kernels.cuh"
+#endif
 #include "scb_track_kernels.cuh"
 
 using namespace scb;
@@ -170,16 +181,37 @@ int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const do
 }
 
 // ------------------------------------------------------------------------------ MPC-CBF
+size_t scb_mpccbf_workspace_bytes(int N) { return mpc_workspace_bytes(N); }
+
+int scb_mpccbf_launch_count(const scb_params* p, int N, int M, int H, int with_workspace) {
+  if (!p || N < 0 || M < 0 || H < 1) return SCB_ERR_BAD_ARG;
+  if (N == 0) return 0;
+  int n = 0;
+  static int dummy;
+  int rc = mpc_launch(*p, N, M, H, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, nullptr, with_workspace ? (void*)&dummy : nullptr,
+                      with_workspace ? mpc_workspace_bytes(N) : 0, nullptr, sm_count_cached(), &n);
+  return rc == SCB_OK ? n : rc;
+}
+
 int scb_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, const double* Uref,
                      const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
                      const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
                      int32_t* iters, double* kkt, void* stream) {
+  return scb_mpccbf_solve_ws(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u,
+                             iters, kkt, nullptr, 0, stream);
+}
+
+int scb_mpccbf_solve_ws(const scb_params* p, int N, int M, int H, const double* X, const double* Uref,
+                        const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
+                        const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
+                        int32_t* iters, double* kkt, void* workspace, size_t workspace_bytes, void* stream) {
   if (!p || N < 0 || M < 0 || H < 1) return SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !goal || !u_prev || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
   if (track && !Uref) return SCB_ERR_BAD_ARG;
   int rc = mpc_launch(*p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u, iters,
-                      kkt, (cudaStream_t)stream, sm_count_cached());
+                      kkt, workspace, workspace_bytes, (cudaStream_t)stream, sm_count_cached());
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
   return SCB_OK;
@@ -246,8 +278,9 @@ static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream
     rc = scb_odcbf_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, nullptr, nullptr, t->status,
                          t->active, s);
   else
-    rc = scb_mpccbf_solve(p, t->N, t->M, t->H, t->X, t->Uref, t->goal, t->u_prev, t->track_flag, t->OBS,
-                          stride, t->nobs, t->U, t->status, nullptr, nullptr, t->mpc_iters, nullptr, s);
+    rc = scb_mpccbf_solve_ws(p, t->N, t->M, t->H, t->X, t->Uref, t->goal, t->u_prev, t->track_flag, t->OBS,
+                             stride, t->nobs, t->U, t->status, nullptr, nullptr, t->mpc_iters, nullptr, t->mpc_ws,
+                             (size_t)t->mpc_ws_bytes, s);
   if (rc != SCB_OK) return rc;
 #define POST(MODEL) case MODEL: launch_post<MODEL>(*p, *t, s, smc); break;
   switch (p->model) {
@@ -307,7 +340,12 @@ long scb_run_all_steps_launches(const scb_params* p, const scb_track* t, int n_s
   if (track_check(p, t) != SCB_OK || t->N == 0 || n_steps <= 0) return 0;
   const long dyn = (t->dynamic_obs && t->K > 0) ? 1 : 0;
   if (fused_applicable(p, t)) return 1 + dyn;
-  return (long)n_steps * (3 + dyn);
+  long solve = 1;
+  if (t->controller == SCB_CTRL_MPC_CBF) {
+    const int n = scb_mpccbf_launch_count(p, t->N, t->M, t->H, t->mpc_ws && t->mpc_ws_bytes >= mpc_workspace_bytes(t->N));
+    if (n > 0) solve = n;
+  }
+  return (long)n_steps * (2 + solve + dyn);
 }
 
 int scb_run_all_steps(const scb_params* p, const scb_track* t, int n_steps, void* stream) {
@@ -545,7 +583,7 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
   const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
   size_t need = padded((size_t)N * nx * 8) + padded((size_t)N * nu * 8) * 3 + padded((size_t)N * ng * 8) +
                 padded(nobs_el * 8) + padded((size_t)N * 4) * 4 + padded((size_t)N * 8) +
-                padded((size_t)N * (H + 1) * nx * 8) + padded((size_t)N * H * nu * 8);
+                padded((size_t)N * (H + 1) * nx * 8) + padded((size_t)N * H * nu * 8) + padded(mpc_workspace_bytes(N));
   int rc = ctx_reserve(c, need);
   if (rc != SCB_OK) return rc;
   Carver cv{c->dbuf, 0};
@@ -562,6 +600,7 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
   double* dK = cv.take<double>(N);
   double* dPx = cv.take<double>((size_t)N * (H + 1) * nx);
   double* dPu = cv.take<double>((size_t)N * H * nu);
+  char* dWs = cv.take<char>(mpc_workspace_bytes(N));
   H2D(dX, X, (size_t)N * nx, double);
   if (Uref) H2D(dUr, Uref, (size_t)N * nu, double);
   H2D(dUp, u_prev, (size_t)N * nu, double);
@@ -569,11 +608,11 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
   if (nobs_el) H2D(dO, OBS, nobs_el, double);
   if (nobs) H2D(dN, nobs, N, int32_t);
   if (track) H2D(dT, track, N, int32_t);
-  rc = scb_mpccbf_solve(p, N, M, H, dX, Uref ? dUr : nullptr, dG, dUp, track ? dT : nullptr, dO, stride,
-                        nobs ? dN : nullptr, dU, dS, pred_x ? dPx : nullptr, pred_u ? dPu : nullptr,
-                        iters ? dI : nullptr, kkt ? dK : nullptr, c->stream);
+  rc = scb_mpccbf_solve_ws(p, N, M, H, dX, Uref ? dUr : nullptr, dG, dUp, track ? dT : nullptr, dO, stride,
+                           nobs ? dN : nullptr, dU, dS, pred_x ? dPx : nullptr, pred_u ? dPu : nullptr,
+                           iters ? dI : nullptr, kkt ? dK : nullptr, dWs, mpc_workspace_bytes(N), c->stream);
   if (rc != SCB_OK) return rc;
-  c->launches += 1;
+  c->launches += scb_mpccbf_launch_count(p, N, M, H, 1);
   D2H(U, dU, (size_t)N * nu, double);
   D2H(status, dS, N, int32_t);
   if (pred_x) D2H(pred_x, dPx, (size_t)N * (H + 1) * nx, double);

@@ -152,4 +152,90 @@ SCB_HD void jclip(Jet1<N>& r, const Jet1<N>& a, double lo, double hi) {
   else r = a;
 }
 
+// ---- entry jets ---------------------------------------------------------------------------------------
+// Every jet operation above is ENTRY-WISE in the derivative index: gradient entry i of a result needs only the
+// values and gradient entry i of the operands, Hessian entry (i, j) only values, gradient entries i, j and Hessian
+// entry (i, j).  So instead of one lane carrying a whole jet (28 doubles at N = 6, ~100 flops per product) a lane
+// can evaluate the same expression for ONE entry with a 2- or 4-double jet: the MPC kernel spreads the
+// (stage, entry) pairs of its derivative passes over the lanes of the agent's group this way.
+struct JetG { double v, g; };              // value, d/dy_i
+struct JetH { double v, gi, gj, h; };      // value, d/dy_i, d/dy_j, d2/(dy_i dy_j)
+
+SCB_HD void jvar_entry(JetG& r, double val, int idx, int i) { r.v = val; r.g = (idx == i) ? 1.0 : 0.0; }
+SCB_HD void jvar_entry(JetH& r, double val, int idx, int i, int j) {
+  r.v = val; r.gi = (idx == i) ? 1.0 : 0.0; r.gj = (idx == j) ? 1.0 : 0.0; r.h = 0.0;
+}
+SCB_HD void jconst(JetG& r, double c) { r.v = c; r.g = 0.0; }
+SCB_HD void jconst(JetH& r, double c) { r.v = c; r.gi = 0.0; r.gj = 0.0; r.h = 0.0; }
+SCB_HD void jaxpy(JetG& r, const JetG& a, double s, const JetG& b) { r.v = a.v + s * b.v; r.g = a.g + s * b.g; }
+SCB_HD void jaxpy(JetH& r, const JetH& a, double s, const JetH& b) {
+  r.v = a.v + s * b.v; r.gi = a.gi + s * b.gi; r.gj = a.gj + s * b.gj; r.h = a.h + s * b.h;
+}
+SCB_HD void jscale(JetG& r, const JetG& a, double s) { r.v = s * a.v; r.g = s * a.g; }
+SCB_HD void jscale(JetH& r, const JetH& a, double s) { r.v = s * a.v; r.gi = s * a.gi; r.gj = s * a.gj; r.h = s * a.h; }
+SCB_HD void jmul(JetG& r, const JetG& a, const JetG& b) {
+  const double av = a.v, bv = b.v;
+  r.g = av * b.g + bv * a.g; r.v = av * bv;
+}
+SCB_HD void jmul(JetH& r, const JetH& a, const JetH& b) {
+  const double av = a.v, bv = b.v, agi = a.gi, agj = a.gj, bgi = b.gi, bgj = b.gj;
+  r.h = av * b.h + bv * a.h + agi * bgj + agj * bgi;
+  r.gi = av * bgi + bv * agi; r.gj = av * bgj + bv * agj; r.v = av * bv;
+}
+SCB_HD void jchain(JetG& r, const JetG& a, double f0, double f1, double) { r.g = f1 * a.g; r.v = f0; }
+SCB_HD void jchain(JetH& r, const JetH& a, double f0, double f1, double f2) {
+  const double agi = a.gi, agj = a.gj;
+  r.h = f1 * a.h + f2 * agi * agj; r.gi = f1 * agi; r.gj = f1 * agj; r.v = f0;
+}
+SCB_HD void jclip(JetG& r, const JetG& a, double lo, double hi) {
+  if (a.v > hi) jconst(r, hi); else if (a.v < lo) jconst(r, lo); else r = a;
+}
+SCB_HD void jclip(JetH& r, const JetH& a, double lo, double hi) {
+  if (a.v > hi) jconst(r, hi); else if (a.v < lo) jconst(r, lo); else r = a;
+}
+SCB_HD double jval(const JetG& a) { return a.v; }
+SCB_HD double jval(const JetH& a) { return a.v; }
+SCB_HD double jval(double a) { return a; }
+SCB_HD void jchain(double& r, const double&, double f0, double, double) { r = f0; }
+
+// sin/cos providers for the stage maps: compute, compute + remember, or replay the remembered values (the entry-jet
+// passes evaluate one stage many times at the same point; the transcendental is paid once per stage and iterate)
+struct TrigCompute {
+  template <class T>
+  SCB_HD void operator()(T& s, T& c, const T& a) {
+    double sv, cv;
+    sincos_pair(jval(a), sv, cv);
+    T a0 = a;                                  // (s or c may alias a)
+    jchain(s, a0, sv, cv, -sv);
+    jchain(c, a0, cv, -sv, -cv);
+  }
+};
+struct TrigStore {
+  double* buf;
+  int n;
+  SCB_HD explicit TrigStore(double* b) : buf(b), n(0) {}
+  template <class T>
+  SCB_HD void operator()(T& s, T& c, const T& a) {
+    double sv, cv;
+    sincos_pair(jval(a), sv, cv);
+    buf[2 * n] = sv; buf[2 * n + 1] = cv; ++n;
+    T a0 = a;
+    jchain(s, a0, sv, cv, -sv);
+    jchain(c, a0, cv, -sv, -cv);
+  }
+};
+struct TrigLoad {
+  const double* buf;
+  int n;
+  SCB_HD explicit TrigLoad(const double* b) : buf(b), n(0) {}
+  template <class T>
+  SCB_HD void operator()(T& s, T& c, const T& a) {
+    const double sv = buf[2 * n], cv = buf[2 * n + 1];
+    ++n;
+    T a0 = a;
+    jchain(s, a0, sv, cv, -sv);
+    jchain(c, a0, cv, -sv, -cv);
+  }
+};
+
 }  // namespace scb

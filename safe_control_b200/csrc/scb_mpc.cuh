@@ -47,11 +47,11 @@ struct MpcModel;
 // Relative degree 1: cbf = d_h + alpha h_k (mpc_cbf.py:312-315).
 template <>
 struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
-  static constexpr int NX = 2, NU = 2, NY = 4, REL = 1, NGOAL = 2, AUX = 0;
+  static constexpr int NX = 2, NU = 2, NY = 4, REL = 1, NGOAL = 2, AUX = 0, NTRIG = 0;
   static constexpr bool VBOUND = false, LINEAR = false;
   static SCB_HD double beta() { return 1.01; }
-  template <class T>
-  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR&) {
     jaxpy(F[0], y[0], p.dt, y[2]);
     jaxpy(F[1], y[1], p.dt, y[3]);
     P1 = F[0]; Q1 = F[1]; P2 = F[0]; Q2 = F[1];
@@ -61,14 +61,15 @@ struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
 // DynamicUnicycle2D: f, g robots/dynamic_unicycle2D.py:42-73, step :75-78, barrier_dt :188-238
 template <>
 struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
-  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0;
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 2;
   static constexpr bool VBOUND = true, LINEAR = false;
   static SCB_HD double beta() { return 1.01; }
   // y = (px, py, theta, v, a, omega).  F = Euler map; (P1,Q1), (P2,Q2) = positions after 1 and 2 own steps.
-  template <class T>
-  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
+  // trig(s, c, angle) supplies sin/cos (computed, or replayed from the per-stage cache; scb_jet.cuh)
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
     T s, c, vc, vs;
-    jsincos(s, c, y[2]);
+    trig(s, c, y[2]);
     jmul(vc, y[3], c); jmul(vs, y[3], s);
     jaxpy(F[0], y[0], p.dt, vc);
     jaxpy(F[1], y[1], p.dt, vs);
@@ -76,7 +77,7 @@ struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
     jaxpy(F[3], y[3], p.dt, y[4]);
     P1 = F[0]; Q1 = F[1];
     T s1, c1, v1c, v1s;
-    jsincos(s1, c1, F[2]);
+    trig(s1, c1, F[2]);
     jmul(v1c, F[3], c1); jmul(v1s, F[3], s1);
     jaxpy(P2, P1, p.dt, v1c);
     jaxpy(Q2, Q1, p.dt, v1s);
@@ -86,14 +87,14 @@ struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
 // KinematicBicycle2D: f, g robots/kinematic_bicycle2D.py:75-110, step (clips v) :112-123, barrier_dt :175-199
 template <>
 struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
-  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0;
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 2;
   static constexpr bool VBOUND = true, LINEAR = false;
   static SCB_HD double beta() { return 1.1; }
-  template <class T>
+  template <class T, class TR>
   static SCB_HD void euler(const scb_params& p, const T& px, const T& py, const T& th, const T& v, const T& a,
-                           const T& b, T* F) {
+                           const T& b, T* F, TR& trig) {
     T s, c, vc, vs, vsb, vcb, t0, t1, vb;
-    jsincos(s, c, th);
+    trig(s, c, th);
     jmul(vc, v, c); jmul(vs, v, s);
     jmul(vsb, vs, b); jmul(vcb, vc, b);
     jaxpy(t0, vc, -1.0, vsb);                 // v c - v s beta
@@ -104,13 +105,13 @@ struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
     jaxpy(F[2], th, p.dt / p.rear_ax_dist, vb);
     jaxpy(F[3], v, p.dt, a);
   }
-  template <class T>
-  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2) {
-    euler(p, y[0], y[1], y[2], y[3], y[4], y[5], F);
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
+    euler(p, y[0], y[1], y[2], y[3], y[4], y[5], F, trig);
     P1 = F[0]; Q1 = F[1];
     T v1, G[4];
     jclip(v1, F[3], p.v_min, p.v_max);        // the model's own step clips v (:116-121)
-    euler(p, P1, Q1, F[2], v1, y[4], y[5], G);
+    euler(p, P1, Q1, F[2], v1, y[4], y[5], G, trig);
     P2 = G[0]; Q2 = G[1];
   }
 };
@@ -122,7 +123,7 @@ struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
 // the AUX block: Ae = I + dt A (12x12), Be = dt B (12x4), rows 0 and 1 of [Ad | Bd] (2 x 16).
 template <>
 struct MpcModel<SCB_QUAD_3D> {
-  static constexpr int NX = 12, NU = 4, NY = 16, REL = 1, NGOAL = 3, AUX = 144 + 48 + 32;
+  static constexpr int NX = 12, NU = 4, NY = 16, REL = 1, NGOAL = 3, AUX = 144 + 48 + 32, NTRIG = 0;
   static constexpr bool VBOUND = false, LINEAR = true;
   static SCB_HD double beta() { return 1.01; }
 
@@ -172,8 +173,9 @@ struct MpcModel<SCB_QUAD_3D> {
   }
 
   // plain-value stage map (rollout / line search)
+  template <class TR>
   static SCB_HD void stage(const scb_params&, const double* aux, const double* y, double* F, double& P1, double& Q1,
-                           double& P2, double& Q2) {
+                           double& P2, double& Q2, TR&) {
     const double* Ae = aux; const double* Be = aux + 144; const double* R = aux + 192;
     for (int i = 0; i < 12; ++i) {
       double v = 0.0;
@@ -192,11 +194,15 @@ struct MpcModel<SCB_QUAD_3D> {
 struct MpcLayout {
   int H, M, n, NS;
   int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, DZ, PM, PV, KG, KF,
-      TM, MM, MV, PT2, DY, ZT, XT, RG, AUX;
+      TM, MM, MV, PT2, DY, ZT, XT, RG, AUX, AS, BS, TR, TRS;
   int total;
 };
 
-template <int NX, int NU, bool VBOUND, bool LINEAR = false, int AUXN = 0>
+// SEQ = true: single-lane (host-sim) build, which needs one extra scratch block (PT2) because one lane plays all
+// matrix columns of the Riccati stage in turn.  Linear models keep ONE copy of (A, B) (their AUX block) instead of H
+// identical ones (AS = BS = 0), and the Riccati value function is double-buffered (the forward sweep only needs the
+// gains), so the workspace is O(H) only in what really differs per stage.
+template <int NX, int NU, bool VBOUND, bool LINEAR = false, int AUXN = 0, bool SEQ = false, int NTRIG = 2>
 SCB_HD MpcLayout mpc_layout(int H, int M) {
   constexpr int NY = NX + NU, NH = NY * (NY + 1) / 2;
   MpcLayout L;
@@ -204,9 +210,10 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += cnt; return r; };
   L.X = take((H + 1) * NX);  L.Z = take(H * NU);
-  L.A = take(H * NX * NX);   L.B = take(H * NX * NU);
-  L.FH = take(0);                        // (curvature is contracted on the fly, see stage_hessians)
   L.AUX = take(AUXN);
+  if (LINEAR) { L.A = L.AUX; L.B = L.AUX + NX * NX; L.AS = 0; L.BS = 0; }
+  else { L.A = take(H * NX * NX); L.B = take(H * NX * NU); L.AS = NX * NX; L.BS = NX * NU; }
+  L.FH = take(0);                        // (curvature is contracted on the fly, see stage_hessians)
   L.JE = take(H * NY); L.JX = take(H * NY); L.JY = take(H * NY);       // gradients gE, gX, gY
   L.PT = take(H * 6);        L.OB = take(M * 3);
   L.C = take(H * M); L.S = take(0); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
@@ -217,12 +224,13 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   L.RD = take(L.n); L.DZ = take(L.n);
   {
     const int NXT = NX + NU, NV = NXT + NU;
-    L.PM = take((H + 1) * NXT * NXT); L.PV = take((H + 1) * NXT);
+    L.PM = take(2 * NXT * NXT); L.PV = take(2 * NXT);     // P_{k+1} / P_k ping-pong (slot k & 1)
     L.KG = take(H * NU * NXT); L.KF = take(H * NU);
     L.TM = take(NXT * NV + NV * NV + NV); L.MM = take(NU * NV); L.MV = take(0);
-    L.PT2 = take((NV + 1) * NV);      // host-sim only scratch (LANES == 1 plays all columns); tiny
+    L.PT2 = take(SEQ ? (NV + 1) * NV : 0);
   }
   L.DY = take((H + 1) * NY);
+  L.TRS = 2 * NTRIG; L.TR = take(H * L.TRS);              // sin/cos of every stage at the current iterate
   L.ZT = take(L.n); L.XT = take((H + 1) * NX); L.RG = take(L.n);
   L.total = o;
   return L;
@@ -267,6 +275,13 @@ SCB_HD void prof_add(int i, long long& tlast) {
 #else
 #define SCB_PH(i) do { } while (0)
 #define SCB_PH_INIT do { } while (0)
+#endif
+
+#ifndef SCB_MPC_STALL_BT
+#define SCB_MPC_STALL_BT 15
+#endif
+#ifndef SCB_MPC_STALL_ITERS
+#define SCB_MPC_STALL_ITERS 6
 #endif
 
 template <int MODEL, int LANES>
@@ -326,7 +341,8 @@ struct MpcSolver {
       for (int i = 0; i < NX; ++i) y[i] = x[i];
 #pragma unroll
       for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
-      Mod::stage(p, w + L.AUX, y, F, a, b, c, d);
+      TrigCompute trig;
+      Mod::stage(p, w + L.AUX, y, F, a, b, c, d, trig);
 #pragma unroll
       for (int i = 0; i < NX; ++i) { x[i] = F[i]; xs[(k + 1) * NX + i] = F[i]; }
     }
@@ -343,7 +359,8 @@ struct MpcSolver {
       for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
 #pragma unroll
       for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
-      Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
+      TrigCompute trig;
+      Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2, trig);
       double* pt = w + L.PT + k * 6;
       pt[0] = y[0]; pt[1] = y[1]; pt[2] = P1; pt[3] = Q1; pt[4] = P2; pt[5] = Q2;
     }
@@ -398,10 +415,7 @@ struct MpcSolver {
         for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
 #pragma unroll
         for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
-        double* A = w + L.A + k * NX * NX;
-        double* B = w + L.B + k * NX * NU;
-        for (int t = 0; t < NX * NX; ++t) A[t] = aux[t];
-        for (int t = 0; t < NX * NU; ++t) B[t] = aux[NX * NX + t];
+        // (A_k, B_k) = (Ae, Be) of the AUX block for every stage: L.A / L.B alias it with stride 0
         double P1 = 0.0, Q1 = 0.0;
         for (int i = 0; i < NY; ++i) { P1 = fma(R0[i], y[i], P1); Q1 = fma(R1[i], y[i], Q1); }
         double* je = w + L.JE + k * NY;
@@ -416,30 +430,41 @@ struct MpcSolver {
       }
       sync();
     } else {
-      using J1 = Jet1<NY>;
-      for (int k = lane; k < H; k += LANES) {
-        J1 y[NY], F[NX], P1, Q1, P2, Q2;
+      // pass 0 (lanes over stages): the stage's sin/cos at the current iterate -> trig cache
+      if constexpr (Mod::NTRIG > 0) {
+        for (int k = lane; k < H; k += LANES) {
+          double y[NY], F[NX], P1, Q1, P2, Q2;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) jvar(y[i], xs[k * NX + i], i);
+          for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) jvar(y[NX + i], z[k * NU + i], NX + i);
-        Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
-        double* A = w + L.A + k * NX * NX;
-        double* B = w + L.B + k * NX * NU;
-#pragma unroll
-        for (int c = 0; c < NX; ++c) {
-#pragma unroll
-          for (int i = 0; i < NX; ++i) A[c * NX + i] = F[c].g[i];
-#pragma unroll
-          for (int i = 0; i < NU; ++i) B[c * NU + i] = F[c].g[NX + i];
+          for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
+          TrigStore trig(w + L.TR + k * L.TRS);
+          Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2, trig);
         }
-        J1 E, PX, PY;
-        barrier_jets(y, P1, Q1, P2, Q2, E, PX, PY);
-        double* je = w + L.JE + k * NY;
-        double* jx = w + L.JX + k * NY;
-        double* jy = w + L.JY + k * NY;
+        sync();
+      }
+      // pass 1 (lanes over (stage, variable) pairs): column i of A_k / B_k and entry i of gE, gX, gY by entry jets
+      for (int t = lane; t < H * NY; t += LANES) {
+        const int k = t / NY, i = t - k * NY;
+        JetG y[NY], F[NX], P1, Q1, P2, Q2;
 #pragma unroll
-        for (int i = 0; i < NY; ++i) { je[i] = E.g[i]; jx[i] = PX.g[i]; jy[i] = PY.g[i]; }
+        for (int m = 0; m < NX; ++m) jvar_entry(y[m], xs[k * NX + m], m, i);
+#pragma unroll
+        for (int m = 0; m < NU; ++m) jvar_entry(y[NX + m], z[k * NU + m], NX + m, i);
+        TrigLoad trig(w + L.TR + k * L.TRS);
+        Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2, trig);
+        double* A = w + L.A + k * L.AS;
+        double* B = w + L.B + k * L.BS;
+        if (i < NX) {
+#pragma unroll
+          for (int c = 0; c < NX; ++c) A[c * NX + i] = F[c].g;
+        } else {
+#pragma unroll
+          for (int c = 0; c < NX; ++c) B[c * NU + (i - NX)] = F[c].g;
+        }
+        JetG E, PX, PY;
+        barrier_jets(y, P1, Q1, P2, Q2, E, PX, PY);
+        w[L.JE + t] = E.g; w[L.JX + t] = PX.g; w[L.JY + t] = PY.g;
       }
       sync();
     }
@@ -465,8 +490,8 @@ struct MpcSolver {
 #pragma unroll
       for (int i = 0; i < NX; ++i) { mu[i] = gam[H * NY + i]; MU[H * NX + i] = mu[i]; }
       for (int k = H - 1; k >= 0; --k) {
-        const double* A = w + L.A + k * NX * NX;
-        const double* B = w + L.B + k * NX * NU;
+        const double* A = w + L.A + k * L.AS;
+        const double* B = w + L.B + k * L.BS;
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
           double v = gam[k * NY + NX + i];
@@ -590,44 +615,35 @@ struct MpcSolver {
   // stage Hessians G_k = hess l_k - sum lam hess c + sum sigma grad c grad c' + bound sigmas + costate curvature
   SCB_HD void stage_hessians() {
     double* Gm = w + L.G;
-    // pass 1 (lanes over stages): all curvature of stage k is the Hessian of ONE scalar function of y,
-    //   Psi_k = sum_c mu_{k+1,c} F_c(y) - Lam0 E(y) + LamX PX(y) + LamY PY(y),
-    // evaluated with second-order jets; only its 21-entry Hessian is kept.  Skipped in Gauss-Newton mode.
-    if constexpr (!Mod::LINEAR) {
-      for (int k = lane; k <= H; k += LANES) {
-        double* Gk = Gm + k * NH;
-        if (k == H || gauss_newton) {
-#pragma unroll
-          for (int e = 0; e < NH; ++e) Gk[e] = 0.0;
-          continue;
-        }
-        J y[NY], F[NX], P1, Q1, P2, Q2, E, PX, PY;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) jvar(y[i], w[L.X + k * NX + i], i);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) jvar(y[NX + i], w[L.Z + k * NU + i], NX + i);
-        Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2);
-        barrier_jets(y, P1, Q1, P2, Q2, E, PX, PY);
-        const double* sm = w + L.SUM + k * 12;
-        const double* mu = w + L.MU + (k + 1) * NX;
-#pragma unroll
-        for (int e = 0; e < NH; ++e) {
-          double v = -sm[6] * E.h[e] + sm[7] * PX.h[e] + sm[8] * PY.h[e];
-#pragma unroll
-          for (int c = 0; c < NX; ++c) v = fma(mu[c], F[c].h[e], v);
-          Gk[e] = v;
-        }
-      }
-      sync();
-    }
-    // pass 2 (lanes over entries): cost Hessian, barrier terms sum sigma grad c grad c', linear-model curvature
+    // All curvature of stage k is the Hessian of ONE scalar function of y,
+    //   Psi_k = sum_c mu_{k+1,c} F_c(y) - Lam0 E(y) + LamX PX(y) + LamY PY(y)      (skipped in Gauss-Newton mode).
+    // Lanes over (stage, packed Hessian entry) pairs: the curvature entry comes from an ENTRY jet (4 doubles per
+    // quantity instead of a 28-double full jet, scb_jet.cuh) replaying the stage's cached sin/cos; the cost Hessian,
+    // the barrier terms sum sigma grad c grad c' and the linear model's constant curvature are added in the same pass.
     for (int t = lane; t < (H + 1) * NH; t += LANES) {
       const int k = t / NH, e = t - k * NH;
       // unpack (i, j) of packed entry e
       int i = 0, rem = e;
       while (rem >= NY - i) { rem -= NY - i; ++i; }
       const int j = i + rem;
-      double v = Mod::LINEAR ? 0.0 : Gm[t];
+      double v = 0.0;
+      if constexpr (!Mod::LINEAR) {
+        if (k < H && !gauss_newton) {
+          JetH y[NY], F[NX], P1, Q1, P2, Q2, E, PX, PY;
+#pragma unroll
+          for (int m = 0; m < NX; ++m) jvar_entry(y[m], w[L.X + k * NX + m], m, i, j);
+#pragma unroll
+          for (int m = 0; m < NU; ++m) jvar_entry(y[NX + m], w[L.Z + k * NU + m], NX + m, i, j);
+          TrigLoad trig(w + L.TR + k * L.TRS);
+          Mod::stage(p, w + L.AUX, y, F, P1, Q1, P2, Q2, trig);
+          barrier_jets(y, P1, Q1, P2, Q2, E, PX, PY);
+          const double* sm = w + L.SUM + k * 12;
+          const double* mu = w + L.MU + (k + 1) * NX;
+          v = -sm[6] * E.h + sm[7] * PX.h + sm[8] * PY.h;
+#pragma unroll
+          for (int c = 0; c < NX; ++c) v = fma(mu[c], F[c].h, v);
+        }
+      }
       if (i == j && i < NX) v += 2.0 * Qs[i];
       if (k < H) {
         const double* sm = w + L.SUM + k * 12;
@@ -668,9 +684,9 @@ struct MpcSolver {
   // F_k[a][c], a < NXT rows (next augmented state), c < NV columns (xt_k, u_k)
   SCB_HD double fm(int k, int a, int c) const {
     if (a < NX) {
-      if (c < NX) return w[L.A + k * NX * NX + a * NX + c];
+      if (c < NX) return w[L.A + k * L.AS + a * NX + c];
       if (c < NXT) return 0.0;
-      return w[L.B + k * NX * NU + a * NU + (c - NXT)];
+      return w[L.B + k * L.BS + a * NU + (c - NXT)];
     }
     return (c == NXT + (a - NX)) ? 1.0 : 0.0;
   }
@@ -691,9 +707,9 @@ struct MpcSolver {
       const int r = t / NXT, c = t - r * NXT;
       double v = 0.0;
       if (r < NX && c < NX) { const int lo = r < c ? r : c, hi = r < c ? c : r; v = w[L.G + H * NH + hidx<NY>(lo, hi)]; }
-      PM[H * NXT * NXT + t] = v;
+      PM[(H & 1) * NXT * NXT + t] = v;
     }
-    for (int t = lane; t < NXT; t += LANES) PV[H * NXT + t] = (t < NX) ? -gam[H * NY + t] : 0.0;
+    for (int t = lane; t < NXT; t += LANES) PV[(H & 1) * NXT + t] = (t < NX) ? -gam[H * NY + t] : 0.0;
     sync();
     bool ok = true;
     double* MU_ = w + L.MM;                         // published input columns: MU_[i * NV + r] = M[r][NXT + i]
@@ -701,8 +717,8 @@ struct MpcSolver {
     double* HS = FD + NXT * NV;                     // dense Hs_k           (NV x NV): stage Hessian + rate terms
     double* HV = HS + NV * NV;                      // h_k                  (NV)
     for (int k = H - 1; k >= 0; --k) {
-      const double* Pn = PM + (k + 1) * NXT * NXT;
-      const double* pn = PV + (k + 1) * NXT;
+      const double* Pn = PM + ((k + 1) & 1) * NXT * NXT;
+      const double* pn = PV + ((k + 1) & 1) * NXT;
       // (a) dense blocks of this stage, lanes over entries: afterwards every lane runs the SAME straight-line code
       for (int t = lane; t < NXT * NV + NV * NV + NV; t += LANES) {
         if (t < NXT * NV) {
@@ -799,7 +815,8 @@ struct MpcSolver {
       // gains for this lane's column (K[:, c] or kff), then its column of P_k (or p_k)
       double* Kg = w + L.KG + k * NU * NXT;
       double* Kf = w + L.KF + k * NU;
-      double* Pk = PM + k * NXT * NXT;
+      double* Pk = PM + (k & 1) * NXT * NXT;
+      double* pk = PV + (k & 1) * NXT;
       for (int c = lane; c <= NV; c += LANES) {
         if (c >= NXT && c < NV) continue;            // input columns carry no gain
         if (LANES == 1) {
@@ -833,7 +850,7 @@ struct MpcSolver {
           double v = Mc[r];
 #pragma unroll
           for (int i = 0; i < NU; ++i) v = fma(MU_[i * NV + r], rhs[i], v);
-          if (isvec) PV[k * NXT + r] = v; else Pk[r * NXT + c] = v;
+          if (isvec) pk[r] = v; else Pk[r * NXT + c] = v;
         }
       }
       sync();
@@ -865,8 +882,8 @@ struct MpcSolver {
 #pragma unroll
         for (int i = 0; i < NU; ++i) w[L.DY + k * NY + NX + i] = du[i];
         double nx_[NX];
-        const double* A = w + L.A + k * NX * NX;
-        const double* B = w + L.B + k * NX * NU;
+        const double* A = w + L.A + k * L.AS;
+        const double* B = w + L.B + k * L.BS;
 #pragma unroll
         for (int a = 0; a < NX; ++a) {
           double v = 0.0;
@@ -1133,8 +1150,13 @@ struct MpcSolver {
              mu_bar, ap, ad, alpha, bt, delta, dpsi, nu_pen);
 #endif
       SCB_PH(12);
-      tiny_steps = (alpha < 1e-10) ? tiny_steps + 1 : 0;
-      if (tiny_steps >= 5) { st = (e_p > 1e-6) ? SCB_INFEASIBLE : SCB_MAXITER; break; }
+      // stalled line search: the step was cut by >= 2^-12 (or to nothing) several iterations in a row.  This is what a
+      // kink of the model's own step does (KinematicBicycle2D clips v inside the barrier, kinematic_bicycle2D.py:116-121):
+      // the Newton direction is a descent direction of a smooth model the merit does not follow, every further
+      // iteration pays ~20 trial rollouts and moves by 1e-6.  Give up instead of repeating that 50 times.  (Only at
+      // feasible iterates: far from feasibility a few heavily damped steps in a row are normal and recover.)
+      tiny_steps = (alpha < 1e-10 || (bt >= SCB_MPC_STALL_BT && e_p <= 1e-9)) ? tiny_steps + 1 : 0;
+      if (tiny_steps >= SCB_MPC_STALL_ITERS) { st = (e_p > 1e-6) ? SCB_INFEASIBLE : SCB_MAXITER; break; }
       // accept: z, x, g; multipliers move with their own step and are kept within kappa_Sigma of mu/g
       for (int t = lane; t < n; t += LANES) w[L.Z + t] = w[L.ZT + t];
       for (int t = lane; t < (H + 1) * NX; t += LANES) w[L.X + t] = w[L.XT + t];
@@ -1180,7 +1202,7 @@ SCB_HD void mpc_agent(const scb_params& p, int H, int M, int nobs, const double*
                       const double* uprev, const double* obs, double* workspace, double* U, int32_t* status,
                       double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
   using Mod = MpcModel<MODEL>;
-  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX>(H, M);
+  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, LANES == 1, Mod::NTRIG>(H, M);
   MpcSolver<MODEL, LANES> s(p, L, workspace);
   if (nobs < 0) nobs = 0;
   if (nobs > M) nobs = M;

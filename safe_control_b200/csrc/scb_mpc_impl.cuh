@@ -1,0 +1,207 @@
+// scb_mpc_impl.cuh -- __global__ wrapper + per-model launcher of the MPC-CBF path (body: scb_mpc.cuh).
+//
+// One lane group per agent; each group owns a private workspace of MpcLayout::total doubles in dynamic shared
+// memory, so a CTA carries as many agents as fit in the SM's 227 KB and the grid is persistent (one CTA per SM,
+// agents pulled from a work counter).  Everything the interior-point loop touches after the initial obstacle
+// load stays on chip; HBM sees the inputs once and U/status once.
+#pragma once
+
+#include "scb_mpc.cuh"
+#include "scb_mpc_kernels.cuh"
+
+namespace scb {
+
+#ifndef SCB_MPC_LANES
+#define SCB_MPC_LANES 32             // lanes per agent (16: two agents per warp, for models whose Riccati stage fits: NV + 1 <= 16)
+#endif
+template <int MODEL>
+constexpr int mpc_lanes() {
+  using Mod = MpcModel<MODEL>;
+  return (Mod::NX + 2 * Mod::NU + 1 <= SCB_MPC_LANES) ? SCB_MPC_LANES : 32;
+}
+
+#ifndef SCB_MPC_MAXTHREADS
+#define SCB_MPC_MAXTHREADS 256       // measured (cfg3): 256 threads (255 regs, 8 agent-warps) 8.3 ms, 384 (168 regs + spills) 8.9 ms, 512 9.5 ms
+#endif
+
+template <int MODEL, int LANES>
+__global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid_constant__ scb_params p, int N, int M, int H, int ws_doubles, int gpb,
+                           const double* __restrict__ X, const double* __restrict__ Uref,
+                           const double* __restrict__ goal, const double* __restrict__ u_prev,
+                           const int32_t* __restrict__ track, const double* __restrict__ OBS, long stride,
+                           const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
+                           double* __restrict__ pred_x, double* __restrict__ pred_u, int32_t* __restrict__ iters,
+                           double* __restrict__ kkt, int* __restrict__ next_agent, const int32_t* __restrict__ order) {
+  extern __shared__ double smem[];
+  using Mod = MpcModel<MODEL>;
+  constexpr int NX = Mod::NX, NU = Mod::NU;
+  const int grp = threadIdx.x / LANES;
+  if (grp >= gpb) return;             // padding lanes of the last warp (gpb * LANES is rounded up to whole warps)
+  double* ws = smem + (size_t)grp * ws_doubles;
+  // Work distribution: the first wave is static, afterwards a group that finishes early pulls the next agent
+  // from a global counter (iteration counts vary 10..60 per agent; static striding left ~30 % of the wave idle).
+  // With a schedule (`order`, hardest-looking agents first, see mpc_key_kernel) slot q runs agent order[q].
+  const long first_dynamic = (long)gridDim.x * gpb;
+  for (long q = (long)blockIdx.x * gpb + grp; q < N;) {
+    const long a = order ? (long)order[q] : q;
+    if (track && track[a] == 0) {
+      // state_machine != 'track': return u_ref untouched, no solve (mpc_cbf.py:379-381)
+      if ((threadIdx.x & (LANES - 1)) == 0) {
+        for (int i = 0; i < NU; ++i) U[a * NU + i] = Uref[a * NU + i];
+        status[a] = SCB_OPTIMAL;
+        if (iters) iters[a] = 0;
+        if (kkt) kkt[a] = 0.0;
+      }
+    } else {
+    mpc_agent<MODEL, LANES>(p, H, M, nobs ? nobs[a] : M, X + a * NX, goal + a * Mod::NGOAL, u_prev + a * NU, OBS + a * stride, ws,
+                            U + a * NU, status + a, pred_x ? pred_x + a * (H + 1) * NX : nullptr,
+                            pred_u ? pred_u + a * H * NU : nullptr, iters ? iters + a : nullptr,
+                            kkt ? kkt + a : nullptr);
+    }
+    int nxt = 0;
+    if ((threadIdx.x & (LANES - 1)) == 0) nxt = atomicAdd(next_agent, 1);
+    nxt = __shfl_sync(Grp<LANES>::gmask(), nxt, 0, LANES);
+    q = first_dynamic + nxt;
+  }
+}
+
+// ---- schedule: hardest-looking agents first ---------------------------------------------------------------
+// Iteration counts are long-tailed (cfg3: mean 17, 99 % <= 22, max ~58) and an agent is a serial job, so a straggler
+// that STARTS late sets the kernel's duration: simulated on cfg3's own iteration counts, index order costs 106
+// iteration-slots per group against 64 ideal and 73 for longest-first.  The stragglers are the agents whose CBF rows
+// are violated or nearly so at the cold start, so the key is the kernel's own constraint function at stage 0,
+//   key = min_j cbf_j(x_0, u_prev),
+// quantised monotonically into kMpcBins bins; a counting sort over the bins gives the schedule (ascending key).
+// Only the ORDER in which agents are started changes -- every agent's result is independent of it.
+constexpr int kMpcBins = 1024;
+
+template <int MODEL>
+__global__ void mpc_key_kernel(const __grid_constant__ scb_params p, int N, const double* __restrict__ X,
+                               const double* __restrict__ u_prev, const int32_t* __restrict__ track,
+                               const double* __restrict__ OBS, long stride, const int32_t* __restrict__ nobs, int M,
+                               int32_t* __restrict__ bin_of, int32_t* __restrict__ hist) {
+  using Mod = MpcModel<MODEL>;
+  constexpr int NX = Mod::NX, NU = Mod::NU, NY = Mod::NY;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= N) return;
+  int bin = kMpcBins - 1;                                  // not solved (state machine != track): last
+  if (!track || track[a] != 0) {
+    double w0, w1, w2, Wsum;
+    if (Mod::REL == 2) {
+      const double g1 = p.alpha1 + p.alpha2, g2 = p.alpha1 * p.alpha2;
+      w2 = 1.0; w1 = g1 - 2.0; w0 = 1.0 - g1 + g2; Wsum = g2;
+    } else {
+      w2 = 0.0; w1 = 1.0; w0 = p.alpha - 1.0; Wsum = p.alpha;
+    }
+    double y[NY], P1, Q1, P2, Q2;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) y[i] = __ldg(X + (long)a * NX + i);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) y[NX + i] = __ldg(u_prev + (long)a * NU + i);
+    if constexpr (Mod::LINEAR) {
+      // (the linear model's barrier points need its RK4 matrices; the plain barrier value at x_0 ranks well enough)
+      P1 = y[0]; Q1 = y[1]; P2 = y[0]; Q2 = y[1];
+      w0 = Wsum; w1 = 0.0; w2 = 0.0;
+    } else {
+      double F[NX];
+      TrigCompute trig;
+      Mod::stage(p, nullptr, y, F, P1, Q1, P2, Q2, trig);
+    }
+    const int no = nobs ? min(max(nobs[a], 0), M) : M;
+    const double* ob = OBS + (long)a * stride;
+    double key = 1e6;
+    for (int j = 0; j < no; ++j) {
+      const double ox = __ldg(ob + j * 7), oy = __ldg(ob + j * 7 + 1), d = __ldg(ob + j * 7 + 2) + p.radius;
+      double v = -Wsum * Mod::beta() * d * d;
+      double dx = y[0] - ox, dy = y[1] - oy;
+      v = fma(w0, dx * dx + dy * dy, v);
+      dx = P1 - ox; dy = Q1 - oy;
+      v = fma(w1, dx * dx + dy * dy, v);
+      dx = P2 - ox; dy = Q2 - oy;
+      v = fma(w2, dx * dx + dy * dy, v);
+      key = fmin(key, v);
+    }
+    if (!(key == key)) key = -1e6;                         // NaN inputs: start them first, they exit at once
+    const double q = key / (fabs(key) + 1.0);              // monotone map to (-1, 1)
+    bin = (int)((q + 1.0) * 0.5 * (kMpcBins - 2));
+    bin = min(max(bin, 0), kMpcBins - 2);
+  }
+  bin_of[a] = bin;
+  atomicAdd(hist + bin, 1);
+}
+
+// one CTA: exclusive scan of the histogram, then scatter (order within a bin is arbitrary)
+static __global__ void __launch_bounds__(kMpcBins) mpc_order_kernel(int N, const int32_t* __restrict__ bin_of,
+                                                            const int32_t* __restrict__ hist, int32_t* __restrict__ order) {
+  __shared__ int cursor[kMpcBins];
+  __shared__ int wsum[kMpcBins / 32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int h = hist[t];
+  int v = h;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+  if (lane == 31) wsum[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    int s = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += u; }
+    wsum[lane] = s;
+  }
+  __syncthreads();
+  cursor[t] = v - h + (wid > 0 ? wsum[wid - 1] : 0);
+  __syncthreads();
+  for (int a = t; a < N; a += kMpcBins) order[atomicAdd(&cursor[bin_of[a]], 1)] = a;
+}
+
+template <int MODEL>
+int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* X, const double* Uref,
+                        const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
+                        const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
+                        int32_t* iters, double* kkt, int* counter, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                 int sm_count, int* count_only) {
+  using Mod = MpcModel<MODEL>;
+  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, false, Mod::NTRIG>(H, M);
+  const size_t per = (size_t)L.total * sizeof(double);
+  const size_t budget = 220 * 1024;
+  constexpr int kLanes = mpc_lanes<MODEL>();
+  constexpr int kMpcMaxGroups = SCB_MPC_MAXTHREADS / kLanes;
+  int gpb = (int)(budget / per);
+  if (gpb < 1) return SCB_ERR_TOO_LARGE;
+  if (gpb > kMpcMaxGroups) gpb = kMpcMaxGroups;
+  const long need = ((long)N + gpb - 1) / gpb;
+  if (need < sm_count) {                       // small batch: spread over all SMs first
+    gpb = (int)(((long)N + sm_count - 1) / sm_count);
+    if (gpb < 1) gpb = 1;
+  }
+  const size_t smem = per * gpb;
+  auto kern = mpc_kernel<MODEL, kLanes>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return SCB_ERR_TOO_LARGE;
+  long blocks = ((long)N + gpb - 1) / gpb;
+  if (blocks > sm_count) blocks = sm_count;
+  // schedule (needs the caller's workspace; without one, or when every agent starts in the first wave, index order)
+  const int32_t* order = nullptr;
+  const bool scheduled = workspace && workspace_bytes >= mpc_workspace_bytes(N) && (long)N > blocks * gpb;
+  if (count_only) { *count_only = scheduled ? 3 : 1; return SCB_OK; }
+  if (scheduled) {
+    int32_t* hist = (int32_t*)workspace;
+    int32_t* bin_of = hist + kMpcBins;
+    int32_t* ord = bin_of + N;
+    if (cudaMemsetAsync(hist, 0, kMpcBins * sizeof(int32_t), s) != cudaSuccess) return SCB_ERR_CUDA;
+    mpc_key_kernel<MODEL><<<(N + 127) / 128, 128, 0, s>>>(p, N, X, u_prev, track, OBS, stride, nobs, M, bin_of, hist);
+    mpc_order_kernel<<<1, kMpcBins, 0, s>>>(N, bin_of, hist, ord);
+    order = ord;
+  }
+  kern<<<(int)blocks, ((gpb * kLanes + 31) / 32) * 32, smem, s>>>(p, N, M, H, L.total, gpb, X, Uref, goal, u_prev, track, OBS, stride, nobs, U,
+                                                  status, pred_x, pred_u, iters, kkt, counter, order);
+  return SCB_OK;
+}
+
+
+#define SCB_MPC_INSTANTIATE(MODEL)                                                                                   \
+  template int mpc_launch_m<MODEL>(const scb_params&, int, int, int, const double*, const double*, const double*,   \
+                                   const double*, const int32_t*, const double*, long, const int32_t*, double*,     \
+                                   int32_t*, double*, double*, int32_t*, double*, int*, void*, size_t, cudaStream_t, int, int*);
+
+}  // namespace scb

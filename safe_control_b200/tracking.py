@@ -177,6 +177,7 @@ class TrackerHostState:
         t.w_max = float(s.get("w_max", 0.5))
         t.att_kp = float(s.get("velocity_tracking_yaw_kp", 1.5))
         t.wheel_base = float(s.get("wheel_base", 0.4)); t.delta_max = float(s.get("delta_max", math.radians(32)))
+        t.mpc_ws_bytes = 4 * (1024 + 2 * self.N)                                 # scb_mpccbf_workspace_bytes(N)
         return t
 
     STATE_ARRAYS = ("X", "yaw", "sm", "wp_idx", "WP", "nwp", "goal", "has_goal", "u_att", "u_prev", "ret", "done",
@@ -186,7 +187,8 @@ class TrackerHostState:
         N, M, nu = self.N, self.M, self.nu
         return dict(Uref=np.zeros((N, nu)), OBS=np.zeros((N, max(M, 1), 7)), nobs=np.zeros(N, np.int32),
                     U=np.zeros((N, nu)), status=np.zeros(N, np.int32), active=np.zeros((N, self.words), np.uint64),
-                    track_flag=np.zeros(N, np.int32), mpc_iters=np.zeros(N, np.int32))
+                    track_flag=np.zeros(N, np.int32), mpc_iters=np.zeros(N, np.int32),
+                    mpc_ws=np.zeros(1024 + 2 * N, np.int32))
 
 
 class BatchedTrackingController:

@@ -107,7 +107,7 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
 #define MPCCASE(MODEL)                                                                                          \
   case MODEL: {                                                                                                 \
     using Mod = MpcModel<MODEL>;                                                                                \
-    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX>(H, M);                                        \
+    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, true, Mod::NTRIG>(H, M);                                      \
     double* ws = new double[L.total];                                                                           \
     for (int t = 0; t < L.total; ++t) ws[t] = 0.0;                                                              \
     mpc_agent<MODEL, 1>(*p, H, M, no, X + (size_t)i * nx, goal + (size_t)i * Mod::NGOAL, u_prev + (size_t)i * nu,        \
@@ -134,7 +134,7 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
 #define STCASE(MODEL)                                                                                           \
   case MODEL: {                                                                                                 \
     using Mod = MpcModel<MODEL>;                                                                                \
-    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX>(1, M);                 \
+    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, true, Mod::NTRIG>(1, M);               \
     std::vector<double> ws(L.total, 0.0);                                                                       \
     MpcSolver<MODEL, 1> s(*p, L, ws.data());                                                                    \
     const double J = s.init(nobs, x, goal, Mod::NGOAL, u, obs);                                                 \
