@@ -115,6 +115,23 @@ SCB_HD void sincos_pair(double th, double& s, double& c) {
 #endif
 }
 
+// out-of-line versions for the (instruction-cache bound) MPC kernel: one copy of the slow paths
+#if defined(__CUDACC__)
+#define SCB_PHASE __host__ __device__ __noinline__
+#else
+#define SCB_PHASE inline
+#endif
+#ifndef SCB_MPC_OUTLINE_MATH
+#define SCB_MPC_OUTLINE_MATH 0
+#endif
+#if SCB_MPC_OUTLINE_MATH
+static SCB_PHASE void sincos_call(double a, double* s, double* c) { sincos_pair(a, *s, *c); }
+static SCB_PHASE double log_call(double a) { return log(a); }
+#else
+SCB_HD void sincos_call(double a, double* s, double* c) { sincos_pair(a, *s, *c); }
+SCB_HD double log_call(double a) { return log(a); }
+#endif
+
 SCB_HD double rsqrt_pos(double x) {
 #if defined(__CUDA_ARCH__)
   return rsqrt(x);

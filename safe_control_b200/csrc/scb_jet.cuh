@@ -204,7 +204,7 @@ struct TrigCompute {
   template <class T>
   SCB_HD void operator()(T& s, T& c, const T& a) {
     double sv, cv;
-    sincos_pair(jval(a), sv, cv);
+    sincos_call(jval(a), &sv, &cv);
     T a0 = a;                                  // (s or c may alias a)
     jchain(s, a0, sv, cv, -sv);
     jchain(c, a0, cv, -sv, -cv);
@@ -217,7 +217,7 @@ struct TrigStore {
   template <class T>
   SCB_HD void operator()(T& s, T& c, const T& a) {
     double sv, cv;
-    sincos_pair(jval(a), sv, cv);
+    sincos_call(jval(a), &sv, &cv);
     buf[2 * n] = sv; buf[2 * n + 1] = cv; ++n;
     T a0 = a;
     jchain(s, a0, sv, cv, -sv);

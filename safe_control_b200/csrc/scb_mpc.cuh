@@ -277,6 +277,39 @@ SCB_HD void prof_add(int i, long long& tlast) {
 #define SCB_PH_INIT do { } while (0)
 #endif
 
+// Loops with run-time trip counts (H, M) are NOT unrolled: measured on cfg3, unrolling the lane-strided loops x2 / x4
+// (17.9 k / 27 k SASS instructions instead of 12.9 k) made the kernel 1.8x / 2.8x slower -- instruction fetch, not
+// latency, is what this kernel waits for.
+#ifndef SCB_MPC_UNROLL
+#define SCB_MPC_UNROLL 1
+#endif
+#define SCB_PRAGMA_(x) _Pragma(#x)
+#define SCB_PRAGMA(x) SCB_PRAGMA_(x)
+#if defined(__CUDACC__)
+#define SCB_LANE_UNROLL SCB_PRAGMA(unroll SCB_MPC_UNROLL)
+#define SCB_LOOP SCB_PRAGMA(unroll 1)
+#else
+#define SCB_LANE_UNROLL
+#define SCB_LOOP
+#endif
+
+// The MPC kernel is instruction-cache bound when everything is inlined (27 k SASS instructions = 430 KB with the
+// loops unrolled x4 ran 2.8x slower than 12.9 k): the phases that are called from several places are real
+// functions on the device, and the transcendental / reduction helpers exist once.
+// (SCB_PHASE, sincos_call, log_call: scb_core.cuh)
+
+// SCB_MPC_PHASE: the solver's phases; inline by default (out-of-line phases measured slower: cfg3 6.4 vs 5.2 ms,
+// `this` and the layout then live in local memory), -DSCB_MPC_PHASES_OUTLINE to compare.
+#if defined(SCB_MPC_PHASES_OUTLINE)
+#define SCB_MPC_PHASE SCB_PHASE
+#else
+#define SCB_MPC_PHASE SCB_HD
+#endif
+
+#ifndef SCB_MPC_OUTLINE_RED
+#define SCB_MPC_OUTLINE_RED 0
+#endif
+
 #ifndef SCB_MPC_STALL_BT
 #define SCB_MPC_STALL_BT 15
 #endif
@@ -316,6 +349,16 @@ struct MpcSolver {
     gauss_newton = false;
   }
 
+  // group reductions as real functions (20 call sites x a 5-step double-precision butterfly is ~1.7 k instructions inline)
+#if SCB_MPC_OUTLINE_RED
+#define SCB_MPC_RED SCB_PHASE
+#else
+#define SCB_MPC_RED SCB_HD
+#endif
+  static SCB_MPC_RED double gsum(double v) { return G::sum(v); }
+  static SCB_MPC_RED double gmin(double v) { return G::vmin(v); }
+  static SCB_MPC_RED double gmax(double v) { return -G::vmin(-v); }
+
   static SCB_HD void sync() {
 #if defined(__CUDA_ARCH__)
     if (LANES > 1) __syncwarp(G::gmask());
@@ -323,11 +366,12 @@ struct MpcSolver {
   }
 
   // ---- rollout + cost at the control sequence `z` (lane 0), states -> xs ----
-  SCB_HD double rollout(const double* z, double* xs) const {
+  SCB_MPC_PHASE double rollout(const double* z, double* xs) const {
     double Jc = 0.0;
     double x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xs[i];
+    SCB_LOOP
     for (int k = 0; k < H; ++k) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) { const double e = x[i] - goal[i]; Jc = fma(Qs[i] * e, e, Jc); }
@@ -352,7 +396,8 @@ struct MpcSolver {
   }
 
   // barrier points of every stage at (xs, z) -> w[L.PT]; CBF values -> dst[H*M]
-  SCB_HD void points_and_cbf(const double* z, const double* xs, double* dst) const {
+  SCB_MPC_PHASE void points_and_cbf(const double* z, const double* xs, double* dst) const {
+    SCB_LANE_UNROLL
     for (int k = lane; k < H; k += LANES) {
       double y[NY], F[NX], P1, Q1, P2, Q2;
 #pragma unroll
@@ -365,6 +410,7 @@ struct MpcSolver {
       pt[0] = y[0]; pt[1] = y[1]; pt[2] = P1; pt[3] = Q1; pt[4] = P2; pt[5] = Q2;
     }
     sync();
+    SCB_LANE_UNROLL
     for (int t = lane; t < H * M; t += LANES) {
       const int k = t / M, j = t - k * M;
       const double* pt = w + L.PT + k * 6;
@@ -401,7 +447,7 @@ struct MpcSolver {
     jscale(PY, y[1], 2.0 * w0); jaxpy(PY, PY, 2.0 * w1, Q1); jaxpy(PY, PY, 2.0 * w2, Q2);
   }
 
-  SCB_HD void stage_derivatives() {
+  SCB_MPC_PHASE void stage_derivatives() {
     const double* xs = w + L.X;
     const double* z = w + L.Z;
     if constexpr (Mod::LINEAR) {
@@ -409,6 +455,7 @@ struct MpcSolver {
       const double* aux = w + L.AUX;
       const double* R0 = aux + NX * NX + NX * NU;
       const double* R1 = R0 + NY;
+      SCB_LANE_UNROLL
       for (int k = lane; k < H; k += LANES) {
         double y[NY];
 #pragma unroll
@@ -432,6 +479,7 @@ struct MpcSolver {
     } else {
       // pass 0 (lanes over stages): the stage's sin/cos at the current iterate -> trig cache
       if constexpr (Mod::NTRIG > 0) {
+        SCB_LANE_UNROLL
         for (int k = lane; k < H; k += LANES) {
           double y[NY], F[NX], P1, Q1, P2, Q2;
 #pragma unroll
@@ -444,6 +492,7 @@ struct MpcSolver {
         sync();
       }
       // pass 1 (lanes over (stage, variable) pairs): column i of A_k / B_k and entry i of gE, gX, gY by entry jets
+      SCB_LANE_UNROLL
       for (int t = lane; t < H * NY; t += LANES) {
         const int k = t / NY, i = t - k * NY;
         JetG y[NY], F[NX], P1, Q1, P2, Q2;
@@ -471,7 +520,8 @@ struct MpcSolver {
   }
 
   // gradient of the input-rate term sum R (u_k - u_{k-1})^2 at z -> out[n]
-  SCB_HD void rate_gradient(const double* z, double* out) const {
+  SCB_MPC_PHASE void rate_gradient(const double* z, double* out) const {
+    SCB_LANE_UNROLL
     for (int t = lane; t < n; t += LANES) {
       const int k = t / NU, i = t - k * NU;
       const double um = (k == 0) ? uprev[i] : z[(k - 1) * NU + i];
@@ -483,12 +533,13 @@ struct MpcSolver {
   }
 
   // adjoint sweep: stage gradients gam[(H+1)*NY] -> z-gradient out[n]; costates -> w[L.MU] (lane 0)
-  SCB_HD void adjoint(const double* gam, double* out) {
+  SCB_MPC_PHASE void adjoint(const double* gam, double* out) {
     if (lane == 0) {
       double mu[NX];
       double* MU = w + L.MU;
 #pragma unroll
       for (int i = 0; i < NX; ++i) { mu[i] = gam[H * NY + i]; MU[H * NX + i] = mu[i]; }
+      SCB_LOOP
       for (int k = H - 1; k >= 0; --k) {
         const double* A = w + L.A + k * L.AS;
         const double* B = w + L.B + k * L.BS;
@@ -518,6 +569,7 @@ struct MpcSolver {
   // segmented xor-shuffle sum over the `seg` (power of two) consecutive lanes this lane belongs to
   static SCB_HD double seg_sum(double v, int seg) {
 #if defined(__CUDA_ARCH__)
+    SCB_LOOP
     for (int o = seg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(G::gmask(), v, o, 32);
 #endif
     (void)seg;
@@ -525,17 +577,19 @@ struct MpcSolver {
   }
 
   // mode 0: lambda sums only (dual residual / costates); 1: + sigma moments and Newton-rhs weights
-  SCB_HD void stage_sums(double mu_bar, bool with_rhs, double floor_s = 0.0) {
+  SCB_MPC_PHASE void stage_sums(double mu_bar, bool with_rhs, double floor_s = 0.0) {
     // A segment of `seg` lanes (smallest power of two >= M, capped at LANES) owns one stage at a time, so
     // LANES/seg stages are processed per pass and each of the <= 12 partial sums needs log2(seg) shuffle steps.
     int seg = 1;
     while (seg < M && seg < LANES) seg <<= 1;
     const int spp = LANES / seg;                       // stages per pass
     const int sub = lane / seg, jl = lane - sub * seg;
+    SCB_LOOP
     for (int k0 = 0; k0 < H; k0 += spp) {
       const int k = k0 + sub;
       double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, l0 = 0, l1 = 0, l2 = 0, r0 = 0, r1 = 0, r2 = 0;
       if (k < H) {
+        SCB_LOOP
         for (int j = jl; j < M; j += seg) {
           const double ox = w[L.OB + j * 3], oy = w[L.OB + j * 3 + 1];
           const double lam = w[L.L + k * M + j];
@@ -570,9 +624,10 @@ struct MpcSolver {
 
   // stage gradient for the dual residual / costates:  gam = grad l_k - sum lam grad g
   // (sign = +1)  or for the Newton rhs:  gam = -grad l_k + sum wt grad g   (sign = -1, weights 9..11)
-  SCB_HD void stage_gradients(bool rhs, double mu_bar) {
+  SCB_MPC_PHASE void stage_gradients(bool rhs, double mu_bar) {
     double* gam = w + L.GAM;
     const double* xs = w + L.X;
+    SCB_LANE_UNROLL
     for (int t = lane; t < (H + 1) * NY; t += LANES) {
       const int k = t / NY, i = t - k * NY;
       double v = 0.0;
@@ -588,6 +643,7 @@ struct MpcSolver {
     }
     sync();
     // simple bounds
+    SCB_LANE_UNROLL
     for (int q = lane; q < L.NS; q += LANES) {
       const SimpleCon c = decode_simple<NX, NU>(p, H, q);
       const double s = w[L.SS + q], lam = w[L.SL + q], is = w[L.SDS + q];
@@ -613,13 +669,14 @@ struct MpcSolver {
   }
 
   // stage Hessians G_k = hess l_k - sum lam hess c + sum sigma grad c grad c' + bound sigmas + costate curvature
-  SCB_HD void stage_hessians() {
+  SCB_MPC_PHASE void stage_hessians() {
     double* Gm = w + L.G;
     // All curvature of stage k is the Hessian of ONE scalar function of y,
     //   Psi_k = sum_c mu_{k+1,c} F_c(y) - Lam0 E(y) + LamX PX(y) + LamY PY(y)      (skipped in Gauss-Newton mode).
     // Lanes over (stage, packed Hessian entry) pairs: the curvature entry comes from an ENTRY jet (4 doubles per
     // quantity instead of a 28-double full jet, scb_jet.cuh) replaying the stage's cached sin/cos; the cost Hessian,
     // the barrier terms sum sigma grad c grad c' and the linear model's constant curvature are added in the same pass.
+    SCB_LANE_UNROLL
     for (int t = lane; t < (H + 1) * NH; t += LANES) {
       const int k = t / NH, e = t - k * NH;
       // unpack (i, j) of packed entry e
@@ -665,6 +722,7 @@ struct MpcSolver {
       Gm[t] = v;
     }
     sync();
+    SCB_LANE_UNROLL
     for (int q = lane; q < L.NS; q += LANES) {
       const SimpleCon c = decode_simple<NX, NU>(p, H, q);
       atomic_add_ws(Gm + c.k * NH + hidx<NY>(c.var, c.var), w[L.SL + q] * w[L.SDS + q]);
@@ -697,18 +755,20 @@ struct MpcSolver {
   // Lane c owns COLUMN c of the stage matrix M_k = Hs_k + F_k' P_{k+1} F_k (c < NV) and lane NV the vector
   // m_k = h_k + F_k' p_{k+1}: t_c = P f_c and M[:, c] = Hs[:, c] + F' t_c need no cross-lane data, so a stage is
   // two barriers (publish the input columns of M; publish P_k, K_k), everything else lives in registers.
-  SCB_HD bool riccati_backward(double delta) {
+  SCB_MPC_PHASE bool riccati_backward(double delta) {
     double* PM = w + L.PM;
     double* PV = w + L.PV;
     const double* gam = w + L.GAM;                  // = -grad l_k + sum w grad g  (the Newton rhs per stage)
     const double* z = w + L.Z;
     // terminal: P_H = G_H (x block), p_H = -gam_H
+    SCB_LANE_UNROLL
     for (int t = lane; t < NXT * NXT; t += LANES) {
       const int r = t / NXT, c = t - r * NXT;
       double v = 0.0;
       if (r < NX && c < NX) { const int lo = r < c ? r : c, hi = r < c ? c : r; v = w[L.G + H * NH + hidx<NY>(lo, hi)]; }
       PM[(H & 1) * NXT * NXT + t] = v;
     }
+    SCB_LANE_UNROLL
     for (int t = lane; t < NXT; t += LANES) PV[(H & 1) * NXT + t] = (t < NX) ? -gam[H * NY + t] : 0.0;
     sync();
     bool ok = true;
@@ -716,10 +776,12 @@ struct MpcSolver {
     double* FD = w + L.TM;                          // dense F_k            (NXT x NV)
     double* HS = FD + NXT * NV;                     // dense Hs_k           (NV x NV): stage Hessian + rate terms
     double* HV = HS + NV * NV;                      // h_k                  (NV)
+    SCB_LOOP
     for (int k = H - 1; k >= 0; --k) {
       const double* Pn = PM + ((k + 1) & 1) * NXT * NXT;
       const double* pn = PV + ((k + 1) & 1) * NXT;
       // (a) dense blocks of this stage, lanes over entries: afterwards every lane runs the SAME straight-line code
+      SCB_LANE_UNROLL
       for (int t = lane; t < NXT * NV + NV * NV + NV; t += LANES) {
         if (t < NXT * NV) {
           const int a2 = t / NV, c = t - a2 * NV;
@@ -758,6 +820,7 @@ struct MpcSolver {
       double Mc[NV];
 #pragma unroll
       for (int b2 = 0; b2 < NV; ++b2) Mc[b2] = 0.0;
+      SCB_LANE_UNROLL
       for (int c = lane; c <= NV; c += LANES) {     // (one pass: NV + 1 <= LANES on the device; sequential on the host)
         const bool isvec = (c == NV);
         const int cc = isvec ? 0 : c;
@@ -817,6 +880,7 @@ struct MpcSolver {
       double* Kf = w + L.KF + k * NU;
       double* Pk = PM + (k & 1) * NXT * NXT;
       double* pk = PV + (k & 1) * NXT;
+      SCB_LANE_UNROLL
       for (int c = lane; c <= NV; c += LANES) {
         if (c >= NXT && c < NV) continue;            // input columns carry no gain
         if (LANES == 1) {
@@ -860,11 +924,12 @@ struct MpcSolver {
   }
 
   // forward sweep: dz (inputs) and the stage directions dy_k = (dx_k, du_k)   (lane 0; O(H (nx+nu)^2))
-  SCB_HD void riccati_forward() {
+  SCB_MPC_PHASE void riccati_forward() {
     if (lane == 0) {
       double dxt[NXT];
 #pragma unroll
       for (int i = 0; i < NXT; ++i) dxt[i] = 0.0;
+      SCB_LOOP
       for (int k = 0; k < H; ++k) {
         const double* Kg = w + L.KG + k * NU * NXT;
         const double* Kf = w + L.KF + k * NU;
@@ -922,6 +987,7 @@ struct MpcSolver {
       sync();
     }
     // obstacles: (ox, oy, beta d^2); missing slots = the reference's dummy [1000, 1000, 0, ...] (mpc_cbf.py:346-364)
+    SCB_LANE_UNROLL
     for (int j = lane; j < M; j += LANES) {
       double ox = 1000.0, oy = 1000.0, r = 0.0;
       if (j < nobs) { ox = ld(obs + j * 7); oy = ld(obs + j * 7 + 1); r = ld(obs + j * 7 + 2); }
@@ -929,7 +995,9 @@ struct MpcSolver {
       w[L.OB + j * 3] = ox; w[L.OB + j * 3 + 1] = oy; w[L.OB + j * 3 + 2] = beta * d * d;
     }
     // cold start: u_k = u_prev (mpc_cbf.py:368-369)
+    SCB_LANE_UNROLL
     for (int t = lane; t < n; t += LANES) w[L.Z + t] = uprev[t % NU];
+    SCB_LANE_UNROLL
     for (int i = lane; i < NX; i += LANES) { w[L.X + i] = ld(x0 + i); w[L.XT + i] = w[L.X + i]; }
     sync();
     double Jcur = 0.0;
@@ -948,6 +1016,7 @@ struct MpcSolver {
     {
       stage_derivatives();
       double* gam = w + L.GAM;
+      SCB_LANE_UNROLL
       for (int t = lane; t < (H + 1) * NY; t += LANES) {
         const int k = t / NY, i = t - k * NY;
         gam[t] = (i < NX) ? 2.0 * Qs[i] * (w[L.X + k * NX + i] - goal[i]) : 0.0;
@@ -955,10 +1024,11 @@ struct MpcSolver {
       sync();
       adjoint(gam, w + L.RD);
       rate_gradient(w + L.Z, w + L.RG);
-      double gmax = 0.0;
-      for (int t = lane; t < n; t += LANES) gmax = fmax(gmax, fabs(w[L.RD + t] + w[L.RG + t]));
-      gmax = -G::vmin(-gmax);
-      const double sf = (gmax > 100.0) ? 100.0 / gmax : 1.0;
+      double g_abs = 0.0;
+      SCB_LANE_UNROLL
+      for (int t = lane; t < n; t += LANES) g_abs = fmax(g_abs, fabs(w[L.RD + t] + w[L.RG + t]));
+      g_abs = gmax(g_abs);
+      const double sf = (g_abs > 100.0) ? 100.0 / g_abs : 1.0;
 #pragma unroll
       for (int i = 0; i < NX; ++i) Qs[i] *= sf;
 #pragma unroll
@@ -974,7 +1044,9 @@ struct MpcSolver {
     // penalty-barrier merit  psi(z) = J(z) + sum_i rho(g_i(z)),  rho(g) = -mu log g  (g >= mu/nu), linear below.
     auto reset_slacks = [&](double floor_) {
       // s -> S, 1/s -> DS (the only division per constraint per iteration; everything else multiplies)
+      SCB_LANE_UNROLL
       for (int t = lane; t < H * M; t += LANES) w[L.DS + t] = 1.0 / fmax(w[L.C + t], floor_);
+      SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
         const double sv = fmax(simple_value(c, w + L.Z, w + L.X), floor_);
@@ -983,7 +1055,9 @@ struct MpcSolver {
       sync();
     };
     reset_slacks(mu_bar / nu_pen);
+    SCB_LANE_UNROLL
     for (int t = lane; t < H * M; t += LANES) w[L.L + t] = mu_bar * w[L.DS + t];
+    SCB_LANE_UNROLL
     for (int q = lane; q < L.NS; q += LANES) w[L.SL + q] = mu_bar * w[L.SDS + q];
     sync();
 
@@ -991,6 +1065,7 @@ struct MpcSolver {
     double err = kInf, err_best = kInf;
     const int max_iter = p.mpc_max_iter > 0 ? p.mpc_max_iter : 150;
     SCB_PH_INIT;
+    SCB_LOOP
     for (; it < max_iter; ++it) {
       stage_derivatives();
       SCB_PH(0);
@@ -1002,20 +1077,23 @@ struct MpcSolver {
       SCB_PH(2);
       // residuals (e_p = constraint violation, e_c = complementarity)
       double e_d = 0.0, e_p = 0.0, e_c = 0.0, e_cm = 0.0, lam_max = 0.0;
+      SCB_LANE_UNROLL
       for (int t = lane; t < n; t += LANES) e_d = fmax(e_d, fabs(w[L.RD + t] + w[L.RG + t]));
+      SCB_LANE_UNROLL
       for (int t = lane; t < H * M; t += LANES) {
         const double g = w[L.C + t], lam = w[L.L + t], sg = fmax(g, 0.0);
         e_p = fmax(e_p, -g); e_c = fmax(e_c, sg * lam); e_cm = fmax(e_cm, fabs(sg * lam - mu_bar));
         lam_max = fmax(lam_max, lam);
       }
+      SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
         const double g = simple_value(c, w + L.Z, w + L.X), lam = w[L.SL + q], sg = fmax(g, 0.0);
         e_p = fmax(e_p, -g); e_c = fmax(e_c, sg * lam); e_cm = fmax(e_cm, fabs(sg * lam - mu_bar));
         lam_max = fmax(lam_max, lam);
       }
-      e_d = -G::vmin(-e_d); e_p = -G::vmin(-e_p); e_c = -G::vmin(-e_c); e_cm = -G::vmin(-e_cm);
-      lam_max = -G::vmin(-lam_max);
+      e_d = gmax(e_d); e_p = gmax(e_p); e_c = gmax(e_c); e_cm = gmax(e_cm);
+      lam_max = gmax(lam_max);
       err = fmax(e_d, fmax(e_p, e_c));
       if (!(err == err) || !(lam_max < 1e200)) { st = SCB_NUMERICAL; break; }
       if (err <= tol) { st = SCB_OPTIMAL; break; }
@@ -1025,22 +1103,26 @@ struct MpcSolver {
       while (fmax(e_d, fmax(e_p, e_cm)) <= 10.0 * mu_bar && mu_bar > tol / 10.0) {
         mu_bar = fmax(tol / 10.0, fmin(0.2 * mu_bar, mu_bar * sqrt(mu_bar)));
         e_cm = 0.0;
+        SCB_LANE_UNROLL
         for (int t = lane; t < H * M; t += LANES) e_cm = fmax(e_cm, fabs(fmax(w[L.C + t], 0.0) * w[L.L + t] - mu_bar));
+        SCB_LANE_UNROLL
         for (int q = lane; q < L.NS; q += LANES) {
           const SimpleCon c = decode_simple<NX, NU>(p, H, q);
           e_cm = fmax(e_cm, fabs(fmax(simple_value(c, w + L.Z, w + L.X), 0.0) * w[L.SL + q] - mu_bar));
         }
-        e_cm = -G::vmin(-e_cm);
+        e_cm = gmax(e_cm);
       }
       nu_pen = fmax(nu_pen, 1.1 * lam_max);
       if (nu_pen > 1e12) { st = SCB_INFEASIBLE; break; }
       const double floor_s = mu_bar / nu_pen;
       reset_slacks(floor_s);
       // keep every multiplier within kappa_Sigma = 1e10 of mu/s (IPOPT's safeguard), using the fresh 1/s
+      SCB_LANE_UNROLL
       for (int t = lane; t < H * M; t += LANES) {
         const double c0 = mu_bar * w[L.DS + t];
         w[L.L + t] = fmin(fmax(w[L.L + t], 1e-10 * c0), 1e10 * c0);
       }
+      SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
         const double c0 = mu_bar * w[L.SDS + q];
         w[L.SL + q] = fmin(fmax(w[L.SL + q], 1e-10 * c0), 1e10 * c0);
@@ -1050,6 +1132,7 @@ struct MpcSolver {
       // Newton system: exact Lagrangian Hessian first; if the reduced matrix is not positive definite,
       // fall back to the Gauss-Newton stage Hessians (PSD by construction) before any diagonal shift
       stage_sums(mu_bar, true, floor_s);
+      SCB_PH(9);
       gauss_newton = false;
       stage_hessians();
       SCB_PH(4);
@@ -1071,11 +1154,11 @@ struct MpcSolver {
       SCB_PH(7);
       riccati_forward();
       SCB_PH(8);
-      SCB_PH(9);
       // linearised constraint change dg (stored in DS), multiplier direction, fraction to the boundary,
       // and the directional derivative of the merit
       const double tau = fmax(0.99, 1.0 - mu_bar);
       double ap = 1.0, ad = 1.0, dpsi = 0.0;
+      SCB_LANE_UNROLL
       for (int t = lane; t < H * M; t += LANES) {
         const int k = t / M, j = t - k * M;
         const double* ob = w + L.OB + j * 3;
@@ -1093,6 +1176,7 @@ struct MpcSolver {
         if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
         dpsi += (g >= floor_s) ? -mu_bar * dg / g : -nu_pen * dg;
       }
+      SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
         const SimpleCon c = decode_simple<NX, NU>(p, H, q);
         const double dg = c.sgn * w[L.DY + c.k * NY + c.var];
@@ -1103,38 +1187,44 @@ struct MpcSolver {
         if (dl < 0.0) ad = fmin(ad, -tau * lam / dl);
         dpsi += (g >= floor_s) ? -mu_bar * dg / g : -nu_pen * dg;
       }
-      ap = G::vmin(ap); ad = G::vmin(ad);
-      dpsi = G::sum(dpsi);
+      ap = gmin(ap); ad = gmin(ad);
+      dpsi = gsum(dpsi);
       SCB_PH(10);
       // directional derivative of the cost: grad J . dz = sum_k grad l_k . dy_k + rate_grad . dz
       double dJ = 0.0;
+      SCB_LANE_UNROLL
       for (int t = lane; t < (H + 1) * NX; t += LANES) {
         const int k = t / NX, i = t - k * NX;
         dJ = fma(2.0 * Qs[i] * (w[L.X + t] - goal[i]), w[L.DY + k * NY + i], dJ);
       }
+      SCB_LANE_UNROLL
       for (int t = lane; t < n; t += LANES) dJ = fma(w[L.RG + t], w[L.DZ + t], dJ);
-      dJ = G::sum(dJ);
+      dJ = gsum(dJ);
       dpsi += dJ;
-      const double rho_lin0 = -mu_bar * log(floor_s) + nu_pen * floor_s;     // rho(g) = rho_lin0 - nu g  below the floor
+      const double rho_lin0 = -mu_bar * log_call(floor_s) + nu_pen * floor_s;     // rho(g) = rho_lin0 - nu g  below the floor
       auto merit_terms = [&](const double* cb, const double* zz, const double* xx) {
         double acc = 0.0;
+        SCB_LANE_UNROLL
         for (int t = lane; t < H * M; t += LANES) {
           const double g = cb[t];
-          acc += (g >= floor_s) ? -mu_bar * log(g) : rho_lin0 - nu_pen * g;
+          acc += (g >= floor_s) ? -mu_bar * log_call(g) : rho_lin0 - nu_pen * g;
         }
+        SCB_LANE_UNROLL
         for (int q = lane; q < L.NS; q += LANES) {
           const SimpleCon c = decode_simple<NX, NU>(p, H, q);
           const double g = simple_value(c, zz, xx);
-          acc += (g >= floor_s) ? -mu_bar * log(g) : rho_lin0 - nu_pen * g;
+          acc += (g >= floor_s) ? -mu_bar * log_call(g) : rho_lin0 - nu_pen * g;
         }
-        return G::sum(acc);
+        return gsum(acc);
       };
       const double psi0 = merit_terms(w + L.C, w + L.Z, w + L.X) + Jcur;
       SCB_PH(11);
       // backtracking
       double alpha = ap, Jt = Jcur;
       int bt = 0;
+      SCB_LOOP
       for (; bt < 20; ++bt) {
+        SCB_LANE_UNROLL
         for (int t = lane; t < n; t += LANES) w[L.ZT + t] = fma(alpha, w[L.DZ + t], w[L.Z + t]);
         sync();
         if (lane == 0) Jt = rollout(w + L.ZT, w + L.XT);
@@ -1158,13 +1248,17 @@ struct MpcSolver {
       tiny_steps = (alpha < 1e-10 || (bt >= SCB_MPC_STALL_BT && e_p <= 1e-9)) ? tiny_steps + 1 : 0;
       if (tiny_steps >= SCB_MPC_STALL_ITERS) { st = (e_p > 1e-6) ? SCB_INFEASIBLE : SCB_MAXITER; break; }
       // accept: z, x, g; multipliers move with their own step and are kept within kappa_Sigma of mu/g
+      SCB_LANE_UNROLL
       for (int t = lane; t < n; t += LANES) w[L.Z + t] = w[L.ZT + t];
+      SCB_LANE_UNROLL
       for (int t = lane; t < (H + 1) * NX; t += LANES) w[L.X + t] = w[L.XT + t];
       sync();
+      SCB_LANE_UNROLL
       for (int t = lane; t < H * M; t += LANES) {
         w[L.C + t] = w[L.CT + t];
         w[L.L + t] = fma(ad, w[L.DL + t], w[L.L + t]);
       }
+      SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
         w[L.SL + q] = fma(ad, w[L.SDL + q], w[L.SL + q]);
       }
@@ -1183,6 +1277,7 @@ struct MpcSolver {
       if (st == SCB_MAXITER && err > 1e-4) {
         // distinguish "did not converge" from "locally infeasible" by the primal residual
         double e_p = 0.0;
+        SCB_LOOP
         for (int t = 0; t < H * M; ++t) e_p = fmax(e_p, -w[L.C + t]);
         if (e_p > 1e-6) st = SCB_INFEASIBLE;
       }
