@@ -226,7 +226,7 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
     const int NXT = NX + NU, NV = NXT + NU;
     L.PM = take(2 * NXT * NXT); L.PV = take(2 * NXT);     // P_{k+1} / P_k ping-pong (slot k & 1)
     L.KG = take(H * NU * NXT); L.KF = take(H * NU);
-    L.TM = take(NXT * NV + NV * NV + NV); L.MM = take(NU * NV); L.MV = take(0);
+    L.TM = take(0); L.MM = take(NU * NV); L.MV = take(0);
     L.PT2 = take(SEQ ? (NV + 1) * NV : 0);
   }
   L.DY = take((H + 1) * NY);
@@ -310,6 +310,9 @@ SCB_HD void prof_add(int i, long long& tlast) {
 #define SCB_MPC_OUTLINE_RED 0
 #endif
 
+#ifndef SCB_MPC_NOPROGRESS
+#define SCB_MPC_NOPROGRESS 50
+#endif
 #ifndef SCB_MPC_STALL_BT
 #define SCB_MPC_STALL_BT 15
 #endif
@@ -755,6 +758,37 @@ struct MpcSolver {
   // Lane c owns COLUMN c of the stage matrix M_k = Hs_k + F_k' P_{k+1} F_k (c < NV) and lane NV the vector
   // m_k = h_k + F_k' p_{k+1}: t_c = P f_c and M[:, c] = Hs[:, c] + F' t_c need no cross-lane data, so a stage is
   // two barriers (publish the input columns of M; publish P_k, K_k), everything else lives in registers.
+  // Hs_k[b][c]: stage Hessian G_k on the (x, u_k) rows/cols + the input-rate terms coupling u_{k-1} and u_k (+ shift)
+  SCB_HD double hs_entry(int k, int b, int c, double delta) const {
+    const int yb = v2y(b), yc = v2y(c);
+    const int ub = (b >= NXT) ? b - NXT : (b >= NX ? b - NX : -1), uc = (c >= NXT) ? c - NXT : (c >= NX ? c - NX : -1);
+    double v = 0.0;
+    if (yb >= 0 && yc >= 0) { const int lo = yb < yc ? yb : yc, hi = yb < yc ? yc : yb; v = w[L.G + k * NH + hidx<NY>(lo, hi)]; }
+    if (ub >= 0 && ub == uc) {
+      double rr = 0.0;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
+      v += ((b >= NXT) == (c >= NXT)) ? rr : -rr;
+    }
+    if (b == c && b >= NXT) v += delta;
+    return v;
+  }
+  // h_k[b] = -(Newton rhs of the stage) + rate-term gradient
+  SCB_HD double hv_entry(int k, int b) const {
+    const int yb = v2y(b);
+    const int ub = (b >= NXT) ? b - NXT : (b >= NX ? b - NX : -1);
+    double v = (yb >= 0) ? -w[L.GAM + k * NY + yb] : 0.0;
+    if (ub >= 0) {
+      const double* z = w + L.Z;
+      double rr = 0.0, du = 0.0;
+#pragma unroll
+      for (int i = 0; i < NU; ++i)
+        if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
+      v += (b >= NXT) ? rr * du : -rr * du;
+    }
+    return v;
+  }
+
   SCB_MPC_PHASE bool riccati_backward(double delta) {
     double* PM = w + L.PM;
     double* PV = w + L.PV;
@@ -773,70 +807,44 @@ struct MpcSolver {
     sync();
     bool ok = true;
     double* MU_ = w + L.MM;                         // published input columns: MU_[i * NV + r] = M[r][NXT + i]
-    double* FD = w + L.TM;                          // dense F_k            (NXT x NV)
-    double* HS = FD + NXT * NV;                     // dense Hs_k           (NV x NV): stage Hessian + rate terms
-    double* HV = HS + NV * NV;                      // h_k                  (NV)
     SCB_LOOP
     for (int k = H - 1; k >= 0; --k) {
       const double* Pn = PM + ((k + 1) & 1) * NXT * NXT;
       const double* pn = PV + ((k + 1) & 1) * NXT;
-      // (a) dense blocks of this stage, lanes over entries: afterwards every lane runs the SAME straight-line code
-      SCB_LANE_UNROLL
-      for (int t = lane; t < NXT * NV + NV * NV + NV; t += LANES) {
-        if (t < NXT * NV) {
-          const int a2 = t / NV, c = t - a2 * NV;
-          FD[t] = fm(k, a2, c);
-        } else if (t < NXT * NV + NV * NV) {
-          const int e = t - NXT * NV, b2 = e / NV, c = e - b2 * NV;
-          const int yb = v2y(b2), yc = v2y(c);
-          const int ub = (b2 >= NXT) ? b2 - NXT : (b2 >= NX ? b2 - NX : -1), uc = (c >= NXT) ? c - NXT : (c >= NX ? c - NX : -1);
-          double v = 0.0;
-          if (yb >= 0 && yc >= 0) { const int lo = yb < yc ? yb : yc, hi = yb < yc ? yc : yb; v = w[L.G + k * NH + hidx<NY>(lo, hi)]; }
-          if (ub >= 0 && ub == uc) {
-            double rr = 0.0;
-#pragma unroll
-            for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
-            v += ((b2 >= NXT) == (c >= NXT)) ? rr : -rr;
-          }
-          if (b2 == c && b2 >= NXT) v += delta;
-          HS[e] = v;
-        } else {
-          const int b2 = t - NXT * NV - NV * NV;
-          const int yb = v2y(b2);
-          const int ub = (b2 >= NXT) ? b2 - NXT : (b2 >= NX ? b2 - NX : -1);
-          double v = (yb >= 0) ? -gam[k * NY + yb] : 0.0;
-          if (ub >= 0) {
-            double rr = 0.0, du = 0.0;
-#pragma unroll
-            for (int i = 0; i < NU; ++i)
-              if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
-            v += (b2 >= NXT) ? rr * du : -rr * du;
-          }
-          HV[b2] = v;
-        }
-      }
-      sync();
-      // (b) lane c: t = P f_c (or p), M[:, c] = Hs[:, c] + F' t  (or m = h + F' p)
+      const double* A = w + L.A + k * L.AS;         // A[a * NX + c]
+      const double* B = w + L.B + k * L.BS;         // B[a * NU + i]
+      // lane c: t = P f_c (or p), M[:, c] = Hs[:, c] + F' t  (or m = h + F' p), with F_k = [[A 0 B], [0 0 I]] used
+      // block-wise (no dense copy of F_k or Hs_k: a lane builds the 8 entries of its own column of Hs_k on the fly)
       double Mc[NV];
 #pragma unroll
       for (int b2 = 0; b2 < NV; ++b2) Mc[b2] = 0.0;
-      SCB_LANE_UNROLL
+      SCB_LOOP
       for (int c = lane; c <= NV; c += LANES) {     // (one pass: NV + 1 <= LANES on the device; sequential on the host)
         const bool isvec = (c == NV);
-        const int cc = isvec ? 0 : c;
+        const bool isx = (c < NX), isu = (c >= NXT && !isvec);
+        const int ci = isu ? c - NXT : 0, cx = isx ? c : 0;
+        double fcol[NX];                             // rows < NX of column c of F_k
+#pragma unroll
+        for (int a2 = 0; a2 < NX; ++a2) fcol[a2] = isx ? A[a2 * NX + cx] : (isu ? B[a2 * NU + ci] : 0.0);
         double tc[NXT];
 #pragma unroll
         for (int r = 0; r < NXT; ++r) {
-          double v = 0.0;
+          double v = isu ? Pn[r * NXT + NX + ci] : 0.0;
 #pragma unroll
-          for (int a2 = 0; a2 < NXT; ++a2) v = fma(Pn[r * NXT + a2], FD[a2 * NV + cc], v);
+          for (int a2 = 0; a2 < NX; ++a2) v = fma(Pn[r * NXT + a2], fcol[a2], v);
           tc[r] = isvec ? pn[r] : v;
         }
 #pragma unroll
         for (int b2 = 0; b2 < NV; ++b2) {
-          double v = isvec ? HV[b2] : HS[b2 * NV + cc];
+          double v = isvec ? hv_entry(k, b2) : hs_entry(k, b2, c, delta);
+          if (b2 < NX) {
 #pragma unroll
-          for (int a2 = 0; a2 < NXT; ++a2) v = fma(FD[a2 * NV + b2], tc[a2], v);
+            for (int a2 = 0; a2 < NX; ++a2) v = fma(A[a2 * NX + b2], tc[a2], v);
+          } else if (b2 >= NXT) {
+            v += tc[NX + (b2 - NXT)];
+#pragma unroll
+            for (int a2 = 0; a2 < NX; ++a2) v = fma(B[a2 * NU + (b2 - NXT)], tc[a2], v);
+          }
           Mc[b2] = v;
         }
         if (c >= NXT && !isvec) {
@@ -1098,7 +1106,7 @@ struct MpcSolver {
       if (!(err == err) || !(lam_max < 1e200)) { st = SCB_NUMERICAL; break; }
       if (err <= tol) { st = SCB_OPTIMAL; break; }
       if (err < 0.5 * err_best) { err_best = err; it_best = it; }
-      else if (it - it_best > 50) break;             // no progress for 50 iterations: give up
+      else if (it - it_best > SCB_MPC_NOPROGRESS) break;   // error not halved for that many iterations: give up
       // monotone barrier update (Fiacco-McCormick with IPOPT's kappa_mu = 0.2, theta_mu = 1.5, kappa_eps = 10)
       while (fmax(e_d, fmax(e_p, e_cm)) <= 10.0 * mu_bar && mu_bar > tol / 10.0) {
         mu_bar = fmax(tol / 10.0, fmin(0.2 * mu_bar, mu_bar * sqrt(mu_bar)));
