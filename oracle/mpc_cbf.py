@@ -44,6 +44,8 @@ MPC_PARAM = {   # mpc_cbf.py:19-39 (Q diag, R), 49-82 (alpha)
     "KinematicBicycle2D": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha1=0.1, alpha2=0.1),
     "KinematicBicycle2D_C3BF": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha=0.15),
     "Quad3D": dict(Q=[30, 30, 5, 20, 20, 1, 10, 10, 10, 20, 20, 1], R=[1, 1, 1, 1], alpha=0.15),
+    "DoubleIntegrator2D": dict(Q=[50, 50, 20, 20], R=[0.5, 0.5], alpha1=0.2, alpha2=0.2),
+    "Quad2D": dict(Q=[25, 25, 50, 10, 10, 50], R=[0.5, 0.5], alpha1=0.15, alpha2=0.15),
 }
 DUMMY = [1000.0, 1000.0, 0.0, 0.0, 0.0, 0.0, 0.0]
 
@@ -55,7 +57,7 @@ class TorchModel:
         self.s, self.dt, self.name = spec, dt, spec["model"]
         self.R = float(spec["radius"])
         n = self.name
-        self.nx, self.nu = {"SingleIntegrator2D": (2, 2), "Quad3D": (12, 4)}.get(n, (4, 2))
+        self.nx, self.nu = {"SingleIntegrator2D": (2, 2), "Quad3D": (12, 4), "Quad2D": (6, 2)}.get(n, (4, 2))
         if n == "Quad3D":
             L, nu, gr = spec["L"], spec["nu"], 9.8
             B2 = torch.tensor([[1, 1, 1, 1], [0, L, 0, -L], [L, 0, -L, 0], [nu, -nu, nu, -nu]], dtype=torch.float64)
@@ -74,6 +76,13 @@ class TorchModel:
             return u
         if n == "Quad3D":
             return x @ self.A.T + u @ self.B.T
+        if n == "DoubleIntegrator2D":                           # double_integrator2D.py:46-78
+            return torch.stack([x[:, 2], x[:, 3], u[:, 0], u[:, 1]], dim=1)
+        if n == "Quad2D":                                       # quad2D.py:46-85
+            m, I, r = self.s["mass"], self.s["inertia"], self.R
+            th, us = x[:, 2], u[:, 0] + u[:, 1]
+            return torch.stack([x[:, 3], x[:, 4], x[:, 5], -torch.sin(th) / m * us, -9.81 + torch.cos(th) / m * us,
+                                r / I * (u[:, 0] - u[:, 1])], dim=1)
         th, v = x[:, 2], x[:, 3]
         c, s = torch.cos(th), torch.sin(th)
         if n == "DynamicUnicycle2D":
@@ -95,6 +104,10 @@ class TorchModel:
             k3 = self.rhs(x + dt / 2 * k2, u); k4 = self.rhs(x + dt * k3, u)
             return x + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
         xn = self.euler(x, u)
+        if n == "DoubleIntegrator2D":                           # velocity rescaled to |v| <= v_max (:80-108)
+            vmag = torch.sqrt(xn[:, 2] ** 2 + xn[:, 3] ** 2)
+            sc = torch.where(vmag > self.s["v_max"], self.s["v_max"] / vmag, torch.ones_like(vmag))
+            xn = torch.cat([xn[:, :2], xn[:, 2:4] * sc[:, None]], dim=1)
         if n.startswith("KinematicBicycle2D"):
             v = torch.clamp(xn[:, 3], self.s["v_min"], self.s["v_max"])
             xn = torch.cat([xn[:, :3], v[:, None]], dim=1)
@@ -113,7 +126,7 @@ class TorchModel:
         beta = 1.1 if n == "KinematicBicycle2D" else 1.01
         dx, dy = x[:, 0:1] - obs[None, :, 0], x[:, 1:2] - obs[None, :, 1]
         circ = dx * dx + dy * dy - beta * (obs[None, :, 2] + self.R) ** 2
-        if n in ("SingleIntegrator2D", "DynamicUnicycle2D") and bool((obs[:, 6] >= 0.5).any()):
+        if n in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D") and bool((obs[:, 6] >= 0.5).any()):
             a = torch.clamp(obs[:, 2].abs(), min=1e-3); b = torch.clamp(obs[:, 3].abs(), min=1e-3)
             e = torch.clamp(obs[:, 4].abs(), min=2.0)
             ct, st = torch.cos(obs[:, 5]), torch.sin(obs[:, 5])
@@ -145,10 +158,14 @@ class OracleMPCCBF:
             lb, ub = [-s["a_max"], -s["w_max"]], [s["a_max"], s["w_max"]]
         elif self.name.startswith("KinematicBicycle2D"):
             lb, ub = [-s["a_max"], -s["beta_max"]], [s["a_max"], s["beta_max"]]
+        elif self.name == "DoubleIntegrator2D":                  # mpc_cbf.py:200-204
+            lb, ub = [-s["ax_max"], -s["ay_max"]], [s["ax_max"], s["ay_max"]]
+        elif self.name == "Quad2D":                              # mpc_cbf.py:212-216
+            lb, ub = [s["f_min"]] * 2, [s["f_max"]] * 2
         else:
             lb, ub = [s["u_min"]] * 4, [s["u_max"]] * 4
         self.u_lb, self.u_ub = np.array(lb, float), np.array(ub, float)
-        self.has_vbound = self.nx == 4
+        self.has_vbound = self.name == "DynamicUnicycle2D" or self.name.startswith("KinematicBicycle2D")
         self.status = "optimal"
 
     # ---- packing: w = [x_0..x_H | u_0..u_{H-1}] ----

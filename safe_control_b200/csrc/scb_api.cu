@@ -16,6 +16,8 @@ SCB_MPC_INSTANTIATE(SCB_SINGLE_INTEGRATOR_2D)
 SCB_MPC_INSTANTIATE(SCB_DYNAMIC_UNICYCLE_2D)
 SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D)
 SCB_MPC_INSTANTIATE(SCB_QUAD_3D)
+SCB_MPC_INSTANTIATE(SCB_DOUBLE_INTEGRATOR_2D)
+SCB_MPC_INSTANTIATE(SCB_QUAD_2D)
 }
 #else
 #include "scb_mpc_kernels.cuh"

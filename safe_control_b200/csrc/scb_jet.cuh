@@ -197,6 +197,7 @@ SCB_HD double jval(const JetG& a) { return a.v; }
 SCB_HD double jval(const JetH& a) { return a.v; }
 SCB_HD double jval(double a) { return a; }
 SCB_HD void jchain(double& r, const double&, double f0, double, double) { r = f0; }
+SCB_HD void jconst(double& r, double c) { r = c; }
 
 // sin/cos providers for the stage maps: compute, compute + remember, or replay the remembered values (the entry-jet
 // passes evaluate one stage many times at the same point; the transcendental is paid once per stage and iterate)

@@ -116,6 +116,65 @@ struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
   }
 };
 
+// DoubleIntegrator2D: f, g robots/double_integrator2D.py:46-78, step (rescales the velocity to |v| <= v_max) :80-108,
+// barrier_dt :223-272 (circle rows; rel. degree 2).  MPC weights / gains / bounds mpc_cbf.py:28-30, 60-63, 200-204.
+template <>
+struct MpcModel<SCB_DOUBLE_INTEGRATOR_2D> {
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 0;
+  static constexpr bool VBOUND = false, LINEAR = false;
+  static SCB_HD double beta() { return 1.01; }
+  // y = (px, py, vx, vy, ax, ay).  The model's own step scales (vx, vy) by v_max / |v| when |v| > v_max (CasADi
+  // if_else, :84-95); the positions after one own step are the Euler ones, after two they use the scaled velocity.
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR&) {
+    jaxpy(F[0], y[0], p.dt, y[2]);
+    jaxpy(F[1], y[1], p.dt, y[3]);
+    jaxpy(F[2], y[2], p.dt, y[4]);
+    jaxpy(F[3], y[3], p.dt, y[5]);
+    P1 = F[0]; Q1 = F[1];
+    T q, t, sc, v1x, v1y;
+    jmul(q, F[2], F[2]); jmul(t, F[3], F[3]); jaxpy(q, q, 1.0, t);       // |v_1|^2
+    const double qv = jval(q), vmax = p.v_max;
+    if (qv > vmax * vmax) {
+      const double r = 1.0 / sqrt(qv), r2 = r * r;                       // scale = v_max q^(-1/2)
+      jchain(sc, q, vmax * r, -0.5 * vmax * r * r2, 0.75 * vmax * r * r2 * r2);
+      jmul(v1x, F[2], sc); jmul(v1y, F[3], sc);
+    } else {
+      v1x = F[2]; v1y = F[3];
+    }
+    jaxpy(P2, P1, p.dt, v1x);
+    jaxpy(Q2, Q1, p.dt, v1y);
+  }
+};
+
+// Quad2D: f, g robots/quad2D.py:46-85 (x, z, theta, xdot, zdot, thetadot; two rotor forces), step = Euler + wrap :87-90,
+// barrier_dt :178-203 (circle rows on (x, z); rel. degree 2).  MPC weights / gains / bounds mpc_cbf.py:34-36, 74-77, 212-216.
+template <>
+struct MpcModel<SCB_QUAD_2D> {
+  static constexpr int NX = 6, NU = 2, NY = 8, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 1;
+  static constexpr bool VBOUND = false, LINEAR = false;
+  static SCB_HD double beta() { return 1.01; }
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
+    T s, c, usum, udif, sx, cz;
+    trig(s, c, y[2]);
+    jaxpy(usum, y[6], 1.0, y[7]);            // u_right + u_left
+    jaxpy(udif, y[6], -1.0, y[7]);           // u_right - u_left
+    jmul(sx, s, usum); jmul(cz, c, usum);
+    jaxpy(F[0], y[0], p.dt, y[3]);
+    jaxpy(F[1], y[1], p.dt, y[4]);
+    jaxpy(F[2], y[2], p.dt, y[5]);
+    jaxpy(F[3], y[3], -p.dt / p.mass, sx);
+    jaxpy(F[4], y[4], p.dt / p.mass, cz);
+    T gconst; jconst(gconst, -p.gravity * p.dt);
+    jaxpy(F[4], F[4], 1.0, gconst);
+    jaxpy(F[5], y[5], p.dt * p.radius / p.Iy, udif);
+    P1 = F[0]; Q1 = F[1];
+    jaxpy(P2, P1, p.dt, F[3]);
+    jaxpy(Q2, Q1, p.dt, F[4]);
+  }
+};
+
 // Quad3D: linear 12-state model xdot = A x + B u (robots/quad3D.py:81-97); the MPC uses plain Euler
 // (mpc_cbf.py:135-141) while the barrier uses the model's own RK4 step (quad3D.py:121-158, 275-297), which for a
 // linear system is the constant affine map x1 = Ad x + Bd u.  Relative degree 1: cbf = d_h + alpha h_k.  Because
@@ -984,7 +1043,8 @@ struct MpcSolver {
   // (stage, obstacle) pair at the cold start (-> w[L.C]).  Returns the unscaled objective.  Split from solve() so
   // the CPU host-sim can compare the kernel's own statement (Euler map, stage cost, CBF rows) with the values the
   // reference's mpc_cbf.py hands to do-mpc (tests/golden/ref_mpc_statement.npz).
-  SCB_HD double init(int nobs, const double* x0, const double* goal_in, int ngoal, const double* up, const double* obs) {
+  SCB_HD double init(int nobs, const double* x0, const double* goal_in, int ngoal, const double* up, const double* obs,
+                     bool push_start = true) {
 #pragma unroll
     for (int i = 0; i < NX; ++i) goal[i] = (i < ngoal) ? ld(goal_in + i) : 0.0;      // goal padded with zeros (mpc_cbf.py:267)
 #pragma unroll
@@ -1004,7 +1064,17 @@ struct MpcSolver {
     }
     // cold start: u_k = u_prev (mpc_cbf.py:368-369)
     SCB_LANE_UNROLL
-    for (int t = lane; t < n; t += LANES) w[L.Z + t] = uprev[t % NU];
+    for (int t = lane; t < n; t += LANES) {
+      // ... moved strictly inside the input box the way IPOPT does before its first iteration (bound_push =
+      // bound_frac = 1e-2): Quad2D's u_prev = 0 start violates f_min <= u, and a start ON a bound has no interior.
+      const int i = t % NU;
+      double lb = 0.0, ub = 0.0, u0 = 0.0;
+#pragma unroll
+      for (int m = 0; m < NU; ++m) if (m == i) { lb = p.u_lb[m]; ub = p.u_ub[m]; u0 = uprev[m]; }
+      const double pl = fmin(1e-2 * fmax(1.0, fabs(lb)), 1e-2 * (ub - lb));
+      const double pu = fmin(1e-2 * fmax(1.0, fabs(ub)), 1e-2 * (ub - lb));
+      w[L.Z + t] = push_start ? fmax(lb + pl, fmin(u0, ub - pu)) : u0;    // (false: the statement probes of the tests)
+    }
     SCB_LANE_UNROLL
     for (int i = lane; i < NX; i += LANES) { w[L.X + i] = ld(x0 + i); w[L.XT + i] = w[L.X + i]; }
     sync();

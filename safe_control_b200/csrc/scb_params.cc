@@ -107,14 +107,21 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       break;
     }
     case SCB_DOUBLE_INTEGRATOR_2D:                     // double_integrator2D.py:40-44, cbf_qp.py:18-20,66-69
-      if (!qp) return SCB_ERR_UNSUPPORTED;             // optimal decay raises NotCompatibleError; MPC: not built
+      if (od) return SCB_ERR_UNSUPPORTED;              // optimal decay raises NotCompatibleError
       p->u_lb[0] = p->u_lb[1] = -1.0; p->u_ub[0] = p->u_ub[1] = 1.0;
       p->v_max = 1.0; p->v_min = -1.0;
       p->alpha1 = p->alpha2 = 1.5;
+      if (mpc) {                                       // mpc_cbf.py:28-30, 60-63
+        p->alpha1 = p->alpha2 = 0.2;
+        p->Q[0] = p->Q[1] = 50; p->Q[2] = p->Q[3] = 20; p->R[0] = p->R[1] = 0.5;
+      }
       break;
     case SCB_QUAD_2D:                                  // quad2D.py:40-46, cbf_qp.py:30-32,74-79, optimal_decay_cbf_qp.py:38-45
-      if (mpc) return SCB_ERR_UNSUPPORTED;             // MPC: not built
       p->mass = 1.0; p->Iy = 0.01; p->gravity = 9.81;
+      if (mpc) {                                       // mpc_cbf.py:34-36, 74-77
+        p->alpha1 = p->alpha2 = 0.15;
+        p->Q[0] = p->Q[1] = 25; p->Q[2] = 50; p->Q[3] = p->Q[4] = 10; p->Q[5] = 50; p->R[0] = p->R[1] = 0.5;
+      }
       p->u_lb[0] = p->u_lb[1] = 1.0; p->u_ub[0] = p->u_ub[1] = 10.0;
       if (qp) p->alpha1 = p->alpha2 = 1.5;
       if (od) { p->alpha1 = p->alpha2 = 0.5; p->omega1_0 = p->omega2_0 = 1.0; p->p_sb1 = p->p_sb2 = 1e4; }

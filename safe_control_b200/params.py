@@ -67,8 +67,11 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
     elif model == "DoubleIntegrator2D":                       # double_integrator2D.py:40-44
         a = float(s.setdefault("a_max", 1.0)); v = float(s.setdefault("v_max", 1.0))
         s.setdefault("ax_max", a); s.setdefault("ay_max", a); s.setdefault("w_max", 0.5)
-        p.u_lb[0] = p.u_lb[1] = -a
+        p.u_lb[0] = p.u_lb[1] = -a                              # cbf_qp.py:66-69 bounds both inputs by a_max
         p.u_ub[0] = p.u_ub[1] = a
+        if controller == "mpc_cbf":                             # mpc_cbf.py:200-204 uses ax_max / ay_max
+            ax, ay = float(s["ax_max"]), float(s["ay_max"])
+            p.u_lb[0], p.u_ub[0], p.u_lb[1], p.u_ub[1] = -ax, ax, -ay, ay
         p.v_max = v; p.v_min = -v
     elif model == "Quad2D":                                   # quad2D.py:40-46
         p.mass = float(s.setdefault("mass", 1.0)); p.Iy = float(s.setdefault("inertia", 0.01))

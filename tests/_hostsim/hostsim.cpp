@@ -119,6 +119,8 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
       MPCCASE(SCB_DYNAMIC_UNICYCLE_2D)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D)
       MPCCASE(SCB_QUAD_3D)
+      MPCCASE(SCB_DOUBLE_INTEGRATOR_2D)
+      MPCCASE(SCB_QUAD_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -137,7 +139,7 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
     const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, true, Mod::NTRIG>(1, M);               \
     std::vector<double> ws(L.total, 0.0);                                                                       \
     MpcSolver<MODEL, 1> s(*p, L, ws.data());                                                                    \
-    const double J = s.init(nobs, x, goal, Mod::NGOAL, u, obs);                                                 \
+    const double J = s.init(nobs, x, goal, Mod::NGOAL, u, obs, false);                                               \
     double term = 0.0;                                                                                          \
     for (int i = 0; i < Mod::NX; ++i) {                                                                         \
       x_next[i] = ws[L.X + Mod::NX + i];                                                                        \
@@ -151,6 +153,8 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
     STCASE(SCB_DYNAMIC_UNICYCLE_2D)
     STCASE(SCB_KINEMATIC_BICYCLE_2D)
     STCASE(SCB_QUAD_3D)
+    STCASE(SCB_DOUBLE_INTEGRATOR_2D)
+    STCASE(SCB_QUAD_2D)
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;

@@ -35,6 +35,8 @@ def solve(ctrl, sc, goal, **kw):
     ("SingleIntegrator2D", 128, 10, 16, False, 12),
     ("Quad3D", 160, 10, 64, False, 8),                 # config-5's third model family
     ("Quad3D", 64, 8, 16, True, 8),
+    ("DoubleIntegrator2D", 256, 10, 16, False, 16),    # the remaining circle-barrier MPC models
+    ("Quad2D", 192, 8, 16, False, 12),
 ])
 def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     from safe_control_b200 import BatchedMPCCBF, scenes
@@ -57,8 +59,23 @@ def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     ok = out["status"] == 0
     np.testing.assert_allclose(px[:, 0], sc["X"], atol=0)
     assert np.abs(pu[ok][:, 0] - U[ok]).max() < 1e-12
-    if ctrl.nx == 4:
+    if model in ("DynamicUnicycle2D", "KinematicBicycle2D"):          # |x_k[3]| <= v_max (mpc_cbf.py:194-195, 206-207)
         assert (np.abs(px[ok][:, :, 3]) <= ctrl.params.v_max + 1e-7).all()
+
+
+def test_mpc_schedule_does_not_change_results():
+    """The hardest-first schedule (scb_mpccbf_solve_ws + workspace) only reorders when agents START: every agent's
+    output must be bit-identical to the index-order launch (scb_mpccbf_solve), and the launch count says which ran."""
+    from safe_control_b200 import BatchedMPCCBF, scenes
+    N, H, M = 3000, 8, 16                                             # more agents than one persistent wave
+    sc = scenes.make_scene("DynamicUnicycle2D", N, M, seed=77)
+    ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
+    a = solve(ctrl, sc, sc["goal"]); n_sched = ctrl.launches
+    ctrl.schedule = False
+    b = solve(ctrl, sc, sc["goal"]); n_plain = ctrl.launches - n_sched
+    assert (n_sched, n_plain) == (3, 1)
+    for k in ("U", "status", "iters", "pred_u", "pred_x", "kkt"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
 def test_mpc_track_mask_and_host_path():

@@ -6,7 +6,8 @@ import numpy as np, torch
 from safe_control_b200 import BatchedMPCCBF, scenes
 t = lambda a: torch.from_numpy(a).cuda()
 CASES = {"cfg3": ("DynamicUnicycle2D", 4096, 16, 8), "du5": ("DynamicUnicycle2D", 2731, 64, 10),
-         "kb5": ("KinematicBicycle2D", 2731, 64, 10), "q5": ("Quad3D", 2730, 64, 10), "si": ("SingleIntegrator2D", 4096, 16, 10)}
+         "kb5": ("KinematicBicycle2D", 2731, 64, 10), "q5": ("Quad3D", 2730, 64, 10), "si": ("SingleIntegrator2D", 4096, 16, 10),
+         "di": ("DoubleIntegrator2D", 4096, 16, 10), "q2d": ("Quad2D", 4096, 16, 10)}
 for name in (sys.argv[1:] or ["cfg3", "du5", "kb5", "q5"]):
     model, N, M, H = CASES[name]
     sc = scenes.make_scene(model, N, M, seed=1234)
