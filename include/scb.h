@@ -67,7 +67,8 @@ enum scb_model {
   SCB_DOUBLE_INTEGRATOR_2D = 5,     /* robots/double_integrator2D.py        (QP paths) */
   SCB_QUAD_2D = 6,                  /* robots/quad2D.py                      (QP paths) */
   SCB_KINEMATIC_BICYCLE_2D_DPCBF = 7,/* dynamic_env/kinematic_bicycle2D_dpcbf.py (cbf_qp + closed loop) */
-  SCB_NUM_MODELS = 8
+  SCB_UNICYCLE_2D = 8,              /* robots/unicycle2D.py (cbf_qp, mpc_cbf) */
+  SCB_NUM_MODELS = 9
 };
 
 enum scb_status { SCB_OPTIMAL = 0, SCB_INFEASIBLE = 1, SCB_MAXITER = 2, SCB_NUMERICAL = 3 };

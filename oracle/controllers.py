@@ -14,11 +14,12 @@ import numpy as np
 from .models import make_model, angle_normalize
 from .qp_exact import solve_qp_exact, OPTIMAL
 
-REL1 = ("SingleIntegrator2D", "KinematicBicycle2D_C3BF", "KinematicBicycle2D_DPCBF", "Quad3D")
+REL1 = ("SingleIntegrator2D", "Unicycle2D", "KinematicBicycle2D_C3BF", "KinematicBicycle2D_DPCBF", "Quad3D")
 REL2 = ("DynamicUnicycle2D", "KinematicBicycle2D", "DoubleIntegrator2D", "Quad2D")
 
 CBFQP_ALPHA = {                       # cbf_qp.py:12-35
     "SingleIntegrator2D": dict(alpha=1.0),
+    "Unicycle2D": dict(alpha=1.0),
     "DynamicUnicycle2D": dict(alpha1=1.5, alpha2=1.5),
     "KinematicBicycle2D": dict(alpha1=1.5, alpha2=1.5),
     "KinematicBicycle2D_C3BF": dict(alpha=1.5),

@@ -22,7 +22,8 @@ import numpy as np
 
 MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D",
           "KinematicBicycle2D_C3BF", "Quad3D")
-MODELS_QP_EXTRA = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")     # SURVEY 8f-2 (QP paths only)
+MODELS_QP_EXTRA = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")     # SURVEY 8f-2, second fixture set
+MODELS_EXTRA3 = ("Unicycle2D",)                                                     # third fixture set
 
 
 def angle_normalize(x):
@@ -43,6 +44,8 @@ def resolve_spec(robot_spec):
         s.setdefault("v_max", 1.0); s.setdefault("w_max", 0.5)
     elif model == "DynamicUnicycle2D":
         s.setdefault("a_max", 0.5); s.setdefault("w_max", 0.5); s.setdefault("v_max", 1.0)
+    elif model == "Unicycle2D":                               # unicycle2D.py:40-41
+        s.setdefault("v_max", 1.0); s.setdefault("w_max", 0.5)
     elif model == "DoubleIntegrator2D":                       # double_integrator2D.py:40-44
         s.setdefault("a_max", 1.0); s.setdefault("v_max", 1.0)
         s.setdefault("ax_max", s["a_max"]); s.setdefault("ay_max", s["a_max"]); s.setdefault("w_max", 0.5)
@@ -146,6 +149,59 @@ class SingleIntegrator2D(Model):
         x1 = self.step(x, u)
         hk = _h_dt_flag(x[0], x[1], obs, self.radius, self.beta)
         h1 = _h_dt_flag(x1[0], x1[1], obs, self.radius, self.beta)
+        return hk, h1 - hk
+
+
+class Unicycle2D(Model):
+    """robots/unicycle2D.py: X = [x, y, theta], U = [v, omega]; relative degree 1 through the sigma(s) term."""
+    nx, nu, rel_degree = 3, 2, 1
+    beta = 1.01
+    k1, k2 = 0.5, 1.8                                           # :36-37
+
+    def f(self, X): return np.zeros(3)                          # :43-51
+    def g(self, X):                                             # :53-63
+        return np.array([[math.cos(X[2]), 0.0], [math.sin(X[2]), 0.0], [0.0, 1.0]])
+
+    def step(self, X, U, wrap=True):                            # :65-68
+        Xn = X + (self.f(X) + self.g(X) @ U) * self.dt
+        if wrap:
+            Xn[2] = angle_normalize(Xn[2])
+        return Xn
+
+    def u_bounds(self):                                         # cbf_qp.py:58-61, mpc_cbf.py:188-192
+        v, w = self.spec["v_max"], self.spec["w_max"]
+        return np.array([-v, -w]), np.array([v, w])
+
+    def nominal_input(self, X, G, d_min=0.05, k_omega=2.0, k_v=1.0):     # :70-86
+        distance = max(np.linalg.norm(X[0:2] - np.asarray(G[0:2], float)) - d_min, 0.05)
+        theta_d = math.atan2(G[1] - X[1], G[0] - X[0])
+        err = angle_normalize(theta_d - X[2])
+        omega = k_omega * err
+        v = 0.0 if abs(err) > np.deg2rad(90) else k_v * distance * math.cos(err)
+        return np.array([v, omega])
+
+    def sigma(self, s):                                         # :100-102
+        return self.k2 * (math.exp(self.k1 - s) - 1) / (math.exp(self.k1 - s) + 1)
+
+    def sigma_der(self, s):                                     # :104-105
+        return -self.k2 * math.exp(self.k1 - s) / (1 + math.exp(self.k1 - s)) * (1 - self.sigma(s) / self.k2)
+
+    def agent_barrier(self, X, obs):
+        """-> h, dh_dx(3,)   (unicycle2D.py:107-125; circle only, the flag column is never read)"""
+        d = X[0:2] - obs[0:2]
+        c, s_ = math.cos(X[2]), math.sin(X[2])
+        h = d @ d - self.beta * (obs[2] + self.radius) ** 2
+        s = d[0] * c + d[1] * s_
+        h = h - self.sigma(s)
+        ds = self.sigma_der(s)
+        dh = np.array([2 * d[0] - ds * c, 2 * d[1] - ds * s_, -ds * (-s_ * d[0] + c * d[1])])
+        return h, dh
+
+    def barrier_dt(self, x, u, obs):
+        """-> h_k, d_h   (unicycle2D.py:127-145: plain circle h, no sigma term)"""
+        x1 = self.step(x, u)
+        hk = _circle_h(x[0], x[1], obs, self.radius, self.beta)
+        h1 = _circle_h(x1[0], x1[1], obs, self.radius, self.beta)
         return hk, h1 - hk
 
 
@@ -529,6 +585,7 @@ _REGISTRY = {
     "KinematicBicycle2D": KinematicBicycle2D,
     "KinematicBicycle2D_C3BF": KinematicBicycle2D_C3BF,
     "Quad3D": Quad3D,
+    "Unicycle2D": Unicycle2D,
     "DoubleIntegrator2D": DoubleIntegrator2D,
     "Quad2D": Quad2D,
     "KinematicBicycle2D_DPCBF": KinematicBicycle2D_DPCBF,

@@ -40,6 +40,7 @@ torch.set_default_dtype(torch.float64)
 
 MPC_PARAM = {   # mpc_cbf.py:19-39 (Q diag, R), 49-82 (alpha)
     "SingleIntegrator2D": dict(Q=[50, 50], R=[5, 5], alpha=0.05),
+    "Unicycle2D": dict(Q=[50, 50, 0.01], R=[0.5, 0.5], alpha=0.05),
     "DynamicUnicycle2D": dict(Q=[50, 50, 0.01, 30], R=[0.5, 0.5], alpha1=0.15, alpha2=0.15),
     "KinematicBicycle2D": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha1=0.1, alpha2=0.1),
     "KinematicBicycle2D_C3BF": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha=0.15),
@@ -57,7 +58,7 @@ class TorchModel:
         self.s, self.dt, self.name = spec, dt, spec["model"]
         self.R = float(spec["radius"])
         n = self.name
-        self.nx, self.nu = {"SingleIntegrator2D": (2, 2), "Quad3D": (12, 4), "Quad2D": (6, 2)}.get(n, (4, 2))
+        self.nx, self.nu = {"SingleIntegrator2D": (2, 2), "Quad3D": (12, 4), "Quad2D": (6, 2), "Unicycle2D": (3, 2)}.get(n, (4, 2))
         if n == "Quad3D":
             L, nu, gr = spec["L"], spec["nu"], 9.8
             B2 = torch.tensor([[1, 1, 1, 1], [0, L, 0, -L], [L, 0, -L, 0], [nu, -nu, nu, -nu]], dtype=torch.float64)
@@ -76,6 +77,8 @@ class TorchModel:
             return u
         if n == "Quad3D":
             return x @ self.A.T + u @ self.B.T
+        if n == "Unicycle2D":                                   # unicycle2D.py:43-63
+            return torch.stack([u[:, 0] * torch.cos(x[:, 2]), u[:, 0] * torch.sin(x[:, 2]), u[:, 1]], dim=1)
         if n == "DoubleIntegrator2D":                           # double_integrator2D.py:46-78
             return torch.stack([x[:, 2], x[:, 3], u[:, 0], u[:, 1]], dim=1)
         if n == "Quad2D":                                       # quad2D.py:46-85
@@ -154,6 +157,8 @@ class OracleMPCCBF:
         s = self.spec
         if self.name == "SingleIntegrator2D":
             lb, ub = [-s["v_max"]] * 2, [s["v_max"]] * 2
+        elif self.name == "Unicycle2D":                          # mpc_cbf.py:188-192
+            lb, ub = [-s["v_max"], -s["w_max"]], [s["v_max"], s["w_max"]]
         elif self.name == "DynamicUnicycle2D":
             lb, ub = [-s["a_max"], -s["w_max"]], [s["a_max"], s["w_max"]]
         elif self.name.startswith("KinematicBicycle2D"):

@@ -9,6 +9,7 @@ MODEL_IDS = {
     "Quad3D": 4,
     "DoubleIntegrator2D": 5,
     "Quad2D": 6,
+    "Unicycle2D": 8,
     "KinematicBicycle2D_DPCBF": 7,
 }
 MODEL_NAMES = {v: k for k, v in MODEL_IDS.items()}

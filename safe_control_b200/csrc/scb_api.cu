@@ -18,6 +18,7 @@ SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D)
 SCB_MPC_INSTANTIATE(SCB_QUAD_3D)
 SCB_MPC_INSTANTIATE(SCB_DOUBLE_INTEGRATOR_2D)
 SCB_MPC_INSTANTIATE(SCB_QUAD_2D)
+SCB_MPC_INSTANTIATE(SCB_UNICYCLE_2D)
 }
 #else
 #include "scb_mpc_kernels.cuh"
@@ -87,7 +88,7 @@ static int forced_lanes() {      // tuning override, read per call (no cached st
 static bool qp_model_ok(int m) {
   return m == SCB_SINGLE_INTEGRATOR_2D || m == SCB_DYNAMIC_UNICYCLE_2D || m == SCB_KINEMATIC_BICYCLE_2D ||
          m == SCB_KINEMATIC_BICYCLE_2D_C3BF || m == SCB_DOUBLE_INTEGRATOR_2D || m == SCB_QUAD_2D ||
-         m == SCB_KINEMATIC_BICYCLE_2D_DPCBF;
+         m == SCB_KINEMATIC_BICYCLE_2D_DPCBF || m == SCB_UNICYCLE_2D;
 }
 
 extern "C" {
@@ -126,6 +127,7 @@ int scb_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const dou
     case SCB_DOUBLE_INTEGRATOR_2D: cbfqp_rows_kernel<SCB_DOUBLE_INTEGRATOR_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
     case SCB_QUAD_2D: cbfqp_rows_kernel<SCB_QUAD_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
     case SCB_KINEMATIC_BICYCLE_2D_DPCBF: cbfqp_rows_kernel<SCB_KINEMATIC_BICYCLE_2D_DPCBF><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_UNICYCLE_2D: cbfqp_rows_kernel<SCB_UNICYCLE_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
   }
   CK(cudaGetLastError());
   return SCB_OK;
@@ -150,6 +152,7 @@ int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const do
     case SCB_DOUBLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_DOUBLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
     case SCB_QUAD_2D: rc = launch_cbfqp_m<SCB_QUAD_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
     case SCB_KINEMATIC_BICYCLE_2D_DPCBF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
   }
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
@@ -161,7 +164,7 @@ int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const do
                     long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
                     uint64_t* active, void* stream) {
   if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
-  if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D || p->model == SCB_DOUBLE_INTEGRATOR_2D ||
+  if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D || p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_UNICYCLE_2D ||
       p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF)
     return SCB_ERR_UNSUPPORTED;                        // optimal_decay_cbf_qp.py:51-52 raises NotCompatibleError
   if (!qp_model_ok(p->model)) return SCB_ERR_BAD_ARG;
@@ -255,7 +258,8 @@ static int track_check(const scb_params* p, const scb_track* t) {
       (t->K > 0 && !t->SCENE))
     return SCB_ERR_BAD_ARG;
   if (t->controller == SCB_CTRL_MPC_CBF && (!t->u_prev || !t->track_flag || t->H < 1)) return SCB_ERR_BAD_ARG;
-  if (p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_QUAD_2D) return SCB_ERR_UNSUPPORTED;   // loop laws not built yet
+  if (p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_QUAD_2D || p->model == SCB_UNICYCLE_2D)
+    return SCB_ERR_UNSUPPORTED;                        // loop laws not built yet
   if (t->controller != SCB_CTRL_MPC_CBF && p->model == SCB_QUAD_3D) return SCB_ERR_UNSUPPORTED;
   if (t->controller != SCB_CTRL_CBF_QP && p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF) return SCB_ERR_UNSUPPORTED;
   if (t->controller == SCB_CTRL_OPTIMAL_DECAY && p->model == SCB_SINGLE_INTEGRATOR_2D) return SCB_ERR_UNSUPPORTED;

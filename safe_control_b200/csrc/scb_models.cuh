@@ -13,6 +13,7 @@
 //   KinematicBicycle2D_DPCBF  dynamic_env/kinematic_bicycle2D_dpcbf.py:16-84
 //   DoubleIntegrator2D        robots/double_integrator2D.py:46-79, 167-222
 //   Quad2D                    robots/quad2D.py:46-82, 166-177
+//   Unicycle2D                robots/unicycle2D.py:43-63, 100-125
 // The arithmetic follows the reference's operation order where that is cheap, so rows
 // agree with the numpy path to a few ulp.  Quad3D has no continuous barrier
 // (quad3D.py:269-273) and is rejected on the host.
@@ -83,6 +84,38 @@ struct ModelCT<SCB_SINGLE_INTEGRATOR_2D> {
     }
     r.a[0] = d0; r.a[1] = d1;                                 // g = I, f = 0
     r.b = (p.cbf_mode == 1) ? h / p.dt : p.alpha * h;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Unicycle2D (robots/unicycle2D.py): X = [x, y, theta], U = [v, omega], f = 0, g = [[c, 0], [s, 0], [0, 1]].
+// h = |p - o|^2 - beta d^2 - sigma(s),  s = (p - o) . (c, s)   (:107-125): the sigma term is what gives omega a
+// non-zero coefficient (relative degree 1).  Circle obstacles only; the flag column is never read.
+// (The reference's own call path hands this model obstacle ROWS, on which its `obs[2][0]` raises IndexError --
+//  tracking.py:611-616 -> cbf_qp.py:156 -> unicycle2D.py:109; implemented is the intended column semantics, the
+//  fixtures in tests/golden/ref_*3.npz were generated by feeding the reference columns.)
+template <>
+struct ModelCT<SCB_UNICYCLE_2D> {
+  static constexpr int NX = 3, NU = 2;
+  static SCB_HD void prep(const scb_params&, const double* x, AgentCT& g) {
+    g.px = x[0]; g.py = x[1]; g.th = x[2];
+    sincos_pair(x[2], g.s, g.c);
+    g.v = 0.0; g.fx = 0.0; g.fy = 0.0;
+  }
+  static SCB_HD void row(const scb_params& p, const AgentCT& g, const double* o, RowOut& r) {
+    const double k1 = 0.5, k2 = 1.8;                          // :36-37
+    const double dx = g.px - o[0], dy = g.py - o[1];
+    const double dmin = o[2] + p.radius;
+    const double sv = dx * g.c + dy * g.s;
+    const double ex = exp(k1 - sv);
+    const double sig = k2 * (ex - 1.0) / (ex + 1.0);          // sigma(s)      :100-102
+    const double dsig = -k2 * ex / (1.0 + ex) * (1.0 - sig / k2);   // sigma'(s)  :104-105
+    const double h = ((dx * dx + dy * dy) - 1.01 * (dmin * dmin)) - sig;
+    const double d0 = 2.0 * dx - dsig * g.c, d1 = 2.0 * dy - dsig * g.s;
+    const double d2 = -dsig * (-g.s * dx + g.c * dy);
+    r.a[0] = d0 * g.c + d1 * g.s;                             // dh/dx g
+    r.a[1] = d2;
+    r.b = (p.cbf_mode == 1) ? h / p.dt : p.alpha * h;         // f = 0
   }
 };
 

@@ -58,6 +58,26 @@ struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
   }
 };
 
+// Unicycle2D: f = 0, g robots/unicycle2D.py:43-63, step = Euler + wrap :65-68, barrier_dt :127-145 (plain circle h, no
+// sigma term; rel. degree 1).  MPC weights / gain / bounds mpc_cbf.py:22-24, 53-55, 188-192.
+template <>
+struct MpcModel<SCB_UNICYCLE_2D> {
+  static constexpr int NX = 3, NU = 2, NY = 5, REL = 1, NGOAL = 2, AUX = 0, NTRIG = 1;
+  static constexpr bool VBOUND = false, LINEAR = false;
+  static SCB_HD double beta() { return 1.01; }
+  // y = (px, py, theta, v, omega)
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
+    T s, c, vc, vs;
+    trig(s, c, y[2]);
+    jmul(vc, y[3], c); jmul(vs, y[3], s);
+    jaxpy(F[0], y[0], p.dt, vc);
+    jaxpy(F[1], y[1], p.dt, vs);
+    jaxpy(F[2], y[2], p.dt, y[4]);
+    P1 = F[0]; Q1 = F[1]; P2 = F[0]; Q2 = F[1];
+  }
+};
+
 // DynamicUnicycle2D: f, g robots/dynamic_unicycle2D.py:42-73, step :75-78, barrier_dt :188-238
 template <>
 struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {

@@ -70,6 +70,9 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X,
     case SCB_QUAD_2D:
       return mpc_launch_m<SCB_QUAD_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
                                        pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
+    case SCB_UNICYCLE_2D:
+      return mpc_launch_m<SCB_UNICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
+                                           pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
     case SCB_QUAD_3D:
       return mpc_launch_m<SCB_QUAD_3D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
                                        pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);

@@ -46,6 +46,7 @@ int scb_model_dims(int model, int* nx, int* nu) {
     case SCB_DOUBLE_INTEGRATOR_2D:
     case SCB_KINEMATIC_BICYCLE_2D_DPCBF: x = 4; u = 2; break;
     case SCB_QUAD_2D: x = 6; u = 2; break;
+    case SCB_UNICYCLE_2D: x = 3; u = 2; break;
     default: return SCB_ERR_BAD_ARG;
   }
   if (nx) *nx = x;
@@ -77,6 +78,12 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       if (qp) p->alpha = 1.0;
       if (mpc) { p->alpha = 0.05; p->Q[0] = p->Q[1] = 50; p->R[0] = p->R[1] = 5; }
       if (od) return SCB_ERR_UNSUPPORTED;             // optimal_decay_cbf_qp.py:51-52 raises
+      break;
+    case SCB_UNICYCLE_2D:                              // unicycle2D.py:40-41, cbf_qp.py:14-15,58-61, mpc_cbf.py:22-24,53-55,188-192
+      if (od) return SCB_ERR_UNSUPPORTED;              // optimal_decay_cbf_qp.py has no Unicycle2D branch (raises)
+      p->u_lb[0] = -1.0; p->u_ub[0] = 1.0; p->u_lb[1] = -0.5; p->u_ub[1] = 0.5;
+      if (qp) p->alpha = 1.0;
+      if (mpc) { p->alpha = 0.05; p->Q[0] = p->Q[1] = 50; p->Q[2] = 0.01; p->R[0] = p->R[1] = 0.5; }
       break;
     case SCB_DYNAMIC_UNICYCLE_2D:
       p->u_lb[0] = -0.5; p->u_ub[0] = 0.5; p->u_lb[1] = -0.5; p->u_ub[1] = 0.5;

@@ -49,6 +49,9 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
         s.setdefault("w_max", 0.5)
         p.u_lb[0] = p.u_lb[1] = -v
         p.u_ub[0] = p.u_ub[1] = v
+    elif model == "Unicycle2D":                               # unicycle2D.py:40-41
+        v = float(s.setdefault("v_max", 1.0)); w = float(s.setdefault("w_max", 0.5))
+        p.u_lb[0], p.u_ub[0], p.u_lb[1], p.u_ub[1] = -v, v, -w, w
     elif model == "DynamicUnicycle2D":
         a = float(s.setdefault("a_max", 0.5)); w = float(s.setdefault("w_max", 0.5))
         v = float(s.setdefault("v_max", 1.0))

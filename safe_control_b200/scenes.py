@@ -19,10 +19,11 @@ ANGLE_UNPASSED = {   # tracking.py:352-357
     "SingleIntegrator2D": 2.0 * np.pi, "Quad3D": 2.0 * np.pi, "DynamicUnicycle2D": 1.2 * np.pi,
     "KinematicBicycle2D": 2.0 * np.pi, "KinematicBicycle2D_C3BF": 2.0 * np.pi,
     "KinematicBicycle2D_DPCBF": 2.0 * np.pi, "DoubleIntegrator2D": 2.0 * np.pi, "Quad2D": 2.0 * np.pi,
+    "Unicycle2D": 1.2 * np.pi,
 }
 BARRIER_BETA = {"SingleIntegrator2D": 1.01, "DynamicUnicycle2D": 1.01, "KinematicBicycle2D": 1.1,
                 "KinematicBicycle2D_C3BF": 1.1, "Quad3D": 1.01, "KinematicBicycle2D_DPCBF": 1.1,
-                "DoubleIntegrator2D": 1.01, "Quad2D": 1.01}
+                "DoubleIntegrator2D": 1.01, "Quad2D": 1.01, "Unicycle2D": 1.01}
 
 
 def angle_normalize(x):
@@ -40,6 +41,11 @@ def nominal_input(model, spec, X, goal, optimal_decay=False):
         mag = np.linalg.norm(err, axis=1, keepdims=True)
         vmax = spec["v_max"]
         return np.where(mag > vmax, err * vmax / np.maximum(mag, 1e-300), err)
+    if model == "Unicycle2D":                                  # unicycle2D.py:70-86
+        dist = np.maximum(np.linalg.norm(X[:, 0:2] - goal[:, 0:2], axis=1) - 0.05, 0.05)
+        err = angle_normalize(np.arctan2(goal[:, 1] - X[:, 1], goal[:, 0] - X[:, 0]) - X[:, 2])
+        v = np.where(np.abs(err) > np.deg2rad(90), 0.0, 1.0 * dist * np.cos(err))
+        return np.stack([v, 2.0 * err], axis=1)
     if model == "DynamicUnicycle2D":                           # dynamic_unicycle2D.py:80-104
         k_omega, k_a, k_v = (3.0, 0.5, 0.5) if optimal_decay else (2.0, 1.0, 1.0)
         k_omega = spec.get("nominal_k_omega", k_omega); k_a = spec.get("nominal_k_a", k_a)
@@ -115,6 +121,8 @@ def default_spec(model):
         s.update(v_max=1.0, w_max=0.5)
     elif model == "DynamicUnicycle2D":
         s.update(a_max=0.5, w_max=0.5, v_max=1.0)
+    elif model == "Unicycle2D":
+        s.update(v_max=1.0, w_max=0.5)
     elif model.startswith("KinematicBicycle2D"):
         dmax = math.radians(32)
         s.update(wheel_base=0.4, front_ax_dist=0.2, rear_ax_dist=0.2, v_max=3.5, a_max=5.0, delta_max=dmax,
@@ -151,7 +159,7 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
         pos[todo[ok]] = cand[ok]
         todo = todo[~ok]
     goal2 = rng.uniform(0, L, (N, 2))
-    nx = {"SingleIntegrator2D": 2, "Quad3D": 12, "Quad2D": 6}.get(model, 4)
+    nx = {"SingleIntegrator2D": 2, "Quad3D": 12, "Quad2D": 6, "Unicycle2D": 3}.get(model, 4)
     X = np.zeros((N, nx)); X[:, 0:2] = pos
     yaw = np.zeros(N)
     if model == "DoubleIntegrator2D":
@@ -172,6 +180,14 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
             dirn = d[np.arange(N), j]; dirn /= np.linalg.norm(dirn, axis=1, keepdims=True)
             X[:, 3:5] = dirn * rng.uniform(0.5, 1.5, (N, 1))
         yaw = X[:, 2].copy()
+        goal = goal2
+    elif model == "Unicycle2D":
+        theta = rng.uniform(-np.pi, np.pi, N)
+        if dense:   # head at the nearest obstacle
+            d = scene[None, :, 0:2] - pos[:, None, :]
+            j = np.argmin((d ** 2).sum(-1), axis=1)
+            theta = angle_normalize(np.arctan2(d[np.arange(N), j, 1], d[np.arange(N), j, 0]) + rng.normal(0, 0.2, N))
+        X[:, 2] = theta; yaw = theta
         goal = goal2
     elif nx == 4:
         theta = rng.uniform(-np.pi, np.pi, N)

@@ -55,6 +55,7 @@ int hostsim_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const
         ROWCASE(SCB_DOUBLE_INTEGRATOR_2D)
         ROWCASE(SCB_QUAD_2D)
         ROWCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+        ROWCASE(SCB_UNICYCLE_2D)
         default: return SCB_ERR_UNSUPPORTED;
       }
       for (int t = 0; t < p->nu; ++t) A[((size_t)i * M + r) * p->nu + t] = a[t];
@@ -75,6 +76,7 @@ int hostsim_cbfqp_solve(const scb_params* p, int N, int M, const double* X, cons
     case SCB_DOUBLE_INTEGRATOR_2D: run_cbfqp<SCB_DOUBLE_INTEGRATOR_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     case SCB_QUAD_2D: run_cbfqp<SCB_QUAD_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     case SCB_KINEMATIC_BICYCLE_2D_DPCBF: run_cbfqp<SCB_KINEMATIC_BICYCLE_2D_DPCBF, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
+    case SCB_UNICYCLE_2D: run_cbfqp<SCB_UNICYCLE_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;
@@ -121,6 +123,7 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
       MPCCASE(SCB_QUAD_3D)
       MPCCASE(SCB_DOUBLE_INTEGRATOR_2D)
       MPCCASE(SCB_QUAD_2D)
+      MPCCASE(SCB_UNICYCLE_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -155,6 +158,7 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
     STCASE(SCB_QUAD_3D)
     STCASE(SCB_DOUBLE_INTEGRATOR_2D)
     STCASE(SCB_QUAD_2D)
+    STCASE(SCB_UNICYCLE_2D)
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;

@@ -38,6 +38,7 @@ from safe_control.dynamic_env.kinematic_bicycle2D_c3bf import KinematicBicycle2D
 from safe_control.robots.quad3D import Quad3D  # noqa: E402
 from safe_control.robots.double_integrator2D import DoubleIntegrator2D  # noqa: E402
 from safe_control.robots.quad2D import Quad2D  # noqa: E402
+from safe_control.robots.unicycle2D import Unicycle2D  # noqa: E402
 from safe_control.dynamic_env.kinematic_bicycle2D_dpcbf import KinematicBicycle2D_DPCBF  # noqa: E402
 from safe_control.position_control.cbf_qp import CBFQP  # noqa: E402
 from safe_control.position_control.optimal_decay_cbf_qp import OptimalDecayCBFQP  # noqa: E402
@@ -51,9 +52,11 @@ MODEL_CLS = {
     "DoubleIntegrator2D": DoubleIntegrator2D,
     "Quad2D": Quad2D,
     "KinematicBicycle2D_DPCBF": KinematicBicycle2D_DPCBF,
+    "Unicycle2D": Unicycle2D,
 }
 BASE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D")
 EXTRA_MODELS = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")      # SURVEY 8f-2, second fixture set
+EXTRA3_MODELS = ("Unicycle2D",)                                                   # third fixture set
 DT = 0.05
 
 
@@ -82,6 +85,8 @@ def rand_state(rng, name):
         return rng.uniform(0, 10, 2)
     if name == "DynamicUnicycle2D":
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi), rng.uniform(0, 1.0)])
+    if name == "Unicycle2D":
+        return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi)])
     if name.startswith("KinematicBicycle2D"):
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi), rng.uniform(0.2, 3.5)])
     if name == "DoubleIntegrator2D":
@@ -99,6 +104,8 @@ def rand_input(rng, spec, name):
         return rng.uniform(-1, 1, 2)
     if name == "DynamicUnicycle2D":
         return rng.uniform(-0.5, 0.5, 2)
+    if name == "Unicycle2D":
+        return np.array([rng.uniform(-1, 1), rng.uniform(-0.5, 0.5)])
     if name.startswith("KinematicBicycle2D"):
         return np.array([rng.uniform(-5, 5), rng.uniform(-0.3, 0.3)])
     if name == "DoubleIntegrator2D":
@@ -146,7 +153,7 @@ def gen_models(rng, n=48, names=BASE_MODELS, fname="ref_models.npz"):
             F.append(np.asarray(fac.f(), float).reshape(-1))
             Gm.append(np.asarray(fac.g(), float))
             xc, uc = x.reshape(-1, 1).copy(), u.reshape(-1, 1)
-            if name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D", "Quad2D"):
+            if name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D", "Quad2D", "Unicycle2D"):
                 STEP.append(np.asarray(m.step(xc, uc), float).reshape(-1))
             else:
                 STEP.append(np.asarray(m.step(xc, uc, casadi=False), float).reshape(-1))
@@ -154,6 +161,8 @@ def gen_models(rng, n=48, names=BASE_MODELS, fname="ref_models.npz"):
                 NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2]), float).reshape(-1))
             elif name == "DoubleIntegrator2D":   # facade: (X, goal, d_min, k_v, k_a) (robots/robot.py:408-409)
                 NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2], 0.05, 1.0, 1.0), float).reshape(-1))
+            elif name == "Unicycle2D":           # facade: (X, goal, d_min, k_omega, k_v) (robots/robot.py:404-405)
+                NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2], 0.05, 2.0, 1.0), float).reshape(-1))
             elif name == "Quad2D":               # cascaded PD law, not on the solve path: not restated
                 NOM.append(np.full(2, np.nan))
             elif name == "Quad3D":
@@ -163,7 +172,8 @@ def gen_models(rng, n=48, names=BASE_MODELS, fname="ref_models.npz"):
             ct_rows, dt_rows = [], []
             for o in obs:
                 if name != "Quad3D":
-                    parts = fac.agent_barrier(o)
+                    # Unicycle2D.agent_barrier indexes obs[2][0] (unicycle2D.py:109): it only accepts COLUMN obstacles
+                    parts = fac.agent_barrier(o.reshape(-1, 1) if name == "Unicycle2D" else o)
                     ct_rows.append(np.concatenate([np.asarray(p, float).reshape(-1) for p in parts]))
                 parts = fac.agent_barrier_dt(x.reshape(-1, 1).copy(), u.reshape(-1, 1), o)
                 dt_rows.append(np.array([float(np.asarray(p).reshape(-1)[0]) for p in parts]))
@@ -198,7 +208,10 @@ def gen_cbfqp(rng, n=64, num_obs=6, cases=BASE_CBFQP, fname="ref_cbfqp.npz"):
             if k and name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D") and i % 4 == 0:
                 obs[0] = rand_superellipsoid(rng, x)
             u_ref = rand_input(rng, fac.robot_spec, name) * 1.3   # sometimes outside the box
-            u = ctrl.solve_control_problem(fac.X, {"u_ref": u_ref.reshape(-1, 1)}, obs)
+            # Unicycle2D: rows of a 2-D obstacle array crash its agent_barrier (obs[2][0] on a scalar), i.e. the
+            # reference's own tracking.py:611-616 call is dead for this model; feed the column form it expects
+            obs_arg = [o.reshape(-1, 1) for o in obs] if (name == "Unicycle2D" and obs is not None) else obs
+            u = ctrl.solve_control_problem(fac.X, {"u_ref": u_ref.reshape(-1, 1)}, obs_arg)
             pad = np.full((num_obs + 2, 7), np.nan)
             if k:
                 pad[:k] = obs
@@ -237,7 +250,7 @@ def gen_odcbf(rng, n=64, names=("KinematicBicycle2D_C3BF", "DynamicUnicycle2D", 
     np.savez_compressed(os.path.join(HERE, fname), **flat)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--third" not in sys.argv:
     rng = np.random.default_rng(20260925)
     gen_models(rng)
     gen_cbfqp(rng)
@@ -246,3 +259,13 @@ if __name__ == "__main__":
     gen_models(rng2, names=EXTRA_MODELS, fname="ref_models2.npz")
     gen_cbfqp(rng2, cases=EXTRA_CBFQP, fname="ref_cbfqp2.npz")
     gen_odcbf(rng2, names=("Quad2D",), fname="ref_odcbf2.npz")
+
+
+def third_set():
+    rng3 = np.random.default_rng(20261018)                   # third fixture set: Unicycle2D
+    gen_models(rng3, names=EXTRA3_MODELS, fname="ref_models3.npz")
+    gen_cbfqp(rng3, cases=[("Unicycle2D", {}), ("Unicycle2D", {"cbf_mode": "hard", "v_max": 2.0})], fname="ref_cbfqp3.npz")
+
+
+if __name__ == "__main__" and "--third" in sys.argv:
+    third_set()

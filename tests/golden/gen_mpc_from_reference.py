@@ -62,11 +62,14 @@ def probe(name, spec, x, u, goal, obs, M):
                 lterm_is_mterm=float(np.array_equal(mpc.objective["lterm"], mpc.objective["mterm"])))
 
 
-def main():
-    rng = np.random.default_rng(20261018)
+CASES2 = [("Unicycle2D", {}), ("Unicycle2D", {"mpc_horizon": 6, "mpc_cbf_alpha": 0.2, "w_max": 1.0})]   # second file
+
+
+def main(cases=CASES, seed=20261018, fname="ref_mpc_statement.npz"):
+    rng = np.random.default_rng(seed)
     M, n = 5, 24
     flat = {}
-    for name, spec in CASES:
+    for name, spec in cases:
         tag = name + ("" if not spec else "+" + ",".join(f"{k}={v}" for k, v in spec.items()))
         rows = {}
         for i in range(n):
@@ -85,8 +88,11 @@ def main():
         for kk, v in rows.items():
             flat[f"{tag}/{kk}"] = np.asarray(v)
         print(tag, "horizon", rows["horizon"][0], "R", rows["R"][0], "alphas", rows["alphas"][0], "min cbf", float(np.min(rows["cbf"])))
-    np.savez_compressed(os.path.join(HERE, "ref_mpc_statement.npz"), **flat)
+    np.savez_compressed(os.path.join(HERE, fname), **flat)
 
 
 if __name__ == "__main__":
-    main()
+    if "--second" in sys.argv:
+        main(CASES2, 20261019, "ref_mpc_statement2.npz")
+    else:
+        main()

@@ -72,7 +72,11 @@ def test_robot_spec_overrides(lib):
     with pytest.raises(NotCompatibleError):
         resolve_params({"model": "SingleIntegrator2D"}, "optimal_decay_cbf_qp")
     with pytest.raises(ValueError):
-        resolve_params({"model": "Unicycle2D"}, "cbf_qp")
+        resolve_params({"model": "VTOL2D"}, "mpc_cbf")            # not built
+    p, s = resolve_params({"model": "Unicycle2D", "w_max": 1.0}, "mpc_cbf")
+    assert (p.nx, p.nu, p.alpha, p.u_ub[1], p.Q[2]) == (3, 2, 0.05, 1.0, 0.01)
+    with pytest.raises(NotCompatibleError):
+        resolve_params({"model": "Unicycle2D"}, "optimal_decay_cbf_qp")
 
 
 def test_no_cpu_fallback():

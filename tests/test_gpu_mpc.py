@@ -37,6 +37,7 @@ def solve(ctrl, sc, goal, **kw):
     ("Quad3D", 64, 8, 16, True, 8),
     ("DoubleIntegrator2D", 256, 10, 16, False, 16),    # the remaining circle-barrier MPC models
     ("Quad2D", 192, 8, 16, False, 12),
+    ("Unicycle2D", 256, 10, 16, False, 16),
 ])
 def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     from safe_control_b200 import BatchedMPCCBF, scenes

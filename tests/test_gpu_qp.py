@@ -73,6 +73,7 @@ def test_reference_fixtures_odcbf():
     ("Quad2D", 16, True),
     ("KinematicBicycle2D_DPCBF", 16, True),
     ("KinematicBicycle2D_DPCBF", 8, False),
+    ("Unicycle2D", 16, True),              # third fixture set (sigma-shaped barrier, rel. degree 1)
 ])
 def test_scene_cbfqp_vs_oracle(model, M, dense):
     from safe_control_b200 import BatchedCBFQP, scenes

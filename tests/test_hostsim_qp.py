@@ -56,7 +56,8 @@ def test_reference_fixtures_odcbf():
 @pytest.mark.parametrize("model,dense", [("DynamicUnicycle2D", False), ("DynamicUnicycle2D", True),
                                          ("KinematicBicycle2D", True), ("KinematicBicycle2D_C3BF", True),
                                          ("SingleIntegrator2D", True), ("DoubleIntegrator2D", True),
-                                         ("Quad2D", True), ("KinematicBicycle2D_DPCBF", True)])
+                                         ("Quad2D", True), ("KinematicBicycle2D_DPCBF", True),
+                                         ("Unicycle2D", True), ("Unicycle2D", False)])
 def test_scene_cbfqp_vs_oracle(model, dense):
     M, N = 16, 160
     sc = scenes.make_scene(model, N, M, seed=1234, dense=dense)

@@ -7,16 +7,16 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from oracle.models import make_model, MODELS, MODELS_QP_EXTRA
+from oracle.models import make_model, MODELS, MODELS_QP_EXTRA, MODELS_EXTRA3
 from oracle.controllers import OracleCBFQP, OracleOptimalDecayCBFQP
 
 RTOL, ATOL = 1e-12, 1e-12
 
 
 def _load(fname):
-    """Both fixture sets: <name>.npz (round-1 models) and <name>2.npz (models added for SURVEY 8f-2)."""
+    """All fixture sets: <name>.npz (first models), <name>2.npz (DI / Quad2D / DPCBF), <name>3.npz (Unicycle2D)."""
     out = {}
-    for f in (fname, fname.replace(".npz", "2.npz")):
+    for f in (fname, fname.replace(".npz", "2.npz"), fname.replace(".npz", "3.npz")):
         path = os.path.join(GOLDEN, f)
         if not os.path.exists(path):
             continue
@@ -27,7 +27,7 @@ def _load(fname):
     return out
 
 
-@pytest.mark.parametrize("name", MODELS + MODELS_QP_EXTRA)
+@pytest.mark.parametrize("name", MODELS + MODELS_QP_EXTRA + MODELS_EXTRA3)
 def test_models_match_reference(name):
     d = _load("ref_models.npz")[name]
     m = make_model({"model": name})
@@ -74,7 +74,7 @@ def _spec_from_tag(tag):
 
 def test_cbfqp_matches_reference_end_to_end():
     data = _load("ref_cbfqp.npz")
-    assert len(data) == 11
+    assert len(data) == 13
     for tag, d in data.items():
         spec = _spec_from_tag(tag)
         num_obs = d["A"].shape[1]
@@ -110,7 +110,7 @@ def test_optimal_decay_matches_reference_end_to_end():
 # obstacle padding, input / state bounds, the rterm weights and the horizon.  do-mpc's transcription of these pieces
 # into the NLP (sum over stages + terminal cost, rterm on input increments) stays as documented in SURVEY.md 8a.
 MPC_ORACLE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D",
-                     "DoubleIntegrator2D", "Quad2D")
+                     "DoubleIntegrator2D", "Quad2D", "Unicycle2D")
 
 
 def test_mpc_statement_matches_reference():
@@ -163,4 +163,4 @@ def test_mpc_statement_matches_reference():
                 x2 = tm.own_step(x1, u); h2 = tm.h(x2, ob)
                 c = (h2 - 2 * h1 + h0) + (p["alpha1"] + p["alpha2"]) * (h1 - h0) + p["alpha1"] * p["alpha2"] * h0
             np.testing.assert_allclose(c[0].numpy(), d["cbf"][i], rtol=1e-9, atol=1e-9, err_msg=f"{tag} probe {i}")
-    assert seen == 8
+    assert seen == 10
