@@ -68,7 +68,9 @@ enum scb_model {
   SCB_QUAD_2D = 6,                  /* robots/quad2D.py                      (QP paths) */
   SCB_KINEMATIC_BICYCLE_2D_DPCBF = 7,/* dynamic_env/kinematic_bicycle2D_dpcbf.py (cbf_qp + closed loop) */
   SCB_UNICYCLE_2D = 8,              /* robots/unicycle2D.py (cbf_qp, mpc_cbf) */
-  SCB_NUM_MODELS = 9
+  SCB_MANIPULATOR_2D = 9,           /* robots/manipulator2D.py (cbf_qp: 3 inputs, 25 link-circle rows per obstacle;
+                                       M = CBFQP's num_obs = the ROW budget, cbf_qp.py:131-149) */
+  SCB_NUM_MODELS = 10
 };
 
 enum scb_status { SCB_OPTIMAL = 0, SCB_INFEASIBLE = 1, SCB_MAXITER = 2, SCB_NUMERICAL = 3 };

@@ -20,6 +20,7 @@ REL2 = ("DynamicUnicycle2D", "KinematicBicycle2D", "DoubleIntegrator2D", "Quad2D
 CBFQP_ALPHA = {                       # cbf_qp.py:12-35
     "SingleIntegrator2D": dict(alpha=1.0),
     "Unicycle2D": dict(alpha=1.0),
+    "Manipulator2D": dict(alpha=1.0),
     "DynamicUnicycle2D": dict(alpha1=1.5, alpha2=1.5),
     "KinematicBicycle2D": dict(alpha1=1.5, alpha2=1.5),
     "KinematicBicycle2D_C3BF": dict(alpha=1.5),
@@ -57,6 +58,17 @@ class OracleCBFQP:
             if r >= self.num_obs:
                 break
             obs = np.asarray(obs, float)
+            if self.name == "Manipulator2D":                  # several rows per obstacle (cbf_qp.py:131-149)
+                h_list, dh_list = m.agent_barrier(X, obs)
+                for h, dh in zip(h_list, dh_list):
+                    if r >= self.num_obs:
+                        break
+                    if self.mode == "hard":
+                        A[r] = dh @ m.g(X); b[r] = h / dt + dh @ m.f(X)
+                    else:
+                        A[r] = dh; b[r] = self.cbf_param["alpha"] * h
+                    r += 1
+                continue
             if self.name in REL1:
                 h, dh = m.agent_barrier(X, obs)
                 A[r] = dh @ m.g(X)

@@ -23,7 +23,7 @@ import numpy as np
 MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D",
           "KinematicBicycle2D_C3BF", "Quad3D")
 MODELS_QP_EXTRA = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")     # SURVEY 8f-2, second fixture set
-MODELS_EXTRA3 = ("Unicycle2D",)                                                     # third fixture set
+MODELS_EXTRA3 = ("Unicycle2D", "Manipulator2D")                                     # third fixture set
 
 
 def angle_normalize(x):
@@ -46,6 +46,8 @@ def resolve_spec(robot_spec):
         s.setdefault("a_max", 0.5); s.setdefault("w_max", 0.5); s.setdefault("v_max", 1.0)
     elif model == "Unicycle2D":                               # unicycle2D.py:40-41
         s.setdefault("v_max", 1.0); s.setdefault("w_max", 0.5)
+    elif model == "Manipulator2D":                            # manipulator2D.py:19-20
+        s.setdefault("w_max", 2.0); s.setdefault("Kp", 3.0)
     elif model == "DoubleIntegrator2D":                       # double_integrator2D.py:40-44
         s.setdefault("a_max", 1.0); s.setdefault("v_max", 1.0)
         s.setdefault("ax_max", s["a_max"]); s.setdefault("ay_max", s["a_max"]); s.setdefault("w_max", 0.5)
@@ -203,6 +205,83 @@ class Unicycle2D(Model):
         hk = _circle_h(x[0], x[1], obs, self.radius, self.beta)
         h1 = _circle_h(x1[0], x1[1], obs, self.radius, self.beta)
         return hk, h1 - hk
+
+
+class Manipulator2D(Model):
+    """robots/manipulator2D.py: 3-link planar arm, X = joint angles, U = joint velocities (q_dot = u).
+    agent_barrier returns one row PER LINK CIRCLE (25 per obstacle), cbf_qp.py:131-149 stacks them until its
+    num_obs rows are full."""
+    nx, nu, rel_degree = 3, 3, 1
+    beta = 1.3                                                   # agent_barrier's default (:189)
+    link_lengths = np.array([80, 70, 50]) / 60.0                 # :15-16
+    step_len = 10.0 / 60.0                                       # :126
+
+    def f(self, X): return np.zeros(3)                           # :24-27
+    def g(self, X): return np.eye(3)                             # :29-32
+    def step(self, X, U): return X + U * self.dt                 # :34-35
+
+    def u_bounds(self):                                          # cbf_qp.py:96-105: |u| <= w_max
+        w = self.spec["w_max"]; return np.full(3, -w), np.full(3, w)
+
+    def joints(self, X):                                         # get_joint_positions :46-53
+        P = [np.zeros(2)]; ang = 0.0
+        for i in range(3):
+            ang += X[i]
+            P.append(P[-1] + self.link_lengths[i] * np.array([math.cos(ang), math.sin(ang)]))
+        return P
+
+    def jacobian(self, X):                                       # get_jacobian :55-92
+        J = np.zeros((2, 3))
+        for i in range(3):
+            jx = jy = 0.0
+            ang = sum(X[k] for k in range(i))
+            for k in range(i, 3):
+                ang += X[k]
+                jx -= self.link_lengths[k] * math.sin(ang)
+                jy += self.link_lengths[k] * math.cos(ang)
+            J[0, i] = jx; J[1, i] = jy
+        return J
+
+    def nominal_input(self, X, G, d_min=0.05):                   # :94-108
+        ee = self.joints(X)[-1]
+        v = self.spec["Kp"] * (np.asarray(G, float).reshape(-1)[0:2] - ee)
+        om = self.jacobian(X).T @ v
+        return np.clip(om, -self.spec["w_max"], self.spec["w_max"])
+
+    def link_circles(self, X):                                   # get_link_circles :110-138 -> [(x, y, link_idx)]
+        out = []; p0 = np.zeros(2); ang = 0.0
+        for i in range(3):
+            ang += X[i]
+            d = self.link_lengths[i] * np.array([math.cos(ang), math.sin(ang)])
+            n = int(np.ceil(self.link_lengths[i] / self.step_len))       # 8, 8, 6 (7.000000000000001 -> 8)
+            for j in range(n + 1):
+                pos = p0 + (j / n) * d
+                out.append((pos[0], pos[1], i))
+            p0 = p0 + d
+        return out
+
+    def point_jacobian(self, X, pt, link_idx):                   # get_points_jacobian :140-160
+        J = np.zeros((2, 3)); P = [np.zeros(2)]; ang = 0.0
+        for i in range(link_idx + 1):
+            if i > 0:
+                ang += X[i - 1]
+                P.append(P[-1] + self.link_lengths[i - 1] * np.array([math.cos(ang), math.sin(ang)]))
+        for k in range(link_idx + 1):
+            J[0, k] = -(pt[1] - P[k][1]); J[1, k] = pt[0] - P[k][0]
+        return J
+
+    def agent_barrier(self, X, obs):
+        """-> h_list, dh_dx_list (25 each)   (manipulator2D.py:163-198)"""
+        hs, dhs = [], []
+        for cx, cy, li in self.link_circles(X):
+            d_min = self.radius + obs[2]
+            dx, dy = cx - obs[0], cy - obs[1]
+            hs.append(dx * dx + dy * dy - self.beta * d_min ** 2)
+            dhs.append(2 * np.array([dx, dy]) @ self.point_jacobian(X, (cx, cy), li))
+        return hs, dhs
+
+    def barrier_dt(self, x, u, obs):
+        raise NotImplementedError("Manipulator2D has no agent_barrier_dt (no MPC in the reference)")
 
 
 class DynamicUnicycle2D(Model):
@@ -586,6 +665,7 @@ _REGISTRY = {
     "KinematicBicycle2D_C3BF": KinematicBicycle2D_C3BF,
     "Quad3D": Quad3D,
     "Unicycle2D": Unicycle2D,
+    "Manipulator2D": Manipulator2D,
     "DoubleIntegrator2D": DoubleIntegrator2D,
     "Quad2D": Quad2D,
     "KinematicBicycle2D_DPCBF": KinematicBicycle2D_DPCBF,

@@ -10,6 +10,7 @@ MODEL_IDS = {
     "DoubleIntegrator2D": 5,
     "Quad2D": 6,
     "Unicycle2D": 8,
+    "Manipulator2D": 9,
     "KinematicBicycle2D_DPCBF": 7,
 }
 MODEL_NAMES = {v: k for k, v in MODEL_IDS.items()}

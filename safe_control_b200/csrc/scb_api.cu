@@ -88,7 +88,7 @@ static int forced_lanes() {      // tuning override, read per call (no cached st
 static bool qp_model_ok(int m) {
   return m == SCB_SINGLE_INTEGRATOR_2D || m == SCB_DYNAMIC_UNICYCLE_2D || m == SCB_KINEMATIC_BICYCLE_2D ||
          m == SCB_KINEMATIC_BICYCLE_2D_C3BF || m == SCB_DOUBLE_INTEGRATOR_2D || m == SCB_QUAD_2D ||
-         m == SCB_KINEMATIC_BICYCLE_2D_DPCBF || m == SCB_UNICYCLE_2D;
+         m == SCB_KINEMATIC_BICYCLE_2D_DPCBF || m == SCB_UNICYCLE_2D || m == SCB_MANIPULATOR_2D;
 }
 
 extern "C" {
@@ -128,6 +128,7 @@ int scb_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const dou
     case SCB_QUAD_2D: cbfqp_rows_kernel<SCB_QUAD_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
     case SCB_KINEMATIC_BICYCLE_2D_DPCBF: cbfqp_rows_kernel<SCB_KINEMATIC_BICYCLE_2D_DPCBF><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
     case SCB_UNICYCLE_2D: cbfqp_rows_kernel<SCB_UNICYCLE_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
+    case SCB_MANIPULATOR_2D: manip_rows_kernel<<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
   }
   CK(cudaGetLastError());
   return SCB_OK;
@@ -139,10 +140,21 @@ int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const do
   if (!qp_model_ok(p->model)) return p->model == SCB_QUAD_3D ? SCB_ERR_UNSUPPORTED : SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
-  LaunchGeom g;
-  if (!pick_geom(N, M + 2 * p->nu, sm_count_cached(), g, forced_lanes())) return SCB_ERR_TOO_LARGE;
   const int words = scb_active_words(M, p->nu);
   cudaStream_t s = (cudaStream_t)stream;
+  if (p->model == SCB_MANIPULATOR_2D) {                 // 3-input QP, warp per arm
+    const int rows = M + 6, need = (rows + 31) / 32;
+    const long blocks = ((long)N + 3) / 4, cap = (long)sm_count_cached() * 16;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    if (need <= 1) manipqp_kernel<1><<<grid, kBlock, 0, s>>>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    else if (need <= 2) manipqp_kernel<2><<<grid, kBlock, 0, s>>>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    else if (need <= 4) manipqp_kernel<4><<<grid, kBlock, 0, s>>>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    else return SCB_ERR_TOO_LARGE;
+    CK(cudaGetLastError());
+    return SCB_OK;
+  }
+  LaunchGeom g;
+  if (!pick_geom(N, M + 2 * p->nu, sm_count_cached(), g, forced_lanes())) return SCB_ERR_TOO_LARGE;
   int rc = SCB_ERR_BAD_ARG;
   switch (p->model) {
     case SCB_SINGLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_SINGLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
@@ -164,7 +176,7 @@ int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const do
                     long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
                     uint64_t* active, void* stream) {
   if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
-  if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D || p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_UNICYCLE_2D ||
+  if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D || p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_UNICYCLE_2D || p->model == SCB_MANIPULATOR_2D ||
       p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF)
     return SCB_ERR_UNSUPPORTED;                        // optimal_decay_cbf_qp.py:51-52 raises NotCompatibleError
   if (!qp_model_ok(p->model)) return SCB_ERR_BAD_ARG;
@@ -258,7 +270,8 @@ static int track_check(const scb_params* p, const scb_track* t) {
       (t->K > 0 && !t->SCENE))
     return SCB_ERR_BAD_ARG;
   if (t->controller == SCB_CTRL_MPC_CBF && (!t->u_prev || !t->track_flag || t->H < 1)) return SCB_ERR_BAD_ARG;
-  if (p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_QUAD_2D || p->model == SCB_UNICYCLE_2D)
+  if (p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_QUAD_2D || p->model == SCB_UNICYCLE_2D ||
+      p->model == SCB_MANIPULATOR_2D)
     return SCB_ERR_UNSUPPORTED;                        // loop laws not built yet
   if (t->controller != SCB_CTRL_MPC_CBF && p->model == SCB_QUAD_3D) return SCB_ERR_UNSUPPORTED;
   if (t->controller != SCB_CTRL_CBF_QP && p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF) return SCB_ERR_UNSUPPORTED;

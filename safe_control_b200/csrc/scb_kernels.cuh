@@ -37,6 +37,40 @@ cbfqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* _
   }
 }
 
+// Manipulator2D: warp per arm (rows = M link-circle rows + 6 box rows, RPL = ceil(rows / 32))
+template <int RPL>
+__global__ void __launch_bounds__(kBlock)
+manipqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
+               const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
+               const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
+               uint64_t* __restrict__ active, int words) {
+  constexpr int GPB = kBlock / 32;
+  for (long a = (long)blockIdx.x * GPB + threadIdx.x / 32; a < N; a += (long)gridDim.x * GPB)
+    manipqp_agent<32, RPL>(p, M, nobs ? nobs[a] : M, X + a * 3, Uref + a * 3, OBS + a * stride, U + a * 3, status + a,
+                           active ? active + a * words : nullptr, words);
+}
+
+__global__ void __launch_bounds__(256)
+manip_rows_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
+                  const double* __restrict__ OBS, long stride, const int32_t* __restrict__ nobs,
+                  double* __restrict__ A, double* __restrict__ b) {
+  const long total = (long)N * M;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const long a = t / M;
+    const int r = (int)(t - a * M);
+    int no = nobs ? nobs[a] : M;
+    no = no < 0 ? 0 : (no > M ? M : no);
+    double q[3];
+    for (int i = 0; i < 3; ++i) q[i] = __ldg(X + a * 3 + i);
+    ManipArm arm;
+    manip_prep(q, arm);
+    double av[3], bv;
+    manip_row<true>(p, arm, OBS + a * stride, no, r, av, bv);
+    for (int i = 0; i < 3; ++i) A[t * 3 + i] = av[i];
+    b[t] = bv;
+  }
+}
+
 template <int MODEL>
 __global__ void __launch_bounds__(256)
 cbfqp_rows_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,

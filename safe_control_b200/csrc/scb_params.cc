@@ -47,6 +47,7 @@ int scb_model_dims(int model, int* nx, int* nu) {
     case SCB_KINEMATIC_BICYCLE_2D_DPCBF: x = 4; u = 2; break;
     case SCB_QUAD_2D: x = 6; u = 2; break;
     case SCB_UNICYCLE_2D: x = 3; u = 2; break;
+    case SCB_MANIPULATOR_2D: x = 3; u = 3; break;
     default: return SCB_ERR_BAD_ARG;
   }
   if (nx) *nx = x;
@@ -78,6 +79,11 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       if (qp) p->alpha = 1.0;
       if (mpc) { p->alpha = 0.05; p->Q[0] = p->Q[1] = 50; p->R[0] = p->R[1] = 5; }
       if (od) return SCB_ERR_UNSUPPORTED;             // optimal_decay_cbf_qp.py:51-52 raises
+      break;
+    case SCB_MANIPULATOR_2D:                           // manipulator2D.py:19-20, cbf_qp.py:34-35, 96-105
+      if (!qp) return SCB_ERR_UNSUPPORTED;             // no agent_barrier_dt (no MPC), no optimal-decay branch
+      for (int i = 0; i < 3; ++i) { p->u_lb[i] = -2.0; p->u_ub[i] = 2.0; }
+      p->alpha = 1.0;
       break;
     case SCB_UNICYCLE_2D:                              // unicycle2D.py:40-41, cbf_qp.py:14-15,58-61, mpc_cbf.py:22-24,53-55,188-192
       if (od) return SCB_ERR_UNSUPPORTED;              // optimal_decay_cbf_qp.py has no Unicycle2D branch (raises)

@@ -110,6 +110,114 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
 }
 
 // ----------------------------------------------------------------------------------------
+// Manipulator2D CBF-QP (cbf_qp.py:96-105 problem, 131-149 rows): 3 joint velocities, |u_i| <= w_max, and one
+// row PER LINK CIRCLE of every obstacle (robots/manipulator2D.py:110-198): the arm is covered by circles every
+// 10/60 m along each link -- 9 + 9 + 7 = 25 per obstacle (ceil(70/10 = 7.000000000000001) = 8 steps on link 2,
+// ceil(5.000000000000001) = 6 on link 3) -- and the reference stacks them obstacle by obstacle until its `num_obs`
+// rows are full.  Here M is that row budget AND the number of obstacle slots of OBS; row r belongs to obstacle
+// r / 25, circle r % 25.  Active bits: bit r = CBF row r, bit M + 2i / M + 2i + 1 = joint i at +/- w_max.
+struct ManipArm {
+  double jx[4], jy[4];        // joint positions P_0 (base) .. P_3 (end effector)
+};
+SCB_HD void manip_prep(const double* q, ManipArm& arm) {
+  const double L[3] = {80.0 / 60.0, 70.0 / 60.0, 50.0 / 60.0};                   // :15-16
+  arm.jx[0] = 0.0; arm.jy[0] = 0.0;
+  double ang = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    ang += q[i];
+    double s, c; sincos_pair(ang, s, c);
+    arm.jx[i + 1] = arm.jx[i] + L[i] * c;
+    arm.jy[i + 1] = arm.jy[i] + L[i] * s;
+  }
+}
+// row r < M of the arm's QP (zero row when its obstacle is beyond nobs)
+template <bool NC = true>
+SCB_HD void manip_row(const scb_params& p, const ManipArm& arm, const double* obs, int nobs, int r, double* a, double& b) {
+  a[0] = 0.0; a[1] = 0.0; a[2] = 0.0; b = 0.0;
+  const int j = r / 25, c = r - j * 25;
+  if (j >= nobs) return;
+  const int link = (c < 9) ? 0 : (c < 18 ? 1 : 2);
+  const int k = c - (link == 0 ? 0 : (link == 1 ? 9 : 18));
+  const double t = (double)k / (double)(link == 2 ? 6 : 8);                      // j / num_steps (:133-134)
+  double sx = 0.0, sy = 0.0, ex = 0.0, ey = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) if (i == link) { sx = arm.jx[i]; sy = arm.jy[i]; ex = arm.jx[i + 1]; ey = arm.jy[i + 1]; }
+  const double cx = sx + t * (ex - sx), cy = sy + t * (ey - sy);                 // p_start + t * [dx, dy]
+  const double ox = ldx<NC>(obs + (size_t)j * 7), oy = ldx<NC>(obs + (size_t)j * 7 + 1), orad = ldx<NC>(obs + (size_t)j * 7 + 2);
+  const double dmin = p.radius + orad;
+  const double dx = cx - ox, dy = cy - oy;
+  const double h = (dx * dx + dy * dy) - 1.3 * (dmin * dmin);                    // beta = 1.3 (:163)
+  // dh/dq_k = 2 [dx, dy] . [-(cy - P_k.y), cx - P_k.x]  for joints k <= link (get_points_jacobian :140-160)
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk)
+    if (kk <= link) a[kk] = 2.0 * dx * (-(cy - arm.jy[kk])) + 2.0 * dy * (cx - arm.jx[kk]);
+  b = (p.cbf_mode == 1) ? h / p.dt : p.alpha * h;                                // f = 0, g = I (:138-146)
+}
+
+template <int LANES, int RPL, bool NC = true>
+SCB_HD void manipqp_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
+                          const double* obs, double* U, int32_t* status, uint64_t* active, int words) {
+  using G = Grp<LANES>;
+  constexpr int NU = 3;
+  const int lane = G::lane();
+  double ur[NU];
+#pragma unroll
+  for (int i = 0; i < NU; ++i) ur[i] = ldx<NC>(uref + i);
+  if (nobs < 0) {                    // obs_list is None -> u_ref unclipped (cbf_qp.py:113-118)
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) U[i] = ur[i];
+      *status = SCB_OPTIMAL;
+      if (active) for (int w = 0; w < words; ++w) active[w] = 0ull;
+    }
+    return;
+  }
+  if (nobs > M) nobs = M;
+  double q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) q[i] = ldx<NC>(x + i);
+  ManipArm arm;
+  manip_prep(q, arm);
+  double ra[RPL][NU], rb[RPL];
+  const int mrows = M + 2 * NU;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    const int r = j * LANES + lane;
+    ra[j][0] = 0.0; ra[j][1] = 0.0; ra[j][2] = 0.0; rb[j] = 0.0;
+    if (r < M) {
+      manip_row<NC>(p, arm, obs, nobs, r, ra[j], rb[j]);
+    } else if (r < mrows) {
+      const int qq = r - M, i = qq >> 1;
+#pragma unroll
+      for (int t = 0; t < NU; ++t)
+        if (t == i) { ra[j][t] = (qq & 1) ? 1.0 : -1.0; rb[j] = (qq & 1) ? -p.u_lb[t] : p.u_ub[t]; }
+    }
+  }
+  const double hd[NU] = {2.0, 2.0, 2.0};
+  QpOut<NU> out;
+  gi_solve<NU, LANES, RPL>(hd, ur, ra, rb, mrows, 8 * mrows + 16, out);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      double v = out.x[i];
+      if (out.status != SCB_OPTIMAL) v = fmin(fmax(v, p.u_lb[i]), p.u_ub[i]);
+      U[i] = v;
+    }
+    *status = out.status;
+    if (active) {
+      for (int w = 0; w < words; ++w) {
+        uint64_t bits = 0ull;
+#pragma unroll
+        for (int a = 0; a < NU; ++a)
+          if (a < out.wk && out.lam[a] > 0.0 && (out.widx[a] >> 6) == w) bits |= 1ull << (out.widx[a] & 63);
+        active[w] = bits;
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // Optimal-decay CBF-QP.  Variables z = [u (2), omega1 (, omega2)], ONE CBF row
 // (optimal_decay_cbf_qp.py:61) built from the nearest valid obstacle of the agent's list
 // (tracking.py:585-586), 4 box rows.  NW = number of omega variables (1: C3BF, 2: DU/KB).

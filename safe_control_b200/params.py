@@ -52,6 +52,10 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
     elif model == "Unicycle2D":                               # unicycle2D.py:40-41
         v = float(s.setdefault("v_max", 1.0)); w = float(s.setdefault("w_max", 0.5))
         p.u_lb[0], p.u_ub[0], p.u_lb[1], p.u_ub[1] = -v, v, -w, w
+    elif model == "Manipulator2D":                            # manipulator2D.py:19-20
+        w = float(s.setdefault("w_max", 2.0)); s.setdefault("Kp", 3.0)
+        for i in range(3):
+            p.u_lb[i], p.u_ub[i] = -w, w
     elif model == "DynamicUnicycle2D":
         a = float(s.setdefault("a_max", 0.5)); w = float(s.setdefault("w_max", 0.5))
         v = float(s.setdefault("v_max", 1.0))

@@ -21,6 +21,8 @@ def obs_rows(obs, num_obs):
     if obs is None:
         return OBS, np.array([-1], np.int32)
     a = np.asarray(obs, dtype=np.float64)
+    if a.ndim == 3:                                # a list of (n, 1) columns (what Unicycle2D.agent_barrier expects)
+        a = a.reshape(a.shape[0], -1)
     if a.ndim == 1 or (a.ndim == 2 and a.shape[1] == 1):
         a = a.reshape(1, -1)
     if a.shape[1] > 7:

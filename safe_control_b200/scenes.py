@@ -136,8 +136,38 @@ def default_spec(model):
     return s
 
 
+def make_manipulator_scene(N, M, seed=1234, dense=False, spec=None):
+    """Manipulator2D (robots/manipulator2D.py): N arms at the origin, joint angles uniform, M = CBFQP's row budget
+    (25 link-circle rows per obstacle, cbf_qp.py:131-149) and also the slot count of OBS; every arm gets its own
+    ceil(M / 25) (+1: one more than fits) circular obstacles placed around its reach, u_ref = the reference's
+    Jacobian-transpose law towards a random goal, scaled so that the box is sometimes active."""
+    rng = np.random.default_rng(seed)
+    spec = dict({"model": "Manipulator2D", "radius": 0.25, "w_max": 2.0, "Kp": 3.0}, **(spec or {}))
+    L = np.array([80, 70, 50]) / 60.0
+    X = rng.uniform(-np.pi, np.pi, (N, 3))
+    ang = np.cumsum(X, axis=1)
+    J = np.concatenate([np.zeros((N, 1, 2)), np.cumsum(L[None, :, None] * np.stack([np.cos(ang), np.sin(ang)], -1), axis=1)], axis=1)
+    ee = J[:, 3]
+    k = min(M, (M + 24) // 25 + 1)
+    OBS = np.zeros((N, M, 7))
+    r_lo, r_hi = (0.8, 2.6) if dense else (1.5, 4.0)
+    a = rng.uniform(-np.pi, np.pi, (N, k)); rad = rng.uniform(r_lo, r_hi, (N, k))
+    OBS[:, :k, 0] = rad * np.cos(a); OBS[:, :k, 1] = rad * np.sin(a); OBS[:, :k, 2] = rng.uniform(0.1, 0.4, (N, k))
+    nobs = rng.integers(0, k + 1, N).astype(np.int32)
+    goal = rng.uniform(-3, 3, (N, 2))
+    v = spec["Kp"] * (goal - ee)
+    U_ref = np.zeros((N, 3))
+    for i in range(3):                                   # J^T v with the geometric Jacobian of the end effector (:55-108)
+        U_ref[:, i] = -(ee[:, 1] - J[:, i, 1]) * v[:, 0] + (ee[:, 0] - J[:, i, 0]) * v[:, 1]
+    U_ref = np.clip(U_ref, -1.3 * spec["w_max"], 1.3 * spec["w_max"])
+    return dict(model="Manipulator2D", spec=spec, X=np.ascontiguousarray(X), U_ref=np.ascontiguousarray(U_ref), goal=goal,
+                OBS=np.ascontiguousarray(OBS), nobs=nobs, obs_idx=None, scene_obs=None, u_prev=np.zeros((N, 3)), L=4.0)
+
+
 def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=False, spec=None):
     """-> dict(X, U_ref, goal, OBS [N,M,7], nobs [N] i32, scene_obs [M,7], u_prev, spec)"""
+    if model == "Manipulator2D":
+        return make_manipulator_scene(N, M, seed, dense, spec)
     rng = np.random.default_rng(seed)
     spec = dict(default_spec(model), **(spec or {}))
     if dynamic is None:

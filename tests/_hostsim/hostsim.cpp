@@ -56,6 +56,10 @@ int hostsim_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const
         ROWCASE(SCB_QUAD_2D)
         ROWCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
         ROWCASE(SCB_UNICYCLE_2D)
+        case SCB_MANIPULATOR_2D: {
+          ManipArm arm; manip_prep(X + (size_t)i * 3, arm);
+          manip_row<false>(*p, arm, OBS + (size_t)i * stride, no, r, a, bb);
+        } break;
         default: return SCB_ERR_UNSUPPORTED;
       }
       for (int t = 0; t < p->nu; ++t) A[((size_t)i * M + r) * p->nu + t] = a[t];
@@ -67,7 +71,7 @@ int hostsim_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const
 
 int hostsim_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
                         long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active) {
-  if (M + 4 > 128) return SCB_ERR_TOO_LARGE;
+  if (M + 6 > 128) return SCB_ERR_TOO_LARGE;
   switch (p->model) {
     case SCB_SINGLE_INTEGRATOR_2D: run_cbfqp<SCB_SINGLE_INTEGRATOR_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     case SCB_DYNAMIC_UNICYCLE_2D: run_cbfqp<SCB_DYNAMIC_UNICYCLE_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
@@ -77,6 +81,12 @@ int hostsim_cbfqp_solve(const scb_params* p, int N, int M, const double* X, cons
     case SCB_QUAD_2D: run_cbfqp<SCB_QUAD_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     case SCB_KINEMATIC_BICYCLE_2D_DPCBF: run_cbfqp<SCB_KINEMATIC_BICYCLE_2D_DPCBF, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
     case SCB_UNICYCLE_2D: run_cbfqp<SCB_UNICYCLE_2D, 128>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active); break;
+    case SCB_MANIPULATOR_2D: {
+      const int words = scb_active_words(M, 3);
+      for (int i = 0; i < N; ++i)
+        manipqp_agent<1, 128, false>(*p, M, nobs ? nobs[i] : M, X + (size_t)i * 3, Uref + (size_t)i * 3, OBS + (size_t)i * stride,
+                                     U + (size_t)i * 3, status + i, active ? active + (size_t)i * words : nullptr, words);
+    } break;
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;

@@ -39,6 +39,7 @@ from safe_control.robots.quad3D import Quad3D  # noqa: E402
 from safe_control.robots.double_integrator2D import DoubleIntegrator2D  # noqa: E402
 from safe_control.robots.quad2D import Quad2D  # noqa: E402
 from safe_control.robots.unicycle2D import Unicycle2D  # noqa: E402
+from safe_control.robots.manipulator2D import Manipulator2D  # noqa: E402
 from safe_control.dynamic_env.kinematic_bicycle2D_dpcbf import KinematicBicycle2D_DPCBF  # noqa: E402
 from safe_control.position_control.cbf_qp import CBFQP  # noqa: E402
 from safe_control.position_control.optimal_decay_cbf_qp import OptimalDecayCBFQP  # noqa: E402
@@ -53,10 +54,11 @@ MODEL_CLS = {
     "Quad2D": Quad2D,
     "KinematicBicycle2D_DPCBF": KinematicBicycle2D_DPCBF,
     "Unicycle2D": Unicycle2D,
+    "Manipulator2D": Manipulator2D,
 }
 BASE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D")
 EXTRA_MODELS = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")      # SURVEY 8f-2, second fixture set
-EXTRA3_MODELS = ("Unicycle2D",)                                                   # third fixture set
+EXTRA3_MODELS = ("Unicycle2D", "Manipulator2D")                                                   # third fixture set
 DT = 0.05
 
 
@@ -87,6 +89,8 @@ def rand_state(rng, name):
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi), rng.uniform(0, 1.0)])
     if name == "Unicycle2D":
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi)])
+    if name == "Manipulator2D":
+        return rng.uniform(-np.pi, np.pi, 3)
     if name.startswith("KinematicBicycle2D"):
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-np.pi, np.pi), rng.uniform(0.2, 3.5)])
     if name == "DoubleIntegrator2D":
@@ -106,6 +110,8 @@ def rand_input(rng, spec, name):
         return rng.uniform(-0.5, 0.5, 2)
     if name == "Unicycle2D":
         return np.array([rng.uniform(-1, 1), rng.uniform(-0.5, 0.5)])
+    if name == "Manipulator2D":
+        return rng.uniform(-2, 2, 3)
     if name.startswith("KinematicBicycle2D"):
         return np.array([rng.uniform(-5, 5), rng.uniform(-0.3, 0.3)])
     if name == "DoubleIntegrator2D":
@@ -153,7 +159,7 @@ def gen_models(rng, n=48, names=BASE_MODELS, fname="ref_models.npz"):
             F.append(np.asarray(fac.f(), float).reshape(-1))
             Gm.append(np.asarray(fac.g(), float))
             xc, uc = x.reshape(-1, 1).copy(), u.reshape(-1, 1)
-            if name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D", "Quad2D", "Unicycle2D"):
+            if name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D", "Quad2D", "Unicycle2D", "Manipulator2D"):
                 STEP.append(np.asarray(m.step(xc, uc), float).reshape(-1))
             else:
                 STEP.append(np.asarray(m.step(xc, uc, casadi=False), float).reshape(-1))
@@ -163,6 +169,8 @@ def gen_models(rng, n=48, names=BASE_MODELS, fname="ref_models.npz"):
                 NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2], 0.05, 1.0, 1.0), float).reshape(-1))
             elif name == "Unicycle2D":           # facade: (X, goal, d_min, k_omega, k_v) (robots/robot.py:404-405)
                 NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2], 0.05, 2.0, 1.0), float).reshape(-1))
+            elif name == "Manipulator2D":        # facade: (X, goal) (robots/robot.py:414-415)
+                NOM.append(np.asarray(m.nominal_input(fac.X, goal[:2].reshape(-1, 1)), float).reshape(-1))
             elif name == "Quad2D":               # cascaded PD law, not on the solve path: not restated
                 NOM.append(np.full(2, np.nan))
             elif name == "Quad3D":
@@ -175,6 +183,8 @@ def gen_models(rng, n=48, names=BASE_MODELS, fname="ref_models.npz"):
                     # Unicycle2D.agent_barrier indexes obs[2][0] (unicycle2D.py:109): it only accepts COLUMN obstacles
                     parts = fac.agent_barrier(o.reshape(-1, 1) if name == "Unicycle2D" else o)
                     ct_rows.append(np.concatenate([np.asarray(p, float).reshape(-1) for p in parts]))
+                if name == "Manipulator2D":                  # no agent_barrier_dt (no MPC for the arm)
+                    dt_rows.append(np.zeros(2)); continue
                 parts = fac.agent_barrier_dt(x.reshape(-1, 1).copy(), u.reshape(-1, 1), o)
                 dt_rows.append(np.array([float(np.asarray(p).reshape(-1)[0]) for p in parts]))
             CT.append(np.stack(ct_rows) if ct_rows else np.zeros((4, 0)))
@@ -193,7 +203,7 @@ EXTRA_CBFQP = [("DoubleIntegrator2D", {}), ("Quad2D", {}), ("KinematicBicycle2D_
                ("KinematicBicycle2D_DPCBF", {"cbf_mode": "hard"}), ("DoubleIntegrator2D", {"cbf_mode": "hard", "a_max": 2.0})]
 
 
-def gen_cbfqp(rng, n=64, num_obs=6, cases=BASE_CBFQP, fname="ref_cbfqp.npz"):
+def gen_cbfqp(rng, n=64, num_obs=6, cases=BASE_CBFQP, fname="ref_cbfqp.npz", max_k=None):
     """Reference CBFQP end to end (row assembly + problem + status)."""
     flat = {}
     for name, spec in cases:
@@ -202,7 +212,7 @@ def gen_cbfqp(rng, n=64, num_obs=6, cases=BASE_CBFQP, fname="ref_cbfqp.npz"):
         for i in range(n):
             x = rand_state(rng, name); fac = Facade(name, x, spec)
             ctrl = CBFQP(fac, fac.robot_spec, num_obs=num_obs)
-            k = int(rng.integers(0, num_obs + 3))             # also more obstacles than rows
+            k = int(rng.integers(0, (max_k if max_k is not None else num_obs + 2) + 1))   # also more obstacles than rows
             dyn = name.endswith("C3BF") or name.endswith("DPCBF")
             obs = np.stack([rand_circle(rng, x, dyn) for _ in range(k)]) if k else None
             if k and name in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D") and i % 4 == 0:
@@ -212,7 +222,7 @@ def gen_cbfqp(rng, n=64, num_obs=6, cases=BASE_CBFQP, fname="ref_cbfqp.npz"):
             # reference's own tracking.py:611-616 call is dead for this model; feed the column form it expects
             obs_arg = [o.reshape(-1, 1) for o in obs] if (name == "Unicycle2D" and obs is not None) else obs
             u = ctrl.solve_control_problem(fac.X, {"u_ref": u_ref.reshape(-1, 1)}, obs_arg)
-            pad = np.full((num_obs + 2, 7), np.nan)
+            pad = np.full(((max_k if max_k is not None else num_obs + 2), 7), np.nan)
             if k:
                 pad[:k] = obs
             X.append(x); UR.append(u_ref); OBS.append(pad); NOBS.append(k)
@@ -265,6 +275,9 @@ def third_set():
     rng3 = np.random.default_rng(20261018)                   # third fixture set: Unicycle2D
     gen_models(rng3, names=EXTRA3_MODELS, fname="ref_models3.npz")
     gen_cbfqp(rng3, cases=[("Unicycle2D", {}), ("Unicycle2D", {"cbf_mode": "hard", "v_max": 2.0})], fname="ref_cbfqp3.npz")
+    # Manipulator2D: 25 rows per obstacle, so give CBFQP a row budget that cuts inside the 2nd / 3rd obstacle
+    gen_cbfqp(rng3, num_obs=60, cases=[("Manipulator2D", {}), ("Manipulator2D", {"cbf_mode": "hard", "w_max": 1.0})],
+              fname="ref_cbfqp4.npz", max_k=4)
 
 
 if __name__ == "__main__" and "--third" in sys.argv:

@@ -37,6 +37,8 @@ def test_reference_fixtures_cbfqp_rows_and_solve():
         M = d["A"].shape[1]
         ctrl = BatchedCBFQP(spec, num_obs=M)
         obs = np.nan_to_num(d["OBS"][:, :M].copy(), nan=0.0)
+        if obs.shape[1] < M:                          # Manipulator2D: M is the ROW budget (25 rows per obstacle)
+            obs = np.concatenate([obs, np.zeros((obs.shape[0], M - obs.shape[1], 7))], axis=1)
         nobs = np.minimum(d["NOBS"], M).astype(np.int32)
         A, b = ctrl.rows(dev(d["X"]), dev(obs), dev(nobs))
         np.testing.assert_allclose(A.cpu().numpy(), d["A"], rtol=1e-11, atol=1e-11, err_msg=tag)
@@ -74,6 +76,9 @@ def test_reference_fixtures_odcbf():
     ("KinematicBicycle2D_DPCBF", 16, True),
     ("KinematicBicycle2D_DPCBF", 8, False),
     ("Unicycle2D", 16, True),              # third fixture set (sigma-shaped barrier, rel. degree 1)
+    ("Manipulator2D", 20, True),           # 3-input QP, 25 link-circle rows per obstacle: RPL = 1 / 2 / 4 paths
+    ("Manipulator2D", 50, True),
+    ("Manipulator2D", 100, False),
 ])
 def test_scene_cbfqp_vs_oracle(model, M, dense):
     from safe_control_b200 import BatchedCBFQP, scenes
@@ -81,8 +86,12 @@ def test_scene_cbfqp_vs_oracle(model, M, dense):
     sc = scenes.make_scene(model, N, M, seed=1234, dense=dense)
     ctrl = BatchedCBFQP(sc["spec"], num_obs=M)
     U, st, act = run_cbfqp(ctrl, (sc["X"], sc["U_ref"], sc["OBS"], sc["nobs"]))
-    stats = check_cbfqp(ctrl.robot_spec, M, sc["X"], sc["U_ref"], sc["OBS"], sc["nobs"], U, st, act)
+    sample = np.arange(0, N, 10) if model == "Manipulator2D" else None      # (oracle: C(M + 6, 3) vertices per arm)
+    stats = check_cbfqp(ctrl.robot_spec, M, sc["X"], sc["U_ref"], sc["OBS"], sc["nobs"], U, st, act, sample=sample)
     print(model, M, dense, stats)
+    if model == "Manipulator2D":                                            # whole batch: inside the box, rows satisfied
+        lib = ctrl.params
+        assert (np.abs(U[st == 0]) <= lib.u_ub[0] + 1e-9).all()
 
 
 @pytest.mark.parametrize("model", ["KinematicBicycle2D_C3BF", "DynamicUnicycle2D", "KinematicBicycle2D", "Quad2D"])

@@ -16,7 +16,7 @@ RTOL, ATOL = 1e-12, 1e-12
 def _load(fname):
     """All fixture sets: <name>.npz (first models), <name>2.npz (DI / Quad2D / DPCBF), <name>3.npz (Unicycle2D)."""
     out = {}
-    for f in (fname, fname.replace(".npz", "2.npz"), fname.replace(".npz", "3.npz")):
+    for f in (fname, fname.replace(".npz", "2.npz"), fname.replace(".npz", "3.npz"), fname.replace(".npz", "4.npz")):
         path = os.path.join(GOLDEN, f)
         if not os.path.exists(path):
             continue
@@ -44,6 +44,8 @@ def test_models_match_reference(name):
             nom = m.nominal_input(x, goal[:2], 0.05, 2.0, 1.0, 1.0)
         elif name == "Quad2D":
             nom = d["NOM"][i]                 # cascaded PD law off the solve path: not restated
+        elif name == "Unicycle2D":
+            nom = m.nominal_input(x, goal[:2], 0.05, 2.0, 1.0)
         else:
             nom = m.nominal_input(x, goal[:2])
         np.testing.assert_allclose(nom, d["NOM"][i], rtol=1e-11, atol=1e-12)
@@ -52,6 +54,8 @@ def test_models_match_reference(name):
                 parts = m.agent_barrier(x, o)
                 got = np.concatenate([np.asarray(p, float).reshape(-1) for p in parts])
                 np.testing.assert_allclose(got, d["CT"][i][j], rtol=1e-11, atol=1e-11)
+            if name == "Manipulator2D":
+                continue                          # no agent_barrier_dt in the reference
             got = np.array(m.barrier_dt(x.copy(), u, o), float)
             np.testing.assert_allclose(got, d["DT"][i][j], rtol=1e-10, atol=1e-11)
 
@@ -74,7 +78,7 @@ def _spec_from_tag(tag):
 
 def test_cbfqp_matches_reference_end_to_end():
     data = _load("ref_cbfqp.npz")
-    assert len(data) == 13
+    assert len(data) == 15
     for tag, d in data.items():
         spec = _spec_from_tag(tag)
         num_obs = d["A"].shape[1]
