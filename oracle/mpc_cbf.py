@@ -44,6 +44,7 @@ MPC_PARAM = {   # mpc_cbf.py:19-39 (Q diag, R), 49-82 (alpha)
     "DynamicUnicycle2D": dict(Q=[50, 50, 0.01, 30], R=[0.5, 0.5], alpha1=0.15, alpha2=0.15),
     "KinematicBicycle2D": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha1=0.1, alpha2=0.1),
     "KinematicBicycle2D_C3BF": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha=0.15),
+    "KinematicBicycle2D_DPCBF": dict(Q=[50, 50, 1, 1], R=[0.5, 5000.0], alpha=0.15),
     "Quad3D": dict(Q=[30, 30, 5, 20, 20, 1, 10, 10, 10, 20, 20, 1], R=[1, 1, 1, 1], alpha=0.15),
     "DoubleIntegrator2D": dict(Q=[50, 50, 20, 20], R=[0.5, 0.5], alpha1=0.2, alpha2=0.2),
     "Quad2D": dict(Q=[25, 25, 50, 10, 10, 50], R=[0.5, 0.5], alpha1=0.15, alpha2=0.15),
@@ -126,6 +127,19 @@ class TorchModel:
             vx, vy = obs[None, :, 3] - v * torch.cos(th), obs[None, :, 4] - v * torch.sin(th)
             pm = torch.sqrt(px * px + py * py); vm = torch.sqrt(vx * vx + vy * vy)
             return (px * vx + py * vy) + pm * vm * torch.sqrt(torch.clamp(pm ** 2 - ego ** 2, min=0.0)) / pm
+        if n == "KinematicBicycle2D_DPCBF":                     # kinematic_bicycle2D_dpcbf.py:86-136
+            th, v = x[:, 2:3], x[:, 3:4]
+            sm = 1.05
+            ego = (obs[None, :, 2] + self.R) * sm
+            px, py = obs[None, :, 0] - x[:, 0:1], obs[None, :, 1] - x[:, 1:2]
+            vx, vy = obs[None, :, 3] - v * torch.cos(th), obs[None, :, 4] - v * torch.sin(th)
+            pm = torch.sqrt(px * px + py * py); vm = torch.sqrt(vx * vx + vy * vy)
+            rot = torch.atan2(py, px)
+            vnx = torch.cos(rot) * vx + torch.sin(rot) * vy
+            vny = -torch.sin(rot) * vx + torch.cos(rot) * vy
+            d_safe = torch.clamp(pm ** 2 - ego ** 2, min=1e-6)
+            kl, km = 0.1 * math.sqrt(sm ** 2 - 1) / ego, 0.5 * math.sqrt(sm ** 2 - 1) / ego
+            return vnx + kl * torch.sqrt(d_safe) / vm * vny ** 2 + km * torch.sqrt(d_safe)
         beta = 1.1 if n == "KinematicBicycle2D" else 1.01
         dx, dy = x[:, 0:1] - obs[None, :, 0], x[:, 1:2] - obs[None, :, 1]
         circ = dx * dx + dy * dy - beta * (obs[None, :, 2] + self.R) ** 2

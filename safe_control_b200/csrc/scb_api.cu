@@ -19,6 +19,8 @@ SCB_MPC_INSTANTIATE(SCB_QUAD_3D)
 SCB_MPC_INSTANTIATE(SCB_DOUBLE_INTEGRATOR_2D)
 SCB_MPC_INSTANTIATE(SCB_QUAD_2D)
 SCB_MPC_INSTANTIATE(SCB_UNICYCLE_2D)
+SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
+SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
 }
 #else
 #include "scb_mpc_kernels.cuh"

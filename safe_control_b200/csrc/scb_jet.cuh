@@ -193,11 +193,36 @@ SCB_HD void jclip(JetG& r, const JetG& a, double lo, double hi) {
 SCB_HD void jclip(JetH& r, const JetH& a, double lo, double hi) {
   if (a.v > hi) jconst(r, hi); else if (a.v < lo) jconst(r, lo); else r = a;
 }
+// plain values speak the same vocabulary, so one stage map serves values (line search) and every jet flavour
+SCB_HD void jsincos(double& s, double& c, double a) { sincos_pair(a, s, c); }
+SCB_HD void jmul(double& r, double a, double b) { r = a * b; }
+SCB_HD void jaxpy(double& r, double a, double s, double b) { r = a + s * b; }
+SCB_HD void jscale(double& r, double a, double s) { r = s * a; }
+SCB_HD void jclip(double& r, double a, double lo, double hi) { r = a > hi ? hi : (a < lo ? lo : a); }
 SCB_HD double jval(const JetG& a) { return a.v; }
 SCB_HD double jval(const JetH& a) { return a.v; }
 SCB_HD double jval(double a) { return a; }
 SCB_HD void jchain(double& r, const double&, double f0, double, double) { r = f0; }
 SCB_HD void jconst(double& r, double c) { r = c; }
+SCB_HD void jvar_entry(double& r, double val, int, int) { r = val; }
+SCB_HD void jvar_entry(double& r, double val, int, int, int) { r = val; }
+
+// sqrt(max(a, 0)) and 1/a through the chain rule, for every jet flavour (double, JetG, JetH)
+template <class T>
+SCB_HD void jsqrt0(T& r, const T& a) {
+  const double v = jval(a);
+  if (v > 1e-300) { const double s = sqrt(v); jchain(r, a, s, 0.5 / s, -0.25 / (s * v)); }
+  else jconst(r, 0.0);                                  // the flat side of the kink (CasADi: fmax(., 0))
+}
+template <class T>
+SCB_HD void jrecip(T& r, const T& a) {
+  const double inv = 1.0 / jval(a);
+  jchain(r, a, inv, -inv * inv, 2.0 * inv * inv * inv);
+}
+template <class T>
+SCB_HD void jadd(T& r, const T& a, const T& b) { jaxpy(r, a, 1.0, b); }
+template <class T>
+SCB_HD void jaddc(T& r, const T& a, double c) { T k; jconst(k, c); jaxpy(r, a, 1.0, k); }
 
 // sin/cos providers for the stage maps: compute, compute + remember, or replay the remembered values (the entry-jet
 // passes evaluate one stage many times at the same point; the transcendental is paid once per stage and iterate)

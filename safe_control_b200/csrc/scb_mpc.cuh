@@ -34,11 +34,7 @@
 namespace scb {
 
 // double overloads so the stage maps below serve both jets (derivatives) and plain values (line search)
-SCB_HD void jsincos(double& s, double& c, double a) { sincos_pair(a, s, c); }
-SCB_HD void jmul(double& r, double a, double b) { r = a * b; }
-SCB_HD void jaxpy(double& r, double a, double s, double b) { r = a + s * b; }
-SCB_HD void jscale(double& r, double a, double s) { r = s * a; }
-SCB_HD void jclip(double& r, double a, double lo, double hi) { r = a > hi ? hi : (a < lo ? lo : a); }
+// (double overloads of the jet vocabulary: scb_jet.cuh)
 
 template <int MODEL>
 struct MpcModel;
@@ -48,7 +44,7 @@ struct MpcModel;
 template <>
 struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
   static constexpr int NX = 2, NU = 2, NY = 4, REL = 1, NGOAL = 2, AUX = 0, NTRIG = 0;
-  static constexpr bool VBOUND = false, LINEAR = false;
+  static constexpr bool VBOUND = false, LINEAR = false, GENERAL = false;
   static SCB_HD double beta() { return 1.01; }
   template <class T, class TR>
   static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR&) {
@@ -63,7 +59,7 @@ struct MpcModel<SCB_SINGLE_INTEGRATOR_2D> {
 template <>
 struct MpcModel<SCB_UNICYCLE_2D> {
   static constexpr int NX = 3, NU = 2, NY = 5, REL = 1, NGOAL = 2, AUX = 0, NTRIG = 1;
-  static constexpr bool VBOUND = false, LINEAR = false;
+  static constexpr bool VBOUND = false, LINEAR = false, GENERAL = false;
   static SCB_HD double beta() { return 1.01; }
   // y = (px, py, theta, v, omega)
   template <class T, class TR>
@@ -82,7 +78,7 @@ struct MpcModel<SCB_UNICYCLE_2D> {
 template <>
 struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
   static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 2;
-  static constexpr bool VBOUND = true, LINEAR = false;
+  static constexpr bool VBOUND = true, LINEAR = false, GENERAL = false;
   static SCB_HD double beta() { return 1.01; }
   // y = (px, py, theta, v, a, omega).  F = Euler map; (P1,Q1), (P2,Q2) = positions after 1 and 2 own steps.
   // trig(s, c, angle) supplies sin/cos (computed, or replayed from the per-stage cache; scb_jet.cuh)
@@ -108,13 +104,19 @@ struct MpcModel<SCB_DYNAMIC_UNICYCLE_2D> {
 template <>
 struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
   static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 2;
-  static constexpr bool VBOUND = true, LINEAR = false;
+  static constexpr bool VBOUND = true, LINEAR = false, GENERAL = false;
   static SCB_HD double beta() { return 1.1; }
   template <class T, class TR>
   static SCB_HD void euler(const scb_params& p, const T& px, const T& py, const T& th, const T& v, const T& a,
                            const T& b, T* F, TR& trig) {
-    T s, c, vc, vs, vsb, vcb, t0, t1, vb;
+    T s, c;
     trig(s, c, th);
+    euler_sc(p, px, py, th, v, a, b, s, c, F);
+  }
+  template <class T>
+  static SCB_HD void euler_sc(const scb_params& p, const T& px, const T& py, const T& th, const T& v, const T& a,
+                              const T& b, const T& s, const T& c, T* F) {
+    T vc, vs, vsb, vcb, t0, t1, vb;
     jmul(vc, v, c); jmul(vs, v, s);
     jmul(vsb, vs, b); jmul(vcb, vc, b);
     jaxpy(t0, vc, -1.0, vsb);                 // v c - v s beta
@@ -136,12 +138,84 @@ struct MpcModel<SCB_KINEMATIC_BICYCLE_2D> {
   }
 };
 
+// ---- models whose barrier is NOT a weighted sum of squared distances ("general" rows) ---------------------------
+// KinematicBicycle2D_C3BF / _DPCBF (dynamic_env/kinematic_bicycle2D_{c3bf,dpcbf}.py): dynamics, own step, MPC weights
+// and bounds of KinematicBicycle2D (mpc_cbf.py:31-33, 205-211), relative degree 1 (alpha = 0.15, :68-73), barrier
+//   cbf_j = h(step(x_k, u_k); o_j) - h(x_k; o_j) + alpha h(x_k; o_j)        (mpc_cbf.py:312-315)
+// with h a collision-cone / dynamic-parabolic function of the FULL state and of the obstacle's velocity.  There is no
+// 12-sums structure: values, gradients and Hessian entries of every (stage, obstacle) row come from the same jets,
+// evaluated per row (MpcSolver's GENERAL branches).  states(): S[0] = x_k, S[1] = own step, with their heading sin/cos.
+template <int MODEL>
+struct MpcModelKBGeneral {
+  using KB = MpcModel<SCB_KINEMATIC_BICYCLE_2D>;
+  static constexpr int NX = 4, NU = 2, NY = 6, REL = 1, NGOAL = 2, AUX = 0, NTRIG = 2, NPT = 2;
+  static constexpr bool VBOUND = true, LINEAR = false, GENERAL = true;
+  static SCB_HD double beta() { return 1.01; }
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
+    KB::euler(p, y[0], y[1], y[2], y[3], y[4], y[5], F, trig);
+    P1 = F[0]; Q1 = F[1]; P2 = F[0]; Q2 = F[1];
+  }
+  template <class T, class TR>
+  static SCB_HD void states(const scb_params& p, const T* y, T* F, T (*S)[NX], T* SN, T* CS, TR& trig) {
+    trig(SN[0], CS[0], y[2]);
+    KB::euler_sc(p, y[0], y[1], y[2], y[3], y[4], y[5], SN[0], CS[0], F);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) S[0][i] = y[i];
+    S[1][0] = F[0]; S[1][1] = F[1]; S[1][2] = F[2];
+    jclip(S[1][3], F[3], p.v_min, p.v_max);                  // the model's own step clips v (kinematic_bicycle2D.py:116-121)
+    trig(SN[1], CS[1], F[2]);
+  }
+  // h(x; obs) of the DISCRETE barrier; ob = raw obstacle row [x, y, r, vx, vy, ., .]
+  template <class T>
+  static SCB_HD void hfun(const scb_params& p, const T* s, const T& sn, const T& cs, const double* ob, T& h) {
+    T px, py, vx, vy, t, pm2, vm2, pm, vm, dot;
+    jscale(px, s[0], -1.0); jaddc(px, px, ob[0]);            // p_rel = o - p
+    jscale(py, s[1], -1.0); jaddc(py, py, ob[1]);
+    jmul(t, s[3], cs); jscale(vx, t, -1.0); jaddc(vx, vx, ob[3]);   // v_rel = o_vel - v (cos, sin)
+    jmul(t, s[3], sn); jscale(vy, t, -1.0); jaddc(vy, vy, ob[4]);
+    jmul(pm2, px, px); jmul(t, py, py); jadd(pm2, pm2, t);
+    jmul(vm2, vx, vx); jmul(t, vy, vy); jadd(vm2, vm2, t);
+    jsqrt0(pm, pm2); jsqrt0(vm, vm2);
+    if (MODEL == SCB_KINEMATIC_BICYCLE_2D_C3BF) {
+      // h = <p_rel, v_rel> + |p_rel| |v_rel| sqrt(max(|p_rel|^2 - ego^2, 0)) / |p_rel|,  ego = (r + R) 1.01   (c3bf.py:82-108)
+      const double ego = (ob[2] + p.radius) * 1.01;
+      T d, sq, ipm;
+      jaddc(d, pm2, -ego * ego); jsqrt0(sq, d);
+      jmul(dot, px, vx); jmul(t, py, vy); jadd(dot, dot, t);
+      jrecip(ipm, pm);
+      jmul(t, pm, vm); jmul(t, t, sq); jmul(t, t, ipm);
+      jadd(h, dot, t);
+    } else {
+      // dynamic-parabolic CBF (dpcbf.py:86-136): v_rel rotated into the line-of-sight frame,
+      //   h = v_n,x + lambda v_n,y^2 + mu,  lambda = k_l sqrt(d_safe) / |v_rel|,  mu = k_m sqrt(d_safe),
+      //   d_safe = max(|p_rel|^2 - ego^2, 1e-6),  ego = (r + R) s,  s = 1.05,  k_l, k_m = (0.1, 0.5) sqrt(s^2 - 1) / ego
+      const double sm = 1.05, ego = (ob[2] + p.radius) * sm;
+      const double kl = 0.1 * sqrt(sm * sm - 1.0) / ego, km = 0.5 * sqrt(sm * sm - 1.0) / ego;
+      T ipm, vnx, vny, d, sd, ivm, lam;
+      jrecip(ipm, pm);
+      jmul(vnx, px, vx); jmul(t, py, vy); jadd(vnx, vnx, t); jmul(vnx, vnx, ipm);      // cos(rot) vx + sin(rot) vy
+      jmul(vny, px, vy); jmul(t, py, vx); jaxpy(vny, vny, -1.0, t); jmul(vny, vny, ipm);   // -sin(rot) vx + cos(rot) vy
+      jaddc(d, pm2, -ego * ego);
+      if (jval(d) < 1e-6) jconst(d, 1e-6);
+      jsqrt0(sd, d);
+      jrecip(ivm, vm);
+      jmul(lam, sd, ivm); jscale(lam, lam, kl);
+      jmul(t, vny, vny); jmul(t, t, lam);
+      jadd(h, vnx, t);
+      jaxpy(h, h, km, sd);
+    }
+  }
+};
+template <> struct MpcModel<SCB_KINEMATIC_BICYCLE_2D_C3BF> : MpcModelKBGeneral<SCB_KINEMATIC_BICYCLE_2D_C3BF> {};
+template <> struct MpcModel<SCB_KINEMATIC_BICYCLE_2D_DPCBF> : MpcModelKBGeneral<SCB_KINEMATIC_BICYCLE_2D_DPCBF> {};
+
 // DoubleIntegrator2D: f, g robots/double_integrator2D.py:46-78, step (rescales the velocity to |v| <= v_max) :80-108,
 // barrier_dt :223-272 (circle rows; rel. degree 2).  MPC weights / gains / bounds mpc_cbf.py:28-30, 60-63, 200-204.
 template <>
 struct MpcModel<SCB_DOUBLE_INTEGRATOR_2D> {
   static constexpr int NX = 4, NU = 2, NY = 6, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 0;
-  static constexpr bool VBOUND = false, LINEAR = false;
+  static constexpr bool VBOUND = false, LINEAR = false, GENERAL = false;
   static SCB_HD double beta() { return 1.01; }
   // y = (px, py, vx, vy, ax, ay).  The model's own step scales (vx, vy) by v_max / |v| when |v| > v_max (CasADi
   // if_else, :84-95); the positions after one own step are the Euler ones, after two they use the scaled velocity.
@@ -172,7 +246,7 @@ struct MpcModel<SCB_DOUBLE_INTEGRATOR_2D> {
 template <>
 struct MpcModel<SCB_QUAD_2D> {
   static constexpr int NX = 6, NU = 2, NY = 8, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 1;
-  static constexpr bool VBOUND = false, LINEAR = false;
+  static constexpr bool VBOUND = false, LINEAR = false, GENERAL = false;
   static SCB_HD double beta() { return 1.01; }
   template <class T, class TR>
   static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
@@ -203,7 +277,7 @@ struct MpcModel<SCB_QUAD_2D> {
 template <>
 struct MpcModel<SCB_QUAD_3D> {
   static constexpr int NX = 12, NU = 4, NY = 16, REL = 1, NGOAL = 3, AUX = 144 + 48 + 32, NTRIG = 0;
-  static constexpr bool VBOUND = false, LINEAR = true;
+  static constexpr bool VBOUND = false, LINEAR = true, GENERAL = false;
   static SCB_HD double beta() { return 1.01; }
 
   static SCB_HD void setup_aux(const scb_params& p, double* aux) {
@@ -273,7 +347,7 @@ struct MpcModel<SCB_QUAD_3D> {
 struct MpcLayout {
   int H, M, n, NS;
   int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, DZ, PM, PV, KG, KF,
-      TM, MM, MV, PT2, DY, ZT, XT, RG, AUX, AS, BS, TR, TRS;
+      TM, MM, MV, PT2, DY, ZT, XT, RG, AUX, AS, BS, TR, TRS, GR, SP, OBS7;
   int total;
 };
 
@@ -281,8 +355,10 @@ struct MpcLayout {
 // matrix columns of the Riccati stage in turn.  Linear models keep ONE copy of (A, B) (their AUX block) instead of H
 // identical ones (AS = BS = 0), and the Riccati value function is double-buffered (the forward sweep only needs the
 // gains), so the workspace is O(H) only in what really differs per stage.
-template <int NX, int NU, bool VBOUND, bool LINEAR = false, int AUXN = 0, bool SEQ = false, int NTRIG = 2>
+template <class Mod, bool SEQ = false>
 SCB_HD MpcLayout mpc_layout(int H, int M) {
+  constexpr int NX = Mod::NX, NU = Mod::NU, AUXN = Mod::AUX, NTRIG = Mod::NTRIG;
+  constexpr bool VBOUND = Mod::VBOUND, LINEAR = Mod::LINEAR, GENERAL = Mod::GENERAL;
   constexpr int NY = NX + NU, NH = NY * (NY + 1) / 2;
   MpcLayout L;
   L.H = H; L.M = M; L.n = H * NU; L.NS = 2 * H * NU + (VBOUND ? 2 * H : 0);
@@ -293,11 +369,13 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   if (LINEAR) { L.A = L.AUX; L.B = L.AUX + NX * NX; L.AS = 0; L.BS = 0; }
   else { L.A = take(H * NX * NX); L.B = take(H * NX * NU); L.AS = NX * NX; L.BS = NX * NU; }
   L.FH = take(0);                        // (curvature is contracted on the fly, see stage_hessians)
-  L.JE = take(H * NY); L.JX = take(H * NY); L.JY = take(H * NY);       // gradients gE, gX, gY
-  L.PT = take(H * 6);        L.OB = take(M * 3);
+  L.JE = take(GENERAL ? 0 : H * NY); L.JX = take(GENERAL ? 0 : H * NY); L.JY = take(GENERAL ? 0 : H * NY);   // gE, gX, gY
+  L.PT = take(GENERAL ? 0 : H * 6);        L.OB = take(GENERAL ? 0 : M * 3);
+  // general rows: gradient of every (stage, obstacle) row, the stage's barrier states (+ sin, cos), raw obstacle rows
+  L.GR = take(GENERAL ? H * M * NY : 0); L.SP = take(GENERAL ? H * 2 * (NX + 2) : 0); L.OBS7 = take(GENERAL ? M * 7 : 0);
   L.C = take(H * M); L.S = take(0); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
   L.SS = take(L.NS); L.SL = take(L.NS); L.SDS = take(L.NS); L.SDL = take(L.NS);
-  L.SUM = take(H * 12);
+  L.SUM = take(GENERAL ? 0 : H * 12);
   L.G = take((H + 1) * NH);  L.GAM = take((H + 1) * NY);
   L.MU = take((H + 1) * NX);
   L.RD = take(L.n); L.DZ = take(L.n);
@@ -415,6 +493,7 @@ struct MpcSolver {
   double uprev[NU];
   double Qs[NX], Rs[NU];        // cost weights times the objective scaling factor (IPOPT-style gradient-based scaling)
   bool gauss_newton;            // assemble stage Hessians without the (possibly indefinite) curvature terms
+  double floor_cur;             // slack floor mu / nu of the current iteration (general rows re-derive their weights)
 
   SCB_HD MpcSolver(const scb_params& p_, const MpcLayout& L_, double* w_) : p(p_), L(L_), w(w_) {
     H = L.H; M = L.M; n = L.n; lane = G::lane();
@@ -428,7 +507,7 @@ struct MpcSolver {
     for (int i = 0; i < NX; ++i) Qs[i] = p.Q[i];
 #pragma unroll
     for (int i = 0; i < NU; ++i) Rs[i] = p.R[i];
-    gauss_newton = false;
+    gauss_newton = false; floor_cur = 0.0;
   }
 
   // group reductions as real functions (20 call sites x a 5-step double-precision butterfly is ~1.7 k instructions inline)
@@ -477,8 +556,37 @@ struct MpcSolver {
     return Jc;
   }
 
+  // ---- general rows (Mod::GENERAL): one (stage, obstacle) row evaluated with any jet flavour -------------------
+  // c = sum_i wgt_i h(S_i; o_j) with wgt = (alpha - 1, 1) for relative degree 1   (mpc_cbf.py:312-315)
+  template <class T>
+  SCB_HD void general_row(const T (*S)[NX], const T* SN, const T* CS, const double* ob, T& c) const {
+    T h0, h1;
+    Mod::hfun(p, S[0], SN[0], CS[0], ob, h0);
+    Mod::hfun(p, S[1], SN[1], CS[1], ob, h1);
+    jaxpy(c, h1, w0, h0);                                      // w1 = 1, w0 = alpha - 1
+  }
+
   // barrier points of every stage at (xs, z) -> w[L.PT]; CBF values -> dst[H*M]
   SCB_MPC_PHASE void points_and_cbf(const double* z, const double* xs, double* dst) const {
+    if constexpr (Mod::GENERAL) {
+      // the stage's barrier states S_0, S_1 and their heading sin/cos (plain values) -> scratch at the END of the
+      // gradient block of each stage is not available here (trial points): recompute per (stage, obstacle) pair
+      SCB_LANE_UNROLL
+      for (int t = lane; t < H * M; t += LANES) {
+        const int k = t / M, j = t - k * M;
+        double y[NY], F[NX], S[2][NX], SN[2], CS[2], c;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
+        TrigCompute trig;
+        Mod::states(p, y, F, S, SN, CS, trig);
+        general_row(S, SN, CS, w + L.OBS7 + j * 7, c);
+        dst[t] = c;
+      }
+      sync();
+      return;
+    } else {
     SCB_LANE_UNROLL
     for (int k = lane; k < H; k += LANES) {
       double y[NY], F[NX], P1, Q1, P2, Q2;
@@ -507,6 +615,7 @@ struct MpcSolver {
       dst[t] = v;
     }
     sync();
+    }
   }
 
   SCB_HD double simple_value(const SimpleCon& c, const double* z, const double* xs) const {
@@ -555,6 +664,47 @@ struct MpcSolver {
           je[i] = 2.0 * w0 * (y[0] * d0 + y[1] * d1) + 2.0 * w1 * (P1 * R0[i] + Q1 * R1[i]);
           jx[i] = 2.0 * w0 * d0 + 2.0 * w1 * R0[i];
           jy[i] = 2.0 * w0 * d1 + 2.0 * w1 * R1[i];
+        }
+      }
+      sync();
+    } else if constexpr (Mod::GENERAL) {
+      // pass 0 (lanes over stages): sin/cos of the headings of S_0 and S_1 -> trig cache
+      SCB_LANE_UNROLL
+      for (int k = lane; k < H; k += LANES) {
+        double y[NY], F[NX], S[2][NX], SN[2], CS[2];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) y[NX + i] = z[k * NU + i];
+        TrigStore trig(w + L.TR + k * L.TRS);
+        Mod::states(p, y, F, S, SN, CS, trig);
+      }
+      sync();
+      // pass 1 (lanes over (stage, variable)): column i of A_k / B_k and d/dy_i of EVERY row of the stage
+      SCB_LANE_UNROLL
+      for (int t = lane; t < H * NY; t += LANES) {
+        const int k = t / NY, i = t - k * NY;
+        JetG y[NY], F[NX], S[2][NX], SN[2], CS[2];
+#pragma unroll
+        for (int m = 0; m < NX; ++m) jvar_entry(y[m], xs[k * NX + m], m, i);
+#pragma unroll
+        for (int m = 0; m < NU; ++m) jvar_entry(y[NX + m], z[k * NU + m], NX + m, i);
+        TrigLoad trig(w + L.TR + k * L.TRS);
+        Mod::states(p, y, F, S, SN, CS, trig);
+        double* A = w + L.A + k * L.AS;
+        double* B = w + L.B + k * L.BS;
+        if (i < NX) {
+#pragma unroll
+          for (int c = 0; c < NX; ++c) A[c * NX + i] = F[c].g;
+        } else {
+#pragma unroll
+          for (int c = 0; c < NX; ++c) B[c * NU + (i - NX)] = F[c].g;
+        }
+        SCB_LOOP
+        for (int j = 0; j < M; ++j) {
+          JetG c;
+          general_row(S, SN, CS, w + L.OBS7 + j * 7, c);
+          w[L.GR + (k * M + j) * NY + i] = c.g;
         }
       }
       sync();
@@ -660,6 +810,7 @@ struct MpcSolver {
 
   // mode 0: lambda sums only (dual residual / costates); 1: + sigma moments and Newton-rhs weights
   SCB_MPC_PHASE void stage_sums(double mu_bar, bool with_rhs, double floor_s = 0.0) {
+    if constexpr (Mod::GENERAL) { floor_cur = floor_s; return; }     // general rows: no sums structure, see stage_gradients / stage_hessians
     // A segment of `seg` lanes (smallest power of two >= M, capped at LANES) owns one stage at a time, so
     // LANES/seg stages are processed per pass and each of the <= 12 partial sums needs log2(seg) shuffle steps.
     int seg = 1;
@@ -716,9 +867,24 @@ struct MpcSolver {
       if (i < NX) v = 2.0 * Qs[i] * (xs[k * NX + i] - goal[i]);
       if (rhs) v = -v;
       if (k < H) {
-        const double* sm = w + L.SUM + k * 12 + (rhs ? 9 : 6);
-        const double ge = w[L.JE + k * NY + i], gx = w[L.JX + k * NY + i], gy = w[L.JY + k * NY + i];
-        const double cg = sm[0] * ge - sm[1] * gx - sm[2] * gy;      // sum_j wt_j grad c_j
+        double cg;                                                    // sum_j wt_j grad c_j
+        if constexpr (Mod::GENERAL) {
+          cg = 0.0;
+          SCB_LOOP
+          for (int j = 0; j < M; ++j) {
+            const double lam = w[L.L + k * M + j];
+            double wt = lam;
+            if (rhs) {
+              const double inv = w[L.DS + k * M + j], g = w[L.C + k * M + j];
+              wt = mu_bar * inv - lam * inv * (g - fmax(g, floor_cur));
+            }
+            cg = fma(wt, w[L.GR + (k * M + j) * NY + i], cg);
+          }
+        } else {
+          const double* sm = w + L.SUM + k * 12 + (rhs ? 9 : 6);
+          const double ge = w[L.JE + k * NY + i], gx = w[L.JX + k * NY + i], gy = w[L.JY + k * NY + i];
+          cg = sm[0] * ge - sm[1] * gx - sm[2] * gy;
+        }
         v += rhs ? cg : -cg;
       }
       gam[t] = v;
@@ -766,6 +932,33 @@ struct MpcSolver {
       while (rem >= NY - i) { rem -= NY - i; ++i; }
       const int j = i + rem;
       double v = 0.0;
+      if constexpr (Mod::GENERAL) {
+        if (k < H) {
+          JetH y[NY], F[NX], S[2][NX], SN[2], CS[2];
+#pragma unroll
+          for (int m = 0; m < NX; ++m) jvar_entry(y[m], w[L.X + k * NX + m], m, i, j);
+#pragma unroll
+          for (int m = 0; m < NU; ++m) jvar_entry(y[NX + m], w[L.Z + k * NU + m], NX + m, i, j);
+          TrigLoad trig(w + L.TR + k * L.TRS);
+          Mod::states(p, y, F, S, SN, CS, trig);
+          if (!gauss_newton) {
+            const double* mu = w + L.MU + (k + 1) * NX;
+#pragma unroll
+            for (int c = 0; c < NX; ++c) v = fma(mu[c], F[c].h, v);
+          }
+          SCB_LOOP
+          for (int jo = 0; jo < M; ++jo) {
+            JetH c;
+            general_row(S, SN, CS, w + L.OBS7 + jo * 7, c);
+            const double lam = w[L.L + k * M + jo], sig = lam * w[L.DS + k * M + jo];
+            v = fma(sig * c.gi, c.gj, v);                              // + sigma grad c grad c'
+            if (!gauss_newton) v = fma(-lam, c.h, v);                  // - lambda hess c
+          }
+        }
+        if (i == j && i < NX) v += 2.0 * Qs[i];
+        Gm[t] = v;
+        continue;
+      }
       if constexpr (!Mod::LINEAR) {
         if (k < H && !gauss_newton) {
           JetH y[NY], F[NX], P1, Q1, P2, Q2, E, PX, PY;
@@ -1077,10 +1270,16 @@ struct MpcSolver {
     // obstacles: (ox, oy, beta d^2); missing slots = the reference's dummy [1000, 1000, 0, ...] (mpc_cbf.py:346-364)
     SCB_LANE_UNROLL
     for (int j = lane; j < M; j += LANES) {
-      double ox = 1000.0, oy = 1000.0, r = 0.0;
-      if (j < nobs) { ox = ld(obs + j * 7); oy = ld(obs + j * 7 + 1); r = ld(obs + j * 7 + 2); }
-      const double d = r + p.radius;
-      w[L.OB + j * 3] = ox; w[L.OB + j * 3 + 1] = oy; w[L.OB + j * 3 + 2] = beta * d * d;
+      if constexpr (Mod::GENERAL) {
+        // raw rows; missing slots = the reference's dummy [1000, 1000, 0, 0, 0, 0, 0]
+#pragma unroll
+        for (int q = 0; q < 7; ++q) w[L.OBS7 + j * 7 + q] = (j < nobs) ? ld(obs + j * 7 + q) : (q < 2 ? 1000.0 : 0.0);
+      } else {
+        double ox = 1000.0, oy = 1000.0, r = 0.0;
+        if (j < nobs) { ox = ld(obs + j * 7); oy = ld(obs + j * 7 + 1); r = ld(obs + j * 7 + 2); }
+        const double d = r + p.radius;
+        w[L.OB + j * 3] = ox; w[L.OB + j * 3 + 1] = oy; w[L.OB + j * 3 + 2] = beta * d * d;
+      }
     }
     // cold start: u_k = u_prev (mpc_cbf.py:368-369)
     SCB_LANE_UNROLL
@@ -1264,7 +1463,9 @@ struct MpcSolver {
         double dg = 0.0;
 #pragma unroll
         for (int i = 0; i < NY; ++i) {
-          const double gi = w[L.JE + k * NY + i] - ob[0] * w[L.JX + k * NY + i] - ob[1] * w[L.JY + k * NY + i];
+          double gi;
+          if constexpr (Mod::GENERAL) gi = w[L.GR + t * NY + i];
+          else gi = w[L.JE + k * NY + i] - ob[0] * w[L.JX + k * NY + i] - ob[1] * w[L.JY + k * NY + i];
           dg = fma(gi, dy[i], dg);
         }
         const double g = w[L.C + t], s = fmax(g, floor_s), lam = w[L.L + t];
@@ -1395,7 +1596,7 @@ SCB_HD void mpc_agent(const scb_params& p, int H, int M, int nobs, const double*
                       const double* uprev, const double* obs, double* workspace, double* U, int32_t* status,
                       double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
   using Mod = MpcModel<MODEL>;
-  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, LANES == 1, Mod::NTRIG>(H, M);
+  const MpcLayout L = mpc_layout<Mod, LANES == 1>(H, M);
   MpcSolver<MODEL, LANES> s(p, L, workspace);
   if (nobs < 0) nobs = 0;
   if (nobs > M) nobs = M;

@@ -161,7 +161,7 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* X, cons
                         int32_t* iters, double* kkt, int* counter, void* workspace, size_t workspace_bytes, cudaStream_t s,
                  int sm_count, int* count_only) {
   using Mod = MpcModel<MODEL>;
-  const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, false, Mod::NTRIG>(H, M);
+  const MpcLayout L = mpc_layout<Mod, false>(H, M);
   const size_t per = (size_t)L.total * sizeof(double);
   const size_t budget = 220 * 1024;
   constexpr int kLanes = mpc_lanes<MODEL>();

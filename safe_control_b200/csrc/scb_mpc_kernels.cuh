@@ -73,11 +73,17 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X,
     case SCB_UNICYCLE_2D:
       return mpc_launch_m<SCB_UNICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
                                            pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF:
+      return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
+                                                         pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF:
+      return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
+                                                          pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
     case SCB_QUAD_3D:
       return mpc_launch_m<SCB_QUAD_3D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
                                        pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
     default:
-      return SCB_ERR_UNSUPPORTED;     // C3BF (collision-cone) barriers in MPC: not yet
+      return SCB_ERR_UNSUPPORTED;     // Manipulator2D: no agent_barrier_dt in the reference
   }
 }
 

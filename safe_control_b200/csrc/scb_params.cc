@@ -107,7 +107,7 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       p->u_lb[0] = -5.0; p->u_ub[0] = 5.0; p->u_lb[1] = -bmax; p->u_ub[1] = bmax;
       p->v_min = 0.2; p->v_max = 3.5;
       const bool c3 = model != SCB_KINEMATIC_BICYCLE_2D;          // C3BF and DPCBF: relative degree 1
-      if (model == SCB_KINEMATIC_BICYCLE_2D_DPCBF && !qp) return SCB_ERR_UNSUPPORTED;   // optimal_decay_cbf_qp.py:51-52 raises; MPC: not built
+      if (model == SCB_KINEMATIC_BICYCLE_2D_DPCBF && od) return SCB_ERR_UNSUPPORTED;    // optimal_decay_cbf_qp.py:51-52 raises
       if (qp) { if (c3) p->alpha = 1.5; else p->alpha1 = p->alpha2 = 1.5; }
       if (od) {
         p->omega1_0 = 1.0; p->p_sb1 = 1e4;

@@ -119,7 +119,7 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
 #define MPCCASE(MODEL)                                                                                          \
   case MODEL: {                                                                                                 \
     using Mod = MpcModel<MODEL>;                                                                                \
-    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, true, Mod::NTRIG>(H, M);                                      \
+    const MpcLayout L = mpc_layout<Mod, true>(H, M);                                      \
     double* ws = new double[L.total];                                                                           \
     for (int t = 0; t < L.total; ++t) ws[t] = 0.0;                                                              \
     mpc_agent<MODEL, 1>(*p, H, M, no, X + (size_t)i * nx, goal + (size_t)i * Mod::NGOAL, u_prev + (size_t)i * nu,        \
@@ -134,6 +134,8 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
       MPCCASE(SCB_DOUBLE_INTEGRATOR_2D)
       MPCCASE(SCB_QUAD_2D)
       MPCCASE(SCB_UNICYCLE_2D)
+      MPCCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
+      MPCCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -149,7 +151,7 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
 #define STCASE(MODEL)                                                                                           \
   case MODEL: {                                                                                                 \
     using Mod = MpcModel<MODEL>;                                                                                \
-    const MpcLayout L = mpc_layout<Mod::NX, Mod::NU, Mod::VBOUND, Mod::LINEAR, Mod::AUX, true, Mod::NTRIG>(1, M);               \
+    const MpcLayout L = mpc_layout<Mod, true>(1, M);               \
     std::vector<double> ws(L.total, 0.0);                                                                       \
     MpcSolver<MODEL, 1> s(*p, L, ws.data());                                                                    \
     const double J = s.init(nobs, x, goal, Mod::NGOAL, u, obs, false);                                               \
@@ -169,6 +171,8 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
     STCASE(SCB_DOUBLE_INTEGRATOR_2D)
     STCASE(SCB_QUAD_2D)
     STCASE(SCB_UNICYCLE_2D)
+    STCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
+    STCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;

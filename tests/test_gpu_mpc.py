@@ -38,6 +38,8 @@ def solve(ctrl, sc, goal, **kw):
     ("DoubleIntegrator2D", 256, 10, 16, False, 16),    # the remaining circle-barrier MPC models
     ("Quad2D", 192, 8, 16, False, 12),
     ("Unicycle2D", 256, 10, 16, False, 16),
+    ("KinematicBicycle2D_C3BF", 192, 8, 16, False, 12),     # general (non-quadratic) rows: collision cone / parabolic
+    ("KinematicBicycle2D_DPCBF", 192, 8, 16, False, 12),
 ])
 def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     from safe_control_b200 import BatchedMPCCBF, scenes
@@ -46,7 +48,7 @@ def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
     out = solve(ctrl, sc, goal)
     frac_ok = (out["status"] == 0).mean()
-    assert frac_ok > 0.9, (frac_ok, np.bincount(out["status"]))
+    assert frac_ok > (0.8 if model.endswith("BF") else 0.9), (frac_ok, np.bincount(out["status"]))
     rng = np.random.default_rng(0)
     sample = rng.choice(N, n_check, replace=False)
     stats = check_mpc(ctrl.robot_spec, M, H, sc["X"], goal, sc["u_prev"], sc["OBS"], sc["nobs"], out, sample=sample,
@@ -60,7 +62,7 @@ def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     ok = out["status"] == 0
     np.testing.assert_allclose(px[:, 0], sc["X"], atol=0)
     assert np.abs(pu[ok][:, 0] - U[ok]).max() < 1e-12
-    if model in ("DynamicUnicycle2D", "KinematicBicycle2D"):          # |x_k[3]| <= v_max (mpc_cbf.py:194-195, 206-207)
+    if model in ("DynamicUnicycle2D",) or model.startswith("KinematicBicycle2D"):   # |x_k[3]| <= v_max (mpc_cbf.py:194-195, 206-207)
         assert (np.abs(px[ok][:, :, 3]) <= ctrl.params.v_max + 1e-7).all()
 
 
@@ -101,7 +103,10 @@ def test_mpc_track_mask_and_host_path():
 def test_mpc_unsupported_models_fail_loudly():
     from safe_control_b200 import BatchedMPCCBF
     from safe_control_b200._lib import ScbError
-    ctrl = BatchedMPCCBF({"model": "KinematicBicycle2D_C3BF"}, num_obs=4, horizon=4)
+    from safe_control_b200.params import NotCompatibleError
+    with pytest.raises(NotCompatibleError):                     # no agent_barrier_dt in the reference -> no MPC
+        BatchedMPCCBF({"model": "Manipulator2D"}, num_obs=4, horizon=4)
+    ctrl = BatchedMPCCBF({"model": "DynamicUnicycle2D"}, num_obs=4, horizon=40)      # beyond the compiled horizon
     z = lambda *s: torch.zeros(s, dtype=torch.float64, device="cuda")
     with pytest.raises(ScbError):
         ctrl.solve(z(2, 4), z(2, 2), z(2, 2), z(2, 4, 7))

@@ -114,7 +114,7 @@ def test_optimal_decay_matches_reference_end_to_end():
 # obstacle padding, input / state bounds, the rterm weights and the horizon.  do-mpc's transcription of these pieces
 # into the NLP (sum over stages + terminal cost, rterm on input increments) stays as documented in SURVEY.md 8a.
 MPC_ORACLE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D",
-                     "DoubleIntegrator2D", "Quad2D", "Unicycle2D")
+                     "DoubleIntegrator2D", "Quad2D", "Unicycle2D", "KinematicBicycle2D_DPCBF")
 
 
 def test_mpc_statement_matches_reference():
@@ -167,4 +167,4 @@ def test_mpc_statement_matches_reference():
                 x2 = tm.own_step(x1, u); h2 = tm.h(x2, ob)
                 c = (h2 - 2 * h1 + h0) + (p["alpha1"] + p["alpha2"]) * (h1 - h0) + p["alpha1"] * p["alpha2"] * h0
             np.testing.assert_allclose(c[0].numpy(), d["cbf"][i], rtol=1e-9, atol=1e-9, err_msg=f"{tag} probe {i}")
-    assert seen == 10
+    assert seen == 11
