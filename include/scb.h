@@ -103,7 +103,9 @@ typedef struct scb_params {
   double R[4];            /* MPC input-rate weights        mpc_cbf.py:19-39, 180 */
   double mass, Ix, Iy, Iz, arm_L, nu_coef, gravity;     /* quad3D.py:53-69; Quad2D: mass, Iy = inertia, gravity 9.81 (quad2D.py:40-46) */
   int32_t mpc_max_iter;   /* interior-point iteration cap (ours) */
-  int32_t reserved;
+  int32_t mpc_superellipsoid; /* mpc_cbf, SingleIntegrator2D / DynamicUnicycle2D / DoubleIntegrator2D: 1 = OBS may hold
+                                 superellipsoid rows (flag 1; *_2D.py agent_barrier_dt if_else): the agents that have one
+                                 are solved by a second launch with general rows.  0: such agents get SCB_NUMERICAL */
   double mpc_tol;         /* KKT tolerance (ours; IPOPT default 1e-8) */
 } scb_params;
 
@@ -225,7 +227,9 @@ typedef struct scb_track {
   int32_t enable_rotation;       /* tracking.py:41 */
   int32_t dynamic_obs;           /* 1: SCENE[:, 0:2] += SCENE[:, 3:5] dt after the selection (dynamic_env/main.py:152) */
   int32_t att_velocity_tracking; /* SingleIntegrator2D: 1 = VelocityTrackingYaw drives yaw in 'track' (tracking.py:156-181) */
-  int32_t reserved;
+  int32_t mpc_superellipsoid; /* mpc_cbf, SingleIntegrator2D / DynamicUnicycle2D / DoubleIntegrator2D: 1 = OBS may hold
+                                 superellipsoid rows (flag 1; *_2D.py agent_barrier_dt if_else): the agents that have one
+                                 are solved by a second launch with general rows.  0: such agents get SCB_NUMERICAL */
   double reached_threshold;      /* 0.3  tracking.py:52 */
   double rotation_threshold;     /* 0.1  tracking.py:50 */
   double k_omega, k_a, k_v;      /* nominal_input gains (robots/robot.py:401; optimal decay: 3.0, 0.5, 0.5 tracking.py:601-602) */

@@ -291,19 +291,24 @@ class OracleMPCCBF:
             parts += [self.spec["v_max"] - x[1:, 3], x[1:, 3] + self.spec["v_max"]]
         return J, torch.cat(parts)
 
-    def kkt_error(self, x_init, goal, u_prev, obs, z, tol_act=1e-4):
-        """Least-squares multiplier estimate on the near-active set -> (stationarity residual, min g)."""
+    def kkt_error(self, x_init, goal, u_prev, obs, z, tol_act=1e-2):
+        """KKT check of a point: non-negative least-squares multipliers over every constraint within tol_act of its
+        bound -> (stationarity residual, min g, complementarity max_i lam_i g_i).  The candidate set is deliberately
+        wide and complementarity is reported separately: a badly scaled row (an e = 6 superellipsoid has gradients
+        ~1e5) can sit 1e-4 away from its bound with a multiplier of 1e-4 and still carry an O(1) share of the
+        stationarity condition -- an interior-point solution at mu = 1e-9 has exactly such rows."""
         zt = torch.tensor(np.asarray(z, float).reshape(-1), requires_grad=True)
         J, g = self.condensed(x_init, goal, u_prev, obs, zt)
         gradJ = torch.autograd.grad(J, zt, retain_graph=True)[0].numpy()
         gv = g.detach().numpy()
         act = np.nonzero(gv < tol_act)[0]
         if act.size == 0:
-            return float(np.abs(gradJ).max()), float(gv.min()), act
+            return float(np.abs(gradJ).max()), float(gv.min()), 0.0
         rows = []
         for i in act:
             rows.append(torch.autograd.grad(g[i], zt, retain_graph=True)[0].numpy())
         A = np.stack(rows, axis=1)
         from scipy.optimize import nnls
         lam, _ = nnls(A, gradJ)
-        return float(np.abs(gradJ - A @ lam).max()), float(gv.min()), act
+        comp = float(np.max(lam * np.maximum(gv[act], 0.0))) if act.size else 0.0
+        return float(np.abs(gradJ - A @ lam).max()), float(gv.min()), comp

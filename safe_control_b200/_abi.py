@@ -33,7 +33,7 @@ class ScbParams(C.Structure):
         ("Q", C.c_double * 12), ("R", C.c_double * 4),
         ("mass", C.c_double), ("Ix", C.c_double), ("Iy", C.c_double), ("Iz", C.c_double),
         ("arm_L", C.c_double), ("nu_coef", C.c_double), ("gravity", C.c_double),
-        ("mpc_max_iter", C.c_int32), ("reserved", C.c_int32), ("mpc_tol", C.c_double),
+        ("mpc_max_iter", C.c_int32), ("mpc_superellipsoid", C.c_int32), ("mpc_tol", C.c_double),
     ]
 
 

@@ -21,6 +21,9 @@ SCB_MPC_INSTANTIATE(SCB_QUAD_2D)
 SCB_MPC_INSTANTIATE(SCB_UNICYCLE_2D)
 SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
 SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
+SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
+SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
 }
 #else
 #include "scb_mpc_kernels.cuh"

@@ -219,6 +219,13 @@ SCB_HD void jrecip(T& r, const T& a) {
   const double inv = 1.0 / jval(a);
   jchain(r, a, inv, -inv * inv, 2.0 * inv * inv * inv);
 }
+// (|a| k)^e, e >= 2
+template <class T>
+SCB_HD void jpowabs(T& r, const T& a, double e, double k) {
+  const double x = jval(a), ax = fabs(x) * k, sg = (x < 0.0) ? -1.0 : 1.0;
+  const double p2 = pow(ax, e - 2.0);                    // ax^(e-2) (1 at e = 2)
+  jchain(r, a, p2 * ax * ax, e * p2 * ax * k * sg, e * (e - 1.0) * p2 * k * k);
+}
 template <class T>
 SCB_HD void jadd(T& r, const T& a, const T& b) { jaxpy(r, a, 1.0, b); }
 template <class T>

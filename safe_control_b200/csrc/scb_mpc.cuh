@@ -269,6 +269,55 @@ struct MpcModel<SCB_QUAD_2D> {
   }
 };
 
+// Superellipsoid obstacles in MPC (SingleIntegrator2D / DynamicUnicycle2D / DoubleIntegrator2D): their agent_barrier_dt
+// picks h per obstacle with if_else(obs[6] < 0.5, circle, superellipsoid) (e.g. dynamic_unicycle2D.py:204-228), and the
+// superellipsoid h = (|x'| / (a + R))^e + (|y'| / (b + R))^e - 1 (guards: a, b >= 1e-3, e >= 2) has no 12-sums
+// structure.  Agents with at least one flagged row run through these "general row" variants of the same models
+// (internal ids kMpcSeBase + base id; selected per agent, see mpc_kernel), everyone else through the fast path.
+constexpr int kMpcSeBase = 100;
+template <int BASE>
+struct MpcModelSE : MpcModel<BASE> {
+  using B = MpcModel<BASE>;
+  static constexpr int NX = B::NX, NPT = B::REL + 1;
+  static constexpr bool GENERAL = true;
+  template <class T, class TR>
+  static SCB_HD void states(const scb_params& p, const T* y, T* F, T (*S)[NX], T* SN, T* CS, TR& trig) {
+    T P1, Q1, P2, Q2;
+    B::stage(p, nullptr, y, F, P1, Q1, P2, Q2, trig);
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+#pragma unroll
+      for (int c = 0; c < NX; ++c) jconst(S[i][c], 0.0);
+      jconst(SN[i], 0.0); jconst(CS[i], 0.0);
+    }
+    S[0][0] = y[0]; S[0][1] = y[1];
+    S[1][0] = P1; S[1][1] = Q1;
+    if constexpr (B::REL == 2) { S[2][0] = P2; S[2][1] = Q2; }
+  }
+  template <class T>
+  static SCB_HD void hfun(const scb_params& p, const T* s, const T&, const T&, const double* ob, T& h) {
+    T dx, dy, t;
+    jaddc(dx, s[0], -ob[0]); jaddc(dy, s[1], -ob[1]);
+    if (ob[6] < 0.5) {                                        // circle
+      const double d = ob[2] + p.radius;
+      jmul(h, dx, dx); jmul(t, dy, dy); jadd(h, h, t); jaddc(h, h, -B::beta() * d * d);
+    } else {                                                  // superellipsoid [x, y, a, b, e, theta, 1]
+      const double a = fmax(fabs(ob[2]), 1e-3), b = fmax(fabs(ob[3]), 1e-3), e = fmax(fabs(ob[4]), 2.0);
+      double st, ct; sincos_pair(ob[5], st, ct);
+      T xp, yp;
+      jscale(xp, dx, ct); jaxpy(xp, xp, st, dy);
+      jscale(yp, dy, ct); jaxpy(yp, yp, -st, dx);
+      T px, py;
+      jpowabs(px, xp, e, 1.0 / (a + p.radius));
+      jpowabs(py, yp, e, 1.0 / (b + p.radius));
+      jadd(h, px, py); jaddc(h, h, -1.0);
+    }
+  }
+};
+template <> struct MpcModel<kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D> : MpcModelSE<SCB_SINGLE_INTEGRATOR_2D> {};
+template <> struct MpcModel<kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D> : MpcModelSE<SCB_DYNAMIC_UNICYCLE_2D> {};
+template <> struct MpcModel<kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D> : MpcModelSE<SCB_DOUBLE_INTEGRATOR_2D> {};
+
 // Quad3D: linear 12-state model xdot = A x + B u (robots/quad3D.py:81-97); the MPC uses plain Euler
 // (mpc_cbf.py:135-141) while the barrier uses the model's own RK4 step (quad3D.py:121-158, 275-297), which for a
 // linear system is the constant affine map x1 = Ad x + Bd u.  Relative degree 1: cbf = d_h + alpha h_k.  Because
@@ -482,6 +531,7 @@ struct MpcSolver {
   using Mod = MpcModel<MODEL>;
   using G = Grp<LANES>;
   static constexpr int NX = Mod::NX, NU = Mod::NU, NY = Mod::NY, NH = NY * (NY + 1) / 2;
+  static constexpr int NPT = Mod::REL + 1;     // barrier states per stage (general rows)
   using J = Jet<NY>;
 
   const scb_params& p;
@@ -557,13 +607,19 @@ struct MpcSolver {
   }
 
   // ---- general rows (Mod::GENERAL): one (stage, obstacle) row evaluated with any jet flavour -------------------
-  // c = sum_i wgt_i h(S_i; o_j) with wgt = (alpha - 1, 1) for relative degree 1   (mpc_cbf.py:312-315)
+  // c = sum_i w_i h(S_i; o_j):  (w0, w1) = (alpha - 1, 1) for relative degree 1, (w0, w1, w2) for 2 (mpc_cbf.py:312-321)
   template <class T>
   SCB_HD void general_row(const T (*S)[NX], const T* SN, const T* CS, const double* ob, T& c) const {
     T h0, h1;
     Mod::hfun(p, S[0], SN[0], CS[0], ob, h0);
     Mod::hfun(p, S[1], SN[1], CS[1], ob, h1);
-    jaxpy(c, h1, w0, h0);                                      // w1 = 1, w0 = alpha - 1
+    jscale(c, h0, w0);
+    jaxpy(c, c, w1, h1);
+    if constexpr (Mod::REL == 2) {
+      T h2;
+      Mod::hfun(p, S[2], SN[2], CS[2], ob, h2);
+      jaxpy(c, c, w2, h2);
+    }
   }
 
   // barrier points of every stage at (xs, z) -> w[L.PT]; CBF values -> dst[H*M]
@@ -574,7 +630,7 @@ struct MpcSolver {
       SCB_LANE_UNROLL
       for (int t = lane; t < H * M; t += LANES) {
         const int k = t / M, j = t - k * M;
-        double y[NY], F[NX], S[2][NX], SN[2], CS[2], c;
+        double y[NY], F[NX], S[NPT][NX], SN[NPT], CS[NPT], c;
 #pragma unroll
         for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
 #pragma unroll
@@ -671,7 +727,7 @@ struct MpcSolver {
       // pass 0 (lanes over stages): sin/cos of the headings of S_0 and S_1 -> trig cache
       SCB_LANE_UNROLL
       for (int k = lane; k < H; k += LANES) {
-        double y[NY], F[NX], S[2][NX], SN[2], CS[2];
+        double y[NY], F[NX], S[NPT][NX], SN[NPT], CS[NPT];
 #pragma unroll
         for (int i = 0; i < NX; ++i) y[i] = xs[k * NX + i];
 #pragma unroll
@@ -684,7 +740,7 @@ struct MpcSolver {
       SCB_LANE_UNROLL
       for (int t = lane; t < H * NY; t += LANES) {
         const int k = t / NY, i = t - k * NY;
-        JetG y[NY], F[NX], S[2][NX], SN[2], CS[2];
+        JetG y[NY], F[NX], S[NPT][NX], SN[NPT], CS[NPT];
 #pragma unroll
         for (int m = 0; m < NX; ++m) jvar_entry(y[m], xs[k * NX + m], m, i);
 #pragma unroll
@@ -934,7 +990,7 @@ struct MpcSolver {
       double v = 0.0;
       if constexpr (Mod::GENERAL) {
         if (k < H) {
-          JetH y[NY], F[NX], S[2][NX], SN[2], CS[2];
+          JetH y[NY], F[NX], S[NPT][NX], SN[NPT], CS[NPT];
 #pragma unroll
           for (int m = 0; m < NX; ++m) jvar_entry(y[m], w[L.X + k * NX + m], m, i, j);
 #pragma unroll

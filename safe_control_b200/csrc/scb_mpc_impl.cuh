@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid
   extern __shared__ double smem[];
   using Mod = MpcModel<MODEL>;
   constexpr int NX = Mod::NX, NU = Mod::NU;
+  constexpr bool kIsSe = MODEL >= kMpcSeBase;
+  constexpr bool kHasSeVariant = MODEL == SCB_SINGLE_INTEGRATOR_2D || MODEL == SCB_DYNAMIC_UNICYCLE_2D || MODEL == SCB_DOUBLE_INTEGRATOR_2D;
   const int grp = threadIdx.x / LANES;
   if (grp >= gpb) return;             // padding lanes of the last warp (gpb * LANES is rounded up to whole warps)
   double* ws = smem + (size_t)grp * ws_doubles;
@@ -44,7 +46,25 @@ __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid
   const long first_dynamic = (long)gridDim.x * gpb;
   for (long q = (long)blockIdx.x * gpb + grp; q < N;) {
     const long a = order ? (long)order[q] : q;
-    if (track && track[a] == 0) {
+    // agents with a superellipsoid row belong to the general-row variant of the model (second launch), all others
+    // to the fast path: each kernel skips what is not its kind
+    bool mine = true, se_unsupported = false;
+    if constexpr (kIsSe || kHasSeVariant) {
+      const int no = nobs ? min(max(nobs[a], 0), M) : M;
+      unsigned se = 0;
+      for (int j = threadIdx.x & (LANES - 1); j < no; j += LANES) se |= (__ldg(OBS + a * stride + j * 7 + 6) >= 0.5) ? 1u : 0u;
+      se = Grp<LANES>::or_reduce(se);
+      if (kIsSe) mine = (se != 0) && !(track && track[a] == 0);
+      else if (se != 0 && !(track && track[a] == 0)) { mine = false; se_unsupported = (p.mpc_superellipsoid == 0); }
+    }
+    if (!mine) {
+      if (se_unsupported && (threadIdx.x & (LANES - 1)) == 0) {      // flagged rows without mpc_superellipsoid: refuse loudly
+        for (int i = 0; i < NU; ++i) U[a * NU + i] = fmin(fmax(u_prev[a * NU + i], p.u_lb[i]), p.u_ub[i]);
+        status[a] = SCB_NUMERICAL;
+        if (iters) iters[a] = 0;
+        if (kkt) kkt[a] = kInf;
+      }
+    } else if (track && track[a] == 0) {
       // state_machine != 'track': return u_ref untouched, no solve (mpc_cbf.py:379-381)
       if ((threadIdx.x & (LANES - 1)) == 0) {
         for (int i = 0; i < NU; ++i) U[a * NU + i] = Uref[a * NU + i];

@@ -46,7 +46,26 @@ inline int* mpc_counter_slot(cudaStream_t s) {
   return slot;
 }
 
-#ifndef SCB_MPC_NO_DISPATCH   // (a per-model translation unit must not see references to the other models' launchers)
+#ifndef SCB_MPC_NO_DISPATCH
+constexpr int kMpcSeBaseId = 100;       // == kMpcSeBase (scb_mpc.cuh): general-row variants of SI / DU / DI for superellipsoid rows
+// fast path + (when p.mpc_superellipsoid) the general-row launch for the agents that have a superellipsoid row
+template <int MODEL>
+inline int mpc_launch_se(const scb_params& p, int N, int M, int H, const double* X, const double* Uref, const double* goal,
+                         const double* u_prev, const int32_t* track, const double* OBS, long stride, const int32_t* nobs,
+                         double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt,
+                         int* counter, void* workspace, size_t workspace_bytes, cudaStream_t s, int sm_count, int* count_only) {
+  int rc = mpc_launch_m<MODEL>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u, iters,
+                               kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
+  if (rc != SCB_OK || !p.mpc_superellipsoid) return rc;
+  int n2 = 0;
+  int* counter2 = count_only ? nullptr : mpc_counter_slot(s);
+  if (!counter2 && !count_only) return SCB_ERR_ALLOC;
+  rc = mpc_launch_m<kMpcSeBaseId + MODEL>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u,
+                                          iters, kkt, counter2, nullptr, 0, s, sm_count, count_only ? &n2 : nullptr);
+  if (count_only) *count_only += n2;
+  return rc;
+}
+   // (a per-model translation unit must not see references to the other models' launchers)
 inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X, const double* Uref, const double* goal,
                       const double* u_prev, const int32_t* track, const double* OBS, long stride, const int32_t* nobs,
                       double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt,
@@ -56,16 +75,16 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X,
   if (!counter && !count_only) return SCB_ERR_ALLOC;
   switch (p.model) {
     case SCB_SINGLE_INTEGRATOR_2D:
-      return mpc_launch_m<SCB_SINGLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
+      return mpc_launch_se<SCB_SINGLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
                                                     pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
     case SCB_DYNAMIC_UNICYCLE_2D:
-      return mpc_launch_m<SCB_DYNAMIC_UNICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
+      return mpc_launch_se<SCB_DYNAMIC_UNICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
                                                    pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
     case SCB_KINEMATIC_BICYCLE_2D:
       return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
                                                     pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
     case SCB_DOUBLE_INTEGRATOR_2D:
-      return mpc_launch_m<SCB_DOUBLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
+      return mpc_launch_se<SCB_DOUBLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
                                                     pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
     case SCB_QUAD_2D:
       return mpc_launch_m<SCB_QUAD_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,

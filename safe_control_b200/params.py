@@ -98,6 +98,10 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
         for k in ("alpha", "alpha1", "alpha2"):
             if prefix + k in s:
                 setattr(p, k, float(s[prefix + k]))
+    if controller == "mpc_cbf" and s.get("mpc_superellipsoid"):
+        if model not in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D"):
+            raise ValueError(f"{model} has no superellipsoid branch in its agent_barrier_dt")
+        p.mpc_superellipsoid = 1
     if "mpc_max_iter" in s:
         p.mpc_max_iter = int(s["mpc_max_iter"])
     if "mpc_tol" in s:

@@ -38,6 +38,9 @@ class MPCCBF:
         goal[0, : min(ng, g.size)] = g[:ng]
         OBS, nobs = obs_rows(nearest_obs, self.num_obs)
         nobs = np.maximum(nobs, 0).astype(np.int32)        # None -> all dummy obstacles (mpc_cbf.py:341-343)
+        if self.robot_spec["model"] in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D"):
+            # superellipsoid rows (flag 1) take the general-row kernel (their agent_barrier_dt's if_else branch)
+            self.params.mpc_superellipsoid = int(bool((OBS[0, : int(nobs[0]), 6] >= 0.5).any()))
         out = host_ctx(self.device).mpccbf_solve(self.params, self.num_obs, self.horizon, X, goal,
                                                  np.ascontiguousarray(self.u_prev), OBS, nobs, want_pred=True)
         self.solver_status = status_string(out["status"][0])

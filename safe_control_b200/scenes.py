@@ -136,6 +136,24 @@ def default_spec(model):
     return s
 
 
+def with_superellipsoids(sc, every=3, seed=7):
+    """Turn every `every`-th obstacle row of each agent's list into a superellipsoid [x, y, a, b, e, theta, 1]
+    (README.md:133-138) of about the same size: exercises the if_else(obs[6] < 0.5, ...) branch of the discrete
+    barriers (single_integrator2D.py / dynamic_unicycle2D.py / double_integrator2D.py agent_barrier_dt)."""
+    rng = np.random.default_rng(seed)
+    OBS = sc["OBS"].copy()
+    N, M, _ = OBS.shape
+    sel = (np.arange(M)[None, :] % every == 0) & (np.arange(M)[None, :] < sc["nobs"][:, None])
+    r = OBS[..., 2]
+    a = r * rng.uniform(0.7, 1.1, (N, M)); b = r * rng.uniform(0.7, 1.1, (N, M))
+    e = rng.choice([2.0, 4.0, 6.0], (N, M)); th = rng.uniform(-np.pi, np.pi, (N, M))
+    for col, v in ((2, a), (3, b), (4, e), (5, th), (6, np.ones((N, M)))):
+        OBS[..., col] = np.where(sel, v, OBS[..., col])
+    out = dict(sc); out["OBS"] = np.ascontiguousarray(OBS)
+    out["spec"] = dict(sc["spec"], mpc_superellipsoid=True)
+    return out
+
+
 def make_manipulator_scene(N, M, seed=1234, dense=False, spec=None):
     """Manipulator2D (robots/manipulator2D.py): N arms at the origin, joint angles uniform, M = CBFQP's row budget
     (25 link-circle rows per obstacle, cbf_qp.py:131-149) and also the slot count of OBS; every arm gets its own

@@ -115,7 +115,12 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
     const int no = nobs ? nobs[i] : M;
     double* px = pred_x ? pred_x + (size_t)i * (H + 1) * nx : nullptr;
     double* pu = pred_u ? pred_u + (size_t)i * H * nu : nullptr;
-    switch (p->model) {
+    // agents with a superellipsoid row (flag >= 0.5) take the general-row variant of their model, like mpc_kernel
+    int model = p->model;
+    if (model == SCB_SINGLE_INTEGRATOR_2D || model == SCB_DYNAMIC_UNICYCLE_2D || model == SCB_DOUBLE_INTEGRATOR_2D)
+      for (int j = 0; j < no && j < M; ++j)
+        if (OBS[(size_t)i * stride + j * 7 + 6] >= 0.5) { model = kMpcSeBase + p->model; break; }
+    switch (model) {
 #define MPCCASE(MODEL)                                                                                          \
   case MODEL: {                                                                                                 \
     using Mod = MpcModel<MODEL>;                                                                                \
@@ -136,6 +141,9 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
       MPCCASE(SCB_UNICYCLE_2D)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+      MPCCASE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
+      MPCCASE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
+      MPCCASE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -147,7 +155,11 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
 // value of every obstacle slot in w[L.C].  Compared with what the reference's mpc_cbf.py hands to do-mpc.
 int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x, const double* u, const double* goal,
                           const double* obs, double* x_next, double* stage_cost, double* cbf) {
-  switch (p->model) {
+  int model = p->model;
+  if (model == SCB_SINGLE_INTEGRATOR_2D || model == SCB_DYNAMIC_UNICYCLE_2D || model == SCB_DOUBLE_INTEGRATOR_2D)
+    for (int j = 0; j < nobs && j < M; ++j)
+      if (obs[j * 7 + 6] >= 0.5) { model = kMpcSeBase + p->model; break; }
+  switch (model) {
 #define STCASE(MODEL)                                                                                           \
   case MODEL: {                                                                                                 \
     using Mod = MpcModel<MODEL>;                                                                                \
@@ -173,6 +185,9 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
     STCASE(SCB_UNICYCLE_2D)
     STCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
     STCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+    STCASE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
+    STCASE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
+    STCASE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
     default: return SCB_ERR_UNSUPPORTED;
   }
   return 0;

@@ -75,7 +75,8 @@ def check_odcbf(spec, M, X, Uref, OBS, nobs, U, omega, sel, status, active, samp
 
 def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1e-4, min_agree=0.9):
     """MPC parity: (a) every 'optimal' answer must be a KKT point of the ORACLE's restated NLP
-    (independent derivatives: torch.autograd on oracle/mpc_cbf.py), feasible to 1e-7; (b) u0 must agree
+    (independent derivatives: torch.autograd on oracle/mpc_cbf.py: stationarity <= 1e-4 with non-negative least-squares
+    multipliers, complementarity max lam_i g_i <= 1e-5), feasible to 1e-7; (b) u0 must agree
     with the oracle's own SLSQP solve within u0_tol (box-normalised) on >= min_agree of the cases the
     oracle converged on -- the NLP is non-convex, so a different local optimum (different cost) is
     counted and reported, not hidden."""
@@ -94,10 +95,11 @@ def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1
         if out["status"][i] != 0:
             continue
         n_ok += 1
-        kk, gmin, _ = o.kkt_error(X[i], goal[i], u_prev[i], obs, out["pred_u"][i])
+        kk, gmin, comp = o.kkt_error(X[i], goal[i], u_prev[i], obs, out["pred_u"][i])
         scale = 1.0 + float(np.abs(out["pred_u"][i]).max())
         assert gmin >= -1e-7, f"agent {i}: infeasible point reported optimal (min g = {gmin:.2e})"
         assert kk <= 1e-4 * scale, f"agent {i}: not a KKT point of the oracle NLP (residual {kk:.2e})"
+        assert comp <= 1e-5 * scale, f"agent {i}: complementarity violated (max lam g = {comp:.2e})"
         worst_kkt = max(worst_kkt, kk)
         u, info = o.solve(X[i], goal[i], u_prev[i], obs)
         if not info["success"] or info["cbf_min"] < -1e-6:

@@ -66,6 +66,33 @@ def test_mpc_vs_oracle(model, N, H, M, near, n_check):
         assert (np.abs(px[ok][:, :, 3]) <= ctrl.params.v_max + 1e-7).all()
 
 
+@pytest.mark.parametrize("model", ["DynamicUnicycle2D", "SingleIntegrator2D", "DoubleIntegrator2D"])
+def test_mpc_superellipsoid_rows(model):
+    """Obstacle lists mixing circles and superellipsoids (flag 1): flagged agents go through the general-row launch,
+    the others through the fast path, and both must be KKT points of the oracle's NLP (which restates the reference's
+    if_else(obs[6] < 0.5, circle, superellipsoid) barrier).  Without mpc_superellipsoid the flagged agents are refused."""
+    from safe_control_b200 import BatchedMPCCBF, scenes
+    N, H, M = 96, 8, 8
+    base = scenes.make_scene(model, N, M, seed=99)
+    sc = scenes.with_superellipsoids(base, every=3)
+    sc["OBS"][::4] = base["OBS"][::4]                                   # every 4th agent keeps circles only
+    flagged = (sc["OBS"][:, :, 6] >= 0.5).any(axis=1) & (sc["nobs"] > 0)
+    assert flagged.any() and (~flagged).any()
+    ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
+    assert ctrl.params.mpc_superellipsoid == 1
+    out = solve(ctrl, sc, sc["goal"])
+    assert (out["status"] == 0).mean() > 0.8, np.bincount(out["status"])
+    sample = np.concatenate([np.nonzero(flagged)[0][:8], np.nonzero(~flagged)[0][:4]])
+    spec = {k: v for k, v in ctrl.robot_spec.items() if k != "mpc_superellipsoid"}
+    stats = check_mpc(spec, M, H, sc["X"], sc["goal"], sc["u_prev"], sc["OBS"], sc["nobs"], out, sample=sample, min_agree=0.75)
+    print(model, stats)
+    # circles-only agents: identical to a plain run of the fast path
+    plain = BatchedMPCCBF(base["spec"], num_obs=M, horizon=H)
+    ref = solve(plain, sc, sc["goal"])
+    np.testing.assert_array_equal(out["U"][~flagged], ref["U"][~flagged])
+    assert (ref["status"][flagged] == 3).all()                           # refused loudly without the flag
+
+
 def test_mpc_schedule_does_not_change_results():
     """The hardest-first schedule (scb_mpccbf_solve_ws + workspace) only reorders when agents START: every agent's
     output must be bit-identical to the index-order launch (scb_mpccbf_solve), and the launch count says which ran."""

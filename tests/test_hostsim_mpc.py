@@ -39,6 +39,19 @@ def test_mpc_vs_oracle(model, N, H, M, near):
     print(model, stats, "iters", out["iters"])
 
 
+@pytest.mark.parametrize("model", ["DynamicUnicycle2D", "SingleIntegrator2D", "DoubleIntegrator2D"])
+def test_mpc_superellipsoid_rows_vs_oracle(model):
+    """if_else(obs[6] < 0.5, circle, superellipsoid) rows (e.g. dynamic_unicycle2D.py:204-228) through the general-row path."""
+    N, H, M = 10, 6, 8
+    sc = scenes.with_superellipsoids(scenes.make_scene(model, N, M, seed=4321))
+    spec = {k: v for k, v in sc["spec"].items() if k != "mpc_superellipsoid"}
+    p, spec = resolve_params(spec, "mpc_cbf", lib=hostsim())
+    out = hs_mpccbf_solve(p, H, sc["X"], sc["goal"], sc["u_prev"], sc["OBS"], sc["nobs"])
+    assert (out["status"] == 0).mean() >= 0.8, out["status"]
+    stats = check_mpc(spec, M, H, sc["X"], sc["goal"], sc["u_prev"], sc["OBS"], sc["nobs"], out, min_agree=0.8)
+    print(model, stats)
+
+
 def test_mpc_no_obstacles_is_box_clipped_tracking():
     """Without obstacles the solution must equal the unconstrained-by-CBF MPC; with the goal far
     ahead and straight, full acceleration saturates: u0 = [a_max, ~0]."""
@@ -64,7 +77,7 @@ def test_kernel_statement_matches_reference():
     from hostsim_util import ptr
     from test_oracle_pinned import _load, _spec_from_tag
     lib = hostsim()
-    seen = 0
+    seen = n_se = 0
     for tag, d in _load("ref_mpc_statement.npz").items():
         spec = _spec_from_tag(tag)
         if spec["model"] not in ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D", "DoubleIntegrator2D",
@@ -76,8 +89,7 @@ def test_kernel_statement_matches_reference():
         for i in range(len(d["X"])):
             k = int(d["NOBS"][i])
             obs = np.nan_to_num(d["OBS"][i][:M].copy(), nan=0.0)
-            if (obs[:k, 6] != 0).any():
-                continue                                  # superellipsoid rows: not built in the MPC kernel yet
+            n_se += int((obs[:k, 6] != 0).any())            # superellipsoid rows -> the general-row variant of the model
             x, u, goal = np.ascontiguousarray(d["X"][i]), np.ascontiguousarray(d["U"][i]), np.ascontiguousarray(d["GOAL"][i])
             xn = np.zeros(p.nx); cost = C.c_double(); cbf = np.zeros(M)
             rc = lib.hostsim_mpc_statement(C.byref(p), M, k, ptr(x), ptr(u), ptr(goal), ptr(np.ascontiguousarray(obs)),
@@ -87,4 +99,4 @@ def test_kernel_statement_matches_reference():
             np.testing.assert_allclose(cost.value, d["cost"][i], rtol=1e-12, err_msg=tag)
             np.testing.assert_allclose(cbf, d["cbf"][i], rtol=1e-9, atol=1e-8, err_msg=f"{tag} probe {i}")
             seen += 1
-    assert seen > 200
+    assert seen > 230 and n_se >= 15
