@@ -291,24 +291,31 @@ class OracleMPCCBF:
             parts += [self.spec["v_max"] - x[1:, 3], x[1:, 3] + self.spec["v_max"]]
         return J, torch.cat(parts)
 
-    def kkt_error(self, x_init, goal, u_prev, obs, z, tol_act=1e-2):
-        """KKT check of a point: non-negative least-squares multipliers over every constraint within tol_act of its
-        bound -> (stationarity residual, min g, complementarity max_i lam_i g_i).  The candidate set is deliberately
-        wide and complementarity is reported separately: a badly scaled row (an e = 6 superellipsoid has gradients
-        ~1e5) can sit 1e-4 away from its bound with a multiplier of 1e-4 and still carry an O(1) share of the
-        stationarity condition -- an interior-point solution at mu = 1e-9 has exactly such rows."""
+    def kkt_error(self, x_init, goal, u_prev, obs, z, res_tol=1e-4):
+        """KKT check of a point -> (stationarity residual, min g, complementarity max_i lam_i g_i).
+        Multipliers: non-negative least squares over the constraints within tau of their bound, for the SMALLEST
+        tau in 1e-7 .. 1e-2 that brings the residual under res_tol (the last one otherwise).  A fixed small tau is
+        not enough: a badly scaled row (an e = 6 superellipsoid has gradients ~1e5) can sit 1e-4 away from its
+        bound with a multiplier of 1e-4 and still carry an O(1) share of stationarity -- an interior-point
+        solution at mu = 1e-9 has exactly such rows -- which is why complementarity is reported separately."""
+        from scipy.optimize import nnls
         zt = torch.tensor(np.asarray(z, float).reshape(-1), requires_grad=True)
         J, g = self.condensed(x_init, goal, u_prev, obs, zt)
         gradJ = torch.autograd.grad(J, zt, retain_graph=True)[0].numpy()
         gv = g.detach().numpy()
-        act = np.nonzero(gv < tol_act)[0]
-        if act.size == 0:
-            return float(np.abs(gradJ).max()), float(gv.min()), 0.0
-        rows = []
-        for i in act:
-            rows.append(torch.autograd.grad(g[i], zt, retain_graph=True)[0].numpy())
-        A = np.stack(rows, axis=1)
-        from scipy.optimize import nnls
-        lam, _ = nnls(A, gradJ)
-        comp = float(np.max(lam * np.maximum(gv[act], 0.0))) if act.size else 0.0
-        return float(np.abs(gradJ - A @ lam).max()), float(gv.min()), comp
+        scale = 1.0 + float(np.abs(np.asarray(z, float)).max())
+        res, comp, grads = float(np.abs(gradJ).max()), 0.0, {}
+        for tau in (1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2):
+            act = np.nonzero(gv < tau)[0]
+            if act.size == 0:
+                continue
+            for i in act:
+                if i not in grads:
+                    grads[i] = torch.autograd.grad(g[i], zt, retain_graph=True)[0].numpy()
+            A = np.stack([grads[i] for i in act], axis=1)
+            lam, _ = nnls(A, gradJ)
+            res = float(np.abs(gradJ - A @ lam).max())
+            comp = float(np.max(lam * np.maximum(gv[act], 0.0)))
+            if res <= res_tol * scale:
+                break
+        return res, float(gv.min()), comp
