@@ -57,13 +57,24 @@ static int sm_count_cached() {
 }
 
 // ------------------------------------------------------------------------------ dispatch
+// dynamic shared memory of cbfqp_kernel: the obstacle staging slices of its warps (warp-per-agent geometry only)
+static size_t qp_stage_bytes(int lanes, int rpl) { return lanes == 32 ? (size_t)(kBlock / 32) * rpl * 32 * 7 * sizeof(double) : 0; }
 template <int MODEL>
 static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
                           const double* OBS, long stride, const int32_t* nobs, double* U, int32_t* status,
-                          uint64_t* active, int words, cudaStream_t s) {
+                          uint64_t* active, int words, cudaStream_t s, bool eager) {
+  // warp per agent (small batches), inputs in device memory: obstacle rows are loaded before nobs is known
+  if (eager && g.lanes == 32 && g.rpl == 1) {
+    cbfqp_kernel<MODEL, 32, 1, true><<<g.grid, kBlock, qp_stage_bytes(32, 1), s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    return SCB_OK;
+  }
+  if (eager && g.lanes == 32 && g.rpl == 2) {
+    cbfqp_kernel<MODEL, 32, 2, true><<<g.grid, kBlock, qp_stage_bytes(32, 2), s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    return SCB_OK;
+  }
 #define GO(L, R)                                                                                           \
   if (g.lanes == L && g.rpl == R) {                                                                        \
-    cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
+    cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, qp_stage_bytes(L, R), s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
     return SCB_OK;                                                                                         \
   }
   GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 3) GO(8, 4) GO(8, 8) GO(4, 5) GO(4, 8)
@@ -139,8 +150,19 @@ int scb_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const dou
   return SCB_OK;
 }
 
+static int cbfqp_solve_impl(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
+                            long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active, void* stream,
+                            bool eager);
+
 int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
                     long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active, void* stream) {
+  return cbfqp_solve_impl(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, stream, true);
+}
+
+// eager = false: the zero-copy host path (inputs are mapped host memory; rows beyond nobs must not cross PCIe)
+static int cbfqp_solve_impl(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
+                            long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active, void* stream,
+                            bool eager) {
   if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
   if (!qp_model_ok(p->model)) return p->model == SCB_QUAD_3D ? SCB_ERR_UNSUPPORTED : SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
@@ -162,14 +184,14 @@ int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const do
   if (!pick_geom(N, M + 2 * p->nu, sm_count_cached(), g, forced_lanes())) return SCB_ERR_TOO_LARGE;
   int rc = SCB_ERR_BAD_ARG;
   switch (p->model) {
-    case SCB_SINGLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_SINGLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
-    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_DYNAMIC_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
-    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
-    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
-    case SCB_DOUBLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_DOUBLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
-    case SCB_QUAD_2D: rc = launch_cbfqp_m<SCB_QUAD_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
-    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
-    case SCB_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s); break;
+    case SCB_SINGLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_SINGLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_DYNAMIC_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_DOUBLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_DOUBLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_QUAD_2D: rc = launch_cbfqp_m<SCB_QUAD_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
   }
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
@@ -511,7 +533,7 @@ int scb_cbfqp_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const do
     const double *mX, *mUr, *mO; const int32_t* mN; double* mU; int32_t* mS; uint64_t* mA;
     if (mapped_alias(X, &mX) && mapped_alias(Uref, &mUr) && mapped_alias(OBS, &mO) && mapped_alias(nobs, &mN) &&
         mapped_alias(U, &mU) && mapped_alias(status, &mS) && mapped_alias(active, &mA)) {
-      rc = scb_cbfqp_solve(p, N, M, mX, mUr, mO, stride, mN, mU, mS, mA, c->stream);
+      rc = cbfqp_solve_impl(p, N, M, mX, mUr, mO, stride, mN, mU, mS, mA, c->stream, false);
       if (rc != SCB_OK) return rc;
       c->launches += 1;
       CK(cudaStreamSynchronize(c->stream));

@@ -45,13 +45,25 @@ SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, 
   }
 }
 
-template <int MODEL, int LANES, int RPL, bool NC = true>
+// STAGE (warp per agent only): the agent's obstacle block (7 M contiguous doubles) is copied into the warp's slice of
+// shared memory with COALESCED loads and the lanes pick their rows there -- instead of every lane fetching its own
+// 56-byte row with seven 8-byte loads (14.5 sectors per request).  EAGER: the copy is issued before anything looks
+// at `nobs` (slot r < M always exists in OBS), so its DRAM round trip overlaps the one that fetches nobs instead of
+// following it -- a warp-per-agent launch of a small batch is a chain of latencies (cfg2: 5.2 us for 1 MB).  Lazy
+// (the zero-copy host path, where rows cross PCIe): only the first nobs rows are copied.
+template <int MODEL, int LANES, int RPL, bool NC = true, bool EAGER = false, bool STAGE = false>
 SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
-                        const double* obs, double* U, int32_t* status, uint64_t* active, int words) {
+                        const double* obs, double* U, int32_t* status, uint64_t* active, int words,
+                        double* stage = nullptr) {
   using Mod = ModelCT<MODEL>;
   using G = Grp<LANES>;
   constexpr int NU = Mod::NU;
   const int lane = G::lane();
+  constexpr bool kStage = STAGE && (LANES == 32) && NC;
+
+  if (kStage && EAGER) {
+    for (int t = lane; t < 7 * M; t += LANES) stage[t] = ldx<NC>(obs + t);
+  }
 
   double ur[NU];
 #pragma unroll
@@ -68,6 +80,15 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
   }
   if (nobs > M) nobs = M;            // "Stop if we exceed allocated constraints" (cbf_qp.py:128-129)
 
+  if (kStage) {
+    if (!EAGER) {
+      for (int t = lane; t < 7 * nobs; t += LANES) stage[t] = ldx<NC>(obs + t);
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+  }
+
   double xs[Mod::NX];
 #pragma unroll
   for (int i = 0; i < Mod::NX; ++i) xs[i] = ldx<NC>(x + i);
@@ -81,7 +102,8 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     double a[NU], b;
-    cbfqp_row<MODEL, NC>(p, g, obs, M, nobs, j * LANES + lane, a, b);
+    if (kStage) cbfqp_row<MODEL, false>(p, g, stage, M, nobs, j * LANES + lane, a, b);
+    else cbfqp_row<MODEL, NC>(p, g, obs, M, nobs, j * LANES + lane, a, b);
     const double n2 = a[0] * a[0] + a[1] * a[1];
     const double inv = (n2 > 0.0) ? rsqrt_pos(n2) : 1.0;
     r0[j] = a[0] * inv; r1[j] = a[1] * inv; rb[j] = b * inv;
