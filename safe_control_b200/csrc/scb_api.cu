@@ -57,24 +57,22 @@ static int sm_count_cached() {
 }
 
 // ------------------------------------------------------------------------------ dispatch
-// dynamic shared memory of cbfqp_kernel: the obstacle staging slices of its warps (warp-per-agent geometry only)
-static size_t qp_stage_bytes(int lanes, int rpl) { return lanes == 32 ? (size_t)(kBlock / 32) * rpl * 32 * 7 * sizeof(double) : 0; }
 template <int MODEL>
 static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
                           const double* OBS, long stride, const int32_t* nobs, double* U, int32_t* status,
                           uint64_t* active, int words, cudaStream_t s, bool eager) {
   // warp per agent (small batches), inputs in device memory: obstacle rows are loaded before nobs is known
   if (eager && g.lanes == 32 && g.rpl == 1) {
-    cbfqp_kernel<MODEL, 32, 1, true><<<g.grid, kBlock, qp_stage_bytes(32, 1), s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    cbfqp_kernel<MODEL, 32, 1, true><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
     return SCB_OK;
   }
   if (eager && g.lanes == 32 && g.rpl == 2) {
-    cbfqp_kernel<MODEL, 32, 2, true><<<g.grid, kBlock, qp_stage_bytes(32, 2), s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    cbfqp_kernel<MODEL, 32, 2, true><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
     return SCB_OK;
   }
 #define GO(L, R)                                                                                           \
   if (g.lanes == L && g.rpl == R) {                                                                        \
-    cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, qp_stage_bytes(L, R), s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
+    cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
     return SCB_OK;                                                                                         \
   }
   GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 3) GO(8, 4) GO(8, 8) GO(4, 5) GO(4, 8)

@@ -31,15 +31,9 @@ cbfqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* _
              uint64_t* __restrict__ active, int words) {
   constexpr int NX = ModelCT<MODEL>::NX, NU = ModelCT<MODEL>::NU;
   constexpr int GPB = kBlock / LANES;
-  // warp per agent: the obstacle block is staged through the warp's slice of shared memory (coalesced loads)
-  constexpr bool kStage = (LANES == 32);
-  extern __shared__ double qp_stage[];
-  double* stage = kStage ? qp_stage + (size_t)(threadIdx.x >> 5) * (RPL * 32 * 7) : nullptr;
   for (long a = (long)blockIdx.x * GPB + threadIdx.x / LANES; a < N; a += (long)gridDim.x * GPB) {
-    cbfqp_agent<MODEL, LANES, RPL, true, EAGER, kStage>(p, M, nobs ? nobs[a] : M, X + a * NX, Uref + a * NU, OBS + a * stride,
-                                                        U + a * NU, status + a, active ? active + a * words : nullptr, words,
-                                                        stage);
-    if (kStage) __syncwarp();          // the slice is reused by the warp's next agent
+    cbfqp_agent<MODEL, LANES, RPL, true, EAGER>(p, M, nobs ? nobs[a] : M, X + a * NX, Uref + a * NU, OBS + a * stride,
+                                   U + a * NU, status + a, active ? active + a * words : nullptr, words);
   }
 }
 

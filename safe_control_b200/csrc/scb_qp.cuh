@@ -15,9 +15,10 @@ namespace scb {
 // Row r of the CBF-QP, r in [0, M + 2 NU):
 //   r <  M      : CBF row of obstacle slot r (vacuous 0 >= 0 when r >= nobs, cbf_qp.py:110-111)
 //   r = M + 2i  : u_i <= ub_i      r = M + 2i + 1 : u_i >= lb_i          (cbf_qp.py:54-73)
+// `pre` != nullptr: the obstacle row was loaded by the caller before `nobs` was known (see cbfqp_agent).
 template <int MODEL, bool NC = true>
 SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, int M, int nobs, int r,
-                      double* a, double& b) {
+                      double* a, double& b, const double* pre = nullptr) {
   constexpr int NU = ModelCT<MODEL>::NU;
 #pragma unroll
   for (int i = 0; i < NU; ++i) a[i] = 0.0;
@@ -26,7 +27,7 @@ SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, 
     if (r < nobs) {
       double o[7];
 #pragma unroll
-      for (int q = 0; q < 7; ++q) o[q] = ldx<NC>(obs + (size_t)r * 7 + q);
+      for (int q = 0; q < 7; ++q) o[q] = pre ? pre[q] : ldx<NC>(obs + (size_t)r * 7 + q);
       RowOut ro;
       ModelCT<MODEL>::row(p, g, o, ro);
 #pragma unroll
@@ -45,24 +46,29 @@ SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, 
   }
 }
 
-// STAGE (warp per agent only): the agent's obstacle block (7 M contiguous doubles) is copied into the warp's slice of
-// shared memory with COALESCED loads and the lanes pick their rows there -- instead of every lane fetching its own
-// 56-byte row with seven 8-byte loads (14.5 sectors per request).  EAGER: the copy is issued before anything looks
-// at `nobs` (slot r < M always exists in OBS), so its DRAM round trip overlaps the one that fetches nobs instead of
-// following it -- a warp-per-agent launch of a small batch is a chain of latencies (cfg2: 5.2 us for 1 MB).  Lazy
-// (the zero-copy host path, where rows cross PCIe): only the first nobs rows are copied.
-template <int MODEL, int LANES, int RPL, bool NC = true, bool EAGER = false, bool STAGE = false>
+template <int MODEL, int LANES, int RPL, bool NC = true, bool EAGER = false>
 SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
-                        const double* obs, double* U, int32_t* status, uint64_t* active, int words,
-                        double* stage = nullptr) {
+                        const double* obs, double* U, int32_t* status, uint64_t* active, int words) {
   using Mod = ModelCT<MODEL>;
   using G = Grp<LANES>;
   constexpr int NU = Mod::NU;
   const int lane = G::lane();
-  constexpr bool kStage = STAGE && (LANES == 32) && NC;
 
-  if (kStage && EAGER) {
-    for (int t = lane; t < 7 * M; t += LANES) stage[t] = ldx<NC>(obs + t);
+  // EAGER (warp per agent, inputs in device memory): a small batch is a chain of latencies (cfg2: 5.2 us for 1 MB), so
+  // the obstacle-row loads are issued BEFORE anything looks at `nobs` (slot r < M always exists in OBS) and their DRAM
+  // round trip overlaps the one that fetches nobs instead of following it: 5.18 -> 4.68 us per 1024-agent step.
+  // Lane-group launches (large batches) and the zero-copy host path (rows would cross PCIe: e2e 18.0 -> 14.5 M/s when
+  // tried) stay lazy -- rows beyond nobs are never read.  (Staging the block through shared memory with coalesced
+  // loads was measured too: 5.66 us, the extra store / barrier / load round trip costs more than the sectors it saves.)
+  constexpr bool kEager = EAGER && (LANES == 32) && NC && (RPL <= 2);
+  double pre[kEager ? RPL : 1][7];
+  if (kEager) {
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+      const int r = j * LANES + lane;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) pre[j][q] = (r < M) ? ldx<NC>(obs + (size_t)r * 7 + q) : 0.0;
+    }
   }
 
   double ur[NU];
@@ -80,15 +86,6 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
   }
   if (nobs > M) nobs = M;            // "Stop if we exceed allocated constraints" (cbf_qp.py:128-129)
 
-  if (kStage) {
-    if (!EAGER) {
-      for (int t = lane; t < 7 * nobs; t += LANES) stage[t] = ldx<NC>(obs + t);
-    }
-#if defined(__CUDA_ARCH__)
-    __syncwarp();
-#endif
-  }
-
   double xs[Mod::NX];
 #pragma unroll
   for (int i = 0; i < Mod::NX; ++i) xs[i] = ldx<NC>(x + i);
@@ -102,8 +99,7 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
 #pragma unroll
   for (int j = 0; j < RPL; ++j) {
     double a[NU], b;
-    if (kStage) cbfqp_row<MODEL, false>(p, g, stage, M, nobs, j * LANES + lane, a, b);
-    else cbfqp_row<MODEL, NC>(p, g, obs, M, nobs, j * LANES + lane, a, b);
+    cbfqp_row<MODEL, NC>(p, g, obs, M, nobs, j * LANES + lane, a, b, kEager ? pre[j] : nullptr);
     const double n2 = a[0] * a[0] + a[1] * a[1];
     const double inv = (n2 > 0.0) ? rsqrt_pos(n2) : 1.0;
     r0[j] = a[0] * inv; r1[j] = a[1] * inv; rb[j] = b * inv;
