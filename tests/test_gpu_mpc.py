@@ -95,6 +95,50 @@ def test_mpc_superellipsoid_rows(model):
     assert (ref["status"][flagged] == 3).all()                           # refused loudly without the flag
 
 
+def test_config5_share_full_size_properties():
+    """One GPU's share of BASELINE config 5 (8192 mixed DynamicUnicycle2D / KinematicBicycle2D / Quad3D agents,
+    mpc_cbf horizon 10, 64 obstacle slots) through MixedMPCCBF (three concurrent launches): for every agent the
+    predictions follow the Euler model from the given state, the first predicted input is the returned one, inputs
+    are inside the box, |v| <= v_max on every optimal trajectory, and every row of the discrete CBF holds at stage 0."""
+    from safe_control_b200 import scenes
+    from safe_control_b200.mixed import MixedMPCCBF, split_counts
+    models = ["DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D"]
+    counts = split_counts(8192, 3)
+    H, M = 10, 64
+    scs = [scenes.make_scene(m, n, M, seed=1234 + i) for i, (m, n) in enumerate(zip(models, counts))]
+    mixed = MixedMPCCBF([s["spec"] for s in scs], num_obs=M, horizon=H)
+    ins = [dict(X=dev(s["X"]), goal=dev(s["goal"]), u_prev=dev(s["u_prev"]), OBS=dev(s["OBS"]), nobs=dev(s["nobs"])) for s in scs]
+    outs = []
+    for g, a in zip(mixed.groups, ins):                       # (want_pred through the groups directly)
+        outs.append({k: v.cpu().numpy() for k, v in g.solve(a["X"], a["goal"], a["u_prev"], a["OBS"], a["nobs"], want_pred=True).items()})
+    torch.cuda.synchronize()
+    both = [{k: v.cpu().numpy() for k, v in o.items()} for o in mixed.solve(ins)]
+    for m, sc, g, o, o2 in zip(models, scs, mixed.groups, outs, both):
+        np.testing.assert_array_equal(o["U"], o2["U"])        # concurrent launches == one after the other
+        ok = o["status"] == 0
+        assert ok.mean() > 0.9, (m, np.bincount(o["status"]))
+        nu = g.nu
+        lb = np.array(list(g.params.u_lb)[:nu]); ub = np.array(list(g.params.u_ub)[:nu])
+        assert ((o["U"] >= lb - 1e-12) & (o["U"] <= ub + 1e-12)).all()
+        np.testing.assert_array_equal(o["pred_x"][:, 0], sc["X"])
+        assert np.abs(o["pred_u"][ok][:, 0] - o["U"][ok]).max() < 1e-12
+        px, pu = o["pred_x"][ok], o["pred_u"][ok]
+        if m != "Quad3D":
+            assert (np.abs(px[:, :, 3]) <= g.params.v_max + 1e-7).all()
+            th, v = px[:, :-1, 2], px[:, :-1, 3]
+            if m == "DynamicUnicycle2D":
+                nxt = np.stack([px[:, :-1, 0] + 0.05 * v * np.cos(th), px[:, :-1, 1] + 0.05 * v * np.sin(th),
+                                th + 0.05 * pu[:, :, 1], v + 0.05 * pu[:, :, 0]], -1)
+            else:
+                b = pu[:, :, 1]; lr = g.params.rear_ax_dist
+                nxt = np.stack([px[:, :-1, 0] + 0.05 * (v * np.cos(th) - v * np.sin(th) * b),
+                                px[:, :-1, 1] + 0.05 * (v * np.sin(th) + v * np.cos(th) * b),
+                                th + 0.05 * v / lr * b, v + 0.05 * pu[:, :, 0]], -1)
+            assert np.abs(nxt - px[:, 1:]).max() < 1e-11, m
+        else:
+            assert np.abs(px[:, 1:, 0:6] - (px[:, :-1, 0:6] + 0.05 * px[:, :-1, 6:12])).max() < 1e-11
+
+
 def test_mpc_schedule_does_not_change_results():
     """The hardest-first schedule (scb_mpccbf_solve_ws + workspace) only reorders when agents START: every agent's
     output must be bit-identical to the index-order launch (scb_mpccbf_solve), and the launch count says which ran."""

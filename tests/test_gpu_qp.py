@@ -173,6 +173,44 @@ def test_full_size_properties():
     assert (U2[ok] - U[ok]).abs().max().item() < 1e-9
 
 
+def test_config4_full_size_properties():
+    """BASELINE config 4 at its full size (8192 KinematicBicycle2D_C3BF agents, optimal_decay_cbf_qp, 32 moving
+    obstacles): the selected row is the nearest obstacle, u is inside the box, the decay variable is feasible
+    (the relaxed row holds at the returned (u, omega)), and without obstacles the filter is the identity
+    (omega = 1, u = clip(u_ref)); a sample is checked against the oracle in test_scene_odcbf_vs_oracle."""
+    from safe_control_b200 import BatchedOptimalDecayCBFQP, BatchedCBFQP, scenes
+    M, N = 32, 8192
+    sc = scenes.make_scene("KinematicBicycle2D_C3BF", N, M, seed=1234, dynamic=True, optimal_decay=True)
+    ctrl = BatchedOptimalDecayCBFQP(sc["spec"], num_obs=M)
+    X, Ur, OBS, nobs = dev(sc["X"]), dev(sc["U_ref"]), dev(sc["OBS"]), dev(sc["nobs"])
+    U, om, sel, st, act = ctrl.solve(X, Ur, OBS, nobs)
+    ok = st == 0
+    assert ok.float().mean() > 0.95
+    d = ((OBS[:, :, :2] - X[:, None, :2]) ** 2).sum(-1)
+    d = torch.where(torch.arange(M, device="cuda")[None] < nobs[:, None], d, torch.full_like(d, float("inf")))
+    has = nobs > 0
+    assert torch.equal(sel[has].long(), d.argmin(1)[has])
+    lb = torch.tensor(list(ctrl.params.u_lb)[:2], device="cuda", dtype=torch.float64)
+    ub = torch.tensor(list(ctrl.params.u_ub)[:2], device="cuda", dtype=torch.float64)
+    assert ((U >= lb - 1e-9) & (U <= ub + 1e-9)).all()       # (4-variable active-set solve: bounds hold to rounding)
+    # the relaxed row  A u + dh.f + alpha_od h omega >= 0  (optimal_decay_cbf_qp.py:98-103) at the returned (u, omega):
+    # A, dh.f and h are recovered from the cbf_qp rows of the same model at two gains (b = dh.f + alpha h, cbf_qp.py:165)
+    qa = BatchedCBFQP(dict(sc["spec"], cbf_alpha=1.5), num_obs=M)
+    qb = BatchedCBFQP(dict(sc["spec"], cbf_alpha=0.5), num_obs=M)
+    A, b15 = qa.rows(X, OBS, nobs); _, b05 = qb.rows(X, OBS, nobs)
+    ar = torch.arange(N, device="cuda"); idx = sel.clamp(min=0).long()
+    a_sel, h_sel = A[ar, idx], (b15 - b05)[ar, idx]
+    lf_sel = b05[ar, idx] - 0.5 * h_sel
+    row = (a_sel * U).sum(-1) + lf_sel + ctrl.params.alpha * h_sel * om[:, 0]
+    scale = 1.0 + a_sel.abs().sum(-1) + lf_sel.abs() + h_sel.abs()
+    m = has & ok
+    assert (row[m] >= -1e-7 * scale[m]).all(), float((row[m] / scale[m]).min())
+    # without any obstacle the filter is the identity: omega = 1, u = clip(u_ref)
+    U2, om2, sel2, st2, _ = ctrl.solve(X, Ur, OBS, torch.zeros_like(nobs))
+    assert (st2 == 0).all() and (sel2 == -1).all() and (om2[:, 0] - 1.0).abs().max().item() < 1e-9
+    assert (U2 - torch.minimum(torch.maximum(Ur, lb), ub)).abs().max().item() < 1e-9
+
+
 def test_host_pointer_path_matches_device_path():
     from safe_control_b200 import BatchedCBFQP, HostContext, scenes
     M, N = 16, 1024
