@@ -395,8 +395,8 @@ struct MpcModel<SCB_QUAD_3D> {
 // workspace layout (in doubles), computed identically on host and device
 struct MpcLayout {
   int H, M, n, NS;
-  int X, Z, A, B, FH, JE, JX, JY, PT, OB, C, S, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, DZ, PM, PV, KG, KF,
-      TM, MM, MV, PT2, DY, ZT, XT, RG, AUX, AS, BS, TR, TRS, GR, SP, OBS7;
+  int X, Z, A, B, JE, JX, JY, PT, OB, C, L, DS, DL, CT, SS, SL, SDS, SDL, SUM, G, GAM, MU, RD, DZ, PM, PV, KG, KF,
+      MM, PT2, DY, ZT, XT, RG, AUX, AS, BS, TR, TRS, GR, SP, OBS7;
   int total;
 };
 
@@ -417,12 +417,11 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   L.AUX = take(AUXN);
   if (LINEAR) { L.A = L.AUX; L.B = L.AUX + NX * NX; L.AS = 0; L.BS = 0; }
   else { L.A = take(H * NX * NX); L.B = take(H * NX * NU); L.AS = NX * NX; L.BS = NX * NU; }
-  L.FH = take(0);                        // (curvature is contracted on the fly, see stage_hessians)
   L.JE = take(GENERAL ? 0 : H * NY); L.JX = take(GENERAL ? 0 : H * NY); L.JY = take(GENERAL ? 0 : H * NY);   // gE, gX, gY
   L.PT = take(GENERAL ? 0 : H * 6);        L.OB = take(GENERAL ? 0 : M * 3);
   // general rows: gradient of every (stage, obstacle) row, the stage's barrier states (+ sin, cos), raw obstacle rows
   L.GR = take(GENERAL ? H * M * NY : 0); L.SP = take(GENERAL ? H * 2 * (NX + 2) : 0); L.OBS7 = take(GENERAL ? M * 7 : 0);
-  L.C = take(H * M); L.S = take(0); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
+  L.C = take(H * M); L.L = take(H * M); L.DS = take(H * M); L.DL = take(H * M); L.CT = take(H * M);
   L.SS = take(L.NS); L.SL = take(L.NS); L.SDS = take(L.NS); L.SDL = take(L.NS);
   L.SUM = take(GENERAL ? 0 : H * 12);
   L.G = take((H + 1) * NH);  L.GAM = take((H + 1) * NY);
@@ -432,7 +431,7 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
     const int NXT = NX + NU, NV = NXT + NU;
     L.PM = take(2 * NXT * NXT); L.PV = take(2 * NXT);     // P_{k+1} / P_k ping-pong (slot k & 1)
     L.KG = take(H * NU * NXT); L.KF = take(H * NU);
-    L.TM = take(0); L.MM = take(NU * NV); L.MV = take(0);
+    L.MM = take(NU * NV);                               // published input columns of a Riccati stage
     L.PT2 = take(SEQ ? (NV + 1) * NV : 0);
   }
   L.DY = take((H + 1) * NY);
@@ -532,7 +531,6 @@ struct MpcSolver {
   using G = Grp<LANES>;
   static constexpr int NX = Mod::NX, NU = Mod::NU, NY = Mod::NY, NH = NY * (NY + 1) / 2;
   static constexpr int NPT = Mod::REL + 1;     // barrier states per stage (general rows)
-  using J = Jet<NY>;
 
   const scb_params& p;
   const MpcLayout& L;
@@ -1070,15 +1068,6 @@ struct MpcSolver {
   // sensitivities + dense n x n Cholesky of a condensed factorisation, and needs O(H) scratch.
   static constexpr int NXT = NX + NU, NV = NXT + NU;
 
-  // F_k[a][c], a < NXT rows (next augmented state), c < NV columns (xt_k, u_k)
-  SCB_HD double fm(int k, int a, int c) const {
-    if (a < NX) {
-      if (c < NX) return w[L.A + k * L.AS + a * NX + c];
-      if (c < NXT) return 0.0;
-      return w[L.B + k * L.BS + a * NU + (c - NXT)];
-    }
-    return (c == NXT + (a - NX)) ? 1.0 : 0.0;
-  }
   // y-index (x, u) of the stage variable v-index, or -1 for the u_{k-1} block
   static SCB_HD int v2y(int c) { return c < NX ? c : (c < NXT ? -1 : NX + (c - NXT)); }
 
