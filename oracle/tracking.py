@@ -45,6 +45,12 @@ class OracleTrackingController:
             if X0.size == 2:
                 X0 = np.array([X0[0], X0[1], 0.0])
             self.yaw = float(X0[2]); X0 = X0[:2]
+        elif self.name == "DoubleIntegrator2D":                 # tracking.py:70-77, robots/robot.py:80-82
+            if X0.size == 3:
+                X0 = np.array([X0[0], X0[1], 0.0, 0.0, X0[2]])
+            elif X0.size == 2:
+                X0 = np.array([X0[0], X0[1], 0.0, 0.0, 0.0])
+            self.yaw = float(X0[4]); X0 = X0[:4]
         elif self.name == "Quad3D":
             if X0.size == 2:
                 X0 = np.concatenate([X0, np.zeros(10)])
@@ -64,7 +70,7 @@ class OracleTrackingController:
         self.u_att = None
         self.goal = None
         self.u_pos = None
-        self.att = enable_rotation and self.name == "SingleIntegrator2D"
+        self.att = enable_rotation and self.name in ("SingleIntegrator2D", "DoubleIntegrator2D")
         if controller == "cbf_qp":
             self.pos = OracleCBFQP(self.spec, num_obs=self.num_constraints, dt=dt)
         elif controller == "optimal_decay_cbf_qp":
@@ -88,6 +94,9 @@ class OracleTrackingController:
         n, X, s = self.name, self.X, self.spec
         if n == "SingleIntegrator2D":
             return np.zeros(2)
+        if n == "DoubleIntegrator2D":                           # double_integrator2D.py:147-153
+            k_a = s.get("nominal_k_a", 1.0)
+            return np.array([k_a * (0.0 - X[2]), k_a * (0.0 - X[3])])
         if n == "DynamicUnicycle2D":
             return np.array([s.get("nominal_k_a", 1.0) * (0.0 - X[3]), 0.0])
         if n.startswith("KinematicBicycle2D"):
@@ -104,6 +113,8 @@ class OracleTrackingController:
         n, X = self.name, self.X
         if n == "SingleIntegrator2D":
             return True
+        if n == "DoubleIntegrator2D":                           # :155-156
+            return np.linalg.norm(X[2:4]) < 0.05
         if n == "Quad3D":
             return np.linalg.norm(X[6:9]) < 0.05 and np.linalg.norm(X[9:12]) < 0.05
         return abs(X[3]) < 0.05
@@ -111,7 +122,7 @@ class OracleTrackingController:
     def rotate_to(self, theta):
         """-> (u_ref, u_att) as tracking.py:589-597 uses them."""
         n, X, s = self.name, self.X, self.spec
-        if n == "SingleIntegrator2D":
+        if n in ("SingleIntegrator2D", "DoubleIntegrator2D"):   # rotate_to(yaw, theta); u_ref = stop() (tracking.py:592-594)
             w = np.clip(2.0 * angle_normalize(theta - self.yaw), -s["w_max"], s["w_max"])
             return self.stop(), float(w)
         if n == "Quad3D":
@@ -127,6 +138,8 @@ class OracleTrackingController:
         n, m = self.name, self.model
         if n == "SingleIntegrator2D":
             return m.nominal_input(self.X, goal, 0.05, k_v)
+        if n == "DoubleIntegrator2D":                           # facade: (X, goal, d_min, k_v, k_a) (robots/robot.py:408-409)
+            return m.nominal_input(self.X, goal, 0.05, k_v, k_a)
         if n == "DynamicUnicycle2D":
             s = self.spec
             return m.nominal_input(self.X, goal, 0.05, s.get("nominal_k_omega", k_omega), s.get("nominal_k_a", k_a),
@@ -245,20 +258,24 @@ class OracleTrackingController:
         self.info = info
 
         if self.att and self.state_machine == "track":         # velocity_tracking_yaw.py:35-62
-            speed = np.hypot(u[0], u[1]) if u is not None else 0.0
-            if u is None or speed < 1e-2:
+            if self.name == "DoubleIntegrator2D":              # heading follows the STATE velocity (:44-50, preview_time 0)
+                vel = self.X[2:4]
+            else:
+                vel = u
+            speed = np.hypot(vel[0], vel[1]) if vel is not None else 0.0
+            if vel is None or speed < 1e-2:
                 self.u_att = 0.0
             else:
                 kp = float(self.spec.get("velocity_tracking_yaw_kp", 1.5))
                 w_max = self.spec.get("w_max", 0.5)
-                self.u_att = float(np.clip(kp * angle_normalize(np.arctan2(u[1], u[0]) - self.yaw), -w_max, w_max))
+                self.u_att = float(np.clip(kp * angle_normalize(np.arctan2(vel[1], vel[0]) - self.yaw), -w_max, w_max))
 
         collide = self.is_collide()
         if self.status != "optimal" or collide:
             return -2
         self.X = self.model.step(self.X, np.asarray(u, float))
         self.u_pos = np.asarray(u, float)
-        if self.name == "SingleIntegrator2D":
+        if self.name in ("SingleIntegrator2D", "DoubleIntegrator2D"):
             if self.u_att is not None:
                 self.yaw = float(angle_normalize(self.yaw + self.u_att * self.dt))
         elif self.name == "Quad3D":

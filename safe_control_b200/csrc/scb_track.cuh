@@ -64,6 +64,50 @@ struct ModelLoop<SCB_SINGLE_INTEGRATOR_2D> {
   static SCB_HD void step(const scb_params& p, double* x, const double* u) {                            // :64-66
     x[0] = x[0] + u[0] * p.dt; x[1] = x[1] + u[1] * p.dt;
   }
+  // VelocityTrackingYaw follows the commanded velocity (velocity_tracking_yaw.py:41-43)
+  static SCB_HD void att_velocity(const double*, const double* u, double& vx, double& vy) { vx = u[0]; vy = u[1]; }
+};
+
+// DoubleIntegrator2D (robots/double_integrator2D.py): X = [x, y, vx, vy], yaw kept outside the state (robots/robot.py:80-82)
+template <>
+struct ModelLoop<SCB_DOUBLE_INTEGRATOR_2D> {
+  static constexpr int NX = 4, NU = 2, NPOS = 2;
+  static constexpr bool HAS_ATT = true;
+  static SCB_HD double half_angle() { return kPi; }           // tracking.py:352-353
+  static SCB_HD double yaw_of(const double*, double yaw) { return yaw; }
+  // :116-143; the facade passes (d_min, k_v, k_a) (robots/robot.py:408-409); a_max = the cbf_qp input bound
+  static SCB_HD void nominal(const scb_params& p, const scb_track& t, const double* x, const double* g, double* u) {
+    double e0 = g[0] - x[0], e1 = g[1] - x[1];
+    const double s0 = (e0 > 0.0) - (e0 < 0.0), s1 = (e1 > 0.0) - (e1 < 0.0);
+    e0 = s0 * fmax(fabs(e0) - 0.05, 0.0);
+    e1 = s1 * fmax(fabs(e1) - 0.05, 0.0);
+    double v0 = t.k_v * e0, v1 = t.k_v * e1;
+    const double vm = sqrt(v0 * v0 + v1 * v1);
+    if (vm > p.v_max) { v0 = v0 * p.v_max / vm; v1 = v1 * p.v_max / vm; }
+    double a0 = t.k_a * (v0 - x[2]), a1 = t.k_a * (v1 - x[3]);
+    const double am = sqrt(a0 * a0 + a1 * a1), amax = p.u_ub[0];
+    if (am > amax) { a0 = a0 * amax / am; a1 = a1 * amax / am; }
+    u[0] = a0; u[1] = a1;
+  }
+  static SCB_HD void stop(const scb_params&, const scb_track& t, const double* x, double* u) {          // :147-153
+    u[0] = t.k_a_stop * (0.0 - x[2]); u[1] = t.k_a_stop * (0.0 - x[3]);
+  }
+  static SCB_HD bool has_stopped(const double* x) { return sqrt(x[2] * x[2] + x[3] * x[3]) < 0.05; }     // :155-156
+  static SCB_HD void rotate_to(const scb_params& p, const scb_track& t, const double* x, double yaw, double th,
+                               double* u, double& u_att) {                                              // :158-162
+    u_att = clipd(2.0 * wrap_floor(th - yaw), -t.w_max, t.w_max);
+    stop(p, t, x, u);
+  }
+  static SCB_HD void step(const scb_params& p, double* x, const double* u) {                            // :80-108
+    const double vx = x[2], vy = x[3];
+    x[0] = x[0] + vx * p.dt; x[1] = x[1] + vy * p.dt;
+    double nvx = vx + u[0] * p.dt, nvy = vy + u[1] * p.dt;
+    const double vm = sqrt(nvx * nvx + nvy * nvy);
+    if (vm > p.v_max) { const double sc = p.v_max / vm; nvx *= sc; nvy *= sc; }
+    x[2] = nvx; x[3] = nvy;
+  }
+  // VelocityTrackingYaw follows the STATE velocity for this model (velocity_tracking_yaw.py:44-50, preview_time = 0)
+  static SCB_HD void att_velocity(const double* x, const double*, double& vx, double& vy) { vx = x[2]; vy = x[3]; }
 };
 
 template <>
@@ -437,9 +481,11 @@ SCB_HD void track_post_agent(const scb_params& p, const scb_track& t, long a, co
 
   // attitude controller, integrators only (tracking.py:621-624; velocity_tracking_yaw.py:35-62)
   if (ML::HAS_ATT && sm == SCB_SM_TRACK && t.att_velocity_tracking && t.enable_rotation) {
-    const double speed = hypot(u[0], u[1]);
+    double vx = 0.0, vy = 0.0;
+    if constexpr (ML::HAS_ATT) ML::att_velocity(x, u, vx, vy);
+    const double speed = hypot(vx, vy);
     if (speed < 1e-2) u_att = 0.0;
-    else u_att = clipd(t.att_kp * wrap_floor(atan2(u[1], u[0]) - yaw), -t.w_max, t.w_max);
+    else u_att = clipd(t.att_kp * wrap_floor(atan2(vy, vx) - yaw), -t.w_max, t.w_max);
   }
 
   int ret;

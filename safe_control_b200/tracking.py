@@ -36,6 +36,14 @@ def pad_initial_state(model, X0):
         elif n != 3:
             raise ValueError("Invalid initial state dimension for SingleIntegrator2D")
         return np.ascontiguousarray(X0[:, :2]), np.ascontiguousarray(X0[:, 2])
+    if model == "DoubleIntegrator2D":                            # tracking.py:70-77; robots/robot.py:80-82: [x, y, vx, vy, theta]
+        if n == 3:
+            X0 = np.hstack([X0[:, 0:2], np.zeros((N, 2)), X0[:, 2:3]])
+        elif n == 2:
+            X0 = np.hstack([X0, np.zeros((N, 3))])
+        elif n != 5:
+            raise ValueError("Invalid initial state dimension for DoubleIntegrator2D")
+        return np.ascontiguousarray(X0[:, :4]), np.ascontiguousarray(X0[:, 4])
     if model == "Quad3D":
         X = np.zeros((N, 12))
         if n == 2:
@@ -165,11 +173,13 @@ class TrackerHostState:
         k_omega, k_a, k_v = (3.0, 0.5, 0.5) if od else (2.0, 1.0, 1.0)          # tracking.py:599-604
         if self.model == "DynamicUnicycle2D":                                    # dynamic_unicycle2D.py:84-86
             k_omega = s.get("nominal_k_omega", k_omega); k_a = s.get("nominal_k_a", k_a); k_v = s.get("nominal_k_v", k_v)
+        if self.model == "DoubleIntegrator2D":                                   # double_integrator2D.py:117-118
+            k_a = s.get("nominal_k_a", k_a); k_v = s.get("nominal_k_v", k_v)
         t.controller = _abi.CONTROLLER_IDS[self.controller]
         t.N, t.K, t.M, t.W, t.H = self.N, self.scene.shape[0], self.M, self.WP.shape[1], self.H
         t.enable_rotation = int(self.enable_rotation)
         t.dynamic_obs = int(self.dynamic_obs)
-        t.att_velocity_tracking = int(self.model == "SingleIntegrator2D" and self.enable_rotation)
+        t.att_velocity_tracking = int(self.model in ("SingleIntegrator2D", "DoubleIntegrator2D") and self.enable_rotation)
         t.reached_threshold = self.reached_threshold
         t.rotation_threshold = 0.1                                               # tracking.py:50
         t.k_omega, t.k_a, t.k_v = float(k_omega), float(k_a), float(k_v)

@@ -215,6 +215,7 @@ int hostsim_select_obstacles(const scb_params* p, int N, int K, int M, const dou
       SELCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       SELCASE(SCB_QUAD_3D)
       SELCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+      SELCASE(SCB_DOUBLE_INTEGRATOR_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -235,6 +236,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       PRECASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       PRECASE(SCB_QUAD_3D)
       PRECASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+      PRECASE(SCB_DOUBLE_INTEGRATOR_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -280,6 +282,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       POSTCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       POSTCASE(SCB_QUAD_3D)
       POSTCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+      POSTCASE(SCB_DOUBLE_INTEGRATOR_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }

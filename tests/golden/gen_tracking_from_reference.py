@@ -155,9 +155,21 @@ def scenarios():
            np.zeros((0, 7)), 200, True, None)
 
 
-def main():
+def scenarios2():
+    """Second file (ref_tracking2.npz): DoubleIntegrator2D -- yaw outside the state, VelocityTrackingYaw on the state
+    velocity, own step rescales the velocity (examples/test_tracking.py --model di)."""
+    wp = TEST_TRACKING_WP
+    yield ("di_test_tracking", LocalTrackingController, wp[0],
+           {"model": "DoubleIntegrator2D", "v_max": 1.0, "a_max": 1.0, "ax_max": 1.0, "ay_max": 1.0, "radius": 0.25},
+           wp, TEST_TRACKING_OBS, 700, True, None)
+    yield ("di_stop_rotate", LocalTrackingController, np.array([2.0, 2.0, 0.6, -0.3, -math.pi / 2]),
+           {"model": "DoubleIntegrator2D", "v_max": 1.0, "a_max": 1.0, "radius": 0.25},
+           np.array([[2, 2, 0], [2.5, 6.5, 0], [6, 4.2, 0]], float), TEST_TRACKING_OBS[:6], 400, True, 16)
+
+
+def main(gen=scenarios, fname="ref_tracking.npz"):
     flat = {}
-    for name, cls, x0, spec, wp, obs, steps, rot, M in scenarios():
+    for name, cls, x0, spec, wp, obs, steps, rot, M in gen():
         out, spec = run(cls, x0, spec, wp, obs, steps, rot, M)
         for k, v in out.items():
             flat[f"{name}/{k}"] = v
@@ -168,8 +180,11 @@ def main():
         r = out["ret"]
         print(f"{name}: {len(r)} steps, last ret {r[-1]}, sm counts {np.bincount(out['sm'], minlength=4)}, "
               f"infeasible {int(out['status'].sum())}, final X {np.round(out['X'][-1], 3)}")
-    np.savez_compressed(os.path.join(HERE, "ref_tracking.npz"), **flat)
+    np.savez_compressed(os.path.join(HERE, fname), **flat)
 
 
 if __name__ == "__main__":
-    main()
+    if "--second" in sys.argv:
+        main(scenarios2, "ref_tracking2.npz")
+    else:
+        main()

@@ -137,6 +137,7 @@ def test_select_obstacles_matches_oracle(model):
     ("DynamicUnicycle2D", "cbf_qp", False),
     ("SingleIntegrator2D", "cbf_qp", False),
     ("KinematicBicycle2D", "cbf_qp", False),
+    ("DoubleIntegrator2D", "cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "cbf_qp", True),
     ("DynamicUnicycle2D", "optimal_decay_cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True),
@@ -197,6 +198,7 @@ def test_mpc_closed_loop(model):
     ("DynamicUnicycle2D", "cbf_qp", False, 8),
     ("DynamicUnicycle2D", "cbf_qp", False, 40),           # RPL = 2 geometry of the fused kernel
     ("SingleIntegrator2D", "cbf_qp", False, 8),
+    ("DoubleIntegrator2D", "cbf_qp", False, 8),
     ("KinematicBicycle2D_C3BF", "cbf_qp", True, 8),
     ("KinematicBicycle2D_DPCBF", "cbf_qp", True, 8),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True, 16),

@@ -14,11 +14,12 @@ TEST_TRACKING_WP = np.array([[2, 2, np.pi / 2], [2, 12, 0], [12, 12, 0], [12, 2,
 
 
 def load_tracking_golden():
-    z = np.load(os.path.join(GOLDEN, "ref_tracking.npz"))
     out = {}
-    for k in z.files:
-        tag, key = k.rsplit("/", 1)
-        out.setdefault(tag, {})[key] = z[k]
+    for f in ("ref_tracking.npz", "ref_tracking2.npz"):              # 2: DoubleIntegrator2D runs
+        z = np.load(os.path.join(GOLDEN, f))
+        for k in z.files:
+            tag, key = k.rsplit("/", 1)
+            out.setdefault(tag, {})[key] = z[k]
     for d in out.values():
         d["spec"] = json.loads(str(d["spec"]))
         for junk in ("robot_id", "exploration", "unknown_obs_detection"):
@@ -32,7 +33,7 @@ def load_tracking_golden():
 
 def golden_initial_state(d):
     """X0 as LocalTrackingController received it (yaw appended for SingleIntegrator2D)."""
-    if d["spec"]["model"] == "SingleIntegrator2D":
+    if d["spec"]["model"] in ("SingleIntegrator2D", "DoubleIntegrator2D"):
         return np.append(d["X"][0], d["yaw"][0])[None]
     return d["X"][0][None]
 
@@ -87,6 +88,8 @@ def random_closed_loop_case(model, N, K, seed, dynamic=False):
         pos[todo[ok]] = cand[ok]; todo = todo[~ok]
     if model == "SingleIntegrator2D":
         X0 = np.hstack([pos, rng.uniform(-np.pi, np.pi, (N, 1))])
+    elif model == "DoubleIntegrator2D":
+        X0 = np.hstack([pos, rng.uniform(-0.6, 0.6, (N, 2)), rng.uniform(-np.pi, np.pi, (N, 1))])
     elif model == "Quad3D":
         X0 = np.zeros((N, 12)); X0[:, :2] = pos; X0[:, 2] = rng.uniform(1, 2, N)
     else:
