@@ -176,6 +176,7 @@ ANGLE_UNPASSED = {                    # tracking.py:352-357
     "DynamicUnicycle2D": 1.2 * np.pi,
     "KinematicBicycle2D": 2.0 * np.pi, "KinematicBicycle2D_C3BF": 2.0 * np.pi,
     "KinematicBicycle2D_DPCBF": 2.0 * np.pi, "DoubleIntegrator2D": 2.0 * np.pi, "Quad2D": 2.0 * np.pi,
+    "Unicycle2D": 1.2 * np.pi,
 }
 
 

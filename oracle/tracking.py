@@ -59,6 +59,8 @@ class OracleTrackingController:
             elif X0.size == 4:
                 X0 = np.array([X0[0], X0[1], X0[2], 0, 0, X0[3], 0, 0, 0, 0, 0, 0], float)
             self.yaw = float(X0[5])
+        elif self.name == "Unicycle2D":                         # no padding (robots/robot.py:84-90)
+            self.yaw = float(X0[2])
         else:
             if X0.size == 3:
                 X0 = np.append(X0, 0.0)
@@ -97,6 +99,8 @@ class OracleTrackingController:
         if n == "DoubleIntegrator2D":                           # double_integrator2D.py:147-153
             k_a = s.get("nominal_k_a", 1.0)
             return np.array([k_a * (0.0 - X[2]), k_a * (0.0 - X[3])])
+        if n == "Unicycle2D":                                   # unicycle2D.py:88-89
+            return np.zeros(2)
         if n == "DynamicUnicycle2D":
             return np.array([s.get("nominal_k_a", 1.0) * (0.0 - X[3]), 0.0])
         if n.startswith("KinematicBicycle2D"):
@@ -111,7 +115,7 @@ class OracleTrackingController:
 
     def has_stopped(self):
         n, X = self.name, self.X
-        if n == "SingleIntegrator2D":
+        if n in ("SingleIntegrator2D", "Unicycle2D"):
             return True
         if n == "DoubleIntegrator2D":                           # :155-156
             return np.linalg.norm(X[2:4]) < 0.05
@@ -138,6 +142,8 @@ class OracleTrackingController:
         n, m = self.name, self.model
         if n == "SingleIntegrator2D":
             return m.nominal_input(self.X, goal, 0.05, k_v)
+        if n == "Unicycle2D":                                   # facade: (X, goal, d_min, k_omega, k_v) (robots/robot.py:404-405)
+            return m.nominal_input(self.X, goal, 0.05, k_omega, k_v)
         if n == "DoubleIntegrator2D":                           # facade: (X, goal, d_min, k_v, k_a) (robots/robot.py:408-409)
             return m.nominal_input(self.X, goal, 0.05, k_v, k_a)
         if n == "DynamicUnicycle2D":

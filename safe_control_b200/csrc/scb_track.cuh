@@ -110,6 +110,35 @@ struct ModelLoop<SCB_DOUBLE_INTEGRATOR_2D> {
   static SCB_HD void att_velocity(const double* x, const double*, double& vx, double& vy) { vx = x[2]; vy = x[3]; }
 };
 
+// Unicycle2D (robots/unicycle2D.py): X = [x, y, theta], U = [v, omega]
+template <>
+struct ModelLoop<SCB_UNICYCLE_2D> {
+  static constexpr int NX = 3, NU = 2, NPOS = 2;
+  static constexpr bool HAS_ATT = false;
+  static SCB_HD double half_angle() { return 0.6 * kPi; }     // angle_unpassed = 1.2 pi (tracking.py:354-355)
+  static SCB_HD double yaw_of(const double* x, double) { return x[2]; }
+  // :70-86; the facade passes (d_min, k_omega, k_v) (robots/robot.py:404-405)
+  static SCB_HD void nominal(const scb_params&, const scb_track& t, const double* x, const double* g, double* u) {
+    const double dx = x[0] - g[0], dy = x[1] - g[1];
+    const double dist = fmax(sqrt(dx * dx + dy * dy) - 0.05, 0.05);
+    const double err = wrap_floor(atan2(g[1] - x[1], g[0] - x[0]) - x[2]);
+    u[1] = t.k_omega * err;
+    u[0] = (fabs(err) > 90.0 * (kPi / 180.0)) ? 0.0 : t.k_v * dist * cos(err);
+  }
+  static SCB_HD void stop(const scb_params&, const scb_track&, const double*, double* u) { u[0] = 0.0; u[1] = 0.0; }   // :88-89
+  static SCB_HD bool has_stopped(const double*) { return true; }                                                      // :91-93
+  static SCB_HD void rotate_to(const scb_params&, const scb_track&, const double* x, double, double th, double* u,
+                               double&) {                                                                            // :95-98
+    u[0] = 0.0; u[1] = 2.0 * wrap_floor(th - x[2]);
+  }
+  static SCB_HD void step(const scb_params& p, double* x, const double* u) {                                          // :65-68
+    double s, c; sincos_pair(x[2], s, c);
+    x[0] = x[0] + (c * u[0]) * p.dt;
+    x[1] = x[1] + (s * u[0]) * p.dt;
+    x[2] = wrap_floor(x[2] + u[1] * p.dt);
+  }
+};
+
 template <>
 struct ModelLoop<SCB_DYNAMIC_UNICYCLE_2D> {
   static constexpr int NX = 4, NU = 2, NPOS = 2;

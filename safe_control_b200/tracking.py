@@ -36,6 +36,10 @@ def pad_initial_state(model, X0):
         elif n != 3:
             raise ValueError("Invalid initial state dimension for SingleIntegrator2D")
         return np.ascontiguousarray(X0[:, :2]), np.ascontiguousarray(X0[:, 2])
+    if model == "Unicycle2D":                                    # no padding in tracking.py; robots/robot.py:84-90
+        if n != 3:
+            raise ValueError("Invalid initial state dimension for Unicycle2D")
+        return np.ascontiguousarray(X0), np.ascontiguousarray(X0[:, 2])
     if model == "DoubleIntegrator2D":                            # tracking.py:70-77; robots/robot.py:80-82: [x, y, vx, vy, theta]
         if n == 3:
             X0 = np.hstack([X0[:, 0:2], np.zeros((N, 2)), X0[:, 2:3]])

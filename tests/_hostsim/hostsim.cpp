@@ -216,6 +216,7 @@ int hostsim_select_obstacles(const scb_params* p, int N, int K, int M, const dou
       SELCASE(SCB_QUAD_3D)
       SELCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       SELCASE(SCB_DOUBLE_INTEGRATOR_2D)
+      SELCASE(SCB_UNICYCLE_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -237,6 +238,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       PRECASE(SCB_QUAD_3D)
       PRECASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       PRECASE(SCB_DOUBLE_INTEGRATOR_2D)
+      PRECASE(SCB_UNICYCLE_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -283,6 +285,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       POSTCASE(SCB_QUAD_3D)
       POSTCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       POSTCASE(SCB_DOUBLE_INTEGRATOR_2D)
+      POSTCASE(SCB_UNICYCLE_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }

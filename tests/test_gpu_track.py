@@ -138,6 +138,7 @@ def test_select_obstacles_matches_oracle(model):
     ("SingleIntegrator2D", "cbf_qp", False),
     ("KinematicBicycle2D", "cbf_qp", False),
     ("DoubleIntegrator2D", "cbf_qp", False),
+    ("Unicycle2D", "cbf_qp", False),            # (oracle only: the reference's own Unicycle2D + cbf_qp loop raises)
     ("KinematicBicycle2D_C3BF", "cbf_qp", True),
     ("DynamicUnicycle2D", "optimal_decay_cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True),
@@ -169,7 +170,7 @@ def test_random_closed_loop_matches_oracle(model, controller, dynamic):
     assert len(seen) >= 2
 
 
-@pytest.mark.parametrize("model", ["DynamicUnicycle2D", "Quad3D"])
+@pytest.mark.parametrize("model", ["DynamicUnicycle2D", "Quad3D", "Unicycle2D", "DoubleIntegrator2D"])
 def test_mpc_closed_loop(model):
     """MPC in the loop: solved only in 'track' (mpc_cbf.py:379-381), u_prev carried, no collision, progress."""
     from safe_control_b200 import BatchedTrackingController
@@ -189,7 +190,7 @@ def test_mpc_closed_loop(model):
         np.testing.assert_array_equal(o["u_prev"][tk], o["U"][tk])
     assert (o["ret"] != -2).mean() >= 0.9
     assert np.isfinite(o["X"]).all() and np.isfinite(o["U"]).all()
-    if model == "DynamicUnicycle2D":          # (Quad3D spends these 3 s in 'stop' / 'rotate': yaw gain 2, quad3D.py:244-268)
+    if model in ("DynamicUnicycle2D", "Unicycle2D", "DoubleIntegrator2D"):          # (Quad3D spends these 3 s in 'stop' / 'rotate': yaw gain 2, quad3D.py:244-268)
         moved = np.linalg.norm(o["X"][:, :2] - start[:, :2], axis=1)
         assert np.median(moved) > 0.5
 
@@ -199,6 +200,7 @@ def test_mpc_closed_loop(model):
     ("DynamicUnicycle2D", "cbf_qp", False, 40),           # RPL = 2 geometry of the fused kernel
     ("SingleIntegrator2D", "cbf_qp", False, 8),
     ("DoubleIntegrator2D", "cbf_qp", False, 8),
+    ("Unicycle2D", "cbf_qp", False, 8),
     ("KinematicBicycle2D_C3BF", "cbf_qp", True, 8),
     ("KinematicBicycle2D_DPCBF", "cbf_qp", True, 8),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True, 16),

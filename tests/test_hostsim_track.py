@@ -122,6 +122,7 @@ def test_selection_matches_oracle(model):
     ("SingleIntegrator2D", "cbf_qp", False),
     ("KinematicBicycle2D", "cbf_qp", False),
     ("DoubleIntegrator2D", "cbf_qp", False),
+    ("Unicycle2D", "cbf_qp", False),            # (oracle only: the reference's own Unicycle2D + cbf_qp loop raises)
     ("KinematicBicycle2D_C3BF", "cbf_qp", True),
     ("DynamicUnicycle2D", "optimal_decay_cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True),
