@@ -170,7 +170,7 @@ def test_random_closed_loop_matches_oracle(model, controller, dynamic):
     assert len(seen) >= 2
 
 
-@pytest.mark.parametrize("model", ["DynamicUnicycle2D", "Quad3D", "Unicycle2D"])
+@pytest.mark.parametrize("model", ["DynamicUnicycle2D", "Quad3D", "Unicycle2D", "DoubleIntegrator2D"])
 def test_mpc_closed_loop(model):
     """MPC in the loop: solved only in 'track' (mpc_cbf.py:379-381), u_prev carried, no collision, progress."""
     from safe_control_b200 import BatchedTrackingController
@@ -190,9 +190,9 @@ def test_mpc_closed_loop(model):
         np.testing.assert_array_equal(o["u_prev"][tk], o["U"][tk])
     assert (o["ret"] != -2).mean() >= 0.9
     assert np.isfinite(o["X"]).all() and np.isfinite(o["U"]).all()
-    if model in ("DynamicUnicycle2D", "Unicycle2D"):          # (Quad3D spends these 3 s in 'stop' / 'rotate': yaw gain 2, quad3D.py:244-268)
+    if model != "Quad3D":                     # (Quad3D spends these 3 s in 'stop' / 'rotate': yaw gain 2, quad3D.py:244-268)
         moved = np.linalg.norm(o["X"][:, :2] - start[:, :2], axis=1)
-        assert np.median(moved) > 0.5
+        assert np.median(moved) > (0.3 if model == "DoubleIntegrator2D" else 0.5)   # (DI first brakes its random start velocity)
 
 
 @pytest.mark.parametrize("model,controller,dynamic,M", [
