@@ -232,5 +232,5 @@ def test_fused_run_equals_per_step_path(model, controller, dynamic, M):
         # same source, but nvcc may contract a*b+c differently once the bodies are inlined into one kernel: allow ulps
         np.testing.assert_allclose(x, y, rtol=0, atol=1e-11, err_msg=k)
     print(model, controller, worst)
-    # the case mixes finished and running agents (DoubleIntegrator2D accelerates from rest: nobody is done in 90 steps)
-    assert 0 < int(a.done.sum()) < N or T < 50 or model == "DoubleIntegrator2D"
+    # the case mixes finished and running agents (DoubleIntegrator2D / Unicycle2D are slower: nobody is done in 90 steps)
+    assert 0 < int(a.done.sum()) < N or T < 50 or model in ("DoubleIntegrator2D", "Unicycle2D")
