@@ -52,6 +52,23 @@ def test_mpc_superellipsoid_rows_vs_oracle(model):
     print(model, stats)
 
 
+@pytest.mark.parametrize("model", ["KinematicBicycle2D_C3BF", "KinematicBicycle2D_DPCBF", "Unicycle2D", "DoubleIntegrator2D",
+                                   "Quad2D", "DynamicUnicycle2D", "Quad3D"])
+def test_mpc_edge_shapes(model):
+    """Smallest and largest compiled shapes, agents without any obstacle (all dummy rows, mpc_cbf.py:346-364) and with
+    one: finite inputs inside the box, a definite status, and the no-obstacle agent always solves."""
+    for M, H in ((1, 1), (4, 3), (16, 16 if model != "Quad3D" else 12)):
+        sc = scenes.make_scene(model, 5, M, seed=5)
+        p, spec = resolve_params(sc["spec"], "mpc_cbf", lib=hostsim())
+        nobs = sc["nobs"].copy(); nobs[0] = 0; nobs[1] = min(1, M)
+        out = hs_mpccbf_solve(p, H, sc["X"], sc["goal"], sc["u_prev"], sc["OBS"], nobs)
+        nu = p.nu
+        lb = np.array(list(p.u_lb)[:nu]); ub = np.array(list(p.u_ub)[:nu])
+        assert np.isfinite(out["U"]).all() and ((out["U"] >= lb - 1e-12) & (out["U"] <= ub + 1e-12)).all(), (model, M, H)
+        assert set(np.unique(out["status"])) <= {0, 1, 2}, (model, M, H, out["status"])
+        assert out["status"][0] == 0, (model, M, H)
+
+
 def test_mpc_no_obstacles_is_box_clipped_tracking():
     """Without obstacles the solution must equal the unconstrained-by-CBF MPC; with the goal far
     ahead and straight, full acceleration saturates: u0 = [a_max, ~0]."""
