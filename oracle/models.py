@@ -586,6 +586,21 @@ class Quad2D(Model):
     def u_bounds(self):
         return np.full(2, self.spec["f_min"]), np.full(2, self.spec["f_max"])
 
+    def nominal_input(self, X, G, k_px=3.0, k_dx=0.5, k_pz=0.1, k_dz=0.5, k_p_theta=0.05, k_d_theta=0.05):
+        """cascaded PD law (quad2D.py:87-150)"""
+        m, g = self.spec["mass"], 9.81
+        f_min, f_max = self.spec["f_min"], self.spec["f_max"]
+        r = self.radius
+        x, z, theta, x_dot, z_dot, theta_dot = X
+        a_d_x = k_px * (G[0] - x) + k_dx * (-x_dot)
+        a_d_z = k_pz * (G[1] - z) + k_dz * (-z_dot) + g
+        T = m * math.sqrt(a_d_x ** 2 + a_d_z ** 2)
+        theta_d = -math.atan2(a_d_x, a_d_z)
+        e = theta_d - theta
+        e = math.atan2(math.sin(e), math.cos(e))
+        tau = float(np.clip(k_p_theta * e + k_d_theta * (-theta_dot), -1, 1))
+        return np.array([np.clip((T + tau / r) / 2.0, f_min, f_max), np.clip((T - tau / r) / 2.0, f_min, f_max)])
+
     def agent_barrier(self, X, obs):
         """-> h, h_dot, dh_dot_dx(6,)   (:166-177; circle only, flag ignored)"""
         d = X[0:2] - obs[0:2]

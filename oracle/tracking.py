@@ -61,6 +61,10 @@ class OracleTrackingController:
             self.yaw = float(X0[5])
         elif self.name == "Unicycle2D":                         # no padding (robots/robot.py:84-90)
             self.yaw = float(X0[2])
+        elif self.name == "Quad2D":                             # tracking.py:81-85: [x, z, theta, x_dot, z_dot, theta_dot]
+            if X0.size in (2, 3):
+                X0 = np.array([X0[0], X0[1], 0.0, 0.0, 0.0, 0.0])
+            self.yaw = float(X0[2])
         else:
             if X0.size == 3:
                 X0 = np.append(X0, 0.0)
@@ -88,6 +92,8 @@ class OracleTrackingController:
 
     # ---- robots/robot.py facade pieces --------------------------------------------------------
     def is_in_fov(self, point):
+        if self.name == "Quad2D":                               # robots/robot.py:858-860: always in view
+            return True
         to_point = np.asarray(point[:2], float) - self.X[:2]
         ang = np.arctan2(to_point[1], to_point[0])
         return abs(angle_normalize(ang - self.yaw)) <= self.fov_angle / 2
@@ -101,6 +107,8 @@ class OracleTrackingController:
             return np.array([k_a * (0.0 - X[2]), k_a * (0.0 - X[3])])
         if n == "Unicycle2D":                                   # unicycle2D.py:88-89
             return np.zeros(2)
+        if n == "Quad2D":                                       # quad2D.py:152-161: nominal input towards the current position
+            return self.model.nominal_input(X, X[0:2])
         if n == "DynamicUnicycle2D":
             return np.array([s.get("nominal_k_a", 1.0) * (0.0 - X[3]), 0.0])
         if n.startswith("KinematicBicycle2D"):
@@ -119,6 +127,8 @@ class OracleTrackingController:
             return True
         if n == "DoubleIntegrator2D":                           # :155-156
             return np.linalg.norm(X[2:4]) < 0.05
+        if n == "Quad2D":                                       # quad2D.py:163-165
+            return np.linalg.norm(X[3:5]) < 0.05
         if n == "Quad3D":
             return np.linalg.norm(X[6:9]) < 0.05 and np.linalg.norm(X[9:12]) < 0.05
         return abs(X[3]) < 0.05
@@ -187,6 +197,8 @@ class OracleTrackingController:
         if self.state_machine == "rotate":
             rotate_goal = self.waypoints[self.current_goal_index]
             goal_angle = np.arctan2(rotate_goal[1] - self.X[1], rotate_goal[0] - self.X[0])
+            if self.name == "Quad2D":                           # tracking.py:512-513: skips the 'rotate' state
+                self.state_machine = "track"
             if not self.enable_rotation:
                 self.state_machine = "track"
             if abs(self.yaw - goal_angle) > self.rotation_threshold:

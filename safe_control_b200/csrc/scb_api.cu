@@ -275,8 +275,8 @@ int scb_select_obstacles(const scb_params* p, int N, int K, int M, const double*
 #define SEL(MODEL) case MODEL: select_kernel<MODEL><<<grid, kTrackBlock, smem, s>>>(*p, N, K, M, X, yaw, SCENE, sstride, OBS, nobs, idx); break;
   switch (p->model) {
     SEL(SCB_SINGLE_INTEGRATOR_2D) SEL(SCB_DYNAMIC_UNICYCLE_2D) SEL(SCB_KINEMATIC_BICYCLE_2D)
-    SEL(SCB_KINEMATIC_BICYCLE_2D_C3BF) SEL(SCB_QUAD_3D) SEL(SCB_KINEMATIC_BICYCLE_2D_DPCBF) SEL(SCB_DOUBLE_INTEGRATOR_2D) SEL(SCB_UNICYCLE_2D)
-    default: return SCB_ERR_UNSUPPORTED;               // Quad2D / Manipulator2D: closed-loop laws not built yet
+    SEL(SCB_KINEMATIC_BICYCLE_2D_C3BF) SEL(SCB_QUAD_3D) SEL(SCB_KINEMATIC_BICYCLE_2D_DPCBF) SEL(SCB_DOUBLE_INTEGRATOR_2D) SEL(SCB_UNICYCLE_2D) SEL(SCB_QUAD_2D)
+    default: return SCB_ERR_UNSUPPORTED;               // Manipulator2D: closed-loop laws not built
   }
 #undef SEL
   CK(cudaGetLastError());
@@ -295,8 +295,7 @@ static int track_check(const scb_params* p, const scb_track* t) {
       (t->K > 0 && !t->SCENE))
     return SCB_ERR_BAD_ARG;
   if (t->controller == SCB_CTRL_MPC_CBF && (!t->u_prev || !t->track_flag || t->H < 1)) return SCB_ERR_BAD_ARG;
-  if (p->model == SCB_QUAD_2D || p->model == SCB_MANIPULATOR_2D)
-    return SCB_ERR_UNSUPPORTED;                        // loop laws not built yet
+  if (p->model == SCB_MANIPULATOR_2D) return SCB_ERR_UNSUPPORTED;   // (the arm is not driven by LocalTrackingController)                        // loop laws not built yet
   if (t->controller != SCB_CTRL_MPC_CBF && p->model == SCB_QUAD_3D) return SCB_ERR_UNSUPPORTED;
   if (t->controller != SCB_CTRL_CBF_QP && p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF) return SCB_ERR_UNSUPPORTED;
   if (t->controller == SCB_CTRL_OPTIMAL_DECAY && (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_DOUBLE_INTEGRATOR_2D ||
@@ -310,7 +309,7 @@ static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream
 #define PRE(MODEL) case MODEL: launch_pre<MODEL>(*p, *t, s, smc); break;
   switch (p->model) {
     PRE(SCB_SINGLE_INTEGRATOR_2D) PRE(SCB_DYNAMIC_UNICYCLE_2D) PRE(SCB_KINEMATIC_BICYCLE_2D)
-    PRE(SCB_KINEMATIC_BICYCLE_2D_C3BF) PRE(SCB_QUAD_3D) PRE(SCB_KINEMATIC_BICYCLE_2D_DPCBF) PRE(SCB_DOUBLE_INTEGRATOR_2D) PRE(SCB_UNICYCLE_2D)
+    PRE(SCB_KINEMATIC_BICYCLE_2D_C3BF) PRE(SCB_QUAD_3D) PRE(SCB_KINEMATIC_BICYCLE_2D_DPCBF) PRE(SCB_DOUBLE_INTEGRATOR_2D) PRE(SCB_UNICYCLE_2D) PRE(SCB_QUAD_2D)
   }
 #undef PRE
   if (t->dynamic_obs && t->K > 0) dyn_obs_kernel<<<(t->K + 127) / 128, 128, 0, s>>>(t->SCENE, t->K, p->dt);
@@ -330,7 +329,7 @@ static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream
 #define POST(MODEL) case MODEL: launch_post<MODEL>(*p, *t, s, smc); break;
   switch (p->model) {
     POST(SCB_SINGLE_INTEGRATOR_2D) POST(SCB_DYNAMIC_UNICYCLE_2D) POST(SCB_KINEMATIC_BICYCLE_2D)
-    POST(SCB_KINEMATIC_BICYCLE_2D_C3BF) POST(SCB_QUAD_3D) POST(SCB_KINEMATIC_BICYCLE_2D_DPCBF) POST(SCB_DOUBLE_INTEGRATOR_2D) POST(SCB_UNICYCLE_2D)
+    POST(SCB_KINEMATIC_BICYCLE_2D_C3BF) POST(SCB_QUAD_3D) POST(SCB_KINEMATIC_BICYCLE_2D_DPCBF) POST(SCB_DOUBLE_INTEGRATOR_2D) POST(SCB_UNICYCLE_2D) POST(SCB_QUAD_2D)
   }
 #undef POST
   CK(cudaGetLastError());
@@ -351,7 +350,7 @@ static bool fused_applicable(const scb_params* p, const scb_track* t) {
     return t->M + 4 <= 64 && (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_DYNAMIC_UNICYCLE_2D ||
                               p->model == SCB_KINEMATIC_BICYCLE_2D || p->model == SCB_KINEMATIC_BICYCLE_2D_C3BF ||
                               p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF || p->model == SCB_DOUBLE_INTEGRATOR_2D ||
-                              p->model == SCB_UNICYCLE_2D);
+                              p->model == SCB_UNICYCLE_2D || p->model == SCB_QUAD_2D);
   if (t->controller == SCB_CTRL_OPTIMAL_DECAY)
     return t->M <= 64 && (p->model == SCB_DYNAMIC_UNICYCLE_2D || p->model == SCB_KINEMATIC_BICYCLE_2D ||
                           p->model == SCB_KINEMATIC_BICYCLE_2D_C3BF);
@@ -370,6 +369,7 @@ static bool run_fused(const scb_params* p, const scb_track* t, int n_steps, cuda
       case SCB_KINEMATIC_BICYCLE_2D_DPCBF: return launch_fused<SCB_KINEMATIC_BICYCLE_2D_DPCBF, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
       case SCB_DOUBLE_INTEGRATOR_2D: return launch_fused<SCB_DOUBLE_INTEGRATOR_2D, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
       case SCB_UNICYCLE_2D: return launch_fused<SCB_UNICYCLE_2D, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
+      case SCB_QUAD_2D: return launch_fused<SCB_QUAD_2D, SCB_CTRL_CBF_QP, 1>(*p, *t, n_steps, s);
       default: return false;
     }
   }

@@ -139,6 +139,49 @@ struct ModelLoop<SCB_UNICYCLE_2D> {
   }
 };
 
+// Quad2D (robots/quad2D.py): X = [x, z, theta, x_dot, z_dot, theta_dot], U = rotor forces [F_r, F_l]
+template <>
+struct ModelLoop<SCB_QUAD_2D> {
+  static constexpr int NX = 6, NU = 2, NPOS = 2;
+  static constexpr bool HAS_ATT = false;
+  static SCB_HD double half_angle() { return kPi; }           // tracking.py:352-353
+  static SCB_HD double yaw_of(const double* x, double) { return x[2]; }
+  // cascaded PD law with the function's own default gains (:87-150; the facade passes no gains, robots/robot.py:410-413)
+  static SCB_HD void nominal(const scb_params& p, const scb_track&, const double* x, const double* g, double* u) {
+    const double grav = 9.81;
+    const double adx = 3.0 * (g[0] - x[0]) + 0.5 * (-x[3]);
+    const double adz = (0.1 * (g[1] - x[1]) + 0.5 * (-x[4])) + grav;
+    const double T = p.mass * sqrt(adx * adx + adz * adz);
+    const double th_d = -atan2(adx, adz);
+    double e = th_d - x[2];
+    e = atan2(sin(e), cos(e));
+    const double tau = clipd(0.05 * e + 0.05 * (-x[5]), -1.0, 1.0);
+    u[0] = clipd((T + tau / p.radius) / 2.0, p.u_lb[0], p.u_ub[0]);
+    u[1] = clipd((T - tau / p.radius) / 2.0, p.u_lb[0], p.u_ub[0]);
+  }
+  static SCB_HD void stop(const scb_params& p, const scb_track& t, const double* x, double* u) {        // :152-161
+    const double here[2] = {x[0], x[1]};
+    nominal(p, t, x, here, u);
+  }
+  static SCB_HD bool has_stopped(const double* x) { return sqrt(x[3] * x[3] + x[4] * x[4]) < 0.05; }     // :163-165
+  static SCB_HD void rotate_to(const scb_params&, const scb_track&, const double* x, double, double th, double* u,
+                               double&) {                                                              // :167-171
+    u[0] = 0.0; u[1] = 2.0 * wrap_floor(th - x[2]);
+  }
+  static SCB_HD void step(const scb_params& p, double* x, const double* u) {                            // :46-90
+    double s, c; sincos_pair(x[2], s, c);
+    const double us = u[0] + u[1];
+    const double f3 = 0.0 + (-s / p.mass) * u[0] + (-s / p.mass) * u[1];
+    const double f4 = -9.81 + (c / p.mass) * u[0] + (c / p.mass) * u[1];
+    const double f5 = 0.0 + (p.radius / p.Iy) * u[0] + (-(p.radius / p.Iy)) * u[1];
+    (void)us;
+    const double x3 = x[3], x4 = x[4], x5 = x[5];
+    x[0] = x[0] + x3 * p.dt; x[1] = x[1] + x4 * p.dt;
+    x[2] = wrap_floor(x[2] + x5 * p.dt);
+    x[3] = x3 + f3 * p.dt; x[4] = x4 + f4 * p.dt; x[5] = x5 + f5 * p.dt;
+  }
+};
+
 template <>
 struct ModelLoop<SCB_DYNAMIC_UNICYCLE_2D> {
   static constexpr int NX = 4, NU = 2, NPOS = 2;
@@ -393,6 +436,7 @@ SCB_HD bool update_goal(const scb_track& t, const double* x, double yaw, const d
   if (sm == SCB_SM_ROTATE && wi < nwp) {
     const double* rg = wp + (size_t)wi * 3;
     const double goal_angle = atan2(rg[1] - x[1], rg[0] - x[0]);
+    if (MODEL == SCB_QUAD_2D) sm = SCB_SM_TRACK;              // "Those skip 'rotate' state" (:512-513)
     if (!t.enable_rotation) sm = SCB_SM_TRACK;
     if (fabs(yaw - goal_angle) > t.rotation_threshold) {
 #pragma unroll

@@ -40,6 +40,12 @@ def pad_initial_state(model, X0):
         if n != 3:
             raise ValueError("Invalid initial state dimension for Unicycle2D")
         return np.ascontiguousarray(X0), np.ascontiguousarray(X0[:, 2])
+    if model == "Quad2D":                                        # tracking.py:81-85
+        if n in (2, 3):
+            X0 = np.hstack([X0[:, 0:2], np.zeros((N, 4))])
+        elif n != 6:
+            raise ValueError("Invalid initial state dimension for Quad2D")
+        return np.ascontiguousarray(X0), np.ascontiguousarray(X0[:, 2])
     if model == "DoubleIntegrator2D":                            # tracking.py:70-77; robots/robot.py:80-82: [x, y, vx, vy, theta]
         if n == 3:
             X0 = np.hstack([X0[:, 0:2], np.zeros((N, 2)), X0[:, 2:3]])
@@ -137,6 +143,8 @@ class TrackerHostState:
                 continue
             to = g[:2] - self.X[i, :2]
             in_fov = abs(_angle_normalize(math.atan2(to[1], to[0]) - self.yaw[i])) <= self.fov_angle / 2
+            if self.model == "Quad2D":                                   # robots/robot.py:858-860: always in view
+                in_fov = True
             if not in_fov:
                 if self.spec.get("exploration", False):
                     self.sm[i] = _abi.SM_ROTATE; self.has_goal[i] = 1; self.goal[i] = g[: self.npos]

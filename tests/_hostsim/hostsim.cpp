@@ -217,6 +217,7 @@ int hostsim_select_obstacles(const scb_params* p, int N, int K, int M, const dou
       SELCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       SELCASE(SCB_DOUBLE_INTEGRATOR_2D)
       SELCASE(SCB_UNICYCLE_2D)
+      SELCASE(SCB_QUAD_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -239,6 +240,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       PRECASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       PRECASE(SCB_DOUBLE_INTEGRATOR_2D)
       PRECASE(SCB_UNICYCLE_2D)
+      PRECASE(SCB_QUAD_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }
@@ -286,6 +288,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       POSTCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       POSTCASE(SCB_DOUBLE_INTEGRATOR_2D)
       POSTCASE(SCB_UNICYCLE_2D)
+      POSTCASE(SCB_QUAD_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
   }

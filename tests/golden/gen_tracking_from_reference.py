@@ -165,6 +165,10 @@ def scenarios2():
     yield ("di_stop_rotate", LocalTrackingController, np.array([2.0, 2.0, 0.6, -0.3, -math.pi / 2]),
            {"model": "DoubleIntegrator2D", "v_max": 1.0, "a_max": 1.0, "radius": 0.25},
            np.array([[2, 2, 0], [2.5, 6.5, 0], [6, 4.2, 0]], float), TEST_TRACKING_OBS[:6], 400, True, 16)
+    # Quad2D (x-z plane, two rotor forces; cascaded PD nominal law, quad2D.py:92-150)
+    yield ("quad2d_tracking", LocalTrackingController, np.array([2.0, 2.0, 0.0]),
+           {"model": "Quad2D", "f_min": 3.0, "f_max": 10.0, "sensor": None, "radius": 0.25},
+           np.array([[2, 2, 0], [2, 12, 0], [12, 12, 0]], float), TEST_TRACKING_OBS, 500, True, None)
 
 
 def main(gen=scenarios, fname="ref_tracking.npz"):

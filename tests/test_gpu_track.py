@@ -139,6 +139,8 @@ def test_select_obstacles_matches_oracle(model):
     ("KinematicBicycle2D", "cbf_qp", False),
     ("DoubleIntegrator2D", "cbf_qp", False),
     ("Unicycle2D", "cbf_qp", False),            # (oracle only: the reference's own Unicycle2D + cbf_qp loop raises)
+    ("Quad2D", "cbf_qp", False),
+    ("Quad2D", "optimal_decay_cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "cbf_qp", True),
     ("DynamicUnicycle2D", "optimal_decay_cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True),
@@ -201,6 +203,7 @@ def test_mpc_closed_loop(model):
     ("SingleIntegrator2D", "cbf_qp", False, 8),
     ("DoubleIntegrator2D", "cbf_qp", False, 8),
     ("Unicycle2D", "cbf_qp", False, 8),
+    ("Quad2D", "cbf_qp", False, 8),
     ("KinematicBicycle2D_C3BF", "cbf_qp", True, 8),
     ("KinematicBicycle2D_DPCBF", "cbf_qp", True, 8),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True, 16),
@@ -233,4 +236,4 @@ def test_fused_run_equals_per_step_path(model, controller, dynamic, M):
         np.testing.assert_allclose(x, y, rtol=0, atol=1e-11, err_msg=k)
     print(model, controller, worst)
     # the case mixes finished and running agents (DoubleIntegrator2D / Unicycle2D are slower: nobody is done in 90 steps)
-    assert 0 < int(a.done.sum()) < N or T < 50 or model in ("DoubleIntegrator2D", "Unicycle2D")
+    assert 0 < int(a.done.sum()) < N or T < 50 or model in ("DoubleIntegrator2D", "Unicycle2D", "Quad2D")

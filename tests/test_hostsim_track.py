@@ -123,6 +123,8 @@ def test_selection_matches_oracle(model):
     ("KinematicBicycle2D", "cbf_qp", False),
     ("DoubleIntegrator2D", "cbf_qp", False),
     ("Unicycle2D", "cbf_qp", False),            # (oracle only: the reference's own Unicycle2D + cbf_qp loop raises)
+    ("Quad2D", "cbf_qp", False),
+    ("Quad2D", "optimal_decay_cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "cbf_qp", True),
     ("DynamicUnicycle2D", "optimal_decay_cbf_qp", False),
     ("KinematicBicycle2D_C3BF", "optimal_decay_cbf_qp", True),
@@ -152,7 +154,8 @@ def test_random_closed_loop_matches_oracle(model, controller, dynamic):
             np.testing.assert_allclose(tr.bufs["X"][i], o.X, rtol=0, atol=1e-7, err_msg=f"step {k} agent {i}")
             if r in (-1, -2):
                 done[i] = True; rets[i] = r
-    assert len(n_sm) >= 2, n_sm          # the scenes exercise more than one state of the machine
+    # the scenes exercise more than one state of the machine (Quad2D is always in view and skips 'rotate': tracking.py:512)
+    assert len(n_sm) >= 2 or model == "Quad2D", n_sm
 
 
 def test_mpc_closed_loop_runs_and_respects_state_machine():

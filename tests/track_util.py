@@ -92,6 +92,8 @@ def random_closed_loop_case(model, N, K, seed, dynamic=False):
         X0 = np.hstack([pos, rng.uniform(-0.6, 0.6, (N, 2)), rng.uniform(-np.pi, np.pi, (N, 1))])
     elif model == "Unicycle2D":
         X0 = np.hstack([pos, rng.uniform(-np.pi, np.pi, (N, 1))])
+    elif model == "Quad2D":
+        X0 = np.hstack([pos, rng.uniform(-0.2, 0.2, (N, 1)), rng.uniform(-0.5, 0.5, (N, 2)), rng.uniform(-0.1, 0.1, (N, 1))])
     elif model == "Quad3D":
         X0 = np.zeros((N, 12)); X0[:, :2] = pos; X0[:, 2] = rng.uniform(1, 2, N)
     else:
