@@ -169,7 +169,7 @@ def test_random_closed_loop_matches_oracle(model, controller, dynamic):
             assert r == o["ret"][i], (k, i, r, o["ret"][i])
             np.testing.assert_allclose(o["X"][i], oc.X, rtol=0, atol=1e-7, err_msg=f"step {k} agent {i}")
             done[i] = r in (-1, -2)
-    assert len(seen) >= 2
+    assert len(seen) >= 2 or model == "Quad2D"     # (Quad2D is always in view and skips 'rotate': tracking.py:512)
 
 
 @pytest.mark.parametrize("model", ["DynamicUnicycle2D", "Quad3D", "Unicycle2D", "DoubleIntegrator2D"])
