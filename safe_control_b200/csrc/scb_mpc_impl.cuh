@@ -195,15 +195,15 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* X, cons
     if (gpb < 1) gpb = 1;
   }
   const size_t smem = per * gpb;
-  auto kern = mpc_kernel<MODEL, kLanes>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return SCB_ERR_TOO_LARGE;
   long blocks = ((long)N + gpb - 1) / gpb;
   if (blocks > sm_count) blocks = sm_count;
   // schedule (needs the caller's workspace; without one, or when every agent starts in the first wave, index order)
   const int32_t* order = nullptr;
   const bool scheduled = workspace && workspace_bytes >= mpc_workspace_bytes(N) && (long)N > blocks * gpb;
-  if (count_only) { *count_only = scheduled ? 3 : 1; return SCB_OK; }
+  if (count_only) { *count_only = scheduled ? 3 : 1; return SCB_OK; }       // (pure host arithmetic: no CUDA call)
+  auto kern = mpc_kernel<MODEL, kLanes>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return SCB_ERR_TOO_LARGE;
   if (scheduled) {
     int32_t* hist = (int32_t*)workspace;
     int32_t* bin_of = hist + kMpcBins;

@@ -79,6 +79,21 @@ def test_robot_spec_overrides(lib):
         resolve_params({"model": "Unicycle2D"}, "optimal_decay_cbf_qp")
 
 
+def test_mpc_launch_count_and_workspace_are_host_arithmetic(lib):
+    """scb_mpccbf_launch_count / scb_mpccbf_workspace_bytes need no device: 1 launch in index order, 3 with the
+    hardest-first schedule once the batch exceeds one persistent wave (148 SMs x agents per CTA), +1 general-row launch
+    when superellipsoid rows are enabled."""
+    from safe_control_b200.params import resolve_params
+    p, _ = resolve_params({"model": "DynamicUnicycle2D"}, "mpc_cbf")
+    assert lib.scb_mpccbf_workspace_bytes(4096) == 4 * (1024 + 2 * 4096)
+    assert lib.scb_mpccbf_launch_count(p, 4096, 16, 8, 0) == 1
+    assert lib.scb_mpccbf_launch_count(p, 4096, 16, 8, 1) == 3
+    assert lib.scb_mpccbf_launch_count(p, 64, 16, 8, 1) == 1            # fits the first wave: nothing to schedule
+    p2, _ = resolve_params({"model": "DynamicUnicycle2D", "mpc_superellipsoid": True}, "mpc_cbf")
+    assert lib.scb_mpccbf_launch_count(p2, 4096, 16, 8, 1) == 4
+    assert lib.scb_mpccbf_launch_count(p, 4096, 16, 40, 1) < 0          # horizon beyond the compiled limit
+
+
 def test_no_cpu_fallback():
     """Solves must refuse to run without a CUDA device instead of silently using the oracle."""
     import torch
