@@ -278,7 +278,10 @@ class BatchedTrackingController:
     def control_step(self):
         """One control_step() for every agent still running -> ret [N] int32 (device tensor)."""
         self._check(self._lib.scb_control_step(self.params, self._t, self._stream()), "scb_control_step")
-        self.launches += 3 + int(self.host.dynamic_obs and self.host.scene.shape[0] > 0)
+        solve = 1
+        if self.pos_controller_type == "mpc_cbf":              # key + counting sort + solve when the schedule applies
+            solve = max(1, int(self._lib.scb_mpccbf_launch_count(self.params, self.N, self.host.M, self.host.H, 1)))
+        self.launches += 2 + solve + int(self.host.dynamic_obs and self.host.scene.shape[0] > 0)
         return self._bufs["ret"]
 
     def run_steps(self, n_steps):
