@@ -105,3 +105,25 @@ def test_no_cpu_fallback():
     with pytest.raises(ScbError):
         ctrl.solve(torch.zeros(1, 4, dtype=torch.float64), torch.zeros(1, 2, dtype=torch.float64),
                    torch.zeros(1, 2, 7, dtype=torch.float64))
+
+
+def test_tracker_initial_state_padding_matches_reference_rules():
+    """pad_initial_state restates tracking.py:60-99 + robots/robot.py:65-131 for every model the loop drives."""
+    import numpy as np
+    from safe_control_b200.tracking import pad_initial_state
+    X, yaw = pad_initial_state("SingleIntegrator2D", [[1.0, 2.0]])
+    assert X.tolist() == [[1.0, 2.0]] and yaw.tolist() == [0.0]
+    X, yaw = pad_initial_state("DoubleIntegrator2D", [[1.0, 2.0, 0.5]])                 # [x, y, theta] -> [x, y, 0, 0], yaw
+    assert X.tolist() == [[1.0, 2.0, 0.0, 0.0]] and yaw.tolist() == [0.5]
+    X, yaw = pad_initial_state("DoubleIntegrator2D", [[1.0, 2.0, 0.3, -0.2, 0.5]])
+    assert X.tolist() == [[1.0, 2.0, 0.3, -0.2]] and yaw.tolist() == [0.5]
+    X, yaw = pad_initial_state("DynamicUnicycle2D", [[1.0, 2.0, 0.5]])                  # velocity 0 appended
+    assert X.tolist() == [[1.0, 2.0, 0.5, 0.0]] and yaw.tolist() == [0.5]
+    X, yaw = pad_initial_state("Unicycle2D", [[1.0, 2.0, 0.5]])
+    assert X.tolist() == [[1.0, 2.0, 0.5]] and yaw.tolist() == [0.5]
+    X, yaw = pad_initial_state("Quad2D", [[1.0, 2.0, 0.5]])                             # only (x, z) kept (tracking.py:81-83)
+    assert X.tolist() == [[1.0, 2.0, 0.0, 0.0, 0.0, 0.0]] and yaw.tolist() == [0.0]
+    X, yaw = pad_initial_state("Quad3D", [[1.0, 2.0, 3.0, 0.5]])
+    assert X.shape == (1, 12) and X[0, :3].tolist() == [1.0, 2.0, 3.0] and X[0, 5] == 0.5 and yaw.tolist() == [0.5]
+    with pytest.raises(ValueError):
+        pad_initial_state("Unicycle2D", [[1.0, 2.0]])
