@@ -62,11 +62,11 @@ enum scb_model {
   SCB_SINGLE_INTEGRATOR_2D = 0,     /* robots/single_integrator2D.py */
   SCB_DYNAMIC_UNICYCLE_2D = 1,      /* robots/dynamic_unicycle2D.py */
   SCB_KINEMATIC_BICYCLE_2D = 2,     /* robots/kinematic_bicycle2D.py */
-  SCB_KINEMATIC_BICYCLE_2D_C3BF = 3,/* dynamic_env/kinematic_bicycle2D_c3bf.py */
+  SCB_KINEMATIC_BICYCLE_2D_C3BF = 3,/* dynamic_env/kinematic_bicycle2D_c3bf.py (all three controllers) */
   SCB_QUAD_3D = 4,                  /* robots/quad3D.py (MPC only: agent_barrier raises, quad3D.py:269-273) */
-  SCB_DOUBLE_INTEGRATOR_2D = 5,     /* robots/double_integrator2D.py        (QP paths) */
-  SCB_QUAD_2D = 6,                  /* robots/quad2D.py                      (QP paths) */
-  SCB_KINEMATIC_BICYCLE_2D_DPCBF = 7,/* dynamic_env/kinematic_bicycle2D_dpcbf.py (cbf_qp + closed loop) */
+  SCB_DOUBLE_INTEGRATOR_2D = 5,     /* robots/double_integrator2D.py        (cbf_qp, mpc_cbf) */
+  SCB_QUAD_2D = 6,                  /* robots/quad2D.py                      (all three controllers) */
+  SCB_KINEMATIC_BICYCLE_2D_DPCBF = 7,/* dynamic_env/kinematic_bicycle2D_dpcbf.py (cbf_qp, mpc_cbf) */
   SCB_UNICYCLE_2D = 8,              /* robots/unicycle2D.py (cbf_qp, mpc_cbf) */
   SCB_MANIPULATOR_2D = 9,           /* robots/manipulator2D.py (cbf_qp: 3 inputs, 25 link-circle rows per obstacle;
                                        M = CBFQP's num_obs = the ROW budget, cbf_qp.py:131-149) */
