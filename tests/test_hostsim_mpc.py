@@ -86,13 +86,24 @@ def test_mpc_no_obstacles_is_box_clipped_tracking():
         np.testing.assert_allclose(out["pred_x"][0, k + 1], x, atol=1e-12)
 
 
-def test_kernel_statement_matches_reference():
-    """The MPC kernel's own problem statement (Euler map, stage cost, CBF constraint of every obstacle slot incl.
+@pytest.mark.parametrize("fma", [False, True], ids=["nofma", "fma"])
+def test_kernel_statement_matches_reference(fma):
+    """(Both CPU builds of the kernel source: without FMA contraction and with it, as nvcc contracts.)
+    The MPC kernel's own problem statement (Euler map, stage cost, CBF constraint of every obstacle slot incl.
     the model's own step, dummy-obstacle padding) vs what the REFERENCE'S mpc_cbf.py hands to do-mpc at seeded probe
     points (tests/golden/ref_mpc_statement.npz, generated through oracle/refshim's probing do_mpc stand-in)."""
     import ctypes as C
     from hostsim_util import ptr
     from test_oracle_pinned import _load, _spec_from_tag
+    import hostsim_util
+    hostsim_util.use_fma(fma)
+    try:
+        _statement_check(_load, _spec_from_tag, C, ptr)
+    finally:
+        hostsim_util.use_fma(False)
+
+
+def _statement_check(_load, _spec_from_tag, C, ptr):
     lib = hostsim()
     seen = n_se = 0
     for tag, d in _load("ref_mpc_statement.npz").items():
