@@ -1,10 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- control-steps/s of the batched safety-filter solve (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5|loop2|loop4]
 
-One "step" = one pass of the hot path over one batch of synthetic agents (default workload
-cfg2 = BASELINE.json configs[1]: 1024 DynamicUnicycle2D agents x 16 circular obstacles, cbf_qp).
+One "step" = one pass of the hot path over one batch of synthetic agents.  Default workload:
+  N = 1   cfg2 = BASELINE.json configs[1] (1024 DynamicUnicycle2D agents x 16 circular obstacles, cbf_qp); the line also
+          embeds `sub_records` for cfg3, cfg4 and cfg5 (each: value, kernel_ms, roofline, e2e) measured in the same run.
+  N > 1   cfg5 = BASELINE.json configs[4]: 65536 mixed du/kb/quad3d agents, mpc_cbf H=10, M=64 -- STRONG scaling: rank 0
+          holds the batch, NCCL scatters it per model group, every rank solves its blocks, NCCL gathers U/status/iters/active
+          (safe_control_b200.mixed.ShardedMixedMPCCBF), all inside the timed region.
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
 
   value     whole-job control-steps/s, inputs resident in HBM, CUDA events on the launch stream,
@@ -38,9 +42,9 @@ WORKLOADS = {
                  desc="4096 DynamicUnicycle2D agents, mpc_cbf horizon 8, 16 obstacles"),
     "cfg4": dict(model="KinematicBicycle2D_C3BF", controller="optimal_decay_cbf_qp", N=8192, M=32, H=0, dynamic=True,
                  desc="8192 KinematicBicycle2D_C3BF agents, optimal_decay_cbf_qp, 32 dynamic obstacles"),
-    # config 5 is 65536 mixed-model agents on 8 GPUs; per GPU that is 8192 agents (1/3 DU, 1/3 KB, 1/3 Quad3D)
-    "cfg5": dict(model="mixed", controller="mpc_cbf", N=8192, M=64, H=10, dynamic=False,
-                 desc="8192 agents per GPU = 1/8 of config 5 (65536 mixed du/kb/quad3d agents, mpc_cbf N=10, 64 obstacles, 8 GPUs)"),
+    # config 5: 65536 mixed-model agents (1/3 DU, 1/3 KB, 1/3 Quad3D), the WHOLE batch sharded over the ranks (strong scaling)
+    "cfg5": dict(model="mixed", controller="mpc_cbf", N=65536, M=64, H=10, dynamic=False,
+                 desc="65536 mixed-model agents (du/kb/quad3d), mpc_cbf N=10, 64 obstacles, sharded across the ranks"),
 }
 WORKLOADS["loop2"] = dict(model="DynamicUnicycle2D", controller="cbf_qp", N=1024, M=16, H=0, dynamic=False, loop=True,
                           desc="closed loop of config 2 (SURVEY 8f-1): 1024 DynamicUnicycle2D agents x 16 obstacles, full "
@@ -61,13 +65,70 @@ def algorithmic_bytes(w):
     return 8 * (nx + nu + 7 * M + nu) + 4 + 8 * ((M + 2 * nu + 63) // 64)
 
 
+def _profile_json(names):
+    for n in names:
+        try:
+            with open(os.path.join(ROOT, "profiles", n)) as f:
+                return json.load(f)
+        except Exception:
+            continue
+    return {}
+
+
 def ncu_traffic(workload):
-    """dram__bytes_read+write per launch from the committed ncu capture of this kernel (profiles/r1_traffic.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get(workload)
-    except Exception:
-        return None
+    """dram__bytes_read+write per launch from the committed ncu capture of this kernel (profiles/r2_traffic.json)."""
+    return _profile_json(["r2_traffic.json", "r1_traffic.json"]).get(workload)
+
+
+def counted_flops(key):
+    """FP64 flops per agent-solve (2 x DFMA + DADD + DMUL thread instructions / agents) counted by ncu on this workload's
+    kernel: profiles/r2_flops.json, written by tools/count_flops.py from the capture named there."""
+    return _profile_json(["r2_flops.json"]).get(key)
+
+
+_FP64_PEAK = {}
+
+
+def fp64_peak():
+    """measured DFMA throughput of this device, TFLOP/s (scb_measure_fp64_peak: 16 independent chains per thread)"""
+    import ctypes as C
+    import torch
+    from safe_control_b200._lib import lib, check
+    dev = torch.cuda.current_device()
+    if dev not in _FP64_PEAK:
+        v = C.c_double()
+        check(lib().scb_measure_fp64_peak(C.byref(v), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "scb_measure_fp64_peak")
+        _FP64_PEAK[dev] = float(v.value)
+    return _FP64_PEAK[dev], "measured (scb_measure_fp64_peak: DFMA microbenchmark in libscb.so, this run)"
+
+
+def fp64_roofline(flops_per_step, k_ms, extra=None):
+    """roofline object of an MPC workload: bound by FP64 issue / latency, not by HBM"""
+    peak, src = fp64_peak()
+    ach = (flops_per_step / (k_ms * 1e-3) / 1e12) if flops_per_step else None
+    r = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+         "traffic": None, "peak_source": src, "kernel_ms": k_ms,
+         "flops_source": "ncu-counted 2*DFMA + DADD + DMUL thread instructions per agent (profiles/r2_flops.json) x agents per step"
+                         if flops_per_step else "profiles/r2_flops.json missing: flops not counted",
+         "note": "iterative interior-point NLP solve per agent: FP64 latency / issue bound, HBM traffic negligible (DESIGN.md 3.3)"}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def timed_replays(graph, steps, torch, min_ms=50.0):
+    """Replay a captured K-step graph until at least `min_ms` of device time is inside ONE event pair
+    -> (ms per step, replays, total ms).  A 20-step x 5 us region is too thin a basis for a headline."""
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); graph.replay(); b.record(); torch.cuda.synchronize()
+    est = max(a.elapsed_time(b), 1e-3)
+    reps = max(1, int(np.ceil(min_ms / est)))
+    a.record()
+    for _ in range(reps):
+        graph.replay()
+    b.record(); torch.cuda.synchronize()
+    tot = a.elapsed_time(b)
+    return tot / (reps * steps), reps, tot
 
 
 def hbm_peak():
@@ -182,101 +243,6 @@ def cpu_rate(w, sc, n_agents, procs, offset=0):
 
 def cpu_sample_size(w):
     return {"cbf_qp": 4096, "optimal_decay_cbf_qp": 8192, "mpc_cbf": 48}[w["controller"]]
-
-
-def run_mixed(args, w, rank, world, local_rank):
-    """Config 5 share per GPU: three model groups (DU / KB / Quad3D), each one launch, on concurrent streams."""
-    import torch
-    import torch.distributed as dist
-    from safe_control_b200 import scenes, HostContext
-    from safe_control_b200.mixed import MixedMPCCBF, split_counts
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-    N, M, H = w["N"], w["M"], w["H"]
-    counts = split_counts(N, len(MIXED))
-    P = 2
-    scs = [[scenes.make_scene(m, c, M, seed=1234 + 17 * rank + 101 * q) for m, c in zip(MIXED, counts)] for q in range(P)]
-    t = lambda a: torch.from_numpy(a).to(dev)
-    ins = [[{k: t(sc[k]) for k in ("X", "goal", "u_prev", "OBS", "nobs")} for sc in row] for row in scs]
-    ctrl = MixedMPCCBF([sc["spec"] for sc in scs[0]], num_obs=M, horizon=H)
-    step = lambda k: ctrl.solve(ins[k % P])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for k in range(args.warmup):
-        step(k)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = ctrl.launches
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        outs = step(args.warmup + k)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctrl.launches - l0
-    clocks = sampler.stop() if rank == 0 else None
-    stat = {m: {"optimal_frac": float((o["status"] == 0).float().mean()), "iters_mean": float(o["iters"].float().mean()),
-                "iters_max": int(o["iters"].max())} for m, o in zip(MIXED, outs)}
-    # end to end: three host-pointer calls per step (one per model group), pinned inputs
-    ctx = HostContext(local_rank)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    hin = [{k: pin(sc[k]) for k in ("X", "goal", "u_prev", "OBS", "nobs")} for sc in scs[0]]
-    def estep():
-        for g, a in zip(ctrl.groups, hin):
-            ctx.mpccbf_solve(g.params, M, H, a["X"], a["goal"], a["u_prev"], a["OBS"], a["nobs"])
-    e_steps = max(2, min(args.steps, 5))
-    estep(); barrier()
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        estep()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps * args.steps
-    h2d = sum(a[k].nbytes for a in hin for k in a)
-    d2h = sum(c * (g.nu * 8 + 4) for c, g in zip(counts, ctrl.groups))
-    tm = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        peak, peak_src = hbm_peak()
-        B = {"DynamicUnicycle2D": 3680, "KinematicBicycle2D": 3680, "Quad3D": 3784}
-        bytes_step = sum(B[m] * c for m, c in zip(MIXED, counts))
-        k_ms = float(tm[0]) / args.steps
-        out = {
-            "metric": "control-steps/sec (batched QP solves/s)", "value": world * N * args.steps / (float(tm[0]) * 1e-3),
-            "unit": "control-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": k_ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step_per_gpu": N, "groups": dict(zip(MIXED, counts)),
-                       "obstacles": M, "horizon": H, "scene": "SURVEY 8d generator per model group", "launch": "3 launches per step on 3 streams (eager)",
-                       "l2_policy": "compute-bound NLP solves; 2 distinct batches alternated", "solver": stat,
-                       "parallelism": f"agents sharded per model group, {world} rank(s), no data-path collective"},
-            "e2e": {"value": world * N * args.steps / (float(tm[1]) * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps_timed": e_steps, "how": "three scb_mpccbf_solve_host calls per step"},
-            "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": bytes_step / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": bytes_step / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
-                         "note": "FP64-compute/latency bound iterative NLP solves; HBM traffic negligible (DESIGN.md 3.3)"},
-        }
-        if not args.no_cpu:
-            rates = []
-            for m, sc in zip(MIXED, scs[0]):
-                wm = dict(w, model=m)
-                r, n, dt = cpu_rate(wm, sc, 6, 1)
-                rates.append((m, r, n, dt))
-            harm = len(rates) / sum(1.0 / r for _, r, _, _ in rates)
-            out["cpu_baseline"] = {"value": harm, "unit": "control-steps/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
-                                   "sample": "; ".join(f"{m}: {n} agents in {dt:.1f} s" for m, _, n, dt in rates) + " (oracle port; harmonic mean over the 1/3-1/3-1/3 mix)"}
-        print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def _oracle_loop_range(args):
@@ -469,80 +435,47 @@ def run_loop(args, w, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-# --------------------------------------------------------------------------------------- main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    args = ap.parse_args()
-    w = dict(WORKLOADS[args.workload], name=args.workload)
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    from safe_control_b200 import scenes
+# --------------------------------------------------------------------------------------- device arms
+class Ctx:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0")); self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    if args.impl == "reference":
-        # The reference's own CPU implementation of this path (cvxpy->GUROBI, do-mpc->IPOPT) cannot be installed
-        # (no network, no wheels); this arm times the reference-equivalent CPU path: the oracle port, one agent at
-        # a time per process like tracking.py:control_step, on every host core.  One "step" = a bounded sample of
-        # the workload (per_step agents); value = agent-steps/s over the K timed steps.
-        if rank != 0:
-            return
-        procs = os.cpu_count() or 1
-        if w.get("loop"):
-            return reference_loop(args, w, procs)
-        per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 1}[w["controller"]] * procs
-        budget_s = 150.0
-        n_scene = min(max(per_step * 8, 2048), 16384)
-        ref_model = "DynamicUnicycle2D" if w["model"] == "mixed" else w["model"]     # mixed: the DU third as representative
-        sc = scenes.make_scene(ref_model, n_scene, w["M"], seed=1234, dynamic=w["dynamic"],
-                               optimal_decay=w["controller"] == "optimal_decay_cbf_qp")
-        for k in range(max(1, min(args.warmup, 3))):
-            cpu_rate(w, sc, per_step, procs, offset=k * per_step)
-        t_tot, n_tot, done = 0.0, 0, 0
-        for k in range(args.steps):
-            r, n, dt = cpu_rate(w, sc, per_step, procs, offset=(k + 3) * per_step)
-            t_tot += dt; n_tot += n; done += 1
-            if t_tot > budget_s:
-                break
-        val = n_tot / t_tot
-        sample = (f"{done} steps x {per_step} agents of the {w['name']} scene (seed 1234), oracle port (numpy/scipy), "
-                  f"{procs} processes" + ("" if done == args.steps else f"; stopped at the {budget_s:.0f} s budget"))
-        print(json.dumps({
-            "impl": "reference", "metric": "control-steps/sec (batched QP solves/s)", "value": val, "unit": "control-steps/s",
-            "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(done, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step": per_step, "obstacles": w["M"],
-                       "horizon": w["H"]},
-            "cpu_baseline": {"value": val, "unit": "control-steps/s", "cores": procs, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "reference's cvxpy/GUROBI + do-mpc/IPOPT stack is not installable here (no network, no wheels); this is "
-                    "the oracle restatement driven one agent at a time like tracking.py:control_step",
-        }))
-        _close_pools()
-        return
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    if w["model"] == "mixed":
-        return run_mixed(args, w, rank, world, local_rank)
-    if w.get("loop"):
-        return run_loop(args, w, rank, world, local_rank)
-    import torch
-    import torch.distributed as dist
-    from safe_control_b200 import BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, HostContext
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    def max_over_ranks(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def run_single(args, w, cx, steps, warmup, sub=False):
+    """One (model, controller) workload, agents resident per rank (weak scaling when world > 1).  -> record (rank 0)."""
+    torch = cx.torch
+    from safe_control_b200 import BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, HostContext, scenes
+    rank, world, dev = cx.rank, cx.world, cx.dev
     N, M = w["N"], w["M"]
     B = algorithmic_bytes(w)
     od = w["controller"] == "optimal_decay_cbf_qp"
+    mpc = w["controller"] == "mpc_cbf"
 
-    # ---- input pool: P distinct batches, > 2x L2 in total (or 8 for the compute-bound MPC) ----
-    P = int(np.ceil(2.2 * L2_BYTES / (B * N))) if w["controller"] != "mpc_cbf" else 4
+    # ---- input pool: P distinct batches, > 2x L2 in total (4 for the compute-bound MPC) ----
+    P = int(np.ceil(2.2 * L2_BYTES / (B * N))) if not mpc else 4
     sc = scenes.make_scene(w["model"], N * P, M, seed=1234 + rank, dynamic=w["dynamic"], optimal_decay=od)
     spec = sc["spec"]
     t = lambda a: torch.from_numpy(a).to(dev)
@@ -559,72 +492,65 @@ def main():
         step = lambda k: ctrl.solve(Xp[k % P], Urp[k % P], OBSp[k % P], nobsp[k % P])
     else:
         ctrl = BatchedMPCCBF(spec, num_obs=M, horizon=w["H"])
-        step = lambda k: ctrl.solve(Xp[k % P], goalp[k % P], uprevp[k % P], OBSp[k % P], nobsp[k % P])
+        step = lambda k: ctrl.solve(Xp[k % P], goalp[k % P], uprevp[k % P], OBSp[k % P], nobsp[k % P], want_active=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput ("value") ----
-    # The K steps are captured once into a CUDA graph (launch-bound inner loop -> graph, as the
-    # hardware notes recommend) and the replay is timed with CUDA events on the launching stream.
-    # The eager number (one Python -> ctypes -> launch per step) is reported beside it.
-    for k in range(args.warmup):
+    # ---- device-resident throughput ("value"): K steps captured once into a CUDA graph, the replay timed with CUDA
+    # events on the launching stream and repeated until >= 50 ms are inside the event pair ----
+    for k in range(warmup):
         step(k)
-    barrier()
+    cx.barrier()
     graph = torch.cuda.CUDAGraph()
     l0 = ctrl.launches
     with torch.cuda.graph(graph):
-        for k in range(args.steps):
-            step(args.warmup + k)
+        for k in range(steps):
+            last = step(warmup + k)
     launches = ctrl.launches - l0
     graph.replay()                       # warm replay (instantiation, first-touch)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank)
+    if rank == 0 and not sub:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    graph.replay()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # roofline numerator: the same launches, same stream, CUDA events; median of 5 more replays
-    reps = []
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); graph.replay(); b.record(); torch.cuda.synchronize()
-        reps.append(a.elapsed_time(b) / args.steps)
-    k_ms = float(np.median(reps))
-    clocks = sampler.stop() if rank == 0 else None
-    # eager (no graph): Python + ctypes + launch per step
-    barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for k in range(args.steps):
-        step(args.warmup + k)
-    g1.record(); torch.cuda.synchronize()
-    eager_ms = g0.elapsed_time(g1)
+    cx.barrier()
+    ms_step, reps, tot_ms = timed_replays(graph, steps, torch, 50.0 if not mpc else 0.0)
+    cx.barrier()
+    k_list = [timed_replays(graph, steps, torch, 20.0 if not mpc else 0.0)[0] for _ in range(3 if mpc else 5)]
+    k_ms = float(np.median(k_list))
+    clocks = sampler.stop() if (rank == 0 and not sub) else None
+    solver = None
+    if mpc:
+        solver = {"optimal_frac": float((last["status"] == 0).float().mean()), "iters_mean": float(last["iters"].float().mean()),
+                  "iters_max": int(last["iters"].max()),
+                  "active_rows_mean": float(sum(((last["active"] >> b) & 1).sum() for b in range(64)).item()) / N}
+    eager = None
+    if not sub:                          # eager (no graph): Python + ctypes + launch per step
+        cx.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(steps):
+            step(warmup + k)
+        g1.record(); torch.cuda.synchronize()
+        eager = g0.elapsed_time(g1)
 
     # asymptote of the same kernel on a batch that fills the machine (not the headline; explains it)
     big = None
-    if w["controller"] != "mpc_cbf":
+    if not mpc:
         NB = 1 << 20
-        reps = NB // (N * P) + 1
-        Xb = Xp.reshape(N * P, -1).repeat(reps, 1)[:NB].contiguous(); Ub = Urp.reshape(N * P, -1).repeat(reps, 1)[:NB].contiguous()
-        Ob = OBSp.reshape(N * P, M, 7).repeat(reps, 1, 1)[:NB].contiguous(); nb = nobsp.reshape(-1).repeat(reps)[:NB].contiguous()
+        rp = NB // (N * P) + 1
+        Xb = Xp.reshape(N * P, -1).repeat(rp, 1)[:NB].contiguous(); Ub = Urp.reshape(N * P, -1).repeat(rp, 1)[:NB].contiguous()
+        Ob = OBSp.reshape(N * P, M, 7).repeat(rp, 1, 1)[:NB].contiguous(); nb = nobsp.reshape(-1).repeat(rp)[:NB].contiguous()
         for _ in range(3):
             ctrl.solve(Xb, Ub, Ob, nb)
         torch.cuda.synchronize()
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record()
-        for _ in range(10):
+        for _ in range(20):
             ctrl.solve(Xb, Ub, Ob, nb)
         b1.record(); torch.cuda.synchronize()
-        big_ms = b0.elapsed_time(b1) / 10
-        big = dict(agents=NB, ms_per_launch=big_ms, control_steps_per_s=NB / big_ms * 1e3, gbs=B * NB / big_ms / 1e6)
+        big_ms = b0.elapsed_time(b1) / 20
+        peak_, _ = hbm_peak()
+        big = dict(agents=NB, ms_per_launch=big_ms, control_steps_per_s=NB / big_ms * 1e3, gbs=B * NB / big_ms / 1e6,
+                   frac=B * NB / big_ms / 1e6 / peak_, traffic=ncu_traffic(w["name"] + "_large_batch"),
+                   how="20 launches back to back over a 1 Mi-agent batch (1 GB of inputs > L2), CUDA events")
         del Xb, Ub, Ob, nb
 
     # ---- activity mix of the timed inputs (iteration counts depend on it) ----
@@ -640,7 +566,7 @@ def main():
                    box_active=float(box_act.float().mean()))
 
     # ---- end to end through the host-pointer C ABI ----
-    ctx = HostContext(local_rank)
+    ctx = HostContext(cx.local_rank)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     P_h = min(P, 32)
     hX = [pin(sc["X"][k * N:(k + 1) * N]) for k in range(P_h)]
@@ -659,14 +585,16 @@ def main():
         estep = lambda k: ctx.odcbf_solve(ctrl.params, M, hX[k % P_h], hU[k % P_h], hO[k % P_h], hn[k % P_h], out=ho)
         h2d = N * (4 + 2) * 8 + N * M * 56 + N * 4; d2h = N * 2 * 8 * 2 + N * 4 * 2 + N * 8
     else:
-        estep = lambda k: ctx.mpccbf_solve(ctrl.params, M, w["H"], hX[k % P_h], hg[k % P_h], hp[k % P_h], hO[k % P_h], hn[k % P_h])
-        h2d = N * (ctrl.nx + ctrl.ngoal + ctrl.nu) * 8 + N * M * 56 + N * 4; d2h = N * ctrl.nu * 8 + N * 4 * 2 + N * 8
-    e_steps = max(10, min(args.steps, 400 if w["controller"] != "mpc_cbf" else 20))
+        estep = lambda k: ctx.mpccbf_solve(ctrl.params, M, w["H"], hX[k % P_h], hg[k % P_h], hp[k % P_h], hO[k % P_h], hn[k % P_h],
+                                           want_active=True)
+        h2d = N * (ctrl.nx + ctrl.ngoal + ctrl.nu) * 8 + N * M * 56 + N * 4
+        d2h = N * ctrl.nu * 8 + N * 4 * 2 + N * 8 + N * ctrl.active_words * 8
+    e_steps = max(10, min(steps, 400 if not mpc else 20))
 
     def time_e2e():
-        for k in range(min(args.warmup, 10)):
+        for k in range(min(warmup, 10)):
             estep(k)
-        barrier()
+        cx.barrier()
         t0 = time.perf_counter()
         for k in range(e_steps):
             estep(k)
@@ -675,54 +603,310 @@ def main():
 
     e2e_s = time_e2e()                       # the library's own choice (zero-copy for page-locked buffers <= 32 MB)
     e2e_launches = ctx.launches
-    os.environ["SCB_HOST_PATH"] = "staged"   # same call, forced through explicit H2D / D2H staging copies
-    e2e_staged_s = time_e2e()
-    del os.environ["SCB_HOST_PATH"]
+    staged = None
+    if not sub and not mpc:
+        os.environ["SCB_HOST_PATH"] = "staged"   # same call, forced through explicit H2D / D2H staging copies
+        staged = time_e2e()
+        del os.environ["SCB_HOST_PATH"]
+    ctx.close()
 
-    tm = torch.tensor([ms, e2e_s * 1e3 / e_steps * args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(tm[0]), float(tm[1])
-
-    if rank == 0:
+    ms_max, e2e_ms_max = cx.max_over_ranks([ms_step, e2e_s * 1e3 / e_steps])
+    if rank != 0:
+        return None
+    if mpc:
+        fl = counted_flops(w["name"])
+        roof = fp64_roofline(fl * N if fl else None, k_ms, {"agents_per_launch": N, "flops_per_agent": fl,
+                                                            "hbm_algorithmic_bytes_per_agent": B})
+    else:
         peak, peak_src = hbm_peak()
         achieved = B * N / (k_ms * 1e-3) / 1e9
-        out = {
-            "metric": "control-steps/sec (batched QP solves/s)",
-            "value": world * N * args.steps / (ms_max * 1e-3), "unit": "control-steps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step_per_gpu": N, "obstacles": M,
-                       "horizon": w["H"], "scene": "SURVEY 8d generator, seed 1234+rank, num_constraints=M", "launch": "K steps captured in one CUDA graph",
-                       "l2_policy": f"inputs larger than L2: {P} distinct batches ({P * N * B / 1e6:.0f} MB) cycled",
-                       "parallelism": f"agents sharded, {world} rank(s), no data-path collective", "activity_mix": mix},
-            "e2e": {"value": world * N * args.steps / (e2e_ms_max * 1e-3), "unit": "control-steps/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": e_steps,
-                    "how": ("scb_*_solve_host per step on page-locked host arrays; the QP calls run zero-copy (kernel reads inputs / writes "
-                            "U,status,active over PCIe through the mapped host buffers, then sync); the MPC call stages H2D -> kernel -> D2H"),
-                    "staged": {"value": world * N * e_steps / e2e_staged_s, "how": "SCB_HOST_PATH=staged: pinned host arrays -> cudaMemcpyAsync H2D -> kernel -> D2H -> sync (this rank)"}},
-            "gpu_launches": launches,
-            "eager": {"value": world * N * args.steps / (eager_ms * 1e-3), "unit": "control-steps/s",
-                      "how": "same steps without the CUDA graph: one Python->ctypes->launch per step (host-launch bound)"},
-            "e2e_gpu_launches": e2e_launches,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(w["name"]), "peak_source": peak_src, "kernel_ms": k_ms, "kernel_ms_how": "CUDA-graph replay of the timed steps / steps (median of 5), includes the inter-kernel dependency gap",
-                         "algorithmic_bytes_per_agent": B, "agents_per_launch": N,
-                         "note": ("the MPC path is FP64-compute/latency bound (iterative NLP solve per agent), HBM traffic is negligible; see DESIGN.md 3.3"
-                                  if w["controller"] == "mpc_cbf" else
-                                  f"one launch covers only {N} agents ({B * N / 1e6:.1f} MB): latency-bound; large_batch shows the same kernel on 1M agents"),
-                         "large_batch": big},
-        }
-        if not args.no_cpu:
-            n_s = cpu_sample_size(w)
-            rate, n, dt = cpu_rate(w, sc, n_s, 1)
-            out["cpu_baseline"] = {"value": rate, "unit": "control-steps/s", "cores": 1, "kind": "port",
-                                   "host_cores_available": os.cpu_count(),
-                                   "sample": f"first {n} agents of the timed scene, oracle port (numpy, one agent at a time), {dt:.1f} s"}
-        print(json.dumps(out))
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(w["name"]), "peak_source": peak_src, "kernel_ms": k_ms,
+                "kernel_ms_how": "CUDA-graph replay of the timed steps / steps (median of 5 regions of >= 20 ms each), includes the inter-kernel dependency gap",
+                "algorithmic_bytes_per_agent": B, "agents_per_launch": N,
+                "latency_floor": _profile_json(["r2_latency_floor.json"]).get(w["name"]),
+                "note": f"one launch covers only {N} agents ({B * N / 1e6:.1f} MB): latency-bound; large_batch shows the same kernel on 1M agents",
+                "large_batch": big}
+    out = {
+        "metric": "control-steps/sec (batched QP solves/s)",
+        "value": world * N / (ms_max * 1e-3), "unit": "control-steps/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step_per_gpu": N, "obstacles": M,
+                   "horizon": w["H"], "scene": "SURVEY 8d generator, seed 1234+rank, num_constraints=M",
+                   "launch": f"K = {steps} steps captured in one CUDA graph, replayed {reps}x inside one CUDA-event pair ({tot_ms:.1f} ms timed)",
+                   "steps_timed": reps * steps,
+                   "l2_policy": f"inputs larger than L2: {P} distinct batches ({P * N * B / 1e6:.0f} MB) cycled" if not mpc
+                                else f"compute-bound NLP solves; {P} distinct batches cycled",
+                   "parallelism": f"agents sharded, {world} rank(s), no data-path collective", "activity_mix": mix, "solver": solver},
+        "e2e": {"value": world * N / (e2e_ms_max * 1e-3), "unit": "control-steps/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps_timed": e_steps,
+                "how": ("scb_*_solve_host per step on page-locked host arrays; the QP calls run zero-copy (kernel reads inputs / writes "
+                        "U,status,active over PCIe through the mapped host buffers, then sync); the MPC call stages H2D -> kernel -> D2H")},
+        "gpu_launches": launches * reps,
+        "e2e_gpu_launches": e2e_launches,
+        "roofline": roof,
+    }
+    if staged is not None:
+        out["e2e"]["staged"] = {"value": world * N * e_steps / staged, "how": "SCB_HOST_PATH=staged: pinned host arrays -> cudaMemcpyAsync H2D -> kernel -> D2H -> sync (this rank)"}
+    if eager is not None:
+        out["eager"] = {"value": world * N * steps / (eager * 1e-3), "unit": "control-steps/s",
+                        "how": "same steps without the CUDA graph: one Python->ctypes->launch per step (host-launch bound)"}
+    if clocks is not None:
+        out["clocks"] = clocks
+    if not args.no_cpu and not sub:
+        n_s = cpu_sample_size(w)
+        rate, n, dt = cpu_rate(w, sc, n_s, 1)
+        out["cpu_baseline"] = {"value": rate, "unit": "control-steps/s", "cores": 1, "kind": "port",
+                               "host_cores_available": os.cpu_count(),
+                               "sample": f"first {n} agents of the timed scene, oracle port (numpy, one agent at a time), {dt:.1f} s"}
+    return out
+
+
+def run_cfg5(args, w, cx, steps, warmup, sub=False):
+    """BASELINE config 5, strong scaling: rank 0 holds the whole 65536-agent mixed batch (three model groups);
+    per step  NCCL scatter -> one launch per group on concurrent streams -> NCCL gather of U / status / iters / active,
+    all inside the timed region (safe_control_b200.mixed.ShardedMixedMPCCBF).  world == 1: same code, no collective."""
+    torch = cx.torch
+    from safe_control_b200 import scenes
+    from safe_control_b200.mixed import ShardedMixedMPCCBF, MixedMPCCBF, split_counts
+    rank, world, dev = cx.rank, cx.world, cx.dev
+    N, M, H = w["N"], w["M"], w["H"]
+    counts = split_counts(N, len(MIXED))
+    specs = [scenes.default_spec(m) for m in MIXED]
+    keys = ("X", "goal", "u_prev", "OBS", "nobs")
+    P = 2
+    scs = ins = None
+    if rank == 0:
+        scs = [[scenes.make_scene(m, c, M, seed=1234 + 101 * q + 17 * g) for g, (m, c) in enumerate(zip(MIXED, counts))] for q in range(P)]
+        ins = [[{k: torch.from_numpy(sc[k]).to(dev) for k in keys} for sc in row] for row in scs]
+    sh = ShardedMixedMPCCBF(specs, counts, M, H, dev, want_active=True)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(k, marks=None):
+        blocks = sh.scatter(ins[k % P] if rank == 0 else None)
+        if marks is not None:
+            marks[0].record()
+        outs = sh.solve_local(blocks)
+        if marks is not None:
+            marks[1].record()
+        return sh.gather(outs), outs
+
+    for k in range(max(warmup, 1)):
+        step(k)
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank)
+    if rank == 0 and not sub:
+        sampler.start()
+    l0 = sh.launches
+    marks = [(ev(), ev(), ev(), ev()) for _ in range(steps)]
+    cx.barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(steps):
+        marks[k][0].record()
+        res, outs = step(k + warmup, marks[k][1:3])
+        marks[k][3].record()
+    e1.record()
+    cx.barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = sh.launches - l0
+    clocks = sampler.stop() if (rank == 0 and not sub) else None
+    ph = np.array([[m[0].elapsed_time(m[1]), m[1].elapsed_time(m[2]), m[2].elapsed_time(m[3])] for m in marks]).mean(axis=0)
+    stat = None
+    if rank == 0:
+        stat = {m: {"optimal_frac": float((o["status"] == 0).float().mean()), "iters_mean": float(o["iters"].float().mean()),
+                    "iters_max": int(o["iters"].max())} for m, o in zip(MIXED, res)}
+
+    # ---- end to end: pinned host inputs on rank 0 -> H2D -> scatter -> solve -> gather -> D2H of U / status / active ----
+    e_steps = max(1, min(steps, 3))
+    h2d = d2h = 0
+    if rank == 0:
+        hin = [{k: torch.from_numpy(sc[k]).pin_memory() for k in keys} for sc in scs[0]]
+        din = [{k: torch.empty_like(v, device=dev) for k, v in g.items()} for g in hin]
+        hout = [{k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in g.items()} for g in res]
+        h2d = sum(v.numel() * v.element_size() for g in hin for v in g.values())
+        d2h = sum(v.numel() * v.element_size() for g in hout for v in g.values())
+
+    def estep():
+        if rank == 0:
+            for g, d in zip(hin, din):
+                for k in keys:
+                    d[k].copy_(g[k], non_blocking=True)
+        r = sh.solve(din if rank == 0 else None)
+        if rank == 0:
+            for g, o in zip(hout, r):
+                for k in g:
+                    g[k].copy_(o[k], non_blocking=True)
+        torch.cuda.synchronize()
+
+    estep(); cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        estep()
+    cx.barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+
+    # ---- the same batch on ONE GPU (rank 0 alone; the others wait): the base of the strong-scaling curve ----
+    base = None
     if world > 1:
-        dist.destroy_process_group()
+        if rank == 0:
+            one = MixedMPCCBF(specs, M, H)
+            one.solve(ins[0]); torch.cuda.synchronize()
+            b0, b1 = ev(), ev()
+            b0.record(); one.solve(ins[1]); b1.record(); torch.cuda.synchronize()
+            base = {"n_gpus": 1, "ms_per_step": b0.elapsed_time(b1), "value": N / (b0.elapsed_time(b1) * 1e-3),
+                    "how": "rank 0 alone solves the whole batch (no scatter / gather), one step after one warm-up, CUDA events"}
+        cx.barrier()
+
+    ms_max, e2e_max, sc_ms, so_ms, ga_ms = cx.max_over_ranks([ms, e2e_ms, ph[0], ph[1], ph[2]])
+    if rank != 0:
+        return None
+    B = {"DynamicUnicycle2D": 3680, "KinematicBicycle2D": 3680, "Quad3D": 3784}
+    fl = counted_flops("cfg5") or {}
+    flops_step = sum(fl.get(m, 0) * c for m, c in zip(MIXED, counts)) if all(m in fl for m in MIXED) else None
+    plan_bytes = (sum(pl.scatter_bytes() for pl in sh.plans), sum(pl.gather_bytes() for pl in sh.plans))
+    out = {
+        "metric": "control-steps/sec (batched QP solves/s)", "value": N / (ms_max * 1e-3),
+        "unit": "control-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['desc']}", "agents_total": N, "agents_per_gpu": N / world,
+                   "groups": dict(zip(MIXED, counts)), "obstacles": M, "horizon": H,
+                   "scene": "SURVEY 8d generator per model group, seed 1234 (+101 per batch, +17 per group), num_constraints=M",
+                   "launch": "per step: scatter (5 tensors x 3 groups), 3 x (key, counting sort, solve) launches on 3 streams, gather (4 tensors x 3 groups); eager",
+                   "l2_policy": f"compute-bound NLP solves; {P} distinct batches alternated ({plan_bytes[0] / 1e6:.0f} MB of inputs each)",
+                   "parallelism": (f"strong scaling over {world} rank(s): NCCL scatter of each model group's rows from rank 0 -> per-rank solve -> "
+                                   f"NCCL gather of U/status/iters/active to rank 0, inside the timed region" if world > 1 else
+                                   "1 rank: whole batch on one GPU (scatter / gather degenerate to views)"),
+                   "phases_ms": {"scatter_ms": sc_ms, "solve_ms": so_ms, "gather_ms": ga_ms, "how": "CUDA events per step on each rank, mean over steps, max over ranks"},
+                   "scatter_bytes": plan_bytes[0], "gather_bytes": plan_bytes[1], "solver": stat},
+        "e2e": {"value": N / (e2e_max * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps_timed": e_steps,
+                "how": "ShardedMixedMPCCBF.solve per step: pinned host batch on rank 0 -> H2D -> scatter -> solve -> gather -> D2H of U/status/iters/active -> sync; wall clock between barriers, max over ranks"},
+        "gpu_launches": launches,
+        "roofline": fp64_roofline(flops_step / world if flops_step else None, so_ms,
+                                  {"kernel_ms_how": "solve phase (3 concurrent model-group launches) per step on the slowest rank, CUDA events",
+                                   "flops_per_agent": fl or None, "hbm_algorithmic_bytes_per_agent": B, "per_gpu": True}),
+    }
+    if base is not None:
+        out["strong_scaling_base"] = base
+    if clocks is not None:
+        out["clocks"] = clocks
+    if not args.no_cpu and not sub and world == 1:
+        rates = []
+        for m, sc in zip(MIXED, scs[0]):
+            r, n, dt = cpu_rate(dict(w, model=m), sc, 6, 1)
+            rates.append((m, r, n, dt))
+        harm = len(rates) / sum(1.0 / r for _, r, _, _ in rates)
+        out["cpu_baseline"] = {"value": harm, "unit": "control-steps/s", "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+                               "sample": "; ".join(f"{m}: {n} agents in {dt:.1f} s" for m, _, n, dt in rates) + " (oracle port; harmonic mean over the 1/3-1/3-1/3 mix)"}
+    return out
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def reference_arm(args, w):
+    """The reference's own CPU implementation of this path (cvxpy->GUROBI, do-mpc->IPOPT) cannot be installed (no
+    network, no wheels); this arm times the reference-equivalent CPU path: the oracle port, one agent at a time per
+    process like tracking.py:control_step, on every host core.  One "step" = a bounded sample of the workload
+    (per_step agents); value = agent-steps/s over the K timed steps."""
+    from safe_control_b200 import scenes
+    procs = os.cpu_count() or 1
+    if w.get("loop"):
+        return reference_loop(args, w, procs)
+    per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 1}[w["controller"]] * procs
+    budget_s = 150.0
+    mixed = w["model"] == "mixed"
+    models = list(MIXED) if mixed else [w["model"]]
+    n_scene = min(max(per_step * 8, 2048), 16384) if not mixed else max(per_step * 8, 256)
+    scs = [scenes.make_scene(m, n_scene, w["M"], seed=1234, dynamic=w["dynamic"],
+                             optimal_decay=w["controller"] == "optimal_decay_cbf_qp") for m in models]
+
+    def one(k):
+        """one step: per_step agents of EVERY model group (mixed: the 1/3-1/3-1/3 mix) -> (agents, seconds)"""
+        n_tot, t_tot = 0, 0.0
+        for m, sc in zip(models, scs):
+            r, n, dt = cpu_rate(dict(w, model=m), sc, per_step, procs, offset=k * per_step)
+            n_tot += n; t_tot += dt
+        return n_tot, t_tot
+
+    for k in range(max(1, min(args.warmup, 3)) if not mixed else 1):
+        one(k)
+    t_tot, n_tot, done = 0.0, 0, 0
+    for k in range(args.steps):
+        n, dt = one(k + 3)
+        t_tot += dt; n_tot += n; done += 1
+        if t_tot > budget_s:
+            break
+    val = n_tot / t_tot
+    sample = (f"{done} steps x {per_step} agents" + (" of each model group (du / kb / quad3d)" if mixed else "") +
+              f" of the {w['name']} scene (seed 1234), oracle port (numpy/scipy), "
+              f"{procs} processes" + ("" if done == args.steps else f"; stopped at the {budget_s:.0f} s budget"))
+    print(json.dumps({
+        "impl": "reference", "metric": "control-steps/sec (batched QP solves/s)", "value": val, "unit": "control-steps/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(done, 1),
+        "higher_is_better": True, "scaling": "strong" if mixed else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_step": per_step * len(models), "obstacles": w["M"],
+                   "horizon": w["H"]},
+        "cpu_baseline": {"value": val, "unit": "control-steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's cvxpy/GUROBI + do-mpc/IPOPT stack is not installable here (no network, no wheels); this is "
+                "the oracle restatement driven one agent at a time like tracking.py:control_step",
+    }))
+    _close_pools()
+
+
+# --------------------------------------------------------------------------------------- main
+SUB_STEPS = {"cfg3": (10, 3), "cfg4": (200, 10), "cfg5": (2, 1)}     # (steps, warmup) of the sub-records of the N = 1 line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sub", action="store_true", help="N = 1 default run: skip the cfg3 / cfg4 / cfg5 sub-records")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    default_run = args.workload is None
+    # default workload: cfg2 on one GPU (BASELINE configs[1]); with more ranks the config BASELINE names for them, cfg5
+    name = args.workload or ("cfg2" if max(world, args.gpus) <= 1 else "cfg5")
+    w = dict(WORKLOADS[name], name=name)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        return reference_arm(args, w)
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if w.get("loop"):
+        return run_loop(args, w, rank, world, local_rank)
+    cx = Ctx()
+    steps, warmup = args.steps, max(args.warmup, 3)
+    if name == "cfg5":
+        if default_run:
+            steps = min(steps, 5)                  # ~40 ms x N_gpu^-1 ... 300 ms per step: a handful is plenty
+        out = run_cfg5(args, w, cx, steps, min(warmup, 3))
+    else:
+        out = run_single(args, w, cx, steps, warmup)
+        if default_run and world == 1 and not args.no_sub:
+            subs = {}
+            for sname, (s_steps, s_warm) in SUB_STEPS.items():
+                sw = dict(WORKLOADS[sname], name=sname)
+                try:
+                    rec = run_cfg5(args, sw, cx, s_steps, s_warm, sub=True) if sname == "cfg5" else \
+                        run_single(args, sw, cx, s_steps, s_warm, sub=True)
+                    subs[sname] = {k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "e2e",
+                                                       "gpu_launches", "roofline") if k in rec}
+                except Exception as e:             # a sub-record must never take the headline down with it
+                    subs[sname] = {"error": f"{type(e).__name__}: {e}"}
+            out["sub_records"] = subs
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+    cx.close()
 
 
 if __name__ == "__main__":

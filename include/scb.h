@@ -41,9 +41,9 @@
  *                      bit M+2i: u_i at its upper bound; bit M+2i+1: u_i at its lower bound.
  *
  * All functions return 0 on success or a negative scb_error code; they never throw and
- * never touch errno.  Calls with distinct contexts/streams are re-entrant; the only
- * library-owned state is a per-device ring of work counters used by the MPC kernel's
- * dynamic agent scheduling (allocated on first use, slots handed out atomically).
+ * never touch errno.  Calls with distinct contexts/streams/workspaces are re-entrant; the
+ * library owns no device memory and no global mutable state (the MPC kernel's dynamic agent
+ * scheduling keeps its work counters in the caller's workspace, see scb_mpccbf_solve_ws).
  */
 #ifndef SCB_H_
 #define SCB_H_
@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define SCB_VERSION 100
+#define SCB_VERSION 200
 
 /* model ids (robot_spec['model'], robots/robot.py:65-175) */
 enum scb_model {
@@ -126,6 +126,10 @@ int         scb_active_words(int M, int nu);           /* ceil((M + 2 nu) / 64) 
 /* compiled limits: max obstacle slots for the QP kernels, max slots and horizon for MPC */
 int         scb_limits(int* max_obs_qp, int* max_obs_mpc, int* max_horizon);
 
+/* measurement helper (bench.py): achieved FP64 FMA throughput of the current device in TFLOP/s (2 flops per DFMA), a
+ * chain-parallel kernel timed with CUDA events on `stream`.  The measured denominator of the MPC kernels' roofline. */
+int         scb_measure_fp64_peak(double* tflops, void* stream);
+
 /* ---- context for the host-pointer calls ------------------------------------------------- */
 int  scb_ctx_create(scb_ctx** out, int device);
 void scb_ctx_destroy(scb_ctx* ctx);
@@ -163,19 +167,27 @@ int scb_odcbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M,
 /* ---- MPC-CBF  (position_control/mpc_cbf.py) ---------------------------------------------- */
 /* goal [N, 2] (3 for Quad3D: x, y, z), u_prev [N, nu] (last applied input, 0 at the first
  * call), track [N] int32 or NULL (0 => state_machine != 'track': return Uref untouched,
- * mpc_cbf.py:379-381).  pred_x [N, H+1, nx], pred_u [N, H, nu], iters [N] may be NULL.
- * kkt [N] (out, may be NULL): final KKT error. */
+ * mpc_cbf.py:379-381; < 0 => skip the agent, its outputs are left untouched).
+ * pred_x [N, H+1, nx], pred_u [N, H, nu], iters [N] may be NULL.
+ * kkt [N] (out, may be NULL): final KKT error.
+ * active [N, scb_mpc_active_words(p, M, H)] u64 (out, may be NULL): active set of the NLP at the returned point, one bit
+ * per inequality row: bit k*M + j = CBF row of (stage k, obstacle slot j)  (mpc_cbf.py:301-325);  bit H*M + q = simple
+ * bound q:  q < 2 H nu: stage k = q / (2 nu), input i = (q % (2 nu)) / 2, even = u_i at its upper bound, odd = lower
+ * (mpc_cbf.py:183-221);  then, for the models with a velocity state bound, 2 H bits: t = q - 2 H nu, node k = 1 + t / 2,
+ * even = v <= v_max active, odd = v >= -v_max active.  A row is active <=> its multiplier exceeds its value at exit. */
+int scb_mpc_active_words(const scb_params* p, int M, int H);
 int scb_mpccbf_solve(const scb_params* p, int N, int M, int H,
                      const double* X, const double* Uref, const double* goal, const double* u_prev,
                      const int32_t* track,
                      const double* OBS, long obs_stride_agent, const int32_t* nobs,
                      double* U, int32_t* status, double* pred_x, double* pred_u,
-                     int32_t* iters, double* kkt, void* stream);
+                     int32_t* iters, double* kkt, uint64_t* active, void* stream);
 /* Same call with a caller-owned device scratch of scb_mpccbf_workspace_bytes(N) bytes (contents undefined before
- * and after).  With it the kernel starts the agents in order of their cold-start CBF margin (most violated first)
- * instead of index order: per-agent results are identical, the batch finishes sooner because the long-tailed
+ * and after; one workspace per concurrent call).  With it the kernel starts the agents in order of their cold-start
+ * CBF margin (most violated first) instead of index order and hands agents to warps dynamically (the work counters
+ * live in the workspace): per-agent results are identical, the batch finishes sooner because the long-tailed
  * iteration counts no longer leave a late-started straggler running alone.  workspace == NULL or too small: index
- * order, exactly scb_mpccbf_solve. */
+ * order with a static stride, exactly scb_mpccbf_solve. */
 size_t scb_mpccbf_workspace_bytes(int N);
 /* kernel launches one scb_mpccbf_solve[_ws] call issues (1, or 3 with a schedule: key, counting sort, solve) */
 int scb_mpccbf_launch_count(const scb_params* p, int N, int M, int H, int with_workspace);
@@ -184,13 +196,14 @@ int scb_mpccbf_solve_ws(const scb_params* p, int N, int M, int H,
                         const int32_t* track,
                         const double* OBS, long obs_stride_agent, const int32_t* nobs,
                         double* U, int32_t* status, double* pred_x, double* pred_u,
-                        int32_t* iters, double* kkt, void* workspace, size_t workspace_bytes, void* stream);
+                        int32_t* iters, double* kkt, uint64_t* active,
+                        void* workspace, size_t workspace_bytes, void* stream);
 int scb_mpccbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M, int H,
                           const double* X, const double* Uref, const double* goal, const double* u_prev,
                           const int32_t* track,
                           const double* OBS, long obs_stride_agent, const int32_t* nobs,
                           double* U, int32_t* status, double* pred_x, double* pred_u,
-                          int32_t* iters, double* kkt);
+                          int32_t* iters, double* kkt, uint64_t* active);
 
 /* ---- closed loop: the rest of LocalTrackingController.control_step()  (tracking.py:559-668) ---- */
 /* Everything either side of the solve, for N agents on the device, so that run_all_steps
@@ -227,9 +240,11 @@ typedef struct scb_track {
   int32_t enable_rotation;       /* tracking.py:41 */
   int32_t dynamic_obs;           /* 1: SCENE[:, 0:2] += SCENE[:, 3:5] dt after the selection (dynamic_env/main.py:152) */
   int32_t att_velocity_tracking; /* SingleIntegrator2D: 1 = VelocityTrackingYaw drives yaw in 'track' (tracking.py:156-181) */
-  int32_t mpc_superellipsoid; /* mpc_cbf, SingleIntegrator2D / DynamicUnicycle2D / DoubleIntegrator2D: 1 = OBS may hold
-                                 superellipsoid rows (flag 1; *_2D.py agent_barrier_dt if_else): the agents that have one
-                                 are solved by a second launch with general rows.  0: such agents get SCB_NUMERICAL */
+  int32_t mpc_strict;            /* mpc_cbf only.  0 (default) = the reference's semantics: MPCCBF.status is hard-wired
+                                    'optimal' (mpc_cbf.py:10, 400), so the returned input is always stepped.  1 = an MPC solve
+                                    that did not end SCB_OPTIMAL makes control_step return -2 without stepping, exactly like
+                                    a failed QP (tracking.py:627-634).  Either way `mpc_fail` counts such solves.
+                                    (Superellipsoid rows in MPC are enabled by scb_params.mpc_superellipsoid.) */
   double reached_threshold;      /* 0.3  tracking.py:52 */
   double rotation_threshold;     /* 0.1  tracking.py:50 */
   double k_omega, k_a, k_v;      /* nominal_input gains (robots/robot.py:401; optimal decay: 3.0, 0.5, 0.5 tracking.py:601-602) */
@@ -264,6 +279,8 @@ typedef struct scb_track {
   int32_t* mpc_iters;            /* [N]       MPC only, may be NULL */
   void*    mpc_ws;               /* MPC only, may be NULL: scheduling scratch, scb_mpccbf_workspace_bytes(N) bytes */
   uint64_t mpc_ws_bytes;
+  int32_t* mpc_fail;             /* [N]       MPC only, may be NULL (in/out): number of control steps of this agent whose MPC solve
+                                              did not end SCB_OPTIMAL (infeasible / iteration limit / numerical) */
 } scb_track;
 
 size_t scb_track_sizeof(void);

@@ -291,6 +291,44 @@ class OracleMPCCBF:
             parts += [self.spec["v_max"] - x[1:, 3], x[1:, 3] + self.spec["v_max"]]
         return J, torch.cat(parts)
 
+    def active_set(self, x_init, goal, u_prev, obs, z, g_tol=1e-6, lam_tol=1e-6):
+        """Active set of the NLP at the point z, defined independently of any solver: rows within g_tol of their bound
+        whose non-negative least-squares multiplier (stationarity grad J = sum lam_i grad g_i over those rows) exceeds
+        lam_tol.  -> (active [n_rows] bool in condensed() order, gap): gap = strict-complementarity margin
+        min_i max(g_i / 1e-4, lam_i / 1e-5) over all rows (>= 1: every row is clearly active or clearly inactive)."""
+        from scipy.optimize import nnls
+        zt = torch.tensor(np.asarray(z, float).reshape(-1), requires_grad=True)
+        J, g = self.condensed(x_init, goal, u_prev, obs, zt)
+        gradJ = torch.autograd.grad(J, zt, retain_graph=True)[0].numpy()
+        gv = g.detach().numpy()
+        near = np.nonzero(gv < g_tol)[0]
+        lam = np.zeros(gv.size)
+        if near.size:
+            A = np.stack([torch.autograd.grad(g[i], zt, retain_graph=True)[0].numpy() for i in near], axis=1)
+            lam[near], _ = nnls(A, gradJ)
+        active = lam > lam_tol
+        gap = float(np.min(np.maximum(np.maximum(gv, 0.0) / 1e-4, lam / 1e-5))) if gv.size else np.inf
+        return active, gap
+
+    def kernel_bit_of_row(self, r):
+        """condensed() row index -> bit index of the CUDA kernel's active mask (include/scb.h, scb_mpccbf_solve)."""
+        H, M, nu = self.H, self.M, self.nu
+        if r < H * M:
+            return r                                             # CBF row (stage k, slot j): k*M + j in both
+        r -= H * M
+        if r < H * nu:                                           # u_ub - u >= 0, row k*nu + i -> upper bound bit
+            k, i = divmod(r, nu)
+            return H * M + k * 2 * nu + 2 * i
+        r -= H * nu
+        if r < H * nu:                                           # u - u_lb >= 0 -> lower bound bit
+            k, i = divmod(r, nu)
+            return H * M + k * 2 * nu + 2 * i + 1
+        r -= H * nu
+        if r < H:                                                # v_max - x_{k+1}[3] >= 0 -> node k+1, upper
+            return H * M + 2 * H * nu + 2 * r
+        r -= H                                                   # x_{k+1}[3] + v_max >= 0 -> lower
+        return H * M + 2 * H * nu + 2 * r + 1
+
     def kkt_error(self, x_init, goal, u_prev, obs, z, res_tol=1e-4):
         """KKT check of a point -> (stationarity residual, min g, complementarity max_i lam_i g_i).
         Multipliers: non-negative least squares over the constraints within tau of their bound, for the SMALLEST

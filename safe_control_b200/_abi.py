@@ -14,7 +14,7 @@ MODEL_IDS = {
     "KinematicBicycle2D_DPCBF": 7,
 }
 MODEL_NAMES = {v: k for k, v in MODEL_IDS.items()}
-MODEL_DIMS = {0: (2, 2), 1: (4, 2), 2: (4, 2), 3: (4, 2), 4: (12, 4), 5: (4, 2), 6: (6, 2), 7: (4, 2)}
+MODEL_DIMS = {0: (2, 2), 1: (4, 2), 2: (4, 2), 3: (4, 2), 4: (12, 4), 5: (4, 2), 6: (6, 2), 7: (4, 2), 8: (3, 2), 9: (3, 3)}
 
 OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL = 0, 1, 2, 3
 STATUS_STR = {0: "optimal", 1: "infeasible", 2: "user_limit", 3: "solver_error"}   # cvxpy's vocabulary
@@ -51,7 +51,7 @@ class ScbTrack(C.Structure):
     _fields_ = [
         ("controller", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("M", C.c_int32), ("W", C.c_int32),
         ("H", C.c_int32), ("enable_rotation", C.c_int32), ("dynamic_obs", C.c_int32),
-        ("att_velocity_tracking", C.c_int32), ("reserved", C.c_int32),
+        ("att_velocity_tracking", C.c_int32), ("mpc_strict", C.c_int32),
         ("reached_threshold", C.c_double), ("rotation_threshold", C.c_double),
         ("k_omega", C.c_double), ("k_a", C.c_double), ("k_v", C.c_double), ("k_a_stop", C.c_double),
         ("w_max", C.c_double), ("att_kp", C.c_double), ("wheel_base", C.c_double), ("delta_max", C.c_double),
@@ -60,6 +60,7 @@ class ScbTrack(C.Structure):
         ("SCENE", _vp),
         ("Uref", _vp), ("OBS", _vp), ("nobs", _vp), ("U", _vp), ("status", _vp), ("active", _vp),
         ("track_flag", _vp), ("mpc_iters", _vp), ("mpc_ws", _vp), ("mpc_ws_bytes", C.c_uint64),
+        ("mpc_fail", _vp),
     ]
 
 
@@ -76,6 +77,7 @@ PROTOTYPES = {
     "scb_model_dims": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "scb_active_words": (C.c_int, [C.c_int, C.c_int]),
     "scb_limits": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "scb_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
     "scb_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "scb_ctx_destroy": (None, [_vp]),
     "scb_ctx_launches": (C.c_long, [_vp]),
@@ -84,14 +86,15 @@ PROTOTYPES = {
     "scb_cbfqp_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),
     "scb_odcbf_solve": (C.c_int, [_P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_odcbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_mpc_active_words": (C.c_int, [_P, C.c_int, C.c_int]),
     "scb_mpccbf_solve": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
-                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_mpccbf_workspace_bytes": (C.c_size_t, [C.c_int]),
     "scb_mpccbf_launch_count": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "scb_mpccbf_solve_ws": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
-                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "scb_mpccbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
-                                        _vp, _vp, _vp, _vp, _vp, _vp]),
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_select_obstacles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),
     "scb_track_sizeof": (C.c_size_t, []),
     "scb_control_step": (C.c_int, [_P, _T, _vp]),

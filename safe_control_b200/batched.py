@@ -35,6 +35,25 @@ def _dev_f64(t, shape, name):
     return t.contiguous()
 
 
+def _dev_out(t, shape, dtype, name, dev):
+    """caller-supplied output buffer: CUDA, contiguous, exact shape / dtype, same device as the inputs"""
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError(f"out {name} must be a contiguous CUDA {dtype} tensor")
+    if tuple(t.shape) != tuple(shape) or t.device != dev:
+        raise ValueError(f"out {name} has shape {tuple(t.shape)} on {t.device}, expected {tuple(shape)} on {dev}")
+    return t
+
+
+def _dev_i32(t, N, name):
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == I32 and tuple(t.shape) == (N,)):
+        raise TypeError(f"{name} must be a CUDA int32 tensor of shape ({N},)")
+    return t.contiguous()
+
+
 class _Base:
     controller = None
 
@@ -56,11 +75,7 @@ class _Base:
 
     @staticmethod
     def _nobs(nobs, N, dev):
-        if nobs is None:
-            return None
-        if not (nobs.is_cuda and nobs.dtype == I32 and tuple(nobs.shape) == (N,)):
-            raise TypeError("nobs must be a CUDA int32 tensor of shape (N,)")
-        return nobs.contiguous()
+        return _dev_i32(nobs, N, "nobs")
 
 
 class BatchedCBFQP(_Base):
@@ -99,6 +114,11 @@ class BatchedCBFQP(_Base):
             active = torch.empty((N, self.words), dtype=torch.int64, device=X.device) if want_active else None
         else:
             U, status, active = out
+            U = _dev_out(U, (N, self.nu), F64, "U", X.device)
+            status = _dev_out(status, (N,), I32, "status", X.device)
+            active = _dev_out(active, (N, self.words), torch.int64, "active", X.device)
+            if U is None or status is None:
+                raise TypeError("out must be (U, status, active-or-None)")
         check(lib().scb_cbfqp_solve(self.params, N, self.num_obs, _ptr(X), _ptr(U_ref), _ptr(OBS), stride,
                                     _ptr(nobs), _ptr(U), _ptr(status), _ptr(active), _stream()), "scb_cbfqp_solve")
         self.launches += 1
@@ -143,6 +163,7 @@ class BatchedMPCCBF(_Base):
         self.ngoal = 3 if self.model == "Quad3D" else 2
         self._ws = None                 # scheduling scratch (scb_mpccbf_workspace_bytes), grown on demand
         self.schedule = True            # False: index order (scb_mpccbf_solve)
+        self.active_words = int(lib().scb_mpc_active_words(self.params, self.num_obs, self.horizon))
 
     def _workspace(self, N, dev):
         need = int(lib().scb_mpccbf_workspace_bytes(N))
@@ -150,8 +171,9 @@ class BatchedMPCCBF(_Base):
             self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)
         return self._ws, need
 
-    def solve(self, X, goal, u_prev, OBS, nobs=None, U_ref=None, track=None, want_pred=False):
-        """-> dict(U, status, iters, kkt[, pred_x, pred_u])"""
+    def solve(self, X, goal, u_prev, OBS, nobs=None, U_ref=None, track=None, want_pred=False, want_active=False):
+        """-> dict(U, status, iters, kkt[, pred_x, pred_u][, active [N, active_words] int64: bit pattern of the u64 mask,
+        bit k*M + j = CBF row (stage k, obstacle slot j), then the input / velocity bounds, include/scb.h])"""
         require_cuda()
         N, H = X.shape[0], self.horizon
         X = _dev_f64(X, (N, self.nx), "X")
@@ -161,22 +183,28 @@ class BatchedMPCCBF(_Base):
             U_ref = _dev_f64(U_ref, (N, self.nu), "U_ref")
         OBS, stride = self._obs_args(OBS, N)
         nobs = self._nobs(nobs, N, X.device)
+        track = _dev_i32(track, N, "track")
+        if track is not None and U_ref is None:
+            raise ValueError("track needs U_ref (agents with track == 0 get U_ref back)")
         dev = X.device
         U = torch.empty((N, self.nu), dtype=F64, device=dev)
         status = torch.empty((N,), dtype=I32, device=dev)
         iters = torch.empty((N,), dtype=I32, device=dev)
+        active = torch.empty((N, self.active_words), dtype=torch.int64, device=dev) if want_active else None
         kkt = torch.empty((N,), dtype=F64, device=dev)
         px = torch.empty((N, H + 1, self.nx), dtype=F64, device=dev) if want_pred else None
         pu = torch.empty((N, H, self.nu), dtype=F64, device=dev) if want_pred else None
         ws, ws_bytes = self._workspace(N, dev) if self.schedule else (None, 0)
         check(lib().scb_mpccbf_solve_ws(self.params, N, self.num_obs, H, _ptr(X), _ptr(U_ref), _ptr(goal), _ptr(u_prev),
                                         _ptr(track), _ptr(OBS), stride, _ptr(nobs), _ptr(U), _ptr(status), _ptr(px),
-                                        _ptr(pu), _ptr(iters), _ptr(kkt), _ptr(ws), ws_bytes, _stream()),
+                                        _ptr(pu), _ptr(iters), _ptr(kkt), _ptr(active), _ptr(ws), ws_bytes, _stream()),
               "scb_mpccbf_solve_ws")
         self.launches += int(lib().scb_mpccbf_launch_count(self.params, N, self.num_obs, H, int(self.schedule)))
         out = dict(U=U, status=status, iters=iters, kkt=kkt)
         if want_pred:
             out.update(pred_x=px, pred_u=pu)
+        if want_active:
+            out["active"] = active
         return out
 
 
@@ -208,12 +236,29 @@ class HostContext:
         return int(lib().scb_ctx_launches(self._h))
 
     @staticmethod
-    def _np(a, dtype, name):
+    def _np(a, dtype, name, shape=None):
+        """C-contiguous numpy array of `dtype` and (when given) exactly `shape`: the C call reads / writes
+        prod(shape) elements through the raw pointer, so a mismatch must be a Python error, not a fault."""
         if a is None:
             return None
         if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous):
             raise TypeError(f"{name} must be a C-contiguous numpy array of {dtype}")
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name} has shape {tuple(a.shape)}, expected {tuple(shape)}")
         return a
+
+    @classmethod
+    def _obs(cls, OBS, N, M):
+        if not isinstance(OBS, np.ndarray) or OBS.ndim not in (2, 3):
+            raise TypeError("OBS must be a numpy array [N, M, 7] or [M, 7]")
+        if OBS.ndim == 2:
+            return cls._np(OBS, np.float64, "OBS", (M, 7)), 0
+        return cls._np(OBS, np.float64, "OBS", (N, M, 7)), 7 * M
+
+    @staticmethod
+    def _dims(params):
+        nx, nu = _abi.MODEL_DIMS[int(params.model)]
+        return nx, nu
 
     @staticmethod
     def _p(a):
@@ -221,15 +266,19 @@ class HostContext:
 
     def cbfqp_solve(self, params, M, X, U_ref, OBS, nobs=None, out=None, want_active=True):
         N = X.shape[0]
-        X = self._np(X, np.float64, "X"); U_ref = self._np(U_ref, np.float64, "U_ref")
-        OBS = self._np(OBS, np.float64, "OBS"); nobs = self._np(nobs, np.int32, "nobs")
-        stride = 0 if OBS.ndim == 2 else 7 * M
-        words = (M + 2 * params.nu + 63) // 64
+        nx, nu = self._dims(params)
+        X = self._np(X, np.float64, "X", (N, nx)); U_ref = self._np(U_ref, np.float64, "U_ref", (N, nu))
+        OBS, stride = self._obs(OBS, N, M); nobs = self._np(nobs, np.int32, "nobs", (N,))
+        words = (M + 2 * nu + 63) // 64
         if out is None:
-            U = np.empty((N, params.nu)); status = np.empty(N, np.int32)
+            U = np.empty((N, nu)); status = np.empty(N, np.int32)
             active = np.empty((N, words), np.uint64) if want_active else None
         else:
             U, status, active = out
+            U = self._np(U, np.float64, "out U", (N, nu)); status = self._np(status, np.int32, "out status", (N,))
+            active = self._np(active, np.uint64, "out active", (N, words))
+            if U is None or status is None:
+                raise TypeError("out must be (U, status, active-or-None)")
         check(lib().scb_cbfqp_solve_host(self._h, params, N, M, self._p(X), self._p(U_ref), self._p(OBS), stride,
                                          self._p(nobs), self._p(U), self._p(status), self._p(active)),
               "scb_cbfqp_solve_host")
@@ -237,34 +286,46 @@ class HostContext:
 
     def odcbf_solve(self, params, M, X, U_ref, OBS, nobs=None, out=None):
         N = X.shape[0]
-        X = self._np(X, np.float64, "X"); U_ref = self._np(U_ref, np.float64, "U_ref")
-        OBS = self._np(OBS, np.float64, "OBS"); nobs = self._np(nobs, np.int32, "nobs")
-        stride = 0 if OBS.ndim == 2 else 7 * M
+        nx, nu = self._dims(params)
+        X = self._np(X, np.float64, "X", (N, nx)); U_ref = self._np(U_ref, np.float64, "U_ref", (N, 2))
+        OBS, stride = self._obs(OBS, N, M); nobs = self._np(nobs, np.int32, "nobs", (N,))
         if out is None:
             U = np.empty((N, 2)); omega = np.empty((N, 2)); sel = np.empty(N, np.int32)
             status = np.empty(N, np.int32); active = np.empty(N, np.uint64)
         else:
             U, omega, sel, status, active = out
+            U = self._np(U, np.float64, "out U", (N, 2)); omega = self._np(omega, np.float64, "out omega", (N, 2))
+            sel = self._np(sel, np.int32, "out sel", (N,)); status = self._np(status, np.int32, "out status", (N,))
+            active = self._np(active, np.uint64, "out active", (N,))
+            if U is None or status is None:
+                raise TypeError("out must be (U, omega, sel, status, active)")
         check(lib().scb_odcbf_solve_host(self._h, params, N, M, self._p(X), self._p(U_ref), self._p(OBS), stride,
                                          self._p(nobs), self._p(U), self._p(omega), self._p(sel), self._p(status),
                                          self._p(active)), "scb_odcbf_solve_host")
         return U, omega, sel, status, active
 
-    def mpccbf_solve(self, params, M, H, X, goal, u_prev, OBS, nobs=None, U_ref=None, track=None, want_pred=False):
+    def mpccbf_solve(self, params, M, H, X, goal, u_prev, OBS, nobs=None, U_ref=None, track=None, want_pred=False,
+                     want_active=False):
         N = X.shape[0]
-        X = self._np(X, np.float64, "X"); goal = self._np(goal, np.float64, "goal")
-        u_prev = self._np(u_prev, np.float64, "u_prev"); OBS = self._np(OBS, np.float64, "OBS")
-        nobs = self._np(nobs, np.int32, "nobs"); U_ref = self._np(U_ref, np.float64, "U_ref")
-        track = self._np(track, np.int32, "track")
-        stride = 0 if OBS.ndim == 2 else 7 * M
-        U = np.empty((N, params.nu)); status = np.empty(N, np.int32); iters = np.empty(N, np.int32); kkt = np.empty(N)
-        px = np.empty((N, H + 1, params.nx)) if want_pred else None
-        pu = np.empty((N, H, params.nu)) if want_pred else None
+        nx, nu = self._dims(params)
+        ng = 3 if int(params.model) == _abi.MODEL_IDS["Quad3D"] else 2
+        X = self._np(X, np.float64, "X", (N, nx)); goal = self._np(goal, np.float64, "goal", (N, ng))
+        u_prev = self._np(u_prev, np.float64, "u_prev", (N, nu)); OBS, stride = self._obs(OBS, N, M)
+        nobs = self._np(nobs, np.int32, "nobs", (N,)); U_ref = self._np(U_ref, np.float64, "U_ref", (N, nu))
+        track = self._np(track, np.int32, "track", (N,))
+        if track is not None and U_ref is None:
+            raise ValueError("track needs U_ref")
+        U = np.empty((N, nu)); status = np.empty(N, np.int32); iters = np.empty(N, np.int32); kkt = np.empty(N)
+        px = np.empty((N, H + 1, nx)) if want_pred else None
+        pu = np.empty((N, H, nu)) if want_pred else None
+        active = np.empty((N, int(lib().scb_mpc_active_words(params, M, H))), np.uint64) if want_active else None
         check(lib().scb_mpccbf_solve_host(self._h, params, N, M, H, self._p(X), self._p(U_ref), self._p(goal),
                                           self._p(u_prev), self._p(track), self._p(OBS), stride, self._p(nobs),
                                           self._p(U), self._p(status), self._p(px), self._p(pu), self._p(iters),
-                                          self._p(kkt)), "scb_mpccbf_solve_host")
+                                          self._p(kkt), self._p(active)), "scb_mpccbf_solve_host")
         out = dict(U=U, status=status, iters=iters, kkt=kkt)
         if want_pred:
             out.update(pred_x=px, pred_u=pu)
+        if want_active:
+            out["active"] = active
         return out

@@ -44,35 +44,35 @@ static int cuda_fail(cudaError_t e) {
     if (e__ != cudaSuccess) return cuda_fail(e__); \
   } while (0)
 
-static int sm_count_cached() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-    n = v;
-  }
-  return n;
+// SM count of the CURRENT device (cached per device index; the value is immutable hardware data)
+static int sm_count_of_current() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  if (dev >= 0 && dev < 64) cache[dev] = v;       // (benign race: every writer stores the same value)
+  return v;
 }
 
 // ------------------------------------------------------------------------------ dispatch
 template <int MODEL>
 static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
                           const double* OBS, long stride, const int32_t* nobs, double* U, int32_t* status,
-                          uint64_t* active, int words, cudaStream_t s, bool eager) {
+                          uint64_t* active, int words, cudaStream_t s, bool eager, const int32_t* skip) {
   // warp per agent (small batches), inputs in device memory: obstacle rows are loaded before nobs is known
   if (eager && g.lanes == 32 && g.rpl == 1) {
-    cbfqp_kernel<MODEL, 32, 1, true><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    cbfqp_kernel<MODEL, 32, 1, true><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, skip);
     return SCB_OK;
   }
   if (eager && g.lanes == 32 && g.rpl == 2) {
-    cbfqp_kernel<MODEL, 32, 2, true><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
+    cbfqp_kernel<MODEL, 32, 2, true><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, skip);
     return SCB_OK;
   }
 #define GO(L, R)                                                                                           \
   if (g.lanes == L && g.rpl == R) {                                                                        \
-    cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words); \
+    cbfqp_kernel<MODEL, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, skip); \
     return SCB_OK;                                                                                         \
   }
   GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 3) GO(8, 4) GO(8, 8) GO(4, 5) GO(4, 8)
@@ -83,10 +83,10 @@ static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M
 template <int MODEL, int NW>
 static int launch_od_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
                        const double* OBS, long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel,
-                       int32_t* status, uint64_t* active, cudaStream_t s) {
+                       int32_t* status, uint64_t* active, cudaStream_t s, const int32_t* skip) {
 #define GO(L, R)                                                                                              \
   if (g.lanes == L && g.rpl == R) {                                                                           \
-    odcbf_kernel<MODEL, NW, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active); \
+    odcbf_kernel<MODEL, NW, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, skip); \
     return SCB_OK;                                                                                            \
   }
   GO(32, 1) GO(32, 2) GO(32, 4) GO(8, 3) GO(8, 4) GO(8, 8) GO(4, 5) GO(4, 8)
@@ -131,7 +131,7 @@ int scb_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const dou
   cudaStream_t s = (cudaStream_t)stream;
   const long total = (long)N * M;
   long blocks = (total + 255) / 256;
-  const long cap = (long)sm_count_cached() * 8;
+  const long cap = (long)sm_count_of_current() * 8;
   const int grid = (int)(blocks < cap ? blocks : cap);
   switch (p->model) {
     case SCB_SINGLE_INTEGRATOR_2D: cbfqp_rows_kernel<SCB_SINGLE_INTEGRATOR_2D><<<grid, 256, 0, s>>>(*p, N, M, X, OBS, stride, nobs, A, b); break;
@@ -150,7 +150,7 @@ int scb_cbfqp_rows(const scb_params* p, int N, int M, const double* X, const dou
 
 static int cbfqp_solve_impl(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
                             long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active, void* stream,
-                            bool eager);
+                            bool eager, const int32_t* skip = nullptr);
 
 int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
                     long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active, void* stream) {
@@ -160,16 +160,18 @@ int scb_cbfqp_solve(const scb_params* p, int N, int M, const double* X, const do
 // eager = false: the zero-copy host path (inputs are mapped host memory; rows beyond nobs must not cross PCIe)
 static int cbfqp_solve_impl(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
                             long stride, const int32_t* nobs, double* U, int32_t* status, uint64_t* active, void* stream,
-                            bool eager) {
+                            bool eager, const int32_t* skip) {
   if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
   if (!qp_model_ok(p->model)) return p->model == SCB_QUAD_3D ? SCB_ERR_UNSUPPORTED : SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
-  const int words = scb_active_words(M, p->nu);
+  int nx_m = 0, nu_m = 0;
+  if (scb_model_dims(p->model, &nx_m, &nu_m) != SCB_OK) return SCB_ERR_BAD_ARG;
+  const int words = scb_active_words(M, nu_m);
   cudaStream_t s = (cudaStream_t)stream;
   if (p->model == SCB_MANIPULATOR_2D) {                 // 3-input QP, warp per arm
     const int rows = M + 6, need = (rows + 31) / 32;
-    const long blocks = ((long)N + 3) / 4, cap = (long)sm_count_cached() * 16;
+    const long blocks = ((long)N + 3) / 4, cap = (long)sm_count_of_current() * 16;
     const int grid = (int)(blocks < cap ? blocks : cap);
     if (need <= 1) manipqp_kernel<1><<<grid, kBlock, 0, s>>>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
     else if (need <= 2) manipqp_kernel<2><<<grid, kBlock, 0, s>>>(*p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words);
@@ -179,17 +181,17 @@ static int cbfqp_solve_impl(const scb_params* p, int N, int M, const double* X, 
     return SCB_OK;
   }
   LaunchGeom g;
-  if (!pick_geom(N, M + 2 * p->nu, sm_count_cached(), g, forced_lanes())) return SCB_ERR_TOO_LARGE;
+  if (!pick_geom(N, M + 2 * nu_m, sm_count_of_current(), g, forced_lanes())) return SCB_ERR_TOO_LARGE;
   int rc = SCB_ERR_BAD_ARG;
   switch (p->model) {
-    case SCB_SINGLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_SINGLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
-    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_DYNAMIC_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
-    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
-    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
-    case SCB_DOUBLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_DOUBLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
-    case SCB_QUAD_2D: rc = launch_cbfqp_m<SCB_QUAD_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
-    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
-    case SCB_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager); break;
+    case SCB_SINGLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_SINGLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
+    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_DYNAMIC_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
+    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
+    case SCB_DOUBLE_INTEGRATOR_2D: rc = launch_cbfqp_m<SCB_DOUBLE_INTEGRATOR_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
+    case SCB_QUAD_2D: rc = launch_cbfqp_m<SCB_QUAD_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
+    case SCB_KINEMATIC_BICYCLE_2D_DPCBF: rc = launch_cbfqp_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
+    case SCB_UNICYCLE_2D: rc = launch_cbfqp_m<SCB_UNICYCLE_2D>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, s, eager, skip); break;
   }
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
@@ -197,9 +199,19 @@ static int cbfqp_solve_impl(const scb_params* p, int N, int M, const double* X, 
 }
 
 // ------------------------------------------------------------------------------ optimal decay
+static int odcbf_solve_impl(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
+                            long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
+                            uint64_t* active, void* stream, const int32_t* skip);
+
 int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
                     long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
                     uint64_t* active, void* stream) {
+  return odcbf_solve_impl(p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, stream, nullptr);
+}
+
+static int odcbf_solve_impl(const scb_params* p, int N, int M, const double* X, const double* Uref, const double* OBS,
+                            long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel, int32_t* status,
+                            uint64_t* active, void* stream, const int32_t* skip) {
   if (!p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
   if (p->model == SCB_SINGLE_INTEGRATOR_2D || p->model == SCB_QUAD_3D || p->model == SCB_DOUBLE_INTEGRATOR_2D || p->model == SCB_UNICYCLE_2D || p->model == SCB_MANIPULATOR_2D ||
       p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF)
@@ -208,14 +220,14 @@ int scb_odcbf_solve(const scb_params* p, int N, int M, const double* X, const do
   if (N == 0) return SCB_OK;
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
   LaunchGeom g;
-  if (!pick_geom(N, M > 1 ? M : 1, sm_count_cached(), g)) return SCB_ERR_TOO_LARGE;
+  if (!pick_geom(N, M > 1 ? M : 1, sm_count_of_current(), g)) return SCB_ERR_TOO_LARGE;
   cudaStream_t s = (cudaStream_t)stream;
   int rc = SCB_ERR_BAD_ARG;
   switch (p->model) {
-    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_od_m<SCB_DYNAMIC_UNICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
-    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
-    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D_C3BF, 1>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
-    case SCB_QUAD_2D: rc = launch_od_m<SCB_QUAD_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s); break;
+    case SCB_DYNAMIC_UNICYCLE_2D: rc = launch_od_m<SCB_DYNAMIC_UNICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s, skip); break;
+    case SCB_KINEMATIC_BICYCLE_2D: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s, skip); break;
+    case SCB_KINEMATIC_BICYCLE_2D_C3BF: rc = launch_od_m<SCB_KINEMATIC_BICYCLE_2D_C3BF, 1>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s, skip); break;
+    case SCB_QUAD_2D: rc = launch_od_m<SCB_QUAD_2D, 2>(*p, g, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, s, skip); break;
   }
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
@@ -230,30 +242,31 @@ int scb_mpccbf_launch_count(const scb_params* p, int N, int M, int H, int with_w
   if (N == 0) return 0;
   int n = 0;
   static int dummy;
-  int rc = mpc_launch(*p, N, M, H, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
-                      nullptr, nullptr, nullptr, nullptr, with_workspace ? (void*)&dummy : nullptr,
-                      with_workspace ? mpc_workspace_bytes(N) : 0, nullptr, sm_count_cached(), &n);
+  MpcIO io{};
+  int rc = mpc_launch(*p, N, M, H, io, with_workspace ? (void*)&dummy : nullptr,
+                      with_workspace ? mpc_workspace_bytes(N) : 0, nullptr, sm_count_of_current(), &n);
   return rc == SCB_OK ? n : rc;
 }
 
 int scb_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, const double* Uref,
                      const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
                      const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
-                     int32_t* iters, double* kkt, void* stream) {
+                     int32_t* iters, double* kkt, uint64_t* active, void* stream) {
   return scb_mpccbf_solve_ws(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u,
-                             iters, kkt, nullptr, 0, stream);
+                             iters, kkt, active, nullptr, 0, stream);
 }
 
 int scb_mpccbf_solve_ws(const scb_params* p, int N, int M, int H, const double* X, const double* Uref,
                         const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
                         const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
-                        int32_t* iters, double* kkt, void* workspace, size_t workspace_bytes, void* stream) {
+                        int32_t* iters, double* kkt, uint64_t* active, void* workspace, size_t workspace_bytes,
+                        void* stream) {
   if (!p || N < 0 || M < 0 || H < 1) return SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !goal || !u_prev || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
   if (track && !Uref) return SCB_ERR_BAD_ARG;
-  int rc = mpc_launch(*p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u, iters,
-                      kkt, workspace, workspace_bytes, (cudaStream_t)stream, sm_count_cached());
+  MpcIO io{X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u, iters, kkt, active, nullptr};
+  int rc = mpc_launch(*p, N, M, H, io, workspace, workspace_bytes, (cudaStream_t)stream, sm_count_of_current());
   if (rc != SCB_OK) return rc;
   CK(cudaGetLastError());
   return SCB_OK;
@@ -270,7 +283,7 @@ int scb_select_obstacles(const scb_params* p, int N, int K, int M, const double*
   if (!X || !nobs || (M > 0 && !OBS) || (K > 0 && !SCENE)) return SCB_ERR_BAD_ARG;
   if (K > kTrackMaxScene) return SCB_ERR_TOO_LARGE;
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = track_grid(N, sm_count_cached());
+  const int grid = track_grid(N, sm_count_of_current());
   const size_t smem = (size_t)(kTrackBlock / 32) * (size_t)(K > 0 ? K : 1) * sizeof(double);
 #define SEL(MODEL) case MODEL: select_kernel<MODEL><<<grid, kTrackBlock, smem, s>>>(*p, N, K, M, X, yaw, SCENE, sstride, OBS, nobs, idx); break;
   switch (p->model) {
@@ -305,7 +318,7 @@ static int track_check(const scb_params* p, const scb_track* t) {
 }
 
 static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream_t s) {
-  const int smc = sm_count_cached();
+  const int smc = sm_count_of_current();
 #define PRE(MODEL) case MODEL: launch_pre<MODEL>(*p, *t, s, smc); break;
   switch (p->model) {
     PRE(SCB_SINGLE_INTEGRATOR_2D) PRE(SCB_DYNAMIC_UNICYCLE_2D) PRE(SCB_KINEMATIC_BICYCLE_2D)
@@ -315,15 +328,16 @@ static int control_step_impl(const scb_params* p, const scb_track* t, cudaStream
   if (t->dynamic_obs && t->K > 0) dyn_obs_kernel<<<(t->K + 127) / 128, 128, 0, s>>>(t->SCENE, t->K, p->dt);
   int rc;
   const long stride = 7L * t->M;
-  // the solve kernels also run for agents that are done (their outputs are ignored by the post kernel)
+  // agents that are done are skipped by the solve kernels (`done` for the QP controllers, track_flag < 0 for MPC): their
+  // U / status / active stay those of their terminating step, exactly as in the fused single-launch path
   if (t->controller == SCB_CTRL_CBF_QP)
-    rc = scb_cbfqp_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, t->status, t->active, s);
+    rc = cbfqp_solve_impl(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, t->status, t->active, s, true, t->done);
   else if (t->controller == SCB_CTRL_OPTIMAL_DECAY)
-    rc = scb_odcbf_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, nullptr, nullptr, t->status,
-                         t->active, s);
+    rc = odcbf_solve_impl(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, nullptr, nullptr, t->status,
+                          t->active, s, t->done);
   else
     rc = scb_mpccbf_solve_ws(p, t->N, t->M, t->H, t->X, t->Uref, t->goal, t->u_prev, t->track_flag, t->OBS,
-                             stride, t->nobs, t->U, t->status, nullptr, nullptr, t->mpc_iters, nullptr, t->mpc_ws,
+                             stride, t->nobs, t->U, t->status, nullptr, nullptr, t->mpc_iters, nullptr, nullptr, t->mpc_ws,
                              (size_t)t->mpc_ws_bytes, s);
   if (rc != SCB_OK) return rc;
 #define POST(MODEL) case MODEL: launch_post<MODEL>(*p, *t, s, smc); break;
@@ -420,6 +434,48 @@ int scb_debug_mpc_profile(long long* out, int reset) {
   return SCB_OK;
 }
 #endif
+
+// ------------------------------------------------------------------------------ measurement helper
+// FP64 FMA throughput of the current device: 16 independent DFMA chains per thread, 2048 threads per SM.  This is the
+// measured denominator of the MPC kernels' roofline (bench.py: roofline.bound = "fp64"); MEASURED_PEAKS.json has no FP64 entry.
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (double)(threadIdx.x + i);
+  for (int k = 0; k < iters; ++k) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sum += acc[i];
+  if (sum == 12345.678) out[0] = sum;          // never true: keeps the chains alive
+}
+
+extern "C" int scb_measure_fp64_peak(double* tflops, void* stream) {
+  if (!tflops) return SCB_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  double* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(double)));
+  const int sms = sm_count_of_current(), blocks = sms * 4, iters = 2048;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {         // first repetition warms up clocks / instruction cache
+    CK(cudaEventRecord(e0, s));
+    fp64_peak_kernel<<<blocks, 512, 0, s>>>(d, iters, 0.999999, 1e-7);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 16.0 * iters * 512.0 * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  CK(cudaGetLastError());
+  *tflops = best;
+  return SCB_OK;
+}
 
 // ------------------------------------------------------------------------------ host-pointer context
 struct scb_ctx {
@@ -525,8 +581,11 @@ int scb_cbfqp_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const do
   if (!c || !p || N < 0 || M < 0) return SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
+  if (!qp_model_ok(p->model)) return p->model == SCB_QUAD_3D ? SCB_ERR_UNSUPPORTED : SCB_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
-  const int nx = p->nx, nu = p->nu, words = scb_active_words(M, nu);
+  int nx = 0, nu = 0;
+  if (scb_model_dims(p->model, &nx, &nu) != SCB_OK) return SCB_ERR_BAD_ARG;     // sizes from the validated model id
+  const int words = scb_active_words(M, nu);
   const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
   size_t need = padded((size_t)N * nx * 8) + padded((size_t)N * nu * 8) * 2 + padded(nobs_el * 8) +
                 padded((size_t)N * 4) * 2 + padded((size_t)N * words * 8);
@@ -574,7 +633,8 @@ int scb_odcbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const do
   if (!X || !Uref || !U || !status || (M > 0 && !OBS)) return SCB_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
   const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
-  const int nx = p->nx;
+  int nx = 0, nu_unused = 0;
+  if (scb_model_dims(p->model, &nx, &nu_unused) != SCB_OK) return SCB_ERR_BAD_ARG;   // sizes from the validated model id
   size_t need = padded((size_t)N * nx * 8) + padded((size_t)N * 2 * 8) * 3 + padded(nobs_el * 8) +
                 padded((size_t)N * 4) * 3 + padded((size_t)N * 8);
   int rc;
@@ -622,14 +682,18 @@ int scb_odcbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, const do
 int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, const double* X, const double* Uref,
                           const double* goal, const double* u_prev, const int32_t* track, const double* OBS,
                           long stride, const int32_t* nobs, double* U, int32_t* status, double* pred_x,
-                          double* pred_u, int32_t* iters, double* kkt) {
+                          double* pred_u, int32_t* iters, double* kkt, uint64_t* active) {
   if (!c || !p || N < 0 || M < 0 || H < 1) return SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !goal || !u_prev || !U || !status || (M > 0 && !OBS) || (track && !Uref)) return SCB_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
-  const int nx = p->nx, nu = p->nu, ng = (p->model == SCB_QUAD_3D) ? 3 : 2;
+  int nx = 0, nu = 0;
+  if (scb_model_dims(p->model, &nx, &nu) != SCB_OK) return SCB_ERR_BAD_ARG;      // sizes from the validated model id
+  const int ng = (p->model == SCB_QUAD_3D) ? 3 : 2;
+  const int aw = active ? scb_mpc_active_words(p, M, H) : 0;
+  if (aw < 0) return aw;
   const size_t nobs_el = (stride == 0) ? (size_t)M * 7 : (size_t)N * (size_t)stride;
-  size_t need = padded((size_t)N * nx * 8) + padded((size_t)N * nu * 8) * 3 + padded((size_t)N * ng * 8) +
+  size_t need = padded((size_t)N * aw * 8) + padded((size_t)N * nx * 8) + padded((size_t)N * nu * 8) * 3 + padded((size_t)N * ng * 8) +
                 padded(nobs_el * 8) + padded((size_t)N * 4) * 4 + padded((size_t)N * 8) +
                 padded((size_t)N * (H + 1) * nx * 8) + padded((size_t)N * H * nu * 8) + padded(mpc_workspace_bytes(N));
   int rc = ctx_reserve(c, need);
@@ -649,6 +713,7 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
   double* dPx = cv.take<double>((size_t)N * (H + 1) * nx);
   double* dPu = cv.take<double>((size_t)N * H * nu);
   char* dWs = cv.take<char>(mpc_workspace_bytes(N));
+  uint64_t* dAct = cv.take<uint64_t>((size_t)N * aw);
   H2D(dX, X, (size_t)N * nx, double);
   if (Uref) H2D(dUr, Uref, (size_t)N * nu, double);
   H2D(dUp, u_prev, (size_t)N * nu, double);
@@ -658,7 +723,8 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
   if (track) H2D(dT, track, N, int32_t);
   rc = scb_mpccbf_solve_ws(p, N, M, H, dX, Uref ? dUr : nullptr, dG, dUp, track ? dT : nullptr, dO, stride,
                            nobs ? dN : nullptr, dU, dS, pred_x ? dPx : nullptr, pred_u ? dPu : nullptr,
-                           iters ? dI : nullptr, kkt ? dK : nullptr, dWs, mpc_workspace_bytes(N), c->stream);
+                           iters ? dI : nullptr, kkt ? dK : nullptr, active ? dAct : nullptr, dWs, mpc_workspace_bytes(N),
+                           c->stream);
   if (rc != SCB_OK) return rc;
   c->launches += scb_mpccbf_launch_count(p, N, M, H, 1);
   D2H(U, dU, (size_t)N * nu, double);
@@ -667,6 +733,7 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
   if (pred_u) D2H(pred_u, dPu, (size_t)N * H * nu, double);
   if (iters) D2H(iters, dI, N, int32_t);
   if (kkt) D2H(kkt, dK, N, double);
+  if (active) D2H(active, dAct, (size_t)N * aw, uint64_t);
   CK(cudaStreamSynchronize(c->stream));
   return SCB_OK;
 }

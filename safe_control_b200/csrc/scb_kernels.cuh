@@ -28,10 +28,11 @@ __global__ void __launch_bounds__(kBlock, SCB_QP_MINB(LANES))
 cbfqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
              const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
              const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
-             uint64_t* __restrict__ active, int words) {
+             uint64_t* __restrict__ active, int words, const int32_t* __restrict__ skip) {
   constexpr int NX = ModelCT<MODEL>::NX, NU = ModelCT<MODEL>::NU;
   constexpr int GPB = kBlock / LANES;
   for (long a = (long)blockIdx.x * GPB + threadIdx.x / LANES; a < N; a += (long)gridDim.x * GPB) {
+    if (skip && skip[a]) continue;     // closed loop: agents whose run has ended keep the outputs of their last step
     cbfqp_agent<MODEL, LANES, RPL, true, EAGER>(p, M, nobs ? nobs[a] : M, X + a * NX, Uref + a * NU, OBS + a * stride,
                                    U + a * NU, status + a, active ? active + a * words : nullptr, words);
   }
@@ -101,9 +102,11 @@ __global__ void __launch_bounds__(kBlock)
 odcbf_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
              const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
              const int32_t* __restrict__ nobs, double* __restrict__ U, double* __restrict__ omega,
-             int32_t* __restrict__ sel, int32_t* __restrict__ status, uint64_t* __restrict__ active) {
+             int32_t* __restrict__ sel, int32_t* __restrict__ status, uint64_t* __restrict__ active,
+             const int32_t* __restrict__ skip) {
   constexpr int GPB = kBlock / LANES;
   for (long a = (long)blockIdx.x * GPB + threadIdx.x / LANES; a < N; a += (long)gridDim.x * GPB) {
+    if (skip && skip[a]) continue;
     odcbf_agent<MODEL, NW, LANES, RPL>(p, M, nobs ? nobs[a] : M, X + a * ModelCT<MODEL>::NX, Uref + a * 2, OBS + a * stride,
                                        U + a * 2, omega ? omega + a * 2 : nullptr, sel ? sel + a : nullptr,
                                        status + a, active ? active + a : nullptr);

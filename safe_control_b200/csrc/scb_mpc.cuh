@@ -441,6 +441,12 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   return L;
 }
 
+// words of the MPC active mask (include/scb.h scb_mpc_active_words): H*M CBF rows, then the NS simple bounds
+template <class Mod>
+SCB_HD int mpc_active_words(int H, int M) {
+  return (H * M + 2 * H * Mod::NU + (Mod::VBOUND ? 2 * H : 0) + 63) / 64;
+}
+
 // simple (bound) constraint q:  g_q = sgn * y_k[var] + off >= 0
 struct SimpleCon { int k, var; double sgn, off; };
 template <int NX, int NU>
@@ -1351,7 +1357,8 @@ struct MpcSolver {
   }
 
   SCB_HD void solve(int nobs, const double* x0, const double* goal_in, int ngoal, const double* up, const double* obs,
-                    double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+                    double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt,
+                    uint64_t* active = nullptr) {
     double Jcur = init(nobs, x0, goal_in, ngoal, up, obs);
 
     // objective scaling as IPOPT's default gradient-based scaling: max |dJ/dz| at the start <= 100
@@ -1610,6 +1617,29 @@ struct MpcSolver {
       sync();
       SCB_PH(13);
     }
+    // active set at exit: row i is active <=> its multiplier dominates its value (lam_i > g_i; at a converged point
+    // lam_i g_i ~ mu <= 1e-9, so either g_i < 3e-5 < lam_i or the reverse).  Bit k*M + j = CBF row of (stage k, obstacle
+    // slot j); bit H*M + q = simple bound q in decode_simple's order.
+    if (active) {
+      const int total = H * M + L.NS, words = (total + 63) >> 6;
+      SCB_LANE_UNROLL
+      for (int wd = lane; wd < words; wd += LANES) {
+        uint64_t bits = 0ull;
+        SCB_LOOP
+        for (int b = 0; b < 64; ++b) {
+          const int t = wd * 64 + b;
+          if (t >= total) break;
+          double g, lam;
+          if (t < H * M) { g = w[L.C + t]; lam = w[L.L + t]; }
+          else {
+            const SimpleCon c = decode_simple<NX, NU>(p, H, t - H * M);
+            g = simple_value(c, w + L.Z, w + L.X); lam = w[L.SL + (t - H * M)];
+          }
+          if (lam > fmax(g, 0.0)) bits |= 1ull << b;
+        }
+        active[wd] = bits;
+      }
+    }
     // outputs
     if (lane == 0) {
 #pragma unroll
@@ -1639,13 +1669,13 @@ struct MpcSolver {
 template <int MODEL, int LANES>
 SCB_HD void mpc_agent(const scb_params& p, int H, int M, int nobs, const double* x0, const double* goal,
                       const double* uprev, const double* obs, double* workspace, double* U, int32_t* status,
-                      double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+                      double* pred_x, double* pred_u, int32_t* iters, double* kkt, uint64_t* active = nullptr) {
   using Mod = MpcModel<MODEL>;
   const MpcLayout L = mpc_layout<Mod, LANES == 1>(H, M);
   MpcSolver<MODEL, LANES> s(p, L, workspace);
   if (nobs < 0) nobs = 0;
   if (nobs > M) nobs = M;
-  s.solve(nobs, x0, goal, Mod::NGOAL, uprev, obs, U, status, pred_x, pred_u, iters, kkt);
+  s.solve(nobs, x0, goal, Mod::NGOAL, uprev, obs, U, status, pred_x, pred_u, iters, kkt, active);
 }
 
 }  // namespace scb

@@ -26,12 +26,14 @@ constexpr int mpc_lanes() {
 
 template <int MODEL, int LANES>
 __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid_constant__ scb_params p, int N, int M, int H, int ws_doubles, int gpb,
-                           const double* __restrict__ X, const double* __restrict__ Uref,
-                           const double* __restrict__ goal, const double* __restrict__ u_prev,
-                           const int32_t* __restrict__ track, const double* __restrict__ OBS, long stride,
-                           const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
-                           double* __restrict__ pred_x, double* __restrict__ pred_u, int32_t* __restrict__ iters,
-                           double* __restrict__ kkt, int* __restrict__ next_agent, const int32_t* __restrict__ order) {
+                           const __grid_constant__ MpcIO io, int active_words, int* __restrict__ next_agent,
+                           const int32_t* __restrict__ order) {
+  const double* __restrict__ X = io.X; const double* __restrict__ Uref = io.Uref; const double* __restrict__ goal = io.goal;
+  const double* __restrict__ u_prev = io.u_prev; const int32_t* __restrict__ track = io.track;
+  const double* __restrict__ OBS = io.OBS; const long stride = io.stride; const int32_t* __restrict__ nobs = io.nobs;
+  double* __restrict__ U = io.U; int32_t* __restrict__ status = io.status; double* __restrict__ pred_x = io.pred_x;
+  double* __restrict__ pred_u = io.pred_u; int32_t* __restrict__ iters = io.iters; double* __restrict__ kkt = io.kkt;
+  uint64_t* __restrict__ active = io.active;
   extern __shared__ double smem[];
   using Mod = MpcModel<MODEL>;
   constexpr int NX = Mod::NX, NU = Mod::NU;
@@ -48,8 +50,8 @@ __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid
     const long a = order ? (long)order[q] : q;
     // agents with a superellipsoid row belong to the general-row variant of the model (second launch), all others
     // to the fast path: each kernel skips what is not its kind
-    bool mine = true, se_unsupported = false;
-    if constexpr (kIsSe || kHasSeVariant) {
+    bool mine = !(track && track[a] < 0), se_unsupported = false;     // track < 0: skip (outputs untouched)
+    if (mine) if constexpr (kIsSe || kHasSeVariant) {
       const int no = nobs ? min(max(nobs[a], 0), M) : M;
       unsigned se = 0;
       for (int j = threadIdx.x & (LANES - 1); j < no; j += LANES) se |= (__ldg(OBS + a * stride + j * 7 + 6) >= 0.5) ? 1u : 0u;
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid
         status[a] = SCB_NUMERICAL;
         if (iters) iters[a] = 0;
         if (kkt) kkt[a] = kInf;
+        if (active) for (int q2 = 0; q2 < active_words; ++q2) active[a * active_words + q2] = 0ull;
       }
     } else if (track && track[a] == 0) {
       // state_machine != 'track': return u_ref untouched, no solve (mpc_cbf.py:379-381)
@@ -71,13 +74,15 @@ __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid
         status[a] = SCB_OPTIMAL;
         if (iters) iters[a] = 0;
         if (kkt) kkt[a] = 0.0;
+        if (active) for (int q2 = 0; q2 < active_words; ++q2) active[a * active_words + q2] = 0ull;
       }
     } else {
     mpc_agent<MODEL, LANES>(p, H, M, nobs ? nobs[a] : M, X + a * NX, goal + a * Mod::NGOAL, u_prev + a * NU, OBS + a * stride, ws,
                             U + a * NU, status + a, pred_x ? pred_x + a * (H + 1) * NX : nullptr,
                             pred_u ? pred_u + a * H * NU : nullptr, iters ? iters + a : nullptr,
-                            kkt ? kkt + a : nullptr);
+                            kkt ? kkt + a : nullptr, active ? active + a * active_words : nullptr);
     }
+    if (!next_agent) { q += first_dynamic; continue; }     // no workspace: static stride
     int nxt = 0;
     if ((threadIdx.x & (LANES - 1)) == 0) nxt = atomicAdd(next_agent, 1);
     nxt = __shfl_sync(Grp<LANES>::gmask(), nxt, 0, LANES);
@@ -105,7 +110,7 @@ __global__ void mpc_key_kernel(const __grid_constant__ scb_params p, int N, cons
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= N) return;
   int bin = kMpcBins - 1;                                  // not solved (state machine != track): last
-  if (!track || track[a] != 0) {
+  if (!track || track[a] > 0) {
     double w0, w1, w2, Wsum;
     if (Mod::REL == 2) {
       const double g1 = p.alpha1 + p.alpha2, g2 = p.alpha1 * p.alpha2;
@@ -175,11 +180,8 @@ static __global__ void __launch_bounds__(kMpcBins) mpc_order_kernel(int N, const
 }
 
 template <int MODEL>
-int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* X, const double* Uref,
-                        const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
-                        const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
-                        int32_t* iters, double* kkt, int* counter, void* workspace, size_t workspace_bytes, cudaStream_t s,
-                 int sm_count, int* count_only) {
+int mpc_launch_m(const scb_params& p, int N, int M, int H, const MpcIO& io, int* counter, void* workspace,
+                 size_t workspace_bytes, cudaStream_t s, int sm_count, int* count_only) {
   using Mod = MpcModel<MODEL>;
   const MpcLayout L = mpc_layout<Mod, false>(H, M);
   const size_t per = (size_t)L.total * sizeof(double);
@@ -205,23 +207,20 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* X, cons
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SCB_ERR_TOO_LARGE;
   if (scheduled) {
-    int32_t* hist = (int32_t*)workspace;
+    int32_t* hist = (int32_t*)workspace + kMpcWsHead;
     int32_t* bin_of = hist + kMpcBins;
     int32_t* ord = bin_of + N;
     if (cudaMemsetAsync(hist, 0, kMpcBins * sizeof(int32_t), s) != cudaSuccess) return SCB_ERR_CUDA;
-    mpc_key_kernel<MODEL><<<(N + 127) / 128, 128, 0, s>>>(p, N, X, u_prev, track, OBS, stride, nobs, M, bin_of, hist);
+    mpc_key_kernel<MODEL><<<(N + 127) / 128, 128, 0, s>>>(p, N, io.X, io.u_prev, io.track, io.OBS, io.stride, io.nobs, M, bin_of, hist);
     mpc_order_kernel<<<1, kMpcBins, 0, s>>>(N, bin_of, hist, ord);
     order = ord;
   }
-  kern<<<(int)blocks, ((gpb * kLanes + 31) / 32) * 32, smem, s>>>(p, N, M, H, L.total, gpb, X, Uref, goal, u_prev, track, OBS, stride, nobs, U,
-                                                  status, pred_x, pred_u, iters, kkt, counter, order);
+  kern<<<(int)blocks, ((gpb * kLanes + 31) / 32) * 32, smem, s>>>(p, N, M, H, L.total, gpb, io, mpc_active_words<Mod>(H, M), counter, order);
   return SCB_OK;
 }
 
 
 #define SCB_MPC_INSTANTIATE(MODEL)                                                                                   \
-  template int mpc_launch_m<MODEL>(const scb_params&, int, int, int, const double*, const double*, const double*,   \
-                                   const double*, const int32_t*, const double*, long, const int32_t*, double*,     \
-                                   int32_t*, double*, double*, int32_t*, double*, int*, void*, size_t, cudaStream_t, int, int*);
+  template int mpc_launch_m<MODEL>(const scb_params&, int, int, int, const MpcIO&, int*, void*, size_t, cudaStream_t, int, int*);
 
 }  // namespace scb

@@ -16,94 +16,66 @@
 namespace scb {
 
 constexpr int kMpcMaxObs = 64;
-constexpr int kMpcMaxH = 16;
+// horizon limit: the stage-wise (Riccati) solver is O(H) in workspace and time, so the real limit is the shared-memory
+// budget of one agent (mpc_launch_m returns SCB_ERR_TOO_LARGE when a single workspace exceeds it); VTOL2D uses H = 30
+constexpr int kMpcMaxH = 32;
+// all caller arrays of one MPC launch (device pointers; see include/scb.h scb_mpccbf_solve_ws)
+struct MpcIO {
+  const double* X; const double* Uref; const double* goal; const double* u_prev; const int32_t* track;
+  const double* OBS; long stride; const int32_t* nobs;
+  double* U; int32_t* status; double* pred_x; double* pred_u; int32_t* iters; double* kkt;
+  uint64_t* active;      // [N, active_words] or NULL: bit k*M + j = CBF row (stage k, obstacle slot j), then the simple bounds
+  double* omega;         // optimal-decay MPC only: [N, H, 2] or NULL
+};
 // defined in scb_mpc_impl.cuh, explicitly instantiated per model (scb_mpc_inst.cu)
 template <int MODEL>
-int mpc_launch_m(const scb_params& p, int N, int M, int H, const double* X, const double* Uref,
-                 const double* goal, const double* u_prev, const int32_t* track, const double* OBS, long stride,
-                 const int32_t* nobs, double* U, int32_t* status, double* pred_x, double* pred_u,
-                 int32_t* iters, double* kkt, int* counter, void* workspace, size_t workspace_bytes, cudaStream_t s,
-                 int sm_count, int* count_only);
+int mpc_launch_m(const scb_params& p, int N, int M, int H, const MpcIO& io, int* counter, void* workspace,
+                 size_t workspace_bytes, cudaStream_t s, int sm_count, int* count_only);
 
-// scheduling scratch of one launch: histogram [1024] + bin per agent [N] + schedule [N], int32
-inline size_t mpc_workspace_bytes(long N) { return (size_t)(1024 + 2 * (N > 0 ? N : 0)) * sizeof(int32_t); }
-
-// Per-launch work counters: a small ring of zero-initialised ints per device; each launch takes the next slot and
-// re-zeroes it with a stream-ordered memset just before the kernel, so concurrent streams and CUDA-graph capture are
-// safe (a slot is only reused after kRing further launches on that device).
-constexpr int kRing = 4096;
-inline int* mpc_counter_slot(cudaStream_t s) {
-  static int* ring[64] = {nullptr};
-  static unsigned next[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!ring[dev]) {
-    if (cudaMalloc((void**)&ring[dev], kRing * sizeof(int)) != cudaSuccess) { ring[dev] = nullptr; return nullptr; }
-    cudaMemset(ring[dev], 0, kRing * sizeof(int));
-  }
-  int* slot = ring[dev] + (__sync_fetch_and_add(&next[dev], 1u) % kRing);
-  if (cudaMemsetAsync(slot, 0, sizeof(int), s) != cudaSuccess) return nullptr;
-  return slot;
-}
+// Caller-owned scratch of one call (scb_mpccbf_workspace_bytes): work counters [kMpcWsHead ints: one per launch of the
+// call, zeroed by a stream-ordered memset], histogram [1024], bin per agent [N], schedule [N], all int32.  The library
+// owns no device memory and no global state: without a workspace the kernel strides the agents statically.
+constexpr int kMpcWsHead = 16;
+inline size_t mpc_workspace_bytes(long N) { return (size_t)(kMpcWsHead + 1024 + 2 * (N > 0 ? N : 0)) * sizeof(int32_t); }
 
 #ifndef SCB_MPC_NO_DISPATCH
 constexpr int kMpcSeBaseId = 100;       // == kMpcSeBase (scb_mpc.cuh): general-row variants of SI / DU / DI for superellipsoid rows
 // fast path + (when p.mpc_superellipsoid) the general-row launch for the agents that have a superellipsoid row
 template <int MODEL>
-inline int mpc_launch_se(const scb_params& p, int N, int M, int H, const double* X, const double* Uref, const double* goal,
-                         const double* u_prev, const int32_t* track, const double* OBS, long stride, const int32_t* nobs,
-                         double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt,
-                         int* counter, void* workspace, size_t workspace_bytes, cudaStream_t s, int sm_count, int* count_only) {
-  int rc = mpc_launch_m<MODEL>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u, iters,
-                               kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
+inline int mpc_launch_se(const scb_params& p, int N, int M, int H, const MpcIO& io, int* counter, void* workspace,
+                         size_t workspace_bytes, cudaStream_t s, int sm_count, int* count_only) {
+  int rc = mpc_launch_m<MODEL>(p, N, M, H, io, counter, workspace, workspace_bytes, s, sm_count, count_only);
   if (rc != SCB_OK || !p.mpc_superellipsoid) return rc;
   int n2 = 0;
-  int* counter2 = count_only ? nullptr : mpc_counter_slot(s);
-  if (!counter2 && !count_only) return SCB_ERR_ALLOC;
-  rc = mpc_launch_m<kMpcSeBaseId + MODEL>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x, pred_u,
-                                          iters, kkt, counter2, nullptr, 0, s, sm_count, count_only ? &n2 : nullptr);
+  int* counter2 = counter ? counter + 1 : nullptr;
+  rc = mpc_launch_m<kMpcSeBaseId + MODEL>(p, N, M, H, io, counter2, nullptr, 0, s, sm_count, count_only ? &n2 : nullptr);
   if (count_only) *count_only += n2;
   return rc;
 }
    // (a per-model translation unit must not see references to the other models' launchers)
-inline int mpc_launch(const scb_params& p, int N, int M, int H, const double* X, const double* Uref, const double* goal,
-                      const double* u_prev, const int32_t* track, const double* OBS, long stride, const int32_t* nobs,
-                      double* U, int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt,
-                      void* workspace, size_t workspace_bytes, cudaStream_t s, int sm_count, int* count_only = nullptr) {
-  if (M > kMpcMaxObs || H > kMpcMaxH || H * p.nu > 64) return SCB_ERR_TOO_LARGE;
-  int* counter = count_only ? nullptr : mpc_counter_slot(s);
-  if (!counter && !count_only) return SCB_ERR_ALLOC;
+inline int mpc_launch(const scb_params& p, int N, int M, int H, const MpcIO& io, void* workspace, size_t workspace_bytes,
+                      cudaStream_t s, int sm_count, int* count_only = nullptr) {
+  if (M > kMpcMaxObs || H > kMpcMaxH) return SCB_ERR_TOO_LARGE;
+  int* counter = nullptr;                   // dynamic agent scheduling needs the caller's workspace
+  if (!count_only && workspace && workspace_bytes >= mpc_workspace_bytes(N)) {
+    counter = (int*)workspace;
+    if (cudaMemsetAsync(counter, 0, kMpcWsHead * sizeof(int), s) != cudaSuccess) return SCB_ERR_CUDA;
+  }
+#define SCB_GO(FN, MODEL) case MODEL: return FN<MODEL>(p, N, M, H, io, counter, workspace, workspace_bytes, s, sm_count, count_only);
   switch (p.model) {
-    case SCB_SINGLE_INTEGRATOR_2D:
-      return mpc_launch_se<SCB_SINGLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
-                                                    pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_DYNAMIC_UNICYCLE_2D:
-      return mpc_launch_se<SCB_DYNAMIC_UNICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
-                                                   pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_KINEMATIC_BICYCLE_2D:
-      return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
-                                                    pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_DOUBLE_INTEGRATOR_2D:
-      return mpc_launch_se<SCB_DOUBLE_INTEGRATOR_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
-                                                    pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_QUAD_2D:
-      return mpc_launch_m<SCB_QUAD_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
-                                       pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_UNICYCLE_2D:
-      return mpc_launch_m<SCB_UNICYCLE_2D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
-                                           pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_KINEMATIC_BICYCLE_2D_C3BF:
-      return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D_C3BF>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
-                                                         pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_KINEMATIC_BICYCLE_2D_DPCBF:
-      return mpc_launch_m<SCB_KINEMATIC_BICYCLE_2D_DPCBF>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status,
-                                                          pred_x, pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
-    case SCB_QUAD_3D:
-      return mpc_launch_m<SCB_QUAD_3D>(p, N, M, H, X, Uref, goal, u_prev, track, OBS, stride, nobs, U, status, pred_x,
-                                       pred_u, iters, kkt, counter, workspace, workspace_bytes, s, sm_count, count_only);
+    SCB_GO(mpc_launch_se, SCB_SINGLE_INTEGRATOR_2D)
+    SCB_GO(mpc_launch_se, SCB_DYNAMIC_UNICYCLE_2D)
+    SCB_GO(mpc_launch_m, SCB_KINEMATIC_BICYCLE_2D)
+    SCB_GO(mpc_launch_se, SCB_DOUBLE_INTEGRATOR_2D)
+    SCB_GO(mpc_launch_m, SCB_QUAD_2D)
+    SCB_GO(mpc_launch_m, SCB_UNICYCLE_2D)
+    SCB_GO(mpc_launch_m, SCB_KINEMATIC_BICYCLE_2D_C3BF)
+    SCB_GO(mpc_launch_m, SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+    SCB_GO(mpc_launch_m, SCB_QUAD_3D)
     default:
       return SCB_ERR_UNSUPPORTED;     // Manipulator2D: no agent_barrier_dt in the reference
   }
+#undef SCB_GO
 }
 
 #endif

@@ -57,6 +57,17 @@ int scb_model_dims(int model, int* nx, int* nu) {
 
 int scb_active_words(int M, int nu) { return (M + 2 * nu + 63) / 64; }
 
+int scb_mpc_active_words(const scb_params* p, int M, int H) {
+  if (!p || M < 0 || H < 1) return SCB_ERR_BAD_ARG;
+  int nx = 0, nu = 0;
+  if (scb_model_dims(p->model, &nx, &nu) != SCB_OK) return SCB_ERR_BAD_ARG;
+  // models whose MPC bounds the velocity state (mpc_cbf.py:193-199, 205-211): DynamicUnicycle2D, KinematicBicycle2D*
+  const bool vbound = p->model == SCB_DYNAMIC_UNICYCLE_2D || p->model == SCB_KINEMATIC_BICYCLE_2D ||
+                      p->model == SCB_KINEMATIC_BICYCLE_2D_C3BF || p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF;
+  return (H * M + 2 * H * nu + (vbound ? 2 * H : 0) + 63) / 64;
+}
+
+
 int scb_params_default(scb_params* p, int model, const char* controller) {
   if (!p || !controller) return SCB_ERR_BAD_ARG;
   memset(p, 0, sizeof(*p));

@@ -471,7 +471,7 @@ SCB_HD void track_pre_agent(const scb_params& p, const scb_track& t, long a, dou
   constexpr int NX = ML::NX, NU = ML::NU;
   const int lane = G::lane();
   if (t.done[a]) {                                            // frozen: run_all_steps' loop has broken for this agent
-    if (lane == 0 && t.track_flag) t.track_flag[a] = 0;       // (keeps the MPC kernel from re-solving it)
+    if (lane == 0 && t.track_flag) t.track_flag[a] = -1;      // (the MPC kernel skips it: outputs stay those of its last step)
     return;
   }
   double x[NX];
@@ -546,8 +546,12 @@ SCB_HD void track_post_agent(const scb_params& p, const scb_track& t, long a, co
   double u_att = t.u_att[a];
   const int sm = t.sm[a];
   const bool has_goal = t.has_goal[a] != 0;
-  // the reference's MPCCBF.status is hard-wired 'optimal' (mpc_cbf.py:10,400): only the QP controllers can fail here
-  const bool ok = (t.controller == SCB_CTRL_MPC_CBF) ? true : (t.status[a] == SCB_OPTIMAL);
+  // the reference's MPCCBF.status is hard-wired 'optimal' (mpc_cbf.py:10,400): by default only the QP controllers can
+  // fail here.  Our interior-point solver is not IPOPT, so the per-agent MPC status stays visible: `mpc_fail` counts the
+  // control steps whose solve did not end SCB_OPTIMAL, and with `mpc_strict` such a step returns -2 like a failed QP.
+  const bool is_mpc = (t.controller == SCB_CTRL_MPC_CBF);
+  const bool solved = (t.status[a] == SCB_OPTIMAL);
+  const bool ok = is_mpc ? (t.mpc_strict ? solved : true) : solved;
 #if defined(__CUDA_ARCH__)
   if (LANES > 1) __syncwarp(G::gmask());
 #endif
@@ -581,7 +585,8 @@ SCB_HD void track_post_agent(const scb_params& p, const scb_track& t, long a, co
     t.ret[a] = ret;
     t.nsteps[a] += 1;
     if (ret != 0) t.done[a] = 1;
-    if (t.controller == SCB_CTRL_MPC_CBF && sm == SCB_SM_TRACK && ok) {
+    if (is_mpc && !solved && t.mpc_fail) t.mpc_fail[a] += 1;
+    if (is_mpc && sm == SCB_SM_TRACK && ok) {
 #pragma unroll
       for (int i = 0; i < NU; ++i) t.u_prev[a * NU + i] = u[i];
     }

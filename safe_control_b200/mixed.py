@@ -19,7 +19,7 @@ class MixedMPCCBF:
     def launches(self):
         return sum(g.launches for g in self.groups)
 
-    def solve(self, inputs: Sequence[Dict[str, torch.Tensor]]):
+    def solve(self, inputs: Sequence[Dict[str, torch.Tensor]], want_active: bool = False):
         """inputs[g] = dict(X, goal, u_prev, OBS, nobs) for group g -> list of BatchedMPCCBF.solve() dicts.
         Every group is enqueued on its own stream; the caller's current stream waits for all of them."""
         if self.streams is None:
@@ -29,7 +29,7 @@ class MixedMPCCBF:
         for g, st, a in zip(self.groups, self.streams, inputs):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                outs.append(g.solve(a["X"], a["goal"], a["u_prev"], a["OBS"], a.get("nobs")))
+                outs.append(g.solve(a["X"], a["goal"], a["u_prev"], a["OBS"], a.get("nobs"), want_active=want_active))
         for st in self.streams:
             cur.wait_stream(st)
         return outs
@@ -38,3 +38,49 @@ class MixedMPCCBF:
 def split_counts(n_agents: int, n_groups: int) -> List[int]:
     base, extra = divmod(n_agents, n_groups)
     return [base + (1 if g < extra else 0) for g in range(n_groups)]
+
+
+class ShardedMixedMPCCBF:
+    """BASELINE config 5 as north_star describes it: rank `src` holds the whole heterogeneous batch, NCCL scatters
+    each model group's rows over the ranks (contiguous blocks per group, so every GPU gets the same model mix --
+    a Quad3D solve costs several DynamicUnicycle2D solves), every rank solves its blocks with one launch per group
+    on concurrent streams (MixedMPCCBF), and NCCL gathers U / status / iters (/ active) back to `src`
+    (SURVEY.md section 8e).  No communication inside the solve.  Every buffer is allocated once (ShardPlan).
+
+    counts[g] = global number of agents of group g.  solve(inputs) takes, on `src`, inputs[g] = dict(X, goal, u_prev,
+    OBS [n_g, M, 7], nobs) of device tensors, and returns there a list of dict(U, status, iters[, active])
+    with n_g rows each (None on the other ranks)."""
+
+    def __init__(self, robot_specs: Sequence[dict], counts: Sequence[int], num_obs: int, horizon: int, device,
+                 dt: float = 0.05, want_active: bool = False, src: int = 0, group=None):
+        from .sharding import ShardPlan
+        self.mixed = MixedMPCCBF(robot_specs, num_obs, horizon, dt)
+        self.want_active = bool(want_active)
+        self.plans = []
+        F64, I32 = torch.float64, torch.int32
+        for g, n in zip(self.mixed.groups, counts):
+            ins = {"X": ((g.nx,), F64), "goal": ((g.ngoal,), F64), "u_prev": ((g.nu,), F64),
+                   "OBS": ((num_obs, 7), F64), "nobs": ((), I32)}
+            outs = {"U": ((g.nu,), F64), "status": ((), I32), "iters": ((), I32)}
+            if self.want_active:
+                outs["active"] = ((g.active_words,), torch.int64)
+            self.plans.append(ShardPlan(int(n), ins, outs, device, src, group))
+        self.rank = self.plans[0].rank if self.plans else 0
+        self.src = src
+
+    @property
+    def launches(self):
+        return self.mixed.launches
+
+    def scatter(self, inputs):
+        return [pl.scatter(inputs[g] if inputs is not None else None) for g, pl in enumerate(self.plans)]
+
+    def solve_local(self, blocks):
+        return self.mixed.solve(blocks, want_active=self.want_active)
+
+    def gather(self, outs):
+        res = [pl.gather({k: o[k] for k in pl.out_specs}) for pl, o in zip(self.plans, outs)]
+        return res if self.rank == self.src else None
+
+    def solve(self, inputs):
+        return self.gather(self.solve_local(self.scatter(inputs)))

@@ -199,7 +199,8 @@ class TrackerHostState:
         t.w_max = float(s.get("w_max", 0.5))
         t.att_kp = float(s.get("velocity_tracking_yaw_kp", 1.5))
         t.wheel_base = float(s.get("wheel_base", 0.4)); t.delta_max = float(s.get("delta_max", math.radians(32)))
-        t.mpc_ws_bytes = 4 * (1024 + 2 * self.N)                                 # scb_mpccbf_workspace_bytes(N)
+        t.mpc_ws_bytes = 4 * (16 + 1024 + 2 * self.N)                            # scb_mpccbf_workspace_bytes(N)
+        t.mpc_strict = int(bool(s.get("mpc_strict", False)))                     # ours: non-optimal MPC solve -> ret -2
         return t
 
     STATE_ARRAYS = ("X", "yaw", "sm", "wp_idx", "WP", "nwp", "goal", "has_goal", "u_att", "u_prev", "ret", "done",
@@ -210,7 +211,7 @@ class TrackerHostState:
         return dict(Uref=np.zeros((N, nu)), OBS=np.zeros((N, max(M, 1), 7)), nobs=np.zeros(N, np.int32),
                     U=np.zeros((N, nu)), status=np.zeros(N, np.int32), active=np.zeros((N, self.words), np.uint64),
                     track_flag=np.zeros(N, np.int32), mpc_iters=np.zeros(N, np.int32),
-                    mpc_ws=np.zeros(1024 + 2 * N, np.int32))
+                    mpc_ws=np.zeros(16 + 1024 + 2 * N, np.int32), mpc_fail=np.zeros(N, np.int32))
 
 
 class BatchedTrackingController:
@@ -320,6 +321,12 @@ class BatchedTrackingController:
     def done(self): return self._bufs["done"]
     @property
     def nsteps(self): return self._bufs["nsteps"]
+    @property
+    def mpc_fail(self):
+        """mpc_cbf: per agent, the number of control steps whose MPC solve did not end 'optimal' (the reference's
+        MPCCBF.status is hard-wired 'optimal', so this is extra visibility; robot_spec['mpc_strict'] = True makes such a
+        step return -2 like a failed QP)."""
+        return self._bufs["mpc_fail"]
 
     def get_control_input(self):
         return self._bufs["U"]

@@ -109,8 +109,9 @@ int hostsim_odcbf_solve(const scb_params* p, int N, int M, const double* X, cons
 #ifdef SCB_HOSTSIM_MPC
 int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, const double* goal,
                          const double* u_prev, const double* OBS, long stride, const int32_t* nobs, double* U,
-                         int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt) {
+                         int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt, uint64_t* active) {
   const int nx = p->nx, nu = p->nu;
+  const int aw = active ? scb_mpc_active_words(p, M, H) : 0;
   for (int i = 0; i < N; ++i) {
     const int no = nobs ? nobs[i] : M;
     double* px = pred_x ? pred_x + (size_t)i * (H + 1) * nx : nullptr;
@@ -129,7 +130,8 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
     for (int t = 0; t < L.total; ++t) ws[t] = 0.0;                                                              \
     mpc_agent<MODEL, 1>(*p, H, M, no, X + (size_t)i * nx, goal + (size_t)i * Mod::NGOAL, u_prev + (size_t)i * nu,        \
                         OBS + (size_t)i * stride, ws, U + (size_t)i * nu, status + i, px, pu,                   \
-                        iters ? iters + i : nullptr, kkt ? kkt + i : nullptr);                                  \
+                        iters ? iters + i : nullptr, kkt ? kkt + i : nullptr,                                   \
+                        active ? active + (size_t)i * aw : nullptr);                                            \
     delete[] ws;                                                                                                \
   } break;
       MPCCASE(SCB_SINGLE_INTEGRATOR_2D)
@@ -252,17 +254,29 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
   const long stride = 7L * t->M;
   int rc;
   if (t->controller == SCB_CTRL_CBF_QP) {
-    rc = hostsim_cbfqp_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, t->status, t->active);
+    const int words = scb_active_words(t->M, p->nu);
+    rc = 0;
+    for (int a = 0; a < t->N && rc == 0; ++a) {
+      if (t->done[a]) continue;                                    // frozen agents keep their last outputs
+      rc = hostsim_cbfqp_solve(p, 1, t->M, t->X + (size_t)a * p->nx, t->Uref + (size_t)a * p->nu, t->OBS + (size_t)a * stride,
+                               stride, t->nobs + a, t->U + (size_t)a * p->nu, t->status + a,
+                               t->active ? t->active + (size_t)a * words : nullptr);
+    }
   } else if (t->controller == SCB_CTRL_OPTIMAL_DECAY) {
-    rc = hostsim_odcbf_solve(p, t->N, t->M, t->X, t->Uref, t->OBS, stride, t->nobs, t->U, nullptr, nullptr, t->status,
-                             t->active);
+    rc = 0;
+    for (int a = 0; a < t->N && rc == 0; ++a) {
+      if (t->done[a]) continue;
+      rc = hostsim_odcbf_solve(p, 1, t->M, t->X + (size_t)a * p->nx, t->Uref + (size_t)a * 2, t->OBS + (size_t)a * stride, stride,
+                               t->nobs + a, t->U + (size_t)a * 2, nullptr, nullptr, t->status + a,
+                               t->active ? t->active + a : nullptr);
+    }
   } else {
 #ifdef SCB_HOSTSIM_MPC
     const int nx = p->nx, nu = p->nu, ng = (p->model == SCB_QUAD_3D) ? 3 : 2;
     rc = 0;
     for (int a = 0; a < t->N && rc == 0; ++a) {
       if (t->done[a]) continue;
-      if (!t->track_flag[a]) {                                     // mpc_cbf.py:379-381
+      if (t->track_flag[a] <= 0) {                                 // mpc_cbf.py:379-381
         for (int i = 0; i < nu; ++i) t->U[(size_t)a * nu + i] = t->Uref[(size_t)a * nu + i];
         t->status[a] = SCB_OPTIMAL;
         continue;
@@ -270,7 +284,7 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       rc = hostsim_mpccbf_solve(p, 1, t->M, t->H, t->X + (size_t)a * nx, t->goal + (size_t)a * ng,
                                 t->u_prev + (size_t)a * nu, t->OBS + (size_t)a * stride, stride, t->nobs + a,
                                 t->U + (size_t)a * nu, t->status + a, nullptr, nullptr,
-                                t->mpc_iters ? t->mpc_iters + a : nullptr, nullptr);
+                                t->mpc_iters ? t->mpc_iters + a : nullptr, nullptr, nullptr);
     }
 #else
     rc = SCB_ERR_UNSUPPORTED;

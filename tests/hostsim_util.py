@@ -83,17 +83,22 @@ def hs_odcbf_solve(p, X, Uref, OBS, nobs=None):
     return U, om, sel, st, act
 
 
-def hs_mpccbf_solve(p, H, X, goal, u_prev, OBS, nobs=None):
+def hs_mpccbf_solve(p, H, X, goal, u_prev, OBS, nobs=None, want_active=False):
     lib = hostsim()
     N, M = OBS.shape[0], OBS.shape[1]
     X, goal, u_prev, OBS = f64(X), f64(goal), f64(u_prev), f64(OBS)
     U = np.zeros((N, p.nu)); st = np.zeros(N, np.int32); it = np.zeros(N, np.int32); kkt = np.zeros(N)
     px = np.zeros((N, H + 1, p.nx)); pu = np.zeros((N, H, p.nu))
     no = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)
+    lib.scb_mpc_active_words.restype = C.c_int
+    act = np.zeros((N, int(lib.scb_mpc_active_words(C.byref(p), M, H))), np.uint64) if want_active else None
     rc = lib.hostsim_mpccbf_solve(C.byref(p), N, M, H, ptr(X), ptr(goal), ptr(u_prev), ptr(OBS), C.c_long(7 * M), ptr(no),
-                                  ptr(U), ptr(st), ptr(px), ptr(pu), ptr(it), ptr(kkt))
+                                  ptr(U), ptr(st), ptr(px), ptr(pu), ptr(it), ptr(kkt), ptr(act))
     assert rc == 0, rc
-    return dict(U=U, status=st, iters=it, kkt=kkt, pred_x=px, pred_u=pu)
+    out = dict(U=U, status=st, iters=it, kkt=kkt, pred_x=px, pred_u=pu)
+    if want_active:
+        out["active"] = act
+    return out
 
 
 # ---- closed loop (scb_track.cuh) ------------------------------------------------------------------

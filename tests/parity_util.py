@@ -73,21 +73,30 @@ def check_odcbf(spec, M, X, Uref, OBS, nobs, U, omega, sel, status, active, samp
     return dict(n=len(list(idx)), cbf_active=n_act, masks_compared=n_cmp)
 
 
-def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1e-4, min_agree=0.9):
+def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1e-4, min_agree=0.9, second_solver=0):
     """MPC parity: (a) every 'optimal' answer must be a KKT point of the ORACLE's restated NLP
     (independent derivatives: torch.autograd on oracle/mpc_cbf.py: stationarity <= 1e-4 with non-negative least-squares
     multipliers, complementarity max lam_i g_i <= 1e-5), feasible to 1e-7; (b) u0 must agree
-    with the oracle's own SLSQP solve within u0_tol (box-normalised) on >= min_agree of the cases the
-    oracle converged on -- the NLP is non-convex, so a different local optimum (different cost) is
-    counted and reported, not hidden."""
+    with the oracle's own SLSQP solve within u0_tol (box-normalised).  The NLP is non-convex, so a miss is classified by
+    the COST of the two points (both feasible KKT points of the same NLP from the same cold start):
+      same_cost   |J - J_slsqp| <= 1e-6 max(1, |J_slsqp|): same optimum value, flat direction / SLSQP stopped early
+      better      the kernel's point is cheaper: SLSQP sits in a worse basin (or stopped early)
+      worse       the kernel's point is more expensive: a different, worse local optimum
+    and the assertion is that agree + same_cost + better >= min_agree of the compared cases (the kernel's optimum is at
+    least as good as the oracle solver's), with every count reported.
+    (c) when out['active'] is present: the kernel's active mask must equal, bit for bit, the oracle's active set at the
+    oracle's own solution (OracleMPCCBF.active_set) on every agreeing case whose strict-complementarity gap is >= 1.
+    second_solver > 0: on that many agreeing cases also solve with scipy trust-constr warm-started at the cold start
+    ('two solvers agree to 1e-6') and require the same u0."""
     import warnings
+    import torch
     from oracle.mpc_cbf import OracleMPCCBF
     warnings.filterwarnings("ignore")
     o = OracleMPCCBF(spec, num_obs=M, horizon=H)
     N = X.shape[0]
     idx = list(range(N) if sample is None else sample)
     rng = o.u_ub - o.u_lb
-    n_ok = n_cmp = n_agree = n_other = 0
+    n_ok = n_cmp = n_agree = n_same = n_better = n_worse = n_mask = n_second = n_ofail = 0
     worst_kkt = worst_du = 0.0
     for i in idx:
         k = M if nobs is None else max(int(nobs[i]), 0)
@@ -103,19 +112,66 @@ def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1
         worst_kkt = max(worst_kkt, kk)
         u, info = o.solve(X[i], goal[i], u_prev[i], obs)
         if not info["success"] or info["cbf_min"] < -1e-6:
+            n_ofail += 1                                  # the oracle's SLSQP did not converge: nothing to compare u0 with
             continue
         n_cmp += 1
         du = float(np.max(np.abs(out["U"][i] - u) / rng))
-        import torch
         Jo = info["fun"]
         Jm = float(o.condensed(X[i], goal[i], u_prev[i], obs, torch.tensor(out["pred_u"][i].reshape(-1)))[0])
         if du <= u0_tol:
             n_agree += 1; worst_du = max(worst_du, du)
-        elif abs(Jm - Jo) > 1e-7 * max(1.0, abs(Jo)):
-            n_other += 1                      # a different local optimum (or SLSQP stopped early)
+            if "active" in out and out["active"] is not None:
+                act, gap = o.active_set(X[i], goal[i], u_prev[i], obs, info["u_pred"])
+                if gap >= 1.0:
+                    n_mask += 1
+                    words = np.asarray(out["active"][i]).view(np.uint64).reshape(-1)
+                    want = np.zeros(words.size, dtype=np.uint64)
+                    for r in np.nonzero(act)[0]:
+                        b = o.kernel_bit_of_row(int(r))
+                        want[b >> 6] |= np.uint64(1) << np.uint64(b & 63)
+                    assert np.array_equal(want, words), f"agent {i}: MPC active mask {words} vs oracle {want} (gap {gap:.2f})"
+            if n_second < second_solver:
+                n_second += 1
+                u2, info2 = o.solve(X[i], goal[i], u_prev[i], obs, method="trust-constr")
+                du2 = float(np.max(np.abs(u2 - u) / rng))
+                assert du2 <= 1e-4 or abs(info2["fun"] - Jo) > 1e-6 * max(1.0, abs(Jo)), \
+                    f"agent {i}: trust-constr and SLSQP disagree at equal cost (du {du2:.2e})"
+                if du2 <= 1e-4:
+                    assert float(np.max(np.abs(out["U"][i] - u2) / rng)) <= 2e-4, f"agent {i}: kernel vs trust-constr"
+        elif abs(Jm - Jo) <= 1e-6 * max(1.0, abs(Jo)):
+            n_same += 1
+        elif Jm < Jo:
+            n_better += 1
         else:
-            n_other += 1
-    stats = dict(n=len(idx), optimal=n_ok, compared=n_cmp, agree=n_agree, other_local=n_other,
-                 worst_kkt=worst_kkt, worst_du=worst_du)
-    assert n_cmp == 0 or n_agree >= min_agree * n_cmp, stats
+            n_worse += 1
+    stats = dict(n=len(idx), optimal=n_ok, compared=n_cmp, agree=n_agree, same_cost=n_same, better=n_better, worse=n_worse,
+                 other_local=n_same + n_better + n_worse, masks_compared=n_mask, second_solver=n_second,
+                 oracle_failed=n_ofail, worst_kkt=worst_kkt, worst_du=worst_du)
+    assert n_cmp == 0 or (n_agree + n_same + n_better) >= min_agree * n_cmp, stats
+    return stats
+
+
+def _check_mpc_chunk(args):
+    import torch
+    torch.set_num_threads(1)
+    spec, M, H, X, goal, u_prev, OBS, nobs, out, sample, kw = args
+    return check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=sample, min_agree=0.0, **kw)
+
+
+def check_mpc_parallel(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample, min_agree=0.9, procs=None, **kw):
+    """check_mpc over `sample` on all host cores (the oracle costs 2-6 s per agent at config-5 shapes): every per-agent
+    assertion of check_mpc still fires (a worker's AssertionError propagates); the agreement fraction is asserted on the
+    merged counts."""
+    import multiprocessing as mp
+    import os
+    sample = list(sample)
+    procs = min(procs or os.cpu_count() or 1, max(1, len(sample)))
+    if procs <= 1:
+        return check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=sample, min_agree=min_agree, **kw)
+    chunks = [sample[r::procs] for r in range(procs)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        parts = pool.map(_check_mpc_chunk, [(spec, M, H, X, goal, u_prev, OBS, nobs, out, c, kw) for c in chunks])
+    stats = {k: (max(p[k] for p in parts) if k.startswith("worst") else sum(p[k] for p in parts)) for k in parts[0]}
+    n_cmp = stats["compared"]
+    assert n_cmp == 0 or (stats["agree"] + stats["same_cost"] + stats["better"]) >= min_agree * n_cmp, stats
     return stats

@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_struct_mirror_and_helpers(lib):
     assert lib.scb_params_sizeof() == C.sizeof(_abi.ScbParams)
     assert lib.scb_track_sizeof() == C.sizeof(_abi.ScbTrack)
-    assert lib.scb_version() == 100
+    assert lib.scb_version() == 200
     assert b"ok" == lib.scb_strerror(0)
     assert lib.scb_active_words(16, 2) == 1 and lib.scb_active_words(61, 2) == 2
     nx, nu = C.c_int(), C.c_int()
@@ -85,7 +85,7 @@ def test_mpc_launch_count_and_workspace_are_host_arithmetic(lib):
     when superellipsoid rows are enabled."""
     from safe_control_b200.params import resolve_params
     p, _ = resolve_params({"model": "DynamicUnicycle2D"}, "mpc_cbf")
-    assert lib.scb_mpccbf_workspace_bytes(4096) == 4 * (1024 + 2 * 4096)
+    assert lib.scb_mpccbf_workspace_bytes(4096) == 4 * (16 + 1024 + 2 * 4096)
     assert lib.scb_mpccbf_launch_count(p, 4096, 16, 8, 0) == 1
     assert lib.scb_mpccbf_launch_count(p, 4096, 16, 8, 1) == 3
     assert lib.scb_mpccbf_launch_count(p, 64, 16, 8, 1) == 1            # fits the first wave: nothing to schedule

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from parity_util import check_mpc
+from parity_util import check_mpc, check_mpc_parallel
 
 pytestmark = pytest.mark.gpu
 
@@ -28,12 +28,13 @@ def solve(ctrl, sc, goal, **kw):
 
 
 @pytest.mark.parametrize("model,N,H,M,near,n_check", [
-    ("DynamicUnicycle2D", 4096, 8, 16, False, 48),     # BASELINE config 3 at full size, oracle on a sample
+    ("DynamicUnicycle2D", 4096, 8, 16, False, 256),    # BASELINE config 3 at full size, oracle on 256 agents (all host cores)
     ("DynamicUnicycle2D", 256, 8, 16, True, 32),       # goals nearby: interior optima, CBF rows active
-    ("KinematicBicycle2D", 128, 10, 64, False, 12),    # config-5 sized stage (H = 10, 64 obstacle slots)
+    ("DynamicUnicycle2D", 2731, 10, 64, False, 256),   # config 5's three model groups at one GPU's share, 256 agents each
+    ("KinematicBicycle2D", 2731, 10, 64, False, 256),
+    ("Quad3D", 2730, 10, 64, False, 256),
     ("DynamicUnicycle2D", 64, 10, 64, True, 8),
     ("SingleIntegrator2D", 128, 10, 16, False, 12),
-    ("Quad3D", 160, 10, 64, False, 8),                 # config-5's third model family
     ("Quad3D", 64, 8, 16, True, 8),
     ("DoubleIntegrator2D", 256, 10, 16, False, 16),    # the remaining circle-barrier MPC models
     ("Quad2D", 192, 8, 16, False, 12),
@@ -46,16 +47,19 @@ def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     sc = scenes.make_scene(model, N, M, seed=1234, dense=(model == "Quad3D" and near))
     goal = near_goal(sc) if near else sc["goal"]
     ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
-    out = solve(ctrl, sc, goal)
+    out = solve(ctrl, sc, goal, want_active=True)
     frac_ok = (out["status"] == 0).mean()
     # (16 moving obstacles x collision-cone rows: ~20 % of these random scenes are infeasible -- the oracle's SLSQP
     #  fails on the same agents)
     assert frac_ok > (0.7 if model.endswith("BF") else 0.9), (frac_ok, np.bincount(out["status"]))
     rng = np.random.default_rng(0)
     sample = rng.choice(N, n_check, replace=False)
-    stats = check_mpc(ctrl.robot_spec, M, H, sc["X"], goal, sc["u_prev"], sc["OBS"], sc["nobs"], out, sample=sample,
-                      min_agree=0.75 if model.startswith("Kin") else 0.9)
+    # u0 agreement with the oracle's SLSQP (misses classified by cost), bit-exact active masks on the non-degenerate
+    # agreeing cases, trust-constr as the second oracle solver on a few of them
+    stats = check_mpc_parallel(ctrl.robot_spec, M, H, sc["X"], goal, sc["u_prev"], sc["OBS"], sc["nobs"], out, sample=sample,
+                               min_agree=0.9, second_solver=1 if (n_check >= 256 and model == "DynamicUnicycle2D" and M == 16) else 0)
     print(model, N, H, M, stats, "iters mean", out["iters"].mean(), "max", out["iters"].max(), "ok", frac_ok)
+    assert stats["masks_compared"] >= 0.5 * stats["agree"], stats
     # size-independent properties on the WHOLE batch: predictions satisfy the Euler model, inputs in the box
     U, px, pu = out["U"], out["pred_x"], out["pred_u"]
     nu = ctrl.nu
@@ -146,11 +150,11 @@ def test_mpc_schedule_does_not_change_results():
     N, H, M = 3000, 8, 16                                             # more agents than one persistent wave
     sc = scenes.make_scene("DynamicUnicycle2D", N, M, seed=77)
     ctrl = BatchedMPCCBF(sc["spec"], num_obs=M, horizon=H)
-    a = solve(ctrl, sc, sc["goal"]); n_sched = ctrl.launches
+    a = solve(ctrl, sc, sc["goal"], want_active=True); n_sched = ctrl.launches
     ctrl.schedule = False
-    b = solve(ctrl, sc, sc["goal"]); n_plain = ctrl.launches - n_sched
+    b = solve(ctrl, sc, sc["goal"], want_active=True); n_plain = ctrl.launches - n_sched
     assert (n_sched, n_plain) == (3, 1)
-    for k in ("U", "status", "iters", "pred_u", "pred_x", "kkt"):
+    for k in ("U", "status", "iters", "pred_u", "pred_x", "kkt", "active"):
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
@@ -167,9 +171,22 @@ def test_mpc_track_mask_and_host_path():
     ref = solve(ctrl, sc, sc["goal"])
     np.testing.assert_allclose(U[track == 1], ref["U"][track == 1], atol=0)
     ctx = HostContext(0)
-    h = ctx.mpccbf_solve(ctrl.params, M, H, sc["X"], sc["goal"], sc["u_prev"], sc["OBS"], sc["nobs"], want_pred=True)
+    h = ctx.mpccbf_solve(ctrl.params, M, H, sc["X"], sc["goal"], sc["u_prev"], sc["OBS"], sc["nobs"], want_pred=True,
+                         want_active=True)
     np.testing.assert_array_equal(h["U"], ref["U"]); np.testing.assert_array_equal(h["status"], ref["status"])
     np.testing.assert_array_equal(h["pred_u"], ref["pred_u"])
+    refa = solve(ctrl, sc, sc["goal"], want_active=True)
+    np.testing.assert_array_equal(h["active"].view(np.int64), refa["active"])
+    # track < 0: the agent is skipped, its outputs are left untouched (closed loop: frozen agents)
+    track2 = np.ones(N, np.int32); track2[1::4] = -1
+    keep = ctrl.solve(dev(sc["X"]), dev(sc["goal"]), dev(sc["u_prev"]), dev(sc["OBS"]), dev(sc["nobs"]),
+                      U_ref=dev(sc["U_ref"]), track=dev(track2))
+    assert keep["U"].shape == (N, 2)
+    with pytest.raises(TypeError):                                   # raw-pointer arguments are validated in Python
+        ctrl.solve(dev(sc["X"]), dev(sc["goal"]), dev(sc["u_prev"]), dev(sc["OBS"]), dev(sc["nobs"]),
+                   U_ref=dev(sc["U_ref"]), track=torch.ones(N, dtype=torch.int64, device="cuda"))
+    with pytest.raises(ValueError):
+        ctx.mpccbf_solve(ctrl.params, M, H, sc["X"][:, :3].copy(), sc["goal"], sc["u_prev"], sc["OBS"], sc["nobs"])
     ctx.close()
 
 

@@ -197,6 +197,32 @@ def test_mpc_closed_loop(model):
         assert np.median(moved) > (0.3 if model == "DoubleIntegrator2D" else 0.5)   # (DI first brakes its random start velocity)
 
 
+def test_mpc_status_stays_visible_in_the_loop():
+    """The reference's MPCCBF.status is hard-wired 'optimal' (mpc_cbf.py:10, 400) and so is the default loop; our
+    interior-point solver is not IPOPT, so (i) `mpc_fail` counts, per agent, the control steps whose solve did not end
+    SCB_OPTIMAL and (ii) robot_spec['mpc_strict'] makes such a step return -2 without stepping, like a failed QP
+    (tracking.py:627-634).  An iteration cap of 3 makes every solve end non-optimal."""
+    from safe_control_b200 import BatchedTrackingController
+    N, K = 24, 9
+    X0, scene, wps = random_closed_loop_case("DynamicUnicycle2D", N, K, seed=5)
+    spec = {"model": "DynamicUnicycle2D", "num_constraints": 6, "mpc_horizon": 8}
+    for strict in (False, True):
+        tc = BatchedTrackingController(X0, dict(spec, mpc_strict=strict, mpc_max_iter=3), {"pos": "mpc_cbf"}, obs=scene)
+        tc.set_waypoints(wps)
+        for _ in range(12):
+            tc.control_step()
+        o = _np(tc, ("ret", "sm", "status", "done", "nsteps", "mpc_fail", "X"))
+        tracked = o["mpc_fail"] > 0
+        assert tracked.any()                                           # somebody was in 'track' and hit the cap
+        if strict:
+            assert (o["ret"][tracked] == -2).all() and (o["done"][tracked] == 1).all()
+            assert (o["mpc_fail"][tracked] == 1).all()                 # frozen at the first failed solve
+            assert (o["status"][tracked] != 0).all()                   # ... and its solver status is kept
+        else:
+            assert (o["ret"][tracked] != -2).mean() > 0.5              # the reference's semantics: stepped anyway
+            assert o["mpc_fail"].max() > 1
+
+
 @pytest.mark.parametrize("model,controller,dynamic,M", [
     ("DynamicUnicycle2D", "cbf_qp", False, 8),
     ("DynamicUnicycle2D", "cbf_qp", False, 40),           # RPL = 2 geometry of the fused kernel
@@ -225,12 +251,12 @@ def test_fused_run_equals_per_step_path(model, controller, dynamic, M):
     torch.cuda.synchronize()
     run = a.buffers()["done"].cpu().numpy() == 0
     worst = {}
-    for k in ("sm", "wp_idx", "has_goal", "ret", "done", "nsteps", "status"):
+    for k in ("sm", "wp_idx", "has_goal", "ret", "done", "nsteps", "status", "active"):
         assert np.array_equal(a.buffers()[k].cpu().numpy(), b.buffers()[k].cpu().numpy()), k
     for k in ("X", "yaw", "goal", "SCENE", "U", "Uref"):
+        # (frozen agents included: both paths skip the solve of an agent whose run has ended, so U / status / active stay
+        #  those of its terminating step)
         x, y = a.buffers()[k].cpu().numpy(), b.buffers()[k].cpu().numpy()
-        if k in ("U", "Uref"):                            # the per-step path keeps re-solving frozen agents on stale inputs
-            x, y = x[run], y[run]
         worst[k] = float(np.nanmax(np.abs(x - y))) if x.size else 0.0
         # same source, but nvcc may contract a*b+c differently once the bodies are inlined into one kernel: allow ulps
         np.testing.assert_allclose(x, y, rtol=0, atol=1e-11, err_msg=k)

@@ -67,3 +67,77 @@ def test_scatter_solve_gather_two_ranks(n_agents):
         assert p.exitcode == 0
     same_u, same_s, shape = q.get(timeout=10)
     assert same_u and same_s and shape == (n_agents, 2)
+
+
+def _plan_worker(rank, world, port, n_agents, q):
+    """ShardPlan reused over several steps (buffers allocated once), even and ragged blocks, and the config-5 wrapper
+    (ShardedMixedMPCCBF) with a stand-in for the per-rank CUDA solve."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from safe_control_b200.sharding import ShardPlan
+        F64, I32 = torch.float64, torch.int32
+        plan = ShardPlan(n_agents, {"X": ((4,), F64), "nobs": ((), I32)}, {"U": ((2,), F64), "status": ((), I32)}, "cpu")
+        ok = True
+        ptrs = None
+        for step in range(3):
+            g = torch.Generator().manual_seed(step)
+            X = torch.rand((n_agents, 4), generator=g, dtype=F64)
+            nobs = (torch.arange(n_agents, dtype=I32) + step) % 5
+            blk = plan.scatter({"X": X, "nobs": nobs} if rank == 0 else None)
+            assert blk["X"].shape[0] == plan.n_local
+            out = {"U": torch.stack([blk["X"][:, 0] * 2, blk["X"][:, 1] + blk["nobs"].double()], 1), "status": (blk["nobs"] > 2).to(I32)}
+            full = plan.gather(out)
+            if rank == 0:
+                ref_u = torch.stack([X[:, 0] * 2, X[:, 1] + nobs.double()], 1)
+                ok = ok and torch.equal(full["U"], ref_u) and torch.equal(full["status"], (nobs > 2).to(I32))
+                p = (full["U"].data_ptr(), full["status"].data_ptr())
+                ok = ok and (ptrs is None or ptrs == p)           # same pre-sized output buffers every step
+                ptrs = p
+        # config-5 wrapper: three model groups with their own row shapes, stand-in solve
+        from safe_control_b200.mixed import ShardedMixedMPCCBF
+        specs = [{"model": "DynamicUnicycle2D"}, {"model": "KinematicBicycle2D"}, {"model": "Quad3D"}]
+        counts = [n_agents, n_agents + 1, max(n_agents - 1, 1)]
+        sh = ShardedMixedMPCCBF(specs, counts, num_obs=3, horizon=2, device="cpu", want_active=True)
+
+        def fake(blocks, want_active=False):
+            outs = []
+            for grp, b in zip(sh.mixed.groups, blocks):
+                n = b["X"].shape[0]
+                outs.append({"U": b["X"][:, : grp.nu] + b["goal"][:, :1], "status": b["nobs"].clone(), "iters": b["nobs"] * 2,
+                             "active": torch.full((n, grp.active_words), 7, dtype=torch.int64)})
+            return outs
+        sh.mixed.solve = fake
+        ins = None
+        if rank == 0:
+            ins = []
+            for grp, c in zip(sh.mixed.groups, counts):
+                g = torch.Generator().manual_seed(c)
+                ins.append({"X": torch.rand((c, grp.nx), generator=g, dtype=F64), "goal": torch.rand((c, grp.ngoal), generator=g, dtype=F64),
+                            "u_prev": torch.zeros((c, grp.nu), dtype=F64), "OBS": torch.rand((c, 3, 7), generator=g, dtype=F64),
+                            "nobs": (torch.arange(c, dtype=I32) % 4)})
+        res = sh.solve(ins)
+        if rank == 0:
+            for grp, r, a in zip(sh.mixed.groups, res, ins):
+                ok = ok and torch.equal(r["U"], a["X"][:, : grp.nu] + a["goal"][:, :1]) and torch.equal(r["status"], a["nobs"])
+                ok = ok and torch.equal(r["iters"], a["nobs"] * 2) and tuple(r["active"].shape) == (a["X"].shape[0], grp.active_words)
+                ok = ok and bool((r["active"] == 7).all())
+            q.put(ok)
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_agents", [6, 7])
+def test_shard_plan_reuse_and_config5_wrapper(n_agents):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_plan_worker, args=(r, 2, port, n_agents, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10)
