@@ -57,6 +57,13 @@ static int sm_count_of_current() {
 }
 
 // ------------------------------------------------------------------------------ dispatch
+// can the obstacle blocks be fetched with 1-D bulk copies?  (16-byte aligned source addresses and sizes)
+static bool tma_ok(const double* OBS, long stride, int M) {
+  const char* e = getenv("SCB_QP_TMA");
+  if (e && e[0] == '0') return false;
+  return OBS && stride > 0 && (stride & 1) == 0 && M > 0 && (M & 1) == 0 && (((uintptr_t)OBS) & 15) == 0;
+}
+
 template <int MODEL>
 static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
                           const double* OBS, long stride, const int32_t* nobs, double* U, int32_t* status,
@@ -69,6 +76,22 @@ static int launch_cbfqp_m(const scb_params& p, const LaunchGeom& g, int N, int M
   if (eager && g.lanes == 32 && g.rpl == 2) {
     cbfqp_kernel<MODEL, 32, 2, true><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, skip);
     return SCB_OK;
+  }
+  // bulk-async staged variant for the lane-group geometries (large batches): per-agent lists, 16-byte aligned blocks.
+  // SCB_QP_TMA=0 forces the LDG kernel (A/B switch, read per call).
+  if (g.lanes < 32 && tma_ok(OBS, stride, M)) {
+    const int slot = tma_slot_doubles(M, g.lanes);
+    const size_t smem = (size_t)(kBlock / 32) * (32 / g.lanes) * slot * sizeof(double);
+#define GOT(L, R)                                                                                                   \
+    if (g.lanes == L && g.rpl == R) {                                                                               \
+      auto kern = cbfqp_tma_kernel<MODEL, L, R>;                                                                    \
+      if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+        return SCB_ERR_TOO_LARGE;                                                                                   \
+      kern<<<g.grid, kBlock, smem, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, status, active, words, skip, slot); \
+      return SCB_OK;                                                                                                \
+    }
+    GOT(8, 3) GOT(8, 4) GOT(8, 8) GOT(4, 5) GOT(4, 8)
+#undef GOT
   }
 #define GO(L, R)                                                                                           \
   if (g.lanes == L && g.rpl == R) {                                                                        \
@@ -84,6 +107,20 @@ template <int MODEL, int NW>
 static int launch_od_m(const scb_params& p, const LaunchGeom& g, int N, int M, const double* X, const double* Uref,
                        const double* OBS, long stride, const int32_t* nobs, double* U, double* omega, int32_t* sel,
                        int32_t* status, uint64_t* active, cudaStream_t s, const int32_t* skip) {
+  if (g.lanes < 32 && tma_ok(OBS, stride, M)) {      // bulk-async staged variant (see odcbf_tma_kernel)
+    const int slot = tma_slot_doubles(M, g.lanes);
+    const size_t smem = (size_t)(kBlock / 32) * (32 / g.lanes) * slot * sizeof(double);
+#define GOT(L, R)                                                                                                   \
+    if (g.lanes == L && g.rpl == R) {                                                                               \
+      auto kern = odcbf_tma_kernel<MODEL, NW, L, R>;                                                                \
+      if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+        return SCB_ERR_TOO_LARGE;                                                                                   \
+      kern<<<g.grid, kBlock, smem, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, skip, slot); \
+      return SCB_OK;                                                                                                \
+    }
+    GOT(8, 3) GOT(8, 4) GOT(8, 8) GOT(4, 5) GOT(4, 8)
+#undef GOT
+  }
 #define GO(L, R)                                                                                              \
   if (g.lanes == L && g.rpl == R) {                                                                           \
     odcbf_kernel<MODEL, NW, L, R><<<g.grid, kBlock, 0, s>>>(p, N, M, X, Uref, OBS, stride, nobs, U, omega, sel, status, active, skip); \

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "scb_qp.cuh"
+#include "scb_tma.cuh"
 
 namespace scb {
 
@@ -35,6 +36,89 @@ cbfqp_kernel(const __grid_constant__ scb_params p, int N, int M, const double* _
     if (skip && skip[a]) continue;     // closed loop: agents whose run has ended keep the outputs of their last step
     cbfqp_agent<MODEL, LANES, RPL, true, EAGER>(p, M, nobs ? nobs[a] : M, X + a * NX, Uref + a * NU, OBS + a * stride,
                                    U + a * NU, status + a, active ? active + a * words : nullptr, words);
+  }
+}
+
+// ---- bulk-async staged variant (lane-group geometries, per-agent obstacle lists) ------------------------------------
+// A warp owns G = 32 / LANES consecutive agents per pass.  Lane 0 asks the TMA engine for the G obstacle blocks
+// (one cp.async.bulk of 56 M bytes per agent into the warp's private shared-memory slots, completion on the warp's
+// mbarrier); while the copy is in flight the lanes fetch X / Uref / nobs (small, coalesced); then every lane reads its
+// rows from shared memory and assembles them into registers.  As soon as the rows are in registers the slots are free:
+// the copy of the warp's NEXT pass is issued before the QP solve, so the DRAM round trip overlaps the active-set
+// iterations instead of preceding them.  Slot stride = 56 M bytes + padding such that the 16 lanes of a half-warp
+// (16 / LANES agents x LANES rows, one 8-byte field each) hit 16 distinct bank pairs: stride = 8 LANES bytes mod 128.
+// Preconditions (checked by the launcher, otherwise the LDG kernel runs): OBS 16-byte aligned, stride even, M even.
+inline int tma_slot_doubles(int M, int lanes) {
+  int bytes = 56 * M;
+  const int want = (8 * lanes) & 127;                  // 32 (4 lanes), 64 (8 lanes), 0 (16 lanes)
+  while ((bytes & 127) != want) bytes += 16;
+  return bytes / 8;
+}
+
+template <int MODEL, int LANES, int RPL>
+__global__ void __launch_bounds__(kBlock, SCB_QP_MINB(LANES))
+cbfqp_tma_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
+                 const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
+                 const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,
+                 uint64_t* __restrict__ active, int words, const int32_t* __restrict__ skip, int slot_doubles) {
+  constexpr int NX = ModelCT<MODEL>::NX, NU = ModelCT<MODEL>::NU;
+  constexpr int G = 32 / LANES, WPB = kBlock / 32;
+  extern __shared__ __align__(128) double tma_stage[];
+  __shared__ uint64_t bars[WPB];
+  const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31, grp = lane32 / LANES;
+  double* slots = tma_stage + (size_t)warp * G * slot_doubles;
+  uint64_t* bar = &bars[warp];
+  if (lane32 == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+  __syncwarp();
+  const uint32_t bytes = (uint32_t)(56 * M);
+  const long npass = ((long)N + G - 1) / G, nwarps = (long)gridDim.x * WPB;
+  auto issue = [&](long ps) {
+    if (lane32 == 0 && ps < npass) {
+      const long a0 = ps * G;
+      const int cnt = (int)((N - a0) < G ? (N - a0) : G);
+      mbar_arrive_expect_tx(bar, bytes * cnt);
+      for (int g = 0; g < cnt; ++g) bulk_copy_g2s(slots + (size_t)g * slot_doubles, OBS + (a0 + g) * stride, bytes, bar);
+    }
+  };
+  long pass = (long)blockIdx.x * WPB + warp;
+  issue(pass);
+  uint32_t parity = 0;
+  for (; pass < npass; pass += nwarps) {
+    const long a = pass * G + grp;
+    const bool live = a < N && !(skip && skip[a]);
+    // small per-agent inputs while the bulk copy is in flight
+    int no = 0;
+    double xs[NX], ur[NU];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) ur[i] = 0.0;
+    if (live) {
+      no = nobs ? __ldg(nobs + a) : M;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xs[i] = __ldg(X + a * NX + i);
+#pragma unroll
+      for (int i = 0; i < NU; ++i) ur[i] = __ldg(Uref + a * NU + i);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    double r0[RPL], r1[RPL], rb[RPL];
+    cbfqp_rows_staged<MODEL, LANES, RPL>(p, M, live ? no : 0, xs, slots + (size_t)grp * slot_doubles, r0, r1, rb);
+    __syncwarp();                  // every lane has its rows in registers: the slots are free
+    fence_proxy_async();
+    issue(pass + nwarps);          // next pass streams in during the solve below
+    if (!live) continue;
+    if (no < 0) {                  // obs_list is None -> u_ref unclipped (cbf_qp.py:113-118)
+      if ((lane32 & (LANES - 1)) == 0) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) U[a * NU + i] = ur[i];
+        status[a] = SCB_OPTIMAL;
+        if (active) for (int w = 0; w < words; ++w) active[a * words + w] = 0ull;
+      }
+      continue;
+    }
+    cbfqp_finish<MODEL, LANES, RPL>(p, M + 2 * NU, ur, r0, r1, rb, U + a * NU, status + a,
+                                    active ? active + a * words : nullptr, words);
   }
 }
 
@@ -110,6 +194,58 @@ odcbf_kernel(const __grid_constant__ scb_params p, int N, int M, const double* _
     odcbf_agent<MODEL, NW, LANES, RPL>(p, M, nobs ? nobs[a] : M, X + a * ModelCT<MODEL>::NX, Uref + a * 2, OBS + a * stride,
                                        U + a * 2, omega ? omega + a * 2 : nullptr, sel ? sel + a : nullptr,
                                        status + a, active ? active + a : nullptr);
+  }
+}
+
+// bulk-async staged variant of the optimal-decay kernel: the nearest-obstacle scan AND the row of the chosen obstacle
+// read shared memory, so the second, dependent DRAM round trip of the LDG kernel (scan x, y -> pick -> load the row)
+// disappears; at BASELINE config 4 (8192 agents x 32 obstacles = 15 MB) every warp's copy is in flight at once.
+template <int MODEL, int NW, int LANES, int RPL>
+__global__ void __launch_bounds__(kBlock, 4)       // <= 128 registers: config 4's 512 CTAs are resident in one wave (4 per SM)
+odcbf_tma_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
+                 const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
+                 const int32_t* __restrict__ nobs, double* __restrict__ U, double* __restrict__ omega,
+                 int32_t* __restrict__ sel, int32_t* __restrict__ status, uint64_t* __restrict__ active,
+                 const int32_t* __restrict__ skip, int slot_doubles) {
+  constexpr int NX = ModelCT<MODEL>::NX;
+  constexpr int G = 32 / LANES, WPB = kBlock / 32;
+  extern __shared__ __align__(128) double tma_stage[];
+  __shared__ uint64_t bars[WPB];
+  const int warp = threadIdx.x >> 5, lane32 = threadIdx.x & 31, grp = lane32 / LANES;
+  double* slots = tma_stage + (size_t)warp * G * slot_doubles;
+  uint64_t* bar = &bars[warp];
+  if (lane32 == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+  __syncwarp();
+  const uint32_t bytes = (uint32_t)(56 * M);
+  const long npass = ((long)N + G - 1) / G, nwarps = (long)gridDim.x * WPB;
+  uint32_t parity = 0;
+  for (long pass = (long)blockIdx.x * WPB + warp; pass < npass; pass += nwarps) {
+    if (lane32 == 0) {
+      const long a0 = pass * G;
+      const int cnt = (int)((N - a0) < G ? (N - a0) : G);
+      mbar_arrive_expect_tx(bar, bytes * cnt);
+      for (int g = 0; g < cnt; ++g) bulk_copy_g2s(slots + (size_t)g * slot_doubles, OBS + (a0 + g) * stride, bytes, bar);
+    }
+    const long a = pass * G + grp;
+    const bool live = a < N && !(skip && skip[a]);
+    int no = 0;
+    double xs[NX], ur[2] = {0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xs[i] = 0.0;
+    if (live) {
+      no = nobs ? __ldg(nobs + a) : M;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xs[i] = __ldg(X + a * NX + i);
+      ur[0] = __ldg(Uref + a * 2); ur[1] = __ldg(Uref + a * 2 + 1);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    if (live)
+      odcbf_agent<MODEL, NW, LANES, RPL, false>(p, M, no, xs, ur, slots + (size_t)grp * slot_doubles, U + a * 2,
+                                                omega ? omega + a * 2 : nullptr, sel ? sel + a : nullptr, status + a,
+                                                active ? active + a : nullptr);
+    __syncwarp();                  // all lanes are done with the slots before the next pass overwrites them
+    fence_proxy_async();
   }
 }
 

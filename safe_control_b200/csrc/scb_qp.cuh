@@ -46,6 +46,10 @@ SCB_HD void cbfqp_row(const scb_params& p, const AgentCT& g, const double* obs, 
   }
 }
 
+template <int MODEL, int LANES, int RPL>
+SCB_HD void cbfqp_finish(const scb_params& p, int mrows, const double* ur, const double (&r0)[RPL], const double (&r1)[RPL],
+                         const double (&rb)[RPL], double* U, int32_t* status, uint64_t* active, int words);
+
 template <int MODEL, int LANES, int RPL, bool NC = true, bool EAGER = false>
 SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, const double* uref,
                         const double* obs, double* U, int32_t* status, uint64_t* active, int words) {
@@ -104,7 +108,15 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
     const double inv = (n2 > 0.0) ? rsqrt_pos(n2) : 1.0;
     r0[j] = a[0] * inv; r1[j] = a[1] * inv; rb[j] = b * inv;
   }
+  cbfqp_finish<MODEL, LANES, RPL>(p, mrows, ur, r0, r1, rb, U, status, active, words);
+}
 
+// second half of cbfqp_agent: exact 2-variable QP over the normalised rows held in registers + outputs
+template <int MODEL, int LANES, int RPL>
+SCB_HD void cbfqp_finish(const scb_params& p, int mrows, const double* ur, const double (&r0)[RPL], const double (&r1)[RPL],
+                         const double (&rb)[RPL], double* U, int32_t* status, uint64_t* active, int words) {
+  using G = Grp<LANES>;
+  const int lane = G::lane();
   Qp2Out q;
   gi_solve2<LANES, RPL>(2.0, ur[0], ur[1], r0, r1, rb, mrows, 8 * mrows + 16, q);
 
@@ -124,6 +136,29 @@ SCB_HD void cbfqp_agent(const scb_params& p, int M, int nobs, const double* x, c
         active[w] = bits;
       }
     }
+  }
+}
+
+// The same rows as cbfqp_agent's first half, from an obstacle block that is already ON CHIP (shared memory filled by
+// a bulk-async copy, scb_kernels.cuh cbfqp_tma_kernel): plain loads, every lane of the warp takes the same path
+// (dead agents / nobs < 0 produce vacuous rows without touching `obs`), so the caller may warp-synchronise after it.
+template <int MODEL, int LANES, int RPL>
+SCB_HD void cbfqp_rows_staged(const scb_params& p, int M, int nobs, const double* xs, const double* obs, double (&r0)[RPL],
+                              double (&r1)[RPL], double (&rb)[RPL]) {
+  using Mod = ModelCT<MODEL>;
+  constexpr int NU = Mod::NU;
+  static_assert(NU == 2, "the fused CBF-QP kernel covers the 2-input models");
+  const int lane = Grp<LANES>::lane();
+  AgentCT g;
+  Mod::prep(p, xs, g);
+  if (nobs > M) nobs = M;
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    double a[NU], b;
+    cbfqp_row<MODEL, false>(p, g, obs, M, nobs, j * LANES + lane, a, b, nullptr);
+    const double n2 = a[0] * a[0] + a[1] * a[1];
+    const double inv = (n2 > 0.0) ? rsqrt_pos(n2) : 1.0;
+    r0[j] = a[0] * inv; r1[j] = a[1] * inv; rb[j] = b * inv;
   }
 }
 
