@@ -102,6 +102,17 @@ def fp64_peak():
     return _FP64_PEAK[dev], "measured (scb_measure_fp64_peak: DFMA microbenchmark in libscb.so, this run)"
 
 
+def latency_floor():
+    """us per launch of an empty / one-round-trip / two-round-trip kernel of cfg2's geometry inside a CUDA graph"""
+    import ctypes as C
+    from safe_control_b200._lib import lib, check
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    check(lib().scb_measure_latency_floor(C.byref(a), C.byref(b), C.byref(c), None), "scb_measure_latency_floor")
+    return {"empty_kernel_us": a.value, "one_dependent_dram_trip_us": b.value, "two_dependent_dram_trips_us": c.value,
+            "how": "scb_measure_latency_floor: 200 launches of 256 CTAs x 128 threads in one CUDA graph, best of 5 replays; "
+                   "the chase kernels read a 512 MB table (4x L2) at per-launch offsets"}
+
+
 def fp64_roofline(flops_per_step, k_ms, extra=None):
     """roofline object of an MPC workload: bound by FP64 issue / latency, not by HBM"""
     peak, src = fp64_peak()
@@ -624,7 +635,7 @@ def run_single(args, w, cx, steps, warmup, sub=False):
                 "traffic": ncu_traffic(w["name"]), "peak_source": peak_src, "kernel_ms": k_ms,
                 "kernel_ms_how": "CUDA-graph replay of the timed steps / steps (median of 5 regions of >= 20 ms each), includes the inter-kernel dependency gap",
                 "algorithmic_bytes_per_agent": B, "agents_per_launch": N,
-                "latency_floor": _profile_json(["r2_latency_floor.json"]).get(w["name"]),
+                "latency_floor": latency_floor() if (w["name"] == "cfg2" and not sub) else None,
                 "note": f"one launch covers only {N} agents ({B * N / 1e6:.1f} MB): latency-bound; large_batch shows the same kernel on 1M agents",
                 "large_batch": big}
     out = {

@@ -70,7 +70,9 @@ enum scb_model {
   SCB_UNICYCLE_2D = 8,              /* robots/unicycle2D.py (cbf_qp, mpc_cbf) */
   SCB_MANIPULATOR_2D = 9,           /* robots/manipulator2D.py (cbf_qp: 3 inputs, 25 link-circle rows per obstacle;
                                        M = CBFQP's num_obs = the ROW budget, cbf_qp.py:131-149) */
-  SCB_NUM_MODELS = 10
+  SCB_VTOL_2D = 10,                 /* robots/vtol2D.py (mpc_cbf only: agent_barrier is not implemented, vtol2D.py:458-460;
+                                       6 states, 4 inputs, horizon 30, mpc_cbf.py:40-43, 83-87, 222-232) */
+  SCB_NUM_MODELS = 11
 };
 
 enum scb_status { SCB_OPTIMAL = 0, SCB_INFEASIBLE = 1, SCB_MAXITER = 2, SCB_NUMERICAL = 3 };
@@ -107,6 +109,11 @@ typedef struct scb_params {
                                  superellipsoid rows (flag 1; *_2D.py agent_barrier_dt if_else): the agents that have one
                                  are solved by a second launch with general rows.  0: such agents get SCB_NUMERICAL */
   double mpc_tol;         /* KKT tolerance (ours; IPOPT default 1e-8) */
+  /* VTOL2D (robots/vtol2D.py:57-110; mass, Iy = inertia, gravity 9.81, v_max above): wing / aero coefficients, lift
+   * blending (M, alpha_0), rotor gains and lever arms, safety limits of the MPC state bounds (mpc_cbf.py:227-232:
+   * |x_dot| <= v_max, z_dot >= -descent_speed_max, |theta| <= pitch_max * 3.14159 / 180, pitch_max in degrees) */
+  double S_wing, rho, C_L0, C_Lalpha, blend_M, alpha_0, C_Ldelta_e, C_D0, C_Dalpha, C_Ddelta_e, C_m0, C_malpha, C_mdelta_e,
+         chord, k_front, k_rear, k_pusher, ell_f, ell_r, pitch_max, descent_speed_max;
 } scb_params;
 
 typedef struct scb_ctx scb_ctx;   /* opaque: device staging buffers + stream for the *_host calls */
@@ -129,6 +136,10 @@ int         scb_limits(int* max_obs_qp, int* max_obs_mpc, int* max_horizon);
 /* measurement helper (bench.py): achieved FP64 FMA throughput of the current device in TFLOP/s (2 flops per DFMA), a
  * chain-parallel kernel timed with CUDA events on `stream`.  The measured denominator of the MPC kernels' roofline. */
 int         scb_measure_fp64_peak(double* tflops, void* stream);
+
+/* measurement helper (bench.py: roofline.latency_floor): microseconds per launch, inside a CUDA graph, of a kernel with
+ * config 2's geometry (256 CTAs x 128 threads) that does nothing / one / two dependent cold-DRAM round trips per warp. */
+int         scb_measure_latency_floor(double* empty_us, double* one_trip_us, double* two_trip_us, void* stream);
 
 /* ---- context for the host-pointer calls ------------------------------------------------- */
 int  scb_ctx_create(scb_ctx** out, int device);
@@ -173,8 +184,10 @@ int scb_odcbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M,
  * active [N, scb_mpc_active_words(p, M, H)] u64 (out, may be NULL): active set of the NLP at the returned point, one bit
  * per inequality row: bit k*M + j = CBF row of (stage k, obstacle slot j)  (mpc_cbf.py:301-325);  bit H*M + q = simple
  * bound q:  q < 2 H nu: stage k = q / (2 nu), input i = (q % (2 nu)) / 2, even = u_i at its upper bound, odd = lower
- * (mpc_cbf.py:183-221);  then, for the models with a velocity state bound, 2 H bits: t = q - 2 H nu, node k = 1 + t / 2,
- * even = v <= v_max active, odd = v >= -v_max active.  A row is active <=> its multiplier exceeds its value at exit. */
+ * (mpc_cbf.py:183-232);  then, for the models with state bounds, nsb H bits: t = q - 2 H nu, node k = 1 + t / nsb, r = t % nsb:
+ * DynamicUnicycle2D / KinematicBicycle2D* (nsb = 2): r = 0: v <= v_max, 1: v >= -v_max;  VTOL2D (nsb = 5): r = 0: x_dot <= v_max,
+ * 1: x_dot >= -v_max, 2: z_dot >= -descent_speed_max, 3: theta <= pitch limit, 4: theta >= -pitch limit.
+ * A row is active <=> its multiplier exceeds its value at exit. */
 int scb_mpc_active_words(const scb_params* p, int M, int H);
 int scb_mpccbf_solve(const scb_params* p, int N, int M, int H,
                      const double* X, const double* Uref, const double* goal, const double* u_prev,

@@ -63,6 +63,14 @@ def resolve_spec(robot_spec):
         s.setdefault("mass", 3.0); s.setdefault("Ix", 0.5); s.setdefault("Iy", 0.5)
         s.setdefault("Iz", 0.5); s.setdefault("L", 0.3); s.setdefault("nu", 0.1)
         s.setdefault("u_max", 10.0); s.setdefault("u_min", -10.0)
+    elif model == "VTOL2D":                                   # vtol2D.py:57-110
+        for k, v in (("mass", 11.0), ("inertia", 1.135), ("S_wing", 0.55), ("rho", 1.2682), ("C_L0", 0.23), ("C_Lalpha", 5.61),
+                     ("M", 50.0), ("alpha_0", np.deg2rad(15)), ("C_Ldelta_e", 0.13), ("C_D0", 0.043), ("C_Dalpha", 0.03),
+                     ("C_Ddelta_e", 0.0), ("C_m0", 0.0135), ("C_malpha", -2.74), ("C_mdelta_e", -0.99), ("chord", 0.18994),
+                     ("k_front", 70.0), ("k_rear", 70.0), ("k_pusher", 60.0), ("ell_f", 0.5), ("ell_r", 0.5),
+                     ("throttle_min", 0.0), ("throttle_max", 1.0), ("elevator_min", -0.5), ("elevator_max", 0.5),
+                     ("v_max", 15.0), ("pitch_max", 15.0), ("descent_speed_max", 5.0)):
+            s.setdefault(k, v)
     else:
         raise ValueError(f"oracle does not restate model {model!r}")
     return s

@@ -48,6 +48,7 @@ MPC_PARAM = {   # mpc_cbf.py:19-39 (Q diag, R), 49-82 (alpha)
     "Quad3D": dict(Q=[30, 30, 5, 20, 20, 1, 10, 10, 10, 20, 20, 1], R=[1, 1, 1, 1], alpha=0.15),
     "DoubleIntegrator2D": dict(Q=[50, 50, 20, 20], R=[0.5, 0.5], alpha1=0.2, alpha2=0.2),
     "Quad2D": dict(Q=[25, 25, 50, 10, 10, 50], R=[0.5, 0.5], alpha1=0.15, alpha2=0.15),
+    "VTOL2D": dict(Q=[10, 10, 250, 10, 10, 50], R=[0.5, 0.5, 0.5, 50000.0], alpha1=0.05, alpha2=0.05),   # mpc_cbf.py:40-43, 83-87
 }
 DUMMY = [1000.0, 1000.0, 0.0, 0.0, 0.0, 0.0, 0.0]
 
@@ -59,7 +60,8 @@ class TorchModel:
         self.s, self.dt, self.name = spec, dt, spec["model"]
         self.R = float(spec["radius"])
         n = self.name
-        self.nx, self.nu = {"SingleIntegrator2D": (2, 2), "Quad3D": (12, 4), "Quad2D": (6, 2), "Unicycle2D": (3, 2)}.get(n, (4, 2))
+        self.nx, self.nu = {"SingleIntegrator2D": (2, 2), "Quad3D": (12, 4), "Quad2D": (6, 2), "Unicycle2D": (3, 2),
+                            "VTOL2D": (6, 4)}.get(n, (4, 2))
         if n == "Quad3D":
             L, nu, gr = spec["L"], spec["nu"], 9.8
             B2 = torch.tensor([[1, 1, 1, 1], [0, L, 0, -L], [L, 0, -L, 0], [nu, -nu, nu, -nu]], dtype=torch.float64)
@@ -82,6 +84,33 @@ class TorchModel:
             return torch.stack([u[:, 0] * torch.cos(x[:, 2]), u[:, 0] * torch.sin(x[:, 2]), u[:, 1]], dim=1)
         if n == "DoubleIntegrator2D":                           # double_integrator2D.py:46-78
             return torch.stack([x[:, 2], x[:, 3], u[:, 0], u[:, 1]], dim=1)
+        if n == "VTOL2D":                                       # vtol2D.py:115-300 (f: baseline aero + gravity; g: rotors, aero at delta_e = 1)
+            sp = self.s
+            th, xd, zd, thd = x[:, 2], x[:, 3], x[:, 4], x[:, 5]
+            c, sn = torch.cos(th), torch.sin(th)
+            ub, wb = c * xd + sn * zd, -sn * xd + c * zd
+            V = torch.sqrt(ub * ub + wb * wb)
+            al = torch.atan2(-wb, ub)
+            CLlin = sp["C_L0"] + sp["C_Lalpha"] * al
+            CLnl = 2 * torch.sin(al) * torch.cos(al)
+            t1 = torch.exp(-sp["M"] * (al - sp["alpha_0"])); t2 = torch.exp(sp["M"] * (al + sp["alpha_0"]))
+            sig = (1 + t1 + t2) / ((1 + t1) * (1 + t2))
+            CLa = (1 - sig) * CLlin + sig * CLnl
+            qS = 0.5 * sp["rho"] * V ** 2 * sp["S_wing"]
+
+            def ldm(de):
+                return (qS * (CLa + sp["C_Ldelta_e"] * de), qS * (sp["C_D0"] + sp["C_Dalpha"] * al ** 2 + sp["C_Ddelta_e"] * de),
+                        qS * (sp["C_m0"] + sp["C_malpha"] * al + sp["C_mdelta_e"] * de) * sp["chord"])
+            ch, sh = torch.cos(th + al), torch.sin(th + al)
+            L0, D0, M0 = ldm(0.0); L1, D1, M1 = ldm(1.0)
+            w2i = lambda D, L: (ch * (-D) - sh * L, sh * (-D) + ch * L)
+            fx0, fz0 = w2i(D0, L0); fx1, fz1 = w2i(D1, L1)
+            m, I = sp["mass"], sp["inertia"]
+            kf, kr, kp = sp["k_front"], sp["k_rear"], sp["k_pusher"]
+            xdd = fx0 / m + (-sn * kf / m) * u[:, 0] + (-sn * kr / m) * u[:, 1] + (c * kp / m) * u[:, 2] + (fx1 / m) * u[:, 3]
+            zdd = (fz0 - m * 9.81) / m + (c * kf / m) * u[:, 0] + (c * kr / m) * u[:, 1] + (sn * kp / m) * u[:, 2] + (fz1 / m) * u[:, 3]
+            tdd = M0 / I + (sp["ell_f"] * kf / I) * u[:, 0] + (-sp["ell_r"] * kr / I) * u[:, 1] + (M1 / I) * u[:, 3]
+            return torch.stack([xd, zd, thd, xdd, zdd, tdd], dim=1)
         if n == "Quad2D":                                       # quad2D.py:46-85
             m, I, r = self.s["mass"], self.s["inertia"], self.R
             th, us = x[:, 2], u[:, 0] + u[:, 1]
@@ -159,6 +188,8 @@ class OracleMPCCBF:
         self.name = self.spec["model"]
         self.dt, self.M = dt, num_obs
         self.H = int(horizon if horizon is not None else self.spec.get("mpc_horizon", 10))
+        if self.name == "VTOL2D" and horizon is None:            # mpc_cbf.py:40-41 overrides the horizon for this model
+            self.H = 30
         par = dict(MPC_PARAM[self.name])
         for k in ("alpha", "alpha1", "alpha2"):                  # mpc_cbf.py:90-95
             if "mpc_cbf_" + k in self.spec:
@@ -181,10 +212,21 @@ class OracleMPCCBF:
             lb, ub = [-s["ax_max"], -s["ay_max"]], [s["ax_max"], s["ay_max"]]
         elif self.name == "Quad2D":                              # mpc_cbf.py:212-216
             lb, ub = [s["f_min"]] * 2, [s["f_max"]] * 2
+        elif self.name == "VTOL2D":                              # mpc_cbf.py:222-226
+            lb, ub = [s["throttle_min"]] * 3 + [s["elevator_min"]], [s["throttle_max"]] * 3 + [s["elevator_max"]]
         else:
             lb, ub = [s["u_min"]] * 4, [s["u_max"]] * 4
         self.u_lb, self.u_ub = np.array(lb, float), np.array(ub, float)
         self.has_vbound = self.name == "DynamicUnicycle2D" or self.name.startswith("KinematicBicycle2D")
+        # state bounds at the nodes 1..H, in the order of the CUDA kernel's active mask (include/scb.h): (state index, sign, offset)
+        # meaning sign * x[i] + offset >= 0
+        self.state_bounds = []
+        if self.has_vbound:                                      # mpc_cbf.py:193-199, 205-211
+            self.state_bounds = [(3, -1.0, s["v_max"]), (3, 1.0, s["v_max"])]
+        if self.name == "VTOL2D":                                # mpc_cbf.py:227-232
+            pitch = s["pitch_max"] * 3.14159 / 180
+            self.state_bounds = [(3, -1.0, s["v_max"]), (3, 1.0, s["v_max"]), (4, 1.0, s["descent_speed_max"]),
+                                 (2, -1.0, pitch), (2, 1.0, pitch)]
         self.status = "optimal"
 
     # ---- packing: w = [x_0..x_H | u_0..u_{H-1}] ----
@@ -249,8 +291,11 @@ class OracleMPCCBF:
         lo = np.full(w0.size, -np.inf); hi = np.full(w0.size, np.inf)
         xl, ul = self.split(lo); xh, uh = self.split(hi)
         ul[:] = self.u_lb; uh[:] = self.u_ub
-        if self.has_vbound:
-            xl[:, 3] = -self.spec["v_max"]; xh[:, 3] = self.spec["v_max"]
+        for i, sgn, off in self.state_bounds:
+            if sgn < 0:
+                xh[:, i] = off
+            else:
+                xl[:, i] = -off
         if method == "SLSQP":
             cons = [dict(type="eq", fun=lambda v: eqf(torch.tensor(v)).numpy(), jac=jac(eqf)),
                     dict(type="ineq", fun=lambda v: cbff(torch.tensor(v)).numpy(), jac=jac(cbff))]
@@ -287,8 +332,7 @@ class OracleMPCCBF:
         J = self.cost(w, g, torch.as_tensor(np.asarray(u_prev, float).reshape(-1)))
         parts = [self.cbf(w, self.pad_obs(obs)),
                  (torch.as_tensor(self.u_ub)[None] - u).reshape(-1), (u - torch.as_tensor(self.u_lb)[None]).reshape(-1)]
-        if self.has_vbound:
-            parts += [self.spec["v_max"] - x[1:, 3], x[1:, 3] + self.spec["v_max"]]
+        parts += [sgn * x[1:, i] + off for i, sgn, off in self.state_bounds]
         return J, torch.cat(parts)
 
     def active_set(self, x_init, goal, u_prev, obs, z, g_tol=1e-6, lam_tol=1e-6):
@@ -323,11 +367,9 @@ class OracleMPCCBF:
         if r < H * nu:                                           # u - u_lb >= 0 -> lower bound bit
             k, i = divmod(r, nu)
             return H * M + k * 2 * nu + 2 * i + 1
-        r -= H * nu
-        if r < H:                                                # v_max - x_{k+1}[3] >= 0 -> node k+1, upper
-            return H * M + 2 * H * nu + 2 * r
-        r -= H                                                   # x_{k+1}[3] + v_max >= 0 -> lower
-        return H * M + 2 * H * nu + 2 * r + 1
+        r -= H * nu                                              # state bounds: condensed() groups them by kind, the kernel by node
+        kind, k = divmod(r, H)
+        return H * M + 2 * H * nu + k * len(self.state_bounds) + kind
 
     def kkt_error(self, x_init, goal, u_prev, obs, z, res_tol=1e-4):
         """KKT check of a point -> (stationarity residual, min g, complementarity max_i lam_i g_i).

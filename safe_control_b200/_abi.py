@@ -12,9 +12,10 @@ MODEL_IDS = {
     "Unicycle2D": 8,
     "Manipulator2D": 9,
     "KinematicBicycle2D_DPCBF": 7,
+    "VTOL2D": 10,
 }
 MODEL_NAMES = {v: k for k, v in MODEL_IDS.items()}
-MODEL_DIMS = {0: (2, 2), 1: (4, 2), 2: (4, 2), 3: (4, 2), 4: (12, 4), 5: (4, 2), 6: (6, 2), 7: (4, 2), 8: (3, 2), 9: (3, 3)}
+MODEL_DIMS = {0: (2, 2), 1: (4, 2), 2: (4, 2), 3: (4, 2), 4: (12, 4), 5: (4, 2), 6: (6, 2), 7: (4, 2), 8: (3, 2), 9: (3, 3), 10: (6, 4)}
 
 OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL = 0, 1, 2, 3
 STATUS_STR = {0: "optimal", 1: "infeasible", 2: "user_limit", 3: "solver_error"}   # cvxpy's vocabulary
@@ -34,6 +35,12 @@ class ScbParams(C.Structure):
         ("mass", C.c_double), ("Ix", C.c_double), ("Iy", C.c_double), ("Iz", C.c_double),
         ("arm_L", C.c_double), ("nu_coef", C.c_double), ("gravity", C.c_double),
         ("mpc_max_iter", C.c_int32), ("mpc_superellipsoid", C.c_int32), ("mpc_tol", C.c_double),
+        # VTOL2D (robots/vtol2D.py:57-110)
+        ("S_wing", C.c_double), ("rho", C.c_double), ("C_L0", C.c_double), ("C_Lalpha", C.c_double), ("blend_M", C.c_double),
+        ("alpha_0", C.c_double), ("C_Ldelta_e", C.c_double), ("C_D0", C.c_double), ("C_Dalpha", C.c_double),
+        ("C_Ddelta_e", C.c_double), ("C_m0", C.c_double), ("C_malpha", C.c_double), ("C_mdelta_e", C.c_double),
+        ("chord", C.c_double), ("k_front", C.c_double), ("k_rear", C.c_double), ("k_pusher", C.c_double),
+        ("ell_f", C.c_double), ("ell_r", C.c_double), ("pitch_max", C.c_double), ("descent_speed_max", C.c_double),
     ]
 
 
@@ -78,6 +85,7 @@ PROTOTYPES = {
     "scb_active_words": (C.c_int, [C.c_int, C.c_int]),
     "scb_limits": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "scb_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double), _vp]),
+    "scb_measure_latency_floor": (C.c_int, [C.POINTER(C.c_double)] * 3 + [_vp]),
     "scb_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "scb_ctx_destroy": (None, [_vp]),
     "scb_ctx_launches": (C.c_long, [_vp]),

@@ -24,7 +24,7 @@ CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-st
           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 # scb_model ids with an MPC kernel (include/scb.h): all but Manipulator2D; 100 + id = the general-row variants of SI / DU / DI
 # for superellipsoid obstacles
-MPC_MODELS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 100, 101, 105]
+MPC_MODELS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 100, 101, 105]
 
 
 def _units(single_tu):

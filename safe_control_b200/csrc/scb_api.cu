@@ -21,6 +21,7 @@ SCB_MPC_INSTANTIATE(SCB_QUAD_2D)
 SCB_MPC_INSTANTIATE(SCB_UNICYCLE_2D)
 SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
 SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+SCB_MPC_INSTANTIATE(SCB_VTOL_2D)
 SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
 SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
 SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
@@ -511,6 +512,61 @@ extern "C" int scb_measure_fp64_peak(double* tflops, void* stream) {
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
   CK(cudaGetLastError());
   *tflops = best;
+  return SCB_OK;
+}
+
+// Latency floor of a small launch on this device (bench.py: roofline.latency_floor): what a kernel of cfg2's geometry
+// (256 CTAs x 128 threads) costs inside a CUDA graph when it does (a) nothing, (b) one and (c) two DEPENDENT cold-DRAM
+// round trips per warp followed by a store.  (c) - (b) is the price of one dependent DRAM round trip; the cfg2 kernel
+// has two (nobs / state, then rows are already in flight) plus ~700 dependent instructions.
+__global__ void floor_empty_kernel(int* sink) { if (sink && threadIdx.x == 9999) *sink = 0; }
+__global__ void floor_init_kernel(unsigned* buf, unsigned n) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    buf[i] = (unsigned)(((unsigned long long)i * 2654435761ull + 12345ull) % n);
+}
+__global__ void floor_chase_kernel(const unsigned* __restrict__ buf, unsigned n, unsigned offset, int hops, unsigned* out) {
+  const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned idx = (offset + w * 1000003u) % n;
+  for (int h = 0; h < hops; ++h) idx = buf[idx];
+  if ((threadIdx.x & 31) == 0) out[w] = idx;
+}
+
+extern "C" int scb_measure_latency_floor(double* empty_us, double* one_trip_us, double* two_trip_us, void* stream) {
+  if (!empty_us || !one_trip_us || !two_trip_us) return SCB_ERR_BAD_ARG;
+  const unsigned n = 128u << 20;                       // 512 MB of uint32: 4x L2
+  const int K = 200, grid = 256, block = 128;
+  unsigned *buf = nullptr, *out = nullptr;
+  CK(cudaMalloc((void**)&buf, (size_t)n * 4));
+  CK(cudaMalloc((void**)&out, (size_t)grid * block / 32 * 4));
+  cudaStream_t s = nullptr;
+  CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  (void)stream;
+  floor_init_kernel<<<1024, 256, 0, s>>>(buf, n);
+  CK(cudaStreamSynchronize(s));
+  double res[3] = {0, 0, 0};
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int mode = 0; mode < 3; ++mode) {
+    cudaGraph_t g; cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < K; ++k) {
+      if (mode == 0) floor_empty_kernel<<<grid, block, 0, s>>>(nullptr);
+      else floor_chase_kernel<<<grid, block, 0, s>>>(buf, n, (unsigned)(k * 7919u * 4099u), mode, out);
+    }
+    CK(cudaStreamEndCapture(s, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    CK(cudaGraphLaunch(ge, s)); CK(cudaStreamSynchronize(s));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(e0, s)); CK(cudaGraphLaunch(ge, s)); CK(cudaEventRecord(e1, s)); CK(cudaEventSynchronize(e1));
+      float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms < best) best = ms;
+    }
+    res[mode] = (double)best * 1e3 / K;
+    cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s); cudaFree(buf); cudaFree(out);
+  *empty_us = res[0]; *one_trip_us = res[1]; *two_trip_us = res[2];
   return SCB_OK;
 }
 

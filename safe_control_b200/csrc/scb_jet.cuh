@@ -66,6 +66,24 @@ SCB_HD void jconst(double& r, double c) { r = c; }
 SCB_HD void jvar_entry(double& r, double val, int, int) { r = val; }
 SCB_HD void jvar_entry(double& r, double val, int, int, int) { r = val; }
 
+// bivariate chain rule r = f(a, b): value f0, first partials fa, fb, second partials faa, fab, fbb
+SCB_HD void jchain2(double& r, const double&, const double&, double f0, double, double, double, double, double) { r = f0; }
+SCB_HD void jchain2(JetG& r, const JetG& a, const JetG& b, double f0, double fa, double fb, double, double, double) {
+  r.g = fa * a.g + fb * b.g; r.v = f0;
+}
+SCB_HD void jchain2(JetH& r, const JetH& a, const JetH& b, double f0, double fa, double fb, double faa, double fab, double fbb) {
+  const double agi = a.gi, agj = a.gj, bgi = b.gi, bgj = b.gj;
+  r.h = fa * a.h + fb * b.h + faa * agi * agj + fab * (agi * bgj + agj * bgi) + fbb * bgi * bgj;
+  r.gi = fa * agi + fb * bgi; r.gj = fa * agj + fb * bgj; r.v = f0;
+}
+// atan2(y, x) with a precomputed value `val` (= atan2(y.v, x.v)): partials  x / r2,  -y / r2;  second partials
+// -2xy / r2^2 (yy),  (y^2 - x^2) / r2^2 (yx),  2xy / r2^2 (xx)
+template <class T>
+SCB_HD void jatan2(T& r, const T& y, const T& x, double val) {
+  const double yv = jval(y), xv = jval(x), r2 = xv * xv + yv * yv, i2 = 1.0 / r2, i4 = i2 * i2;
+  jchain2(r, y, x, val, xv * i2, -yv * i2, -2.0 * xv * yv * i4, (yv * yv - xv * xv) * i4, 2.0 * xv * yv * i4);
+}
+
 // sqrt(max(a, 0)) and 1/a through the chain rule, for every jet flavour (double, JetG, JetH)
 template <class T>
 SCB_HD void jsqrt0(T& r, const T& a) {
@@ -93,6 +111,9 @@ SCB_HD void jaddc(T& r, const T& a, double c) { T k; jconst(k, c); jaxpy(r, a, 1
 // sin/cos providers for the stage maps: compute, compute + remember, or replay the remembered values (the entry-jet
 // passes evaluate one stage many times at the same point; the transcendental is paid once per stage and iterate)
 struct TrigCompute {
+  // a scalar the stage map needs at the iterate (exp, atan2 ...): compute / compute + remember / replay, like sin and cos
+  template <class F>
+  SCB_HD double memo(F f) { return f(); }
   template <class T>
   SCB_HD void operator()(T& s, T& c, const T& a) {
     double sv, cv;
@@ -106,6 +127,8 @@ struct TrigStore {
   double* buf;
   int n;
   SCB_HD explicit TrigStore(double* b) : buf(b), n(0) {}
+  template <class F>
+  SCB_HD double memo(F f) { const double v = f(); buf[2 * n] = v; buf[2 * n + 1] = 0.0; ++n; return v; }
   template <class T>
   SCB_HD void operator()(T& s, T& c, const T& a) {
     double sv, cv;
@@ -120,6 +143,8 @@ struct TrigLoad {
   const double* buf;
   int n;
   SCB_HD explicit TrigLoad(const double* b) : buf(b), n(0) {}
+  template <class F>
+  SCB_HD double memo(F) { const double v = buf[2 * n]; ++n; return v; }
   template <class T>
   SCB_HD void operator()(T& s, T& c, const T& a) {
     const double sv = buf[2 * n], cv = buf[2 * n + 1];

@@ -269,6 +269,118 @@ struct MpcModel<SCB_QUAD_2D> {
   }
 };
 
+// VTOL2D (quadplane in the x-z plane, robots/vtol2D.py): X = [x, z, theta, x_dot, z_dot, theta_dot], U = [front, rear,
+// pusher rotor throttle, elevator]; control affine:  f = baseline aerodynamics (elevator 0) + gravity (:115-193),
+// g = rotor thrusts rotated by theta and the aerodynamic forces / moment AT elevator deflection 1 (:198-300 -- the full
+// value, transcribed literally, not the increment).  step = Euler + wrap (:302-310); barrier_dt (:462-488): circle h on
+// (x, z), relative degree 2, positions after two own steps = p_1 + v_1 dt, so the aerodynamics are evaluated once per
+// stage.  MPC weights / gains / bounds / horizon 30: mpc_cbf.py:40-43, 83-87, 222-232.
+template <>
+struct MpcModel<SCB_VTOL_2D> {
+  static constexpr int NX = 6, NU = 4, NY = 10, REL = 2, NGOAL = 2, AUX = 0, NTRIG = 6;   // 3 sin/cos pairs + alpha, 2 exp
+  static constexpr bool VBOUND = false, LINEAR = false, GENERAL = false;
+  static SCB_HD double beta() { return 1.01; }
+  // lift, drag, pitching moment at elevator deflection de  (_lift_blending :351-377, _lift_drag_moment :379-412)
+  template <class T>
+  static SCB_HD void lift_drag_moment(const scb_params& p, const T& V2, const T& al, const T& CLa, double de, T& L, T& D, T& Mo) {
+    T CL, CD, CM, t, q;
+    jaddc(CL, CLa, p.C_Ldelta_e * de);
+    jmul(t, al, al); jscale(CD, t, p.C_Dalpha); jaddc(CD, CD, p.C_D0 + p.C_Ddelta_e * de);
+    jscale(CM, al, p.C_malpha); jaddc(CM, CM, p.C_m0 + p.C_mdelta_e * de);
+    jscale(q, V2, 0.5 * p.rho);                                  // qbar = 0.5 rho V^2
+    jmul(L, q, CL); jscale(L, L, p.S_wing);
+    jmul(D, q, CD); jscale(D, D, p.S_wing);
+    jmul(Mo, q, CM); jscale(Mo, Mo, p.S_wing * p.chord);
+  }
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double*, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
+    const T &th = y[2], &xd = y[3], &zd = y[4];
+    T s, c, ub, wb, nwb, t, V2, al;
+    trig(s, c, th);
+    jmul(ub, c, xd); jmul(t, s, zd); jadd(ub, ub, t);            // u_b =  c x_dot + s z_dot   (:333-343)
+    jmul(wb, c, zd); jmul(t, s, xd); jaxpy(wb, wb, -1.0, t);     // w_b = -s x_dot + c z_dot
+    jmul(V2, ub, ub); jmul(t, wb, wb); jadd(V2, V2, t);          // V^2
+    jscale(nwb, wb, -1.0);
+    const double alv = trig.memo([&] { return atan2(-jval(wb), jval(ub)); });
+    jatan2(al, nwb, ub, alv);                                    // alpha = atan2(-w_b, u_b)
+    // blended lift coefficient
+    T CLlin, sa, ca, CLnl, e1, e2, num, den, sig, CLa, a1, a2;
+    jscale(CLlin, al, p.C_Lalpha); jaddc(CLlin, CLlin, p.C_L0);
+    trig(sa, ca, al);
+    jmul(CLnl, sa, ca); jscale(CLnl, CLnl, 2.0);
+    jaddc(a1, al, -p.alpha_0); jscale(a1, a1, -p.blend_M);       // -M (alpha - alpha_0)
+    jaddc(a2, al, p.alpha_0); jscale(a2, a2, p.blend_M);         //  M (alpha + alpha_0)
+    const double e1v = trig.memo([&] { return exp(jval(a1)); }), e2v = trig.memo([&] { return exp(jval(a2)); });
+    jchain(e1, a1, e1v, e1v, e1v); jchain(e2, a2, e2v, e2v, e2v);
+    jadd(num, e1, e2); jaddc(num, num, 1.0);                     // 1 + tmp1 + tmp2
+    T d1, d2, iden;
+    jaddc(d1, e1, 1.0); jaddc(d2, e2, 1.0); jmul(den, d1, d2);
+    jrecip(iden, den); jmul(sig, num, iden);                     // sigma
+    jaxpy(t, CLnl, -1.0, CLlin); jmul(t, sig, t); jadd(CLa, CLlin, t);     // (1 - sigma) CL_lin + sigma CL_nl
+    // forces: baseline (delta_e = 0) and the elevator column (delta_e = 1), wind -> inertial by theta + alpha
+    T L0, D0, M0, L1, D1, M1, hd, sh, ch;
+    lift_drag_moment(p, V2, al, CLa, 0.0, L0, D0, M0);
+    lift_drag_moment(p, V2, al, CLa, 1.0, L1, D1, M1);
+    jadd(hd, th, al);
+    trig(sh, ch, hd);
+    T fx0, fz0, fx1, fz1;
+    jmul(fx0, ch, D0); jscale(fx0, fx0, -1.0); jmul(t, sh, L0); jaxpy(fx0, fx0, -1.0, t);    // c (-D) - s L
+    jmul(fz0, sh, D0); jscale(fz0, fz0, -1.0); jmul(t, ch, L0); jadd(fz0, fz0, t);           // s (-D) + c L
+    jmul(fx1, ch, D1); jscale(fx1, fx1, -1.0); jmul(t, sh, L1); jaxpy(fx1, fx1, -1.0, t);
+    jmul(fz1, sh, D1); jscale(fz1, fz1, -1.0); jmul(t, ch, L1); jadd(fz1, fz1, t);
+    const double im = 1.0 / p.mass, iI = 1.0 / p.Iy;
+    // accelerations: f + g u
+    T xdd, zdd, tdd, rot, g3;
+    jscale(xdd, fx0, im);
+    jscale(zdd, fz0, im); jaddc(zdd, zdd, -p.gravity);           // (fz - m g) / m
+    jscale(tdd, M0, iI);
+    jaxpy(rot, y[6], p.k_rear / p.k_front, y[7]); jscale(rot, rot, p.k_front * im);   // (k_f u0 + k_r u1) / m
+    jmul(t, s, rot); jaxpy(xdd, xdd, -1.0, t);                   // front / rear rotors: (-s, c) k / m
+    jmul(t, c, rot); jadd(zdd, zdd, t);
+    jscale(g3, y[8], p.k_pusher * im);                           // pusher: (c, s) k_p / m
+    jmul(t, c, g3); jadd(xdd, xdd, t);
+    jmul(t, s, g3); jadd(zdd, zdd, t);
+    jmul(t, fx1, y[9]); jaxpy(xdd, xdd, im, t);                  // elevator column
+    jmul(t, fz1, y[9]); jaxpy(zdd, zdd, im, t);
+    jaxpy(tdd, tdd, p.ell_f * p.k_front * iI, y[6]);
+    jaxpy(tdd, tdd, -p.ell_r * p.k_rear * iI, y[7]);
+    jmul(t, M1, y[9]); jaxpy(tdd, tdd, iI, t);
+    jaxpy(F[0], y[0], p.dt, xd);
+    jaxpy(F[1], y[1], p.dt, zd);
+    jaxpy(F[2], th, p.dt, y[5]);
+    jaxpy(F[3], xd, p.dt, xdd);
+    jaxpy(F[4], zd, p.dt, zdd);
+    jaxpy(F[5], y[5], p.dt, tdd);
+    P1 = F[0]; Q1 = F[1];
+    jaxpy(P2, P1, p.dt, F[3]);                                   // second own step moves the position by v_1 dt
+    jaxpy(Q2, Q1, p.dt, F[4]);
+  }
+};
+
+// state-bound rows of the MPC per node k = 1..H (mpc_cbf.py:193-199, 205-211: |x[3]| <= v_max for the unicycle / bicycle
+// models; :227-232 for VTOL2D): row r of a node is  sgn * x[var] + off >= 0
+template <class Mod>
+struct MpcStateBounds {
+  static constexpr int NSB = Mod::VBOUND ? 2 : 0;
+  static SCB_HD void get(const scb_params& p, int r, int& var, double& sgn, double& off) {
+    var = 3; sgn = (r & 1) ? 1.0 : -1.0; off = p.v_max;
+  }
+};
+template <>
+struct MpcStateBounds<MpcModel<SCB_VTOL_2D>> {
+  static constexpr int NSB = 5;
+  static SCB_HD void get(const scb_params& p, int r, int& var, double& sgn, double& off) {
+    const double pitch = p.pitch_max * 3.14159 / 180.0;          // (the reference's own constant, mpc_cbf.py:231-232)
+    switch (r) {
+      case 0: var = 3; sgn = -1.0; off = p.v_max; break;
+      case 1: var = 3; sgn = 1.0; off = p.v_max; break;
+      case 2: var = 4; sgn = 1.0; off = p.descent_speed_max; break;
+      case 3: var = 2; sgn = -1.0; off = pitch; break;
+      default: var = 2; sgn = 1.0; off = pitch; break;
+    }
+  }
+};
+
 // Superellipsoid obstacles in MPC (SingleIntegrator2D / DynamicUnicycle2D / DoubleIntegrator2D): their agent_barrier_dt
 // picks h per obstacle with if_else(obs[6] < 0.5, circle, superellipsoid) (e.g. dynamic_unicycle2D.py:204-228), and the
 // superellipsoid h = (|x'| / (a + R))^e + (|y'| / (b + R))^e - 1 (guards: a, b >= 1e-3, e >= 2) has no 12-sums
@@ -410,7 +522,7 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   constexpr bool VBOUND = Mod::VBOUND, LINEAR = Mod::LINEAR, GENERAL = Mod::GENERAL;
   constexpr int NY = NX + NU, NH = NY * (NY + 1) / 2;
   MpcLayout L;
-  L.H = H; L.M = M; L.n = H * NU; L.NS = 2 * H * NU + (VBOUND ? 2 * H : 0);
+  L.H = H; L.M = M; L.n = H * NU; L.NS = 2 * H * NU + MpcStateBounds<Mod>::NSB * H;
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += cnt; return r; };
   L.X = take((H + 1) * NX);  L.Z = take(H * NU);
@@ -444,13 +556,14 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
 // words of the MPC active mask (include/scb.h scb_mpc_active_words): H*M CBF rows, then the NS simple bounds
 template <class Mod>
 SCB_HD int mpc_active_words(int H, int M) {
-  return (H * M + 2 * H * Mod::NU + (Mod::VBOUND ? 2 * H : 0) + 63) / 64;
+  return (H * M + 2 * H * Mod::NU + MpcStateBounds<Mod>::NSB * H + 63) / 64;
 }
 
 // simple (bound) constraint q:  g_q = sgn * y_k[var] + off >= 0
 struct SimpleCon { int k, var; double sgn, off; };
-template <int NX, int NU>
+template <class Mod>
 SCB_HD SimpleCon decode_simple(const scb_params& p, int H, int q) {
+  constexpr int NX = Mod::NX, NU = Mod::NU, NSB = MpcStateBounds<Mod>::NSB;
   SimpleCon c;
   if (q < 2 * H * NU) {
     c.k = q / (2 * NU);
@@ -458,9 +571,9 @@ SCB_HD SimpleCon decode_simple(const scb_params& p, int H, int q) {
     c.var = NX + i;
     if (r & 1) { c.sgn = 1.0; c.off = -p.u_lb[i]; } else { c.sgn = -1.0; c.off = p.u_ub[i]; }
   } else {
-    const int t = q - 2 * H * NU;
-    c.k = 1 + (t >> 1); c.var = 3;
-    if (t & 1) { c.sgn = 1.0; c.off = p.v_max; } else { c.sgn = -1.0; c.off = p.v_max; }
+    const int t = q - 2 * H * NU, nsb = NSB > 0 ? NSB : 1;
+    c.k = 1 + t / nsb;
+    MpcStateBounds<Mod>::get(p, t - (c.k - 1) * nsb, c.var, c.sgn, c.off);
   }
   return c;
 }
@@ -953,7 +1066,7 @@ struct MpcSolver {
     // simple bounds
     SCB_LANE_UNROLL
     for (int q = lane; q < L.NS; q += LANES) {
-      const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+      const SimpleCon c = decode_simple<Mod>(p, H, q);
       const double s = w[L.SS + q], lam = w[L.SL + q], is = w[L.SDS + q];
       double wt;
       if (rhs) {
@@ -1059,7 +1172,7 @@ struct MpcSolver {
     sync();
     SCB_LANE_UNROLL
     for (int q = lane; q < L.NS; q += LANES) {
-      const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+      const SimpleCon c = decode_simple<Mod>(p, H, q);
       atomic_add_ws(Gm + c.k * NH + hidx<NY>(c.var, c.var), w[L.SL + q] * w[L.SDS + q]);
     }
     sync();
@@ -1397,7 +1510,7 @@ struct MpcSolver {
       for (int t = lane; t < H * M; t += LANES) w[L.DS + t] = 1.0 / fmax(w[L.C + t], floor_);
       SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
-        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        const SimpleCon c = decode_simple<Mod>(p, H, q);
         const double sv = fmax(simple_value(c, w + L.Z, w + L.X), floor_);
         w[L.SS + q] = sv; w[L.SDS + q] = 1.0 / sv;
       }
@@ -1436,7 +1549,7 @@ struct MpcSolver {
       }
       SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
-        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        const SimpleCon c = decode_simple<Mod>(p, H, q);
         const double g = simple_value(c, w + L.Z, w + L.X), lam = w[L.SL + q], sg = fmax(g, 0.0);
         e_p = fmax(e_p, -g); e_c = fmax(e_c, sg * lam); e_cm = fmax(e_cm, fabs(sg * lam - mu_bar));
         lam_max = fmax(lam_max, lam);
@@ -1456,7 +1569,7 @@ struct MpcSolver {
         for (int t = lane; t < H * M; t += LANES) e_cm = fmax(e_cm, fabs(fmax(w[L.C + t], 0.0) * w[L.L + t] - mu_bar));
         SCB_LANE_UNROLL
         for (int q = lane; q < L.NS; q += LANES) {
-          const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+          const SimpleCon c = decode_simple<Mod>(p, H, q);
           e_cm = fmax(e_cm, fabs(fmax(simple_value(c, w + L.Z, w + L.X), 0.0) * w[L.SL + q] - mu_bar));
         }
         e_cm = gmax(e_cm);
@@ -1529,7 +1642,7 @@ struct MpcSolver {
       }
       SCB_LANE_UNROLL
       for (int q = lane; q < L.NS; q += LANES) {
-        const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+        const SimpleCon c = decode_simple<Mod>(p, H, q);
         const double dg = c.sgn * w[L.DY + c.k * NY + c.var];
         const double g = simple_value(c, w + L.Z, w + L.X), s = w[L.SS + q], lam = w[L.SL + q];
         const double ds = dg + (g - s), dl = -((s * lam - mu_bar) + lam * ds) * w[L.SDS + q];
@@ -1562,7 +1675,7 @@ struct MpcSolver {
         }
         SCB_LANE_UNROLL
         for (int q = lane; q < L.NS; q += LANES) {
-          const SimpleCon c = decode_simple<NX, NU>(p, H, q);
+          const SimpleCon c = decode_simple<Mod>(p, H, q);
           const double g = simple_value(c, zz, xx);
           acc += (g >= floor_s) ? -mu_bar * log_call(g) : rho_lin0 - nu_pen * g;
         }
@@ -1632,7 +1745,7 @@ struct MpcSolver {
           double g, lam;
           if (t < H * M) { g = w[L.C + t]; lam = w[L.L + t]; }
           else {
-            const SimpleCon c = decode_simple<NX, NU>(p, H, t - H * M);
+            const SimpleCon c = decode_simple<Mod>(p, H, t - H * M);
             g = simple_value(c, w + L.Z, w + L.X); lam = w[L.SL + (t - H * M)];
           }
           if (lam > fmax(g, 0.0)) bits |= 1ull << b;

@@ -72,6 +72,7 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const MpcIO& io,
     SCB_GO(mpc_launch_m, SCB_KINEMATIC_BICYCLE_2D_C3BF)
     SCB_GO(mpc_launch_m, SCB_KINEMATIC_BICYCLE_2D_DPCBF)
     SCB_GO(mpc_launch_m, SCB_QUAD_3D)
+    SCB_GO(mpc_launch_m, SCB_VTOL_2D)
     default:
       return SCB_ERR_UNSUPPORTED;     // Manipulator2D: no agent_barrier_dt in the reference
   }

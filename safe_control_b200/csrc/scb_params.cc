@@ -48,6 +48,7 @@ int scb_model_dims(int model, int* nx, int* nu) {
     case SCB_QUAD_2D: x = 6; u = 2; break;
     case SCB_UNICYCLE_2D: x = 3; u = 2; break;
     case SCB_MANIPULATOR_2D: x = 3; u = 3; break;
+    case SCB_VTOL_2D: x = 6; u = 4; break;
     default: return SCB_ERR_BAD_ARG;
   }
   if (nx) *nx = x;
@@ -64,7 +65,8 @@ int scb_mpc_active_words(const scb_params* p, int M, int H) {
   // models whose MPC bounds the velocity state (mpc_cbf.py:193-199, 205-211): DynamicUnicycle2D, KinematicBicycle2D*
   const bool vbound = p->model == SCB_DYNAMIC_UNICYCLE_2D || p->model == SCB_KINEMATIC_BICYCLE_2D ||
                       p->model == SCB_KINEMATIC_BICYCLE_2D_C3BF || p->model == SCB_KINEMATIC_BICYCLE_2D_DPCBF;
-  return (H * M + 2 * H * nu + (vbound ? 2 * H : 0) + 63) / 64;
+  const int nsb = vbound ? 2 : (p->model == SCB_VTOL_2D ? 5 : 0);       // state-bound rows per node (mpc_cbf.py:193-232)
+  return (H * M + 2 * H * nu + nsb * H + 63) / 64;
 }
 
 
@@ -150,6 +152,22 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       if (qp) p->alpha1 = p->alpha2 = 1.5;
       if (od) { p->alpha1 = p->alpha2 = 0.5; p->omega1_0 = p->omega2_0 = 1.0; p->p_sb1 = p->p_sb2 = 1e4; }
       break;
+    case SCB_VTOL_2D: {                                // robots/vtol2D.py:57-110; mpc_cbf.py:40-43, 83-87, 222-232
+      if (!mpc) return SCB_ERR_UNSUPPORTED;            // agent_barrier is not implemented (vtol2D.py:458-460)
+      p->mass = 11.0; p->Iy = 1.135; p->gravity = 9.81;
+      p->S_wing = 0.55; p->rho = 1.2682; p->C_L0 = 0.23; p->C_Lalpha = 5.61; p->blend_M = 50.0; p->alpha_0 = 15.0 * M_PI / 180.0;
+      p->C_Ldelta_e = 0.13; p->C_D0 = 0.043; p->C_Dalpha = 0.03; p->C_Ddelta_e = 0.0;
+      p->C_m0 = 0.0135; p->C_malpha = -2.74; p->C_mdelta_e = -0.99; p->chord = 0.18994;
+      p->k_front = 70.0; p->k_rear = 70.0; p->k_pusher = 60.0; p->ell_f = 0.5; p->ell_r = 0.5;
+      p->v_max = 15.0; p->v_min = -15.0; p->pitch_max = 15.0; p->descent_speed_max = 5.0;
+      for (int i = 0; i < 3; ++i) { p->u_lb[i] = 0.0; p->u_ub[i] = 1.0; }     // throttle_min / max
+      p->u_lb[3] = -0.5; p->u_ub[3] = 0.5;                                       // elevator_min / max
+      const double Q[6] = {10, 10, 250, 10, 10, 50};
+      for (int i = 0; i < 6; ++i) p->Q[i] = Q[i];
+      p->R[0] = p->R[1] = p->R[2] = 0.5; p->R[3] = 50000.0;
+      p->alpha1 = p->alpha2 = 0.05;
+      break;
+    }
     case SCB_QUAD_3D: {
       if (!mpc) return SCB_ERR_UNSUPPORTED;            // agent_barrier raises, quad3D.py:269-273
       p->mass = 3.0; p->Ix = p->Iy = p->Iz = 0.5; p->arm_L = 0.3; p->nu_coef = 0.1;

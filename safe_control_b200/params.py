@@ -93,6 +93,24 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
         for i in range(4):
             p.u_lb[i], p.u_ub[i] = umin, umax
 
+    elif model == "VTOL2D":                                   # vtol2D.py:57-110 (same key names)
+        p.mass = float(s.setdefault("mass", 11.0)); p.Iy = float(s.setdefault("inertia", 1.135))
+        for key, field, dflt in (("S_wing", "S_wing", 0.55), ("rho", "rho", 1.2682), ("C_L0", "C_L0", 0.23), ("C_Lalpha", "C_Lalpha", 5.61),
+                                 ("M", "blend_M", 50.0), ("alpha_0", "alpha_0", math.radians(15)), ("C_Ldelta_e", "C_Ldelta_e", 0.13),
+                                 ("C_D0", "C_D0", 0.043), ("C_Dalpha", "C_Dalpha", 0.03), ("C_Ddelta_e", "C_Ddelta_e", 0.0),
+                                 ("C_m0", "C_m0", 0.0135), ("C_malpha", "C_malpha", -2.74), ("C_mdelta_e", "C_mdelta_e", -0.99),
+                                 ("chord", "chord", 0.18994), ("k_front", "k_front", 70.0), ("k_rear", "k_rear", 70.0),
+                                 ("k_pusher", "k_pusher", 60.0), ("ell_f", "ell_f", 0.5), ("ell_r", "ell_r", 0.5),
+                                 ("pitch_max", "pitch_max", 15.0), ("descent_speed_max", "descent_speed_max", 5.0)):
+            setattr(p, field, float(s.setdefault(key, dflt)))
+        v = float(s.setdefault("v_max", 15.0)); p.v_max = v; p.v_min = -v
+        tmin = float(s.setdefault("throttle_min", 0.0)); tmax = float(s.setdefault("throttle_max", 1.0))
+        emin = float(s.setdefault("elevator_min", -0.5)); emax = float(s.setdefault("elevator_max", 0.5))
+        for i in range(3):
+            p.u_lb[i], p.u_ub[i] = tmin, tmax
+        p.u_lb[3], p.u_ub[3] = emin, emax
+        s.setdefault("mpc_horizon", 30)                         # mpc_cbf.py:41
+
     prefix = {"cbf_qp": "cbf_", "mpc_cbf": "mpc_cbf_"}.get(controller)
     if prefix:
         for k in ("alpha", "alpha1", "alpha2"):
@@ -111,7 +129,7 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
 
 def cbf_param_dict(p, controller, model):
     """The `.cbf_param` dict the reference exposes (tracking.py:738 reads alpha1/alpha2)."""
-    rel2 = model in ("DynamicUnicycle2D", "KinematicBicycle2D", "DoubleIntegrator2D", "Quad2D")
+    rel2 = model in ("DynamicUnicycle2D", "KinematicBicycle2D", "DoubleIntegrator2D", "Quad2D", "VTOL2D")
     d = {"alpha1": p.alpha1, "alpha2": p.alpha2} if rel2 else {"alpha": p.alpha}
     if controller == "optimal_decay_cbf_qp":
         d.update(omega1=p.omega1_0, p_sb1=p.p_sb1)

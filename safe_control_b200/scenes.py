@@ -19,11 +19,11 @@ ANGLE_UNPASSED = {   # tracking.py:352-357
     "SingleIntegrator2D": 2.0 * np.pi, "Quad3D": 2.0 * np.pi, "DynamicUnicycle2D": 1.2 * np.pi,
     "KinematicBicycle2D": 2.0 * np.pi, "KinematicBicycle2D_C3BF": 2.0 * np.pi,
     "KinematicBicycle2D_DPCBF": 2.0 * np.pi, "DoubleIntegrator2D": 2.0 * np.pi, "Quad2D": 2.0 * np.pi,
-    "Unicycle2D": 1.2 * np.pi,
+    "Unicycle2D": 1.2 * np.pi, "VTOL2D": 1.2 * np.pi,
 }
 BARRIER_BETA = {"SingleIntegrator2D": 1.01, "DynamicUnicycle2D": 1.01, "KinematicBicycle2D": 1.1,
                 "KinematicBicycle2D_C3BF": 1.1, "Quad3D": 1.01, "KinematicBicycle2D_DPCBF": 1.1,
-                "DoubleIntegrator2D": 1.01, "Quad2D": 1.01, "Unicycle2D": 1.01}
+                "DoubleIntegrator2D": 1.01, "Quad2D": 1.01, "Unicycle2D": 1.01, "VTOL2D": 1.01}
 
 
 def angle_normalize(x):
@@ -75,6 +75,8 @@ def nominal_input(model, spec, X, goal, optimal_decay=False):
         rng = np.random.default_rng(X.shape[0])
         hover = spec["mass"] * 9.81 / 2.0
         return hover + rng.uniform(-2.0, 2.0, (X.shape[0], 2))
+    if model == "VTOL2D":                                      # vtol2D.py:446-448: "not implemented" -> zeros
+        return np.zeros((X.shape[0], 4))
     if model == "Quad3D":                                      # quad3D.py:160-206
         g, m = 9.8, spec["mass"]
         k_p, k_d, k_ang = 1.0, 2.0, 5.0
@@ -133,6 +135,9 @@ def default_spec(model):
         s.update(a_max=1.0, v_max=1.0, w_max=0.5)
     elif model == "Quad2D":
         s.update(mass=1.0, inertia=0.01, f_min=1.0, f_max=10.0)
+    elif model == "VTOL2D":
+        s.update(v_max=15.0, pitch_max=15.0, descent_speed_max=5.0, throttle_min=0.0, throttle_max=1.0, elevator_min=-0.5,
+                 elevator_max=0.5)
     return s
 
 
@@ -207,7 +212,7 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
         pos[todo[ok]] = cand[ok]
         todo = todo[~ok]
     goal2 = rng.uniform(0, L, (N, 2))
-    nx = {"SingleIntegrator2D": 2, "Quad3D": 12, "Quad2D": 6, "Unicycle2D": 3}.get(model, 4)
+    nx = {"SingleIntegrator2D": 2, "Quad3D": 12, "Quad2D": 6, "Unicycle2D": 3, "VTOL2D": 6}.get(model, 4)
     X = np.zeros((N, nx)); X[:, 0:2] = pos
     yaw = np.zeros(N)
     if model == "DoubleIntegrator2D":
@@ -220,6 +225,11 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
         X[:, 2] = sp * np.cos(hd); X[:, 3] = sp * np.sin(hd)
         yaw = rng.uniform(-np.pi, np.pi, N)
         goal = goal2
+    elif model == "VTOL2D":       # cruise: forward speed 6..12 m/s, small pitch; the goal lies 20..40 m ahead at a similar height
+        X[:, 2] = rng.uniform(-0.1, 0.1, N); X[:, 3] = rng.uniform(6.0, 12.0, N); X[:, 4] = rng.uniform(-0.5, 0.5, N)
+        X[:, 5] = rng.normal(0, 0.05, N)
+        yaw = X[:, 2].copy()
+        goal = np.stack([pos[:, 0] + rng.uniform(20, 40, N), np.maximum(pos[:, 1] + rng.uniform(-2, 2, N), 2.0)], axis=1)
     elif model == "Quad2D":
         X[:, 2] = rng.uniform(-0.4, 0.4, N); X[:, 3:5] = rng.uniform(-1.0, 1.0, (N, 2)); X[:, 5] = rng.normal(0, 0.2, N)
         if dense:
@@ -260,7 +270,7 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
         goal = goal2
     U_ref = nominal_input(model, spec, X, goal, optimal_decay=optimal_decay)
     OBS, nobs, idx = nearest_unpassed_obs(model, pos, yaw, scene, M)
-    nu = 4 if model == "Quad3D" else 2
+    nu = 4 if model in ("Quad3D", "VTOL2D") else 2
     return dict(model=model, spec=spec, X=np.ascontiguousarray(X), U_ref=np.ascontiguousarray(U_ref),
                 goal=np.ascontiguousarray(goal), OBS=np.ascontiguousarray(OBS), nobs=nobs, obs_idx=idx,
                 scene_obs=scene, u_prev=np.zeros((N, nu)), L=L)

@@ -143,6 +143,7 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
       MPCCASE(SCB_UNICYCLE_2D)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+      MPCCASE(SCB_VTOL_2D)
       MPCCASE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
       MPCCASE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
       MPCCASE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
@@ -187,6 +188,7 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
     STCASE(SCB_UNICYCLE_2D)
     STCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
     STCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
+    STCASE(SCB_VTOL_2D)
     STCASE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
     STCASE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
     STCASE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)

@@ -40,6 +40,7 @@ from safe_control.robots.double_integrator2D import DoubleIntegrator2D  # noqa: 
 from safe_control.robots.quad2D import Quad2D  # noqa: E402
 from safe_control.robots.unicycle2D import Unicycle2D  # noqa: E402
 from safe_control.robots.manipulator2D import Manipulator2D  # noqa: E402
+from safe_control.robots.vtol2D import VTOL2D  # noqa: E402
 from safe_control.dynamic_env.kinematic_bicycle2D_dpcbf import KinematicBicycle2D_DPCBF  # noqa: E402
 from safe_control.position_control.cbf_qp import CBFQP  # noqa: E402
 from safe_control.position_control.optimal_decay_cbf_qp import OptimalDecayCBFQP  # noqa: E402
@@ -55,6 +56,7 @@ MODEL_CLS = {
     "KinematicBicycle2D_DPCBF": KinematicBicycle2D_DPCBF,
     "Unicycle2D": Unicycle2D,
     "Manipulator2D": Manipulator2D,
+    "VTOL2D": VTOL2D,
 }
 BASE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D")
 EXTRA_MODELS = ("DoubleIntegrator2D", "Quad2D", "KinematicBicycle2D_DPCBF")      # SURVEY 8f-2, second fixture set
@@ -97,6 +99,9 @@ def rand_state(rng, name):
         return np.array([*rng.uniform(0, 10, 2), *rng.uniform(-0.7, 0.7, 2)])
     if name == "Quad2D":
         return np.array([*rng.uniform(0, 10, 2), rng.uniform(-0.5, 0.5), *rng.uniform(-1, 1, 2), rng.uniform(-0.3, 0.3)])
+    if name == "VTOL2D":          # cruise-like states: forward speed 3..12 m/s, small pitch / pitch rate
+        return np.array([rng.uniform(0, 10), rng.uniform(2, 10), rng.uniform(-0.25, 0.25), rng.uniform(3, 12), rng.uniform(-1.5, 1.5),
+                         rng.uniform(-0.2, 0.2)])
     x = np.zeros(12)
     x[0:2] = rng.uniform(0, 10, 2); x[2] = rng.uniform(1, 3)
     x[3:6] = rng.normal(0, 0.05, 3); x[6:9] = rng.normal(0, 0.5, 3); x[9:12] = rng.normal(0, 0.05, 3)
@@ -118,6 +123,8 @@ def rand_input(rng, spec, name):
         return rng.uniform(-1, 1, 2)
     if name == "Quad2D":
         return rng.uniform(1, 10, 2)
+    if name == "VTOL2D":
+        return np.array([*rng.uniform(0, 1, 3), rng.uniform(-0.5, 0.5)])
     return rng.uniform(-10, 10, 4)
 
 

@@ -63,6 +63,7 @@ def probe(name, spec, x, u, goal, obs, M):
 
 
 CASES2 = [("Unicycle2D", {}), ("Unicycle2D", {"mpc_horizon": 6, "mpc_cbf_alpha": 0.2, "w_max": 1.0})]   # second file
+CASES3 = [("VTOL2D", {}), ("VTOL2D", {"mpc_cbf_alpha1": 0.35, "mpc_cbf_alpha2": 0.35, "v_max": 20.0, "pitch_max": 20.0})]   # third file
 
 
 def main(cases=CASES, seed=20261018, fname="ref_mpc_statement.npz"):
@@ -92,7 +93,9 @@ def main(cases=CASES, seed=20261018, fname="ref_mpc_statement.npz"):
 
 
 if __name__ == "__main__":
-    if "--second" in sys.argv:
+    if "--third" in sys.argv:
+        main(CASES3, 20261020, "ref_mpc_statement3.npz")
+    elif "--second" in sys.argv:
         main(CASES2, 20261019, "ref_mpc_statement2.npz")
     else:
         main()

@@ -151,26 +151,48 @@ def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1
     return stats
 
 
-def _check_mpc_chunk(args):
-    import torch
-    torch.set_num_threads(1)
-    spec, M, H, X, goal, u_prev, OBS, nobs, out, sample, kw = args
-    return check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=sample, min_agree=0.0, **kw)
-
-
-def check_mpc_parallel(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample, min_agree=0.9, procs=None, **kw):
+def check_mpc_parallel(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample, min_agree=0.9, procs=None, timeout_s=900, **kw):
     """check_mpc over `sample` on all host cores (the oracle costs 2-6 s per agent at config-5 shapes): every per-agent
-    assertion of check_mpc still fires (a worker's AssertionError propagates); the agreement fraction is asserted on the
-    merged counts."""
-    import multiprocessing as mp
+    assertion of check_mpc still fires (a worker's AssertionError fails the test with its message); the agreement fraction
+    is asserted on the merged counts.  The workers are separate python processes (tests/mpc_check_worker.py) fed through
+    an .npz file -- never a fork of this process: the parent has initialised CUDA and torch's thread pools, and a forked
+    child's autograd engine hangs (observed: a whole GPU lease lost)."""
+    import json
     import os
-    sample = list(sample)
+    import subprocess
+    import sys
+    import tempfile
+    sample = [int(i) for i in sample]
     procs = min(procs or os.cpu_count() or 1, max(1, len(sample)))
     if procs <= 1:
         return check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=sample, min_agree=min_agree, **kw)
-    chunks = [sample[r::procs] for r in range(procs)]
-    with mp.get_context("fork").Pool(procs) as pool:
-        parts = pool.map(_check_mpc_chunk, [(spec, M, H, X, goal, u_prev, OBS, nobs, out, c, kw) for c in chunks])
+    idx = np.array(sample)
+    sub = lambda a: np.ascontiguousarray(np.asarray(a)[idx])          # ship only the sampled rows
+    here = os.path.dirname(os.path.abspath(__file__))
+    with tempfile.TemporaryDirectory() as tmp:
+        arrays = dict(X=sub(X), goal=sub(goal), u_prev=sub(u_prev), OBS=sub(OBS),
+                      nobs=sub(nobs) if nobs is not None else np.full(len(sample), M, np.int32))
+        for k in ("U", "status", "pred_u", "active"):
+            if k in out and out[k] is not None:
+                arrays["out_" + k] = sub(out[k])
+        np.savez(os.path.join(tmp, "in.npz"), **arrays)
+        with open(os.path.join(tmp, "meta.json"), "w") as f:
+            json.dump(dict(spec={k: v for k, v in spec.items() if isinstance(v, (int, float, str, bool))}, M=M, H=H, kw=kw), f)
+        ps = []
+        for r in range(procs):
+            env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+            ps.append(subprocess.Popen([sys.executable, os.path.join(here, "mpc_check_worker.py"), tmp, str(r), str(procs)],
+                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+        parts = []
+        for r, pr in enumerate(ps):
+            try:
+                so, se = pr.communicate(timeout=timeout_s)
+            except subprocess.TimeoutExpired:
+                for q in ps:
+                    q.kill()
+                raise AssertionError(f"oracle worker {r} exceeded {timeout_s} s")
+            assert pr.returncode == 0, f"oracle worker {r} failed:\n{se[-2000:]}"
+            parts.append(json.loads(so.strip().splitlines()[-1]))
     stats = {k: (max(p[k] for p in parts) if k.startswith("worst") else sum(p[k] for p in parts)) for k in parts[0]}
     n_cmp = stats["compared"]
     assert n_cmp == 0 or (stats["agree"] + stats["same_cost"] + stats["better"]) >= min_agree * n_cmp, stats

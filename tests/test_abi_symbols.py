@@ -71,8 +71,12 @@ def test_robot_spec_overrides(lib):
     assert p.radius == 0.25 and s["v_min"] == 0.2          # robots/robot.py:49 beats the model's 0.3 default
     with pytest.raises(NotCompatibleError):
         resolve_params({"model": "SingleIntegrator2D"}, "optimal_decay_cbf_qp")
+    p, s = resolve_params({"model": "VTOL2D", "pitch_max": 20.0}, "mpc_cbf")     # mpc_cbf.py:40-43, 83-87, 222-232
+    assert (p.nx, p.nu, s["mpc_horizon"], p.pitch_max, p.alpha1, list(p.R)) == (6, 4, 30, 20.0, 0.05, [0.5, 0.5, 0.5, 50000.0])
+    with pytest.raises(NotCompatibleError):
+        resolve_params({"model": "VTOL2D"}, "cbf_qp")             # agent_barrier is not implemented (vtol2D.py:458-460)
     with pytest.raises(ValueError):
-        resolve_params({"model": "VTOL2D"}, "mpc_cbf")            # not built
+        resolve_params({"model": "Hovercraft"}, "mpc_cbf")
     p, s = resolve_params({"model": "Unicycle2D", "w_max": 1.0}, "mpc_cbf")
     assert (p.nx, p.nu, p.alpha, p.u_ub[1], p.Q[2]) == (3, 2, 0.05, 1.0, 0.01)
     with pytest.raises(NotCompatibleError):

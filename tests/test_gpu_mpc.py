@@ -41,6 +41,7 @@ def solve(ctrl, sc, goal, **kw):
     ("Unicycle2D", 256, 10, 16, False, 16),
     ("KinematicBicycle2D_C3BF", 192, 8, 16, False, 12),     # general (non-quadratic) rows: collision cone / parabolic
     ("KinematicBicycle2D_DPCBF", 192, 8, 16, False, 12),
+    ("VTOL2D", 128, 8, 8, False, 16),                        # 6 states, 4 inputs, 5 state-bound rows per node
 ])
 def test_mpc_vs_oracle(model, N, H, M, near, n_check):
     from safe_control_b200 import BatchedMPCCBF, scenes
@@ -97,6 +98,26 @@ def test_mpc_superellipsoid_rows(model):
     ref = solve(plain, sc, sc["goal"])
     np.testing.assert_array_equal(out["U"][~flagged], ref["U"][~flagged])
     assert (ref["status"][flagged] == 3).all()                           # refused loudly without the flag
+
+
+def test_vtol2d_reference_horizon():
+    """VTOL2D at the reference's horizon 30 (mpc_cbf.py:41; 96 KB of workspace per agent): statuses are definite, inputs in
+    the box, predictions follow the kernel's own Euler map (x_{k+1}[0:3] = x_k[0:3] + dt x_k[3:6]), state bounds hold."""
+    from safe_control_b200 import BatchedMPCCBF, scenes
+    N, M = 300, 8
+    sc = scenes.make_scene("VTOL2D", N, M, seed=11)
+    ctrl = BatchedMPCCBF(sc["spec"], num_obs=M)
+    assert ctrl.horizon == 30 and ctrl.active_words == (30 * 8 + 2 * 30 * 4 + 5 * 30 + 63) // 64
+    out = solve(ctrl, sc, sc["goal"], want_active=True)
+    ok = out["status"] == 0
+    assert ok.mean() > 0.6, np.bincount(out["status"])
+    lb = np.array(list(ctrl.params.u_lb)); ub = np.array(list(ctrl.params.u_ub))
+    assert ((out["U"] >= lb - 1e-12) & (out["U"] <= ub + 1e-12)).all()
+    px = out["pred_x"][ok]
+    assert np.abs(px[:, 1:, 0:3] - (px[:, :-1, 0:3] + 0.05 * px[:, :-1, 3:6])).max() < 1e-11
+    pitch = ctrl.params.pitch_max * 3.14159 / 180
+    assert (np.abs(px[:, 1:, 3]) <= ctrl.params.v_max + 1e-7).all() and (px[:, 1:, 4] >= -ctrl.params.descent_speed_max - 1e-7).all()
+    assert (np.abs(px[:, 1:, 2]) <= pitch + 1e-7).all()
 
 
 def test_config5_share_full_size_properties():

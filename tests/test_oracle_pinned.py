@@ -114,7 +114,7 @@ def test_optimal_decay_matches_reference_end_to_end():
 # obstacle padding, input / state bounds, the rterm weights and the horizon.  do-mpc's transcription of these pieces
 # into the NLP (sum over stages + terminal cost, rterm on input increments) stays as documented in SURVEY.md 8a.
 MPC_ORACLE_MODELS = ("SingleIntegrator2D", "DynamicUnicycle2D", "KinematicBicycle2D", "KinematicBicycle2D_C3BF", "Quad3D",
-                     "DoubleIntegrator2D", "Quad2D", "Unicycle2D", "KinematicBicycle2D_DPCBF")
+                     "DoubleIntegrator2D", "Quad2D", "Unicycle2D", "KinematicBicycle2D_DPCBF", "VTOL2D")
 
 
 def test_mpc_statement_matches_reference():
@@ -135,7 +135,16 @@ def test_mpc_statement_matches_reference():
         assert float(d["lterm_is_mterm"][0]) == 1.0                       # terminal cost == stage cost expression
         np.testing.assert_array_equal(o.Rw.numpy(), d["R"][0])
         np.testing.assert_array_equal(o.u_lb, d["lb_u"][0]); np.testing.assert_array_equal(o.u_ub, d["ub_u"][0])
-        if o.has_vbound:                                                    # |x[3]| <= v_max, nothing else bounded
+        if spec["model"] == "VTOL2D":                                       # mpc_cbf.py:227-232
+            lbx = np.full(6, -np.inf); ubx = np.full(6, np.inf)
+            for i_, sgn, off in o.state_bounds:
+                if sgn < 0:
+                    ubx[i_] = off
+                else:
+                    lbx[i_] = -off
+            np.testing.assert_array_equal(d["ub_x"][0], ubx); np.testing.assert_array_equal(d["lb_x"][0], lbx)
+            assert len(o.state_bounds) == 5
+        elif o.has_vbound:                                                  # |x[3]| <= v_max, nothing else bounded
             v = o.spec["v_max"]
             np.testing.assert_array_equal(d["ub_x"][0], [np.inf, np.inf, np.inf, v])
             np.testing.assert_array_equal(d["lb_x"][0], [-np.inf, -np.inf, -np.inf, -v])
@@ -167,4 +176,4 @@ def test_mpc_statement_matches_reference():
                 x2 = tm.own_step(x1, u); h2 = tm.h(x2, ob)
                 c = (h2 - 2 * h1 + h0) + (p["alpha1"] + p["alpha2"]) * (h1 - h0) + p["alpha1"] * p["alpha2"] * h0
             np.testing.assert_allclose(c[0].numpy(), d["cbf"][i], rtol=1e-9, atol=1e-9, err_msg=f"{tag} probe {i}")
-    assert seen == 11
+    assert seen == 13
