@@ -347,7 +347,7 @@ SCB_HD void gi_solve2(double hd, double x0, double x1, const double (&r0)[RPL], 
         // z = hinv p, t = -sp / (hinv pp)  ->  x += t z = -(sp / pp) p
         const double step = -sp / pp;
         x0 = fma(step, p0, x0); x1 = fma(step, p1, x1);
-        a00 = p0; a01 = p1; w0 = bi; l0 = step * hd; k = 1;
+        a00 = p0; a01 = p1; w0 = bi; l0 = lp + step * hd; k = 1;      // (lp: dual steps already taken for this row while rows were dropped)
         done = true;
       } else if (k == 1) {
         // r = a0.p (|a0| = 1);  z = hinv (p - r a0);  z.p = hinv (pp - r^2)

@@ -134,3 +134,40 @@ def test_scene_inputs_match_oracle():
             assert k == len(rows)
             np.testing.assert_array_equal(sc["OBS"][i][:k], rows)
             assert np.all(sc["OBS"][i][k:] == scenes.DUMMY_OBS)
+
+
+def test_active_set_fuzz_near_degenerate_rows():
+    """Fuzz of the closed-form 2-variable active-set solver (scb_gi.cuh gi_solve2) on hand-made row geometries:
+    SingleIntegrator2D rows are A = 2 (p - o), b = alpha h, so obstacle placement controls the half-planes directly --
+    clusters of nearly parallel rows, rows that just touch the input box, wedges whose apex is the optimum (drop / re-add
+    sequences, where a re-added row keeps the dual steps it already took).  Everything must equal the exact enumeration
+    oracle: status, u to 1e-8, and the active mask wherever strict complementarity holds."""
+    rng = np.random.default_rng(2026)
+    N, M = 4000, 12
+    X = rng.uniform(-1, 1, (N, 2))
+    OBS = np.zeros((N, M, 7))
+    kind = rng.integers(0, 4, N)
+    for i in range(N):
+        base = rng.uniform(-np.pi, np.pi)
+        if kind[i] == 0:      # a fan of nearly parallel rows (angles within 1e-3 .. 1e-1 rad)
+            ang = base + rng.normal(0, 10.0 ** rng.uniform(-3, -1), M)
+        elif kind[i] == 1:    # a wedge: two clusters 60..170 degrees apart
+            half = rng.uniform(0.5, 1.5)
+            ang = base + np.where(rng.random(M) < 0.5, -half, half) + rng.normal(0, 0.02, M)
+        elif kind[i] == 2:    # surrounded (often infeasible)
+            ang = base + np.linspace(0, 2 * np.pi, M, endpoint=False) + rng.normal(0, 0.05, M)
+        else:
+            ang = rng.uniform(-np.pi, np.pi, M)
+        r = rng.uniform(0.2, 0.6, M)
+        gapd = 10.0 ** rng.uniform(-2.5, 0.3, M)                       # distance of the boundary beyond the barrier radius
+        if kind[i] == 2:                                               # already inside some barriers: b < 0, opposing rows
+            gapd = np.where(rng.random(M) < 0.4, -gapd * 0.2, gapd)
+        d = np.sqrt(1.01) * (r + 0.25) + gapd
+        OBS[i, :, 0] = X[i, 0] + d * np.cos(ang); OBS[i, :, 1] = X[i, 1] + d * np.sin(ang); OBS[i, :, 2] = r
+    nobs = rng.integers(1, M + 1, N).astype(np.int32)
+    head = rng.uniform(-np.pi, np.pi, N)
+    Uref = np.stack([np.cos(head), np.sin(head)], 1) * rng.uniform(0.2, 1.6, (N, 1))   # some beyond the box (v_max = 1)
+    p, spec = resolve_params({"model": "SingleIntegrator2D"}, "cbf_qp", lib=hostsim())
+    U, st, act = hs_cbfqp_solve(p, X, Uref, OBS, nobs)
+    stats = check_cbfqp(spec, M, X, Uref, OBS, nobs, U, st, act)
+    assert stats["infeasible"] > 50 and stats["cbf_active"] > 1500 and stats["masks_compared"] > 2000, stats
