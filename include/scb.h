@@ -114,6 +114,11 @@ typedef struct scb_params {
    * |x_dot| <= v_max, z_dot >= -descent_speed_max, |theta| <= pitch_max * 3.14159 / 180, pitch_max in degrees) */
   double S_wing, rho, C_L0, C_Lalpha, blend_M, alpha_0, C_Ldelta_e, C_D0, C_Dalpha, C_Ddelta_e, C_m0, C_malpha, C_mdelta_e,
          chord, k_front, k_rear, k_pusher, ell_f, ell_r, pitch_max, descent_speed_max;
+  int32_t od_mpc;         /* 1: optimal-decay MPC-CBF (position_control/optimal_decay_mpc_cbf.py): every stage has two more
+                             inputs omega1, omega2; the u_prev / Uref / U / pred_u arrays of scb_mpccbf_solve* then hold
+                             nu + 2 columns [u, omega1, omega2].  Set by scb_params_default(.., "optimal_decay_mpc_cbf"). */
+  int32_t od_sum_rterms;  /* optimal-decay MPC: 0 = do-mpc's assignment semantics of the two set_rterm calls (:178-185: the omega
+                             penalty replaces sum R_i u_i^2), 1 = both terms (the reference's evident intent).  UNPINNED. */
 } scb_params;
 
 typedef struct scb_ctx scb_ctx;   /* opaque: device staging buffers + stream for the *_host calls */
@@ -125,7 +130,7 @@ const char* scb_strerror(int err);
 int         scb_last_cuda_error(void);                 /* cudaError_t of the last SCB_ERR_CUDA on this thread */
 int         scb_device_count(void);
 /* Fill `p` with the reference's defaults for (model, controller); controller is one of
- * "cbf_qp", "optimal_decay_cbf_qp", "mpc_cbf".  Returns SCB_ERR_UNSUPPORTED for pairs the
+ * "cbf_qp", "optimal_decay_cbf_qp", "mpc_cbf", "optimal_decay_mpc_cbf".  Returns SCB_ERR_UNSUPPORTED for pairs the
  * reference has no branch for. */
 int         scb_params_default(scb_params* p, int model, const char* controller);
 int         scb_model_dims(int model, int* nx, int* nu);

@@ -393,9 +393,106 @@ class OracleMPCCBF:
                 if i not in grads:
                     grads[i] = torch.autograd.grad(g[i], zt, retain_graph=True)[0].numpy()
             A = np.stack([grads[i] for i in act], axis=1)
-            lam, _ = nnls(A, gradJ)
+            # multipliers: non-negative least squares on stationarity, with complementarity as a soft equation
+            # (10 g_i lam_i = 0: the same 10:1 weighting as the two acceptance thresholds).  Without it, nearly collinear rows
+            # (the same obstacle at consecutive stages) let NNLS shift multiplier mass onto a row that is 1e-3 away from
+            # its bound -- a KKT point then "violates" complementarity only because of how the checker chose lam.
+            gpos = np.maximum(gv[act], 0.0)
+            lam, _ = nnls(np.vstack([A, np.diag(10.0 * gpos)]), np.concatenate([gradJ, np.zeros(act.size)]))
             res = float(np.abs(gradJ - A @ lam).max())
-            comp = float(np.max(lam * np.maximum(gv[act], 0.0)))
+            comp = float(np.max(lam * gpos))
             if res <= res_tol * scale:
                 break
         return res, float(gv.min()), comp
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+OD_MPC_PARAM = {   # optimal_decay_mpc_cbf.py:28-50 (Q diag, R), 60-85 (alphas); omega0 = 1, p_sb = 10 (:87-90)
+    "DynamicUnicycle2D": dict(Q=[50, 50, 0.01, 30], R=[0.5, 0.5], alpha1=0.01, alpha2=0.01),
+    "KinematicBicycle2D": dict(Q=[50, 50, 1, 1], R=[0.5, 50.0], alpha1=0.05, alpha2=0.05),
+    "Quad2D": dict(Q=[25, 25, 50, 10, 10, 50], R=[0.5, 0.5], alpha1=0.15, alpha2=0.15),
+    "VTOL2D": dict(Q=[10, 10, 250, 10, 10, 50], R=[0.5, 0.5, 0.5, 50000.0], alpha1=0.35, alpha2=0.35),
+}
+
+
+class OracleODMPCCBF(OracleMPCCBF):
+    """Oracle restatement of OptimalDecayMPCCBF (TEST INFRASTRUCTURE): the MPC-CBF NLP above with two more inputs per
+    stage, omega1 and omega2 (optimal_decay_mpc_cbf.py:122-124), the bilinear row
+        dd_h + (alpha1 omega1 + alpha2 omega2) d_h + alpha1 alpha2 omega1 omega2 h_k >= 0            (:296-300)
+    for each of 5 obstacle slots (:271-280), horizon 10 (30 for VTOL2D, :24, 47) and an input cost evaluated at u_k (no
+    rate penalty): the reference hands do-mpc two expression rterms (:178-185), sum_i R_i u_i^2 and
+    p_sb1 (omega1 - 1)^2 + p_sb2 (omega2 - 1)^2.  `sum_rterms` False = do-mpc's assignment semantics (the second call
+    replaces the first), True = both.  The per-stage pieces are pinned by tests/golden/ref_odmpc_statement.npz
+    (gen_odmpc_from_reference.py); do-mpc's use of them is UNPINNED like the rest of its transcription.
+    (DynamicUnicycle2D: the reference itself raises IndexError at construction -- its agent_barrier_dt reads obs[6] of
+    the 5-column obstacle row; restated here with the circle branch that row can only mean.)"""
+
+    def __init__(self, robot_spec, sum_rterms=False, dt=0.05, horizon=None):
+        name = robot_spec["model"]
+        if name not in OD_MPC_PARAM:
+            raise ValueError(f"optimal_decay_mpc_cbf: {name} not restated")
+        MPC_PARAM_SAVE = MPC_PARAM.get(name)
+        MPC_PARAM[name] = dict(OD_MPC_PARAM[name])               # same ctor, this controller's weights / gains
+        try:
+            super().__init__(robot_spec, num_obs=5, horizon=horizon if horizon is not None else (30 if name == "VTOL2D" else 10), dt=dt)
+        finally:
+            MPC_PARAM[name] = MPC_PARAM_SAVE
+        self.nu_model = self.nu
+        self.nu = self.nu_model + 2
+        self.p_sb = (10.0, 10.0); self.omega0 = (1.0, 1.0)
+        self.sum_rterms = bool(sum_rterms)
+        self.u_range = np.concatenate([self.u_ub - self.u_lb, [1.0, 1.0]])
+        self.u_lb = np.concatenate([self.u_lb, [-np.inf, -np.inf]]); self.u_ub = np.concatenate([self.u_ub, [np.inf, np.inf]])
+        ra = list(self.par["R"]) if self.sum_rterms else [0.0] * self.nu_model
+        self.Ra = torch.tensor(ra + list(self.p_sb), dtype=torch.float64)
+        self.ut = torch.tensor([0.0] * self.nu_model + list(self.omega0), dtype=torch.float64)
+
+    def cost(self, w, goal_full, u_prev):
+        x, u = self.split(w)
+        e = x - goal_full[None]
+        d = u - self.ut[None]
+        return (e * e * self.Q[None]).sum() + (d * d * self.Ra[None]).sum()
+
+    def eq(self, w, x0):
+        x, u = self.split(w)
+        return torch.cat([(x[0] - x0), (x[1:] - self.tm.euler(x[:-1], u[:, : self.nu_model])).reshape(-1)])
+
+    def cbf(self, w, obs):
+        x, u = self.split(w)
+        xk, ur, o1, o2 = x[:-1], u[:, : self.nu_model], u[:, self.nu_model:self.nu_model + 1], u[:, self.nu_model + 1:]
+        tm, p = self.tm, self.par
+        x1 = tm.own_step(xk, ur); x2 = tm.own_step(x1, ur)
+        h0, h1, h2 = tm.h(xk, obs), tm.h(x1, obs), tm.h(x2, obs)
+        a1, a2 = p["alpha1"], p["alpha2"]
+        return ((h2 - 2 * h1 + h0) + (a1 * o1 + a2 * o2) * (h1 - h0) + a1 * a2 * h0 * o1 * o2).reshape(-1)
+
+    def rollout(self, x_init, u_seq):
+        return super().rollout(x_init, u_seq[:, : self.nu_model])
+
+    def condensed(self, x_init, goal, u_prev, obs, z):
+        H, nu, nm = self.H, self.nu, self.nu_model
+        u = z.reshape(H, nu)
+        x = self.rollout(x_init, u)
+        g = torch.zeros(self.nx); gl = torch.as_tensor(np.asarray(goal, float).reshape(-1)); g[: gl.numel()] = gl
+        w = torch.cat([x.reshape(-1), u.reshape(-1)])
+        J = self.cost(w, g, None)
+        parts = [self.cbf(w, self.pad_obs(obs)),
+                 (torch.as_tensor(self.u_ub[:nm])[None] - u[:, :nm]).reshape(-1), (u[:, :nm] - torch.as_tensor(self.u_lb[:nm])[None]).reshape(-1)]
+        parts += [sgn * x[1:, i] + off for i, sgn, off in self.state_bounds]
+        return J, torch.cat(parts)
+
+    def kernel_bit_of_row(self, r):
+        H, M, nm = self.H, self.M, self.nu_model
+        if r < H * M:
+            return r
+        r -= H * M
+        if r < H * nm:
+            k, i = divmod(r, nm)
+            return H * M + k * 2 * nm + 2 * i
+        r -= H * nm
+        if r < H * nm:
+            k, i = divmod(r, nm)
+            return H * M + k * 2 * nm + 2 * i + 1
+        r -= H * nm
+        kind, k = divmod(r, H)
+        return H * M + 2 * H * nm + k * len(self.state_bounds) + kind

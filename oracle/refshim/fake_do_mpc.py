@@ -70,6 +70,7 @@ class MPC:
         self.settings = _Settings()
         self.params, self.bounds, self.nl_cons = {}, _Bounds(), {}
         self.objective, self.rterm, self.tvp_fun = {}, {}, None
+        self.rterm_calls = []
         self.x0 = None
         LAST["mpc"] = self
 
@@ -79,8 +80,12 @@ class MPC:
     def set_objective(self, mterm=None, lterm=None):
         self.objective = dict(mterm=np.array(mterm, dtype=float), lterm=np.array(lterm, dtype=float))
 
-    def set_rterm(self, **kw):
-        self.rterm = {k: np.array(v, dtype=float) for k, v in kw.items()}
+    def set_rterm(self, expr=None, **kw):
+        """keyword form (mpc_cbf.py:180: set_rterm(u=R)) or expression form (optimal_decay_mpc_cbf.py:184-185, called twice):
+        every call is recorded in order; what do-mpc does with repeated expression calls is NOT modelled here."""
+        if expr is not None:
+            self.rterm_calls.append(float(np.asarray(expr, dtype=float).reshape(-1)[0]))
+        self.rterm.update({k: np.array(v, dtype=float) for k, v in kw.items()})
 
     def set_nl_cons(self, name, expr, ub=None, **kw):
         self.nl_cons[name] = (float(np.asarray(expr, dtype=float).reshape(-1)[0]), ub)

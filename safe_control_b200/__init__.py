@@ -6,9 +6,10 @@ independent agents.  Host code is Python over torch CUDA tensors; all arithmetic
 runs in hand-written sm_100a kernels behind the C ABI in include/scb.h.
 """
 from .params import resolve_params, NotCompatibleError  # noqa: F401
-from .batched import BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, HostContext  # noqa: F401
+from .batched import (BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, BatchedOptimalDecayMPCCBF,  # noqa: F401
+                      HostContext)
 from .tracking import BatchedTrackingController  # noqa: F401
 from ._abi import MODEL_IDS, OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL  # noqa: F401
 
-__all__ = ["BatchedTrackingController", "BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "HostContext", "resolve_params",
+__all__ = ["BatchedTrackingController", "BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "BatchedOptimalDecayMPCCBF", "HostContext", "resolve_params",
            "NotCompatibleError", "MODEL_IDS", "OPTIMAL", "INFEASIBLE", "MAXITER", "NUMERICAL"]

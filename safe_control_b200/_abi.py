@@ -41,6 +41,7 @@ class ScbParams(C.Structure):
         ("C_Ddelta_e", C.c_double), ("C_m0", C.c_double), ("C_malpha", C.c_double), ("C_mdelta_e", C.c_double),
         ("chord", C.c_double), ("k_front", C.c_double), ("k_rear", C.c_double), ("k_pusher", C.c_double),
         ("ell_f", C.c_double), ("ell_r", C.c_double), ("pitch_max", C.c_double), ("descent_speed_max", C.c_double),
+        ("od_mpc", C.c_int32), ("od_sum_rterms", C.c_int32),
     ]
 
 

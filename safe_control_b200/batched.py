@@ -208,6 +208,18 @@ class BatchedMPCCBF(_Base):
         return out
 
 
+class BatchedOptimalDecayMPCCBF(BatchedMPCCBF):
+    """N optimal-decay MPC-CBF problems (position_control/optimal_decay_mpc_cbf.py): omega1, omega2 are two extra inputs of
+    every stage, so u_prev / U_ref / U / pred_u carry nu + 2 columns [u, omega1, omega2] (`self.nu` is that width,
+    `self.nu_model` the robot's own).  The reference fixes 5 obstacle slots (:125, 271-280) and horizon 10 (30 for VTOL2D)."""
+    controller = "optimal_decay_mpc_cbf"
+
+    def __init__(self, robot_spec, num_obs=5, dt=0.05, horizon=None):
+        super().__init__(robot_spec, num_obs, dt, horizon)
+        self.nu_model = self.nu
+        self.nu = self.nu_model + 2
+
+
 class HostContext:
     """Host-buffer (numpy) entry points: H2D + kernel + D2H inside one C call.
     This is the path a reference-side binding uses and what bench.py's e2e times.
@@ -308,6 +320,8 @@ class HostContext:
                      want_active=False):
         N = X.shape[0]
         nx, nu = self._dims(params)
+        if int(params.od_mpc):
+            nu += 2                                             # optimal decay: [u, omega1, omega2]
         ng = 3 if int(params.model) == _abi.MODEL_IDS["Quad3D"] else 2
         X = self._np(X, np.float64, "X", (N, nx)); goal = self._np(goal, np.float64, "goal", (N, ng))
         u_prev = self._np(u_prev, np.float64, "u_prev", (N, nu)); OBS, stride = self._obs(OBS, N, M)

@@ -23,8 +23,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 # scb_model ids with an MPC kernel (include/scb.h): all but Manipulator2D; 100 + id = the general-row variants of SI / DU / DI
-# for superellipsoid obstacles
-MPC_MODELS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 100, 101, 105]
+# for superellipsoid obstacles; 200 + id = the optimal-decay MPC variants (omega1, omega2 as stage inputs)
+MPC_MODELS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 100, 101, 105, 201, 202, 206, 210]
 
 
 def _units(single_tu):

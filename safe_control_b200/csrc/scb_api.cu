@@ -22,6 +22,10 @@ SCB_MPC_INSTANTIATE(SCB_UNICYCLE_2D)
 SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
 SCB_MPC_INSTANTIATE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
 SCB_MPC_INSTANTIATE(SCB_VTOL_2D)
+SCB_MPC_INSTANTIATE(kMpcOdBase + SCB_DYNAMIC_UNICYCLE_2D)
+SCB_MPC_INSTANTIATE(kMpcOdBase + SCB_KINEMATIC_BICYCLE_2D)
+SCB_MPC_INSTANTIATE(kMpcOdBase + SCB_QUAD_2D)
+SCB_MPC_INSTANTIATE(kMpcOdBase + SCB_VTOL_2D)
 SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
 SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
 SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
@@ -782,6 +786,7 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
   CK(cudaSetDevice(c->device));
   int nx = 0, nu = 0;
   if (scb_model_dims(p->model, &nx, &nu) != SCB_OK) return SCB_ERR_BAD_ARG;      // sizes from the validated model id
+  if (p->od_mpc) nu += 2;                                  // optimal decay: [u, omega1, omega2] per stage
   const int ng = (p->model == SCB_QUAD_3D) ? 3 : 2;
   const int aw = active ? scb_mpc_active_words(p, M, H) : 0;
   if (aw < 0) return aw;

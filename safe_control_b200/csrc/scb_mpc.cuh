@@ -29,6 +29,8 @@
 // all scratch lives in a per-agent workspace (shared memory on the device).
 #pragma once
 
+#include <type_traits>
+
 #include "scb_jet.cuh"
 
 namespace scb {
@@ -357,6 +359,60 @@ struct MpcModel<SCB_VTOL_2D> {
   }
 };
 
+// ---- optimal-decay MPC-CBF (position_control/optimal_decay_mpc_cbf.py) ---------------------------------------------
+// Same dynamics / state cost / bounds as MPC-CBF, plus two extra STAGE INPUTS omega1, omega2 (:122-124) that scale the
+// class-K gains of the relative-degree-2 discrete CBF row (:296-300):
+//     dd_h + (alpha1 omega1 + alpha2 omega2) d_h + alpha1 alpha2 omega1 omega2 h_k >= 0,
+// and an input cost that is NOT a rate penalty: the reference passes do-mpc two expression rterms (:178-185),
+// sum_i R_i u_i^2 and p_sb1 (omega1 - 1)^2 + p_sb2 (omega2 - 1)^2, evaluated at u_k (see MpcSolver::Ra / ut).
+// The row weights depend on the stage inputs, so every (stage, obstacle) row goes through the general-row jets with the
+// omegas riding along in the (otherwise unused) heading slots of the barrier states.  Inputs of the NLP per stage:
+// [u (NUB, bounded), omega1, omega2 (unbounded)].
+constexpr int kMpcOdBase = 200;
+template <int BASE>
+struct MpcModelOD : MpcModel<BASE> {
+  using B = MpcModel<BASE>;
+  static_assert(B::REL == 2 && !B::LINEAR, "optimal-decay rows exist for the relative-degree-2 models");
+  static constexpr int NX = B::NX, NUB = B::NU, NU = B::NU + 2, NY = NX + NU, NPT = 3;
+  static constexpr bool GENERAL = true, OD = true;
+  template <class T, class TR>
+  static SCB_HD void stage(const scb_params& p, const double* aux, const T* y, T* F, T& P1, T& Q1, T& P2, T& Q2, TR& trig) {
+    B::stage(p, aux, y, F, P1, Q1, P2, Q2, trig);          // (the base map reads y[0 .. NX + NUB) only)
+  }
+  template <class T, class TR>
+  static SCB_HD void states(const scb_params& p, const T* y, T* F, T (*S)[NX], T* SN, T* CS, TR& trig) {
+    T P1, Q1, P2, Q2;
+    B::stage(p, nullptr, y, F, P1, Q1, P2, Q2, trig);
+#pragma unroll
+    for (int i = 0; i < NPT; ++i) {
+#pragma unroll
+      for (int c = 0; c < NX; ++c) jconst(S[i][c], 0.0);
+      jconst(SN[i], 0.0); jconst(CS[i], 0.0);
+    }
+    S[0][0] = y[0]; S[0][1] = y[1];
+    S[1][0] = P1; S[1][1] = Q1;
+    S[2][0] = P2; S[2][1] = Q2;
+    SN[0] = y[NX + NUB]; CS[0] = y[NX + NUB + 1];          // omega1, omega2
+  }
+  template <class T>
+  static SCB_HD void hfun(const scb_params& p, const T* s, const T&, const T&, const double* ob, T& h) {
+    T dx, dy, t;
+    jaddc(dx, s[0], -ob[0]); jaddc(dy, s[1], -ob[1]);
+    const double d = ob[2] + p.radius;
+    jmul(h, dx, dx); jmul(t, dy, dy); jadd(h, h, t); jaddc(h, h, -B::beta() * d * d);
+  }
+};
+template <> struct MpcModel<kMpcOdBase + SCB_DYNAMIC_UNICYCLE_2D> : MpcModelOD<SCB_DYNAMIC_UNICYCLE_2D> {};
+template <> struct MpcModel<kMpcOdBase + SCB_KINEMATIC_BICYCLE_2D> : MpcModelOD<SCB_KINEMATIC_BICYCLE_2D> {};
+template <> struct MpcModel<kMpcOdBase + SCB_QUAD_2D> : MpcModelOD<SCB_QUAD_2D> {};
+template <> struct MpcModel<kMpcOdBase + SCB_VTOL_2D> : MpcModelOD<SCB_VTOL_2D> {};
+
+// number of BOUNDED inputs (the first NUB of the NU stage inputs) and the optimal-decay flag, with defaults
+template <class Mod, class = void> struct MpcNub { static constexpr int value = Mod::NU; };
+template <class Mod> struct MpcNub<Mod, std::void_t<decltype(Mod::NUB)>> { static constexpr int value = Mod::NUB; };
+template <class Mod, class = void> struct MpcOd { static constexpr bool value = false; };
+template <class Mod> struct MpcOd<Mod, std::void_t<decltype(Mod::OD)>> { static constexpr bool value = Mod::OD; };
+
 // state-bound rows of the MPC per node k = 1..H (mpc_cbf.py:193-199, 205-211: |x[3]| <= v_max for the unicycle / bicycle
 // models; :227-232 for VTOL2D): row r of a node is  sgn * x[var] + off >= 0
 template <class Mod>
@@ -503,6 +559,9 @@ struct MpcModel<SCB_QUAD_3D> {
   }
 };
 
+template <>
+struct MpcStateBounds<MpcModel<kMpcOdBase + SCB_VTOL_2D>> : MpcStateBounds<MpcModel<SCB_VTOL_2D>> {};
+
 // ---------------------------------------------------------------------------------------------
 // workspace layout (in doubles), computed identically on host and device
 struct MpcLayout {
@@ -522,7 +581,7 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
   constexpr bool VBOUND = Mod::VBOUND, LINEAR = Mod::LINEAR, GENERAL = Mod::GENERAL;
   constexpr int NY = NX + NU, NH = NY * (NY + 1) / 2;
   MpcLayout L;
-  L.H = H; L.M = M; L.n = H * NU; L.NS = 2 * H * NU + MpcStateBounds<Mod>::NSB * H;
+  L.H = H; L.M = M; L.n = H * NU; L.NS = 2 * H * MpcNub<Mod>::value + MpcStateBounds<Mod>::NSB * H;
   int o = 0;
   auto take = [&](int cnt) { int r = o; o += cnt; return r; };
   L.X = take((H + 1) * NX);  L.Z = take(H * NU);
@@ -556,22 +615,22 @@ SCB_HD MpcLayout mpc_layout(int H, int M) {
 // words of the MPC active mask (include/scb.h scb_mpc_active_words): H*M CBF rows, then the NS simple bounds
 template <class Mod>
 SCB_HD int mpc_active_words(int H, int M) {
-  return (H * M + 2 * H * Mod::NU + MpcStateBounds<Mod>::NSB * H + 63) / 64;
+  return (H * M + 2 * H * MpcNub<Mod>::value + MpcStateBounds<Mod>::NSB * H + 63) / 64;
 }
 
 // simple (bound) constraint q:  g_q = sgn * y_k[var] + off >= 0
 struct SimpleCon { int k, var; double sgn, off; };
 template <class Mod>
 SCB_HD SimpleCon decode_simple(const scb_params& p, int H, int q) {
-  constexpr int NX = Mod::NX, NU = Mod::NU, NSB = MpcStateBounds<Mod>::NSB;
+  constexpr int NX = Mod::NX, NUB = MpcNub<Mod>::value, NSB = MpcStateBounds<Mod>::NSB;
   SimpleCon c;
-  if (q < 2 * H * NU) {
-    c.k = q / (2 * NU);
-    const int r = q - c.k * 2 * NU, i = r >> 1;
+  if (q < 2 * H * NUB) {
+    c.k = q / (2 * NUB);
+    const int r = q - c.k * 2 * NUB, i = r >> 1;
     c.var = NX + i;
     if (r & 1) { c.sgn = 1.0; c.off = -p.u_lb[i]; } else { c.sgn = -1.0; c.off = p.u_ub[i]; }
   } else {
-    const int t = q - 2 * H * NU, nsb = NSB > 0 ? NSB : 1;
+    const int t = q - 2 * H * NUB, nsb = NSB > 0 ? NSB : 1;
     c.k = 1 + t / nsb;
     MpcStateBounds<Mod>::get(p, t - (c.k - 1) * nsb, c.var, c.sgn, c.off);
   }
@@ -650,6 +709,8 @@ struct MpcSolver {
   using G = Grp<LANES>;
   static constexpr int NX = Mod::NX, NU = Mod::NU, NY = Mod::NY, NH = NY * (NY + 1) / 2;
   static constexpr int NPT = Mod::REL + 1;     // barrier states per stage (general rows)
+  static constexpr int NUB = MpcNub<Mod>::value;          // bounded inputs (optimal decay: omega1, omega2 follow, unbounded)
+  static constexpr bool OD = MpcOd<Mod>::value;
 
   const scb_params& p;
   const MpcLayout& L;
@@ -659,6 +720,12 @@ struct MpcSolver {
   double goal[NX];
   double uprev[NU];
   double Qs[NX], Rs[NU];        // cost weights times the objective scaling factor (IPOPT-style gradient-based scaling)
+  // optimal decay only: the input cost is sum_i Ra_i (u_i - ut_i)^2 at every stage instead of the input-RATE penalty --
+  // the two expression rterms of optimal_decay_mpc_cbf.py:178-185.  do-mpc's MPC.set_rterm ASSIGNS the expression, so the
+  // second call (the omega penalty) replaces the first (sum R_i u_i^2): Ra = [0 ..., p_sb1, p_sb2], ut = [0 ..., omega1_0,
+  // omega2_0].  scb_params.od_sum_rterms = 1 keeps both terms (the evident intent of the reference).  UNPINNED: do-mpc is
+  // not installable here.
+  double Ra[NU], ut[NU];
   bool gauss_newton;            // assemble stage Hessians without the (possibly indefinite) curvature terms
   double floor_cur;             // slack floor mu / nu of the current iteration (general rows re-derive their weights)
 
@@ -673,7 +740,13 @@ struct MpcSolver {
 #pragma unroll
     for (int i = 0; i < NX; ++i) Qs[i] = p.Q[i];
 #pragma unroll
-    for (int i = 0; i < NU; ++i) Rs[i] = p.R[i];
+    for (int i = 0; i < NU; ++i) { Rs[i] = (!OD && i < 4) ? p.R[i] : 0.0; Ra[i] = 0.0; ut[i] = 0.0; }
+    if constexpr (OD) {
+#pragma unroll
+      for (int i = 0; i < NUB; ++i) Ra[i] = (p.od_sum_rterms && i < 4) ? p.R[i] : 0.0;
+      Ra[NUB] = p.p_sb1; ut[NUB] = p.omega1_0;
+      Ra[NUB + 1] = p.p_sb2; ut[NUB + 1] = p.omega2_0;
+    }
     gauss_newton = false; floor_cur = 0.0;
   }
 
@@ -707,6 +780,7 @@ struct MpcSolver {
       for (int i = 0; i < NU; ++i) {
         const double d = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]);
         Jc = fma(Rs[i] * d, d, Jc);
+        if constexpr (OD) { const double e = z[k * NU + i] - ut[i]; Jc = fma(Ra[i] * e, e, Jc); }
       }
       double y[NY], F[NX], a, b, c, d;
 #pragma unroll
@@ -727,6 +801,21 @@ struct MpcSolver {
   // c = sum_i w_i h(S_i; o_j):  (w0, w1) = (alpha - 1, 1) for relative degree 1, (w0, w1, w2) for 2 (mpc_cbf.py:312-321)
   template <class T>
   SCB_HD void general_row(const T (*S)[NX], const T* SN, const T* CS, const double* ob, T& c) const {
+    if constexpr (OD) {
+      // dd_h + (alpha1 omega1 + alpha2 omega2) d_h + alpha1 alpha2 omega1 omega2 h_k   (optimal_decay_mpc_cbf.py:296-300)
+      T h0, h1, h2, sg, tt, dh, ddh, tmp;
+      Mod::hfun(p, S[0], SN[0], CS[0], ob, h0);
+      Mod::hfun(p, S[1], SN[1], CS[1], ob, h1);
+      Mod::hfun(p, S[2], SN[2], CS[2], ob, h2);
+      const T& o1 = SN[0]; const T& o2 = CS[0];
+      jscale(sg, o1, p.alpha1); jaxpy(sg, sg, p.alpha2, o2);
+      jmul(tt, o1, o2); jscale(tt, tt, p.alpha1 * p.alpha2);
+      jaxpy(dh, h1, -1.0, h0);
+      jaxpy(ddh, h2, -2.0, h1); jadd(ddh, ddh, h0);
+      jmul(tmp, sg, dh); jadd(c, ddh, tmp);
+      jmul(tmp, tt, h0); jadd(c, c, tmp);
+      return;
+    }
     T h0, h1;
     Mod::hfun(p, S[0], SN[0], CS[0], ob, h0);
     Mod::hfun(p, S[1], SN[1], CS[1], ob, h1);
@@ -932,6 +1021,7 @@ struct MpcSolver {
       const double um = (k == 0) ? uprev[i] : z[(k - 1) * NU + i];
       double g = 2.0 * Rs[i] * (z[t] - um);
       if (k + 1 < H) g -= 2.0 * Rs[i] * (z[(k + 1) * NU + i] - z[t]);
+      if constexpr (OD) g += 2.0 * Ra[i] * (z[t] - ut[i]);
       out[t] = g;
     }
     sync();
@@ -1205,6 +1295,12 @@ struct MpcSolver {
 #pragma unroll
       for (int i = 0; i < NU; ++i) if (i == ub) rr = 2.0 * Rs[i];
       v += ((b >= NXT) == (c >= NXT)) ? rr : -rr;
+      if constexpr (OD) {
+        if (b == c && b >= NXT) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) if (i == ub) v += 2.0 * Ra[i];
+        }
+      }
     }
     if (b == c && b >= NXT) v += delta;
     return v;
@@ -1221,6 +1317,12 @@ struct MpcSolver {
       for (int i = 0; i < NU; ++i)
         if (i == ub) { rr = 2.0 * Rs[i]; du = z[k * NU + i] - (k == 0 ? uprev[i] : z[(k - 1) * NU + i]); }
       v += (b >= NXT) ? rr * du : -rr * du;
+      if constexpr (OD) {
+        if (b >= NXT) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) if (i == ub) v += 2.0 * Ra[i] * (z[k * NU + i] - ut[i]);
+        }
+      }
     }
     return v;
   }
@@ -1453,10 +1555,11 @@ struct MpcSolver {
       const int i = t % NU;
       double lb = 0.0, ub = 0.0, u0 = 0.0;
 #pragma unroll
-      for (int m = 0; m < NU; ++m) if (m == i) { lb = p.u_lb[m]; ub = p.u_ub[m]; u0 = uprev[m]; }
+      for (int m = 0; m < NU; ++m) if (m == i) { u0 = uprev[m]; if (m < NUB && m < 4) { lb = p.u_lb[m]; ub = p.u_ub[m]; } }
       const double pl = fmin(1e-2 * fmax(1.0, fabs(lb)), 1e-2 * (ub - lb));
       const double pu = fmin(1e-2 * fmax(1.0, fabs(ub)), 1e-2 * (ub - lb));
-      w[L.Z + t] = push_start ? fmax(lb + pl, fmin(u0, ub - pu)) : u0;    // (false: the statement probes of the tests)
+      // (push_start false: the statement probes of the tests; the unbounded omegas start where they are)
+      w[L.Z + t] = (push_start && i < NUB) ? fmax(lb + pl, fmin(u0, ub - pu)) : u0;
     }
     SCB_LANE_UNROLL
     for (int i = lane; i < NX; i += LANES) { w[L.X + i] = ld(x0 + i); w[L.XT + i] = w[L.X + i]; }
@@ -1494,7 +1597,7 @@ struct MpcSolver {
 #pragma unroll
       for (int i = 0; i < NX; ++i) Qs[i] *= sf;
 #pragma unroll
-      for (int i = 0; i < NU; ++i) Rs[i] *= sf;
+      for (int i = 0; i < NU; ++i) { Rs[i] *= sf; Ra[i] *= sf; }
       Jcur *= sf;
       sync();
     }
@@ -1688,6 +1791,7 @@ struct MpcSolver {
       int bt = 0;
       SCB_LOOP
       for (; bt < 20; ++bt) {
+        sync();                                     // every lane is done reading the previous trial point (merit terms)
         SCB_LANE_UNROLL
         for (int t = lane; t < n; t += LANES) w[L.ZT + t] = fma(alpha, w[L.DZ + t], w[L.Z + t]);
         sync();
@@ -1759,7 +1863,7 @@ struct MpcSolver {
       for (int i = 0; i < NU; ++i) {
         double v = w[L.Z + i];
         if (!(v == v)) v = uprev[i];
-        U[i] = fmin(fmax(v, p.u_lb[i]), p.u_ub[i]);
+        U[i] = (i < NUB && i < 4) ? fmin(fmax(v, p.u_lb[i]), p.u_ub[i]) : v;
       }
       if (st == SCB_MAXITER && err > 1e-4) {
         // distinguish "did not converge" from "locally infeasible" by the primal residual

@@ -62,6 +62,16 @@ inline int mpc_launch(const scb_params& p, int N, int M, int H, const MpcIO& io,
     if (cudaMemsetAsync(counter, 0, kMpcWsHead * sizeof(int), s) != cudaSuccess) return SCB_ERR_CUDA;
   }
 #define SCB_GO(FN, MODEL) case MODEL: return FN<MODEL>(p, N, M, H, io, counter, workspace, workspace_bytes, s, sm_count, count_only);
+  if (p.od_mpc) {                       // optimal-decay MPC-CBF: omega1, omega2 as extra stage inputs (scb_mpc.cuh MpcModelOD)
+    constexpr int kOd = 200;            // == kMpcOdBase
+    switch (p.model) {
+      case SCB_DYNAMIC_UNICYCLE_2D: return mpc_launch_m<kOd + SCB_DYNAMIC_UNICYCLE_2D>(p, N, M, H, io, counter, workspace, workspace_bytes, s, sm_count, count_only);
+      case SCB_KINEMATIC_BICYCLE_2D: return mpc_launch_m<kOd + SCB_KINEMATIC_BICYCLE_2D>(p, N, M, H, io, counter, workspace, workspace_bytes, s, sm_count, count_only);
+      case SCB_QUAD_2D: return mpc_launch_m<kOd + SCB_QUAD_2D>(p, N, M, H, io, counter, workspace, workspace_bytes, s, sm_count, count_only);
+      case SCB_VTOL_2D: return mpc_launch_m<kOd + SCB_VTOL_2D>(p, N, M, H, io, counter, workspace, workspace_bytes, s, sm_count, count_only);
+      default: return SCB_ERR_UNSUPPORTED;     // optimal_decay_mpc_cbf.py:19-20 (Quad3D: see include/scb.h)
+    }
+  }
   switch (p.model) {
     SCB_GO(mpc_launch_se, SCB_SINGLE_INTEGRATOR_2D)
     SCB_GO(mpc_launch_se, SCB_DYNAMIC_UNICYCLE_2D)

@@ -77,7 +77,8 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
   if (scb_model_dims(model, &nx, &nu) != SCB_OK) return SCB_ERR_BAD_ARG;
   const bool qp = strcmp(controller, "cbf_qp") == 0;
   const bool od = strcmp(controller, "optimal_decay_cbf_qp") == 0;
-  const bool mpc = strcmp(controller, "mpc_cbf") == 0;
+  const bool odm = strcmp(controller, "optimal_decay_mpc_cbf") == 0;
+  const bool mpc = strcmp(controller, "mpc_cbf") == 0 || odm;
   if (!qp && !od && !mpc) return SCB_ERR_BAD_ARG;
   p->model = model; p->nx = nx; p->nu = nu;
   p->dt = 0.05;
@@ -176,6 +177,20 @@ int scb_params_default(scb_params* p, int model, const char* controller) {
       for (int i = 0; i < 12; ++i) p->Q[i] = Q[i];
       p->alpha = 0.15;
       break;
+    }
+  }
+  if (odm) {
+    // optimal_decay_mpc_cbf.py:19-20 admits DynamicUnicycle2D, KinematicBicycle2D, Quad2D, Quad3D, VTOL2D; built here are the
+    // relative-degree-2 ones, where the omegas enter the CBF row (:296-300).  (Quad3D's row has no omega, :292-295.)
+    if (model != SCB_DYNAMIC_UNICYCLE_2D && model != SCB_KINEMATIC_BICYCLE_2D && model != SCB_QUAD_2D && model != SCB_VTOL_2D)
+      return SCB_ERR_UNSUPPORTED;
+    p->od_mpc = 1; p->od_sum_rterms = 0;
+    p->omega1_0 = p->omega2_0 = 1.0; p->p_sb1 = p->p_sb2 = 10.0;                   // :87-90
+    switch (model) {                                                               // gains :60-85, weights :28-50
+      case SCB_DYNAMIC_UNICYCLE_2D: p->alpha1 = p->alpha2 = 0.01; break;
+      case SCB_KINEMATIC_BICYCLE_2D: p->alpha1 = p->alpha2 = 0.05; p->R[1] = 50.0; break;
+      case SCB_QUAD_2D: p->alpha1 = p->alpha2 = 0.15; break;
+      case SCB_VTOL_2D: p->alpha1 = p->alpha2 = 0.35; break;
     }
   }
   return SCB_OK;

@@ -12,7 +12,7 @@ import math
 
 from ._abi import MODEL_IDS, ScbParams, ERR_UNSUPPORTED
 
-CONTROLLERS = ("cbf_qp", "optimal_decay_cbf_qp", "mpc_cbf")
+CONTROLLERS = ("cbf_qp", "optimal_decay_cbf_qp", "mpc_cbf", "optimal_decay_mpc_cbf")
 
 
 class NotCompatibleError(Exception):
@@ -76,7 +76,7 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
         s.setdefault("ax_max", a); s.setdefault("ay_max", a); s.setdefault("w_max", 0.5)
         p.u_lb[0] = p.u_lb[1] = -a                              # cbf_qp.py:66-69 bounds both inputs by a_max
         p.u_ub[0] = p.u_ub[1] = a
-        if controller == "mpc_cbf":                             # mpc_cbf.py:200-204 uses ax_max / ay_max
+        if controller in ("mpc_cbf", "optimal_decay_mpc_cbf"):   # mpc_cbf.py:200-204 uses ax_max / ay_max
             ax, ay = float(s["ax_max"]), float(s["ay_max"])
             p.u_lb[0], p.u_ub[0], p.u_lb[1], p.u_ub[1] = -ax, ax, -ay, ay
         p.v_max = v; p.v_min = -v
@@ -120,6 +120,12 @@ def resolve_params(robot_spec, controller, dt=0.05, lib=None):
         if model not in ("SingleIntegrator2D", "DynamicUnicycle2D", "DoubleIntegrator2D"):
             raise ValueError(f"{model} has no superellipsoid branch in its agent_barrier_dt")
         p.mpc_superellipsoid = 1
+    if controller == "optimal_decay_mpc_cbf":                  # ours: which of the two do-mpc rterm readings (include/scb.h)
+        p.od_sum_rterms = int(bool(s.get("od_sum_rterms", False)))
+        if model == "VTOL2D":
+            s["mpc_horizon"] = 30                               # optimal_decay_mpc_cbf.py:47 (hard-wired, like 10 for the others)
+        else:
+            s["mpc_horizon"] = int(s.get("od_mpc_horizon", 10))  # :24 ignores robot_spec['mpc_horizon']
     if "mpc_max_iter" in s:
         p.mpc_max_iter = int(s["mpc_max_iter"])
     if "mpc_tol" in s:
@@ -135,4 +141,6 @@ def cbf_param_dict(p, controller, model):
         d.update(omega1=p.omega1_0, p_sb1=p.p_sb1)
         if rel2:
             d.update(omega2=p.omega2_0, p_sb2=p.p_sb2)
+    if controller == "optimal_decay_mpc_cbf":                  # optimal_decay_mpc_cbf.py:87-90
+        d.update(omega1=p.omega1_0, p_sb1=p.p_sb1, omega2=p.omega2_0, p_sb2=p.p_sb2)
     return d

@@ -3,3 +3,4 @@
 from .cbf_qp import CBFQP  # noqa: F401
 from .optimal_decay_cbf_qp import OptimalDecayCBFQP, NotCompatibleError  # noqa: F401
 from .mpc_cbf import MPCCBF  # noqa: F401
+from .optimal_decay_mpc_cbf import OptimalDecayMPCCBF  # noqa: F401

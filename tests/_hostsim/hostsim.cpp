@@ -110,7 +110,7 @@ int hostsim_odcbf_solve(const scb_params* p, int N, int M, const double* X, cons
 int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double* X, const double* goal,
                          const double* u_prev, const double* OBS, long stride, const int32_t* nobs, double* U,
                          int32_t* status, double* pred_x, double* pred_u, int32_t* iters, double* kkt, uint64_t* active) {
-  const int nx = p->nx, nu = p->nu;
+  const int nx = p->nx, nu = p->nu + (p->od_mpc ? 2 : 0);
   const int aw = active ? scb_mpc_active_words(p, M, H) : 0;
   for (int i = 0; i < N; ++i) {
     const int no = nobs ? nobs[i] : M;
@@ -121,6 +121,7 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
     if (model == SCB_SINGLE_INTEGRATOR_2D || model == SCB_DYNAMIC_UNICYCLE_2D || model == SCB_DOUBLE_INTEGRATOR_2D)
       for (int j = 0; j < no && j < M; ++j)
         if (OBS[(size_t)i * stride + j * 7 + 6] >= 0.5) { model = kMpcSeBase + p->model; break; }
+    if (p->od_mpc) model = kMpcOdBase + p->model;             // optimal decay: nu = model inputs + 2 (omega1, omega2)
     switch (model) {
 #define MPCCASE(MODEL)                                                                                          \
   case MODEL: {                                                                                                 \
@@ -144,6 +145,10 @@ int hostsim_mpccbf_solve(const scb_params* p, int N, int M, int H, const double*
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
       MPCCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
       MPCCASE(SCB_VTOL_2D)
+      MPCCASE(kMpcOdBase + SCB_DYNAMIC_UNICYCLE_2D)
+      MPCCASE(kMpcOdBase + SCB_KINEMATIC_BICYCLE_2D)
+      MPCCASE(kMpcOdBase + SCB_QUAD_2D)
+      MPCCASE(kMpcOdBase + SCB_VTOL_2D)
       MPCCASE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
       MPCCASE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
       MPCCASE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
@@ -162,6 +167,7 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
   if (model == SCB_SINGLE_INTEGRATOR_2D || model == SCB_DYNAMIC_UNICYCLE_2D || model == SCB_DOUBLE_INTEGRATOR_2D)
     for (int j = 0; j < nobs && j < M; ++j)
       if (obs[j * 7 + 6] >= 0.5) { model = kMpcSeBase + p->model; break; }
+  if (p->od_mpc) model = kMpcOdBase + p->model;               // u then holds [u, omega1, omega2]
   switch (model) {
 #define STCASE(MODEL)                                                                                           \
   case MODEL: {                                                                                                 \
@@ -189,6 +195,10 @@ int hostsim_mpc_statement(const scb_params* p, int M, int nobs, const double* x,
     STCASE(SCB_KINEMATIC_BICYCLE_2D_C3BF)
     STCASE(SCB_KINEMATIC_BICYCLE_2D_DPCBF)
     STCASE(SCB_VTOL_2D)
+    STCASE(kMpcOdBase + SCB_DYNAMIC_UNICYCLE_2D)
+    STCASE(kMpcOdBase + SCB_KINEMATIC_BICYCLE_2D)
+    STCASE(kMpcOdBase + SCB_QUAD_2D)
+    STCASE(kMpcOdBase + SCB_VTOL_2D)
     STCASE(kMpcSeBase + SCB_SINGLE_INTEGRATOR_2D)
     STCASE(kMpcSeBase + SCB_DYNAMIC_UNICYCLE_2D)
     STCASE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)

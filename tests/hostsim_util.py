@@ -87,8 +87,10 @@ def hs_mpccbf_solve(p, H, X, goal, u_prev, OBS, nobs=None, want_active=False):
     lib = hostsim()
     N, M = OBS.shape[0], OBS.shape[1]
     X, goal, u_prev, OBS = f64(X), f64(goal), f64(u_prev), f64(OBS)
-    U = np.zeros((N, p.nu)); st = np.zeros(N, np.int32); it = np.zeros(N, np.int32); kkt = np.zeros(N)
-    px = np.zeros((N, H + 1, p.nx)); pu = np.zeros((N, H, p.nu))
+    nu = p.nu + (2 if p.od_mpc else 0)                  # optimal-decay MPC: [u, omega1, omega2] per stage
+    assert u_prev.shape == (N, nu), (u_prev.shape, nu)
+    U = np.zeros((N, nu)); st = np.zeros(N, np.int32); it = np.zeros(N, np.int32); kkt = np.zeros(N)
+    px = np.zeros((N, H + 1, p.nx)); pu = np.zeros((N, H, nu))
     no = None if nobs is None else np.ascontiguousarray(nobs, dtype=np.int32)
     lib.scb_mpc_active_words.restype = C.c_int
     act = np.zeros((N, int(lib.scb_mpc_active_words(C.byref(p), M, H))), np.uint64) if want_active else None

@@ -73,7 +73,8 @@ def check_odcbf(spec, M, X, Uref, OBS, nobs, U, omega, sel, status, active, samp
     return dict(n=len(list(idx)), cbf_active=n_act, masks_compared=n_cmp)
 
 
-def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1e-4, min_agree=0.9, second_solver=0):
+def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1e-4, min_agree=0.9, second_solver=0,
+              optimal_decay=False, sum_rterms=False):
     """MPC parity: (a) every 'optimal' answer must be a KKT point of the ORACLE's restated NLP
     (independent derivatives: torch.autograd on oracle/mpc_cbf.py: stationarity <= 1e-4 with non-negative least-squares
     multipliers, complementarity max lam_i g_i <= 1e-5), feasible to 1e-7; (b) u0 must agree
@@ -92,10 +93,17 @@ def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1
     import torch
     from oracle.mpc_cbf import OracleMPCCBF
     warnings.filterwarnings("ignore")
-    o = OracleMPCCBF(spec, num_obs=M, horizon=H)
+    if optimal_decay:                                        # optimal_decay_mpc_cbf: [u, omega1, omega2] per stage, 5 obstacle slots
+        from oracle.mpc_cbf import OracleODMPCCBF
+        o = OracleODMPCCBF(spec, sum_rterms=sum_rterms, horizon=H)
+        assert M == 5
+    else:
+        o = OracleMPCCBF(spec, num_obs=M, horizon=H)
     N = X.shape[0]
     idx = list(range(N) if sample is None else sample)
-    rng = o.u_ub - o.u_lb
+    rng = getattr(o, "u_range", None)
+    if rng is None:
+        rng = o.u_ub - o.u_lb
     n_ok = n_cmp = n_agree = n_same = n_better = n_worse = n_mask = n_second = n_ofail = n_second_agree = 0
     worst_kkt = worst_du = 0.0
     for i in idx:
@@ -122,7 +130,10 @@ def check_mpc(spec, M, H, X, goal, u_prev, OBS, nobs, out, sample=None, u0_tol=1
             n_agree += 1; worst_du = max(worst_du, du)
             if "active" in out and out["active"] is not None:
                 act, gap = o.active_set(X[i], goal[i], u_prev[i], obs, info["u_pred"])
-                if gap >= 1.0:
+                # (the mask covers the whole horizon: compare it only where the two input TRAJECTORIES coincide -- with
+                #  flat directions, e.g. optimal decay without an input cost, u0 can agree while later stages differ)
+                dtraj = float(np.max(np.abs(np.asarray(out["pred_u"][i]) - info["u_pred"]) / rng))
+                if gap >= 1.0 and dtraj <= 10 * u0_tol:
                     n_mask += 1
                     words = np.asarray(out["active"][i]).view(np.uint64).reshape(-1)
                     want = np.zeros(words.size, dtype=np.uint64)

@@ -77,6 +77,8 @@ def test_robot_spec_overrides(lib):
         resolve_params({"model": "VTOL2D"}, "cbf_qp")             # agent_barrier is not implemented (vtol2D.py:458-460)
     with pytest.raises(ValueError):
         resolve_params({"model": "Hovercraft"}, "mpc_cbf")
+    p, s = resolve_params({"model": "KinematicBicycle2D"}, "optimal_decay_mpc_cbf")   # optimal_decay_mpc_cbf.py:37-39, 73-75, 87-90
+    assert (p.od_mpc, p.od_sum_rterms, list(p.R)[:2], p.alpha1, p.p_sb1, p.omega1_0, s["mpc_horizon"]) == (1, 0, [0.5, 50.0], 0.05, 10.0, 1.0, 10)
     p, s = resolve_params({"model": "Unicycle2D", "w_max": 1.0}, "mpc_cbf")
     assert (p.nx, p.nu, p.alpha, p.u_ub[1], p.Q[2]) == (3, 2, 0.05, 1.0, 0.01)
     with pytest.raises(NotCompatibleError):

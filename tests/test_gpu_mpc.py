@@ -100,6 +100,27 @@ def test_mpc_superellipsoid_rows(model):
     assert (ref["status"][flagged] == 3).all()                           # refused loudly without the flag
 
 
+@pytest.mark.parametrize("model,sum_rterms", [("KinematicBicycle2D", False), ("DynamicUnicycle2D", False), ("Quad2D", True)])
+def test_optimal_decay_mpc_vs_oracle(model, sum_rterms):
+    """optimal_decay_mpc_cbf: omega1 / omega2 as extra stage inputs, bilinear CBF rows, 5 obstacle slots,
+    horizon 10; [u, omega1, omega2] columns in u_prev / U / pred_u.  KKT of the oracle's NLP, u0 vs SLSQP, active masks."""
+    from safe_control_b200 import BatchedOptimalDecayMPCCBF, scenes
+    N = 96
+    sc = scenes.make_scene(model, N, 5, seed=77, dense=True)
+    ctrl = BatchedOptimalDecayMPCCBF(dict(sc["spec"], od_sum_rterms=sum_rterms), num_obs=5)
+    assert ctrl.horizon == 10 and ctrl.nu == ctrl.nu_model + 2 and ctrl.params.od_mpc == 1
+    up = np.zeros((N, ctrl.nu))
+    out = ctrl.solve(dev(sc["X"]), dev(sc["goal"]), dev(up), dev(sc["OBS"]), dev(sc["nobs"]), want_pred=True, want_active=True)
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert out["U"].shape == (N, ctrl.nu) and out["pred_u"].shape == (N, 10, ctrl.nu)
+    assert (out["status"] == 0).mean() > 0.6, np.bincount(out["status"])
+    stats = check_mpc_parallel(ctrl.robot_spec, 5, 10, sc["X"], sc["goal"], up, sc["OBS"], sc["nobs"], out, sample=range(0, N, 4),
+                               min_agree=0.75, optimal_decay=True, sum_rterms=sum_rterms)
+    print(model, sum_rterms, stats)
+    assert stats["optimal"] >= 10
+
+
 def test_vtol2d_reference_horizon():
     """VTOL2D at the reference's horizon 30 (mpc_cbf.py:41; 96 KB of workspace per agent): statuses are definite, inputs in
     the box, predictions follow the kernel's own Euler map (x_{k+1}[0:3] = x_k[0:3] + dt x_k[3:6]), state bounds hold."""

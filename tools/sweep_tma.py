@@ -45,7 +45,8 @@ def run(name, ctrl, base, N, B, lanes_list):
 
 base = scenes.make_scene("DynamicUnicycle2D", 1 << 18, 16, seed=1234)
 ctrl = BatchedCBFQP(base["spec"], num_obs=16)
-for N in (8192, 65536, 1 << 20):
+ONLY_BIG = os.environ.get("SWEEP_ONLY") == "big"
+for N in ((1 << 20,) if ONLY_BIG else (8192, 65536, 1 << 20)):
     run("cbfqp", ctrl, base, N, 972, [8, 4] if N > 8192 else [8])
 base4 = scenes.make_scene("KinematicBicycle2D_C3BF", 1 << 17, 32, seed=1234, optimal_decay=True)
 od = BatchedOptimalDecayCBFQP(base4["spec"], num_obs=32)
