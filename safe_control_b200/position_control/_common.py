@@ -34,3 +34,27 @@ def obs_rows(obs, num_obs):
 
 def status_string(code):
     return STATUS_STR.get(int(code), "solver_error")
+
+
+class PinnedIO:
+    """Page-locked (hence device-mapped) host buffers of ONE controller object, allocated at its first solve: with them
+    the host-pointer C calls take the zero-copy path (the kernel reads X / u_ref / obstacles and writes u / status over
+    PCIe directly, csrc/scb_api.cu) instead of seven staged cudaMemcpyAsync -- what the reference-side binding of
+    INTEGRATION.md gets for free when it keeps its arrays in such buffers."""
+
+    def __init__(self, **shapes):
+        import torch
+        self.buf = {}
+        pin = torch.cuda.is_available()         # (buffers only: without a device the solve call itself raises)
+        for name, (shape, dtype) in shapes.items():
+            t = torch.empty(shape, dtype=dtype)
+            self.buf[name] = (t.pin_memory() if pin else t).numpy()
+        self._keep = None
+
+    def __getitem__(self, k):
+        return self.buf[k]
+
+    def put(self, k, value):
+        b = self.buf[k]
+        b[...] = value
+        return b
