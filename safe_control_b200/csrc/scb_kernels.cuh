@@ -55,8 +55,10 @@ inline int tma_slot_doubles(int M, int lanes) {
   return bytes / 8;
 }
 
+// (min CTAs per SM, measured at 1 Mi agents, us per launch at 6 / 5 / 4: 4 lanes 301.9 / 291.2 / 289.6, 8 lanes 389.5 / 426.4 / 421.1;
+//  profiles/r2_sweep_minblocks_v1.txt)
 template <int MODEL, int LANES, int RPL>
-__global__ void __launch_bounds__(kBlock, SCB_QP_MINB(LANES))
+__global__ void __launch_bounds__(kBlock, (LANES == 4) ? 4 : SCB_QP_MINB(LANES))
 cbfqp_tma_kernel(const __grid_constant__ scb_params p, int N, int M, const double* __restrict__ X,
                  const double* __restrict__ Uref, const double* __restrict__ OBS, long stride,
                  const int32_t* __restrict__ nobs, double* __restrict__ U, int32_t* __restrict__ status,

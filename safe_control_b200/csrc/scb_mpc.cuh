@@ -693,6 +693,16 @@ SCB_HD void prof_add(int i, long long& tlast) {
 #define SCB_MPC_OUTLINE_RED 0
 #endif
 
+// barrier schedule (IPOPT's defaults: mu_init 0.1, kappa_mu 0.2, theta_mu 1.5, kappa_epsilon 10)
+#ifndef SCB_MPC_MU0
+#define SCB_MPC_MU0 0.1
+#endif
+#ifndef SCB_MPC_KAPPA_MU
+#define SCB_MPC_KAPPA_MU 0.2
+#endif
+#ifndef SCB_MPC_KAPPA_EPS
+#define SCB_MPC_KAPPA_EPS 10.0
+#endif
 #ifndef SCB_MPC_NOPROGRESS
 #define SCB_MPC_NOPROGRESS 50
 #endif
@@ -1601,7 +1611,7 @@ struct MpcSolver {
       Jcur *= sf;
       sync();
     }
-    double mu_bar = 0.1, nu_pen = 10.0;
+    double mu_bar = SCB_MPC_MU0, nu_pen = 10.0;
     const double tol = p.mpc_tol;
     // slacks are not independent iterates: s_i = max(g_i(z), mu/nu) is re-derived from the constraint values
     // every iteration, so satisfied rows carry no primal residual however non-linear they are, and only rows
@@ -1665,8 +1675,8 @@ struct MpcSolver {
       if (err < 0.5 * err_best) { err_best = err; it_best = it; }
       else if (it - it_best > SCB_MPC_NOPROGRESS) break;   // error not halved for that many iterations: give up
       // monotone barrier update (Fiacco-McCormick with IPOPT's kappa_mu = 0.2, theta_mu = 1.5, kappa_eps = 10)
-      while (fmax(e_d, fmax(e_p, e_cm)) <= 10.0 * mu_bar && mu_bar > tol / 10.0) {
-        mu_bar = fmax(tol / 10.0, fmin(0.2 * mu_bar, mu_bar * sqrt(mu_bar)));
+      while (fmax(e_d, fmax(e_p, e_cm)) <= SCB_MPC_KAPPA_EPS * mu_bar && mu_bar > tol / 10.0) {
+        mu_bar = fmax(tol / 10.0, fmin(SCB_MPC_KAPPA_MU * mu_bar, mu_bar * sqrt(mu_bar)));
         e_cm = 0.0;
         SCB_LANE_UNROLL
         for (int t = lane; t < H * M; t += LANES) e_cm = fmax(e_cm, fabs(fmax(w[L.C + t], 0.0) * w[L.L + t] - mu_bar));
