@@ -200,7 +200,8 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------- CPU arm
 def _cpu_solve_range(args):
     """Worker: oracle port over a slice of agents, one at a time (the reference's control flow)."""
-    w, sc, lo, hi = args
+    w, sc, lo, hi = args[:4]
+    budget = args[4] if len(args) > 4 else None          # seconds this worker may spend (MPC: SLSQP can stall for minutes)
     from oracle.controllers import OracleCBFQP, OracleOptimalDecayCBFQP
     M = w["M"]
     t0 = time.perf_counter()
@@ -217,9 +218,16 @@ def _cpu_solve_range(args):
     else:
         from oracle.mpc_cbf import OracleMPCCBF
         ctrl = OracleMPCCBF(sc["spec"], num_obs=M, horizon=w["H"])
+        done = 0
         for i in range(lo, hi):
             k = int(sc["nobs"][i])
-            ctrl.solve(sc["X"][i], sc["goal"][i], sc["u_prev"][i], sc["OBS"][i][:k])
+            # (iteration cap 100 instead of the tests' 400: a stalled SLSQP run would otherwise take minutes; IPOPT in the
+            #  reference likewise returns its last iterate at its own limit)
+            ctrl.solve(sc["X"][i], sc["goal"][i], sc["u_prev"][i], sc["OBS"][i][:k], maxiter=100)
+            done += 1
+            if budget is not None and time.perf_counter() - t0 > budget:
+                break
+        return done, time.perf_counter() - t0
     return hi - lo, time.perf_counter() - t0
 
 
@@ -232,13 +240,14 @@ def _close_pools():
     _POOL.clear()
 
 
-def cpu_rate(w, sc, n_agents, procs, offset=0):
-    """agent-steps/s of the oracle port on `procs` host processes over agents [offset, offset + n_agents)."""
+def cpu_rate(w, sc, n_agents, procs, offset=0, budget=None):
+    """agent-steps/s of the oracle port on `procs` host processes over agents [offset, offset + n_agents); `budget` =
+    seconds after which a worker stops taking new agents (it still counts what it finished)."""
     n_tot = sc["X"].shape[0]
     offset = offset % max(n_tot - n_agents + 1, 1)
     n_agents = min(n_agents, n_tot)
     if procs <= 1:
-        n, dt = _cpu_solve_range((w, sc, offset, offset + n_agents))
+        n, dt = _cpu_solve_range((w, sc, offset, offset + n_agents, budget))
         return n / dt, n, dt
     import multiprocessing as mp
     if procs not in _POOL:
@@ -246,7 +255,7 @@ def cpu_rate(w, sc, n_agents, procs, offset=0):
     bounds = offset + np.linspace(0, n_agents, procs + 1).astype(int)
     small = {k: sc[k] for k in ("spec", "X", "U_ref", "OBS", "nobs", "goal", "u_prev")}
     t0 = time.perf_counter()
-    res = _POOL[procs].map(_cpu_solve_range, [(w, small, int(bounds[j]), int(bounds[j + 1])) for j in range(procs)])
+    res = _POOL[procs].map(_cpu_solve_range, [(w, small, int(bounds[j]), int(bounds[j + 1]), budget) for j in range(procs)])
     dt = time.perf_counter() - t0
     n = sum(r[0] for r in res)
     return n / dt, n, dt
@@ -824,8 +833,9 @@ def reference_arm(args, w):
     procs = os.cpu_count() or 1
     if w.get("loop"):
         return reference_loop(args, w, procs)
-    per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 1}[w["controller"]] * procs
-    budget_s = 150.0
+    per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 2}[w["controller"]] * procs
+    budget_s = 120.0
+    slice_s = 8.0 if w["controller"] == "mpc_cbf" else None   # MPC: a worker stops taking new agents after this long
     mixed = w["model"] == "mixed"
     models = list(MIXED) if mixed else [w["model"]]
     n_scene = min(max(per_step * 8, 2048), 16384) if not mixed else max(per_step * 8, 256)
@@ -836,12 +846,12 @@ def reference_arm(args, w):
         """one step: per_step agents of EVERY model group (mixed: the 1/3-1/3-1/3 mix) -> (agents, seconds)"""
         n_tot, t_tot = 0, 0.0
         for m, sc in zip(models, scs):
-            r, n, dt = cpu_rate(dict(w, model=m), sc, per_step, procs, offset=k * per_step)
+            r, n, dt = cpu_rate(dict(w, model=m), sc, per_step, procs, offset=k * per_step, budget=slice_s)
             n_tot += n; t_tot += dt
         return n_tot, t_tot
 
-    for k in range(max(1, min(args.warmup, 3)) if not mixed else 1):
-        one(k)
+    for k in range(max(1, min(args.warmup, 3)) if w["controller"] != "mpc_cbf" else 0):
+        one(k)                                   # (MPC: no warm-up step, the oracle has no state to warm and a step costs ~20 s)
     t_tot, n_tot, done = 0.0, 0, 0
     for k in range(args.steps):
         n, dt = one(k + 3)
@@ -849,7 +859,8 @@ def reference_arm(args, w):
         if t_tot > budget_s:
             break
     val = n_tot / t_tot
-    sample = (f"{done} steps x {per_step} agents" + (" of each model group (du / kb / quad3d)" if mixed else "") +
+    sample = (f"{done} steps x up to {per_step} agents" + (" of each model group (du / kb / quad3d)" if mixed else "") +
+              (f" ({n_tot} agents solved; a worker stops taking new agents {slice_s:.0f} s into a step, SLSQP capped at 100 iterations)" if slice_s else "") +
               f" of the {w['name']} scene (seed 1234), oracle port (numpy/scipy), "
               f"{procs} processes" + ("" if done == args.steps else f"; stopped at the {budget_s:.0f} s budget"))
     print(json.dumps({

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid
   extern __shared__ double smem[];
   using Mod = MpcModel<MODEL>;
   constexpr int NX = Mod::NX, NU = Mod::NU;
-  constexpr bool kIsSe = MODEL >= kMpcSeBase;
+  constexpr bool kIsSe = MODEL >= kMpcSeBase && MODEL < kMpcOdBase;       // (200 + id: the optimal-decay variants)
   constexpr bool kHasSeVariant = MODEL == SCB_SINGLE_INTEGRATOR_2D || MODEL == SCB_DYNAMIC_UNICYCLE_2D || MODEL == SCB_DOUBLE_INTEGRATOR_2D;
   const int grp = threadIdx.x / LANES;
   if (grp >= gpb) return;             // padding lanes of the last warp (gpb * LANES is rounded up to whole warps)
