@@ -221,9 +221,9 @@ def _cpu_solve_range(args):
         done = 0
         for i in range(lo, hi):
             k = int(sc["nobs"][i])
-            # (iteration cap 100 instead of the tests' 400: a stalled SLSQP run would otherwise take minutes; IPOPT in the
-            #  reference likewise returns its last iterate at its own limit)
-            ctrl.solve(sc["X"][i], sc["goal"][i], sc["u_prev"][i], sc["OBS"][i][:k], maxiter=100)
+            # (iteration cap 40 instead of the tests' 400 -- converging runs take 15-30 -- because a stalled SLSQP run costs
+            #  minutes at config-5 size; IPOPT in the reference likewise returns its last iterate at its own limit)
+            ctrl.solve(sc["X"][i], sc["goal"][i], sc["u_prev"][i], sc["OBS"][i][:k], maxiter=40)
             done += 1
             if budget is not None and time.perf_counter() - t0 > budget:
                 break
@@ -860,7 +860,7 @@ def reference_arm(args, w):
             break
     val = n_tot / t_tot
     sample = (f"{done} steps x up to {per_step} agents" + (" of each model group (du / kb / quad3d)" if mixed else "") +
-              (f" ({n_tot} agents solved; a worker stops taking new agents {slice_s:.0f} s into a step, SLSQP capped at 100 iterations)" if slice_s else "") +
+              (f" ({n_tot} agents solved; a worker stops taking new agents {slice_s:.0f} s into a step, SLSQP capped at 40 iterations)" if slice_s else "") +
               f" of the {w['name']} scene (seed 1234), oracle port (numpy/scipy), "
               f"{procs} processes" + ("" if done == args.steps else f"; stopped at the {budget_s:.0f} s budget"))
     print(json.dumps({
