@@ -724,7 +724,17 @@ struct MpcSolver {
 
   const scb_params& p;
   const MpcLayout& L;
-  double* w;
+  // The workspace.  On the device it is the group's slice of dynamic shared memory, addressed as (shared array + offset)
+  // at every use so that the compiler emits LDS / STS with the offset folded in; a stored generic pointer made it emit
+  // generic LD / ST (897 of them in the DynamicUnicycle2D kernel), which resolve the address space at run time.
+#if defined(__CUDA_ARCH__) && !defined(SCB_MPC_GENERIC_WS)
+  unsigned wofs;
+  SCB_HD double* wbase() const { extern __shared__ double scb_mpc_smem_[]; return scb_mpc_smem_ + wofs; }
+#else
+  double* wptr;
+  SCB_HD double* wbase() const { return wptr; }
+#endif
+#define w (wbase())
   int H, M, n, lane;
   double w0, w1, w2, Wsum;      // c_j = w0 h(p0) + w1 h(p1) + w2 h(p2),  h = |p - o|^2 - beta d^2
   double goal[NX];
@@ -739,7 +749,13 @@ struct MpcSolver {
   bool gauss_newton;            // assemble stage Hessians without the (possibly indefinite) curvature terms
   double floor_cur;             // slack floor mu / nu of the current iteration (general rows re-derive their weights)
 
-  SCB_HD MpcSolver(const scb_params& p_, const MpcLayout& L_, double* w_) : p(p_), L(L_), w(w_) {
+  SCB_HD MpcSolver(const scb_params& p_, const MpcLayout& L_, double* w_) : p(p_), L(L_) {
+#if defined(__CUDA_ARCH__) && !defined(SCB_MPC_GENERIC_WS)
+    extern __shared__ double scb_mpc_smem_[];
+    wofs = (unsigned)(w_ - scb_mpc_smem_);
+#else
+    wptr = w_;
+#endif
     H = L.H; M = L.M; n = L.n; lane = G::lane();
     if (Mod::REL == 2) {
       const double g1 = p.alpha1 + p.alpha2, g2 = p.alpha1 * p.alpha2;
@@ -1890,6 +1906,7 @@ struct MpcSolver {
     }
     sync();
   }
+#undef w
 };
 
 // entry point shared by the kernel and the host-sim
