@@ -126,6 +126,8 @@ typedef struct scb_ctx scb_ctx;   /* opaque: device staging buffers + stream for
 /* ---- library / parameter helpers ------------------------------------------------------- */
 int         scb_version(void);
 size_t      scb_params_sizeof(void);                   /* sizeof(scb_params): lets a binding verify its struct mirror */
+long        scb_params_offsetof(const char* field);    /* offsetof(scb_params, field) by name, -1 if unknown */
+long        scb_track_offsetof(const char* field);     /* offsetof(scb_track, field) by name, -1 if unknown */
 const char* scb_strerror(int err);
 int         scb_last_cuda_error(void);                 /* cudaError_t of the last SCB_ERR_CUDA on this thread */
 int         scb_device_count(void);

@@ -78,6 +78,8 @@ _T = C.POINTER(ScbTrack)
 PROTOTYPES = {
     "scb_version": (C.c_int, []),
     "scb_params_sizeof": (C.c_size_t, []),
+    "scb_params_offsetof": (C.c_long, [C.c_char_p]),
+    "scb_track_offsetof": (C.c_long, [C.c_char_p]),
     "scb_strerror": (C.c_char_p, [C.c_int]),
     "scb_last_cuda_error": (C.c_int, []),
     "scb_device_count": (C.c_int, []),

@@ -22,6 +22,24 @@ int scb_version(void) { return SCB_VERSION; }
 
 size_t scb_params_sizeof(void) { return sizeof(scb_params); }
 
+/* offsetof of a field by name (-1: unknown): lets a binding verify its struct mirror field by field, not only by size */
+#include <stddef.h>
+long scb_params_offsetof(const char* field) {
+  if (!field) return -1;
+#define F(name) if (strcmp(field, #name) == 0) return (long)offsetof(scb_params, name);
+  F(model) F(cbf_mode) F(nx) F(nu) F(dt) F(radius) F(alpha) F(alpha1) F(alpha2) F(u_lb) F(u_ub) F(v_min) F(v_max) F(rear_ax_dist) F(omega1_0) F(omega2_0) F(p_sb1) F(p_sb2) F(Q) F(R) F(mass) F(Ix) F(Iy) F(Iz) F(arm_L) F(nu_coef) F(gravity) F(mpc_max_iter) F(mpc_superellipsoid) F(mpc_tol) F(S_wing) F(rho) F(C_L0) F(C_Lalpha) F(blend_M) F(alpha_0) F(C_Ldelta_e) F(C_D0) F(C_Dalpha) F(C_Ddelta_e) F(C_m0) F(C_malpha) F(C_mdelta_e) F(chord) F(k_front) F(k_rear) F(k_pusher) F(ell_f) F(ell_r) F(pitch_max) F(descent_speed_max) F(od_mpc) F(od_sum_rterms)
+#undef F
+  return -1;
+}
+long scb_track_offsetof(const char* field) {
+  if (!field) return -1;
+#define F(name) if (strcmp(field, #name) == 0) return (long)offsetof(scb_track, name);
+  F(controller) F(N) F(K) F(M) F(W) F(H) F(enable_rotation) F(dynamic_obs) F(att_velocity_tracking) F(mpc_strict) F(reached_threshold) F(rotation_threshold) F(k_omega) F(k_a) F(k_v) F(k_a_stop) F(w_max) F(att_kp) F(wheel_base) F(delta_max) F(X) F(yaw) F(sm) F(wp_idx) F(WP) F(nwp) F(goal) F(has_goal) F(u_att) F(u_prev) F(ret) F(done) F(nsteps) F(SCENE) F(Uref) F(OBS) F(nobs) F(U) F(status) F(active) F(track_flag) F(mpc_iters) F(mpc_ws) F(mpc_ws_bytes) F(mpc_fail)
+#undef F
+  return -1;
+}
+
+
 const char* scb_strerror(int err) {
   switch (err) {
     case SCB_OK: return "ok";

@@ -133,3 +133,12 @@ def test_tracker_initial_state_padding_matches_reference_rules():
     assert X.shape == (1, 12) and X[0, :3].tolist() == [1.0, 2.0, 3.0] and X[0, 5] == 0.5 and yaw.tolist() == [0.5]
     with pytest.raises(ValueError):
         pad_initial_state("Unicycle2D", [[1.0, 2.0]])
+
+
+def test_struct_mirrors_field_by_field(lib):
+    """offsetof of every field of scb_params / scb_track as the C compiler laid them out vs the ctypes mirrors (a renamed
+    or reordered field of equal size would pass a sizeof-only check)."""
+    for struct, fn in ((_abi.ScbParams, lib.scb_params_offsetof), (_abi.ScbTrack, lib.scb_track_offsetof)):
+        for name, _ in struct._fields_:
+            assert fn(name.encode()) == getattr(struct, name).offset, (struct.__name__, name)
+    assert lib.scb_params_offsetof(b"no_such_field") == -1
