@@ -202,6 +202,12 @@ def _cpu_solve_range(args):
     """Worker: oracle port over a slice of agents, one at a time (the reference's control flow)."""
     w, sc, lo, hi = args[:4]
     budget = args[4] if len(args) > 4 else None          # seconds this worker may spend (MPC: SLSQP can stall for minutes)
+    if budget != "inproc":
+        try:                                             # pool worker: one core each -- BLAS / OpenMP pools of 16 processes x 16
+            from threadpoolctl import threadpool_limits  # threads would fight over the same cores (observed: 60x slower)
+            threadpool_limits(1)
+        except Exception:
+            pass
     from oracle.controllers import OracleCBFQP, OracleOptimalDecayCBFQP
     M = w["M"]
     t0 = time.perf_counter()
@@ -216,6 +222,8 @@ def _cpu_solve_range(args):
             k = int(sc["nobs"][i])
             ctrl.solve(sc["X"][i], sc["U_ref"][i], sc["OBS"][i][0] if k else None)   # lists are distance-sorted
     else:
+        import torch
+        torch.set_num_threads(1)               # one core per worker process (the pool already uses every host core)
         from oracle.mpc_cbf import OracleMPCCBF
         ctrl = OracleMPCCBF(sc["spec"], num_obs=M, horizon=w["H"])
         done = 0
@@ -225,7 +233,7 @@ def _cpu_solve_range(args):
             #  minutes at config-5 size; IPOPT in the reference likewise returns its last iterate at its own limit)
             ctrl.solve(sc["X"][i], sc["goal"][i], sc["u_prev"][i], sc["OBS"][i][:k], maxiter=40)
             done += 1
-            if budget is not None and time.perf_counter() - t0 > budget:
+            if isinstance(budget, (int, float)) and time.perf_counter() - t0 > budget:
                 break
         return done, time.perf_counter() - t0
     return hi - lo, time.perf_counter() - t0
@@ -247,7 +255,7 @@ def cpu_rate(w, sc, n_agents, procs, offset=0, budget=None):
     offset = offset % max(n_tot - n_agents + 1, 1)
     n_agents = min(n_agents, n_tot)
     if procs <= 1:
-        n, dt = _cpu_solve_range((w, sc, offset, offset + n_agents, budget))
+        n, dt = _cpu_solve_range((w, sc, offset, offset + n_agents, "inproc"))
         return n / dt, n, dt
     import multiprocessing as mp
     if procs not in _POOL:
@@ -255,6 +263,16 @@ def cpu_rate(w, sc, n_agents, procs, offset=0, budget=None):
     bounds = offset + np.linspace(0, n_agents, procs + 1).astype(int)
     small = {k: sc[k] for k in ("spec", "X", "U_ref", "OBS", "nobs", "goal", "u_prev")}
     t0 = time.perf_counter()
+    if w["controller"] == "mpc_cbf":
+        # solve times vary 10x between agents (SLSQP stalls on some): hand agents out one at a time so that no worker idles
+        # behind a straggler; only the rows a task needs travel to the worker
+        tasks = []
+        for i in range(offset, offset + n_agents):
+            one = {k: (small[k] if k == "spec" else small[k][i:i + 1]) for k in small}
+            tasks.append((w, one, 0, 1, None))
+        res = list(_POOL[procs].imap_unordered(_cpu_solve_range, tasks, chunksize=1))
+        dt = time.perf_counter() - t0
+        return sum(r[0] for r in res) / dt, sum(r[0] for r in res), dt
     res = _POOL[procs].map(_cpu_solve_range, [(w, small, int(bounds[j]), int(bounds[j + 1]), budget) for j in range(procs)])
     dt = time.perf_counter() - t0
     n = sum(r[0] for r in res)
@@ -810,6 +828,9 @@ def run_cfg5(args, w, cx, steps, warmup, sub=False):
     }
     if base is not None:
         out["strong_scaling_base"] = base
+        out["strong_scaling_efficiency_vs_base"] = out["value"] / (world * base["value"])
+        out["config"]["scaling_note"] = ("the N = 1 line of bench.py is config 2 (BASELINE configs[1]); the 1-GPU point of THIS workload is "
+                                         "strong_scaling_base (same batch, rank 0 alone, measured in this run) and sub_records.cfg5 of the N = 1 line")
     if clocks is not None:
         out["clocks"] = clocks
     if not args.no_cpu and not sub and world == 1:
@@ -833,9 +854,9 @@ def reference_arm(args, w):
     procs = os.cpu_count() or 1
     if w.get("loop"):
         return reference_loop(args, w, procs)
-    per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 2}[w["controller"]] * procs
+    per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 3}[w["controller"]] * procs
     budget_s = 120.0
-    slice_s = 8.0 if w["controller"] == "mpc_cbf" else None   # MPC: a worker stops taking new agents after this long
+    slice_s = None
     mixed = w["model"] == "mixed"
     models = list(MIXED) if mixed else [w["model"]]
     n_scene = min(max(per_step * 8, 2048), 16384) if not mixed else max(per_step * 8, 256)
@@ -860,7 +881,7 @@ def reference_arm(args, w):
             break
     val = n_tot / t_tot
     sample = (f"{done} steps x up to {per_step} agents" + (" of each model group (du / kb / quad3d)" if mixed else "") +
-              (f" ({n_tot} agents solved; a worker stops taking new agents {slice_s:.0f} s into a step, SLSQP capped at 40 iterations)" if slice_s else "") +
+              (f" ({n_tot} agents solved; agents handed to the workers one at a time, SLSQP capped at 40 iterations)" if w["controller"] == "mpc_cbf" else "") +
               f" of the {w['name']} scene (seed 1234), oracle port (numpy/scipy), "
               f"{procs} processes" + ("" if done == args.steps else f"; stopped at the {budget_s:.0f} s budget"))
     print(json.dumps({

@@ -279,7 +279,7 @@ class OracleMPCCBF:
 
         def f(v):
             t = tn(v); c = self.cost(t, gf, up); c.backward()
-            return float(c), t.grad.numpy().copy()
+            return float(c.detach()), t.grad.numpy().copy()
 
         def jac(fn):
             def j(v):
