@@ -73,13 +73,26 @@ class ShardedMixedMPCCBF:
         return self.mixed.launches
 
     def scatter(self, inputs):
-        return [pl.scatter(inputs[g] if inputs is not None else None) for g, pl in enumerate(self.plans)]
+        """all 15 tensors (5 per model group) leave rank src in ONE coalesced NCCL group of point-to-point sends: exact
+        blocks straight out of the caller's tensors, no padding, no staging copy"""
+        from .sharding import run_p2p
+        ops, blocks = [], []
+        for g, pl in enumerate(self.plans):
+            o, b = pl.scatter_ops(inputs[g] if inputs is not None else None)
+            ops += o; blocks.append(b)
+        run_p2p(ops)
+        return blocks
 
     def solve_local(self, blocks):
         return self.mixed.solve(blocks, want_active=self.want_active)
 
     def gather(self, outs):
-        res = [pl.gather({k: o[k] for k in pl.out_specs}) for pl, o in zip(self.plans, outs)]
+        from .sharding import run_p2p
+        ops, res = [], []
+        for pl, o in zip(self.plans, outs):
+            p, r = pl.gather_ops({k: o[k] for k in pl.out_specs})
+            ops += p; res.append(r)
+        run_p2p(ops)
         return res if self.rank == self.src else None
 
     def solve(self, inputs):

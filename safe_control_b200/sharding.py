@@ -8,6 +8,12 @@ There is no collective inside the solve.
     out = solve(block)                                             # per-rank launch(es), no communication
     full = plan.gather(out)                                        # NCCL gather -> [n_agents, ...] on src
 
+or, for several tensors / several plans at once, the point-to-point form (exact unpadded blocks, everything coalesced
+into one NCCL group -- what mixed.ShardedMixedMPCCBF uses for BASELINE config 5):
+
+    ops, block = plan.scatter_ops(inputs_on_src); run_p2p(ops)
+    ops, full = plan.gather_ops(out);             run_p2p(ops)
+
 Works with any torch.distributed backend: NCCL over NVLink on CUDA tensors in production (bench.py --gpus N runs
 BASELINE config 5 through it), gloo on CPU tensors in the tests (tests/test_sharding_gloo.py).
 """
@@ -58,11 +64,16 @@ class ShardPlan:
         # per-rank send blocks (outputs), only needed when the solve's output is narrower than `width`
         self._out_block = {k: mk((self.width, *shp), dt) for k, (shp, dt) in self.out_specs.items()}
         self._in_stage = self._out_stage = self._out_full = None
+        self._mk = mk
         if self.rank == src:
             self._out_full = {k: mk((self.n, *shp), dt) for k, (shp, dt) in self.out_specs.items()}
-            if not self.even:
-                self._in_stage = {k: mk((self.world, self.width, *shp), dt) for k, (shp, dt) in self.in_specs.items()}
-                self._out_stage = {k: mk((self.world, self.width, *shp), dt) for k, (shp, dt) in self.out_specs.items()}
+
+    def _stages(self):
+        """staging buffers of the COLLECTIVE form for ragged blocks, allocated at its first use (the point-to-point form
+        needs none)"""
+        if self._in_stage is None and self.rank == self.src and not self.even:
+            self._in_stage = {k: self._mk((self.world, self.width, *shp), dt) for k, (shp, dt) in self.in_specs.items()}
+            self._out_stage = {k: self._mk((self.world, self.width, *shp), dt) for k, (shp, dt) in self.out_specs.items()}
 
     @property
     def n_local(self) -> int:
@@ -74,9 +85,58 @@ class ShardPlan:
     def gather_bytes(self) -> int:
         return sum(self.n * int(torch.tensor([], dtype=dt).element_size()) * _numel(shp) for shp, dt in self.out_specs.values())
 
+    # ---- point-to-point form: exact (unpadded) blocks, any number of plans coalesced into ONE NCCL group ------------------
+    def scatter_ops(self, inputs: Optional[Dict[str, torch.Tensor]]):
+        """-> (P2POp list, this rank's blocks).  Rank src sends rows [lo_r, hi_r) of every input tensor straight out of the
+        caller's tensors (views, no staging, no padding); rank r receives into its pre-sized block buffers.  Hand the ops
+        of several plans to run_p2p() together: NCCL then issues them as one group."""
+        ops, out = [], {}
+        for k, (shp, dt) in self.in_specs.items():
+            if self.world == 1:
+                out[k] = inputs[k]
+                continue
+            blk = self._in_block[k][: self.n_local]
+            if self.rank == self.src:
+                full = inputs[k]
+                if tuple(full.shape) != (self.n, *shp) or full.dtype != dt:
+                    raise ValueError(f"{k}: expected [{self.n}, {shp}] {dt}, got {tuple(full.shape)} {full.dtype}")
+                full = full.contiguous()
+                for r, (l, h) in enumerate(self.bounds):
+                    if r == self.src:
+                        out[k] = full[l:h]                               # own rows: a view, no copy
+                    elif h > l:
+                        ops.append(dist.P2POp(dist.isend, full[l:h], r, self.group))
+            else:
+                if self.n_local > 0:
+                    ops.append(dist.P2POp(dist.irecv, blk, self.src, self.group))
+                out[k] = blk
+        return ops, out
+
+    def gather_ops(self, outputs: Dict[str, torch.Tensor]):
+        """-> (P2POp list, full outputs on rank src or None).  Every rank sends its rows, rank src receives them in place into
+        its [n_agents, ...] buffers (valid until the next gather)."""
+        ops, res = [], {}
+        for k, (shp, dt) in self.out_specs.items():
+            mine = outputs[k]
+            if self.world == 1:
+                res[k] = mine
+                continue
+            if self.rank == self.src:
+                full = self._out_full[k]
+                for r, (l, h) in enumerate(self.bounds):
+                    if r == self.src:
+                        full[l:h].copy_(mine)
+                    elif h > l:
+                        ops.append(dist.P2POp(dist.irecv, full[l:h], r, self.group))
+                res[k] = full
+            elif self.n_local > 0:
+                ops.append(dist.P2POp(dist.isend, mine.contiguous(), self.src, self.group))
+        return ops, (res if self.rank == self.src else None)
+
     def scatter(self, inputs: Optional[Dict[str, torch.Tensor]]) -> Dict[str, torch.Tensor]:
         """`inputs[k]` = [n_agents, *shape] on rank src (device tensors; ignored elsewhere) -> this rank's rows."""
         out = {}
+        self._stages()
         for k, (shp, dt) in self.in_specs.items():
             buf = self._in_block[k]
             if self.world == 1:
@@ -103,6 +163,7 @@ class ShardPlan:
         """`outputs[k]` = this rank's [n_r, *shape] -> [n_agents, *shape] on rank src (None elsewhere).  The
         returned tensors are the plan's own buffers: valid until the next gather()."""
         res = {}
+        self._stages()
         for k, (shp, dt) in self.out_specs.items():
             mine = outputs[k]
             if self.world == 1:
@@ -127,6 +188,14 @@ class ShardPlan:
             else:
                 dist.gather(send, None, dst=self.src, group=self.group)
         return res if self.rank == self.src else None
+
+
+def run_p2p(ops) -> None:
+    """Issue a list of P2POps as one coalesced group (NCCL: a single ncclGroupStart/End) and wait for them."""
+    if not ops:
+        return
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
 
 
 def _numel(shape) -> int:

@@ -94,6 +94,17 @@ def _plan_worker(rank, world, port, n_agents, q):
                 p = (full["U"].data_ptr(), full["status"].data_ptr())
                 ok = ok and (ptrs is None or ptrs == p)           # same pre-sized output buffers every step
                 ptrs = p
+        # point-to-point form of the same plan (exact blocks, one coalesced group)
+        from safe_control_b200.sharding import run_p2p
+        X = torch.rand((n_agents, 4), generator=torch.Generator().manual_seed(9), dtype=F64)
+        nobs = torch.arange(n_agents, dtype=I32) % 3
+        ops, blk = plan.scatter_ops({"X": X, "nobs": nobs} if rank == 0 else None)
+        run_p2p(ops)
+        out = {"U": torch.stack([blk["X"][:, 2], blk["X"][:, 3] - blk["nobs"].double()], 1), "status": blk["nobs"].clone()}
+        ops, full = plan.gather_ops(out)
+        run_p2p(ops)
+        if rank == 0:
+            ok = ok and torch.equal(full["U"], torch.stack([X[:, 2], X[:, 3] - nobs.double()], 1)) and torch.equal(full["status"], nobs)
         # config-5 wrapper: three model groups with their own row shapes, stand-in solve
         from safe_control_b200.mixed import ShardedMixedMPCCBF
         specs = [{"model": "DynamicUnicycle2D"}, {"model": "KinematicBicycle2D"}, {"model": "Quad3D"}]
