@@ -819,6 +819,9 @@ def run_cfg5(args, w, cx, steps, warmup, sub=False):
                                    f"NCCL gather of U/status/iters/active to rank 0, inside the timed region" if world > 1 else
                                    "1 rank: whole batch on one GPU (scatter / gather degenerate to views)"),
                    "phases_ms": {"scatter_ms": sc_ms, "solve_ms": so_ms, "gather_ms": ga_ms, "how": "CUDA events per step on each rank, mean over steps, max over ranks"},
+                   "phases_ms_rank0": {"scatter_ms": float(ph[0]), "solve_ms": float(ph[1]), "gather_ms": float(ph[2]),
+                                       "how": "the same events on rank 0 (the source / sink of the data) alone: on the other ranks the scatter and gather "
+                                              "phases also contain the wait for rank 0 and for the slowest rank, so the max over ranks above over-counts them"},
                    "scatter_bytes": plan_bytes[0], "gather_bytes": plan_bytes[1], "solver": stat},
         "e2e": {"value": N / (e2e_max * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps_timed": e_steps,

@@ -6,6 +6,8 @@
 // load stays on chip; HBM sees the inputs once and U/status once.
 #pragma once
 
+#include <stdlib.h>
+
 #include "scb_mpc.cuh"
 #include "scb_mpc_kernels.cuh"
 
@@ -188,17 +190,19 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const MpcIO& io, int*
   const size_t budget = 220 * 1024;
   constexpr int kLanes = mpc_lanes<MODEL>();
   constexpr int kMpcMaxGroups = SCB_MPC_MAXTHREADS / kLanes;
-  int gpb = (int)(budget / per);
-  if (gpb < 1) return SCB_ERR_TOO_LARGE;
-  if (gpb > kMpcMaxGroups) gpb = kMpcMaxGroups;
-  const long need = ((long)N + gpb - 1) / gpb;
-  if (need < sm_count) {                       // small batch: spread over all SMs first
-    gpb = (int)(((long)N + sm_count - 1) / sm_count);
-    if (gpb < 1) gpb = 1;
-  }
+  int slots = (int)(budget / per);                       // agent-warps one SM can hold (shared memory)
+  if (slots < 1) return SCB_ERR_TOO_LARGE;
+  if (slots > kMpcMaxGroups) slots = kMpcMaxGroups;
+  // CTA shape.  One agent-warp per CTA (default): the warps of a CTA are independent, so small CTAs lose nothing, and an SM
+  // slot is released the moment ITS agent queue runs dry instead of when the slowest of `slots` warps is done -- which is
+  // what lets the CTAs of another launch (the next model group of a mixed batch, on another stream) move in during the
+  // tail.  SCB_MPC_GPB=n packs n agent-warps per CTA (round 1's shape: n = slots, one CTA per SM).
+  int gpb = 1;
+  if (const char* e = getenv("SCB_MPC_GPB")) { const int v = atoi(e); if (v >= 1) gpb = v < slots ? v : slots; }
+  const int cta_per_sm = slots / gpb > 0 ? slots / gpb : 1;
   const size_t smem = per * gpb;
   long blocks = ((long)N + gpb - 1) / gpb;
-  if (blocks > sm_count) blocks = sm_count;
+  if (blocks > (long)sm_count * cta_per_sm) blocks = (long)sm_count * cta_per_sm;
   // schedule (needs the caller's workspace; without one, or when every agent starts in the first wave, index order)
   const int32_t* order = nullptr;
   const bool scheduled = workspace && workspace_bytes >= mpc_workspace_bytes(N) && (long)N > blocks * gpb;

@@ -14,6 +14,11 @@ class MixedMPCCBF:
     def __init__(self, robot_specs: Sequence[dict], num_obs: int, horizon: int, dt: float = 0.05):
         self.groups: List[BatchedMPCCBF] = [BatchedMPCCBF(s, num_obs=num_obs, dt=dt, horizon=horizon) for s in robot_specs]
         self.streams = None
+        # launch order: the group whose single hardest agent runs longest goes first, so that its tail overlaps the other
+        # groups' bulk instead of ending the step alone (measured per-launch times at config-5 shapes: KinematicBicycle2D 17 ms,
+        # Quad3D 12 ms, DynamicUnicycle2D 9.5 ms for 2731 agents; results do not depend on the order)
+        cost = {"KinematicBicycle2D": 3, "KinematicBicycle2D_C3BF": 4, "KinematicBicycle2D_DPCBF": 4, "VTOL2D": 5, "Quad3D": 2}
+        self.launch_order = sorted(range(len(self.groups)), key=lambda g: -cost.get(self.groups[g].model, 1))
 
     @property
     def launches(self):
@@ -25,11 +30,12 @@ class MixedMPCCBF:
         if self.streams is None:
             self.streams = [torch.cuda.Stream() for _ in self.groups]
         cur = torch.cuda.current_stream()
-        outs = []
-        for g, st, a in zip(self.groups, self.streams, inputs):
+        outs = [None] * len(self.groups)
+        for i in self.launch_order:
+            g, st, a = self.groups[i], self.streams[i], inputs[i]
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                outs.append(g.solve(a["X"], a["goal"], a["u_prev"], a["OBS"], a.get("nobs"), want_active=want_active))
+                outs[i] = g.solve(a["X"], a["goal"], a["u_prev"], a["OBS"], a.get("nobs"), want_active=want_active)
         for st in self.streams:
             cur.wait_stream(st)
         return outs
