@@ -52,6 +52,9 @@ WORKLOADS["loop2"] = dict(model="DynamicUnicycle2D", controller="cbf_qp", N=1024
 WORKLOADS["loop4"] = dict(model="KinematicBicycle2D_C3BF", controller="optimal_decay_cbf_qp", N=8192, M=32, H=0, dynamic=True,
                           loop=True, desc="closed loop of config 4: 8192 KinematicBicycle2D_C3BF agents, optimal_decay_cbf_qp, "
                                           "32 moving obstacles, full control_step() on the device")
+WORKLOADS["backup"] = dict(model="DoubleIntegrator2D", controller="backup_cbf_qp", N=65536, M=1, H=120, dynamic=True,
+                           desc="SURVEY 8f-3: 65536 DoubleIntegrator2D agents in the evade scene, Backup-CBF QP "
+                                "(120 backup steps with forward-difference sensitivities -> 120 rows + 4 box rows x 2 inputs), 1 moving obstacle each")
 L2_BYTES = 126e6
 MIXED = ("DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D")
 
@@ -850,6 +853,111 @@ def run_cfg5(args, w, cx, steps, warmup, sub=False):
 
 
 # --------------------------------------------------------------------------------------- reference arm
+def _backup_cpu_range(args):
+    """one process of the Backup-CBF CPU leg: oracle/backup_cbf.py (the restatement of backup_cbf_qp.py:563-794) on agents [lo, hi)"""
+    lo, hi, X, Ur, MOV = args
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import backup_cbf as B
+    sc = B.EvadeScene()
+    t0 = time.perf_counter()
+    for a in range(lo, hi):
+        B.solve(sc, X[a], Ur[a], MOV[a])
+    return hi - lo, time.perf_counter() - t0
+
+
+def backup_cpu_rate(X, Ur, MOV, procs, per_proc):
+    import multiprocessing as mp
+    n = procs * per_proc
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pool.map(_backup_cpu_range, [(0, 1, X, Ur, MOV)] * procs)            # imports / warm-up
+        t0 = time.perf_counter()
+        pool.map(_backup_cpu_range, [(k * per_proc, (k + 1) * per_proc, X[:n], Ur[:n], MOV[:n]) for k in range(procs)])
+        dt = time.perf_counter() - t0
+    return n / dt, n
+
+
+def run_backup(args, w, cx, steps, warmup, sub=False):
+    """Backup-CBF QP: one step = scb_backupcbf_solve over N agents (rollout launch + QP launch)."""
+    torch = cx.torch
+    from safe_control_b200 import BatchedBackupCBF, HostContext, scenes
+    from safe_control_b200.backup import host_solve
+    N = w["N"]
+    P = 2
+    batches = [scenes.make_evade_batch(N, seed=1234 + 101 * q) for q in range(P)]
+    dins = [[torch.from_numpy(v).to(cx.dev) for v in b] for b in batches]
+    ctrl = BatchedBackupCBF()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for k in range(max(warmup, 3)):
+        out = ctrl.solve(*dins[k % P])
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank)
+    if cx.rank == 0 and not sub:
+        sampler.start()
+    l0 = ctrl.launches
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(steps):
+        out = ctrl.solve(*dins[k % P])
+    e1.record(); cx.barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = ctrl.launches - l0
+    clocks = sampler.stop() if (cx.rank == 0 and not sub) else None
+    st = out["status"]
+    # end to end: pageable numpy batch -> H2D + 2 launches + D2H of U / status / intervene / h_min inside scb_backupcbf_solve_host
+    hc = HostContext(cx.local_rank)
+    host_solve(hc, ctrl.params, *batches[0])
+    e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for k in range(e_steps):
+        host_solve(hc, ctrl.params, *batches[k % P])
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+    # one agent alone: the latency a single-robot caller of the drop-in class sees on the device
+    one = [v[:1].contiguous() for v in dins[0]]
+    for _ in range(3):
+        ctrl.solve(*one)
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(20):
+        ctrl.solve(*one)
+    b.record(); torch.cuda.synchronize()
+    ms_max, e2e_max = cx.max_over_ranks([ms, e2e_ms])
+    if cx.rank != 0:
+        return None
+    fl = _profile_json(["r2_flops_backup.json"]).get("flops_per_agent")
+    h2d = sum(v.nbytes for v in batches[0]); d2h = N * (16 + 4 + 4 + 8)
+    rec = {
+        "metric": "control-steps/sec (batched QP solves/s)", "value": cx.world * N / (ms_max * 1e-3), "unit": "control-steps/s",
+        "n_gpus": cx.world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_gpu": N, "backup_steps": 120, "rows_per_qp": 124,
+                   "scene": "scenes.make_evade_batch seed 1234 (+101 per batch): evade hallway + pocket, one bullet per agent",
+                   "launch": "2 launches per step (backup_rollout_kernel<8>: 8 lanes per agent; backup_qp_kernel<8,16>), eager",
+                   "l2_policy": f"{P} distinct batches alternated; compute-bound (189 MB of rows per step stream through L2)",
+                   "solver": {"optimal_frac": float((st == 0).float().mean()), "intervene_frac": float(out["intervene"].float().mean())},
+                   "single_agent_latency_ms": a.elapsed_time(b) / 20},
+        "e2e": {"value": cx.world * N / (e2e_max * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps_timed": e_steps, "how": "scb_backupcbf_solve_host on pageable numpy buffers (staged H2D, 2 launches, D2H, sync), wall clock"},
+        "gpu_launches": launches,
+        "roofline": fp64_roofline(fl * N if fl else None, ms_max,
+                                  {"kernel_ms_how": "both launches of one step (rollout ~91 %, QP ~9 % under ncu: profiles/r2_ncu_backup_summary.txt), CUDA events",
+                                   "flops_source": "ncu-counted 2*DFMA + DADD + DMUL per agent (profiles/r2_flops_backup.json) x agents per step" if fl else
+                                                   "profiles/r2_flops_backup.json missing",
+                                   "note": "chain of dependent fp64 sqrt / div per backup step: issue / FP64-pipe bound (ncu: issue slots 70 %, FP64 pipe 41 % busy), HBM traffic negligible"}),
+    }
+    if clocks is not None:
+        rec["clocks"] = clocks
+    if not args.no_cpu and not sub:
+        procs = min(16, os.cpu_count() or 1)
+        v, n = backup_cpu_rate(*batches[0], procs, 12)
+        rec["cpu_baseline"] = {"value": v, "unit": "control-steps/s", "cores": procs, "kind": "port",
+                               "sample": f"{n} agents of the same batch through oracle/backup_cbf.py (numpy restatement of backup_cbf_qp.py:563-794, exact QP), {procs} processes"}
+    return rec
+
+
 def reference_arm(args, w):
     """The reference's own CPU implementation of this path (cvxpy->GUROBI, do-mpc->IPOPT) cannot be installed (no
     network, no wheels); this arm times the reference-equivalent CPU path: the oracle port, one agent at a time per
@@ -859,6 +967,19 @@ def reference_arm(args, w):
     procs = os.cpu_count() or 1
     if w.get("loop"):
         return reference_loop(args, w, procs)
+    if w["controller"] == "backup_cbf_qp":
+        batch = scenes.make_evade_batch(4096, seed=1234)
+        per = max(4, min(16, 2 * args.steps))
+        val, n = backup_cpu_rate(*batch, procs, per)
+        sample = f"{n} agents of the backup scene (seed 1234) through oracle/backup_cbf.py, {procs} processes"
+        print(json.dumps({
+            "impl": "reference", "metric": "control-steps/sec (batched QP solves/s)", "value": val, "unit": "control-steps/s",
+            "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": 1e3 * n / val, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": f"{w['name']}: {w['desc']}"},
+            "cpu_baseline": {"value": val, "unit": "control-steps/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "reference's cvxpy / OSQP stack is not installable here; this is the numpy restatement of backup_cbf_qp.py:563-794"}))
+        return
     per_step = {"cbf_qp": 16, "optimal_decay_cbf_qp": 64, "mpc_cbf": 3}[w["controller"]] * procs
     budget_s = 120.0
     slice_s = None
@@ -905,7 +1026,7 @@ def reference_arm(args, w):
 
 
 # --------------------------------------------------------------------------------------- main
-SUB_STEPS = {"cfg3": (10, 3), "cfg4": (200, 10), "cfg5": (2, 1)}     # (steps, warmup) of the sub-records of the N = 1 line
+SUB_STEPS = {"cfg3": (10, 3), "cfg4": (200, 10), "cfg5": (2, 1), "backup": (10, 3)}     # (steps, warmup) of the sub-records of the N = 1 line
 
 
 def main():
@@ -938,6 +1059,8 @@ def main():
         if default_run:
             steps = min(steps, 5)                  # ~40 ms x N_gpu^-1 ... 300 ms per step: a handful is plenty
         out = run_cfg5(args, w, cx, steps, min(warmup, 3))
+    elif name == "backup":
+        out = run_backup(args, w, cx, min(steps, 50), min(warmup, 5))
     else:
         out = run_single(args, w, cx, steps, warmup)
         if default_run and world == 1 and not args.no_sub:
@@ -946,7 +1069,8 @@ def main():
                 sw = dict(WORKLOADS[sname], name=sname)
                 try:
                     rec = run_cfg5(args, sw, cx, s_steps, s_warm, sub=True) if sname == "cfg5" else \
-                        run_single(args, sw, cx, s_steps, s_warm, sub=True)
+                        (run_backup(args, sw, cx, s_steps, s_warm, sub=True) if sname == "backup" else
+                         run_single(args, sw, cx, s_steps, s_warm, sub=True))
                     subs[sname] = {k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "e2e",
                                                        "gpu_launches", "roofline") if k in rec}
                 except Exception as e:             # a sub-record must never take the headline down with it

@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define SCB_VERSION 200
+#define SCB_VERSION 210
 
 /* model ids (robot_spec['model'], robots/robot.py:65-175) */
 enum scb_model {
@@ -224,6 +224,54 @@ int scb_mpccbf_solve_host(scb_ctx* ctx, const scb_params* p, int N, int M, int H
                           const double* OBS, long obs_stride_agent, const int32_t* nobs,
                           double* U, int32_t* status, double* pred_x, double* pred_u,
                           int32_t* iters, double* kkt, uint64_t* active);
+
+/* ---- Backup-CBF QP  (position_control/backup_cbf_qp.py) ---------------------------------- */
+/* BackupCBF.solve_control_problem (backup_cbf_qp.py:563-794) for N double-integrator agents in the evade scene
+ * (envs/evade_env.py; examples/evade/test_evade.py --algo backupcbf): per agent, rollout of the backup policy
+ * (EvadeBackupController, position_control/backup_controller.py:420-575) over n_backup = int(backup_horizon / dt) steps of
+ * DoubleIntegrator2D.step with forward-difference sensitivities (:236-318), one CBF row per backup step + the terminal
+ * row (:613-673), QP in inputs scaled by a_max with |z| <= 1 (:676-733) and the reference's two fall-backs when the QP
+ * is infeasible (:768-783).  The other scenes of that file (drift car: 8-state Fiala-tyre model) are not covered. */
+typedef struct scb_backup_params {
+  /* EvadeEnv geometry (evade_env.py:62-76) */
+  double hallway_length, half_width;
+  double pocket_x_min, pocket_x_max, pocket_y_min, pocket_y_max;
+  double center_x, center_y;                       /* pocket centre = target of the backup policy */
+  double goal_x_min, goal_x_max, goal_y_min, goal_y_max;   /* goal_bounds of EvadeBackupController (test_evade.py:308-313) */
+  /* robot_spec (test_evade.py:74-88) + BackupCBF parameters (backup_cbf_qp.py:91-110) */
+  double radius, a_max, v_max, safety_margin;
+  double Kp, Kd;                                   /* backup_controller.py:449-450 */
+  double dt, backup_horizon;
+  double alpha, alpha_terminal;                    /* class-K gains, 1.0 and 2.0 */
+  double q0, q1;                                   /* Q_u */
+  int32_t use_goal;                                /* goal_bounds is not None */
+  int32_t n_backup;                                /* N = int(backup_horizon / dt), computed by the caller; <= 252 */
+} scb_backup_params;
+
+/* the evade example's defaults (test_evade.py:60-100) */
+void scb_backup_params_default(scb_backup_params* p);
+size_t scb_backup_params_sizeof(void);
+/* uint64 words of one agent's active mask: bit r < n_backup - 1 = safety row of backup step r + 1, bit n_backup - 1 = the
+ * terminal row, bits n_backup + {0, 1} = z_{0,1} >= -1, n_backup + {2, 3} = z_{0,1} <= 1 */
+int  scb_backup_active_words(int n_backup);
+
+/* X [N, 4], Uref [N, 2] (the nominal input, backup_cbf_qp.py:173-180).  MOV [N, K, 8] (mov_stride_agent = 8 K) or one
+ * shared [K, 8] list (stride 0): moving obstacles [x, y, vx, vy, length, width, radius, kind] (kind 0 absent / inactive,
+ * 1 rectangle, 2 circle) at x + vx t, y + vy t -- the reference's callable t -> dict (test_evade.py:373-385).
+ * Out: U [N, 2]; status [N] (SCB_OPTIMAL, or SCB_INFEASIBLE = QP infeasible, U is the reference's fall-back: clipped u_ref
+ * when h_min > 0.01, else the backup policy's input); intervene [N] = is_using_backup() (:757-766); h_min [N] = _last_h_min;
+ * optional phi [N, n_backup, 4] = latest_backup_trajectory, rows [N, n_backup, 3] = (lhs_0, lhs_1, rhs) of every row before
+ * the reference's ||lhs|| > 1e-6 filter, active [N, scb_backup_active_words]. */
+/* With `rows` and `h_min` given the solve is two launches (rollout + rows, then the QP: 8x more agents resident per SM);
+ * without, one fused launch that keeps the rows in shared memory. */
+int scb_backupcbf_solve(const scb_backup_params* p, int N, int K,
+                        const double* X, const double* Uref, const double* MOV, long mov_stride_agent,
+                        double* U, int32_t* status, int32_t* intervene, double* h_min,
+                        double* phi, double* rows, uint64_t* active, void* stream);
+int scb_backupcbf_solve_host(scb_ctx* ctx, const scb_backup_params* p, int N, int K,
+                             const double* X, const double* Uref, const double* MOV, long mov_stride_agent,
+                             double* U, int32_t* status, int32_t* intervene, double* h_min,
+                             double* phi, double* rows, uint64_t* active);
 
 /* ---- closed loop: the rest of LocalTrackingController.control_step()  (tracking.py:559-668) ---- */
 /* Everything either side of the solve, for N agents on the device, so that run_all_steps

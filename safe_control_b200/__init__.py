@@ -9,7 +9,8 @@ from .params import resolve_params, NotCompatibleError  # noqa: F401
 from .batched import (BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, BatchedOptimalDecayMPCCBF,  # noqa: F401
                       HostContext)
 from .tracking import BatchedTrackingController  # noqa: F401
+from .backup import BatchedBackupCBF, EvadeSceneParams  # noqa: F401
 from ._abi import MODEL_IDS, OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL  # noqa: F401
 
-__all__ = ["BatchedTrackingController", "BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "BatchedOptimalDecayMPCCBF", "HostContext", "resolve_params",
+__all__ = ["BatchedTrackingController", "BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "BatchedOptimalDecayMPCCBF", "BatchedBackupCBF", "EvadeSceneParams", "HostContext", "resolve_params",
            "NotCompatibleError", "MODEL_IDS", "OPTIMAL", "INFEASIBLE", "MAXITER", "NUMERICAL"]

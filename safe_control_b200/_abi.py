@@ -45,7 +45,16 @@ class ScbParams(C.Structure):
     ]
 
 
+class ScbBackupParams(C.Structure):
+    """Mirror of `struct scb_backup_params` (include/scb.h): evade scene + Backup-CBF parameters."""
+    _fields_ = [(k, C.c_double) for k in (
+        "hallway_length", "half_width", "pocket_x_min", "pocket_x_max", "pocket_y_min", "pocket_y_max", "center_x", "center_y",
+        "goal_x_min", "goal_x_max", "goal_y_min", "goal_y_max", "radius", "a_max", "v_max", "safety_margin", "Kp", "Kd",
+        "dt", "backup_horizon", "alpha", "alpha_terminal", "q0", "q1")] + [("use_goal", C.c_int32), ("n_backup", C.c_int32)]
+
+
 _P = C.POINTER(ScbParams)
+_B = C.POINTER(ScbBackupParams)
 _vp = C.c_void_p
 
 SM_IDLE, SM_TRACK, SM_STOP, SM_ROTATE = 0, 1, 2, 3
@@ -106,6 +115,11 @@ PROTOTYPES = {
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "scb_mpccbf_solve_host": (C.c_int, [_vp, _P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_long, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_backup_params_default": (None, [_B]),
+    "scb_backup_params_sizeof": (C.c_size_t, []),
+    "scb_backup_active_words": (C.c_int, [C.c_int]),
+    "scb_backupcbf_solve": (C.c_int, [_B, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_backupcbf_solve_host": (C.c_int, [_vp, _B, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_select_obstacles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),
     "scb_track_sizeof": (C.c_size_t, []),
     "scb_control_step": (C.c_int, [_P, _T, _vp]),

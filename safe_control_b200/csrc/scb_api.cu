@@ -34,6 +34,7 @@ SCB_MPC_INSTANTIATE(kMpcSeBase + SCB_DOUBLE_INTEGRATOR_2D)
 #include "scb_mpc_kernels.cuh"
 #endif
 #include "scb_track_kernels.cuh"
+#include "scb_backup_kernels.cuh"
 
 using namespace scb;
 
@@ -837,3 +838,112 @@ int scb_mpccbf_solve_host(scb_ctx* c, const scb_params* p, int N, int M, int H, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------- Backup-CBF QP
+static int backup_check(const scb_backup_params* p, int N, int K) {
+  if (!p || N < 0 || K < 0) return SCB_ERR_BAD_ARG;
+  if (p->n_backup < 1 || !(p->dt > 0.0) || !(p->a_max > 0.0) || !(p->q0 > 0.0) || !(p->q1 > 0.0)) return SCB_ERR_BAD_ARG;
+  if (p->n_backup + 4 > 256) return SCB_ERR_TOO_LARGE;
+  return SCB_OK;
+}
+
+extern "C" int scb_backupcbf_solve(const scb_backup_params* p, int N, int K, const double* X, const double* Uref,
+                                   const double* MOV, long mov_stride, double* U, int32_t* status, int32_t* intervene,
+                                   double* h_min, double* phi, double* rows, uint64_t* active, void* stream) {
+  int rc = backup_check(p, N, K);
+  if (rc != SCB_OK) return rc;
+  if (N == 0) return SCB_OK;
+  if (!X || !Uref || !U || !status || (K > 0 && !MOV) || mov_stride < 0) return SCB_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = p->n_backup, words = scb_backup_active_words(nb);
+  int forced = 0;
+  if (const char* e = getenv("SCB_BK_LANES")) forced = atoi(e);
+  if (rows && h_min && !getenv("SCB_BK_FUSED")) {
+    // two launches (the caller gave the [N, n_backup, 3] row buffer): rollout with 8 lanes per agent (5 carry the step
+    // variants, 4 the barrier variants) -- a warp per agent when the batch cannot fill the device anyway -- then the QP
+    const int rl = (forced == 8 || forced == 32) ? forced : (((long)N * 8 > (long)sm_count_of_current() * 1024) ? 8 : 32);
+    const unsigned rgrid = (unsigned)((N + kBkBlock / rl - 1) / (kBkBlock / rl));
+    if (rl == 8) backup_rollout_kernel<8><<<rgrid, kBkBlock, 0, s>>>(*p, N, K, X, K > 0 ? MOV : nullptr, mov_stride, h_min, phi, rows);
+    else         backup_rollout_kernel<32><<<rgrid, kBkBlock, 0, s>>>(*p, N, K, X, K > 0 ? MOV : nullptr, mov_stride, h_min, phi, rows);
+    const int ql = (forced == 8 && nb + 4 <= 128) ? 8 : ((forced == 32 || nb + 4 > 128 || (long)N * 32 <= (long)sm_count_of_current() * 512) ? 32 : 8);
+    const unsigned qgrid = (unsigned)((N + kBkBlock / ql - 1) / (kBkBlock / ql));
+#define GQ(L, R) backup_qp_kernel<L, R><<<qgrid, kBkBlock, 0, s>>>(*p, N, X, Uref, rows, h_min, U, status, intervene, active, words);
+    if (ql == 8) {
+      if (nb + 4 <= 64) GQ(8, 8) else GQ(8, 16)
+    } else {
+      if (nb + 4 <= 64) GQ(32, 2) else if (nb + 4 <= 128) GQ(32, 4) else GQ(32, 8)
+    }
+#undef GQ
+    CK(cudaGetLastError());
+    return SCB_OK;
+  }
+  // one fused launch: lane group of 8 for batches that fill the device, a warp per agent for small ones (rows spread
+  // thinner, shorter QP scan) and for horizons whose rows do not fit 8 x 16 registers
+  int lanes = (nb + 4 <= 128 && (long)N * 32 > (long)sm_count_of_current() * 512) ? 8 : 32;
+  if (forced == 8 && nb + 4 <= 128) lanes = 8;
+  if (forced == 32) lanes = 32;
+  const int groups = kBkBlock / lanes;
+  const size_t smem = (size_t)groups * bk_agent_doubles(nb) * sizeof(double);
+  const unsigned grid = (unsigned)((N + groups - 1) / groups);
+#define GO(L, R)                                                                                                          \
+  {                                                                                                                       \
+    auto kern = backupcbf_kernel<L, R>;                                                                                   \
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) \
+      return SCB_ERR_TOO_LARGE;                                                                                           \
+    kern<<<grid, kBkBlock, smem, s>>>(*p, N, K, X, Uref, K > 0 ? MOV : nullptr, mov_stride, U, status, intervene, h_min, phi, \
+                                      rows, active, words);                                                               \
+  }
+  if (lanes == 8) {
+    if (nb + 4 <= 64) GO(8, 8) else GO(8, 16)
+  } else {
+    if (nb + 4 <= 64) GO(32, 2) else if (nb + 4 <= 128) GO(32, 4) else GO(32, 8)
+  }
+#undef GO
+  CK(cudaGetLastError());
+  return SCB_OK;
+}
+
+extern "C" int scb_backupcbf_solve_host(scb_ctx* c, const scb_backup_params* p, int N, int K, const double* X,
+                                        const double* Uref, const double* MOV, long mov_stride, double* U, int32_t* status,
+                                        int32_t* intervene, double* h_min, double* phi, double* rows, uint64_t* active) {
+  if (!c) return SCB_ERR_BAD_ARG;
+  int rc = backup_check(p, N, K);
+  if (rc != SCB_OK) return rc;
+  if (N == 0) return SCB_OK;
+  if (!X || !Uref || !U || !status || (K > 0 && !MOV) || mov_stride < 0) return SCB_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  const int nb = p->n_backup, words = scb_backup_active_words(nb);
+  const size_t mov_el = (K == 0) ? 0 : (mov_stride == 0 ? (size_t)K * kBkMov : (size_t)N * (size_t)mov_stride);
+  const size_t need = padded((size_t)N * 4 * 8) + padded((size_t)N * 2 * 8) * 2 + padded(mov_el * 8) + padded((size_t)N * 4) * 2 +
+                      padded((size_t)N * 8) + padded((size_t)N * nb * 4 * 8) + padded((size_t)N * nb * 3 * 8) +
+                      padded((size_t)N * words * 8);
+  rc = ctx_reserve(c, need);
+  if (rc != SCB_OK) return rc;
+  Carver cv{c->dbuf, 0};
+  double* dX = cv.take<double>((size_t)N * 4);
+  double* dUr = cv.take<double>((size_t)N * 2);
+  double* dU = cv.take<double>((size_t)N * 2);
+  double* dM = cv.take<double>(mov_el);
+  int32_t* dS = cv.take<int32_t>(N);
+  int32_t* dI = cv.take<int32_t>(N);
+  double* dH = cv.take<double>(N);
+  double* dP = cv.take<double>((size_t)N * nb * 4);
+  double* dR = cv.take<double>((size_t)N * nb * 3);
+  uint64_t* dA = cv.take<uint64_t>((size_t)N * words);
+  H2D(dX, X, (size_t)N * 4, double);
+  H2D(dUr, Uref, (size_t)N * 2, double);
+  if (mov_el) H2D(dM, MOV, mov_el, double);
+  rc = scb_backupcbf_solve(p, N, K, dX, dUr, mov_el ? dM : nullptr, mov_stride, dU, dS, intervene ? dI : nullptr, dH,
+                           phi ? dP : nullptr, dR, active ? dA : nullptr, c->stream);       // (row buffer given: two launches)
+  if (rc != SCB_OK) return rc;
+  c->launches += 2;
+  D2H(U, dU, (size_t)N * 2, double);
+  D2H(status, dS, N, int32_t);
+  if (intervene) D2H(intervene, dI, N, int32_t);
+  if (h_min) D2H(h_min, dH, N, double);
+  if (phi) D2H(phi, dP, (size_t)N * nb * 4, double);
+  if (rows) D2H(rows, dR, (size_t)N * nb * 3, double);
+  if (active) D2H(active, dA, (size_t)N * words, uint64_t);
+  CK(cudaStreamSynchronize(c->stream));
+  return SCB_OK;
+}

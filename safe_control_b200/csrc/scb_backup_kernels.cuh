@@ -1,0 +1,92 @@
+// Backup-CBF QP kernel: one lane group per agent (scb_backup.cuh), groups packed into 128-thread CTAs.
+#pragma once
+#include "scb_backup.cuh"
+
+namespace scb {
+
+constexpr int kBkBlock = 128;
+
+SCB_HD int bk_agent_doubles(int n_backup) {            // scratch + rows, padded to a multiple of 4 doubles + 4 (bank spread)
+  return ((kBkScratch + 3 * n_backup + 3) & ~3) + 4;
+}
+
+template <int LANES, int RPL>
+__global__ void __launch_bounds__(kBkBlock)
+backupcbf_kernel(const scb_backup_params p, int N, int K, const double* __restrict__ X, const double* __restrict__ Uref,
+                 const double* __restrict__ MOV, long mov_stride, double* __restrict__ U, int32_t* __restrict__ status,
+                 int32_t* __restrict__ intervene, double* __restrict__ h_min, double* __restrict__ phi,
+                 double* __restrict__ rows_out, uint64_t* __restrict__ active, int words) {
+  extern __shared__ double scb_bk_smem_[];
+  constexpr int kGroups = kBkBlock / LANES;
+  const int g = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  const long agent = (long)blockIdx.x * kGroups + g;
+  if (agent >= N) return;                              // (whole groups leave together)
+  const int nb = p.n_backup;
+  double* scr = scb_bk_smem_ + (size_t)g * bk_agent_doubles(nb);
+  double* rows = scr + kBkScratch;
+  BackupOut o;
+  backup_agent<LANES, RPL>(p, X + agent * 4, Uref + agent * 2, MOV ? MOV + agent * mov_stride : nullptr, MOV ? K : 0, scr,
+                           rows, phi ? phi + agent * (long)nb * 4 : nullptr, o);
+  if (rows_out)
+    for (int k = lane; k < 3 * nb; k += LANES) rows_out[agent * (long)nb * 3 + k] = rows[k];
+  if (lane == 0) {
+    U[agent * 2] = o.u0; U[agent * 2 + 1] = o.u1;
+    status[agent] = o.status;
+    if (intervene) intervene[agent] = o.intervene;
+    if (h_min) h_min[agent] = o.h_min;
+    if (active) {
+      for (int w = 0; w < words; ++w) {
+        uint64_t bits = 0ull;
+        if (o.w0 >= 0 && o.lam0 > 0.0 && (o.w0 >> 6) == w) bits |= 1ull << (o.w0 & 63);
+        if (o.w1 >= 0 && o.lam1 > 0.0 && (o.w1 >> 6) == w) bits |= 1ull << (o.w1 & 63);
+        active[agent * words + w] = bits;
+      }
+    }
+  }
+}
+
+// ---- the same work as two launches: rollout + rows (few registers, 352 B of shared memory per agent -> the SM holds 8x
+// more agents than the fused kernel, and the rollout is a chain of dependent fp64 sqrt / div latencies), then the QP ----
+template <int LANES>
+__global__ void __launch_bounds__(kBkBlock)
+backup_rollout_kernel(const scb_backup_params p, int N, int K, const double* __restrict__ X, const double* __restrict__ MOV,
+                      long mov_stride, double* __restrict__ h_min, double* __restrict__ phi, double* __restrict__ rows) {
+  constexpr int kGroups = kBkBlock / LANES;
+  __shared__ double scr_all[kGroups * kBkScratch];
+  const int g = threadIdx.x / LANES;
+  const long agent = (long)blockIdx.x * kGroups + g;
+  if (agent >= N) return;
+  const int nb = p.n_backup;
+  const double h = backup_rollout<LANES>(p, X + agent * 4, MOV ? MOV + agent * mov_stride : nullptr, MOV ? K : 0,
+                                         scr_all + g * kBkScratch, rows + agent * (long)nb * 3,
+                                         phi ? phi + agent * (long)nb * 4 : nullptr);
+  if (threadIdx.x % LANES == 0) h_min[agent] = h;
+}
+
+template <int LANES, int RPL>
+__global__ void __launch_bounds__(kBkBlock)
+backup_qp_kernel(const scb_backup_params p, int N, const double* __restrict__ X, const double* __restrict__ Uref,
+                 const double* __restrict__ rows, const double* __restrict__ h_min, double* __restrict__ U,
+                 int32_t* __restrict__ status, int32_t* __restrict__ intervene, uint64_t* __restrict__ active, int words) {
+  constexpr int kGroups = kBkBlock / LANES;
+  const int g = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  const long agent = (long)blockIdx.x * kGroups + g;
+  if (agent >= N) return;
+  BackupOut o;
+  backup_qp<LANES, RPL>(p, X + agent * 4, Uref + agent * 2, rows + agent * (long)p.n_backup * 3, h_min[agent], o);
+  if (lane == 0) {
+    U[agent * 2] = o.u0; U[agent * 2 + 1] = o.u1;
+    status[agent] = o.status;
+    if (intervene) intervene[agent] = o.intervene;
+    if (active) {
+      for (int w = 0; w < words; ++w) {
+        uint64_t bits = 0ull;
+        if (o.w0 >= 0 && o.lam0 > 0.0 && (o.w0 >> 6) == w) bits |= 1ull << (o.w0 & 63);
+        if (o.w1 >= 0 && o.lam1 > 0.0 && (o.w1 >> 6) == w) bits |= 1ull << (o.w1 & 63);
+        active[agent * words + w] = bits;
+      }
+    }
+  }
+}
+
+}  // namespace scb

@@ -88,6 +88,37 @@ int scb_mpc_active_words(const scb_params* p, int M, int H) {
 }
 
 
+size_t scb_backup_params_sizeof(void) { return sizeof(scb_backup_params); }
+int scb_backup_active_words(int n_backup) { return n_backup < 1 ? SCB_ERR_BAD_ARG : (n_backup + 4 + 63) / 64; }
+
+// examples/evade/test_evade.py:60-100 (EnvironmentConfig, RobotConfig, SimulationConfig), envs/evade_env.py:62-76
+void scb_backup_params_default(scb_backup_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  const double hallway_length = 60.0, hallway_width = 4.0, pocket_x = 25.0, pocket_length = 10.0, pocket_width = 4.0,
+               goal_length = 5.0;
+  p->hallway_length = hallway_length;
+  p->half_width = hallway_width / 2;
+  p->pocket_x_min = pocket_x;
+  p->pocket_x_max = pocket_x + pocket_length;
+  p->pocket_y_min = p->half_width;
+  p->pocket_y_max = p->half_width + pocket_width;
+  p->center_x = (p->pocket_x_min + p->pocket_x_max) / 2;
+  p->center_y = (p->pocket_y_min + p->pocket_y_max) / 2;
+  p->goal_x_min = hallway_length - goal_length;
+  p->goal_x_max = hallway_length;
+  p->goal_y_min = -p->half_width;
+  p->goal_y_max = p->half_width;
+  p->use_goal = 1;
+  p->radius = 0.5; p->a_max = 2.0; p->v_max = 1.5; p->safety_margin = 0.5;
+  p->Kp = 2.0; p->Kd = 2.0;
+  p->dt = 0.1; p->backup_horizon = 12.0;
+  p->n_backup = (int)(p->backup_horizon / p->dt);
+  p->alpha = 1.0; p->alpha_terminal = 2.0;
+  p->q0 = 1.0; p->q1 = 1.0;
+}
+
+
 int scb_params_default(scb_params* p, int model, const char* controller) {
   if (!p || !controller) return SCB_ERR_BAD_ARG;
   memset(p, 0, sizeof(*p));

@@ -274,3 +274,30 @@ def make_scene(model, N, M, seed=1234, dense=False, dynamic=None, optimal_decay=
     return dict(model=model, spec=spec, X=np.ascontiguousarray(X), U_ref=np.ascontiguousarray(U_ref),
                 goal=np.ascontiguousarray(goal), OBS=np.ascontiguousarray(OBS), nobs=nobs, obs_idx=idx,
                 scene_obs=scene, u_prev=np.zeros((N, nu)), L=L)
+
+
+def make_evade_batch(n, seed=1234, k_mov=1, hallway_length=60.0, pocket=(25.0, 35.0, 2.0, 6.0), a_max=2.0, v_max=1.5):
+    """Seeded batch for the Backup-CBF QP path (examples/evade/test_evade.py's scene): states spread over the hallway (70 %)
+    and the pocket / its mouth (30 %), speeds up to v_max, nominal inputs up to 1.25 a_max, one bullet per agent somewhere
+    between its spawn point and the end of the hallway (10 % inactive) [+ optional slow discs].
+    -> X [n, 4], U_ref [n, 2], MOV [n, k_mov, 8] (safe_control_b200.backup row layout)."""
+    from .backup import bullet_row, KIND_CIRCLE, KIND_NONE
+    rng = np.random.default_rng(seed)
+    X = np.zeros((n, 4)); MOV = np.zeros((n, max(k_mov, 1), 8))
+    X[:, 0] = rng.uniform(0.3, hallway_length - 0.3, n)
+    in_pocket = rng.random(n) < 0.3
+    X[:, 0] = np.where(in_pocket, rng.uniform(pocket[0] + 0.2, pocket[1] - 0.2, n), X[:, 0])
+    X[:, 1] = np.where(in_pocket, rng.uniform(0.0, pocket[3] - 0.6, n), rng.uniform(-1.6, 1.6, n))
+    X[:, 2:] = rng.uniform(-1.0, 1.0, (n, 2)) * rng.uniform(0.0, v_max, (n, 1))
+    U_ref = rng.uniform(-1.25 * a_max, 1.25 * a_max, (n, 2))
+    bx = rng.uniform(-10.0, hallway_length + 2.0, n); act = rng.random(n) < 0.9
+    base = bullet_row(0.0)
+    MOV[:, 0, :] = base[None, :]
+    MOV[:, 0, 0] = bx + base[0]
+    MOV[:, 0, 7] = np.where(act, base[7], float(KIND_NONE))
+    for k in range(1, k_mov):
+        MOV[:, k, 0] = rng.uniform(0, hallway_length, n); MOV[:, k, 1] = rng.uniform(-1.5, 1.5, n)
+        MOV[:, k, 2] = rng.uniform(-0.5, 0.5, n); MOV[:, k, 3] = rng.uniform(-0.2, 0.2, n)
+        MOV[:, k, 6] = rng.uniform(0.2, 0.8, n)
+        MOV[:, k, 7] = np.where(rng.random(n) < 0.5, float(KIND_CIRCLE), float(KIND_NONE))
+    return np.ascontiguousarray(X), np.ascontiguousarray(U_ref), np.ascontiguousarray(MOV)

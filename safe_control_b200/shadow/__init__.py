@@ -19,7 +19,7 @@ import os
 import sys
 
 SHADOW_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "safe_control", "position_control")
-MODULES = ("cbf_qp", "mpc_cbf", "optimal_decay_cbf_qp", "optimal_decay_mpc_cbf")
+MODULES = ("cbf_qp", "mpc_cbf", "optimal_decay_cbf_qp", "optimal_decay_mpc_cbf", "backup_cbf_qp")
 
 
 def install():

@@ -5,6 +5,7 @@
 // libscb.so + a CUDA device.
 #include "../../safe_control_b200/csrc/scb_qp.cuh"
 #include "../../safe_control_b200/csrc/scb_track.cuh"
+#include "../../safe_control_b200/csrc/scb_backup.cuh"
 #include <vector>
 #ifdef SCB_HOSTSIM_MPC
 #include "../../safe_control_b200/csrc/scb_mpc.cuh"
@@ -317,6 +318,32 @@ int hostsim_control_step(const scb_params* p, const scb_track* t) {
       POSTCASE(SCB_QUAD_2D)
       default: return SCB_ERR_UNSUPPORTED;
     }
+  }
+  return 0;
+}
+
+// Backup-CBF QP bodies (scb_backup.cuh), one agent after the other; same outputs as scb_backupcbf_solve
+int hostsim_backupcbf_solve(const scb_backup_params* p, int N, int K, const double* X, const double* Uref, const double* MOV,
+                            long mov_stride, double* U, int32_t* status, int32_t* intervene, double* h_min, double* phi,
+                            double* rows, uint64_t* active) {
+  const int nb = p->n_backup, words = scb_backup_active_words(nb);
+  if (nb < 1 || nb + 4 > 256) return SCB_ERR_TOO_LARGE;
+  std::vector<double> scr(kBkScratch), rw((size_t)3 * nb);
+  for (long a = 0; a < N; ++a) {
+    BackupOut o;
+    backup_agent<1, 256>(*p, X + a * 4, Uref + a * 2, K > 0 ? MOV + a * mov_stride : nullptr, K, scr.data(), rw.data(),
+                         phi ? phi + a * nb * 4 : nullptr, o);
+    U[a * 2] = o.u0; U[a * 2 + 1] = o.u1; status[a] = o.status;
+    if (intervene) intervene[a] = o.intervene;
+    if (h_min) h_min[a] = o.h_min;
+    if (rows) for (int k = 0; k < 3 * nb; ++k) rows[a * nb * 3 + k] = rw[k];
+    if (active)
+      for (int w = 0; w < words; ++w) {
+        uint64_t bits = 0ull;
+        if (o.w0 >= 0 && o.lam0 > 0.0 && (o.w0 >> 6) == w) bits |= 1ull << (o.w0 & 63);
+        if (o.w1 >= 0 && o.lam1 > 0.0 && (o.w1 >> 6) == w) bits |= 1ull << (o.w1 & 63);
+        active[a * words + w] = bits;
+      }
   }
   return 0;
 }

@@ -37,7 +37,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_struct_mirror_and_helpers(lib):
     assert lib.scb_params_sizeof() == C.sizeof(_abi.ScbParams)
     assert lib.scb_track_sizeof() == C.sizeof(_abi.ScbTrack)
-    assert lib.scb_version() == 200
+    assert lib.scb_version() == 210
     assert b"ok" == lib.scb_strerror(0)
     assert lib.scb_active_words(16, 2) == 1 and lib.scb_active_words(61, 2) == 2
     nx, nu = C.c_int(), C.c_int()

@@ -27,7 +27,7 @@ def run_cbfqp(ctrl, sc_or_arrays):
 def test_library_loads_and_reports_device():
     from safe_control_b200._lib import lib
     assert lib().scb_device_count() >= 1
-    assert lib().scb_version() == 200
+    assert lib().scb_version() == 210
 
 
 def test_reference_fixtures_cbfqp_rows_and_solve():
