@@ -55,6 +55,11 @@ WORKLOADS["loop4"] = dict(model="KinematicBicycle2D_C3BF", controller="optimal_d
 WORKLOADS["backup"] = dict(model="DoubleIntegrator2D", controller="backup_cbf_qp", N=65536, M=1, H=120, dynamic=True,
                            desc="SURVEY 8f-3: 65536 DoubleIntegrator2D agents in the evade scene, Backup-CBF QP "
                                 "(120 backup steps with forward-difference sensitivities -> 120 rows + 4 box rows x 2 inputs), 1 moving obstacle each")
+WORKLOADS["gatekeeper"] = dict(model="DoubleIntegrator2D", controller="gatekeeper", N=65536, M=1, H=120, dynamic=True,
+                               desc="SURVEY 8f-4: 65536 DoubleIntegrator2D agents in the evade scene, gatekeeper shield: per step 22 candidates "
+                                    "(nominal prefix of 100, 95, .. 0 steps + 120-step backup rollout) validated against walls + bullet")
+WORKLOADS["mps"] = dict(WORKLOADS["gatekeeper"], controller="mps",
+                        desc="SURVEY 8f-4: 65536 DoubleIntegrator2D agents in the evade scene, MPS shield: one candidate (1 nominal step + 120-step backup rollout) per step")
 L2_BYTES = 126e6
 MIXED = ("DynamicUnicycle2D", "KinematicBicycle2D", "Quad3D")
 
@@ -958,6 +963,101 @@ def run_backup(args, w, cx, steps, warmup, sub=False):
     return rec
 
 
+def _shield_cpu_range(args):
+    """one process of the shield CPU leg: oracle/shielding.py (restatement of gatekeeper.py:553-672 / mps.py:59-160), first
+    control step of agents [lo, hi) (initial backup commitment + the full backward search)"""
+    lo, hi, mode, X, NOMX, NOMU, MOV, STAT = args
+    from oracle import backup_cbf as B, shielding as S
+    sc = B.EvadeScene()
+    t0 = time.perf_counter()
+    for a in range(lo, hi):
+        S.OracleShield(sc, mode=mode).solve(X[a], NOMX[a], NOMU[a], MOV[a], STAT[a])
+    return hi - lo, time.perf_counter() - t0
+
+
+def shield_cpu_rate(mode, arrays, procs, per_proc):
+    import multiprocessing as mp
+    n = procs * per_proc
+    arrs = [a[:n] for a in arrays]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pool.map(_shield_cpu_range, [(0, 1, mode, *arrs)] * procs)
+        t0 = time.perf_counter()
+        pool.map(_shield_cpu_range, [(k * per_proc, (k + 1) * per_proc, mode, *arrs) for k in range(procs)])
+        dt = time.perf_counter() - t0
+    return n / dt, n
+
+
+def run_shield(args, w, cx, steps, warmup, sub=False):
+    """gatekeeper / MPS (SURVEY 8f-4): one step = scb_shield_step over N agents (one launch), shield state resident in HBM;
+    every step all agents re-plan from the same inputs (the steady state of the example: an event every control step)."""
+    torch = cx.torch
+    from safe_control_b200 import BatchedShield, scenes
+    N, T, mode = w["N"], 100, w["controller"]
+    P = 2
+    batches = []
+    for q in range(P):
+        X, _, MOV = scenes.make_evade_batch(N, seed=1234 + 101 * q)
+        NOMX, NOMU = scenes.make_evade_plans(X, T)
+        batches.append((X, NOMX, NOMU, MOV, scenes.evade_static_rects(MOV)))
+    dins = [[torch.from_numpy(v).to(cx.dev) for v in b] for b in batches]
+    sh = BatchedShield(N, mode, None, 0.05, None, T, device=cx.dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for k in range(max(warmup, 3)):
+        out = sh.step(*dins[k % P])
+    cx.barrier()
+    l0 = sh.launches
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(steps):
+        out = sh.step(*dins[k % P])
+    e1.record(); cx.barrier()
+    ms = e0.elapsed_time(e1) / steps
+    # end to end: pinned host batch -> device, one launch, inputs + backup flags back
+    hin = [[torch.from_numpy(v).pin_memory() for v in b] for b in batches]
+    hU = torch.empty((N, 2), dtype=torch.float64).pin_memory(); hB = torch.empty((N,), dtype=torch.int32).pin_memory()
+    def estep(k):
+        for dst, src in zip(dins[k % P], hin[k % P]):
+            dst.copy_(src, non_blocking=True)
+        o = sh.step(*dins[k % P])
+        hU.copy_(o["U"], non_blocking=True); hB.copy_(o["using_backup"], non_blocking=True)
+        torch.cuda.synchronize()
+    estep(0)
+    e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for k in range(e_steps):
+        estep(k)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
+    ms_max, e2e_max = cx.max_over_ranks([ms, e2e_ms])
+    if cx.rank != 0:
+        return None
+    h2d = sum(v.nbytes for v in batches[0]); d2h = N * (16 + 4)
+    rec = {
+        "metric": "control-steps/sec (batched QP solves/s)", "value": cx.world * N / (ms_max * 1e-3), "unit": "control-steps/s",
+        "n_gpus": cx.world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_gpu": N, "nominal_steps": T, "backup_steps": 120,
+                   "scene": "scenes.make_evade_batch seed 1234 (+101 per batch) + make_evade_plans (PD nominal plans)",
+                   "launch": "1 launch per step (shield_step_kernel: 8 lanes per agent for gatekeeper, a thread per agent for MPS), eager",
+                   "l2_policy": f"{P} distinct batches alternated ({h2d / 1e6:.0f} MB of plans + state each, > L2)",
+                   "outcome": {"nominal_leg_committed_frac": float((sh.nsteps > 0).float().mean()),
+                               "mean_committed_nominal_steps": float(sh.nsteps.float().mean()),
+                               "using_backup_frac": float(out["using_backup"].float().mean())}},
+        "e2e": {"value": cx.world * N / (e2e_max * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps_timed": e_steps, "how": "pinned host plans / states / obstacles -> H2D -> scb_shield_step -> D2H of U + backup flags -> sync, wall clock"},
+        "gpu_launches": sh.launches - l0,
+        "roofline": {"bound": "hbm", "achieved": h2d / (ms_max * 1e-3) / 1e9, "peak": hbm_peak()[0], "unit": "GB/s",
+                     "frac": h2d / (ms_max * 1e-3) / 1e9 / hbm_peak()[0], "traffic": None,
+                     "note": "rollout-bound, not bandwidth-bound: every candidate is a chain of 120 dependent closed-loop steps (fp64 sqrt / div); "
+                             "the algorithmic bytes are the nominal plans read once"},
+    }
+    if not args.no_cpu and not sub:
+        procs = min(16, os.cpu_count() or 1)
+        v, n = shield_cpu_rate(mode, batches[0], procs, 4 if mode == "gatekeeper" else 16)
+        rec["cpu_baseline"] = {"value": v, "unit": "control-steps/s", "cores": procs, "kind": "port",
+                               "sample": f"first control step of {n} agents of the same batch through oracle/shielding.py, {procs} processes"}
+    return rec
+
+
 def reference_arm(args, w):
     """The reference's own CPU implementation of this path (cvxpy->GUROBI, do-mpc->IPOPT) cannot be installed (no
     network, no wheels); this arm times the reference-equivalent CPU path: the oracle port, one agent at a time per
@@ -967,6 +1067,19 @@ def reference_arm(args, w):
     procs = os.cpu_count() or 1
     if w.get("loop"):
         return reference_loop(args, w, procs)
+    if w["controller"] in ("gatekeeper", "mps"):
+        X, _, MOV = scenes.make_evade_batch(1024, seed=1234)
+        NOMX, NOMU = scenes.make_evade_plans(X, 100)
+        val, n = shield_cpu_rate(w["controller"], (X, NOMX, NOMU, MOV, scenes.evade_static_rects(MOV)), procs, 4 if w["controller"] == "gatekeeper" else 16)
+        sample = f"first control step of {n} agents of the shield scene (seed 1234) through oracle/shielding.py, {procs} processes"
+        print(json.dumps({
+            "impl": "reference", "metric": "control-steps/sec (batched QP solves/s)", "value": val, "unit": "control-steps/s",
+            "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": 1e3 * n / val, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": f"{w['name']}: {w['desc']}"},
+            "cpu_baseline": {"value": val, "unit": "control-steps/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "control-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "numpy restatement of shielding/gatekeeper.py:553-672 / mps.py:59-160 (the reference itself is pure numpy; its example needs matplotlib)"}))
+        return
     if w["controller"] == "backup_cbf_qp":
         batch = scenes.make_evade_batch(4096, seed=1234)
         per = max(4, min(16, 2 * args.steps))
@@ -1026,7 +1139,7 @@ def reference_arm(args, w):
 
 
 # --------------------------------------------------------------------------------------- main
-SUB_STEPS = {"cfg3": (10, 3), "cfg4": (200, 10), "cfg5": (2, 1), "backup": (10, 3)}     # (steps, warmup) of the sub-records of the N = 1 line
+SUB_STEPS = {"cfg3": (10, 3), "cfg4": (200, 10), "cfg5": (2, 1), "backup": (10, 3), "gatekeeper": (10, 3), "mps": (20, 3)}     # (steps, warmup) of the sub-records of the N = 1 line
 
 
 def main():
@@ -1061,6 +1174,8 @@ def main():
         out = run_cfg5(args, w, cx, steps, min(warmup, 3))
     elif name == "backup":
         out = run_backup(args, w, cx, min(steps, 50), min(warmup, 5))
+    elif name in ("gatekeeper", "mps"):
+        out = run_shield(args, w, cx, min(steps, 50), min(warmup, 5))
     else:
         out = run_single(args, w, cx, steps, warmup)
         if default_run and world == 1 and not args.no_sub:
@@ -1070,7 +1185,8 @@ def main():
                 try:
                     rec = run_cfg5(args, sw, cx, s_steps, s_warm, sub=True) if sname == "cfg5" else \
                         (run_backup(args, sw, cx, s_steps, s_warm, sub=True) if sname == "backup" else
-                         run_single(args, sw, cx, s_steps, s_warm, sub=True))
+                         (run_shield(args, sw, cx, s_steps, s_warm, sub=True) if sname in ("gatekeeper", "mps") else
+                          run_single(args, sw, cx, s_steps, s_warm, sub=True)))
                     subs[sname] = {k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "e2e",
                                                        "gpu_launches", "roofline") if k in rec}
                 except Exception as e:             # a sub-record must never take the headline down with it

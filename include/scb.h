@@ -273,6 +273,43 @@ int scb_backupcbf_solve_host(scb_ctx* ctx, const scb_backup_params* p, int N, in
                              double* U, int32_t* status, int32_t* intervene, double* h_min,
                              double* phi, double* rows, uint64_t* active);
 
+/* ---- gatekeeper / MPS shields  (shielding/gatekeeper.py, shielding/mps.py) ----------------- */
+/* Gatekeeper.solve_control_problem (gatekeeper.py:553-672) and MPS.solve_control_problem (mps.py:59-160) for N
+ * double-integrator agents in the evade scene, with an external nominal trajectory per agent (set_nominal_trajectory, the
+ * way examples/evade/test_evade.py:424-426 drives both): candidate = nominal prefix + backup-policy rollout, validated
+ * state by state against the walls, the bullet's current hitbox and the moving obstacles at t = k dt; gatekeeper searches
+ * the nominal horizon backwards in steps of `discount_steps`, MPS tries one nominal step every call.  The shield's state
+ * (committed trajectory, event timing) stays in caller-owned device arrays between calls. */
+typedef struct scb_shield_params {
+  scb_backup_params scene;        /* geometry, backup policy, robot, dt, n_backup = int(backup_horizon / dt), safety_margin
+                                     (the `safety_margin` constructor argument, gatekeeper.py:45) */
+  double  event_offset;           /* gatekeeper.py:67 */
+  int32_t mode;                   /* 0 gatekeeper, 1 MPS */
+  int32_t discount_steps;         /* max(1, int(horizon_discount / dt)), horizon_discount = 5 dt by default (:68, 601) */
+  int32_t nom_cap;                /* T: capacity of the nominal buffers in STEPS */
+  int32_t reserved;
+} scb_shield_params;
+
+typedef struct scb_shield_state { /* device pointers, caller-owned, persistent across calls */
+  double*  CU;                    /* [N, T + n_backup, 2]      committed_u_traj */
+  double*  CX;                    /* [N, T + n_backup + 1, 4]  committed_x_traj, or NULL */
+  int32_t* clen;                  /* [N] len(committed_u_traj); -1 = no committed trajectory yet (:571) */
+  int32_t* cidx;                  /* [N] current_time_idx */
+  int32_t* nsteps;                /* [N] actual_nominal_steps (committed_horizon = nsteps dt) */
+  double*  next_event;            /* [N] next_event_time */
+} scb_shield_state;
+
+size_t scb_shield_params_sizeof(void);
+/* One control step.  X [N, 4]; NOMX [N, T + 1, 4], NOMU [N, T, 2] = nominal_x_traj / nominal_u_traj, nom_len [N] (may be
+ * NULL = T + 1) = number of nominal STATES available (0 = empty trajectory); MOV / mov_stride_agent as in
+ * scb_backupcbf_solve; STAT [N, 5] (may be NULL) = x_min, x_max, y_min, y_max, active of the obstacle hitbox checked with
+ * the bare robot radius at every candidate state (evade_env.py:454-485: the bullet where it is now).
+ * Out: U [N, 2]; using_backup [N] = is_using_backup() after the call (gatekeeper.py:741-744, mps.py:55-57). */
+int scb_shield_step(const scb_shield_params* p, const scb_shield_state* s, int N, int K,
+                    const double* X, const double* NOMX, const double* NOMU, const int32_t* nom_len,
+                    const double* MOV, long mov_stride_agent, const double* STAT,
+                    double* U, int32_t* using_backup, void* stream);
+
 /* ---- closed loop: the rest of LocalTrackingController.control_step()  (tracking.py:559-668) ---- */
 /* Everything either side of the solve, for N agents on the device, so that run_all_steps
  * (tracking.py:711-747) never leaves the GPU:

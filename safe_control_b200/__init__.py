@@ -10,7 +10,8 @@ from .batched import (BatchedCBFQP, BatchedOptimalDecayCBFQP, BatchedMPCCBF, Bat
                       HostContext)
 from .tracking import BatchedTrackingController  # noqa: F401
 from .backup import BatchedBackupCBF, EvadeSceneParams  # noqa: F401
+from .shield import BatchedShield  # noqa: F401
 from ._abi import MODEL_IDS, OPTIMAL, INFEASIBLE, MAXITER, NUMERICAL  # noqa: F401
 
-__all__ = ["BatchedTrackingController", "BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "BatchedOptimalDecayMPCCBF", "BatchedBackupCBF", "EvadeSceneParams", "HostContext", "resolve_params",
+__all__ = ["BatchedTrackingController", "BatchedCBFQP", "BatchedOptimalDecayCBFQP", "BatchedMPCCBF", "BatchedOptimalDecayMPCCBF", "BatchedBackupCBF", "EvadeSceneParams", "BatchedShield", "HostContext", "resolve_params",
            "NotCompatibleError", "MODEL_IDS", "OPTIMAL", "INFEASIBLE", "MAXITER", "NUMERICAL"]

@@ -53,6 +53,18 @@ class ScbBackupParams(C.Structure):
         "dt", "backup_horizon", "alpha", "alpha_terminal", "q0", "q1")] + [("use_goal", C.c_int32), ("n_backup", C.c_int32)]
 
 
+class ScbShieldParams(C.Structure):
+    """Mirror of `struct scb_shield_params` (include/scb.h)."""
+    _fields_ = [("scene", ScbBackupParams), ("event_offset", C.c_double), ("mode", C.c_int32), ("discount_steps", C.c_int32),
+                ("nom_cap", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ScbShieldState(C.Structure):
+    """Mirror of `struct scb_shield_state`: device pointers of the per-agent shield state."""
+    _fields_ = [("CU", C.c_void_p), ("CX", C.c_void_p), ("clen", C.c_void_p), ("cidx", C.c_void_p), ("nsteps", C.c_void_p),
+                ("next_event", C.c_void_p)]
+
+
 _P = C.POINTER(ScbParams)
 _B = C.POINTER(ScbBackupParams)
 _vp = C.c_void_p
@@ -120,6 +132,9 @@ PROTOTYPES = {
     "scb_backup_active_words": (C.c_int, [C.c_int]),
     "scb_backupcbf_solve": (C.c_int, [_B, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scb_backupcbf_solve_host": (C.c_int, [_vp, _B, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scb_shield_params_sizeof": (C.c_size_t, []),
+    "scb_shield_step": (C.c_int, [C.POINTER(ScbShieldParams), C.POINTER(ScbShieldState), C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
+                                  C.c_long, _vp, _vp, _vp, _vp]),
     "scb_select_obstacles": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_long, _vp, _vp, _vp, _vp]),
     "scb_track_sizeof": (C.c_size_t, []),
     "scb_control_step": (C.c_int, [_P, _T, _vp]),

@@ -947,3 +947,32 @@ extern "C" int scb_backupcbf_solve_host(scb_ctx* c, const scb_backup_params* p, 
   CK(cudaStreamSynchronize(c->stream));
   return SCB_OK;
 }
+
+// ---------------------------------------------------------------------------------------- gatekeeper / MPS
+extern "C" int scb_shield_step(const scb_shield_params* p, const scb_shield_state* st, int N, int K, const double* X,
+                               const double* NOMX, const double* NOMU, const int32_t* nom_len, const double* MOV,
+                               long mov_stride, const double* STAT, double* U, int32_t* using_backup, void* stream) {
+  if (!p || !st) return SCB_ERR_BAD_ARG;
+  int rc = backup_check(&p->scene, N, K);
+  if (rc != SCB_OK) return rc;
+  if (p->nom_cap < 0 || (p->mode != 0 && p->mode != 1) || !(p->event_offset >= 0.0)) return SCB_ERR_BAD_ARG;
+  if (N == 0) return SCB_OK;
+  if (!X || !U || !st->CU || !st->clen || !st->cidx || !st->nsteps || !st->next_event || (p->nom_cap > 0 && (!NOMX || !NOMU)) ||
+      (K > 0 && !MOV) || mov_stride < 0)
+    return SCB_ERR_BAD_ARG;
+  if (p->nom_cap == 0 && !NOMX) return SCB_ERR_BAD_ARG;            // (NOMX always holds at least the start state)
+  cudaStream_t s = (cudaStream_t)stream;
+  // gatekeeper: one candidate per lane (T / discount + 2 of them); MPS has a single candidate: a thread per agent
+  // (8 lanes beat 32 at 22 candidates: 4.0 vs 5.5 ms per 65 536-agent step -- the longest nominal horizon is valid for most
+  // agents, so most of a warp's 22 speculative rollouts are wasted; with 8 lanes a lane walks candidates c, c + 8, c + 16)
+  int lanes = p->mode == 1 ? 1 : 8;
+  if (p->mode == 0 && (long)N * 8 <= (long)sm_count_of_current() * 64) lanes = 32;      // few agents: latency, not throughput
+  if (const char* e = getenv("SCB_SHIELD_LANES")) { const int v = atoi(e); if (v == 1 || v == 8 || v == 32) lanes = v; }
+  const int groups = kBkBlock / lanes;
+  const unsigned grid = (unsigned)((N + groups - 1) / groups);
+  if (lanes == 32)     shield_step_kernel<32><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, K > 0 ? MOV : nullptr, mov_stride, STAT, U, using_backup);
+  else if (lanes == 8) shield_step_kernel<8><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, K > 0 ? MOV : nullptr, mov_stride, STAT, U, using_backup);
+  else                 shield_step_kernel<1><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, K > 0 ? MOV : nullptr, mov_stride, STAT, U, using_backup);
+  CK(cudaGetLastError());
+  return SCB_OK;
+}

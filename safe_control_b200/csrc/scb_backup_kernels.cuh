@@ -1,6 +1,7 @@
 // Backup-CBF QP kernel: one lane group per agent (scb_backup.cuh), groups packed into 128-thread CTAs.
 #pragma once
 #include "scb_backup.cuh"
+#include "scb_shield.cuh"
 
 namespace scb {
 
@@ -86,6 +87,38 @@ backup_qp_kernel(const scb_backup_params p, int N, const double* __restrict__ X,
         active[agent * words + w] = bits;
       }
     }
+  }
+}
+
+// ---- gatekeeper / MPS: one control step of N agents, one lane group per agent (scb_shield.cuh) ----
+template <int LANES>
+__global__ void __launch_bounds__(kBkBlock)
+shield_step_kernel(const scb_shield_params sp, const scb_shield_state st, int N, int K, const double* __restrict__ X,
+                   const double* __restrict__ NOMX, const double* __restrict__ NOMU, const int32_t* __restrict__ nom_len,
+                   const double* __restrict__ MOV, long mov_stride, const double* __restrict__ STAT, double* __restrict__ U,
+                   int32_t* __restrict__ using_backup) {
+  constexpr int kGroups = kBkBlock / LANES;
+  const int g = threadIdx.x / LANES, lane = threadIdx.x % LANES;
+  const long a = (long)blockIdx.x * kGroups + g;
+  if (a >= N) return;
+  const int T = sp.nom_cap, Nb = sp.scene.n_backup;
+  ShieldIO io;
+  io.x = X + a * 4;
+  io.nomx = NOMX + a * (long)(T + 1) * 4;
+  io.nomu = NOMU + a * (long)T * 2;
+  int nl = nom_len ? nom_len[a] : T + 1;
+  io.nom_len = nl < 0 ? 0 : (nl > T + 1 ? T + 1 : nl);
+  io.mov = MOV ? MOV + a * mov_stride : nullptr; io.K = MOV ? K : 0;
+  io.stat = STAT ? STAT + a * 5 : nullptr;
+  io.cu = st.CU + a * (long)(T + Nb) * 2;
+  io.cx = st.CX ? st.CX + a * (long)(T + Nb + 1) * 4 : nullptr;
+  int clen = st.clen[a], cidx = st.cidx[a], nsteps = st.nsteps[a], ub = 0;
+  double ne = st.next_event[a], u[2];
+  shield_agent<LANES>(sp, io, clen, cidx, nsteps, ne, u, ub);
+  if (lane == 0) {
+    st.clen[a] = clen; st.cidx[a] = cidx; st.nsteps[a] = nsteps; st.next_event[a] = ne;
+    U[a * 2] = u[0]; U[a * 2 + 1] = u[1];
+    if (using_backup) using_backup[a] = ub;
   }
 }
 

@@ -88,6 +88,7 @@ int scb_mpc_active_words(const scb_params* p, int M, int H) {
 }
 
 
+size_t scb_shield_params_sizeof(void) { return sizeof(scb_shield_params); }
 size_t scb_backup_params_sizeof(void) { return sizeof(scb_backup_params); }
 int scb_backup_active_words(int n_backup) { return n_backup < 1 ? SCB_ERR_BAD_ARG : (n_backup + 4 + 63) / 64; }
 

@@ -301,3 +301,30 @@ def make_evade_batch(n, seed=1234, k_mov=1, hallway_length=60.0, pocket=(25.0, 3
         MOV[:, k, 6] = rng.uniform(0.2, 0.8, n)
         MOV[:, k, 7] = np.where(rng.random(n) < 0.5, float(KIND_CIRCLE), float(KIND_NONE))
     return np.ascontiguousarray(X), np.ascontiguousarray(U_ref), np.ascontiguousarray(MOV)
+
+
+def make_evade_plans(X, T=100, dt=0.1, a_max=2.0, v_max=1.5):
+    """Nominal plans of the evade example for a batch (examples/evade/test_evade.py:141-168, 387-408: PD law towards the
+    hallway axis at v_max, rolled out with DoubleIntegrator2D.step), vectorised over agents.
+    -> NOMX [n, T + 1, 4], NOMU [n, T, 2]"""
+    n = X.shape[0]
+    NOMX = np.zeros((n, T + 1, 4)); NOMU = np.zeros((n, T, 2))
+    s = np.array(X, dtype=np.float64); NOMX[:, 0] = s
+    for k in range(T):
+        ax = 2.0 * (v_max - s[:, 2]); ay = 2.0 * (0.0 - s[:, 1]) + 2.0 * (0.0 - s[:, 3])
+        am = np.sqrt(ax ** 2 + ay ** 2); f = np.where(am > a_max, a_max / np.maximum(am, 1e-300), 1.0)
+        ax, ay = ax * f, ay * f
+        nxt = np.stack([s[:, 0] + s[:, 2] * dt, s[:, 1] + s[:, 3] * dt, s[:, 2] + ax * dt, s[:, 3] + ay * dt], axis=1)
+        vm = np.sqrt(nxt[:, 2] ** 2 + nxt[:, 3] ** 2); g = np.where(vm > v_max, v_max / np.maximum(vm, 1e-300), 1.0)
+        nxt[:, 2] *= g; nxt[:, 3] *= g
+        NOMU[:, k, 0] = ax; NOMU[:, k, 1] = ay; NOMX[:, k + 1] = nxt; s = nxt
+    return NOMX, NOMU
+
+
+def evade_static_rects(MOV, bullet_length=3.0, bullet_width=4.0):
+    """the bullet's current hitbox per agent (envs/evade_env.py:469-473) from the bullet rows of make_evade_batch"""
+    bx = MOV[:, 0, 0] - bullet_length / 6
+    S = np.zeros((MOV.shape[0], 5))
+    S[:, 0] = bx - bullet_length / 2; S[:, 1] = bx + bullet_length / 2 + bullet_length / 3
+    S[:, 2] = MOV[:, 0, 1] - bullet_width / 2; S[:, 3] = MOV[:, 0, 1] + bullet_width / 2; S[:, 4] = (MOV[:, 0, 7] != 0)
+    return S

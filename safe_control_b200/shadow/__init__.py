@@ -20,6 +20,9 @@ import sys
 
 SHADOW_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "safe_control", "position_control")
 MODULES = ("cbf_qp", "mpc_cbf", "optimal_decay_cbf_qp", "optimal_decay_mpc_cbf", "backup_cbf_qp")
+# the trajectory-rollout shields (examples/evade/test_evade.py:41-42 imports them by module path too)
+SHIELD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "safe_control", "shielding")
+SHIELD_MODULES = {"gatekeeper": "Gatekeeper", "mps": "MPS"}
 
 
 def install():
@@ -34,6 +37,31 @@ def install():
         if hasattr(pc, m):
             delattr(pc, m)
     return pc
+
+
+def install_shielding():
+    """The same for `safe_control.shielding.{gatekeeper,mps}`; the package's own `Gatekeeper` / `MPS` attributes
+    (shielding/__init__.py:5-6) are re-pointed as well."""
+    sp = importlib.import_module("safe_control.shielding")
+    if SHIELD_DIR not in list(sp.__path__):
+        sp.__path__.insert(0, SHIELD_DIR)
+    for m, cls in SHIELD_MODULES.items():
+        sys.modules.pop(f"safe_control.shielding.{m}", None)
+        mod = importlib.import_module(f"safe_control.shielding.{m}")
+        setattr(sp, m, mod); setattr(sp, cls, getattr(mod, cls))
+    return sp
+
+
+def uninstall_shielding():
+    sp = sys.modules.get("safe_control.shielding")
+    if sp is None:
+        return
+    if SHIELD_DIR in list(sp.__path__):
+        sp.__path__.remove(SHIELD_DIR)
+    for m, cls in SHIELD_MODULES.items():
+        sys.modules.pop(f"safe_control.shielding.{m}", None)
+        mod = importlib.import_module(f"safe_control.shielding.{m}")
+        setattr(sp, m, mod); setattr(sp, cls, getattr(mod, cls))
 
 
 def uninstall():

@@ -1,0 +1,2 @@
+"""Shadow of the reference's shielding/mps.py (see safe_control_b200/shadow/__init__.py)."""
+from safe_control_b200.shield import MPS  # noqa: F401

@@ -6,6 +6,7 @@
 #include "../../safe_control_b200/csrc/scb_qp.cuh"
 #include "../../safe_control_b200/csrc/scb_track.cuh"
 #include "../../safe_control_b200/csrc/scb_backup.cuh"
+#include "../../safe_control_b200/csrc/scb_shield.cuh"
 #include <vector>
 #ifdef SCB_HOSTSIM_MPC
 #include "../../safe_control_b200/csrc/scb_mpc.cuh"
@@ -344,6 +345,27 @@ int hostsim_backupcbf_solve(const scb_backup_params* p, int N, int K, const doub
         if (o.w1 >= 0 && o.lam1 > 0.0 && (o.w1 >> 6) == w) bits |= 1ull << (o.w1 & 63);
         active[a * words + w] = bits;
       }
+  }
+  return 0;
+}
+
+// gatekeeper / MPS bodies (scb_shield.cuh), one agent after the other on HOST arrays laid out like scb_shield_step's
+int hostsim_shield_step(const scb_shield_params* sp, const scb_shield_state* st, int N, int K, const double* X, const double* NOMX,
+                        const double* NOMU, const int32_t* nom_len, const double* MOV, long mov_stride, const double* STAT,
+                        double* U, int32_t* using_backup) {
+  const int T = sp->nom_cap, Nb = sp->scene.n_backup;
+  for (long a = 0; a < N; ++a) {
+    ShieldIO io;
+    io.x = X + a * 4; io.nomx = NOMX + a * (long)(T + 1) * 4; io.nomu = NOMU + a * (long)T * 2;
+    int nl = nom_len ? nom_len[a] : T + 1;
+    io.nom_len = nl < 0 ? 0 : (nl > T + 1 ? T + 1 : nl);
+    io.mov = (K > 0 && MOV) ? MOV + a * mov_stride : nullptr; io.K = (K > 0 && MOV) ? K : 0;
+    io.stat = STAT ? STAT + a * 5 : nullptr;
+    io.cu = st->CU + a * (long)(T + Nb) * 2;
+    io.cx = st->CX ? st->CX + a * (long)(T + Nb + 1) * 4 : nullptr;
+    int ub = 0;
+    shield_agent<1>(*sp, io, st->clen[a], st->cidx[a], st->nsteps[a], st->next_event[a], U + a * 2, ub);
+    if (using_backup) using_backup[a] = ub;
   }
   return 0;
 }
