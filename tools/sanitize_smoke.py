@@ -1,5 +1,5 @@
 """Small invocation of every kernel family for compute-sanitizer (tools/sanitize.sh): CBF-QP (warp-per-agent LDG kernel,
-lane-group bulk-async kernel), optimal-decay (both), MPC (fast path, general rows, schedule), closed loop (fused + per-step)."""
+lane-group bulk-async kernel), optimal-decay (both), MPC (fast path, general rows, schedule), closed loop (fused + per-step), Backup-CBF QP (split / fused), gatekeeper / MPS."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -30,5 +30,25 @@ for ctrl in ("cbf_qp", "mpc_cbf"):
     tc.set_waypoints(wps)
     tc.run_steps(4)
     tc.control_step()
+torch.cuda.synchronize()
+# Backup-CBF QP (split and fused launches, both lane-group geometries) and the gatekeeper / MPS step kernels (evade scene)
+from safe_control_b200 import BatchedBackupCBF, BatchedShield, EvadeSceneParams
+for n in (37, 700):
+    X, Ur, MOV = scenes.make_evade_batch(n, seed=5, k_mov=2)
+    for lanes, fused in ((8, 0), (32, 0), (8, 1), (32, 1)):
+        os.environ["SCB_BK_LANES"] = str(lanes)
+        os.environ.pop("SCB_BK_FUSED", None)
+        if fused:
+            os.environ["SCB_BK_FUSED"] = "1"
+        BatchedBackupCBF(EvadeSceneParams(dt=0.1, backup_horizon=4.0)).solve(t(X), t(Ur), t(MOV), want_phi=True, want_active=True)
+    os.environ.pop("SCB_BK_LANES", None); os.environ.pop("SCB_BK_FUSED", None)
+    NOMX, NOMU = scenes.make_evade_plans(X, 30)
+    STAT = scenes.evade_static_rects(MOV)
+    for mode, lanes in (("gatekeeper", 32), ("gatekeeper", 8), ("gatekeeper", 1), ("mps", 1)):
+        os.environ["SCB_SHIELD_LANES"] = str(lanes)
+        sh = BatchedShield(n, mode, EvadeSceneParams(dt=0.1, backup_horizon=4.0), 0.05, None, 30, keep_states=True)
+        for _ in range(3):
+            sh.step(t(X), t(NOMX), t(NOMU), t(MOV), t(STAT))
+    os.environ.pop("SCB_SHIELD_LANES", None)
 torch.cuda.synchronize()
 print("sanitize smoke done")
