@@ -193,11 +193,12 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const MpcIO& io, int*
   int slots = (int)(budget / per);                       // agent-warps one SM can hold (shared memory)
   if (slots < 1) return SCB_ERR_TOO_LARGE;
   if (slots > kMpcMaxGroups) slots = kMpcMaxGroups;
-  // CTA shape.  One agent-warp per CTA (default): the warps of a CTA are independent, so small CTAs lose nothing, and an SM
+  // CTA shape.  One agent-warp per CTA (batches of a few waves): the warps of a CTA are independent, so small CTAs lose nothing, and an SM
   // slot is released the moment ITS agent queue runs dry instead of when the slowest of `slots` warps is done -- which is
   // what lets the CTAs of another launch (the next model group of a mixed batch, on another stream) move in during the
   // tail.  SCB_MPC_GPB=n packs n agent-warps per CTA (round 1's shape: n = slots, one CTA per SM).
-  int gpb = 1;
+  // Launches of >= 4 waves keep round 1's packed CTAs (measured 3 % faster there: config 5 on one GPU 201.8 vs 208.7 ms).
+  int gpb = ((long)N >= 4L * sm_count * slots) ? slots : 1;
   if (const char* e = getenv("SCB_MPC_GPB")) { const int v = atoi(e); if (v >= 1) gpb = v < slots ? v : slots; }
   const int cta_per_sm = slots / gpb > 0 ? slots / gpb : 1;
   const size_t smem = per * gpb;
