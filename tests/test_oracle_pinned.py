@@ -108,6 +108,44 @@ def test_optimal_decay_matches_reference_end_to_end():
                 np.testing.assert_allclose(om, d["OMEGA"][i], rtol=1e-9, atol=1e-10, err_msg=name)
 
 
+def test_qp_fixtures_against_an_independent_solver():
+    """The fixture's u comes from oracle/qp_exact.py (through the cvxpy stand-in): cross-check the same stated QPs --
+    (P, q, G, h) as the reference's own problem statement produces them -- with scipy's SLSQP, which shares no code with
+    the enumeration solver (an independent third solver)."""
+    from scipy.optimize import minimize
+    checked = 0
+    for fname, make in (("ref_cbfqp.npz", lambda tag: OracleCBFQP(_spec_from_tag(tag), num_obs=None)),
+                        ("ref_odcbf.npz", lambda tag: OracleOptimalDecayCBFQP({"model": tag}))):
+        for tag, d in _load(fname).items():
+            ctrl = make(tag)
+            if isinstance(ctrl, OracleCBFQP):
+                ctrl.num_obs = d["A"].shape[1]
+            for i in range(0, len(d["X"]), 3):
+                if d["STATUS"][i] != 0:
+                    continue
+                if isinstance(ctrl, OracleCBFQP):
+                    k = int(d["NOBS"][i])
+                    if k == 0:
+                        continue
+                    P, q, G, h = ctrl.qp(d["X"][i], d["UREF"][i], d["OBS"][i][:k])
+                    want = d["U"][i]
+                else:
+                    P, q, G, h = ctrl.qp(d["X"][i], d["UREF"][i], d["OBS"][i] if d["HAS"][i] else None)
+                    want = np.concatenate([d["U"][i], d["OMEGA"][i]])
+                sc = 1.0 / max(1.0, float(np.abs(np.diag(P)).max()))           # (the slack penalty is 1e4: scale the cost)
+                res = minimize(lambda z: sc * (0.5 * z @ P @ z + q @ z), np.zeros(q.size), jac=lambda z: sc * (P @ z + q), method="SLSQP",
+                               constraints=[{"type": "ineq", "fun": lambda z: h - G @ z, "jac": lambda z: -G}],
+                               options={"ftol": 1e-14, "maxiter": 400})
+                if not res.success:
+                    continue
+                J = lambda z: 0.5 * z @ P @ z + q @ z
+                assert np.all(G @ res.x - h <= 1e-7)
+                assert J(want) <= J(res.x) + 1e-7 * max(1.0, abs(J(want))), (fname, tag, i)      # the fixture's point is at least as good
+                np.testing.assert_allclose(res.x, want, rtol=2e-5, atol=2e-5, err_msg=f"{fname} {tag} {i}")
+                checked += 1
+    assert checked >= 60
+
+
 # ---- MPC-CBF problem statement: oracle/mpc_cbf.py vs what the REFERENCE'S OWN mpc_cbf.py hands to do-mpc ----------
 # (tests/golden/gen_mpc_from_reference.py; probing stand-in for do_mpc, nothing solved).  Pins the Euler rhs, the
 # stage cost (Q, goal padding), every CBF constraint value incl. the model's own step and the alphas, the dummy
