@@ -940,7 +940,7 @@ def run_backup(args, w, cx, steps, warmup, sub=False):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_gpu": N, "backup_steps": 120, "rows_per_qp": 124,
                    "scene": "scenes.make_evade_batch seed 1234 (+101 per batch): evade hallway + pocket, one bullet per agent",
-                   "launch": "2 launches per step (backup_rollout_kernel<8>: 8 lanes per agent; backup_qp_kernel<8,16>), eager",
+                   "launch": "2 launches per step (backup_rollout_kernel<5>: 5 lanes per agent, 6 agents per warp; backup_qp_kernel<8,16>), eager",
                    "l2_policy": f"{P} distinct batches alternated; compute-bound (189 MB of rows per step stream through L2)",
                    "solver": {"optimal_frac": float((st == 0).float().mean()), "intervene_frac": float(out["intervene"].float().mean())},
                    "single_agent_latency_ms": a.elapsed_time(b) / 20},
@@ -948,7 +948,7 @@ def run_backup(args, w, cx, steps, warmup, sub=False):
                 "steps_timed": e_steps, "how": "scb_backupcbf_solve_host on pageable numpy buffers (staged H2D, 2 launches, D2H, sync), wall clock"},
         "gpu_launches": launches,
         "roofline": fp64_roofline(fl * N if fl else None, ms_max,
-                                  {"kernel_ms_how": "both launches of one step (rollout ~91 %, QP ~9 % under ncu: profiles/r2_ncu_backup_summary.txt), CUDA events",
+                                  {"kernel_ms_how": "both launches of one step (rollout ~88 %, QP ~12 %: profiles/r2_launches_backup.csv), CUDA events",
                                    "flops_source": "ncu-counted 2*DFMA + DADD + DMUL per agent (profiles/r2_flops_backup.json) x agents per step" if fl else
                                                    "profiles/r2_flops_backup.json missing",
                                    "note": "chain of dependent fp64 sqrt / div per backup step: issue / FP64-pipe bound (ncu: issue slots 70 %, FP64 pipe 41 % busy), HBM traffic negligible"}),

@@ -137,17 +137,30 @@ SCB_HD double bk_h_terminal(const scb_backup_params& p, const double* s, const d
 // Scratch of one agent: SCR doubles.  [0, 20) step variants / A columns, [20, 36) S, [36, 44) barrier variants
 constexpr int kBkScratch = 44;
 
+// Lane groups of the rollout: the usual power-of-two groups (Grp<>), or LANES = 5 -- six agents per warp, lanes 30 and 31
+// idle (they leave the kernel before the first barrier): exactly one lane per step variant, 30 of 32 lanes busy in the
+// step phase and 24 in the barrier phase instead of 20 and 16 with groups of 8.  The six agents of a warp run the same
+// number of backup steps, so the 30 lanes synchronise as one group.
+constexpr unsigned kBkMask5 = 0x3fffffffu;
+template <int LANES>
+SCB_HD int bk_lane() {
+#if defined(__CUDA_ARCH__)
+  if (LANES == 5) return (int)((threadIdx.x & 31u) % 5u);
+#endif
+  return Grp<LANES == 5 ? 1 : LANES>::lane();
+}
 template <int LANES>
 SCB_HD void bk_sync() {
 #if defined(__CUDA_ARCH__)
-  if (LANES > 1) __syncwarp(Grp<LANES>::gmask());
+  if (LANES == 5) __syncwarp(kBkMask5);
+  else if (LANES > 1) __syncwarp(Grp<LANES == 5 ? 1 : LANES>::gmask());
 #endif
 }
 
 // closed-loop step from x and its forward-difference Jacobian: scr[0..3] = x_next, scr[4 + 4 k + r] = A[r][k]
 template <int LANES>
 SCB_HD void bk_step_fd(const scb_backup_params& p, const double* x, double* scr) {
-  const int lane = Grp<LANES>::lane();
+  const int lane = bk_lane<LANES>();
   for (int v = lane; v < 5; v += LANES) {
     const double xp[4] = {x[0] + (v == 1 ? kBkEps : 0.0), x[1] + (v == 2 ? kBkEps : 0.0), x[2] + (v == 3 ? kBkEps : 0.0),
                           x[3] + (v == 4 ? kBkEps : 0.0)};
@@ -163,7 +176,7 @@ SCB_HD void bk_step_fd(const scb_backup_params& p, const double* x, double* scr)
 // S <- A S (S at scr + 20, row-major); lane c owns column c
 template <int LANES>
 SCB_HD void bk_advance_S(double* scr) {
-  const int lane = Grp<LANES>::lane();
+  const int lane = bk_lane<LANES>();
   double* S = scr + 20;
   for (int c = lane; c < 4; c += LANES) {
     const double s0 = S[c], s1 = S[4 + c], s2 = S[8 + c], s3 = S[12 + c];
@@ -185,8 +198,7 @@ struct BackupOut {
 template <int LANES>
 SCB_HD double backup_rollout(const scb_backup_params& p, const double* x0, const double* mov, int K, double* scr,
                              double* rows, double* phi) {
-  using G = Grp<LANES>;
-  const int lane = G::lane();
+  const int lane = bk_lane<LANES>();
   const int N = p.n_backup;
   const double dt = p.dt;
   double* S = scr + 20;
@@ -227,7 +239,7 @@ SCB_HD double backup_rollout(const scb_backup_params& p, const double* x0, const
       const double gS0 = gx * S[0] + gy * S[4], gS1 = gx * S[1] + gy * S[5];
       const double gS2 = gx * S[2] + gy * S[6], gS3 = gx * S[3] + gy * S[7];
       const double rhs = -(gS0 * x0[2] + gS1 * x0[3]) + (gx * f0 + gy * f1) - dh_dt - nmul(p.alpha, h_val);   // :646-647
-      if (lane == 0) { rows[3 * (i - 1)] = gS2; rows[3 * (i - 1) + 1] = gS3; rows[3 * (i - 1) + 2] = rhs; }
+      if (lane == 0 && rows) { rows[3 * (i - 1)] = gS2; rows[3 * (i - 1) + 1] = gS3; rows[3 * (i - 1) + 2] = rhs; }
       h_min = fmin(h_min, h_val);
     }
     bk_sync<LANES>();                                                           // S and hv are read before they change
@@ -250,7 +262,7 @@ SCB_HD double backup_rollout(const scb_backup_params& p, const double* x0, const
     double gS[4];
     for (int c = 0; c < 4; ++c) gS[c] = g[0] * S[c] + g[1] * S[4 + c] + g[2] * S[8 + c] + g[3] * S[12 + c];
     const double rhs = -(gS[0] * x0[2] + gS[1] * x0[3] + nmul(p.alpha_terminal, h_T));
-    if (lane == 0 && N >= 1) { rows[3 * (N - 1)] = gS[2]; rows[3 * (N - 1) + 1] = gS[3]; rows[3 * (N - 1) + 2] = rhs; }
+    if (lane == 0 && rows) { rows[3 * (N - 1)] = gS[2]; rows[3 * (N - 1) + 1] = gS[3]; rows[3 * (N - 1) + 2] = rhs; }
     h_min = fmin(h_min, h_T);
     bk_sync<LANES>();
   }

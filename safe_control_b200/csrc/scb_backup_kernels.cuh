@@ -52,16 +52,24 @@ template <int LANES>
 __global__ void __launch_bounds__(kBkBlock)
 backup_rollout_kernel(const scb_backup_params p, int N, int K, const double* __restrict__ X, const double* __restrict__ MOV,
                       long mov_stride, double* __restrict__ h_min, double* __restrict__ phi, double* __restrict__ rows) {
-  constexpr int kGroups = kBkBlock / LANES;
+  // agents per CTA: kBkBlock / LANES, or 6 per warp for LANES = 5 (lanes 30, 31 of every warp idle)
+  constexpr int kPerWarp = (LANES == 5) ? 6 : 32 / LANES;
+  constexpr int kGroups = (kBkBlock / 32) * kPerWarp;
   __shared__ double scr_all[kGroups * kBkScratch];
-  const int g = threadIdx.x / LANES;
-  const long agent = (long)blockIdx.x * kGroups + g;
-  if (agent >= N) return;
+  const int wl = threadIdx.x & 31;
+  if (LANES == 5 && wl >= 30) return;
+  const int g = (threadIdx.x >> 5) * kPerWarp + wl / LANES;
+  long agent = (long)blockIdx.x * kGroups + g;
+  bool valid = agent < N;
+  if (!valid) {
+    if (LANES != 5) return;                            // (whole power-of-two groups leave together)
+    agent = N - 1;                                     // the 30 lanes of a warp synchronise as one group: keep them all, write nothing
+  }
   const int nb = p.n_backup;
   const double h = backup_rollout<LANES>(p, X + agent * 4, MOV ? MOV + agent * mov_stride : nullptr, MOV ? K : 0,
-                                         scr_all + g * kBkScratch, rows + agent * (long)nb * 3,
-                                         phi ? phi + agent * (long)nb * 4 : nullptr);
-  if (threadIdx.x % LANES == 0) h_min[agent] = h;
+                                         scr_all + g * kBkScratch, valid ? rows + agent * (long)nb * 3 : nullptr,
+                                         (phi && valid) ? phi + agent * (long)nb * 4 : nullptr);
+  if (valid && wl % LANES == 0) h_min[agent] = h;
 }
 
 template <int LANES, int RPL>

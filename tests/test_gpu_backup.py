@@ -44,7 +44,7 @@ def gpu_solve(sc, X, Ur, MOV, lanes=None, fused=False, **want):
     return o
 
 
-@pytest.mark.parametrize("lanes,fused", [(8, False), (32, False), (8, True), (32, True)])
+@pytest.mark.parametrize("lanes,fused", [(None, False), (5, False), (8, False), (32, False), (8, True), (32, True)])
 @pytest.mark.parametrize("tag", SETS)
 def test_reference_fixtures(tag, lanes, fused):
     gold = np.load(GOLD)
@@ -88,9 +88,11 @@ def test_full_size_properties_and_geometries():
     a8 = gpu_solve(sc, X, Ur, MOV, lanes=8, want_active=True)
     a32 = gpu_solve(sc, X, Ur, MOV, lanes=32, want_active=True)
     f8 = gpu_solve(sc, X, Ur, MOV, lanes=8, fused=True, want_active=True)      # the one-launch variant
+    a5 = gpu_solve(sc, X, Ur, MOV, lanes=5, want_active=True)                  # six agents per warp (the default for this size)
     for k in ("U", "status", "intervene", "h_min", "active"):
         assert np.array_equal(a8[k], a32[k]), k
         assert np.array_equal(a8[k], f8[k]), k
+        assert np.array_equal(a8[k], a5[k]), k
     sub = np.arange(0, n, 257)
     small = gpu_solve(sc, X[sub], Ur[sub], MOV[sub], want_active=True)
     for k in ("U", "status", "intervene", "h_min", "active"):

@@ -35,7 +35,7 @@ torch.cuda.synchronize()
 from safe_control_b200 import BatchedBackupCBF, BatchedShield, EvadeSceneParams
 for n in (37, 700):
     X, Ur, MOV = scenes.make_evade_batch(n, seed=5, k_mov=2)
-    for lanes, fused in ((8, 0), (32, 0), (8, 1), (32, 1)):
+    for lanes, fused in ((5, 0), (8, 0), (32, 0), (8, 1), (32, 1)):
         os.environ["SCB_BK_LANES"] = str(lanes)
         os.environ.pop("SCB_BK_FUSED", None)
         if fused:

@@ -18,7 +18,7 @@ def clocks():
                               capture_output=True, text=True, timeout=10).stdout.strip()
     except Exception as e:
         return str(e)
-for lanes, fused in ((8, 0), (8, 1), (8, 0), (32, 0), (32, 1), (0, 0)):
+for lanes, fused in ((5, 0), (8, 0), (8, 1), (32, 0), (0, 0)):
     os.environ.pop("SCB_BK_LANES", None); os.environ.pop("SCB_BK_FUSED", None)
     if lanes: os.environ["SCB_BK_LANES"] = str(lanes)
     if fused: os.environ["SCB_BK_FUSED"] = "1"
