@@ -291,12 +291,13 @@ typedef struct scb_shield_params {
 } scb_shield_params;
 
 typedef struct scb_shield_state { /* device pointers, caller-owned, persistent across calls */
-  double*  CU;                    /* [N, T + n_backup, 2]      committed_u_traj */
-  double*  CX;                    /* [N, T + n_backup + 1, 4]  committed_x_traj, or NULL */
+  double*  CU;                    /* [N, 2, T + n_backup, 2]      committed_u_traj, double-buffered: agent i's is CU[i, cbuf[i]] */
+  double*  CX;                    /* [N, 2, T + n_backup + 1, 4]  committed_x_traj (same buffering), or NULL */
   int32_t* clen;                  /* [N] len(committed_u_traj); -1 = no committed trajectory yet (:571) */
   int32_t* cidx;                  /* [N] current_time_idx */
   int32_t* nsteps;                /* [N] actual_nominal_steps (committed_horizon = nsteps dt) */
   double*  next_event;            /* [N] next_event_time */
+  int32_t* cbuf;                  /* [N] which of the two buffers holds the committed trajectory (start: 0) */
 } scb_shield_state;
 
 size_t scb_shield_params_sizeof(void);

@@ -961,7 +961,7 @@ extern "C" int scb_shield_step(const scb_shield_params* p, const scb_shield_stat
   if (rc != SCB_OK) return rc;
   if (p->nom_cap < 0 || (p->mode != 0 && p->mode != 1) || !(p->event_offset >= 0.0)) return SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
-  if (!X || !U || !st->CU || !st->clen || !st->cidx || !st->nsteps || !st->next_event || (p->nom_cap > 0 && (!NOMX || !NOMU)) ||
+  if (!X || !U || !st->CU || !st->clen || !st->cidx || !st->nsteps || !st->next_event || !st->cbuf || (p->nom_cap > 0 && (!NOMX || !NOMU)) ||
       (K > 0 && !MOV) || mov_stride < 0)
     return SCB_ERR_BAD_ARG;
   if (p->nom_cap == 0 && !NOMX) return SCB_ERR_BAD_ARG;            // (NOMX always holds at least the start state)

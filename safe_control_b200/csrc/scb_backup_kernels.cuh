@@ -118,13 +118,17 @@ shield_step_kernel(const scb_shield_params sp, const scb_shield_state st, int N,
   io.nom_len = nl < 0 ? 0 : (nl > T + 1 ? T + 1 : nl);
   io.mov = MOV ? MOV + a * mov_stride : nullptr; io.K = MOV ? K : 0;
   io.stat = STAT ? STAT + a * 5 : nullptr;
-  io.cu = st.CU + a * (long)(T + Nb) * 2;
-  io.cx = st.CX ? st.CX + a * (long)(T + Nb + 1) * 4 : nullptr;
+  const int cb = st.cbuf[a] & 1;
+  const long lu = (long)(T + Nb) * 2, lx = (long)(T + Nb + 1) * 4;
+  io.cu = st.CU + (a * 2 + cb) * lu; io.cu_spare = st.CU + (a * 2 + (cb ^ 1)) * lu;
+  io.cx = st.CX ? st.CX + (a * 2 + cb) * lx : nullptr; io.cx_spare = st.CX ? st.CX + (a * 2 + (cb ^ 1)) * lx : nullptr;
   int clen = st.clen[a], cidx = st.cidx[a], nsteps = st.nsteps[a], ub = 0;
   double ne = st.next_event[a], u[2];
-  shield_agent<LANES>(sp, io, clen, cidx, nsteps, ne, u, ub);
+  bool flip = false;
+  shield_agent<LANES>(sp, io, clen, cidx, nsteps, ne, u, ub, flip);
   if (lane == 0) {
     st.clen[a] = clen; st.cidx[a] = cidx; st.nsteps[a] = nsteps; st.next_event[a] = ne;
+    if (flip) st.cbuf[a] = cb ^ 1;
     U[a * 2] = u[0]; U[a * 2 + 1] = u[1];
     if (using_backup) using_backup[a] = ub;
   }

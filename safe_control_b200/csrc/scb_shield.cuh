@@ -101,20 +101,25 @@ struct ShieldIO {
   int nom_len;            // states available (0: no nominal trajectory)
   const double* mov; int K;
   const double* stat;     // [5] or null
-  double* cu;             // [T + n_backup, 2] committed inputs
+  double* cu;             // [T + n_backup, 2] committed inputs (the active one of the agent's two buffers)
   double* cx;             // [T + n_backup + 1, 4] committed states or null
+  double* cu_spare;       // the other buffer: a new commitment is built there, then the two are swapped
+  double* cx_spare;
 };
 
 // one control step of one agent; the scalar state is passed by reference and stored by the caller
+// `flip` is set when the commitment moved to the spare buffer (the caller toggles the agent's buffer index).
 template <int LANES>
 SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& clen, int& cidx, int& nsteps, double& next_event,
-                         double* u_out, int& using_backup) {
+                         double* u_out, int& using_backup, bool& flip) {
   using G = Grp<LANES>;
   const scb_backup_params& p = sp.scene;
   const int lane = G::lane();
   const int Nb = p.n_backup;
   const double dt = p.dt;
   const int nl = io.nom_len;
+  double* cu = io.cu;
+  flip = false;
 
   if (clen < 0) {                                   // first call: commit the pure backup trajectory (gatekeeper.py:571-583)
     if (lane == 0) {
@@ -140,22 +145,29 @@ SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& c
       const double* base = (nl > 0) ? io.nomx : io.x;
       bool ok = true;
       for (int k = 0; k < n_use && ok; ++k) ok = !sh_collides(p, base[4 * k], base[4 * k + 1], k, io.mov, io.K, io.stat);
-      if (ok) ok = sh_backup_leg(p, base + 4 * (n_use - 1), n_use, true, io.mov, io.K, io.stat, nullptr, nullptr);
+      // candidate 0 (the longest nominal horizon, the winner for most agents) writes its backup leg straight into the spare
+      // buffer while it is being checked: when it wins, nothing has to be rolled out twice
+      const bool spec = (c == 0);
+      if (ok) ok = sh_backup_leg(p, base + 4 * (n_use - 1), n_use, true, io.mov, io.K, io.stat,
+                                 spec ? io.cu_spare + 2 * (n_use - 1) : nullptr,
+                                 (spec && io.cx_spare) ? io.cx_spare + 4 * n_use : nullptr);
       if (ok) best = c;
     }
     best = (int)G::vmin((double)best);
-    if (best != kNone) {                            // _update_committed_trajectory (gatekeeper.py:529-551)
+    if (best != kNone) {                            // _update_committed_trajectory (gatekeeper.py:529-551), built in the spare buffer
       int steps = max_steps - best * disc;
       if (steps < 0) steps = 0;
       const int n_use = (nl > 0) ? ((steps + 1 < nl) ? steps + 1 : nl) : 1;
       const int actual = n_use - 1;
       const double* base = (nl > 0) ? io.nomx : io.x;
-      for (int k = lane; k < 2 * actual; k += LANES) io.cu[k] = io.nomu[k];
-      if (io.cx) for (int k = lane; k < 4 * n_use; k += LANES) io.cx[k] = base[k];
-      if (lane == 0)
-        sh_backup_leg(p, base + 4 * (n_use - 1), n_use, false, nullptr, 0, nullptr, io.cu + 2 * actual,
-                      io.cx ? io.cx + 4 * n_use : nullptr);
+      bk_sync<LANES>();                             // (candidate 0's speculative leg is complete and visible)
+      for (int k = lane; k < 2 * actual; k += LANES) io.cu_spare[k] = io.nomu[k];
+      if (io.cx_spare) for (int k = lane; k < 4 * n_use; k += LANES) io.cx_spare[k] = base[k];
+      if (best != 0 && lane == 0)
+        sh_backup_leg(p, base + 4 * (n_use - 1), n_use, false, nullptr, 0, nullptr, io.cu_spare + 2 * actual,
+                      io.cx_spare ? io.cx_spare + 4 * n_use : nullptr);
       clen = actual + Nb; nsteps = actual; cidx = 0; next_event = sp.event_offset;
+      cu = io.cu_spare; flip = true;
       bk_sync<LANES>();
     } else {
       next_event = nmul((double)cidx, dt) + sp.event_offset;                    // gatekeeper.py:654; mps.py:127
@@ -163,7 +175,7 @@ SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& c
   }
 
   double u0, u1;
-  if (cidx < clen) { u0 = io.cu[2 * cidx]; u1 = io.cu[2 * cidx + 1]; }          // gatekeeper.py:656-667
+  if (cidx < clen) { u0 = cu[2 * cidx]; u1 = cu[2 * cidx + 1]; }          // gatekeeper.py:656-667
   else bk_policy(p, io.x, u0, u1);
   u_out[0] = u0; u_out[1] = u1;
   cidx += 1;

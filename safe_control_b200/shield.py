@@ -51,20 +51,36 @@ class BatchedShield:
         if dev.type == "cuda" and dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         L = self.T + self.Nb
-        self.CU = torch.zeros((self.N, L, 2), dtype=F64, device=dev)
-        self.CX = torch.zeros((self.N, L + 1, 4), dtype=F64, device=dev) if keep_states else None
+        # committed trajectories are double-buffered on the device (a new commitment is built in the spare buffer, then swapped)
+        self._CU2 = torch.zeros((self.N, 2, L, 2), dtype=F64, device=dev)
+        self._CX2 = torch.zeros((self.N, 2, L + 1, 4), dtype=F64, device=dev) if keep_states else None
+        self.cbuf = torch.zeros((self.N,), dtype=I32, device=dev)
         self.clen = torch.full((self.N,), -1, dtype=I32, device=dev)
         self.cidx = torch.zeros((self.N,), dtype=I32, device=dev)
         self.nsteps = torch.zeros((self.N,), dtype=I32, device=dev)
         self.next_event = torch.zeros((self.N,), dtype=F64, device=dev)
-        self._state = _abi.ScbShieldState(self.CU.data_ptr(), self.CX.data_ptr() if keep_states else None, self.clen.data_ptr(),
-                                          self.cidx.data_ptr(), self.nsteps.data_ptr(), self.next_event.data_ptr())
+        self._state = _abi.ScbShieldState(self._CU2.data_ptr(), self._CX2.data_ptr() if keep_states else None, self.clen.data_ptr(),
+                                          self.cidx.data_ptr(), self.nsteps.data_ptr(), self.next_event.data_ptr(),
+                                          self.cbuf.data_ptr())
         self.device = dev
         self.launches = 0
 
+    @property
+    def CU(self):
+        """[N, T + n_backup, 2]: every agent's committed input trajectory (rows beyond clen are stale)"""
+        idx = self.cbuf.long().view(-1, 1, 1, 1).expand(-1, 1, *self._CU2.shape[2:])
+        return self._CU2.gather(1, idx).squeeze(1)
+
+    @property
+    def CX(self):
+        if self._CX2 is None:
+            return None
+        idx = self.cbuf.long().view(-1, 1, 1, 1).expand(-1, 1, *self._CX2.shape[2:])
+        return self._CX2.gather(1, idx).squeeze(1)
+
     def reset(self):
         """forget every committed trajectory (the state of a freshly constructed Gatekeeper, gatekeeper.py:103-112)"""
-        self.clen.fill_(-1); self.cidx.zero_(); self.nsteps.zero_(); self.next_event.zero_()
+        self.clen.fill_(-1); self.cidx.zero_(); self.nsteps.zero_(); self.next_event.zero_(); self.cbuf.zero_()
 
     def step(self, X, NOMX, NOMU, MOV=None, STAT=None, nom_len=None):
         """X [N,4]; NOMX [N,T+1,4], NOMU [N,T,2] nominal trajectories (NOMX[:,0] = start state); MOV [N,K,8] / [K,8] moving

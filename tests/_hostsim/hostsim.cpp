@@ -361,10 +361,14 @@ int hostsim_shield_step(const scb_shield_params* sp, const scb_shield_state* st,
     io.nom_len = nl < 0 ? 0 : (nl > T + 1 ? T + 1 : nl);
     io.mov = (K > 0 && MOV) ? MOV + a * mov_stride : nullptr; io.K = (K > 0 && MOV) ? K : 0;
     io.stat = STAT ? STAT + a * 5 : nullptr;
-    io.cu = st->CU + a * (long)(T + Nb) * 2;
-    io.cx = st->CX ? st->CX + a * (long)(T + Nb + 1) * 4 : nullptr;
+    const int cb = st->cbuf[a] & 1;
+    const long lu = (long)(T + Nb) * 2, lx = (long)(T + Nb + 1) * 4;
+    io.cu = st->CU + (a * 2 + cb) * lu; io.cu_spare = st->CU + (a * 2 + (cb ^ 1)) * lu;
+    io.cx = st->CX ? st->CX + (a * 2 + cb) * lx : nullptr; io.cx_spare = st->CX ? st->CX + (a * 2 + (cb ^ 1)) * lx : nullptr;
     int ub = 0;
-    shield_agent<1>(*sp, io, st->clen[a], st->cidx[a], st->nsteps[a], st->next_event[a], U + a * 2, ub);
+    bool flip = false;
+    shield_agent<1>(*sp, io, st->clen[a], st->cidx[a], st->nsteps[a], st->next_event[a], U + a * 2, ub, flip);
+    if (flip) st->cbuf[a] = cb ^ 1;
     if (using_backup) using_backup[a] = ub;
   }
   return 0;

@@ -42,16 +42,25 @@ class HostShield:
     def __init__(self, lib, sc, mode, n, T=T_NOM, **kw):
         self.lib, self.N, self.T, self.Nb = lib, n, T, sc.N
         self.sp = shield_c_params(sc, mode, T, **kw)
-        self.CU = np.zeros((n, T + self.Nb, 2)); self.CX = np.zeros((n, T + self.Nb + 1, 4))
+        self.CU2 = np.zeros((n, 2, T + self.Nb, 2)); self.CX2 = np.zeros((n, 2, T + self.Nb + 1, 4))
         self.clen = np.full(n, -1, np.int32); self.cidx = np.zeros(n, np.int32); self.nsteps = np.zeros(n, np.int32)
-        self.next_event = np.zeros(n)
+        self.next_event = np.zeros(n); self.cbuf = np.zeros(n, np.int32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
-        self.st = _abi.ScbShieldState(p(self.CU), p(self.CX), p(self.clen), p(self.cidx), p(self.nsteps), p(self.next_event))
+        self.st = _abi.ScbShieldState(p(self.CU2), p(self.CX2), p(self.clen), p(self.cidx), p(self.nsteps), p(self.next_event),
+                                      p(self.cbuf))
         f = lib.hostsim_shield_step
         f.restype = C.c_int
         f.argtypes = [C.POINTER(_abi.ScbShieldParams), C.POINTER(_abi.ScbShieldState), C.c_int, C.c_int] + [C.c_void_p] * 5 + \
                      [C.c_long] + [C.c_void_p] * 3
         self.f = f
+
+    @property
+    def CU(self):
+        return self.CU2[np.arange(self.N), self.cbuf]
+
+    @property
+    def CX(self):
+        return self.CX2[np.arange(self.N), self.cbuf]
 
     def step(self, X, NOMX, NOMU, MOV, STAT, nom_len=None):
         p = lambda a: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
