@@ -1037,7 +1037,7 @@ def run_shield(args, w, cx, steps, warmup, sub=False):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{w['name']}: {w['desc']}", "agents_per_gpu": N, "nominal_steps": T, "backup_steps": 120,
                    "scene": "scenes.make_evade_batch seed 1234 (+101 per batch) + make_evade_plans (PD nominal plans)",
-                   "launch": "1 launch per step (shield_step_kernel: 8 lanes per agent for gatekeeper, a thread per agent for MPS), eager",
+                   "launch": "gatekeeper: 2 launches per step (candidate 0 with a thread per agent, the other candidates with 8 lanes per queued agent); MPS: 1 launch (a thread per agent); eager",
                    "l2_policy": f"{P} distinct batches alternated ({h2d / 1e6:.0f} MB of plans + state each, > L2)",
                    "outcome": {"nominal_leg_committed_frac": float((sh.nsteps > 0).float().mean()),
                                "mean_committed_nominal_steps": float(sh.nsteps.float().mean()),

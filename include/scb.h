@@ -298,6 +298,9 @@ typedef struct scb_shield_state { /* device pointers, caller-owned, persistent a
   int32_t* nsteps;                /* [N] actual_nominal_steps (committed_horizon = nsteps dt) */
   double*  next_event;            /* [N] next_event_time */
   int32_t* cbuf;                  /* [N] which of the two buffers holds the committed trajectory (start: 0) */
+  int32_t* work;                  /* [N + 1] scratch (contents irrelevant between calls), or NULL.  With it a gatekeeper step of
+                                     a large batch is two launches: candidate 0 of every agent with a thread per agent, then
+                                     the remaining candidates, a lane group per agent that still needs one. */
 } scb_shield_state;
 
 size_t scb_shield_params_sizeof(void);

@@ -62,7 +62,7 @@ class ScbShieldParams(C.Structure):
 class ScbShieldState(C.Structure):
     """Mirror of `struct scb_shield_state`: device pointers of the per-agent shield state."""
     _fields_ = [("CU", C.c_void_p), ("CX", C.c_void_p), ("clen", C.c_void_p), ("cidx", C.c_void_p), ("nsteps", C.c_void_p),
-                ("next_event", C.c_void_p), ("cbuf", C.c_void_p)]
+                ("next_event", C.c_void_p), ("cbuf", C.c_void_p), ("work", C.c_void_p)]
 
 
 _P = C.POINTER(ScbParams)

@@ -967,16 +967,30 @@ extern "C" int scb_shield_step(const scb_shield_params* p, const scb_shield_stat
   if (p->nom_cap == 0 && !NOMX) return SCB_ERR_BAD_ARG;            // (NOMX always holds at least the start state)
   cudaStream_t s = (cudaStream_t)stream;
   // gatekeeper: one candidate per lane (T / discount + 2 of them); MPS has a single candidate: a thread per agent
-  // (8 lanes beat 32 at 22 candidates: 4.0 vs 5.5 ms per 65 536-agent step -- the longest nominal horizon is valid for most
+  // (8 lanes beat 32 at 22 candidates: 3.8 vs 4.7 ms per 65 536-agent step -- the longest nominal horizon is valid for most
   // agents, so most of a warp's 22 speculative rollouts are wasted; with 8 lanes a lane walks candidates c, c + 8, c + 16)
   int lanes = p->mode == 1 ? 1 : 8;
   if (p->mode == 0 && (long)N * 8 <= (long)sm_count_of_current() * 64) lanes = 32;      // few agents: latency, not throughput
   if (const char* e = getenv("SCB_SHIELD_LANES")) { const int v = atoi(e); if (v == 1 || v == 8 || v == 32) lanes = v; }
+  const double* mov = K > 0 ? MOV : nullptr;
+  // two-launch search (gatekeeper, work list given, batch large enough to matter; SCB_SHIELD_TWO_PHASE=0/1 overrides)
+  bool two = p->mode == 0 && st->work && N >= 1024;
+  if (const char* e = getenv("SCB_SHIELD_TWO_PHASE")) two = p->mode == 0 && st->work && e[0] == '1';
+  if (two) {
+    CK(cudaMemsetAsync(st->work, 0, sizeof(int32_t), s));
+    shield_step_kernel<1, 1><<<(unsigned)((N + kBkBlock - 1) / kBkBlock), kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, mov, mov_stride, STAT, U, using_backup, st->work);
+    const int l2 = lanes == 32 ? 32 : 8;
+    const unsigned g2 = (unsigned)((N + kBkBlock / l2 - 1) / (kBkBlock / l2));        // sized for "every agent pending"; surplus groups exit at once
+    if (l2 == 32) shield_step_kernel<32, 2><<<g2, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, mov, mov_stride, STAT, U, using_backup, st->work);
+    else          shield_step_kernel<8, 2><<<g2, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, mov, mov_stride, STAT, U, using_backup, st->work);
+    CK(cudaGetLastError());
+    return SCB_OK;
+  }
   const int groups = kBkBlock / lanes;
   const unsigned grid = (unsigned)((N + groups - 1) / groups);
-  if (lanes == 32)     shield_step_kernel<32><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, K > 0 ? MOV : nullptr, mov_stride, STAT, U, using_backup);
-  else if (lanes == 8) shield_step_kernel<8><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, K > 0 ? MOV : nullptr, mov_stride, STAT, U, using_backup);
-  else                 shield_step_kernel<1><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, K > 0 ? MOV : nullptr, mov_stride, STAT, U, using_backup);
+  if (lanes == 32)     shield_step_kernel<32, 0><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, mov, mov_stride, STAT, U, using_backup, nullptr);
+  else if (lanes == 8) shield_step_kernel<8, 0><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, mov, mov_stride, STAT, U, using_backup, nullptr);
+  else                 shield_step_kernel<1, 0><<<grid, kBkBlock, 0, s>>>(*p, *st, N, K, X, NOMX, NOMU, nom_len, mov, mov_stride, STAT, U, using_backup, nullptr);
   CK(cudaGetLastError());
   return SCB_OK;
 }

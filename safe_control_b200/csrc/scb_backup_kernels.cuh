@@ -99,16 +99,22 @@ backup_qp_kernel(const scb_backup_params p, int N, const double* __restrict__ X,
 }
 
 // ---- gatekeeper / MPS: one control step of N agents, one lane group per agent (scb_shield.cuh) ----
-template <int LANES>
+// PHASE 0: the whole step in one launch.  PHASE 1 / 2: the two-launch search (see shield_agent); `work` = [count, agent ids...].
+template <int LANES, int PHASE>
 __global__ void __launch_bounds__(kBkBlock)
 shield_step_kernel(const scb_shield_params sp, const scb_shield_state st, int N, int K, const double* __restrict__ X,
                    const double* __restrict__ NOMX, const double* __restrict__ NOMU, const int32_t* __restrict__ nom_len,
                    const double* __restrict__ MOV, long mov_stride, const double* __restrict__ STAT, double* __restrict__ U,
-                   int32_t* __restrict__ using_backup) {
+                   int32_t* __restrict__ using_backup, int32_t* __restrict__ work) {
   constexpr int kGroups = kBkBlock / LANES;
   const int g = threadIdx.x / LANES, lane = threadIdx.x % LANES;
-  const long a = (long)blockIdx.x * kGroups + g;
-  if (a >= N) return;
+  long a = (long)blockIdx.x * kGroups + g;
+  if (PHASE == 2) {
+    if (a >= work[0]) return;                          // (work[0] = number of pending agents, written by the phase-1 launch)
+    a = work[1 + a];
+  } else if (a >= N) {
+    return;
+  }
   const int T = sp.nom_cap, Nb = sp.scene.n_backup;
   ShieldIO io;
   io.x = X + a * 4;
@@ -125,9 +131,13 @@ shield_step_kernel(const scb_shield_params sp, const scb_shield_state st, int N,
   int clen = st.clen[a], cidx = st.cidx[a], nsteps = st.nsteps[a], ub = 0;
   double ne = st.next_event[a], u[2];
   bool flip = false;
-  shield_agent<LANES>(sp, io, clen, cidx, nsteps, ne, u, ub, flip);
+  const bool done = shield_agent<LANES, PHASE>(sp, io, clen, cidx, nsteps, ne, u, ub, flip);
   if (lane == 0) {
     st.clen[a] = clen; st.cidx[a] = cidx; st.nsteps[a] = nsteps; st.next_event[a] = ne;
+    if (!done) {                                       // (phase 1 only) queue the agent for the lane-group search
+      work[1 + atomicAdd(work, 1)] = (int32_t)a;
+      return;
+    }
     if (flip) st.cbuf[a] = cb ^ 1;
     U[a * 2] = u[0]; U[a * 2 + 1] = u[1];
     if (using_backup) using_backup[a] = ub;

@@ -109,8 +109,14 @@ struct ShieldIO {
 
 // one control step of one agent; the scalar state is passed by reference and stored by the caller
 // `flip` is set when the commitment moved to the spare buffer (the caller toggles the agent's buffer index).
-template <int LANES>
-SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& clen, int& cidx, int& nsteps, double& next_event,
+// PHASE 0: the whole step.  The search can also be split in two launches (scb_shield_step with a work list):
+//   PHASE 1 (a thread per agent): everything, but only candidate 0 is tried; when it fails and there are more candidates
+//            the function returns false -- nothing but the first-call commitment has been changed, the agent is `pending`;
+//   PHASE 2 (a lane group per pending agent): the remaining candidates 1 .. n_cand - 1 and the rest of the step.
+// Candidate 0 wins for most agents, and 32 agents per warp walking their own 220 states run converged; the speculative
+// lane-per-candidate search then only pays for the agents that need it.
+template <int LANES, int PHASE = 0>
+SCB_HD bool shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& clen, int& cidx, int& nsteps, double& next_event,
                          double* u_out, int& using_backup, bool& flip) {
   using G = Grp<LANES>;
   const scb_backup_params& p = sp.scene;
@@ -121,7 +127,7 @@ SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& c
   double* cu = io.cu;
   flip = false;
 
-  if (clen < 0) {                                   // first call: commit the pure backup trajectory (gatekeeper.py:571-583)
+  if (PHASE != 2 && clen < 0) {                     // first call: commit the pure backup trajectory (gatekeeper.py:571-583)
     if (lane == 0) {
       if (io.cx) { io.cx[0] = io.x[0]; io.cx[1] = io.x[1]; io.cx[2] = io.x[2]; io.cx[3] = io.x[3]; }
       sh_backup_leg(p, io.x, 1, false, nullptr, 0, nullptr, io.cu, io.cx ? io.cx + 4 : nullptr);
@@ -131,14 +137,15 @@ SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& c
   }
 
   const bool mps = sp.mode == 1;
-  const bool event = mps ? (nl > 1) : ((double)cidx >= next_event / dt);       // mps.py:92-95; gatekeeper.py:590
+  const bool event = (PHASE == 2) || (mps ? (nl > 1) : ((double)cidx >= next_event / dt));   // mps.py:92-95; gatekeeper.py:590
   if (event) {
     const int max_steps = mps ? 1 : (nl > 0 ? nl - 1 : 0);                      // gatekeeper.py:592-599; mps.py:88
     const int disc = sp.discount_steps > 0 ? sp.discount_steps : 1;
     const int n_cand = mps ? 1 : max_steps / disc + 2;                          // gatekeeper.py:605
     constexpr int kNone = 0x7fffffff;
     int best = kNone;
-    for (int c = lane; c < n_cand && best == kNone; c += LANES) {
+    const int c_begin = (PHASE == 2) ? 1 : 0, c_end = (PHASE == 1) ? 1 : n_cand;
+    for (int c = c_begin + lane; c < c_end && best == kNone; c += LANES) {
       int steps = max_steps - c * disc;
       if (steps < 0) steps = 0;
       const int n_use = (nl > 0) ? ((steps + 1 < nl) ? steps + 1 : nl) : 1;     // gatekeeper.py:328-341
@@ -154,6 +161,7 @@ SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& c
       if (ok) best = c;
     }
     best = (int)G::vmin((double)best);
+    if (PHASE == 1 && best == kNone && n_cand > 1) return false;                // pending: phase 2 tries the other candidates
     if (best != kNone) {                            // _update_committed_trajectory (gatekeeper.py:529-551), built in the spare buffer
       int steps = max_steps - best * disc;
       if (steps < 0) steps = 0;
@@ -189,6 +197,7 @@ SCB_HD void shield_agent(const scb_shield_params& sp, const ShieldIO& io, int& c
   } else {                                          // gatekeeper.py:741-744, evaluated after the increment
     using_backup = (cidx >= (int)(nmul((double)nsteps, dt) / dt)) ? 1 : 0;
   }
+  return true;
 }
 
 }  // namespace scb

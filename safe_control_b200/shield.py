@@ -2,7 +2,7 @@
 the evade scene -- batched, with the shields' state resident on the device.
 
     sh = BatchedShield(n_agents, mode="gatekeeper", scene=EvadeSceneParams(...), nominal_steps=100, device="cuda:0")
-    out = sh.step(X, NOMX, NOMU, MOV, STAT)          # one control step of every agent: ONE kernel launch
+    out = sh.step(X, NOMX, NOMU, MOV, STAT)          # one control step of every agent: one or two kernel launches
     out["U"], out["using_backup"]; sh.committed_horizon(), sh.current_time_idx, ...
 
 and the drop-in classes `Gatekeeper` / `MPS` with the reference's constructor, set_* methods, solve_control_problem,
@@ -55,13 +55,14 @@ class BatchedShield:
         self._CU2 = torch.zeros((self.N, 2, L, 2), dtype=F64, device=dev)
         self._CX2 = torch.zeros((self.N, 2, L + 1, 4), dtype=F64, device=dev) if keep_states else None
         self.cbuf = torch.zeros((self.N,), dtype=I32, device=dev)
+        self._work = torch.zeros((self.N + 1,), dtype=I32, device=dev)        # pending list of the two-launch search
         self.clen = torch.full((self.N,), -1, dtype=I32, device=dev)
         self.cidx = torch.zeros((self.N,), dtype=I32, device=dev)
         self.nsteps = torch.zeros((self.N,), dtype=I32, device=dev)
         self.next_event = torch.zeros((self.N,), dtype=F64, device=dev)
         self._state = _abi.ScbShieldState(self._CU2.data_ptr(), self._CX2.data_ptr() if keep_states else None, self.clen.data_ptr(),
                                           self.cidx.data_ptr(), self.nsteps.data_ptr(), self.next_event.data_ptr(),
-                                          self.cbuf.data_ptr())
+                                          self.cbuf.data_ptr(), self._work.data_ptr())
         self.device = dev
         self.launches = 0
 
@@ -107,7 +108,7 @@ class BatchedShield:
         check(lib().scb_shield_step(C.byref(self.params), C.byref(self._state), N, K, _ptr(X), _ptr(NOMX), _ptr(NOMU),
                                     _ptr(nom_len), _ptr(MOV) if K else None, stride, _ptr(STAT), _ptr(U), _ptr(ub), _stream()),
               "scb_shield_step")
-        self.launches += 1
+        self.launches += 2 if (self.mode == "gatekeeper" and N >= 1024) else 1     # (csrc/scb_api.cu: two-launch search)
         return dict(U=U, using_backup=ub)
 
     def committed_horizon(self):

@@ -367,7 +367,7 @@ int hostsim_shield_step(const scb_shield_params* sp, const scb_shield_state* st,
     io.cx = st->CX ? st->CX + (a * 2 + cb) * lx : nullptr; io.cx_spare = st->CX ? st->CX + (a * 2 + (cb ^ 1)) * lx : nullptr;
     int ub = 0;
     bool flip = false;
-    shield_agent<1>(*sp, io, st->clen[a], st->cidx[a], st->nsteps[a], st->next_event[a], U + a * 2, ub, flip);
+    shield_agent<1, 0>(*sp, io, st->clen[a], st->cidx[a], st->nsteps[a], st->next_event[a], U + a * 2, ub, flip);
     if (flip) st->cbuf[a] = cb ^ 1;
     if (using_backup) using_backup[a] = ub;
   }

@@ -19,20 +19,25 @@ def dev(a):
 
 
 class Lanes:
-    """SCB_SHIELD_LANES = 1 / 8 / 32 for the calls inside the block (A/B switch of the dispatch, read per call)"""
+    """SCB_SHIELD_LANES = 1 / 8 / 32 and SCB_SHIELD_TWO_PHASE = 0 / 1 for the calls inside the block (A/B switches of the
+    dispatch in csrc/scb_api.cu, read per call)"""
 
-    def __init__(self, lanes):
-        self.lanes = lanes
+    def __init__(self, lanes, two_phase=None):
+        self.lanes, self.two = lanes, two_phase
 
     def __enter__(self):
-        self.old = os.environ.pop("SCB_SHIELD_LANES", None)
+        self.old = (os.environ.pop("SCB_SHIELD_LANES", None), os.environ.pop("SCB_SHIELD_TWO_PHASE", None))
         if self.lanes:
             os.environ["SCB_SHIELD_LANES"] = str(self.lanes)
+        if self.two is not None:
+            os.environ["SCB_SHIELD_TWO_PHASE"] = str(int(self.two))
 
     def __exit__(self, *a):
-        os.environ.pop("SCB_SHIELD_LANES", None)
-        if self.old is not None:
-            os.environ["SCB_SHIELD_LANES"] = self.old
+        os.environ.pop("SCB_SHIELD_LANES", None); os.environ.pop("SCB_SHIELD_TWO_PHASE", None)
+        if self.old[0] is not None:
+            os.environ["SCB_SHIELD_LANES"] = self.old[0]
+        if self.old[1] is not None:
+            os.environ["SCB_SHIELD_TWO_PHASE"] = self.old[1]
 
 
 def make_shield(sc, mode, n, T, event_offset=0.05, disc_steps=5, keep_states=True):
@@ -40,18 +45,21 @@ def make_shield(sc, mode, n, T, event_offset=0.05, disc_steps=5, keep_states=Tru
     return BatchedShield(n, mode, c_params(sc), event_offset, disc_steps * sc.dt, T, device="cuda", keep_states=keep_states)
 
 
-@pytest.mark.parametrize("lanes", [None, 8, 1])
+@pytest.mark.parametrize("lanes", [None, 8, 1, "two-phase"])
 @pytest.mark.parametrize("algo,tag", RUNS)
 def test_reference_runs(algo, tag, lanes):
     if lanes is not None and tag == "scenario":
         pytest.skip("geometry variants replay the short runs")
+    two = None
+    if lanes == "two-phase":                       # candidate 0 with a thread per agent, the rest with a lane group (forced: N = 1)
+        lanes, two = None, True
     gold = np.load(GOLD)
 
     def make(sc):
         sh = make_shield(sc, algo, 1, 100)
 
         def step(x, nx, nu, mov, stat):
-            with Lanes(lanes):
+            with Lanes(lanes, two):
                 o = sh.step(dev(x[None]), dev(nx[None]), dev(nu[None]), dev(mov[None]), dev(stat[None]))
             return o["U"].cpu().numpy()[0], bool(o["using_backup"].cpu()[0])
 
@@ -126,15 +134,18 @@ def test_full_size_geometries_and_properties(mode):
     sc, X, NOMX, NOMU, MOV, STAT = full_batch(n, T, seed=5)
     d = [dev(v) for v in (X, NOMX, NOMU, MOV, STAT)]
     res = {}
-    for lanes in ((32, 8) if mode == "gatekeeper" else (1, 32)):
+    # (lanes, two-launch search): the default for this size is the two-launch search with 8 lanes in its second launch
+    for cfg in (((32, True), (8, True), (8, False), (32, False)) if mode == "gatekeeper" else ((1, None), (32, None))):
         sh = make_shield(sc, mode, n, T, keep_states=False)
-        with Lanes(lanes):
+        with Lanes(*cfg):
             o1 = sh.step(*d); o2 = sh.step(*d)
         torch.cuda.synchronize()
-        res[lanes] = [t.cpu().numpy() for t in (o1["U"], o2["U"], o2["using_backup"], sh.cidx, sh.clen, sh.nsteps, sh.next_event, sh.CU)]
-    a, b = list(res.values())
-    for u, v in zip(a, b):
-        assert np.array_equal(u, v)
+        res[cfg] = [t.cpu().numpy() for t in (o1["U"], o2["U"], o2["using_backup"], sh.cidx, sh.clen, sh.nsteps, sh.next_event, sh.CU)]
+        res[cfg][-1][np.arange(res[cfg][-1].shape[1])[None, :] >= res[cfg][4][:, None]] = 0.0      # rows beyond clen are stale
+    a = list(res.values())[0]
+    for b in list(res.values())[1:]:
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
     U1, U2, ub, cidx, clen, ns, ne, CU = a
     sub = np.arange(0, n, 331)
     shs = make_shield(sc, mode, sub.size, T, keep_states=False)

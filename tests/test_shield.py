@@ -47,7 +47,7 @@ class HostShield:
         self.next_event = np.zeros(n); self.cbuf = np.zeros(n, np.int32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         self.st = _abi.ScbShieldState(p(self.CU2), p(self.CX2), p(self.clen), p(self.cidx), p(self.nsteps), p(self.next_event),
-                                      p(self.cbuf))
+                                      p(self.cbuf), None)
         f = lib.hostsim_shield_step
         f.restype = C.c_int
         f.argtypes = [C.POINTER(_abi.ScbShieldParams), C.POINTER(_abi.ScbShieldState), C.c_int, C.c_int] + [C.c_void_p] * 5 + \

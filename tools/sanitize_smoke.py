@@ -44,11 +44,12 @@ for n in (37, 700):
     os.environ.pop("SCB_BK_LANES", None); os.environ.pop("SCB_BK_FUSED", None)
     NOMX, NOMU = scenes.make_evade_plans(X, 30)
     STAT = scenes.evade_static_rects(MOV)
-    for mode, lanes in (("gatekeeper", 32), ("gatekeeper", 8), ("gatekeeper", 1), ("mps", 1)):
+    for mode, lanes, two in (("gatekeeper", 32, 0), ("gatekeeper", 8, 0), ("gatekeeper", 1, 0), ("gatekeeper", 8, 1), ("gatekeeper", 32, 1), ("mps", 1, 0)):
         os.environ["SCB_SHIELD_LANES"] = str(lanes)
+        os.environ["SCB_SHIELD_TWO_PHASE"] = str(two)
         sh = BatchedShield(n, mode, EvadeSceneParams(dt=0.1, backup_horizon=4.0), 0.05, None, 30, keep_states=True)
         for _ in range(3):
             sh.step(t(X), t(NOMX), t(NOMU), t(MOV), t(STAT))
-    os.environ.pop("SCB_SHIELD_LANES", None)
+    os.environ.pop("SCB_SHIELD_LANES", None); os.environ.pop("SCB_SHIELD_TWO_PHASE", None)
 torch.cuda.synchronize()
 print("sanitize smoke done")
