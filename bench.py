@@ -1030,6 +1030,7 @@ def run_shield(args, w, cx, steps, warmup, sub=False):
     ms_max, e2e_max = cx.max_over_ranks([ms, e2e_ms])
     if cx.rank != 0:
         return None
+    fl = (_profile_json(["r2_flops_shield.json"]).get(mode) or {}).get("flops_per_agent_step")
     h2d = sum(v.nbytes for v in batches[0]); d2h = N * (16 + 4)
     rec = {
         "metric": "control-steps/sec (batched QP solves/s)", "value": cx.world * N / (ms_max * 1e-3), "unit": "control-steps/s",
@@ -1045,10 +1046,13 @@ def run_shield(args, w, cx, steps, warmup, sub=False):
         "e2e": {"value": cx.world * N / (e2e_max * 1e-3), "unit": "control-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps_timed": e_steps, "how": "pinned host plans / states / obstacles -> H2D -> scb_shield_step -> D2H of U + backup flags -> sync, wall clock"},
         "gpu_launches": sh.launches - l0,
-        "roofline": {"bound": "hbm", "achieved": h2d / (ms_max * 1e-3) / 1e9, "peak": hbm_peak()[0], "unit": "GB/s",
-                     "frac": h2d / (ms_max * 1e-3) / 1e9 / hbm_peak()[0], "traffic": None,
-                     "note": "rollout-bound, not bandwidth-bound: every candidate is a chain of 120 dependent closed-loop steps (fp64 sqrt / div); "
-                             "the algorithmic bytes are the nominal plans read once"},
+        "roofline": fp64_roofline(fl * N if fl else None, ms_max,
+                                  {"kernel_ms_how": "all launches of one step, CUDA events",
+                                   "flops_source": "ncu-counted 2*DFMA + DADD + DMUL per agent-step on the tools/prof_shield.py scene (profiles/r2_flops_shield.json; "
+                                                   "the count depends on how many candidates an agent has to try) x agents per step" if fl else "profiles/r2_flops_shield.json missing",
+                                   "hbm_algorithmic_bytes_per_step": h2d,
+                                   "note": "rollout-bound: every candidate is a chain of 120 dependent closed-loop steps (fp64 sqrt / div); issue slots 70 % busy at "
+                                           "8-13 of 32 threads active per instruction (profiles/r2_ncu_shield_summary.txt, r2_launches_shield.csv)"}),
     }
     if not args.no_cpu and not sub:
         procs = min(16, os.cpu_count() or 1)
