@@ -146,8 +146,21 @@ class Gatekeeper:
         self._using_backup = True
 
     def set_nominal_controller(self, nominal_controller):
-        if nominal_controller is not None:
-            raise NotImplementedError("on B200 the nominal plan is an external trajectory (set_nominal_trajectory)")
+        """A nominal CONTROLLER (callable state (n, 1) -> input) instead of an external trajectory: its closed-loop rollout
+        with `robot.step` (gatekeeper.py:235-269) is done here on the host, once per control step, and handed to the kernel as
+        the nominal trajectory -- every candidate's nominal leg is a prefix of that one rollout."""
+        self.nominal_controller = nominal_controller
+
+    def _rollout_nominal(self, x):
+        if self.robot is None or not hasattr(self.robot, "step"):
+            raise NotImplementedError("a nominal controller needs robot.step to roll its plan out")
+        steps = (len(self.nominal_x_traj) - 1) if self.nominal_x_traj is not None else int(self.nominal_horizon / self.dt)   # :592-599
+        xs, us = [np.array(x, dtype=np.float64).reshape(-1)], []
+        for _ in range(max(steps, 0)):
+            u = np.array(self.nominal_controller(xs[-1].reshape(-1, 1)), dtype=np.float64).reshape(-1)
+            us.append(u)
+            xs.append(np.array(self.robot.step(xs[-1].reshape(-1, 1), u.reshape(-1, 1)), dtype=np.float64).reshape(-1))
+        return np.array(xs), (np.array(us) if us else np.zeros((0, 2)))
 
     def set_backup_controller(self, backup_controller, target=None):
         self.backup_controller, self.backup_target = backup_controller, target
@@ -184,8 +197,11 @@ class Gatekeeper:
 
     def solve_control_problem(self, robot_state, friction=None):
         x = np.ascontiguousarray(np.array(robot_state, dtype=np.float64).reshape(1, -1)[:, :4])
-        nx = self.nominal_x_traj if self.nominal_x_traj is not None else np.zeros((0, 4))
-        nu = self.nominal_u_traj if self.nominal_u_traj is not None else np.zeros((0, 2))
+        if self.nominal_controller is not None:
+            nx, nu = self._rollout_nominal(x[0])
+        else:
+            nx = self.nominal_x_traj if self.nominal_x_traj is not None else np.zeros((0, 4))
+            nu = self.nominal_u_traj if self.nominal_u_traj is not None else np.zeros((0, 2))
         T = max(int(self.nominal_horizon / self.dt), len(nx) - 1, 1)
         if self._sh is None or self._sh.T < T:
             if self._sh is not None:

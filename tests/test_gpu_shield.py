@@ -220,3 +220,47 @@ def test_dropin_classes_closed_loop(algo):
         state = B.di_step(sc, state, u.flatten())
     if algo == "gatekeeper":
         assert n == g("u").shape[0] and 55.0 <= state[0] <= 60.0 and abs(state[1]) <= 2.0        # goal zone (evade_env.py:487-500)
+
+
+def test_dropin_gatekeeper_with_a_nominal_controller():
+    """set_nominal_controller(callable) (gatekeeper.py:159-166, 235-269) instead of an external trajectory: same answers."""
+    from safe_control_b200.shield import Gatekeeper
+    sc = B.EvadeScene()
+
+    class Env:
+        hallway_length, half_width = 60.0, 2.0
+        pocket_x_min, pocket_x_max, pocket_y_max = 25.0, 35.0, 6.0
+        bullet_x, bullet_y, bullet_length, bullet_width, bullet_active = 8.0, 0.0, 3.0, 4.0, True
+
+        def get_pocket_bounds(self):
+            return dict(x_min=25.0, x_max=35.0, y_min=2.0, y_max=6.0)
+
+    class Policy:
+        safe_center, safe_bounds = np.array([30.0, 4.0]), dict(x_min=25.0, x_max=35.0, y_min=2.0, y_max=6.0)
+        goal_bounds = dict(x_min=55.0, x_max=60.0, y_min=-2.0, y_max=2.0)
+        Kp = Kd = 2.0
+
+    class Robot:                    # DoubleIntegrator2D.step (robots/double_integrator2D.py:79-107)
+        def step(self, X, U):
+            return B.di_step(sc, np.asarray(X, float).reshape(-1), np.asarray(U, float).reshape(-1)).reshape(-1, 1)
+
+    spec = {"model": "DoubleIntegrator2D", "radius": 0.5, "a_max": 2.0, "v_max": 1.5}
+    env = Env()
+    mov = lambda t=0.0: dict(x=env.bullet_x + 0.5 + 3.0 * t, y=0.0, vx=3.0, vy=0.0, length=4.0, width=4.0, active=True)
+    shields = []
+    for use_controller in (False, True):
+        sh = Gatekeeper(Robot(), spec, dt=0.1, backup_horizon=12.0, nominal_horizon=10.0, event_offset=0.05, safety_margin=0.5)
+        sh.set_backup_controller(Policy()); sh.set_environment(env); sh.set_moving_obstacles(mov)
+        if use_controller:
+            sh.set_nominal_controller(lambda s: B.nominal_control(sc, np.asarray(s).reshape(-1)).reshape(-1, 1))
+        shields.append(sh)
+    state = np.array([20.0, 0.0, 0.5, 0.0])
+    for k in range(25):
+        nx, nu = S.nominal_rollout(sc, state)
+        shields[0].set_nominal_trajectory(nx, nu)
+        u0 = shields[0].solve_control_problem(state.reshape(-1, 1))
+        u1 = shields[1].solve_control_problem(state.reshape(-1, 1))
+        assert np.array_equal(u0, u1), k
+        assert shields[0].get_status() == shields[1].get_status()
+        state = B.di_step(sc, state, u0.flatten())
+        env.bullet_x += 0.3
