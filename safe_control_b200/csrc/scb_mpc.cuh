@@ -1936,4 +1936,18 @@ SCB_HD void mpc_agent(const scb_params& p, int H, int M, int nobs, const double*
   s.solve(nobs, x0, goal, Mod::NGOAL, uprev, obs, U, status, pred_x, pred_u, iters, kkt, active);
 }
 
+// The same with the layout supplied by the caller.  The kernel passes its __grid_constant__ copy: the 47 workspace offsets
+// are then read from the constant bank (LDC / uniform registers) next to the access that needs them, instead of from a
+// struct on the thread's local-memory stack (53 M local loads per cfg3 launch when the layout was built per agent).
+template <int MODEL, int LANES>
+SCB_HD void mpc_agent(const scb_params& p, const MpcLayout& L, int nobs, const double* x0, const double* goal,
+                      const double* uprev, const double* obs, double* workspace, double* U, int32_t* status,
+                      double* pred_x, double* pred_u, int32_t* iters, double* kkt, uint64_t* active = nullptr) {
+  using Mod = MpcModel<MODEL>;
+  MpcSolver<MODEL, LANES> s(p, L, workspace);
+  if (nobs < 0) nobs = 0;
+  if (nobs > L.M) nobs = L.M;
+  s.solve(nobs, x0, goal, Mod::NGOAL, uprev, obs, U, status, pred_x, pred_u, iters, kkt, active);
+}
+
 }  // namespace scb

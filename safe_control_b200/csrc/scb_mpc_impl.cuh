@@ -29,7 +29,7 @@ constexpr int mpc_lanes() {
 template <int MODEL, int LANES>
 __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid_constant__ scb_params p, int N, int M, int H, int ws_doubles, int gpb,
                            const __grid_constant__ MpcIO io, int active_words, int* __restrict__ next_agent,
-                           const int32_t* __restrict__ order) {
+                           const int32_t* __restrict__ order, const __grid_constant__ MpcLayout lay) {
   const double* __restrict__ X = io.X; const double* __restrict__ Uref = io.Uref; const double* __restrict__ goal = io.goal;
   const double* __restrict__ u_prev = io.u_prev; const int32_t* __restrict__ track = io.track;
   const double* __restrict__ OBS = io.OBS; const long stride = io.stride; const int32_t* __restrict__ nobs = io.nobs;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(SCB_MPC_MAXTHREADS, 1) mpc_kernel(const __grid
         if (active) for (int q2 = 0; q2 < active_words; ++q2) active[a * active_words + q2] = 0ull;
       }
     } else {
-    mpc_agent<MODEL, LANES>(p, H, M, nobs ? nobs[a] : M, X + a * NX, goal + a * Mod::NGOAL, u_prev + a * NU, OBS + a * stride, ws,
+    mpc_agent<MODEL, LANES>(p, lay, nobs ? nobs[a] : M, X + a * NX, goal + a * Mod::NGOAL, u_prev + a * NU, OBS + a * stride, ws,
                             U + a * NU, status + a, pred_x ? pred_x + a * (H + 1) * NX : nullptr,
                             pred_u ? pred_u + a * H * NU : nullptr, iters ? iters + a : nullptr,
                             kkt ? kkt + a : nullptr, active ? active + a * active_words : nullptr);
@@ -200,6 +200,21 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const MpcIO& io, int*
   // Launches of >= 4 waves keep round 1's packed CTAs (measured 3 % faster there: config 5 on one GPU 201.8 vs 208.7 ms).
   int gpb = ((long)N >= 4L * sm_count * slots) ? slots : 1;
   if (const char* e = getenv("SCB_MPC_GPB")) { const int v = atoi(e); if (v >= 1) gpb = v < slots ? v : slots; }
+  auto kern = mpc_kernel<MODEL, kLanes>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per * (gpb > 1 ? gpb : 1)));
+  if (e != cudaSuccess) {
+    if (!count_only) return SCB_ERR_TOO_LARGE;
+    cudaGetLastError();                                  // launch-count query on a box without a device: the estimate above stands
+  } else if (gpb == 1 && !getenv("SCB_MPC_SLOTS8")) {
+    // one-warp CTAs are not bound to 256 threads per SM: as many as registers and shared memory allow (the occupancy
+    // calculator knows the kernel's register count; 144 registers -> 14 warps, 220 KB / 16.7 KB -> 13 at the cfg3 shape)
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kLanes, per) == cudaSuccess && occ > 0) {
+      const int by_smem = (int)(budget / per);
+      slots = occ < by_smem ? occ : by_smem;
+      if (slots > 16) slots = 16;
+    }
+  }
   const int cta_per_sm = slots / gpb > 0 ? slots / gpb : 1;
   const size_t smem = per * gpb;
   long blocks = ((long)N + gpb - 1) / gpb;
@@ -207,9 +222,8 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const MpcIO& io, int*
   // schedule (needs the caller's workspace; without one, or when every agent starts in the first wave, index order)
   const int32_t* order = nullptr;
   const bool scheduled = workspace && workspace_bytes >= mpc_workspace_bytes(N) && (long)N > blocks * gpb;
-  if (count_only) { *count_only = scheduled ? 3 : 1; return SCB_OK; }       // (pure host arithmetic: no CUDA call)
-  auto kern = mpc_kernel<MODEL, kLanes>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (count_only) { *count_only = scheduled ? 3 : 1; return SCB_OK; }       // (nothing launched; works without a device)
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return SCB_ERR_TOO_LARGE;
   if (scheduled) {
     int32_t* hist = (int32_t*)workspace + kMpcWsHead;
@@ -220,7 +234,7 @@ int mpc_launch_m(const scb_params& p, int N, int M, int H, const MpcIO& io, int*
     mpc_order_kernel<<<1, kMpcBins, 0, s>>>(N, bin_of, hist, ord);
     order = ord;
   }
-  kern<<<(int)blocks, ((gpb * kLanes + 31) / 32) * 32, smem, s>>>(p, N, M, H, L.total, gpb, io, mpc_active_words<Mod>(H, M), counter, order);
+  kern<<<(int)blocks, ((gpb * kLanes + 31) / 32) * 32, smem, s>>>(p, N, M, H, L.total, gpb, io, mpc_active_words<Mod>(H, M), counter, order, L);
   return SCB_OK;
 }
 
