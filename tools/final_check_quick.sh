@@ -1,5 +1,6 @@
 #!/bin/bash
 # 1 GPU: the driver's round-end sequence (GPU tests, smoke, reference arm, default bench) + sanitizer over every kernel family
+#   gpurun --timeout 1500 -- 'bash tools/final_check_quick.sh'
 O=gpurun_out/final; mkdir -p $O
 (time timeout 1700 python -m pytest tests -m gpu -x -q) > $O/pytest_gpu.log 2>&1; tail -4 $O/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
