@@ -115,8 +115,32 @@ class BatchedShield:
         """[N] seconds: committed_horizon of every agent (gatekeeper.py:538)"""
         return self.nsteps.to(F64) * self.params.scene.dt
 
+    # ---- numpy in / out (what the N = 1 drop-in classes use) ----
+    def step_numpy(self, X, NOMX, NOMU, MOV=None, STAT=None, nom_len=None):
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        out = self.step(t(X), t(NOMX), t(NOMU), t(MOV), t(STAT), t(nom_len))
+        return out["U"].cpu().numpy(), out["using_backup"].cpu().numpy()
+
+    def state_numpy(self, agent=0):
+        """scalar state + committed trajectories of one agent as numpy"""
+        clen = int(self.clen[agent].cpu())
+        d = dict(clen=clen, cidx=int(self.cidx[agent].cpu()), nsteps=int(self.nsteps[agent].cpu()),
+                 next_event=float(self.next_event[agent].cpu()), CU=None, CX=None)
+        if clen >= 0:
+            cb = int(self.cbuf[agent].cpu())
+            d["CU"] = self._CU2[agent, cb, :clen].cpu().numpy()
+            if self._CX2 is not None:
+                d["CX"] = self._CX2[agent, cb, : clen + 1].cpu().numpy()
+        return d
+
 
 # ---------------------------------------------------------------------------------------------------------------- drop-in classes
+def _new_shield(mode, scene, event_offset, horizon_discount, nominal_steps, device):
+    """the N = 1 shield behind a drop-in object (one place to stand a test double in)"""
+    return BatchedShield(1, mode, scene, event_offset, horizon_discount, nominal_steps, device=torch.device("cuda", device),
+                         keep_states=True)
+
+
 def _obstacle_rows(moving_obstacles):
     from .position_control.backup_cbf_qp import _obstacle_rows as rows
     return rows(moving_obstacles)
@@ -206,46 +230,41 @@ class Gatekeeper:
         if self._sh is None or self._sh.T < T:
             if self._sh is not None:
                 raise NotImplementedError("nominal trajectory longer than the first one handed over")
-            self._sh = BatchedShield(1, self._mode, self._scene(), self.event_offset, self.horizon_discount, T,
-                                     device=torch.device("cuda", self.device), keep_states=True)
+            self._sh = _new_shield(self._mode, self._scene(), self.event_offset, self.horizon_discount, T, self.device)
         sh = self._sh
         sh.params.scene = self._scene()                           # (the scene objects may have changed between steps)
         NOMX = np.zeros((1, sh.T + 1, 4)); NOMU = np.zeros((1, sh.T, 2))
         n = min(len(nx), sh.T + 1)
         NOMX[0, :n] = nx[:n]; NOMU[0, : max(n - 1, 0)] = nu[: max(n - 1, 0)]
-        dev = sh.device
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         mov = _obstacle_rows(self.moving_obstacles)
-        stat = self._static_rect()
-        out = sh.step(t(x), t(NOMX), t(NOMU), None if mov is None or mov.shape[0] == 0 else t(mov[None]),
-                      None if stat is None else t(stat), t(np.array([n], np.int32)))
-        self._using_backup = bool(out["using_backup"].cpu()[0])
-        return out["U"].cpu().numpy().reshape(-1, 1)
+        U, ub = sh.step_numpy(x, NOMX, NOMU, None if mov is None or mov.shape[0] == 0 else mov[None], self._static_rect(),
+                              np.array([n], np.int32))
+        self._using_backup = bool(ub[0])
+        return U.reshape(-1, 1)
 
     # ---- state queries (gatekeeper.py:721-754) ----
+    def _st(self):
+        return self._sh.state_numpy(0) if self._sh is not None else None
+
     @property
     def current_time_idx(self):
-        return int(self._sh.cidx.cpu()[0]) if self._sh is not None else int(self.backup_horizon / self.dt)
+        return self._st()["cidx"] if self._sh is not None else int(self.backup_horizon / self.dt)
 
     @property
     def committed_horizon(self):
-        return float(self._sh.committed_horizon().cpu()[0]) if self._sh is not None else 0.0
+        return self._st()["nsteps"] * self.dt if self._sh is not None else 0.0
 
     @property
     def next_event_time(self):
-        return float(self._sh.next_event.cpu()[0]) if self._sh is not None else 0.0
+        return self._st()["next_event"] if self._sh is not None else 0.0
 
     @property
     def committed_u_traj(self):
-        if self._sh is None or int(self._sh.clen.cpu()[0]) < 0:
-            return None
-        return self._sh.CU[0, : int(self._sh.clen.cpu()[0])].cpu().numpy()
+        return self._st()["CU"] if self._sh is not None else None
 
     @property
     def committed_x_traj(self):
-        if self._sh is None or int(self._sh.clen.cpu()[0]) < 0:
-            return None
-        return self._sh.CX[0, : int(self._sh.clen.cpu()[0]) + 1].cpu().numpy()
+        return self._st()["CX"] if self._sh is not None else None
 
     def get_committed_trajectory(self):
         return self.committed_x_traj, self.committed_u_traj
