@@ -23,7 +23,7 @@ constexpr int mpc_lanes() {
 }
 
 #ifndef SCB_MPC_MAXTHREADS
-#define SCB_MPC_MAXTHREADS 256       // measured (cfg3): 256 threads (255 regs, 8 agent-warps) 8.3 ms, 384 (168 regs + spills) 8.9 ms, 512 9.5 ms
+#define SCB_MPC_MAXTHREADS 256       // packed CTAs: at most 8 agent-warps (round 1, cfg3: 256 threads 8.3 ms, 384 with spills 8.9 ms, 512 9.5 ms)
 #endif
 
 template <int MODEL, int LANES>

@@ -1,10 +1,10 @@
 // scb_mpc_kernels.cuh -- __global__ wrapper + launch for the MPC-CBF path (scb_mpc.cuh).
 //
 // One lane group (LANES = 32: a full warp) per agent; each group owns a private workspace of
-// MpcLayout::total doubles in dynamic shared memory (~35 KB at H = 8, M = 16), so a CTA carries as
-// many agents as fit in the SM's 227 KB and the grid is persistent (one CTA per SM, agents
-// grid-strided).  Everything the interior-point loop touches after the initial obstacle load
-// stays on chip; HBM sees the inputs once and U/status once.
+// MpcLayout::total doubles in dynamic shared memory (17 KB at H = 8, M = 16; 40 KB at H = 10, M = 64).  The grid is
+// persistent: one-warp CTAs, as many per SM as registers and shared memory allow, for launches of a few waves; CTAs of
+// up to 8 agent-warps, one per SM, for launches of four waves or more (mpc_launch_m in scb_mpc_impl.cuh).  Everything
+// the interior-point loop touches after the initial obstacle load stays on chip; HBM sees the inputs once and U/status once.
 #pragma once
 // (the kernel and its per-model launcher live in scb_mpc_impl.cuh; each model is its own translation unit,
 // scb_mpc_inst.cu compiled with -DSCB_MPC_INST=<model id>, so the library builds in parallel)
