@@ -160,6 +160,43 @@ def test_kernel_body_vs_oracle_random(dt, hor, goal, fma):
     assert n_mask >= 4
 
 
+def test_other_geometries_and_parameters():
+    """nothing of the example's scene is baked into the kernel: other hallway / pocket sizes, radii, limits, gains, class-K
+    gains and margins (all of them fields of scb_backup_params) against the oracle"""
+    lib = H.hostsim(False)
+    rng = np.random.default_rng(21)
+    n_opt = 0
+    for trial in range(6):
+        sc = B.EvadeScene(hallway_length=rng.uniform(40, 80), hallway_width=rng.uniform(3, 6), pocket_x=rng.uniform(10, 30),
+                          pocket_length=rng.uniform(6, 12), pocket_width=rng.uniform(3, 5), goal_length=rng.uniform(3, 8),
+                          radius=rng.uniform(0.3, 0.7), a_max=rng.uniform(1.0, 3.0), v_max=rng.uniform(1.0, 2.5),
+                          safety_margin=rng.uniform(0.0, 0.8), use_goal=bool(trial % 2), dt=0.1, backup_horizon=rng.choice([3.0, 5.0, 8.0]))
+        sc.Kp, sc.Kd = rng.uniform(1.0, 3.0), rng.uniform(1.0, 3.0)
+        sc.alpha, sc.alpha_terminal = rng.uniform(0.5, 2.0), rng.uniform(1.0, 3.0)
+        n = 16
+        X = np.zeros((n, 4))
+        X[:, 0] = rng.uniform(0.8, sc.hallway_length - 0.8, n)
+        X[:, 1] = rng.uniform(-sc.half_width + 0.8, sc.half_width - 0.8, n)
+        inp = rng.random(n) < 0.3
+        X[inp, 0] = rng.uniform(sc.pocket_x_min + 0.8, sc.pocket_x_max - 0.8, inp.sum())
+        X[inp, 1] = rng.uniform(0.0, sc.pocket_y_max - 0.9, inp.sum())
+        X[:, 2:] = rng.uniform(-1, 1, (n, 2)) * rng.uniform(0, sc.v_max, (n, 1))
+        Ur = rng.uniform(-1.2 * sc.a_max, 1.2 * sc.a_max, (n, 2))
+        MOV = np.zeros((n, 1, 8))
+        for a in range(n):
+            MOV[a, 0] = B.bullet_row(rng.uniform(-10, sc.hallway_length), bullet_length=rng.uniform(2, 4), bullet_width=2 * sc.half_width,
+                                     bullet_speed=rng.uniform(1, 4))
+        o = hs_solve(lib, sc, X, Ur, MOV)
+        for a in range(n):
+            ref = B.solve(sc, X[a], Ur[a], MOV[a])
+            assert np.abs(o["phi"][a] - ref["phi"]).max() < 1e-12, (trial, a)
+            assert abs(o["h_min"][a] - ref["h_min"]) < 1e-12
+            assert o["status"][a] == ref["status"] and bool(o["intervene"][a]) == ref["intervene"], (trial, a)
+            assert np.abs(o["U"][a] - ref["u"]).max() < 1e-8, (trial, a)
+            n_opt += ref["status"] == 0
+    assert n_opt >= 10
+
+
 def test_no_obstacles_and_tiny_horizons():
     lib = H.hostsim(False)
     for hor in (0.1, 0.2, 0.5):

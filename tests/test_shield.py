@@ -175,6 +175,45 @@ def test_kernel_body_vs_oracle_multi_step(mode):
     assert len(flags) >= 3          # committed nominal legs and pure-backup commitments both occurred
 
 
+@pytest.mark.parametrize("mode", ["gatekeeper", "mps"])
+def test_other_geometries_and_parameters(mode):
+    """other hallway / pocket sizes, radii, limits, gains, margins, event offsets and discounts against the oracle"""
+    rng = np.random.default_rng(33)
+    for trial in range(3):
+        sc = B.EvadeScene(hallway_length=rng.uniform(40, 80), hallway_width=rng.uniform(3, 6), pocket_x=rng.uniform(10, 30),
+                          pocket_length=rng.uniform(6, 12), pocket_width=rng.uniform(3, 5), goal_length=rng.uniform(3, 8),
+                          radius=rng.uniform(0.3, 0.6), a_max=rng.uniform(1.0, 3.0), v_max=rng.uniform(1.0, 2.5),
+                          safety_margin=rng.uniform(0.0, 0.8), use_goal=bool(trial % 2), dt=0.1, backup_horizon=float(rng.choice([3.0, 5.0])))
+        sc.Kp, sc.Kd = rng.uniform(1.0, 3.0), rng.uniform(1.0, 3.0)
+        T, n, steps = 30, 12, 8
+        off, disc = float(rng.choice([0.05, 0.15, 0.3])), int(rng.choice([2, 5, 7]))
+        X = np.zeros((n, 4))
+        X[:, 0] = rng.uniform(1.0, sc.hallway_length - 1.0, n)
+        X[:, 1] = rng.uniform(-sc.half_width + 0.8, sc.half_width - 0.8, n)
+        X[:, 2:] = rng.uniform(-0.8, 0.8, (n, 2))
+        bullet = rng.uniform(-10.0, sc.hallway_length, n); speed = rng.uniform(1.0, 4.0)
+        hs = HostShield(H.hostsim(False), sc, mode, n, T=T, event_offset=off, disc=disc)
+        orc = [S.OracleShield(sc, mode=mode, event_offset=off, horizon_discount=disc * sc.dt) for _ in range(n)]
+        for k in range(steps):
+            NOMX = np.zeros((n, T + 1, 4)); NOMU = np.zeros((n, T, 2)); MOV = np.zeros((n, 1, 8)); STAT = np.zeros((n, 5))
+            plans = []
+            for a in range(n):
+                nx, nu = S.nominal_rollout(sc, X[a], horizon_time=T * sc.dt)
+                NOMX[a], NOMU[a] = nx, nu
+                MOV[a, 0] = B.bullet_row(bullet[a], bullet_width=2 * sc.half_width, bullet_speed=speed)
+                STAT[a] = S.bullet_static_rect(bullet[a], bullet_width=2 * sc.half_width)
+                plans.append((nx, nu))
+            U, ub = hs.step(X, NOMX, NOMU, MOV, STAT)
+            for a in range(n):
+                u = orc[a].solve(X[a], plans[a][0], plans[a][1], MOV[a], STAT[a])
+                assert np.abs(U[a] - u).max() < 1e-12, (trial, k, a)
+                assert bool(ub[a]) == orc[a].is_using_backup()
+                assert hs.cidx[a] == orc[a].current_time_idx and hs.clen[a] == len(orc[a].committed_u) and hs.nsteps[a] == orc[a].actual_nominal_steps
+                assert abs(hs.next_event[a] - orc[a].next_event_time) < 1e-12
+                X[a] = B.di_step(sc, X[a], U[a])
+            bullet = bullet + speed * sc.dt
+
+
 def test_shadow_route_for_the_shields():
     from unittest import mock
     from oracle import refshim
