@@ -853,7 +853,7 @@ extern "C" int scb_backupcbf_solve(const scb_backup_params* p, int N, int K, con
   int rc = backup_check(p, N, K);
   if (rc != SCB_OK) return rc;
   if (N == 0) return SCB_OK;
-  if (!X || !Uref || !U || !status || (K > 0 && !MOV) || mov_stride < 0) return SCB_ERR_BAD_ARG;
+  if (!X || !Uref || !U || !status || (K > 0 && !MOV) || mov_stride < 0 || (mov_stride > 0 && mov_stride < (long)K * kBkMov)) return SCB_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   const int nb = p->n_backup, words = scb_backup_active_words(nb);
   int forced = 0;
@@ -914,7 +914,7 @@ extern "C" int scb_backupcbf_solve_host(scb_ctx* c, const scb_backup_params* p, 
   int rc = backup_check(p, N, K);
   if (rc != SCB_OK) return rc;
   if (N == 0) return SCB_OK;
-  if (!X || !Uref || !U || !status || (K > 0 && !MOV) || mov_stride < 0) return SCB_ERR_BAD_ARG;
+  if (!X || !Uref || !U || !status || (K > 0 && !MOV) || mov_stride < 0 || (mov_stride > 0 && mov_stride < (long)K * kBkMov)) return SCB_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
   const int nb = p->n_backup, words = scb_backup_active_words(nb);
   const size_t mov_el = (K == 0) ? 0 : (mov_stride == 0 ? (size_t)K * kBkMov : (size_t)N * (size_t)mov_stride);
@@ -962,7 +962,7 @@ extern "C" int scb_shield_step(const scb_shield_params* p, const scb_shield_stat
   if (p->nom_cap < 0 || (p->mode != 0 && p->mode != 1) || !(p->event_offset >= 0.0)) return SCB_ERR_BAD_ARG;
   if (N == 0) return SCB_OK;
   if (!X || !U || !st->CU || !st->clen || !st->cidx || !st->nsteps || !st->next_event || !st->cbuf || (p->nom_cap > 0 && (!NOMX || !NOMU)) ||
-      (K > 0 && !MOV) || mov_stride < 0)
+      (K > 0 && !MOV) || mov_stride < 0 || (mov_stride > 0 && mov_stride < (long)K * kBkMov))
     return SCB_ERR_BAD_ARG;
   if (p->nom_cap == 0 && !NOMX) return SCB_ERR_BAD_ARG;            // (NOMX always holds at least the start state)
   cudaStream_t s = (cudaStream_t)stream;

@@ -129,6 +129,15 @@ def test_edge_cases_and_errors():
         BatchedBackupCBF(big).solve(dev(X), dev(Ur))
     with pytest.raises(ValueError):
         BatchedBackupCBF(c_params(sc)).solve(dev(X), dev(Ur[:, :1]))
+    # an obstacle stride shorter than one agent's list is refused by the C entry point itself
+    import ctypes as C
+    from safe_control_b200._lib import lib
+    p = c_params(sc)
+    t = [dev(v) for v in (X, Ur, MOV)]
+    U = torch.empty((8, 2), dtype=torch.float64, device="cuda"); st = torch.empty((8,), dtype=torch.int32, device="cuda")
+    vp = lambda x: C.c_void_p(x.data_ptr())
+    rc = lib().scb_backupcbf_solve(C.byref(p), 8, 2, vp(t[0]), vp(t[1]), vp(t[2]), 8, vp(U), vp(st), None, None, None, None, None, None)
+    assert rc == -1
 
 
 def test_host_path_matches_device_path():
