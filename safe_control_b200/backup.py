@@ -136,3 +136,40 @@ def host_solve(ctx: HostContext, params, X, U_ref, MOV=None, want_phi=False, wan
     if want_active:
         out["active"] = active
     return out
+
+
+class ShardedBackupCBF:
+    """Backup-CBF QPs of a batch held by rank 0, solved by all ranks (agents are independent: contiguous blocks, no collective
+    inside the solve; sharding.ShardPlan moves X / U_ref / MOV out and U / status / intervene / h_min back).
+
+        sh = ShardedBackupCBF(n_agents, k_mov, params, device)           # every rank, once
+        out = sh.solve(dict(X=.., U_ref=.., MOV=..) if rank == 0 else None)   # rank 0: dict of [n_agents, ...]; others: None
+
+    `solve_block` (default: BatchedBackupCBF on this rank's device) is the per-rank solve; the gloo test substitutes the CPU
+    build of the kernel body."""
+
+    def __init__(self, n_agents, k_mov, params=None, device="cuda", src=0, group=None, solve_block=None):
+        from .sharding import ShardPlan
+        self.k_mov = int(k_mov)
+        ins = {"X": ((4,), F64), "U_ref": ((2,), F64)}
+        if self.k_mov > 0:
+            ins["MOV"] = ((self.k_mov, MOV_COLS), F64)
+        outs = {"U": ((2,), F64), "status": ((), I32), "intervene": ((), I32), "h_min": ((), F64)}
+        self.plan = ShardPlan(n_agents, ins, outs, device, src, group)
+        if solve_block is None:
+            ctrl = BatchedBackupCBF(params)
+            solve_block = lambda b: ctrl.solve(b["X"], b["U_ref"], b.get("MOV"))
+        self._solve_block = solve_block
+
+    def solve(self, inputs):
+        from .sharding import run_p2p
+        ops, block = self.plan.scatter_ops(inputs)
+        run_p2p(ops)
+        if self.plan.n_local > 0:
+            out = self._solve_block(block)
+            out = {k: out[k] for k in self.plan.out_specs}
+        else:
+            out = {k: torch.empty((0, *shp), dtype=dt, device=self.plan.device) for k, (shp, dt) in self.plan.out_specs.items()}
+        ops, res = self.plan.gather_ops(out)
+        run_p2p(ops)
+        return res

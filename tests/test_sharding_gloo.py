@@ -152,3 +152,49 @@ def test_shard_plan_reuse_and_config5_wrapper(n_agents):
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=10)
+
+
+# ---- Backup-CBF QP sharded over two ranks: the per-rank solve is the CPU build of the REAL kernel body ----------------------
+def _backup_worker(rank, world, port, n_agents, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import hostsim_util as H
+        from oracle import backup_cbf as B
+        from test_backupcbf import hs_solve, random_batch
+        from safe_control_b200.backup import ShardedBackupCBF
+        sc = B.EvadeScene(dt=0.1, backup_horizon=4.0)
+
+        def solve_block(b):
+            o = hs_solve(H.hostsim(False), sc, b["X"].numpy(), b["U_ref"].numpy(), b["MOV"].numpy())
+            return {"U": torch.from_numpy(o["U"]), "status": torch.from_numpy(o["status"]), "intervene": torch.from_numpy(o["intervene"]),
+                    "h_min": torch.from_numpy(o["h_min"])}
+
+        sh = ShardedBackupCBF(n_agents, 2, None, "cpu", solve_block=solve_block)
+        X, Ur, MOV = random_batch(sc, n_agents, seed=9)
+        ins = {"X": torch.from_numpy(X), "U_ref": torch.from_numpy(Ur), "MOV": torch.from_numpy(MOV)}
+        out = sh.solve(ins if rank == 0 else None)
+        if rank == 0:
+            ref = solve_block(ins)
+            q.put(all(torch.equal(out[k], ref[k]) for k in ref) and tuple(out["U"].shape) == (n_agents, 2) and
+                  int((ref["status"] == 0).sum()) > 0)
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_agents", [9, 32])
+def test_backupcbf_sharded_two_ranks(n_agents):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_backup_worker, args=(r, 2, port, n_agents, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10)
